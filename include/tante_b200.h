@@ -1,0 +1,138 @@
+/*
+ * tante_b200.h -- C ABI of the B200-native TANTE hot path (libtante_b200.so).
+ *
+ * Plain C: opaque handle, raw device pointers, sizes, CUDA stream as void*.
+ * No torch / C++ types cross this boundary.  Every entry point returns an int
+ * status (0 = TANTE_OK); tante_last_error() gives the thread-local message.
+ * The library allocates only in tante_create / tante_reserve (workspace,
+ * packed-weight arena, rollout state, CUDA graphs); it never owns parameters,
+ * gradients, inputs or outputs -- the caller (PyTorch) does.  All work is
+ * enqueued on the caller's stream; the only host syncs are the documented
+ * ones (tante_forward with n_host != NULL, tante_rollout with sync != 0).
+ * A handle is single-threaded: one per process per GPU.
+ *
+ * The reference (zwu88/TANTE) is pure Python; nothing native exists to mirror,
+ * so each entry point cites the Python call it replaces (paths under the
+ * reference root).
+ */
+#ifndef TANTE_B200_H_
+#define TANTE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TANTE_API __attribute__((visibility("default")))
+#else
+#define TANTE_API
+#endif
+
+#define TANTE_OK 0
+#define TANTE_ERR_INVALID 1   /* bad argument / unsupported configuration        */
+#define TANTE_ERR_CUDA 2      /* a CUDA runtime call failed                      */
+#define TANTE_ERR_STATE 3     /* call order violated (e.g. params not bound)     */
+#define TANTE_ERR_NOMEM 4
+
+#define TANTE_MAX_ORDER 8
+#define TANTE_MAX_LAYERS 32
+
+#define TANTE_PREC_FP32 0  /* FP32 FFMA everywhere: the <=1e-5 parity mode                    */
+#define TANTE_PREC_BF16 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate/residual */
+
+/* Mirror of the TANTE constructor (models/tante.py:38-60) + dataset metadata
+ * (n_fields, spatial_resolution: models/tante.py:64-66). */
+typedef struct tante_config {
+    int32_t in_T;
+    int32_t n_fields;
+    int32_t H, W;
+    int32_t taylor_order;
+    int32_t n_head;
+    int32_t embed_dim;
+    int32_t patch_scale;
+    int32_t deg;            /* 1: fixed step (output_length frames), 0: adaptive   */
+    int32_t output_length;
+    float frame_interval;
+    int32_t precision;      /* TANTE_PREC_*                                         */
+    int32_t n_layers[TANTE_MAX_ORDER];                 /* len(segment k) of attn_axes */
+    char axes[TANTE_MAX_ORDER][TANTE_MAX_LAYERS];      /* axis letter per layer: T/H/W */
+} tante_config_t;
+
+typedef struct tante_handle_s* tante_handle_t;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+TANTE_API const char* tante_last_error(void);
+TANTE_API int tante_version(void);
+
+/* models.TANTE(...) construction (models/tante.py:37-123).  Validates the config
+ * (ValueError/KeyError cases of tante.py:76-83, enc_dec_cnn.py:199 map to
+ * TANTE_ERR_INVALID). */
+TANTE_API int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out);
+TANTE_API int tante_destroy(tante_handle_t h);
+
+/* (Re)size the library-owned workspace for batches up to max_batch and rollouts up
+ * to max_roll frames.  Called by the host module before the first forward/rollout
+ * of a new size; the only allocating call besides tante_create. */
+TANTE_API int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t training);
+TANTE_API int64_t tante_workspace_bytes(tante_handle_t h);
+
+/* ---- parameters: state_dict ABI -------------------------------- */
+TANTE_API int32_t tante_param_count(tante_handle_t h);
+TANTE_API const char* tante_param_name(tante_handle_t h, int32_t i);
+TANTE_API int64_t tante_param_numel(tante_handle_t h, int32_t i);
+/* model.parameters()/load_state_dict (trainer/r_trainer.py:102, r_evaler.py:82): the
+ * fp32 master tensor stays owned by the caller; `grad` may be NULL (inference). */
+TANTE_API int tante_bind_param(tante_handle_t h, const char* name, const float* data, float* grad, int64_t numel);
+/* Re-derive the packed device weights (GEMM-ready layouts, bf16 copies) from the bound
+ * masters.  Call after binding and after every optimizer step. */
+TANTE_API int tante_pack_params(tante_handle_t h, void* stream);
+
+/* ---- one model step: TANTE.forward (models/tante.py:125-176) ---------------------- */
+/* input  : f32[B, T, D, H, W] (already cropped to the last in_T frames)
+ * frames : f32[B, n_cap, D, H, W]; sample b gets n_b frames written, the rest untouched
+ * R_t    : f32[B] (adaptive only, may be NULL when deg)
+ * n_dev  : i32[B] device array of emitted frame counts (may be NULL)
+ * n_host : if non-NULL the call synchronises the stream and stores n for sample 0 --
+ *          the reference's own `math.floor(R_t[0])` host sync (tante.py:163).
+ * per_sample = 0 reproduces the reference (sample 0 governs the batch);
+ * per_sample = 1 gives every sample its own n = floor(R_t[b]). */
+TANTE_API int tante_forward(tante_handle_t h, const float* input, int32_t B, float out_T, int32_t n_cap,
+                  int32_t per_sample, float* frames, float* R_t, int32_t* n_dev, int32_t* n_host,
+                  void* stream);
+
+/* ---- adaptive rollout: R_Evaler.rollout_model (trainer/r_evaler.py:87-105),
+ *      R_Trainer.rollout_model in eval mode (trainer/r_trainer.py:112-133),
+ *      Evaler/Trainer.rollout_model for deg (trainer/evaler.py:121-138) ------------- */
+/* window   : f32[B, T, D, H, W] channels-first initial frames (read only)
+ * y_out    : f32[B, n_roll, H, W, D] channels-last (DefaultChannelsFirstFormatter.process_output)
+ * rts_out  : f32[max_steps, B] R_t per model call (row s valid for samples with steps_out[b] > s)
+ * ns_out   : i32[max_steps, B] frames emitted per model call
+ * steps_out: i32[B] number of model calls each sample took
+ * max_steps = n_roll (every call emits >= 1 frame).
+ * The whole loop runs on the device (ring-buffer window, per-sample counters, one CUDA
+ * graph per step); `sync` != 0 makes the call return after the rollout finished. */
+TANTE_API int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_roll, float out_T,
+                  int32_t per_sample, float* y_out, float* rts_out, int32_t* ns_out,
+                  int32_t* steps_out, int32_t sync, void* stream);
+
+/* ---- introspection for tests / profiling ------------------------------------------ */
+/* Copy an internal stage tensor of the last tante_forward into `dst` (f32, device).
+ * stage: "latent_in" (after embed), "latent" (after the last backbone), "deriv<k>"
+ * ([B,D,H,W] decoded k-th derivative field), "rt<k>".  Returns the element count in *numel. */
+TANTE_API int tante_debug_stage(tante_handle_t h, const char* stage, float* dst, int64_t cap, int64_t* numel,
+                      void* stream);
+/* Number of kernel launches enqueued by this handle since creation (bench.py's gpu_launches). */
+TANTE_API int64_t tante_launch_count(tante_handle_t h);
+
+/* Stand-alone launch of the fused Taylor head (K decoded stage-2 activations -> n frames),
+ * for the K x patch-size microbenchmark (BASELINE.json configs[4]). */
+TANTE_API int tante_bench_head(tante_handle_t h, int32_t B, int32_t n_frames, int32_t iters, float* ms_out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TANTE_B200_H_ */

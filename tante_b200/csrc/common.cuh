@@ -1,0 +1,120 @@
+// Shared device helpers for the TANTE B200 kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tante {
+
+constexpr int kWarp = 32;
+
+// ---- element conversion -------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-wide vector load/store of either element type (16 B for f32, 8 B for bf16).
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+        float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&a);
+        t.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
+
+// ---- activations (accurate versions: the fp32 parity mode is compiled without fast-math) --
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float k = 0.79788456080286535588f;  // sqrt(2/pi)
+    return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+// derivatives (training path)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+    const float k = 0.79788456080286535588f;
+    const float u = k * (x + 0.044715f * x * x * x);
+    const float t = tanhf(u);
+    const float du = k * (1.0f + 3.0f * 0.044715f * x * x);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Epilogue selector shared by the SIMT and tcgen05 GEMMs.
+enum Epilogue : int {
+    EPI_BIAS = 0,        // C = acc + bias
+    EPI_BIAS_RELU = 1,
+    EPI_BIAS_GELU_ERF = 2,
+    EPI_BIAS_GELU_TANH = 3,
+    EPI_BIAS_RESID = 4,  // C = resid + acc + bias   (fp32 residual stream, may alias C)
+    EPI_EMBED = 5,       // encoder tail: v=acc+bias; v += v*scale[t]+shift[t]; v += s_emb[hw]; v += t_emb[t]
+};
+
+struct EpiParams {
+    const float* bias = nullptr;    // [N]
+    const float* resid = nullptr;   // [M, ldr] fp32
+    int ldr = 0;                    // row stride of resid (EPI_BIAS_RESID) / of film,s_emb,t_emb (EPI_EMBED)
+    // EPI_EMBED
+    const float* film = nullptr;    // [T][2][N] scale,shift of t_encode
+    const float* s_emb = nullptr;   // [L][N]
+    const float* t_emb = nullptr;   // [T][N]
+    int T = 0, L = 0;
+};
+
+template <int EPI>
+__device__ __forceinline__ float apply_epilogue(float acc, int m, int n, const EpiParams& p) {
+    float v = acc + p.bias[n];
+    if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.0f);
+    if (EPI == EPI_BIAS_GELU_ERF) v = gelu_erf(v);
+    if (EPI == EPI_BIAS_GELU_TANH) v = gelu_tanh(v);
+    if (EPI == EPI_BIAS_RESID) v = p.resid[(size_t)m * p.ldr + n] + v;
+    if (EPI == EPI_EMBED) {
+        const int hw = m % p.L;
+        const int t = (m / p.L) % p.T;
+        v = v + (v * p.film[(size_t)(t * 2 + 0) * p.ldr + n] + p.film[(size_t)(t * 2 + 1) * p.ldr + n]);
+        v = v + p.s_emb[(size_t)hw * p.ldr + n];
+        v = v + p.t_emb[(size_t)t * p.ldr + n];
+    }
+    return v;
+}
+
+}  // namespace tante

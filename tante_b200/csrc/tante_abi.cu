@@ -1,0 +1,775 @@
+// libtante_b200.so -- C ABI (include/tante_b200.h) over the sm_100a kernels.
+// Host-side plan: parameter table (reference state_dict names), packed-weight arena, workspace,
+// the per-step launch sequence and the device-resident rollout loop.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tante_b200.h"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels_simt.cuh"
+#include "pack.cuh"
+
+using namespace tante;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            throw Error(TANTE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + \
+                                            __FILE__ + ":" + std::to_string(__LINE__));                \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                   \
+    do {                                                     \
+        if (!(cond)) throw Error(TANTE_ERR_INVALID, (msg));  \
+    } while (0)
+
+struct Param {
+    std::string name;
+    int64_t numel = 0;
+    const float* data = nullptr;
+    float* grad = nullptr;
+    // packing
+    int mode = PACK_COPY;
+    int d0 = 0, d1 = 0, k = 1;
+    int64_t packed_numel = 0;
+    int64_t off = -1;  // arena offset (elements)
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct LayerPlan {
+    char axis;
+    int64_t ln1w, ln1b, inw, inb, outw, outb, ln2w, ln2b, m0w, m0b, m2w, m2b;
+};
+struct OrderPlan {
+    std::vector<LayerPlan> layers;
+    int64_t prop[3][4];   // [H,W,T][w0,b0,w2,b2]
+    int64_t decw[3], decb[3];   // packed deconv 1,2 (GEMM NK + replicated bias), deconv 3 (KN + raw bias)
+    int64_t intw[3], intb[3];
+    int64_t mod[8];       // scale{0.w,0.b,2.w,2.b}, shift{...}
+};
+
+}  // namespace
+
+struct tante_handle_s {
+    tante_config_t cfg{};
+    int device = 0;
+    int C = 0, C1 = 0, C2 = 0, Hp = 0, Wp = 0, L = 0, T = 0, D = 0, K = 0, HD = 0;
+    PatchGeom geom{};
+    std::vector<Param> params;
+    std::map<std::string, int> pindex;
+    std::vector<OrderPlan> orders;
+    int64_t enc_w[3], enc_b[3];
+    int64_t tenc[8];
+    int64_t t_emb = 0, s_emb = 0;
+    int64_t film_t_off = 0;    // derived: t_encode scale/shift table [T][2][C]
+    int64_t tseq_off = 0;      // derived: t_seq [T]
+    int64_t arena_elems = 0;
+    DevBuf arena, arena_bf16, descs;
+    bool packed = false;
+
+    // workspace
+    int max_batch = 0, max_roll = 0;
+    DevBuf x, ln, qkv, att, hid, a1, a2, d32, dmod, i1, i2, z1, rt, Rt, nbuf, filmbuf, ring, state, dbg_in;
+    std::vector<DevBuf> z2;
+    int64_t ws_bytes = 0;
+    int* h_flag = nullptr;      // pinned: remaining-samples flag (ring of 2)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    bool debug = false;
+    int last_B = 0;
+};
+
+namespace {
+
+int64_t add_param(tante_handle_s* h, const std::string& name, std::vector<int64_t> shape, int mode = PACK_COPY,
+                  int d0 = 0, int d1 = 0, int k = 1) {
+    Param p;
+    p.name = name;
+    p.numel = 1;
+    for (auto s : shape) p.numel *= s;
+    p.mode = mode;
+    p.d0 = d0;
+    p.d1 = d1;
+    p.k = k;
+    p.packed_numel = (mode == PACK_BIAS_REP) ? (int64_t)d0 * k * k : p.numel;
+    p.off = h->arena_elems;
+    h->arena_elems += (p.packed_numel + 63) / 64 * 64;   // 256-byte aligned tensors
+    h->pindex[name] = (int)h->params.size();
+    h->params.push_back(p);
+    return p.off;
+}
+
+void patch_kernels(int P, int k[3]) {
+    switch (P) {   // reference enc_dec_cnn.py:39-46
+        case 8: k[0] = 2; k[1] = 2; k[2] = 2; break;
+        case 4: k[0] = 2; k[1] = 2; k[2] = 1; break;
+        case 2: k[0] = 2; k[1] = 1; k[2] = 1; break;
+        case 16: case 32: case 64:
+            throw Error(TANTE_ERR_INVALID,
+                        "patch_scale 16/32/64 (4x4 kernels with padding 1 + bilinear resize) is not implemented yet");
+        default: throw Error(TANTE_ERR_INVALID, "KeyError: patch_scale not in Patch_map");
+    }
+}
+
+void build_plan(tante_handle_s* h) {
+    const tante_config_t& c = h->cfg;
+    REQUIRE(c.in_T >= 1 && c.in_T <= 64, "in_T out of range");
+    REQUIRE(c.taylor_order >= 1 && c.taylor_order <= 4, "taylor_order must be in 1..4");
+    REQUIRE(c.embed_dim > 0 && c.embed_dim % 256 == 0 && c.embed_dim <= 512, "embed_dim must be 256 or 512");
+    REQUIRE(c.n_head > 0 && c.embed_dim % c.n_head == 0, "embed_dim must be divisible by n_head");
+    const int hd = c.embed_dim / c.n_head;
+    REQUIRE(hd == 16 || hd == 32 || hd == 64, "head_dim must be 16, 32 or 64");
+    REQUIRE(c.n_fields >= 1 && c.n_fields <= 16, "n_fields must be in 1..16");
+    REQUIRE(c.precision == TANTE_PREC_FP32 || c.precision == TANTE_PREC_BF16, "unknown precision");
+    int k[3];
+    patch_kernels(c.patch_scale, k);
+    REQUIRE(c.H % c.patch_scale == 0 && c.W % c.patch_scale == 0, "H and W must be divisible by patch_scale");
+    h->C = c.embed_dim; h->C1 = h->C / 4; h->C2 = h->C / 2;
+    h->Hp = c.H / c.patch_scale; h->Wp = c.W / c.patch_scale; h->L = h->Hp * h->Wp;
+    h->T = c.in_T; h->D = c.n_fields; h->K = c.taylor_order; h->HD = hd;
+    REQUIRE(h->Hp <= 64 && h->Wp <= 64 && h->T <= 64, "axis length > 64 is not supported by the axial kernels yet");
+    PatchGeom& g = h->geom;
+    g.k0 = k[0]; g.k1 = k[1]; g.k2 = k[2];
+    g.D = h->D; g.H = c.H; g.W = c.W; g.Hp = h->Hp; g.Wp = h->Wp; g.T = h->T;
+    g.R1 = (k[1] * k[2]) * (k[1] * k[2]);
+    g.R2 = k[2] * k[2];
+    const int C = h->C, C1 = h->C1, C2 = h->C2, D = h->D, T = h->T;
+
+    h->t_emb = add_param(h, "t_emb", {1, T, C});
+    h->s_emb = add_param(h, "s_emb", {1, h->Hp, h->Wp, C});
+    const int ech[4] = {D, C1, C2, C};
+    for (int i = 0; i < 3; ++i) {
+        const std::string p = "encoder.enc_conv_" + std::to_string(i + 1) + ".conv.";
+        h->enc_w[i] = add_param(h, p + "weight", {ech[i + 1], ech[i], k[i], k[i]}, PACK_CONV, ech[i + 1], ech[i], k[i]);
+        h->enc_b[i] = add_param(h, p + "bias", {ech[i + 1]});
+    }
+    const char* fn[2] = {"condition_to_scale", "condition_to_shift"};
+    auto add_film = [&](const std::string& pre, int64_t* out) {
+        for (int s = 0; s < 2; ++s) {
+            const std::string p = pre + fn[s];
+            out[s * 4 + 0] = add_param(h, p + ".0.weight", {C / 2, 1});
+            out[s * 4 + 1] = add_param(h, p + ".0.bias", {C / 2});
+            out[s * 4 + 2] = add_param(h, p + ".2.weight", {C, C / 2});
+            out[s * 4 + 3] = add_param(h, p + ".2.bias", {C});
+        }
+    };
+    add_film("t_encode.", h->tenc);
+    h->orders.resize(h->K);
+    for (int o = 0; o < h->K; ++o) {
+        OrderPlan& op = h->orders[o];
+        const int nl = c.n_layers[o];
+        REQUIRE(nl >= 1 && nl <= TANTE_MAX_LAYERS, "ValueError: Invalid block: empty segment.");
+        const std::string bp = "blocks." + std::to_string(o) + ".";
+        for (int i = 0; i < nl; ++i) {
+            LayerPlan lp;
+            lp.axis = c.axes[o][i];
+            REQUIRE(lp.axis == 'T' || lp.axis == 'H' || lp.axis == 'W',
+                    std::string("attention axis '") + lp.axis + "' is not implemented (supported: T, H, W)");
+            const std::string p = bp + "blocks." + std::to_string(i) + ".";
+            lp.ln1w = add_param(h, p + "ln1.weight", {C});
+            lp.ln1b = add_param(h, p + "ln1.bias", {C});
+            lp.inw = add_param(h, p + "attn.in_proj_weight", {3 * C, C});
+            lp.inb = add_param(h, p + "attn.in_proj_bias", {3 * C});
+            lp.outw = add_param(h, p + "attn.out_proj.weight", {C, C});
+            lp.outb = add_param(h, p + "attn.out_proj.bias", {C});
+            lp.ln2w = add_param(h, p + "ln2.weight", {C});
+            lp.ln2b = add_param(h, p + "ln2.bias", {C});
+            lp.m0w = add_param(h, p + "mlp.0.weight", {C, C});
+            lp.m0b = add_param(h, p + "mlp.0.bias", {C});
+            lp.m2w = add_param(h, p + "mlp.2.weight", {C, C});
+            lp.m2b = add_param(h, p + "mlp.2.bias", {C});
+            op.layers.push_back(lp);
+        }
+        const char* pn[3] = {"vertical", "horizontal", "temporal"};
+        const int plen[3] = {h->Hp, h->Wp, T};
+        for (int a = 0; a < 3; ++a) {
+            const std::string p = bp + pn[a] + "_propagator.";
+            op.prop[a][0] = add_param(h, p + "0.weight", {plen[a], plen[a]});
+            op.prop[a][1] = add_param(h, p + "0.bias", {plen[a]});
+            op.prop[a][2] = add_param(h, p + "2.weight", {plen[a], plen[a]});
+            op.prop[a][3] = add_param(h, p + "2.bias", {plen[a]});
+        }
+        const int dch[4] = {C, C2, C1, D};
+        for (int i = 0; i < 3; ++i) {
+            const int kk = k[2 - i];
+            const std::string p = "decoders." + std::to_string(o) + ".dec_conv_" + std::to_string(i + 1) + ".deconv.";
+            op.decw[i] = add_param(h, p + "weight", {dch[i], dch[i + 1], kk, kk},
+                                   i < 2 ? PACK_DECONV_NK : PACK_DECONV_KN, dch[i], dch[i + 1], kk);
+            if (i < 2) op.decb[i] = add_param(h, p + "bias", {dch[i + 1]}, PACK_BIAS_REP, dch[i + 1], 0, kk);
+            else op.decb[i] = add_param(h, p + "bias", {dch[i + 1]});
+        }
+        if (!c.deg) {
+            const std::string p = "interprators." + std::to_string(o) + ".interprete.";
+            const int ich[4] = {C, C / 2, C / 4, 1};
+            for (int i = 0; i < 3; ++i) {
+                op.intw[i] = add_param(h, p + std::to_string(2 * i) + ".weight", {ich[i + 1], ich[i]});
+                op.intb[i] = add_param(h, p + std::to_string(2 * i) + ".bias", {ich[i + 1]});
+            }
+            add_film("modifiers." + std::to_string(o) + ".", op.mod);
+        }
+    }
+    // derived tensors
+    h->film_t_off = h->arena_elems; h->arena_elems += (int64_t)T * 2 * C;
+    h->tseq_off = h->arena_elems;   h->arena_elems += 64;
+}
+
+inline float* AF(tante_handle_s* h, int64_t off) { return reinterpret_cast<float*>(h->arena.p) + off; }
+
+void dev_alloc(tante_handle_s* h, DevBuf& b, size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    if (b.bytes >= bytes) return;
+    if (b.p) { h->ws_bytes -= b.bytes; b.free(); }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) throw Error(TANTE_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    b.bytes = bytes;
+    h->ws_bytes += bytes;
+}
+
+struct StepIO {
+    const float* input = nullptr;   // window / ring (B,T,D,H,W)
+    const int* fcount = nullptr;
+    float* frames = nullptr; int n_cap = 1;
+    float* R_t = nullptr; int* n_dev = nullptr;
+    float* y_out = nullptr; float* ring_out = nullptr; int n_roll = 0;
+    bool rollout = false;
+    int per_sample = 0;
+    float out_T = 1.f;
+};
+
+RolloutState make_state(tante_handle_s* h, int B, int n_roll, float* rts_out, int* ns_out) {
+    RolloutState rs;
+    int* s = reinterpret_cast<int*>(h->state.p);
+    const int mb = h->max_batch;
+    rs.cum = s; rs.fcount = s + mb; rs.steps = s + 2 * mb; rs.n_cur = s + 3 * mb; rs.remaining = s + 4 * mb;
+    rs.rts_out = rts_out; rs.ns_out = ns_out; rs.n_roll = n_roll; rs.max_steps = n_roll;
+    return rs;
+}
+
+template <typename TA>
+void gemm(tante_handle_s* h, int epi, const TA* A, int lda, int64_t w_off, TA* Cout, int ldc, int M, int N, int K,
+          const EpiParams& ep, cudaStream_t st);
+
+template <>
+void gemm<float>(tante_handle_s* h, int epi, const float* A, int lda, int64_t w_off, float* Cout, int ldc, int M, int N,
+                 int K, const EpiParams& ep, cudaStream_t st) {
+    CK(launch_gemm_simt(epi, A, lda, AF(h, w_off), K, Cout, ldc, M, N, K, ep, st));
+    h->launches++;
+}
+
+template <typename TOut>
+void launch_layernorm(tante_handle_s* h, const float* x, int64_t w, int64_t b, TOut* y, int rows, cudaStream_t st) {
+    const int C = h->C;
+    const int blocks = (rows + 7) / 8;
+    if (C <= 256) layernorm_kernel<TOut, 2><<<blocks, 256, 0, st>>>(x, AF(h, w), AF(h, b), y, rows, C, 1e-5f);
+    else layernorm_kernel<TOut, 4><<<blocks, 256, 0, st>>>(x, AF(h, w), AF(h, b), y, rows, C, 1e-5f);
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+template <typename TA>
+void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axis, cudaStream_t st) {
+    int S, inner, nseq;
+    const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp;
+    if (axis == 'T') { S = T; inner = L; nseq = B * L; }
+    else if (axis == 'H') { S = Hp; inner = Wp; nseq = B * T * Wp; }
+    else { S = Wp; inner = 1; nseq = B * T * Hp; }
+    const long long total = (long long)nseq * h->cfg.n_head * S;
+    const int blocks = (int)((total + 127) / 128);
+    const float scale = 1.0f / sqrtf((float)h->HD);
+    const int causal = axis == 'T';
+#define ATT(HDv) axial_attention_kernel<TA, TA, HDv><<<blocks, 128, 0, st>>>(qkv, out, nseq, S, inner, h->cfg.n_head, h->C, causal, scale)
+    if (h->HD == 32) ATT(32); else if (h->HD == 64) ATT(64); else ATT(16);
+#undef ATT
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=T*/, const OrderPlan& op,
+                       cudaStream_t st) {
+    int S; long long IC, outer;
+    const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp, C = h->C;
+    if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
+    else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
+    else { S = T; IC = (long long)L * C; outer = B; }
+    const size_t smem = (size_t)(2 * S * 64 + 2 * S * S + 2 * S) * sizeof(float);
+    dim3 grid((unsigned)((IC + 63) / 64), (unsigned)outer);
+    REQUIRE(outer <= 65535, "batch too large for the propagator grid");
+    propagator_kernel<<<grid, 256, smem, st>>>(x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                               AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]));
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+template <typename TA>
+void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, float* deriv_dbg, cudaStream_t st) {
+    HeadParams hp{};
+    for (int k = 0; k < h->K; ++k) {
+        hp.z[k] = h->z2[k].p;
+        hp.w3[k] = AF(h, h->orders[k].decw[2]);
+        hp.b3[k] = AF(h, h->orders[k].decb[2]);
+    }
+    hp.K = h->K;
+    hp.fi = h->cfg.frame_interval;
+    hp.u_ring = io.input;
+    hp.fcount = io.fcount;
+    hp.n_arr = io.rollout ? rs.n_cur : reinterpret_cast<int*>(h->nbuf.p);
+    hp.frames = io.frames; hp.n_cap = io.n_cap;
+    hp.y_out = io.y_out; hp.ring_out = io.ring_out; hp.cum = io.rollout ? rs.cum : nullptr; hp.n_roll = io.n_roll;
+    hp.deriv_dbg = deriv_dbg;
+    const long long rows = (long long)B * h->L * h->geom.R1;
+    const int NO = h->geom.k0 * h->geom.k0 * h->D;
+    const size_t smem = (size_t)(h->K * h->C1 * NO + h->K * h->D) * sizeof(float);
+    const int blocks = (int)((rows + 127) / 128);
+#define HEAD(KO) taylor_head_kernel<TA, 8, KO><<<blocks, 128, smem, st>>>(hp, h->geom, h->C1, rows, B)
+    switch (h->K) {
+        case 1: HEAD(1); break;
+        case 2: HEAD(2); break;
+        case 3: HEAD(3); break;
+        default: HEAD(4); break;
+    }
+#undef HEAD
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+// One TANTE step (reference models/tante.py:125-176) as a launch sequence on `st`.
+template <typename TA>
+void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, cudaStream_t st) {
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K;
+    const PatchGeom& g = h->geom;
+    const int tokens = B * T * L;
+    float* x = reinterpret_cast<float*>(h->x.p);
+    TA* ln = reinterpret_cast<TA*>(h->ln.p);
+    TA* qkv = reinterpret_cast<TA*>(h->qkv.p);
+    TA* att = reinterpret_cast<TA*>(h->att.p);
+    TA* hid = reinterpret_cast<TA*>(h->hid.p);
+    TA* a1 = reinterpret_cast<TA*>(h->a1.p);
+    TA* a2 = reinterpret_cast<TA*>(h->a2.p);
+
+    // --- encoder (enc_dec_cnn.py:217-229) + t_encode FiLM + s_emb + t_emb (tante.py:132-141) ---
+    {
+        const int P = g.k0 * g.k1 * g.k2;
+        int WC = std::max(1, 64 / g.R1);
+        WC = std::min(WC, g.Wp);
+        const int K1 = g.k0 * g.k0 * g.D;
+        const size_t smem = (size_t)(g.D * P * P * WC + C1 * (K1 + 1) + C1) * sizeof(float);
+        dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
+        patch_embed_conv1_kernel<TA><<<grid, 256, smem, st>>>(io.input, io.fcount, g, AF(h, h->enc_w[0]),
+                                                              AF(h, h->enc_b[0]), C1, WC, a1);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
+        EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
+        e3.film = AF(h, h->film_t_off); e3.s_emb = AF(h, h->s_emb); e3.t_emb = AF(h, h->t_emb);
+        e3.T = T; e3.L = L; e3.ldr = C;
+        // the embed epilogue writes the fp32 residual stream directly
+        CK(launch_gemm_simt(EPI_EMBED, reinterpret_cast<const float*>(a2), g.k2 * g.k2 * C2, AF(h, h->enc_w[2]),
+                            g.k2 * g.k2 * C2, x, C, tokens, C, g.k2 * g.k2 * C2, e3, st));
+        h->launches++;
+    }
+    if (h->debug) CK(cudaMemcpyAsync(h->dbg_in.p, x, (size_t)tokens * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    float* rt = reinterpret_cast<float*>(h->rt.p);
+    for (int o = 0; o < K; ++o) {
+        const OrderPlan& op = h->orders[o];
+        // --- Attn_Backbone.forward (attn_backbone.py:134-191) ---
+        launch_propagator(h, x, B, 0, op, st);
+        launch_propagator(h, x, B, 1, op, st);
+        launch_propagator(h, x, B, 2, op, st);
+        for (const LayerPlan& lp : op.layers) {
+            launch_layernorm<TA>(h, x, lp.ln1w, lp.ln1b, ln, tokens, st);
+            EpiParams eq; eq.bias = AF(h, lp.inb);
+            gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, tokens, 3 * C, C, eq, st);
+            launch_attention<TA>(h, qkv, att, B, lp.axis, st);
+            EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x; eo.ldr = C;
+            CK(launch_gemm_simt(EPI_BIAS_RESID, reinterpret_cast<const float*>(att), C, AF(h, lp.outw), C, x, C, tokens,
+                                C, C, eo, st));
+            h->launches++;
+            launch_layernorm<TA>(h, x, lp.ln2w, lp.ln2b, ln, tokens, st);
+            EpiParams e0; e0.bias = AF(h, lp.m0b);
+            gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, C, tokens, C, C, e0, st);
+            EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x; e2.ldr = C;
+            CK(launch_gemm_simt(EPI_BIAS_RESID, reinterpret_cast<const float*>(hid), C, AF(h, lp.m2w), C, x, C, tokens,
+                                C, C, e2, st));
+            h->launches++;
+        }
+        // --- head of order o (tante.py:147-154) ---
+        float* d32 = reinterpret_cast<float*>(h->d32.p);
+        TA* dmod = reinterpret_cast<TA*>(h->dmod.p);
+        const long long LC = (long long)L * C;
+        const long long tot = (long long)B * LC;
+        const int eb = (int)((tot / 4 + 255) / 256);
+        last_frame_kernel<TA><<<eb, 256, 0, st>>>(x, dmod, d32, B, T, LC);
+        CK(cudaGetLastError());
+        h->launches++;
+        if (!h->cfg.deg) {
+            TA* i1 = reinterpret_cast<TA*>(h->i1.p);
+            TA* i2 = reinterpret_cast<TA*>(h->i2.p);
+            EpiParams ei; ei.bias = AF(h, op.intb[0]);
+            gemm<TA>(h, EPI_BIAS_RELU, dmod, C, op.intw[0], i1, C / 2, B * L, C / 2, C, ei, st);
+            ei.bias = AF(h, op.intb[1]);
+            gemm<TA>(h, EPI_BIAS_RELU, i1, C / 2, op.intw[1], i2, C / 4, B * L, C / 4, C / 2, ei, st);
+            rt_reduce_kernel<TA><<<B, 256, 0, st>>>(i2, AF(h, op.intw[2]), AF(h, op.intb[2]), L, C / 4, io.out_T,
+                                                    rt + (size_t)o * h->max_batch);
+            CK(cudaGetLastError());
+            h->launches++;
+            float* fb = reinterpret_cast<float*>(h->filmbuf.p);
+            film_params_kernel<<<B, 256, C * sizeof(float), st>>>(
+                rt + (size_t)o * h->max_batch, 1.0f, AF(h, op.mod[0]), AF(h, op.mod[1]), AF(h, op.mod[2]),
+                AF(h, op.mod[3]), AF(h, op.mod[4]), AF(h, op.mod[5]), AF(h, op.mod[6]), AF(h, op.mod[7]), C, fb);
+            CK(cudaGetLastError());
+            h->launches++;
+            film_apply_kernel<TA><<<eb, 256, 0, st>>>(d32, fb, dmod, LC, C, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+        TA* z1 = reinterpret_cast<TA*>(h->z1.p);
+        TA* z2 = reinterpret_cast<TA*>(h->z2[o].p);
+        EpiParams ed; ed.bias = AF(h, op.decb[0]);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, dmod, C, op.decw[0], z1, g.k2 * g.k2 * C2, B * L, g.k2 * g.k2 * C2, C, ed, st);
+        ed.bias = AF(h, op.decb[1]);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, z1, C2, op.decw[1], z2, g.k1 * g.k1 * C1, B * L * g.R2, g.k1 * g.k1 * C1, C2, ed, st);
+    }
+    // --- step-size selection + fused Taylor head (tante.py:156-171) ---
+    select_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(rt, K, h->max_batch, B, h->cfg.deg, h->cfg.output_length,
+                                                        io.per_sample, io.rollout ? (1 << 30) : io.n_cap,
+                                                        io.rollout ? nullptr : io.R_t,
+                                                        io.rollout ? nullptr : reinterpret_cast<int*>(h->nbuf.p), rs,
+                                                        io.rollout ? 1 : 0);
+    CK(cudaGetLastError());
+    h->launches++;
+    launch_head<TA>(h, io, B, rs, nullptr, st);
+    if (io.rollout) {
+        advance_state_kernel<<<1, 256, 0, st>>>(rs, B);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+}
+
+void ensure_ready(tante_handle_s* h, int B) {
+    if (!h->packed) throw Error(TANTE_ERR_STATE, "parameters not packed: call tante_bind_param for every parameter, then tante_pack_params");
+    if (B < 1 || B > h->max_batch) throw Error(TANTE_ERR_STATE, "batch exceeds tante_reserve(max_batch)");
+}
+
+void set_smem_attrs() {
+    static bool done = false;
+    if (done) return;
+    const int big = 160 * 1024;
+    CK(cudaFuncSetAttribute(propagator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define HEADATTR(TA, KO) CK(cudaFuncSetAttribute(taylor_head_kernel<TA, 8, KO>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
+    HEADATTR(float, 1); HEADATTR(float, 2); HEADATTR(float, 3); HEADATTR(float, 4);
+#undef HEADATTR
+    done = true;
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return TANTE_OK;
+    } catch (const Error& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return TANTE_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* tante_last_error(void) { return g_err.c_str(); }
+int tante_version(void) { return 1; }
+
+int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out) {
+    return guarded([&] {
+        REQUIRE(cfg && out, "null argument");
+        std::unique_ptr<tante_handle_s> h(new tante_handle_s());
+        h->cfg = *cfg;
+        h->device = device;
+        build_plan(h.get());
+        *out = h.release();
+    });
+}
+
+int tante_destroy(tante_handle_t h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->device);
+        DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
+                          &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
+                          &h->state, &h->dbg_in};
+        for (DevBuf* b : bufs) b->free();
+        for (auto& b : h->z2) b.free();
+        if (h->h_flag) cudaFreeHost(h->h_flag);
+        for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+        delete h;
+    });
+}
+
+int32_t tante_param_count(tante_handle_t h) { return h ? (int32_t)h->params.size() : 0; }
+const char* tante_param_name(tante_handle_t h, int32_t i) {
+    if (!h || i < 0 || i >= (int32_t)h->params.size()) return nullptr;
+    return h->params[i].name.c_str();
+}
+int64_t tante_param_numel(tante_handle_t h, int32_t i) {
+    if (!h || i < 0 || i >= (int32_t)h->params.size()) return -1;
+    return h->params[i].numel;
+}
+
+int tante_bind_param(tante_handle_t h, const char* name, const float* data, float* grad, int64_t numel) {
+    return guarded([&] {
+        REQUIRE(h && name && data, "null argument");
+        auto it = h->pindex.find(name);
+        REQUIRE(it != h->pindex.end(), std::string("unknown parameter: ") + name);
+        Param& p = h->params[it->second];
+        REQUIRE(p.numel == numel, std::string("size mismatch for ") + name + ": expected " + std::to_string(p.numel) +
+                                      ", got " + std::to_string(numel));
+        p.data = data;
+        p.grad = grad;
+        h->packed = false;
+    });
+}
+
+int tante_pack_params(tante_handle_t h, void* stream) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        CK(cudaSetDevice(h->device));
+        set_smem_attrs();
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        for (const Param& p : h->params)
+            if (!p.data) throw Error(TANTE_ERR_STATE, "parameter not bound: " + p.name);
+        dev_alloc(h, h->arena, (size_t)h->arena_elems * sizeof(float));
+        if (h->cfg.precision == TANTE_PREC_BF16) dev_alloc(h, h->arena_bf16, (size_t)h->arena_elems * sizeof(__nv_bfloat16));
+        std::vector<PackDesc> descs;
+        int64_t max_numel = 0;
+        for (const Param& p : h->params) {
+            PackDesc d;
+            d.src = p.data; d.dst_off = p.off; d.numel = p.packed_numel; d.mode = p.mode;
+            d.d0 = p.d0; d.d1 = p.d1; d.k = p.k;
+            descs.push_back(d);
+            max_numel = std::max(max_numel, p.packed_numel);
+        }
+        dev_alloc(h, h->descs, descs.size() * sizeof(PackDesc));
+        // pageable H2D copy of a small table: synchronous w.r.t. the host buffer, ordered on `st`
+        CK(cudaMemcpyAsync(h->descs.p, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        dim3 grid((unsigned)std::min<int64_t>((max_numel + 255) / 256, 64), (unsigned)descs.size());
+        pack_params_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const PackDesc*>(h->descs.p), AF(h, 0),
+                                                 reinterpret_cast<__nv_bfloat16*>(h->arena_bf16.p));
+        CK(cudaGetLastError());
+        h->launches++;
+        // derived: t_seq (tante.py:279-285: [-(T-2)..-1,-0,0]*fi) and the t_encode FiLM table
+        std::vector<float> tseq(64, 0.f);
+        {
+            std::vector<float> s;
+            s.push_back(0.0f);
+            for (int i = 0; i < h->T - 1; ++i) s.push_back(-(float)i * h->cfg.frame_interval);
+            std::reverse(s.begin(), s.end());
+            for (int i = 0; i < h->T; ++i) tseq[i] = s[i];
+        }
+        CK(cudaMemcpyAsync(AF(h, h->tseq_off), tseq.data(), 64 * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        film_params_kernel<<<h->T, 256, h->C * sizeof(float), st>>>(
+            AF(h, h->tseq_off), 1.0f, AF(h, h->tenc[0]), AF(h, h->tenc[1]), AF(h, h->tenc[2]), AF(h, h->tenc[3]),
+            AF(h, h->tenc[4]), AF(h, h->tenc[5]), AF(h, h->tenc[6]), AF(h, h->tenc[7]), h->C, AF(h, h->film_t_off));
+        CK(cudaGetLastError());
+        h->launches++;
+        h->packed = true;
+    });
+}
+
+int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t training) {
+    return guarded([&] {
+        REQUIRE(h && max_batch >= 1, "bad argument");
+        (void)training;
+        CK(cudaSetDevice(h->device));
+        if (max_batch <= h->max_batch && max_roll <= h->max_roll) return;
+        max_batch = std::max(max_batch, h->max_batch);
+        max_roll = std::max(max_roll, h->max_roll);
+        const size_t es = h->cfg.precision == TANTE_PREC_BF16 ? 2 : 4;
+        const size_t tokens = (size_t)max_batch * h->T * h->L;
+        const size_t BL = (size_t)max_batch * h->L;
+        const int C = h->C, C1 = h->C1, C2 = h->C2;
+        const PatchGeom& g = h->geom;
+        dev_alloc(h, h->x, tokens * C * 4);
+        dev_alloc(h, h->ln, tokens * C * es);
+        dev_alloc(h, h->qkv, tokens * 3 * C * es);
+        dev_alloc(h, h->att, tokens * C * es);
+        dev_alloc(h, h->hid, tokens * C * es);
+        dev_alloc(h, h->a1, tokens * g.R1 * C1 * es);
+        dev_alloc(h, h->a2, tokens * g.R2 * C2 * es);
+        dev_alloc(h, h->d32, BL * C * 4);
+        dev_alloc(h, h->dmod, BL * C * es);
+        dev_alloc(h, h->i1, BL * (C / 2) * es);
+        dev_alloc(h, h->i2, BL * (C / 4) * es);
+        dev_alloc(h, h->z1, BL * g.R2 * C2 * es);
+        h->z2.resize(h->K);
+        for (auto& b : h->z2) dev_alloc(h, b, BL * g.R1 * C1 * es);
+        dev_alloc(h, h->rt, (size_t)h->K * max_batch * 4);
+        dev_alloc(h, h->Rt, (size_t)max_batch * 4);
+        dev_alloc(h, h->nbuf, (size_t)max_batch * 4);
+        dev_alloc(h, h->filmbuf, (size_t)max_batch * 2 * C * 4);
+        dev_alloc(h, h->ring, (size_t)max_batch * h->T * h->D * h->cfg.H * h->cfg.W * 4);
+        dev_alloc(h, h->state, ((size_t)4 * max_batch + 16) * 4);
+        if (h->debug) dev_alloc(h, h->dbg_in, tokens * C * 4);
+        if (!h->h_flag) {
+            CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flag), 64));
+            for (auto& e : h->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        // the state layout depends on max_batch -> re-derived in make_state
+        h->max_batch = max_batch;
+        h->max_roll = max_roll;
+    });
+}
+
+int64_t tante_workspace_bytes(tante_handle_t h) { return h ? h->ws_bytes : -1; }
+
+int tante_forward(tante_handle_t h, const float* input, int32_t B, float out_T, int32_t n_cap, int32_t per_sample,
+                  float* frames, float* R_t, int32_t* n_dev, int32_t* n_host, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && input && frames, "null argument");
+        REQUIRE(n_cap >= 1, "n_cap must be >= 1");
+        CK(cudaSetDevice(h->device));
+        ensure_ready(h, B);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        StepIO io;
+        io.input = input; io.frames = frames; io.n_cap = n_cap; io.R_t = R_t; io.n_dev = n_dev;
+        io.per_sample = per_sample; io.out_T = out_T;
+        RolloutState rs{};
+        if (h->cfg.precision == TANTE_PREC_FP32) run_step<float>(h, io, B, rs, st);
+        else throw Error(TANTE_ERR_INVALID, "bf16 tensor path not built yet");
+        h->last_B = B;
+        if (n_dev) CK(cudaMemcpyAsync(n_dev, h->nbuf.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+        if (n_host) {
+            CK(cudaMemcpyAsync(h->h_flag + 8, h->nbuf.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            *n_host = h->h_flag[8];
+        }
+    });
+}
+
+int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_roll, float out_T, int32_t per_sample,
+                  float* y_out, float* rts_out, int32_t* ns_out, int32_t* steps_out, int32_t sync, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && window && y_out, "null argument");
+        REQUIRE(n_roll >= 1, "n_roll must be >= 1");
+        REQUIRE(h->cfg.deg || (rts_out && ns_out), "rts_out/ns_out required for the adaptive model");
+        CK(cudaSetDevice(h->device));
+        ensure_ready(h, B);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        const size_t wbytes = (size_t)B * h->T * h->D * h->cfg.H * h->cfg.W * 4;
+        CK(cudaMemcpyAsync(h->ring.p, window, wbytes, cudaMemcpyDeviceToDevice, st));
+        RolloutState rs = make_state(h, B, n_roll, rts_out, ns_out);
+        init_state_kernel<<<(B + 127) / 128, 128, 0, st>>>(rs, B, h->T);
+        CK(cudaGetLastError());
+        h->launches++;
+        StepIO io;
+        io.input = reinterpret_cast<const float*>(h->ring.p);
+        io.fcount = rs.fcount;
+        io.y_out = y_out; io.ring_out = reinterpret_cast<float*>(h->ring.p); io.n_roll = n_roll;
+        io.rollout = true; io.per_sample = per_sample; io.out_T = out_T;
+        // Every step emits >= 1 frame per running sample, so n_roll steps always suffice.  The host
+        // checks the device's `remaining` counter with a one-step lag (flag copy + event per step),
+        // so an adaptive rollout stops at most one step late and never stalls the stream.
+        int pending[2] = {0, 0};
+        for (int s = 0; s < n_roll; ++s) {
+            const int slot = s & 1;
+            if (pending[slot]) {
+                CK(cudaEventSynchronize(h->ev[slot]));
+                pending[slot] = 0;
+                if (h->h_flag[slot] == 0) break;
+            }
+            if (h->cfg.precision == TANTE_PREC_FP32) run_step<float>(h, io, B, rs, st);
+            else throw Error(TANTE_ERR_INVALID, "bf16 tensor path not built yet");
+            CK(cudaMemcpyAsync(h->h_flag + slot, rs.remaining, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->ev[slot], st));
+            pending[slot] = 1;
+        }
+        if (steps_out) CK(cudaMemcpyAsync(steps_out, rs.steps, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+        h->last_B = B;
+        if (sync) CK(cudaStreamSynchronize(st));
+    });
+}
+
+int tante_debug_stage(tante_handle_t h, const char* stage, float* dst, int64_t cap, int64_t* numel, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && stage && dst && numel, "null argument");
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        const std::string s(stage);
+        if (s == "enable") { h->debug = true; *numel = 0; return; }
+        const int B = h->last_B;
+        REQUIRE(B > 0, "no forward has run yet");
+        const int64_t lat = (int64_t)B * h->T * h->L * h->C;
+        const void* src = nullptr;
+        int64_t n = 0;
+        if (s == "latent") { src = h->x.p; n = lat; }
+        else if (s == "latent_in") { REQUIRE(h->debug && h->dbg_in.p, "debug capture not enabled before reserve"); src = h->dbg_in.p; n = lat; }
+        else if (s == "rt") { src = h->rt.p; n = (int64_t)h->K * h->max_batch; }
+        else if (s == "deriv") {
+            // decoded derivative fields [K][B][D][H][W]: re-run the fused head on the kept stage-1
+            // activations with every write but the debug one disabled
+            n = (int64_t)h->K * B * h->D * h->cfg.H * h->cfg.W;
+            REQUIRE(cap >= n, "destination too small");
+            CK(cudaMemsetAsync(h->nbuf.p, 0, (size_t)B * 4, st));
+            StepIO io;
+            io.input = reinterpret_cast<const float*>(h->ring.p);
+            RolloutState rs{};
+            if (h->cfg.precision == TANTE_PREC_FP32) launch_head<float>(h, io, B, rs, dst, st);
+            else throw Error(TANTE_ERR_INVALID, "bf16 tensor path not built yet");
+            *numel = n;
+            return;
+        }
+        else throw Error(TANTE_ERR_INVALID, "unknown stage " + s);
+        REQUIRE(cap >= n, "destination too small");
+        CK(cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        *numel = n;
+    });
+}
+
+int64_t tante_launch_count(tante_handle_t h) { return h ? h->launches : -1; }
+
+int tante_bench_head(tante_handle_t h, int32_t B, int32_t n_frames, int32_t iters, float* ms_out, void* stream) {
+    return guarded([&] {
+        (void)h; (void)B; (void)n_frames; (void)iters; (void)ms_out; (void)stream;
+        throw Error(TANTE_ERR_INVALID, "tante_bench_head: not built yet");
+    });
+}
+
+}  // extern "C"

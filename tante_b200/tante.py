@@ -1,0 +1,383 @@
+"""`TANTE` -- drop-in for the reference `models.TANTE` (reference models/tante.py:37-176).
+
+Same constructor signature, same `forward(input, out_T)` contract, same `state_dict` keys,
+shapes and default initialisation stream (the parameter containers are created in the
+reference's order with the same torch initialisers, so `torch.manual_seed(s); TANTE(...)`
+yields the reference's weights).  All arithmetic runs in libtante_b200.so (hand-written
+sm_100a CUDA) through the C ABI in include/tante_b200.h; PyTorch only owns the tensors.
+There is no CPU path: calling the module on a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+
+# reference models/enc_dec_cnn.py:39-46
+Patch_map = {64: (4, 4, 4), 32: (4, 4, 2), 16: (4, 2, 2), 8: (2, 2, 2), 4: (2, 2, 1), 2: (2, 1, 1)}
+
+
+@dataclass
+class TanteMetadata:
+    """Same fields as the reference dataclass (data/dataset.py:43-63); only `n_fields` and
+    `spatial_resolution` are read by the model (models/tante.py:64-66)."""
+    dataset_name: str = "synthetic"
+    n_spatial_dims: int = 2
+    spatial_resolution: Tuple[int, ...] = (128, 384)
+    field_names: Optional[Dict[int, List[str]]] = None
+    boundary_condition_types: Optional[List[str]] = None
+    n_files: int = 0
+    n_trajectories_per_file: Optional[List[int]] = None
+    n_steps_per_trajectory: Optional[List[int]] = None
+    n_fields: int = 4
+
+    @property
+    def sample_shapes(self):
+        return {
+            "input_fields": [*self.spatial_resolution, self.n_fields],
+            "output_fields": [*self.spatial_resolution, self.n_fields],
+            "space_grid": [*self.spatial_resolution, self.n_spatial_dims],
+        }
+
+
+class _ParamsOnly(nn.Module):
+    """Parameter container: keeps the reference's module tree (hence state_dict keys and the
+    init RNG stream) but owns no arithmetic."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container of tante_b200.TANTE: compute goes through libtante_b200.so")
+
+
+class _PatchConv(_ParamsOnly):       # RealConv2d (enc_dec_cnn.py:49-94)
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size=(k, k), stride=(k, k), padding=((k - 1) // 2, (k - 1) // 2))
+
+
+class _PatchDeconv(_ParamsOnly):     # RealTransConv2d (enc_dec_cnn.py:113-160)
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.deconv = nn.ConvTranspose2d(cin, cout, kernel_size=(k, k), stride=(k, k),
+                                         padding=((k - 1) // 2, (k - 1) // 2), output_padding=0)
+
+
+class _EncCNN(_ParamsOnly):          # enc_CNN (enc_dec_cnn.py:187-215)
+    def __init__(self, D, C, ks):
+        super().__init__()
+        self.enc_conv_1 = _PatchConv(D, C // 4, ks[0])
+        self.enc_conv_2 = _PatchConv(C // 4, C // 2, ks[1])
+        self.enc_conv_3 = _PatchConv(C // 2, C, ks[2])
+
+
+class _DecCNN(_ParamsOnly):          # dec_CNN (enc_dec_cnn.py:232-261)
+    def __init__(self, D, C, ks):
+        super().__init__()
+        self.dec_conv_1 = _PatchDeconv(C, C // 2, ks[2])
+        self.dec_conv_2 = _PatchDeconv(C // 2, C // 4, ks[1])
+        self.dec_conv_3 = _PatchDeconv(C // 4, D, ks[0])
+
+
+class _Block(_ParamsOnly):           # TransformerBlock (attn_backbone.py:38-57)
+    def __init__(self, C, n_head, mlp_ratio, dropout):
+        super().__init__()
+        self.ln1 = nn.LayerNorm(C)
+        self.attn = nn.MultiheadAttention(C, n_head, batch_first=True, dropout=dropout, bias=True)
+        self.ln2 = nn.LayerNorm(C)
+        hidden = int(C * mlp_ratio)
+        self.mlp = nn.Sequential(nn.Linear(C, hidden), nn.GELU(approximate="tanh"), nn.Linear(hidden, C))
+        self.drop = nn.Dropout(dropout)
+
+
+class _Backbone(_ParamsOnly):        # Attn_Backbone (attn_backbone.py:88-132)
+    def __init__(self, T, Hp, Wp, C, axes, n_head, mlp_ratio, dropout):
+        super().__init__()
+        if axes == "":
+            raise ValueError("Invalid block: empty segment.")
+        self.blocks = nn.ModuleList()
+        self.vertical_propagator = nn.Sequential(nn.Linear(Hp, Hp), nn.GELU(), nn.Linear(Hp, Hp))
+        self.horizontal_propagator = nn.Sequential(nn.Linear(Wp, Wp), nn.GELU(), nn.Linear(Wp, Wp))
+        self.temporal_propagator = nn.Sequential(nn.Linear(T, T), nn.GELU(), nn.Linear(T, T))
+        self.channel_blocks = nn.ModuleList()
+        for _ in axes:
+            self.blocks.append(_Block(C, n_head, mlp_ratio, dropout))
+
+
+class _Film(_ParamsOnly):            # film (tante.py:203-216)
+    def __init__(self, C):
+        super().__init__()
+        self.condition_to_scale = nn.Sequential(nn.Linear(1, C // 2), nn.ReLU(), nn.Linear(C // 2, C))
+        self.condition_to_shift = nn.Sequential(nn.Linear(1, C // 2), nn.ReLU(), nn.Linear(C // 2, C))
+
+
+class _Interprator(_ParamsOnly):     # interprator (tante.py:178-189)
+    def __init__(self, C):
+        super().__init__()
+        self.interprete = nn.Sequential(nn.Linear(C, C // 2), nn.ReLU(), nn.Linear(C // 2, C // 4), nn.ReLU(),
+                                        nn.Linear(C // 4, 1))
+
+
+def _sincos_1d(embed_dim, pos):       # tante.py:232-242
+    omega = torch.arange(embed_dim // 2, dtype=torch.float32)
+    omega /= embed_dim / 2.0
+    omega = 1.0 / 10000 ** omega
+    out = torch.einsum("m,d->md", pos.reshape(-1), omega)
+    return torch.cat([torch.sin(out), torch.cos(out)], dim=1)
+
+
+def _t_emb_init(C, T):                # tante.py:243-249
+    return _sincos_1d(C, torch.arange(T, dtype=torch.float32)).unsqueeze(0)
+
+
+def _s_emb_init(C, Hp, Wp):           # tante.py:251-276 ("w goes first" meshgrid + raw reshape)
+    gw, gh = torch.meshgrid(torch.arange(Wp, dtype=torch.float32), torch.arange(Hp, dtype=torch.float32),
+                            indexing="ij")
+    grid = torch.stack([gh, gw], dim=0).reshape(2, 1, Hp, Wp)
+    emb = torch.cat([_sincos_1d(C // 2, grid[0]), _sincos_1d(C // 2, grid[1])], dim=1)
+    return emb.view(Hp, Wp, C).unsqueeze(0)
+
+
+class _Engine:
+    """One libtante_b200 handle = (config, precision, device) + bound parameters."""
+
+    def __init__(self, model: "TANTE", precision: int, device: torch.device):
+        self.lib = _abi.load()
+        cfg = _abi.TanteConfig()
+        cfg.in_T = model.T
+        cfg.n_fields = model.n_channel
+        cfg.H, cfg.W = model.shape
+        cfg.taylor_order = model.taylor_order
+        cfg.n_head = model.n_head
+        cfg.embed_dim = model.C
+        cfg.patch_scale = model.patch_scale
+        cfg.deg = 1 if model.deg else 0
+        cfg.output_length = int(model.output_length)
+        cfg.frame_interval = float(model.frame_interval)
+        cfg.precision = precision
+        for k, seg in enumerate(model.blocks_axes):
+            if len(seg) > _abi.TANTE_MAX_LAYERS:
+                raise ValueError("too many layers in one attn_axes segment")
+            cfg.n_layers[k] = len(seg)
+            cfg.axes[k].value = seg.encode()
+        self.handle = ctypes.c_void_p()
+        self.device = device
+        _abi.check(self.lib.tante_create(ctypes.byref(cfg), device.index or 0, ctypes.byref(self.handle)))
+        self.names = [self.lib.tante_param_name(self.handle, i).decode()
+                      for i in range(self.lib.tante_param_count(self.handle))]
+        self.bound_sig = None
+        self.max_batch = 0
+        self.max_roll = 0
+
+    def close(self):
+        if self.handle:
+            self.lib.tante_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync_params(self, model: "TANTE", stream: int):
+        """(Re)bind + repack when any parameter storage or version changed (optimizer step,
+        load_state_dict, .to())."""
+        params = dict(model.named_parameters())
+        sig = tuple((n, params[n].data_ptr(), params[n]._version) for n in self.names)
+        if sig == self.bound_sig:
+            return
+        for n in self.names:
+            p = params[n]
+            if p.device != self.device or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError(f"parameter {n} must be a contiguous float32 tensor on {self.device}")
+            _abi.check(self.lib.tante_bind_param(self.handle, n.encode(), p.data_ptr(), None, p.numel()))
+        _abi.check(self.lib.tante_pack_params(self.handle, stream))
+        self.bound_sig = sig
+
+    def reserve(self, B: int, n_roll: int = 0):
+        if B > self.max_batch or n_roll > self.max_roll:
+            self.max_batch = max(B, self.max_batch)
+            self.max_roll = max(n_roll, self.max_roll)
+            _abi.check(self.lib.tante_reserve(self.handle, self.max_batch, self.max_roll, 0))
+
+
+class TANTE(nn.Module):
+    """B200-native TANTE.  Constructor mirrors reference models/tante.py:38-60."""
+
+    def __init__(
+        self,
+        in_T,
+        dset_metadata=None,
+        taylor_order: int = 1,
+        frame_interval: float = 1.0,
+        output_length=1,
+        attn_axes: str = "THWTHWTHW",
+        expanded_channel: int = 128,
+        n_head: int = 8,
+        mlp_ratio: float = 1.0,
+        dropout: float = 0.0,
+        enc_dec_type: str = "cnn",
+        embed_dim: int = 256,
+        modes1: int = 32,
+        modes2: int = 32,
+        patch_scale: int = 32,
+        overlap_ratio: float = 0.0,
+        deg: bool = True,
+        precision: str = "fp32",
+    ):
+        super().__init__()
+        self.n_channel = dset_metadata.n_fields if dset_metadata else 4
+        self.T = in_T
+        self.shape = tuple(dset_metadata.spatial_resolution) if dset_metadata else (128, 384)
+        self.patch_scale = patch_scale
+        self.H_p = self.shape[0] // patch_scale
+        self.W_p = self.shape[1] // patch_scale
+        self.C = embed_dim
+        self.n_head = n_head
+        self.taylor_order = taylor_order
+        self.frame_interval = frame_interval
+        self.output_length = output_length
+        self.deg = deg
+        self.dropout = dropout
+        self.precision = precision
+
+        # validation identical to tante.py:75-83 (including the unreachable 'X,' entry)
+        self.attn_axes = attn_axes.replace(" ", "")
+        if set(self.attn_axes) - {'T', 'H', 'W', 'L', 'A', 'C', 'X,', 'Y', '-'}:
+            raise ValueError("There are invalid letters")
+        self.blocks_axes = [p.strip() for p in self.attn_axes.split("-")]
+        if len(self.blocks_axes) != taylor_order:
+            raise ValueError(
+                f"Block allocation doesn't match expansion order: expected {taylor_order} parts, "
+                f"got {len(self.blocks_axes)} (input='{self.attn_axes}').")
+        if enc_dec_type != "cnn":
+            raise NotImplementedError("enc_dec_type='fno' is outside the B200 hot path (SURVEY.md §8(f) rank 2)")
+        if overlap_ratio != 0.0:
+            raise NotImplementedError("overlap_ratio != 0 is not supported by the patch-GEMM kernels")
+        if float(mlp_ratio) != 1.0:
+            raise NotImplementedError("mlp_ratio != 1.0 is not supported yet")
+        ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
+
+        # parameter containers, created in the reference's order (tante.py:85-123)
+        self.decoders = nn.ModuleList()
+        self.encoder = _EncCNN(self.n_channel, embed_dim, ks)
+        for _ in range(taylor_order):
+            self.decoders.append(_DecCNN(self.n_channel, embed_dim, ks))
+        self.blocks = nn.ModuleList()
+        for seg in self.blocks_axes:
+            self.blocks.append(_Backbone(self.T, self.H_p, self.W_p, self.C, seg, n_head, mlp_ratio, dropout))
+        self.t_emb = nn.Parameter(_t_emb_init(self.C, self.T))
+        self.s_emb = nn.Parameter(_s_emb_init(self.C, self.H_p, self.W_p))
+        self.t_encode = _Film(self.C)
+        if not self.deg:
+            self.interprators = nn.ModuleList([_Interprator(self.C) for _ in range(taylor_order)])
+            self.modifiers = nn.ModuleList([_Film(self.C) for _ in range(taylor_order)])
+        self._engines: Dict[Tuple[int, str], _Engine] = {}
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engines"] = {}          # native handles are per-process, rebuilt lazily
+        return st
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _precision_code(self) -> int:
+        if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            return _abi.PREC_BF16
+        return _abi.PREC_BF16 if self.precision == "bf16" else _abi.PREC_FP32
+
+    def _engine(self, device: torch.device) -> _Engine:
+        if device.type != "cuda":
+            raise RuntimeError("tante_b200.TANTE runs only on CUDA (sm_100a) tensors; there is no CPU path")
+        prec = self._precision_code()
+        key = (prec, str(device))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, prec, device)
+            self._engines[key] = eng
+        eng.sync_params(self, torch.cuda.current_stream(device).cuda_stream)
+        return eng
+
+    def _check_inference(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "tante_b200.TANTE: the differentiable (training) path is not built yet; call under "
+                "torch.inference_mode()/no_grad() as the reference evaluators do (r_evaler.py:117)")
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not supported")
+
+    def _prep_input(self, input: torch.Tensor) -> torch.Tensor:
+        if input.dim() != 5:
+            raise ValueError("input must be (B, T, D, H, W)")
+        if input.shape[1] != self.T:
+            input = input[:, -self.T:, ...]           # tante.py:127-128
+        B, T, D, H, W = input.shape
+        if T != self.T or D != self.n_channel or (H, W) != tuple(self.shape):
+            raise ValueError(f"input shape {tuple(input.shape)} does not match the model "
+                             f"(T={self.T}, D={self.n_channel}, HxW={self.shape})")
+        return input.to(torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, input, out_T=1):
+        """(B,>=T,D,H,W) -> frames (B,n,D,H,W) [and R_t (B,) when deg=False] (tante.py:125-176)."""
+        self._check_inference()
+        x = self._prep_input(input)
+        eng = self._engine(x.device)
+        B = x.shape[0]
+        if not self.deg and out_T < 1:
+            raise ValueError("out_T must be >= 1")
+        n_cap = int(self.output_length) if self.deg else max(1, int(math.floor(out_T + 0.001)))
+        eng.reserve(B)
+        frames = torch.empty((B, n_cap, self.n_channel, *self.shape), device=x.device, dtype=torch.float32)
+        R_t = None if self.deg else torch.empty((B,), device=x.device, dtype=torch.float32)
+        n_host = ctypes.c_int32(0)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _abi.check(eng.lib.tante_forward(eng.handle, x.data_ptr(), B, float(out_T), n_cap, 0, frames.data_ptr(),
+                                         None if R_t is None else R_t.data_ptr(), None, ctypes.byref(n_host),
+                                         stream))
+        n = n_host.value
+        out = frames if n == n_cap else frames[:, :n].contiguous()
+        if self.deg:
+            return out
+        return out, R_t
+
+    @torch.no_grad()
+    def rollout(self, window, n_steps_rollout: int, out_T=None, per_sample: bool = False, sync: bool = True):
+        """Device-resident adaptive rollout (R_Evaler.rollout_model, r_evaler.py:87-105).
+
+        window (B,>=T,D,H,W) channels-first -> y (B,n_roll,H,W,D) channels-last, Rts (max_steps,B),
+        ns (max_steps,B) frames per model call, steps (B,) model calls per sample.  `per_sample=False`
+        reproduces the reference (sample 0's R_t governs the batch); `per_sample=True` gives each
+        trajectory its own step sequence (the reference's B=1 behaviour, applied per trajectory)."""
+        x = self._prep_input(window)
+        eng = self._engine(x.device)
+        B = x.shape[0]
+        out_T = float(n_steps_rollout if out_T is None else out_T)
+        eng.reserve(B, n_steps_rollout)
+        dev = x.device
+        y = torch.empty((B, n_steps_rollout, *self.shape, self.n_channel), device=dev, dtype=torch.float32)
+        rts = torch.zeros((n_steps_rollout, B), device=dev, dtype=torch.float32)
+        ns = torch.zeros((n_steps_rollout, B), device=dev, dtype=torch.int32)
+        steps = torch.zeros((B,), device=dev, dtype=torch.int32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _abi.check(eng.lib.tante_rollout(eng.handle, x.data_ptr(), B, int(n_steps_rollout), out_T,
+                                         1 if per_sample else 0, y.data_ptr(), rts.data_ptr(), ns.data_ptr(),
+                                         steps.data_ptr(), 1 if sync else 0, stream))
+        return y, rts, ns, steps
+
+    # ------------------------------------------------------------------ test / profiling hooks
+    def debug_stage(self, stage: str, numel: int) -> torch.Tensor:
+        dev = next(self.parameters()).device
+        eng = self._engine(dev)
+        out = torch.empty((max(numel, 1),), device=dev, dtype=torch.float32)
+        got = ctypes.c_int64(0)
+        _abi.check(eng.lib.tante_debug_stage(eng.handle, stage.encode(), out.data_ptr(), out.numel(), ctypes.byref(got),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+        return out[:got.value]
+
+    def launch_count(self) -> int:
+        return sum(int(e.lib.tante_launch_count(e.handle)) for e in self._engines.values())

@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(256) propagator_kernel(float* __restrict__ x, 
     float* sw2 = sw1 + S * S;      // [S][S]
     float* sb1 = sw2 + S * S;
     float* sb2 = sb1 + S;
-    const long long col0 = (long long)blockIdx.x * 64;
-    const long long outer = blockIdx.y;
+    const long long col0 = (long long)blockIdx.y * 64;
+    const long long outer = blockIdx.x;
     float* base = x + (size_t)outer * S * IC + col0;
     const int col = threadIdx.x % 64, rg = threadIdx.x / 64;  // 4 row groups
     for (int i = threadIdx.x; i < S * S; i += blockDim.x) { sw1[i] = W1[i]; sw2[i] = W2[i]; }

@@ -321,8 +321,8 @@ void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
     const size_t smem = (size_t)(2 * S * 64 + 2 * S * S + 2 * S) * sizeof(float);
-    dim3 grid((unsigned)((IC + 63) / 64), (unsigned)outer);
-    REQUIRE(outer <= 65535, "batch too large for the propagator grid");
+    dim3 grid((unsigned)outer, (unsigned)((IC + 63) / 64));
+    REQUIRE((IC + 63) / 64 <= 65535, "latent too large for the propagator grid");
     propagator_kernel<<<grid, 256, smem, st>>>(x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
                                                AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]));
     CK(cudaGetLastError());

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- TANTE hot-path throughput on B200 (driver contract: one JSON line on rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200-native arm
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+Workload `rollout` (BASELINE.json configs[2]): adaptive-step rollout inference on the synthetic
+Rayleigh-Benard shape (4 fields, 512x128), n_steps_rollout frames per trajectory, trajectories sharded
+over the ranks with NO data-path collective (weak scaling: fixed trajectories per GPU).
+A "step" = one rollout pass over one batch of trajectories.  value = trajectories/s (whole job).
+
+Timed regions use CUDA events on the launching stream, W >= 3 warm-up steps, inputs far larger than
+L2 per step (stated in `config`), barrier + synchronize on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPES = {  # (D, H, W)
+    "trl": (4, 128, 384), "active_matter": (11, 256, 256), "rayleigh_benard": (4, 512, 128),
+    "viscoelastic": (8, 512, 512),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="rollout", choices=["rollout"])
+    ap.add_argument("--shape", default="rayleigh_benard", choices=sorted(SHAPES))
+    ap.add_argument("--batch", type=int, default=64, help="trajectories per GPU per step")
+    ap.add_argument("--n-roll", type=int, default=8)
+    ap.add_argument("--taylor-order", type=int, default=1)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--rt-bias", type=float, default=0.0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def model_axes(K):
+    return "-".join(["THWTHWTHW"] + ["THW"] * (K - 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_setup(args):
+    import torch
+    from oracle import tante_oracle as O
+    D, H, W = SHAPES[args.shape]
+    cfg = O.OracleConfig(n_fields=D, H=H, W=W, taylor_order=args.taylor_order, attn_axes=model_axes(args.taylor_order),
+                         deg=False)
+    return O, cfg
+
+
+def cpu_leg(args, seconds, state_dict=None):
+    """The reference's CPU implementation of the path (oracle port of models/tante.py + r_evaler.py:87-105)
+    on all host threads, on a bounded sample of the same workload: single-trajectory rollouts."""
+    import torch
+    O, cfg = oracle_setup(args)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = state_dict if state_dict is not None else O.make_state_dict(cfg, 211, args.rt_bias)
+    x = O.make_input(cfg, 1, 212)
+    with torch.inference_mode():
+        O.rollout_eval(sd, cfg, x, args.n_roll)            # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while True:
+            O.rollout_eval(sd, cfg, x, args.n_roll)
+            n += 1
+            el = time.perf_counter() - t0
+            if el > seconds or n >= 64:
+                break
+    return {"value": n / el, "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} single-trajectory rollouts (B=1, {args.n_roll} frames, {args.shape} shape, fp32, "
+                      f"torch {torch.__version__} CPU) in {el:.1f}s"}, el / max(n, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = max(args.warmup, 1)
+    steps = max(args.steps, 1)
+    import torch
+    O, cfg = oracle_setup(args)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.make_state_dict(cfg, 211, args.rt_bias)
+    x = O.make_input(cfg, 1, 212)
+    # each step = a bounded sample of the workload: ONE trajectory rollout (the b200 arm does `batch` per step)
+    with torch.inference_mode():
+        for _ in range(min(warm, 2)):
+            O.rollout_eval(sd, cfg, x, args.n_roll)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.rollout_eval(sd, cfg, x, args.n_roll)
+        el = time.perf_counter() - t0
+    val = steps / el
+    D, H, W = SHAPES[args.shape]
+    line = {
+        "impl": "reference", "metric": "rollout_trajectories_per_s", "value": val, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} single-trajectory rollouts, one per step"},
+        "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(args, batch):
+    D, H, W = SHAPES[args.shape]
+    return {"workload": f"adaptive rollout inference, synthetic {args.shape} shape ({D} fields, {H}x{W}), "
+                        f"{args.n_roll} frames/trajectory (BASELINE.json configs[2])",
+            "trajectories_per_gpu_per_step": batch, "n_steps_rollout": args.n_roll, "taylor_order": args.taylor_order,
+            "attn_axes": model_axes(args.taylor_order), "patch_scale": 8, "embed_dim": 256, "deg": False,
+            "weights": "random init, torch.manual_seed(211), reference initialisers", "rt_bias": args.rt_bias,
+            "l2_hygiene": "per-step working set (latents+activations) >> 126 MB L2; no explicit flush",
+            "parallelism": f"trajectory-sharded x{args.gpus}, no collective"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from tante_b200 import TANTE, TanteMetadata
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D, H, W = SHAPES[args.shape]
+    B, n_roll = args.batch, args.n_roll
+
+    torch.manual_seed(211)                                 # configs/tante.yaml:1
+    model = TANTE(4, TanteMetadata(spatial_resolution=(H, W), n_fields=D), taylor_order=args.taylor_order,
+                  attn_axes=model_axes(args.taylor_order), patch_scale=8, deg=False, dropout=0.0,
+                  precision=args.precision)
+    if args.rt_bias:
+        with torch.no_grad():
+            for ip in model.interprators:
+                ip.interprete[4].bias.add_(args.rt_bias)
+    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev).eval()
+
+    g = torch.Generator().manual_seed(212 + rank)
+    host_in = torch.randn(B, 4, D, H, W, generator=g).pin_memory()
+    host_out = torch.empty(B, n_roll, H, W, D).pin_memory()
+    dev_in = host_in.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    W_, K_ = max(args.warmup, 3), max(args.steps, 1)
+    with torch.inference_mode():
+        for _ in range(W_):
+            y, rts, ns, steps = model.rollout(dev_in, n_roll, per_sample=True, sync=False)
+        barrier()
+        # ---- timed region 1: device-resident inputs (value) ----
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = model.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(K_):
+            y, rts, ns, steps = model.rollout(dev_in, n_roll, per_sample=True, sync=False)
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = model.launch_count() - l0
+        clocks = sampler.stop()
+        model_calls = int(steps.max().item())
+
+        # ---- timed region 2: end to end through the public API with host buffers ----
+        for _ in range(2):
+            d = host_in.to(dev, non_blocking=True)
+            y, *_ = model.rollout(d, n_roll, per_sample=True, sync=False)
+            host_out.copy_(y, non_blocking=True)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(K_):
+            d = host_in.to(dev, non_blocking=True)
+            y, *_ = model.rollout(d, n_roll, per_sample=True, sync=False)
+            host_out.copy_(y, non_blocking=True)
+        e3.record()
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+        # ---- live per-kernel timing of the dominant kernel class (GEMMs) over the same K steps ----
+        model.profile_gemms(True)
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(K_):
+            model.rollout(dev_in, n_roll, per_sample=True, sync=False)
+        e5.record()
+        torch.cuda.synchronize(dev)
+        gemm_ms, gemm_flops, gemm_n = model.profile_read()
+        model.profile_gemms(False)
+        ms_prof = e4.elapsed_time(e5)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_mode = args.precision == "bf16"
+    if tensor_mode:
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    else:
+        peak = 72.0   # 148 SMs x 128 FFMA x 2 x ~1.9 GHz: fp32 FFMA peak; no measured figure exists for it
+        peak_src = "nominal fp32 FFMA 72 TFLOP/s (no measured fp32 peak in MEASURED_PEAKS.json)"
+    achieved = (gemm_flops / (gemm_ms * 1e-3)) / 1e12 if gemm_ms > 0 else None
+    traj = B * world
+    line = {
+        "metric": "rollout_trajectories_per_s", "value": traj * K_ / (ms_total * 1e-3), "unit": "trajectories/s",
+        "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_total / K_, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
+        "config": bench_config(args, B),
+        "model_calls_per_trajectory": model_calls,
+        "frames_per_s": traj * n_roll * K_ / (ms_total * 1e-3),
+        "e2e": {"value": traj * K_ / (ms_e2e * 1e-3), "unit": "trajectories/s",
+                "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                "ms_per_step": ms_e2e / K_},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "kernel": ("gemm_tc_kernel (tcgen05 bf16, all GEMMs of the step)" if tensor_mode
+                       else "gemm_simt_kernel (FFMA fp32, all GEMMs of the step)"),
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / K_, "gemm_share_of_step": gemm_ms / ms_prof,
+            "algorithmic_flops_per_step": gemm_flops / K_,
+            "note": "achieved = sum(2*M*N*K) / sum(CUDA-event time) over every GEMM launch of K steps, events on the launch stream",
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_leg(args, args.cpu_seconds, cpu_sd)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

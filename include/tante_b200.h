@@ -132,6 +132,21 @@ TANTE_API int64_t tante_launch_count(tante_handle_t h);
 TANTE_API int tante_bench_head(tante_handle_t h, int32_t B, int32_t n_frames, int32_t iters, float* ms_out,
                      void* stream);
 
+/* Live per-kernel-class timing for bench.py's roofline: while enabled, every GEMM launch of this handle
+ * is bracketed by CUDA events on the launching stream (un-graphed launches).  tante_profile_read
+ * synchronises, returns the summed GEMM device time, the algorithmic FLOPs (2*M*N*K per launch) and the
+ * launch count since enabling, and clears the counters. */
+TANTE_API int tante_profile(tante_handle_t h, int32_t enable);
+TANTE_API int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+
+/* Test hook: run one GEMM of the library stand-alone, C[M,N] = epi(A[M,K] * W[N,K]^T + bias).
+ * use_tc = 1: tcgen05 bf16 kernel (A, W bf16; C bf16 when out_bf16 else f32);
+ * use_tc = 0: FFMA fp32 kernel (A, W, C f32).  epi: 0 bias, 1 +relu, 2 +gelu(erf), 3 +gelu(tanh),
+ * 4 + resid (f32 [M,N], may alias C).  iters > 1 repeats the launch (timing from the caller's events). */
+TANTE_API int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const void* W, const float* bias,
+                    const float* resid, void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K,
+                    int32_t iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

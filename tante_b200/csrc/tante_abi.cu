@@ -16,6 +16,7 @@
 #include "../../include/tante_b200.h"
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
 
@@ -106,6 +107,12 @@ struct tante_handle_s {
     int64_t launches = 0;
     bool debug = false;
     int last_B = 0;
+    int num_sms = 148;
+    // live GEMM timing (tante_profile)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    double prof_flops = 0;
 };
 
 namespace {
@@ -274,14 +281,43 @@ RolloutState make_state(tante_handle_s* h, int B, int n_roll, float* rts_out, in
     return rs;
 }
 
+inline __nv_bfloat16* AH(tante_handle_s* h, int64_t off) { return reinterpret_cast<__nv_bfloat16*>(h->arena_bf16.p) + off; }
+
+// C = epi(A * W^T): fp32 mode -> FFMA GEMM; bf16 mode -> tcgen05 GEMM (C is fp32 when out_f32, else bf16).
 template <typename TA>
-void gemm(tante_handle_s* h, int epi, const TA* A, int lda, int64_t w_off, TA* Cout, int ldc, int M, int N, int K,
-          const EpiParams& ep, cudaStream_t st);
+void gemm(tante_handle_s* h, int epi, const TA* A, int lda, int64_t w_off, void* Cout, int ldc, bool out_f32, int M, int N,
+          int K, const EpiParams& ep, cudaStream_t st);
+
+struct ProfScope {
+    tante_handle_s* h; cudaStream_t st; bool on;
+    ProfScope(tante_handle_s* h_, cudaStream_t st_, double flops) : h(h_), st(st_), on(h_->prof_on) {
+        if (!on) return;
+        if (h->prof_used + 2 > h->prof_ev.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
+        }
+        CK(cudaEventRecord(h->prof_ev[h->prof_used], st));
+        h->prof_flops += flops;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(h->prof_ev[h->prof_used + 1], st);
+        h->prof_used += 2;
+    }
+};
 
 template <>
-void gemm<float>(tante_handle_s* h, int epi, const float* A, int lda, int64_t w_off, float* Cout, int ldc, int M, int N,
-                 int K, const EpiParams& ep, cudaStream_t st) {
-    CK(launch_gemm_simt(epi, A, lda, AF(h, w_off), K, Cout, ldc, M, N, K, ep, st));
+void gemm<float>(tante_handle_s* h, int epi, const float* A, int lda, int64_t w_off, void* Cout, int ldc, bool, int M,
+                 int N, int K, const EpiParams& ep, cudaStream_t st) {
+    ProfScope ps(h, st, 2.0 * M * N * K);
+    CK(launch_gemm_simt(epi, A, lda, AF(h, w_off), K, reinterpret_cast<float*>(Cout), ldc, M, N, K, ep, st));
+    h->launches++;
+}
+
+template <>
+void gemm<__nv_bfloat16>(tante_handle_s* h, int epi, const __nv_bfloat16* A, int lda, int64_t w_off, void* Cout, int ldc,
+                         bool out_f32, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+    ProfScope ps(h, st, 2.0 * M * N * K);
+    CK(launch_gemm_tc(epi, A, lda, AH(h, w_off), K, Cout, ldc, out_f32 ? 0 : 1, M, N, K, ep, h->num_sms, st));
     h->launches++;
 }
 
@@ -388,14 +424,12 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
-        gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, false, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
         EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
         e3.film = AF(h, h->film_t_off); e3.s_emb = AF(h, h->s_emb); e3.t_emb = AF(h, h->t_emb);
         e3.T = T; e3.L = L; e3.ldr = C;
         // the embed epilogue writes the fp32 residual stream directly
-        CK(launch_gemm_simt(EPI_EMBED, reinterpret_cast<const float*>(a2), g.k2 * g.k2 * C2, AF(h, h->enc_w[2]),
-                            g.k2 * g.k2 * C2, x, C, tokens, C, g.k2 * g.k2 * C2, e3, st));
-        h->launches++;
+        gemm<TA>(h, EPI_EMBED, a2, g.k2 * g.k2 * C2, h->enc_w[2], x, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
     }
     if (h->debug) CK(cudaMemcpyAsync(h->dbg_in.p, x, (size_t)tokens * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
@@ -409,19 +443,15 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         for (const LayerPlan& lp : op.layers) {
             launch_layernorm<TA>(h, x, lp.ln1w, lp.ln1b, ln, tokens, st);
             EpiParams eq; eq.bias = AF(h, lp.inb);
-            gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, tokens, 3 * C, C, eq, st);
+            gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, qkv, att, B, lp.axis, st);
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x; eo.ldr = C;
-            CK(launch_gemm_simt(EPI_BIAS_RESID, reinterpret_cast<const float*>(att), C, AF(h, lp.outw), C, x, C, tokens,
-                                C, C, eo, st));
-            h->launches++;
+            gemm<TA>(h, EPI_BIAS_RESID, att, C, lp.outw, x, C, true, tokens, C, C, eo, st);
             launch_layernorm<TA>(h, x, lp.ln2w, lp.ln2b, ln, tokens, st);
             EpiParams e0; e0.bias = AF(h, lp.m0b);
-            gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, C, tokens, C, C, e0, st);
+            gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, C, false, tokens, C, C, e0, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x; e2.ldr = C;
-            CK(launch_gemm_simt(EPI_BIAS_RESID, reinterpret_cast<const float*>(hid), C, AF(h, lp.m2w), C, x, C, tokens,
-                                C, C, e2, st));
-            h->launches++;
+            gemm<TA>(h, EPI_BIAS_RESID, hid, C, lp.m2w, x, C, true, tokens, C, C, e2, st);
         }
         // --- head of order o (tante.py:147-154) ---
         float* d32 = reinterpret_cast<float*>(h->d32.p);
@@ -436,9 +466,9 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             TA* i1 = reinterpret_cast<TA*>(h->i1.p);
             TA* i2 = reinterpret_cast<TA*>(h->i2.p);
             EpiParams ei; ei.bias = AF(h, op.intb[0]);
-            gemm<TA>(h, EPI_BIAS_RELU, dmod, C, op.intw[0], i1, C / 2, B * L, C / 2, C, ei, st);
+            gemm<TA>(h, EPI_BIAS_RELU, dmod, C, op.intw[0], i1, C / 2, false, B * L, C / 2, C, ei, st);
             ei.bias = AF(h, op.intb[1]);
-            gemm<TA>(h, EPI_BIAS_RELU, i1, C / 2, op.intw[1], i2, C / 4, B * L, C / 4, C / 2, ei, st);
+            gemm<TA>(h, EPI_BIAS_RELU, i1, C / 2, op.intw[1], i2, C / 4, false, B * L, C / 4, C / 2, ei, st);
             rt_reduce_kernel<TA><<<B, 256, 0, st>>>(i2, AF(h, op.intw[2]), AF(h, op.intb[2]), L, C / 4, io.out_T,
                                                     rt + (size_t)o * h->max_batch);
             CK(cudaGetLastError());
@@ -456,9 +486,9 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         TA* z1 = reinterpret_cast<TA*>(h->z1.p);
         TA* z2 = reinterpret_cast<TA*>(h->z2[o].p);
         EpiParams ed; ed.bias = AF(h, op.decb[0]);
-        gemm<TA>(h, EPI_BIAS_GELU_ERF, dmod, C, op.decw[0], z1, g.k2 * g.k2 * C2, B * L, g.k2 * g.k2 * C2, C, ed, st);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, dmod, C, op.decw[0], z1, g.k2 * g.k2 * C2, false, B * L, g.k2 * g.k2 * C2, C, ed, st);
         ed.bias = AF(h, op.decb[1]);
-        gemm<TA>(h, EPI_BIAS_GELU_ERF, z1, C2, op.decw[1], z2, g.k1 * g.k1 * C1, B * L * g.R2, g.k1 * g.k1 * C1, C2, ed, st);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, z1, C2, op.decw[1], z2, g.k1 * g.k1 * C1, false, B * L * g.R2, g.k1 * g.k1 * C1, C2, ed, st);
     }
     // --- step-size selection + fused Taylor head (tante.py:156-171) ---
     select_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(rt, K, h->max_batch, B, h->cfg.deg, h->cfg.output_length,
@@ -490,6 +520,7 @@ void set_smem_attrs() {
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 #define HEADATTR(TA, KO) CK(cudaFuncSetAttribute(taylor_head_kernel<TA, 8, KO>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
     HEADATTR(float, 1); HEADATTR(float, 2); HEADATTR(float, 3); HEADATTR(float, 4);
+    HEADATTR(__nv_bfloat16, 1); HEADATTR(__nv_bfloat16, 2); HEADATTR(__nv_bfloat16, 3); HEADATTR(__nv_bfloat16, 4);
 #undef HEADATTR
     done = true;
 }
@@ -523,6 +554,9 @@ int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out) {
         h->cfg = *cfg;
         h->device = device;
         build_plan(h.get());
+        int sms = 0;   // stays at the B200 default when no device is visible (CPU-side plan checks)
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
+        else (void)cudaGetLastError();
         *out = h.release();
     });
 }
@@ -538,6 +572,7 @@ int tante_destroy(tante_handle_t h) {
         for (auto& b : h->z2) b.free();
         if (h->h_flag) cudaFreeHost(h->h_flag);
         for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+        for (auto& e : h->prof_ev) cudaEventDestroy(e);
         delete h;
     });
 }
@@ -673,7 +708,7 @@ int tante_forward(tante_handle_t h, const float* input, int32_t B, float out_T, 
         io.per_sample = per_sample; io.out_T = out_T;
         RolloutState rs{};
         if (h->cfg.precision == TANTE_PREC_FP32) run_step<float>(h, io, B, rs, st);
-        else throw Error(TANTE_ERR_INVALID, "bf16 tensor path not built yet");
+        else run_step<__nv_bfloat16>(h, io, B, rs, st);
         h->last_B = B;
         if (n_dev) CK(cudaMemcpyAsync(n_dev, h->nbuf.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
         if (n_host) {
@@ -716,7 +751,7 @@ int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_ro
                 if (h->h_flag[slot] == 0) break;
             }
             if (h->cfg.precision == TANTE_PREC_FP32) run_step<float>(h, io, B, rs, st);
-            else throw Error(TANTE_ERR_INVALID, "bf16 tensor path not built yet");
+            else run_step<__nv_bfloat16>(h, io, B, rs, st);
             CK(cudaMemcpyAsync(h->h_flag + slot, rs.remaining, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(h->ev[slot], st));
             pending[slot] = 1;
@@ -752,7 +787,7 @@ int tante_debug_stage(tante_handle_t h, const char* stage, float* dst, int64_t c
             io.input = reinterpret_cast<const float*>(h->ring.p);
             RolloutState rs{};
             if (h->cfg.precision == TANTE_PREC_FP32) launch_head<float>(h, io, B, rs, dst, st);
-            else throw Error(TANTE_ERR_INVALID, "bf16 tensor path not built yet");
+            else launch_head<__nv_bfloat16>(h, io, B, rs, dst, st);
             *numel = n;
             return;
         }
@@ -769,6 +804,56 @@ int tante_bench_head(tante_handle_t h, int32_t B, int32_t n_frames, int32_t iter
     return guarded([&] {
         (void)h; (void)B; (void)n_frames; (void)iters; (void)ms_out; (void)stream;
         throw Error(TANTE_ERR_INVALID, "tante_bench_head: not built yet");
+    });
+}
+
+int tante_profile(tante_handle_t h, int32_t enable) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        h->prof_on = enable != 0;
+        h->prof_used = 0;
+        h->prof_flops = 0;
+    });
+}
+
+int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+    return guarded([&] {
+        REQUIRE(h && gemm_ms && gemm_flops && gemm_launches, "null argument");
+        CK(cudaSetDevice(h->device));
+        double ms = 0;
+        for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+            CK(cudaEventSynchronize(h->prof_ev[i + 1]));
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+            ms += t;
+        }
+        *gemm_ms = ms;
+        *gemm_flops = h->prof_flops;
+        *gemm_launches = (int64_t)(h->prof_used / 2);
+        h->prof_used = 0;
+        h->prof_flops = 0;
+    });
+}
+
+int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const void* W, const float* bias, const float* resid,
+                    void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K, int32_t iters, void* stream) {
+    return guarded([&] {
+        REQUIRE(A && W && bias && C, "null argument");
+        REQUIRE(epi >= EPI_BIAS && epi <= EPI_BIAS_RESID, "unsupported epilogue for the test hook");
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        EpiParams ep;
+        ep.bias = bias; ep.resid = resid; ep.ldr = N;
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        for (int i = 0; i < std::max(1, iters); ++i) {
+            if (use_tc)
+                CK(launch_gemm_tc(epi, reinterpret_cast<const __nv_bfloat16*>(A), K, reinterpret_cast<const __nv_bfloat16*>(W),
+                                  K, C, N, out_bf16, M, N, K, ep, sms, st));
+            else
+                CK(launch_gemm_simt(epi, reinterpret_cast<const float*>(A), K, reinterpret_cast<const float*>(W), K,
+                                    reinterpret_cast<float*>(C), N, M, N, K, ep, st));
+        }
     });
 }
 

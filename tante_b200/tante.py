@@ -188,7 +188,12 @@ class _Engine:
         """(Re)bind + repack when any parameter storage or version changed (optimizer step,
         load_state_dict, .to())."""
         params = dict(model.named_parameters())
-        sig = tuple((n, params[n].data_ptr(), params[n]._version) for n in self.names)
+        def version(p):
+            try:
+                return p._version
+            except RuntimeError:      # inference tensors carry no version counter (immutable outside inference mode)
+                return -1
+        sig = tuple((n, params[n].data_ptr(), version(params[n])) for n in self.names)
         if sig == self.bound_sig:
             return
         for n in self.names:
@@ -378,6 +383,22 @@ class TANTE(nn.Module):
         _abi.check(eng.lib.tante_debug_stage(eng.handle, stage.encode(), out.data_ptr(), out.numel(), ctypes.byref(got),
                                              torch.cuda.current_stream(dev).cuda_stream))
         return out[:got.value]
+
+    def profile_gemms(self, enable: bool):
+        for e in self._engines.values():
+            _abi.check(e.lib.tante_profile(e.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """(gemm_ms, gemm_flops, gemm_launches) accumulated since profile_gemms(True)."""
+        ms = fl = 0.0
+        n = 0
+        for e in self._engines.values():
+            a, b, c = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+            _abi.check(e.lib.tante_profile_read(e.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+            ms += a.value
+            fl += b.value
+            n += c.value
+        return ms, fl, n
 
     def launch_count(self) -> int:
         return sum(int(e.lib.tante_launch_count(e.handle)) for e in self._engines.values())

@@ -1,0 +1,77 @@
+"""Unit parity of the two GEMM kernels (through the C-ABI test hook) against torch fp32 matmul."""
+import pytest
+import torch
+
+from tante_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(epi, A, W, bias, resid):
+    y = A.float() @ W.float().t() + bias
+    if epi == 1:
+        y = torch.relu(y)
+    elif epi == 2:
+        y = torch.nn.functional.gelu(y)
+    elif epi == 3:
+        y = torch.nn.functional.gelu(y, approximate="tanh")
+    elif epi == 4:
+        y = resid + y
+    return y
+
+
+def _run(use_tc, epi, A, W, bias, resid, out_bf16):
+    lib = _abi.load()
+    M, K = A.shape
+    N = W.shape[0]
+    if epi == 4:
+        C = resid.clone()           # in-place residual, as the residual stream uses it
+        r = C
+    else:
+        C = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        r = None
+    _abi.check(lib.tante_test_gemm(use_tc, epi, A.data_ptr(), W.data_ptr(), bias.data_ptr(),
+                                   None if r is None else r.data_ptr(), C.data_ptr(), int(out_bf16), M, N, K, 1,
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return C
+
+
+SHAPES = [(128, 256, 256), (4096, 768, 256), (1000, 256, 256), (333, 128, 256), (5000, 64, 128), (777, 256, 512),
+          (2048, 512, 256), (260, 128, 64), (40000, 768, 256), (3072, 256, 128)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("epi", [0, 2, 4])
+def test_tcgen05_gemm_matches_torch(M, N, K, epi):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K + epi)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    ref = _ref(epi, A, W, bias, resid)
+    out = _run(1, epi, A, W, bias, resid, out_bf16=False)
+    err = float((out - ref).norm() / ref.norm())
+    assert err < 2e-6, err                     # same bf16 inputs, fp32 accumulate: order-of-summation only
+    assert float((out - ref).abs().max()) < 1e-4
+    if epi != 4:
+        outb = _run(1, epi, A, W, bias, resid, out_bf16=True)
+        errb = float((outb.float() - ref).norm() / ref.norm())
+        assert errb < 4e-3, errb               # one bf16 rounding of the output
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1000, 768, 256), (333, 64, 128), (777, 256, 512)])
+@pytest.mark.parametrize("epi", [0, 1, 3, 4])
+def test_ffma_gemm_matches_torch(M, N, K, epi):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + epi)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = _ref(epi, A.double(), W.double(), bias.double(), resid.double())
+    ref = (A.double() @ W.double().t() + bias.double())
+    ref = {0: ref, 1: torch.relu(ref), 3: torch.nn.functional.gelu(ref, approximate="tanh"), 4: resid.double() + ref}[epi]
+    out = _run(0, epi, A, W, bias, resid, out_bf16=False)
+    err = float((out.double() - ref).norm() / ref.norm())
+    assert err < 1e-6, err

@@ -4,13 +4,15 @@
 //   * every GEMM of the TANTE block has a short reduction (K = 64..512) and a huge M (tokens), so the
 //     K-major weight slice W[n0:n0+BN, :] (<= 128 KB) is TMA-loaded into shared memory ONCE per CTA and
 //     stays resident while the CTA walks over its M tiles; only activations stream (16 KB k-blocks
-//     through a 4-6 stage mbarrier ring) -> ~256 FLOP per byte of L2/HBM traffic at BN = 256;
+//     through an mbarrier ring) -> ~256 FLOP per byte of L2/HBM traffic at BN = 256;
 //   * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) with both operands in SWIZZLE_128B
 //     shared memory; the fp32 accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of
 //     tile i overlaps the MMAs of tile i+1;
-//   * 4 epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns), transpose through a private,
-//     conflict-free shared-memory patch and apply bias / activation / residual / FiLM+embeddings with
-//     fully coalesced 128-byte global accesses.
+//   * 4 epilogue warps (one per TMEM lane quarter): tcgen05.ld -> registers (thread = row) -> bias /
+//     activation -> swizzled shared-memory staging -> TMA bulk STORE (cp.async.bulk.tensor, OOB rows
+//     clipped by the tensor map).  The fp32 residual-stream variants (x += ...) TMA-LOAD the residual
+//     chunk into the same staging buffer one chunk ahead, add in place and TMA-store it back, so the
+//     epilogue issues no per-element global memory instructions at all.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
 #pragma once
 #include "common.cuh"
@@ -22,45 +24,47 @@ constexpr int kTcBlockM = 128;
 constexpr int kTcBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
 constexpr int kTcStageBytes = kTcBlockM * 128;      // 16 KB
 constexpr int kTcMaxStages = 8;
-constexpr int kTcEpiBytes = 4 * 32 * 33 * 4;        // per-warp 32x33 fp32 transpose patches
+constexpr int kTcEpiBuf = 32 * 128;                 // one staging buffer: 32 rows x 128 B (SWIZZLE_128B)
+constexpr int kTcEpiBytes = 4 * 2 * kTcEpiBuf;      // 4 warps x 2 buffers
 constexpr int kTcThreads = 192;
 
-__device__ __forceinline__ float epi_apply_rt(int epi, float acc, int m, int n, const EpiParams& p) {
-    float v = acc + p.bias[n];
-    switch (epi) {
-        case EPI_BIAS_RELU: v = fmaxf(v, 0.0f); break;
-        case EPI_BIAS_GELU_ERF: v = gelu_erf(v); break;
-        case EPI_BIAS_GELU_TANH: v = gelu_tanh(v); break;
-        case EPI_BIAS_RESID: v = p.resid[(size_t)m * p.ldr + n] + v; break;
-        case EPI_EMBED: {
-            const int hw = m % p.L;
-            const int t = (m / p.L) % p.T;
-            v = v + (v * p.film[(size_t)(t * 2 + 0) * p.ldr + n] + p.film[(size_t)(t * 2 + 1) * p.ldr + n]);
-            v = v + p.s_emb[(size_t)hw * p.ldr + n];
-            v = v + p.t_emb[(size_t)t * p.ldr + n];
-            break;
-        }
-        default: break;
-    }
-    return v;
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    const float k = 0.79788456080286535588f;
+    const float u = k * fmaf(0.044715f * x, x * x, x);
+    return 0.5f * x * (1.0f + ptx::tanh_approx(u));
 }
+
+__device__ __forceinline__ float act_rt(int epi, float v) {
+    switch (epi) {
+        case EPI_BIAS_RELU: return fmaxf(v, 0.0f);
+        case EPI_BIAS_GELU_ERF: return gelu_erf(v);
+        case EPI_BIAS_GELU_TANH: return gelu_tanh_fast(v);
+        default: return v;
+    }
+}
+
+// byte offset of 16-byte chunk `c` of row `r` inside a SWIZZLE_128B staging buffer (1024-B aligned)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, void* __restrict__ C,
-               int ldc, int M, int N, int nkb, int nstage, int epi, int out_bf16, EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int nkb,
+               int nstage, int epi, int out_bf16, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;                                   // [nkb][BN rows][128 B]
     uint8_t* sA = sW + (size_t)nkb * BN * 128;            // [nstage][128 rows][128 B]
-    float* sEpi = reinterpret_cast<float*>(sA + (size_t)nstage * kTcStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sEpi) + kTcEpiBytes);
+    uint8_t* sEpi = sA + (size_t)nstage * kTcStageBytes;  // [4 warps][2][4 KB]
+    float* sBias = reinterpret_cast<float*>(sEpi + kTcEpiBytes);   // [BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
     uint64_t* full = bars;                    // [kTcMaxStages]
     uint64_t* empty = bars + kTcMaxStages;    // [kTcMaxStages]
     uint64_t* w_full = bars + 2 * kTcMaxStages;
     uint64_t* tmem_full = w_full + 1;         // [2]
     uint64_t* tmem_empty = tmem_full + 2;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* rbar = tmem_empty + 2;          // [4 warps][2] residual-chunk barriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int n_slices = N / BN;
@@ -70,12 +74,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m_tiles = (M + kTcBlockM - 1) / kTcBlockM;
     const int n0 = slice * BN;
 
+    for (int i = threadIdx.x; i < BN; i += kTcThreads) sBias[i] = ep.bias[n0 + i];
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmW);
+        ptx::prefetch_tmap(&tmC);
+        if (epi == EPI_BIAS_RESID) ptx::prefetch_tmap(&tmR);
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 8; ++i) ptx::mbar_init(&rbar[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -132,38 +140,126 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4 =====
+        // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4, thread = one output row =====
         const int q = warp & 3;
-        float* patch = sEpi + q * 32 * 33;
+        uint8_t* ebuf = sEpi + q * 2 * kTcEpiBuf;
+        uint64_t* rb = rbar + q * 2;
+        uint32_t rphase[2] = {0, 0};
+        int nbuf = 0;        // staging buffer the next chunk uses (alternates every chunk, across tiles)
         int t = 0;
         for (int mt = rank; mt < m_tiles; mt += per_slice, ++t) {
             const int acc = t & 1;
-            ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
-            ptx::tc_fence_after();
             const int row0 = mt * kTcBlockM + q * 32;
+            const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            if (out_bf16) {
+                ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
+                ptx::tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
-                ptx::tc_wait_ld();
+                for (int ch = 0; ch < BN / 64; ++ch) {
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64), r0);
+                    ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64 + 32), r1);
+                    if (lane == 0) ptx::bulk_wait_read<1>();      // the store that last used this buffer has drained
+                    __syncwarp();
+                    ptx::tc_wait_ld();
+                    uint8_t* buf = ebuf + nbuf * kTcEpiBuf;
+                    const float* bsm = sBias + ch * 64;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) patch[lane * 33 + c] = __uint_as_float(r[c]);
-                __syncwarp();
-                const int n = n0 + ch * 32 + lane;
-#pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int m = row0 + rr;
-                    if (m < M) {
-                        const float v = epi_apply_rt(epi, patch[rr * 33 + lane], m, n, ep);
-                        if (out_bf16) reinterpret_cast<__nv_bfloat16*>(C)[(size_t)m * ldc + n] = __float2bfloat16_rn(v);
-                        else reinterpret_cast<float*>(C)[(size_t)m * ldc + n] = v;
+                    for (int c = 0; c < 8; ++c) {                 // 8 x 16 B chunks = 64 bf16 columns
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = c * 8 + j * 2;
+                            const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bsm[col];
+                            const float b = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + bsm[col + 1];
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(act_rt(epi, a), act_rt(epi, b));
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        *reinterpret_cast<uint4*>(buf + sw128_off(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmC, buf, n0 + ch * 64, row0);
+                        ptx::bulk_commit();
+                    }
+                    nbuf ^= 1;
                 }
-                __syncwarp();
+            } else {
+                // fp32 output in 32-column chunks; EPI_BIAS_RESID prefetches the residual chunk by TMA
+                const bool has_res = epi == EPI_BIAS_RESID;
+                if (has_res && lane == 0) {
+                    ptx::bulk_wait_read<0>();
+                    ptx::mbar_arrive_expect_tx(&rb[nbuf], kTcEpiBuf);
+                    ptx::tma_load_2d(ebuf + nbuf * kTcEpiBuf, &tmR, &rb[nbuf], n0, row0);
+                }
+                ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
+                ptx::tc_fence_after();
+                const int m = row0 + lane;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t r0[32];
+                    ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 32), r0);
+                    uint8_t* buf = ebuf + nbuf * kTcEpiBuf;
+                    if (lane == 0) {
+                        // buffer nbuf^1 was last read by the store of the previous chunk: drain, then prefetch into it
+                        if (has_res) {
+                            ptx::bulk_wait_read<0>();
+                            if (ch + 1 < BN / 32) {
+                                ptx::mbar_arrive_expect_tx(&rb[nbuf ^ 1], kTcEpiBuf);
+                                ptx::tma_load_2d(ebuf + (nbuf ^ 1) * kTcEpiBuf, &tmR, &rb[nbuf ^ 1], n0 + (ch + 1) * 32, row0);
+                            }
+                        } else {
+                            ptx::bulk_wait_read<1>();
+                        }
+                    }
+                    __syncwarp();
+                    if (has_res) { ptx::mbar_wait(&rb[nbuf], rphase[nbuf]); rphase[nbuf] ^= 1; }
+                    ptx::tc_wait_ld();
+                    const float* bsm = sBias + ch * 32;
+                    const int ncol = n0 + ch * 32;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {                 // 8 x 16 B chunks = 32 fp32 columns
+                        float4* p = reinterpret_cast<float4*>(buf + sw128_off(lane, c));
+                        float4 o;
+                        o.x = __uint_as_float(r0[c * 4 + 0]) + bsm[c * 4 + 0];
+                        o.y = __uint_as_float(r0[c * 4 + 1]) + bsm[c * 4 + 1];
+                        o.z = __uint_as_float(r0[c * 4 + 2]) + bsm[c * 4 + 2];
+                        o.w = __uint_as_float(r0[c * 4 + 3]) + bsm[c * 4 + 3];
+                        if (has_res) {
+                            const float4 x = *p;
+                            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                        } else if (epi == EPI_EMBED) {
+                            if (m < M) {
+                                const int hw = m % ep.L, tt = (m / ep.L) % ep.T;
+                                const int n = ncol + c * 4;
+                                const float4 sc = *reinterpret_cast<const float4*>(ep.film + (size_t)(tt * 2 + 0) * ep.ldr + n);
+                                const float4 sh = *reinterpret_cast<const float4*>(ep.film + (size_t)(tt * 2 + 1) * ep.ldr + n);
+                                const float4 se = *reinterpret_cast<const float4*>(ep.s_emb + (size_t)hw * ep.ldr + n);
+                                const float4 te = *reinterpret_cast<const float4*>(ep.t_emb + (size_t)tt * ep.ldr + n);
+                                o.x = o.x + (o.x * sc.x + sh.x) + se.x + te.x;
+                                o.y = o.y + (o.y * sc.y + sh.y) + se.y + te.y;
+                                o.z = o.z + (o.z * sc.z + sh.z) + se.z + te.z;
+                                o.w = o.w + (o.w * sc.w + sh.w) + se.w + te.w;
+                            }
+                        } else {
+                            o.x = act_rt(epi, o.x); o.y = act_rt(epi, o.y); o.z = act_rt(epi, o.z); o.w = act_rt(epi, o.w);
+                        }
+                        *p = o;
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmC, buf, ncol, row0);
+                        ptx::bulk_commit();
+                    }
+                    nbuf ^= 1;
+                }
             }
             ptx::tc_fence_before();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) ptx::bulk_wait_all<0>();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -188,16 +284,17 @@ static PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// 2-D bf16 K-major tensor map: dims {K, rows}, box {64, box_rows}, 128-byte swizzle, zero OOB fill.
-static bool make_tmap_bf16(CUtensorMap* m, const void* base, int rows, int K, int ld_elems, int box_rows) {
+// 2-D row-major tensor map with a 128-byte-wide box (SWIZZLE_128B): dims {cols, rows}.
+static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int rows, int cols,
+                         int ld_elems, int box_cols, int box_rows) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_elems * esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    return enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -208,7 +305,7 @@ static bool tc_plan(int M, int N, int K, int num_sms, TcPlan* p) {
     const int nkb = K / kTcBlockK;
     int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
     while ((size_t)nkb * BN * 128 > 128 * 1024 && BN > 64) BN /= 2;   // keep the resident slice <= 128 KB
-    const size_t fixed = (size_t)nkb * BN * 128 + kTcEpiBytes + 256 + 1024;
+    const size_t fixed = (size_t)nkb * BN * 128 + kTcEpiBytes + BN * 4 + 512 + 1024;
     const size_t budget = 227 * 1024;
     int nstage = (int)((budget - fixed) / kTcStageBytes);
     nstage = nstage > 6 ? 6 : nstage;
@@ -229,9 +326,20 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
     if (M <= 0) return cudaSuccess;
     TcPlan p;
     if (!tc_plan(M, N, K, num_sms, &p)) return cudaErrorInvalidValue;
-    CUtensorMap tmA, tmW;
-    if (!make_tmap_bf16(&tmA, A, M, K, lda, kTcBlockM)) return cudaErrorInvalidValue;
-    if (!make_tmap_bf16(&tmW, W, N, K, ldw, p.BN)) return cudaErrorInvalidValue;
+    if (!out_bf16 && N % 32 != 0) return cudaErrorInvalidValue;
+    CUtensorMap tmA, tmW, tmC, tmR;
+    if (!make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kTcBlockK, kTcBlockM)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kTcBlockK, p.BN)) return cudaErrorInvalidValue;
+    if (out_bf16) {
+        if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, M, N, ldc, 64, 32)) return cudaErrorInvalidValue;
+    } else {
+        if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ldc, 32, 32)) return cudaErrorInvalidValue;
+    }
+    tmR = tmC;
+    if (epi == EPI_BIAS_RESID) {
+        if (out_bf16) return cudaErrorInvalidValue;
+        if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.resid, M, N, ep.ldr, 32, 32)) return cudaErrorInvalidValue;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e;
@@ -241,9 +349,9 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
         attr_done = true;
     }
     switch (p.BN) {
-        case 256: gemm_tc_kernel<256><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, C, ldc, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
-        case 128: gemm_tc_kernel<128><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, C, ldc, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
-        default: gemm_tc_kernel<64><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, C, ldc, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
+        case 256: gemm_tc_kernel<256><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
+        case 128: gemm_tc_kernel<128><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
+        default: gemm_tc_kernel<64><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
     }
     return cudaGetLastError();
 }

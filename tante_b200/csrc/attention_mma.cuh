@@ -1,0 +1,204 @@
+// Axial multi-head attention on short sequences (S <= 64, head_dim 32) for the bf16 tensor mode.
+//
+// Sequences are addressed in place in the (B,T,Hp,Wp) token order (no rearrange copies, reference
+// attn_backbone.py:149-162): token(gid, p) = outer*S*inner_sz + p*inner_sz + inner with
+// outer = gid / inner_sz, inner = gid % inner_sz  (T: inner_sz = L, causal; H: inner_sz = Wp; W: inner_sz = 1).
+//
+// One CTA (4 warps) = one block of R_pad rows x 4 heads (one warp per head).  Short sequences are
+// packed: G = 16 / S sequences share a 16-row block and attention is masked to stay inside a sequence
+// (block-diagonal), so the causal T axis (S = 4) runs on the same tensor-core path as H and W.
+// Q/K/V head slices are staged once in XOR-swizzled shared memory with coalesced 16-byte loads;
+// QK^T and PV run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate; the tiles are far too small for
+// tcgen05), the softmax lives in registers (whole score row fits: S <= 64), O is written back
+// through shared memory with coalesced 16-byte stores.  HBM traffic = read qkv once + write out once.
+#pragma once
+#include "common.cuh"
+
+namespace tante {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// tile row = 64 B (32 bf16) = four 16-byte chunks, chunk index XOR-swizzled by (row >> 1) & 3
+__device__ __forceinline__ uint32_t att_off(int r, int chunk) { return (uint32_t)(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); }
+
+template <int NKB /* R_pad / 8 */>
+__global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                  __nv_bfloat16* __restrict__ out, int n_groups, int S,
+                                                                  int inner_sz, int C, int causal, int G,
+                                                                  float scale_log2e) {
+    constexpr int R = NKB * 8;
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    __shared__ long long s_tok[R];
+    // tiles: [mat q,k,v][head 0..3][R rows][64 B]
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int blk = blockIdx.x, hq = blockIdx.y;
+    const int Gv = min(G, n_groups - blk * G);           // sequences actually present in this block
+    const int rows_valid = Gv * S;
+
+    if (tid < R) {
+        long long tok = -1;
+        if (tid < rows_valid) {
+            const int i = tid / S, p = tid % S;
+            const long long gid = (long long)blk * G + i;
+            const long long outer = gid / inner_sz, inner = gid % inner_sz;
+            tok = outer * S * inner_sz + (long long)p * inner_sz + inner;
+        }
+        s_tok[tid] = tok;
+    }
+    __syncthreads();
+    // ---- stage Q/K/V slices of 4 heads: per row 3 x 256 contiguous bytes ----
+    for (int idx = tid; idx < R * 48; idx += 128) {
+        const int r = idx / 48, c = idx % 48;
+        const int mat = c / 16, hh = (c % 16) / 4, part = c % 4;
+        const long long tok = s_tok[r];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tok >= 0)
+            v = *reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + (size_t)mat * C + (hq * 4 + hh) * 32 + part * 8);
+        *reinterpret_cast<uint4*>(att_smem + (size_t)((mat * 4 + hh) * R) * 64 + att_off(r, part)) = v;
+    }
+    __syncthreads();
+
+    const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(att_smem + (size_t)((0 * 4 + warp) * R) * 64);
+    const uint32_t sK = (uint32_t)__cvta_generic_to_shared(att_smem + (size_t)((1 * 4 + warp) * R) * 64);
+    const uint32_t sV = (uint32_t)__cvta_generic_to_shared(att_smem + (size_t)((2 * 4 + warp) * R) * 64);
+    uint8_t* gQ = att_smem + (size_t)((0 * 4 + warp) * R) * 64;
+    const int g = lane >> 2, t = lane & 3;
+    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);   // ldmatrix row supplied by this lane (A / V pattern)
+    const int lchk = lane >> 4;                            // 0/1: which 16-byte chunk of the pair
+
+#pragma unroll 1
+    for (int qb = 0; qb < R / 16; ++qb) {
+        if (qb * 16 >= rows_valid) break;
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            ldsm_x4(sQ + att_off(qb * 16 + lrow, ks * 2 + lchk), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+        float s[NKB][4];
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+            s[kb][0] = s[kb][1] = s[kb][2] = s[kb][3] = 0.f;
+            uint32_t k0, k1, k2, k3;
+            ldsm_x4(sK + att_off(kb * 8 + (lane & 7), lane >> 3), k0, k1, k2, k3);
+            mma_bf16_16816(s[kb], qa[0], k0, k1);
+            mma_bf16_16816(s[kb], qa[1], k2, k3);
+        }
+        // ---- mask + softmax over the key axis (rows g and g+8 of this 16-row block) ----
+        const int r0 = qb * 16 + g, r1 = r0 + 8;
+        const int g0 = r0 / S, p0 = r0 % S, g1 = r1 / S, p1 = r1 % S;
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int key = kb * 8 + 2 * t + j;
+                const int kg = key / S, kp = key % S;
+                const bool kv = key < rows_valid;
+                const bool ok0 = kv && kg == g0 && (!causal || kp <= p0);
+                const bool ok1 = kv && kg == g1 && (!causal || kp <= p1);
+                s[kb][j] = ok0 ? s[kb][j] : -INFINITY;
+                s[kb][2 + j] = ok1 ? s[kb][2 + j] : -INFINITY;
+                m0 = fmaxf(m0, s[kb][j]);
+                m1 = fmaxf(m1, s[kb][2 + j]);
+            }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        if (m0 == -INFINITY) m0 = 0.f;      // fully masked (padding) row
+        if (m1 == -INFINITY) m1 = 0.f;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                s[kb][j] = exp2f((s[kb][j] - m0) * scale_log2e);
+                s[kb][2 + j] = exp2f((s[kb][2 + j] - m1) * scale_log2e);
+                l0 += s[kb][j];
+                l1 += s[kb][2 + j];
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // ---- O = P V ----
+        float o[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NKB / 2; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t v0, v1, v2, v3;
+                ldsm_x4_t(sV + att_off(kk * 16 + lrow, 2 * j + lchk), v0, v1, v2, v3);
+                mma_bf16_16816(o[2 * j], pa, v0, v1);
+                mma_bf16_16816(o[2 * j + 1], pa, v2, v3);
+            }
+        }
+        const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+        __syncwarp();   // all lanes finished reading this q-block's Q rows before they are overwritten with O
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            *reinterpret_cast<uint32_t*>(gQ + att_off(r0, nb) + t * 4) = pack_bf16x2(o[nb][0] * i0, o[nb][1] * i0);
+            *reinterpret_cast<uint32_t*>(gQ + att_off(r1, nb) + t * 4) = pack_bf16x2(o[nb][2] * i1, o[nb][3] * i1);
+        }
+    }
+    __syncthreads();
+    // ---- coalesced write-back: per row 4 heads x 64 B = 256 contiguous bytes ----
+    for (int idx = tid; idx < R * 16; idx += 128) {
+        const int r = idx / 16, c = idx % 16;
+        const int hh = c / 4, part = c % 4;
+        const long long tok = s_tok[r];
+        if (tok < 0) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(att_smem + (size_t)((0 * 4 + hh) * R) * 64 + att_off(r, part));
+        *reinterpret_cast<uint4*>(out + (size_t)tok * C + (hq * 4 + hh) * 32 + part * 8) = v;
+    }
+}
+
+// Host launcher.  Returns false when the configuration is outside this kernel (caller falls back).
+static bool launch_attention_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, long long n_groups, int S, int inner_sz,
+                                 int n_head, int C, int head_dim, int causal, cudaStream_t st, cudaError_t* err) {
+    if (head_dim != 32 || n_head % 4 != 0 || S > 64 || S < 1) return false;
+    const int G = S <= 16 ? 16 / S : 1;
+    const int R = S <= 16 ? 16 : ((S + 15) / 16) * 16;
+    const long long blocks = (n_groups + G - 1) / G;
+    if (blocks > 0x7fffffffLL) return false;
+    dim3 grid((unsigned)blocks, (unsigned)(n_head / 4));
+    const size_t smem = (size_t)3 * 4 * R * 64;
+    const float sl2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(axial_attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(axial_attention_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr = true;
+    }
+    switch (R) {
+        case 16: axial_attention_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
+        case 32: axial_attention_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
+        case 48: axial_attention_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
+        default: axial_attention_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
+    }
+    *err = cudaGetLastError();
+    return true;
+}
+
+}  // namespace tante

@@ -41,18 +41,20 @@ __device__ __forceinline__ void stage1_row_to_hw(const PatchGeom& g, int hp, int
 // lives in slot (fcount[b] + t) % T (rollout window, see rollout.cuh).
 // ------------------------------------------------------------------------------------------------
 template <typename TOut>
-__global__ void __launch_bounds__(256) patch_embed_conv1_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(128) patch_embed_conv1_kernel(const float* __restrict__ x,
                                                                 const int* __restrict__ fcount, PatchGeom g,
                                                                 const float* __restrict__ w1p,  // [C1][k0*k0*D]
-                                                                const float* __restrict__ b1, int C1, int WC,
+                                                                const float* __restrict__ b1, int WC,
                                                                 TOut* __restrict__ out) {
+    constexpr int C1 = 64;
     extern __shared__ __align__(16) float smem[];
     const int P = g.k0 * g.k1 * g.k2;
     const int K1 = g.k0 * g.k0 * g.D;
-    const int slabW = P * WC;
+    const int slabW = P * WC + 1;               // +1: rows of the slab start in different banks
     float* s_in = smem;                         // [D][P][slabW]
-    float* s_w = s_in + g.D * P * slabW;        // [C1][K1+1]
-    float* s_b = s_w + C1 * (K1 + 1);           // [C1]
+    float* s_w = s_in + ((g.D * P * slabW + 3) & ~3);   // [K1][C1]  (transposed: one 256-B row per input tap)
+    float* s_b = s_w + K1 * C1;                 // [C1]
+    TOut* s_out = reinterpret_cast<TOut*>(s_b + C1);    // [rows][C1] staged for a coalesced write-back
 
     const int bt = blockIdx.x / g.Hp, hp = blockIdx.x % g.Hp;
     const int wp0 = blockIdx.y * WC;
@@ -61,9 +63,8 @@ __global__ void __launch_bounds__(256) patch_embed_conv1_kernel(const float* __r
     const int slot = fcount ? (fcount[b] + t) % g.T : t;
     const float* xin = x + ((size_t)(b * g.T + slot) * g.D) * g.H * g.W;
 
-    for (int i = threadIdx.x; i < C1 * K1; i += blockDim.x) s_w[(i / K1) * (K1 + 1) + (i % K1)] = w1p[i];
+    for (int i = threadIdx.x; i < C1 * K1; i += blockDim.x) s_w[(i % K1) * C1 + (i / K1)] = w1p[i];
     for (int i = threadIdx.x; i < C1; i += blockDim.x) s_b[i] = b1[i];
-    // slab load, float4 along w (W and P*wp0 are multiples of 4 when P >= 4; fall back to scalars otherwise)
     const int validW = P * nwp;
     if ((validW & 3) == 0 && (g.W & 3) == 0 && ((P * wp0) & 3) == 0) {
         const int vec = validW / 4;
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(256) patch_embed_conv1_kernel(const float* __r
             const int v = i % vec, row = (i / vec) % P, d = i / (vec * P);
             const float4 val = *reinterpret_cast<const float4*>(
                 xin + ((size_t)d * g.H + hp * P + row) * g.W + wp0 * P + v * 4);
-            *reinterpret_cast<float4*>(s_in + (d * P + row) * slabW + v * 4) = val;
+            float* dst = s_in + (d * P + row) * slabW + v * 4;
+            dst[0] = val.x; dst[1] = val.y; dst[2] = val.z; dst[3] = val.w;
         }
     } else {
         for (int i = threadIdx.x; i < g.D * P * validW; i += blockDim.x) {
@@ -81,32 +83,50 @@ __global__ void __launch_bounds__(256) patch_embed_conv1_kernel(const float* __r
     }
     __syncthreads();
 
-    const int CG = C1 / 16;               // channel groups of 16
-    const int rows = nwp * g.R1;          // stage-1 pixels in this CTA
-    for (int item = threadIdx.x; item < rows * CG; item += blockDim.x) {
-        const int cg = item % CG, rr = item / CG;
+    const int rows = nwp * g.R1;          // stage-1 pixels in this CTA (consecutive rows of `out`)
+    for (int rr = threadIdx.x; rr < rows; rr += blockDim.x) {
         const int wpl = rr / g.R1, r = rr % g.R1;
         int h1, w1;
         stage1_row_to_hw(g, 0, wpl, r, h1, w1);   // local coordinates inside the slab (hp -> 0)
-        float acc[16];
+        float acc[C1];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = s_b[cg * 16 + j];
+        for (int j = 0; j < C1; ++j) acc[j] = s_b[j];
         int kk = 0;
         for (int c = 0; c < g.k0; ++c)
             for (int cp = 0; cp < g.k0; ++cp)
                 for (int d = 0; d < g.D; ++d, ++kk) {
                     const float v = s_in[(d * P + h1 * g.k0 + c) * slabW + w1 * g.k0 + cp];
+                    const float4* wr = reinterpret_cast<const float4*>(s_w + kk * C1);   // warp-broadcast reads
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, s_w[(cg * 16 + j) * (K1 + 1) + kk], acc[j]);
+                    for (int j4 = 0; j4 < C1 / 4; ++j4) {
+                        const float4 w4 = wr[j4];
+                        acc[j4 * 4 + 0] = fmaf(v, w4.x, acc[j4 * 4 + 0]);
+                        acc[j4 * 4 + 1] = fmaf(v, w4.y, acc[j4 * 4 + 1]);
+                        acc[j4 * 4 + 2] = fmaf(v, w4.z, acc[j4 * 4 + 2]);
+                        acc[j4 * 4 + 3] = fmaf(v, w4.w, acc[j4 * 4 + 3]);
+                    }
                 }
-        const size_t row_g = ((size_t)(bt * g.Hp + hp) * g.Wp + wp0 + wpl) * g.R1 + r;
-        TOut* o = out + row_g * C1 + cg * 16;
+        // stage with a 16-byte-chunk rotation per row so that neither this store nor the copy below conflicts
+        constexpr int CH = (int)(16 / sizeof(TOut));       // elements per 16-byte chunk
+        constexpr int NCH = C1 / CH;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
+        for (int c4 = 0; c4 < C1 / 4; ++c4) {
             float v4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v4[j] = gelu_erf(acc[j4 * 4 + j]);
-            Vec4<TOut>::store(o + j4 * 4, v4);
+            for (int j = 0; j < 4; ++j) v4[j] = gelu_erf(acc[c4 * 4 + j]);
+            const int chunk = (c4 * 4) / CH, within = (c4 * 4) % CH;
+            Vec4<TOut>::store(s_out + (size_t)rr * C1 + ((chunk + rr) % NCH) * CH + within, v4);
+        }
+    }
+    __syncthreads();
+    {
+        constexpr int CH = (int)(16 / sizeof(TOut));
+        constexpr int NCH = C1 / CH;
+        const size_t row_g0 = ((size_t)(bt * g.Hp + hp) * g.Wp + wp0) * g.R1;
+        uint4* dst = reinterpret_cast<uint4*>(out + row_g0 * C1);
+        for (int i = threadIdx.x; i < rows * NCH; i += blockDim.x) {
+            const int rr = i / NCH, chunk = i % NCH;
+            dst[i] = *reinterpret_cast<const uint4*>(s_out + (size_t)rr * C1 + ((chunk + rr) % NCH) * CH);
         }
     }
 }
@@ -245,32 +265,70 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const TIn* __restr
 __global__ void __launch_bounds__(256) propagator_kernel(float* __restrict__ x, int S, long long IC,
                                                          const float* __restrict__ W1, const float* __restrict__ b1,
                                                          const float* __restrict__ W2, const float* __restrict__ b2) {
+    // Register-tiled: each thread owns a 4 (axis positions) x 4 (columns) output tile; per reduction step it
+    // reads one float4 of transposed weights (warp-broadcast) and one float4 of the slab -> 16 FMAs / 2 LDS.128.
     extern __shared__ __align__(16) float smem[];
-    float* sv = smem;              // [S][64]
-    float* sh = sv + S * 64;       // [S][64]
-    float* sw1 = sh + S * 64;      // [S][S]
-    float* sw2 = sw1 + S * S;      // [S][S]
-    float* sb1 = sw2 + S * S;
-    float* sb2 = sb1 + S;
-    const long long col0 = (long long)blockIdx.y * 64;
+    const int S4 = (S + 3) & ~3;
+    float* sv = smem;                // [S4][128]
+    float* sh = sv + S4 * 128;       // [S4][128]
+    float* sw1 = sh + S4 * 128;      // [S4][S4]  transposed: sw1[i][j] = W1[j][i]
+    float* sw2 = sw1 + S4 * S4;      // [S4][S4]  transposed
+    float* sb1 = sw2 + S4 * S4;      // [S4]
+    float* sb2 = sb1 + S4;
+    const long long col0 = (long long)blockIdx.y * 128;
     const long long outer = blockIdx.x;
     float* base = x + (size_t)outer * S * IC + col0;
-    const int col = threadIdx.x % 64, rg = threadIdx.x / 64;  // 4 row groups
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) { sw1[i] = W1[i]; sw2[i] = W2[i]; }
-    for (int i = threadIdx.x; i < S; i += blockDim.x) { sb1[i] = b1[i]; sb2[i] = b2[i]; }
-    const bool colok = col0 + col < IC;
-    for (int p = rg; p < S; p += 4) sv[p * 64 + col] = colok ? base[(size_t)p * IC + col] : 0.f;
-    __syncthreads();
-    for (int j = rg; j < S; j += 4) {
-        float a = sb1[j];
-        for (int i = 0; i < S; ++i) a = fmaf(sw1[j * S + i], sv[i * 64 + col], a);
-        sh[j * 64 + col] = gelu_erf(a);
+    for (int i = threadIdx.x; i < S4 * S4; i += blockDim.x) {
+        const int ii = i / S4, jj = i % S4;            // sw[ii][jj] = W[jj][ii]
+        const bool ok = ii < S && jj < S;
+        sw1[i] = ok ? W1[jj * S + ii] : 0.f;
+        sw2[i] = ok ? W2[jj * S + ii] : 0.f;
+    }
+    for (int i = threadIdx.x; i < S4; i += blockDim.x) { sb1[i] = i < S ? b1[i] : 0.f; sb2[i] = i < S ? b2[i] : 0.f; }
+    const int ncol = (int)min((long long)128, IC - col0);      // IC is a multiple of 4
+    for (int i = threadIdx.x; i < S4 * 32; i += blockDim.x) {
+        const int p = i / 32, c4 = (i % 32) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < S && c4 < ncol) v = *reinterpret_cast<const float4*>(base + (size_t)p * IC + c4);
+        *reinterpret_cast<float4*>(sv + p * 128 + c4) = v;
     }
     __syncthreads();
-    for (int i = rg; i < S; i += 4) {
-        float a = sb2[i];
-        for (int j = 0; j < S; ++j) a = fmaf(sw2[i * S + j], sh[j * 64 + col], a);
-        if (colok) base[(size_t)i * IC + col] = sv[i * 64 + col] + a;
+    const int cg = threadIdx.x % 32, rg = threadIdx.x / 32, nrg = blockDim.x / 32;
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* src = pass == 0 ? sv : sh;
+        const float* wt = pass == 0 ? sw1 : sw2;
+        const float* bb = pass == 0 ? sb1 : sb2;
+        for (int jt = rg; jt < S4 / 4; jt += nrg) {
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = bb[jt * 4 + a];
+#pragma unroll 4
+            for (int i = 0; i < S4; ++i) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wt + i * S4 + jt * 4);
+                const float4 v4 = *reinterpret_cast<const float4*>(src + i * 128 + cg * 4);
+                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(w[a], v[c], acc[a][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int p = jt * 4 + a;
+                if (pass == 0) {
+                    *reinterpret_cast<float4*>(sh + p * 128 + cg * 4) =
+                        make_float4(gelu_erf(acc[a][0]), gelu_erf(acc[a][1]), gelu_erf(acc[a][2]), gelu_erf(acc[a][3]));
+                } else if (p < S && cg * 4 < ncol) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(sv + p * 128 + cg * 4);
+                    *reinterpret_cast<float4*>(base + (size_t)p * IC + cg * 4) =
+                        make_float4(x4.x + acc[a][0], x4.y + acc[a][1], x4.z + acc[a][2], x4.w + acc[a][3]);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

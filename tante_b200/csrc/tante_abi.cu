@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "attention_mma.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
 
@@ -151,7 +152,7 @@ void build_plan(tante_handle_s* h) {
     const tante_config_t& c = h->cfg;
     REQUIRE(c.in_T >= 1 && c.in_T <= 64, "in_T out of range");
     REQUIRE(c.taylor_order >= 1 && c.taylor_order <= 4, "taylor_order must be in 1..4");
-    REQUIRE(c.embed_dim > 0 && c.embed_dim % 256 == 0 && c.embed_dim <= 512, "embed_dim must be 256 or 512");
+    REQUIRE(c.embed_dim == 256, "embed_dim must be 256 (the kernels are specialised for C = 256)");
     REQUIRE(c.n_head > 0 && c.embed_dim % c.n_head == 0, "embed_dim must be divisible by n_head");
     const int hd = c.embed_dim / c.n_head;
     REQUIRE(hd == 16 || hd == 32 || hd == 64, "head_dim must be 16, 32 or 64");
@@ -338,6 +339,15 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
     if (axis == 'T') { S = T; inner = L; nseq = B * L; }
     else if (axis == 'H') { S = Hp; inner = Wp; nseq = B * T * Wp; }
     else { S = Wp; inner = 1; nseq = B * T * Hp; }
+    if (sizeof(TA) == 2) {
+        cudaError_t e = cudaSuccess;
+        if (launch_attention_mma(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
+                                 inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
     const long long total = (long long)nseq * h->cfg.n_head * S;
     const int blocks = (int)((total + 127) / 128);
     const float scale = 1.0f / sqrtf((float)h->HD);
@@ -356,10 +366,12 @@ void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
-    const size_t smem = (size_t)(2 * S * 64 + 2 * S * S + 2 * S) * sizeof(float);
-    dim3 grid((unsigned)outer, (unsigned)((IC + 63) / 64));
-    REQUIRE((IC + 63) / 64 <= 65535, "latent too large for the propagator grid");
-    propagator_kernel<<<grid, 256, smem, st>>>(x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+    const int S4 = (S + 3) & ~3;
+    const size_t smem = (size_t)(2 * S4 * 128 + 2 * S4 * S4 + 2 * S4) * sizeof(float);
+    dim3 grid((unsigned)outer, (unsigned)((IC + 127) / 128));
+    REQUIRE((IC + 127) / 128 <= 65535, "latent too large for the propagator grid");
+    const int threads = 32 * std::min(8, S4 / 4);
+    propagator_kernel<<<grid, threads, smem, st>>>(x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
                                                AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]));
     CK(cudaGetLastError());
     h->launches++;
@@ -414,13 +426,15 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
     // --- encoder (enc_dec_cnn.py:217-229) + t_encode FiLM + s_emb + t_emb (tante.py:132-141) ---
     {
         const int P = g.k0 * g.k1 * g.k2;
-        int WC = std::max(1, 64 / g.R1);
+        int WC = std::max(1, 128 / g.R1);
         WC = std::min(WC, g.Wp);
         const int K1 = g.k0 * g.k0 * g.D;
-        const size_t smem = (size_t)(g.D * P * P * WC + C1 * (K1 + 1) + C1) * sizeof(float);
+        REQUIRE(C1 == 64, "patch embed kernel is specialised for embed_dim 256 (C/4 = 64)");
+        const size_t smem = (size_t)(((g.D * P * (P * WC + 1) + 3) & ~3) + C1 * K1 + C1) * sizeof(float) +
+                            (size_t)WC * g.R1 * C1 * sizeof(TA);
         dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
-        patch_embed_conv1_kernel<TA><<<grid, 256, smem, st>>>(io.input, io.fcount, g, AF(h, h->enc_w[0]),
-                                                              AF(h, h->enc_b[0]), C1, WC, a1);
+        patch_embed_conv1_kernel<TA><<<grid, 128, smem, st>>>(io.input, io.fcount, g, AF(h, h->enc_w[0]),
+                                                              AF(h, h->enc_b[0]), WC, a1);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);

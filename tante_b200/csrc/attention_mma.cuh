@@ -64,14 +64,21 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
     }
     __syncthreads();
     // ---- stage Q/K/V slices of 4 heads: per row 3 x 256 contiguous bytes ----
-    for (int idx = tid; idx < R * 48; idx += 128) {
-        const int r = idx / 48, c = idx % 48;
-        const int mat = c / 16, hh = (c % 16) / 4, part = c % 4;
-        const long long tok = s_tok[r];
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (tok >= 0)
-            v = *reinterpret_cast<const uint4*>(qkv + (size_t)tok * 3 * C + (size_t)mat * C + (hq * 4 + hh) * 32 + part * 8);
-        *reinterpret_cast<uint4*>(att_smem + (size_t)((mat * 4 + hh) * R) * 64 + att_off(r, part)) = v;
+    // (cp.async: all 16-byte requests of a thread are in flight at once, no register staging; src-size 0 zero-fills)
+    {
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(att_smem);
+#pragma unroll 4
+        for (int idx = tid; idx < R * 48; idx += 128) {
+            const int r = idx / 48, c = idx % 48;
+            const int mat = c / 16, hh = (c % 16) / 4, part = c % 4;
+            const long long tok = s_tok[r];
+            const __nv_bfloat16* src = qkv + (tok >= 0 ? (size_t)tok * 3 * C + (size_t)mat * C + (hq * 4 + hh) * 32 + part * 8 : 0);
+            const uint32_t dst = sbase + (uint32_t)((mat * 4 + hh) * R) * 64 + att_off(r, part);
+            const int nbytes = tok >= 0 ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
@@ -82,6 +89,17 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
     const int g = lane >> 2, t = lane & 3;
     const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);   // ldmatrix row supplied by this lane (A / V pattern)
     const int lchk = lane >> 4;                            // 0/1: which 16-byte chunk of the pair
+
+    // per-thread key metadata (the keys this lane sees in every score fragment): group id and position
+    int kgrp[NKB][2], kpos[NKB][2];
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int key = kb * 8 + 2 * t + j;
+            if (G == 1) { kgrp[kb][j] = key < rows_valid ? 0 : -1; kpos[kb][j] = key; }
+            else { kgrp[kb][j] = key < rows_valid ? key / S : -1; kpos[kb][j] = key % S; }
+        }
 
 #pragma unroll 1
     for (int qb = 0; qb < R / 16; ++qb) {
@@ -101,17 +119,16 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
         }
         // ---- mask + softmax over the key axis (rows g and g+8 of this 16-row block) ----
         const int r0 = qb * 16 + g, r1 = r0 + 8;
-        const int g0 = r0 / S, p0 = r0 % S, g1 = r1 / S, p1 = r1 % S;
+        const int g0 = G == 1 ? 0 : r0 / S, p0 = G == 1 ? r0 : r0 % S;
+        const int g1 = G == 1 ? 0 : r1 / S, p1 = G == 1 ? r1 : r1 % S;
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int key = kb * 8 + 2 * t + j;
-                const int kg = key / S, kp = key % S;
-                const bool kv = key < rows_valid;
-                const bool ok0 = kv && kg == g0 && (!causal || kp <= p0);
-                const bool ok1 = kv && kg == g1 && (!causal || kp <= p1);
+                const int kg = kgrp[kb][j], kp = kpos[kb][j];
+                const bool ok0 = kg == g0 && (!causal || kp <= p0);
+                const bool ok1 = kg == g1 && (!causal || kp <= p1);
                 s[kb][j] = ok0 ? s[kb][j] : -INFINITY;
                 s[kb][2 + j] = ok1 ? s[kb][2 + j] : -INFINITY;
                 m0 = fmaxf(m0, s[kb][j]);
@@ -174,6 +191,14 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
     }
 }
 
+static void att_set_attrs() {
+    static bool attr = false;
+    if (attr) return;
+    cudaFuncSetAttribute(axial_attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(axial_attention_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+}
+
 // Host launcher.  Returns false when the configuration is outside this kernel (caller falls back).
 static bool launch_attention_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, long long n_groups, int S, int inner_sz,
                                  int n_head, int C, int head_dim, int causal, cudaStream_t st, cudaError_t* err) {
@@ -185,12 +210,7 @@ static bool launch_attention_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, l
     dim3 grid((unsigned)blocks, (unsigned)(n_head / 4));
     const size_t smem = (size_t)3 * 4 * R * 64;
     const float sl2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(axial_attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(axial_attention_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr = true;
-    }
+    att_set_attrs();
     switch (R) {
         case 16: axial_attention_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
         case 32: axial_attention_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;

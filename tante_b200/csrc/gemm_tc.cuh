@@ -320,6 +320,18 @@ static bool tc_plan(int M, int N, int K, int num_sms, TcPlan* p) {
     return true;
 }
 
+static cudaError_t tc_set_attrs() {
+    static bool attr_done = false;
+    if (attr_done) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if (!get_encode_tiled()) return cudaErrorNotSupported;
+    attr_done = true;
+    return cudaSuccess;
+}
+
 static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, void* C,
                                   int ldc, int out_bf16, int M, int N, int K, const EpiParams& ep, int num_sms,
                                   cudaStream_t st) {
@@ -340,14 +352,7 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
         if (out_bf16) return cudaErrorInvalidValue;
         if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.resid, M, N, ep.ldr, 32, 32)) return cudaErrorInvalidValue;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e;
-        if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-        attr_done = true;
-    }
+    { cudaError_t e = tc_set_attrs(); if (e != cudaSuccess) return e; }
     switch (p.BN) {
         case 256: gemm_tc_kernel<256><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
         case 128: gemm_tc_kernel<128><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;

@@ -431,17 +431,27 @@ __global__ void __launch_bounds__(256) film_apply_kernel(const float* __restrict
 // Step-size selection (reference tante.py:156-163): R_t = mean_k rt_k, n = floor(R_t[gov]) with
 // gov = b (per-sample) or 0 (reference batch semantics).  Also the rollout bookkeeping.
 // ------------------------------------------------------------------------------------------------
+struct RolloutPtrs {   // caller-owned output buffers, kept in device memory so that captured graphs are reusable
+    float* y_out;      // (B, n_roll, H, W, D) channels-last history
+    float* rts_out;    // [max_steps][B]
+    int* ns_out;       // [max_steps][B]
+};
+
 struct RolloutState {
     int* cum;       // [B] frames emitted so far
     int* fcount;    // [B] frames ever in the ring (starts at T)
     int* steps;     // [B] model calls so far
     int* n_cur;     // [B] frames to emit this step (0 = sample finished)
     int* remaining; // [1] samples still running (written at the end of each step)
-    float* rts_out; // [max_steps][B]
-    int* ns_out;    // [max_steps][B]
+    int* iter;      // [1] model calls issued in this rollout
+    const RolloutPtrs* ptrs;
     int n_roll;
     int max_steps;
 };
+
+__global__ void set_rollout_ptrs_kernel(RolloutPtrs* dst, float* y, float* rts, int* ns) {
+    dst->y_out = y; dst->rts_out = rts; dst->ns_out = ns;
+}
 
 __global__ void select_step_kernel(const float* __restrict__ rt /* [K][Bstride] */, int K, int Bstride, int B,
                                    int deg, int output_length, int per_sample, int n_cap,
@@ -471,8 +481,8 @@ __global__ void select_step_kernel(const float* __restrict__ rt /* [K][Bstride] 
         else {
             const int s = rs.steps[b];
             if (s < rs.max_steps) {
-                rs.ns_out[(size_t)s * B + b] = n;
-                if (!deg) rs.rts_out[(size_t)s * B + b] = Rb;
+                rs.ptrs->ns_out[(size_t)s * B + b] = n;
+                if (!deg) rs.ptrs->rts_out[(size_t)s * B + b] = Rb;
             }
         }
         rs.n_cur[b] = n;
@@ -480,8 +490,9 @@ __global__ void select_step_kernel(const float* __restrict__ rt /* [K][Bstride] 
     if (n_out) n_out[b] = n;
 }
 
-__global__ void advance_state_kernel(RolloutState rs, int B) {
-    // single CTA; after the head kernel of a step
+__global__ void advance_state_kernel(RolloutState rs, int B, cudaGraphConditionalHandle cond, int use_cond) {
+    // single CTA; after the head kernel of a step.  When the step runs as the body of a CUDA-graph WHILE
+    // node, the loop condition (any trajectory still short of n_roll frames) is set here, on the device.
     __shared__ int rem;
     if (threadIdx.x == 0) rem = 0;
     __syncthreads();
@@ -495,13 +506,18 @@ __global__ void advance_state_kernel(RolloutState rs, int B) {
         if (rs.cum[b] < rs.n_roll) atomicAdd(&rem, 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) *rs.remaining = rem;
+    if (threadIdx.x == 0) {
+        *rs.remaining = rem;
+        const int it = *rs.iter + 1;
+        *rs.iter = it;
+        if (use_cond) cudaGraphSetConditional(cond, (rem > 0 && it < rs.max_steps) ? 1u : 0u);
+    }
 }
 
 __global__ void init_state_kernel(RolloutState rs, int B, int T) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) { rs.cum[b] = 0; rs.fcount[b] = T; rs.steps[b] = 0; rs.n_cur[b] = 0; }
-    if (b == 0) *rs.remaining = B;
+    if (b == 0) { *rs.remaining = B; *rs.iter = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -526,8 +542,8 @@ struct HeadParams {
     const int* n_arr;               // [B] frames to emit
     // plain forward: frames (B, n_cap, D, H, W)
     float* frames; int n_cap;
-    // rollout: channels-last history (B, n_roll, H, W, D) + ring write-back
-    float* y_out; float* ring_out; const int* cum; int n_roll;
+    // rollout: channels-last history (B, n_roll, H, W, D) (pointer read from `ptrs`) + ring write-back
+    const RolloutPtrs* ptrs; float* ring_out; const int* cum; int n_roll;
     // optional: decoded derivative fields for debugging/tests [K][B][D][H][W]
     float* deriv_dbg;
 };
@@ -566,6 +582,7 @@ __global__ void __launch_bounds__(128) taylor_head_kernel(HeadParams hp, PatchGe
     const int u_slot = (fc + g.T - 1) % g.T;
     const float* u0p = hp.u_ring + ((size_t)(b * g.T + u_slot) * g.D) * HW;
     const int cum = hp.cum ? hp.cum[b] : 0;
+    float* y_out = hp.ptrs ? hp.ptrs->y_out : nullptr;
 
     for (int o0 = 0; o0 < NO; o0 += MAXO) {
         float acc[KORD][MAXO];
@@ -607,9 +624,9 @@ __global__ void __launch_bounds__(128) taylor_head_kernel(HeadParams hp, PatchGe
                 for (int k = KORD; k >= 1; --k) v = (acc[k - 1][o] + v) * (dt / (float)k);
                 const float val = v + u0;
                 if (hp.frames) hp.frames[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix] = val;
-                if (hp.y_out) {
+                if (y_out) {
                     const int fidx = cum + i - 1;
-                    if (fidx < hp.n_roll) hp.y_out[(((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D + d] = val;
+                    if (fidx < hp.n_roll) y_out[(((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D + d] = val;
                     if (i > n - g.T) {
                         const int slot = (fc + i - 1) % g.T;
                         hp.ring_out[((size_t)(b * g.T + slot) * g.D + d) * HW + pix] = val;

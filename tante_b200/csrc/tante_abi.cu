@@ -109,6 +109,14 @@ struct tante_handle_s {
     bool debug = false;
     int last_B = 0;
     int num_sms = 148;
+    // rollout graphs: key -> instantiated graph (WHILE node whose body is one model step)
+    struct RollGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; bool while_node = false; int64_t launches_per_step = 0; };
+    std::map<std::string, RollGraph> graphs;
+    cudaStream_t cap_stream = nullptr;
+    int rollout_mode = 2;       // 0 = eager launches, 1 = one graph per step + host loop, 2 = device WHILE graph
+    cudaGraphConditionalHandle cond_handle = 0;
+    int use_cond = 0;
+    int last_graph_steps = 0;
     // live GEMM timing (tante_profile)
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -267,18 +275,20 @@ struct StepIO {
     const int* fcount = nullptr;
     float* frames = nullptr; int n_cap = 1;
     float* R_t = nullptr; int* n_dev = nullptr;
-    float* y_out = nullptr; float* ring_out = nullptr; int n_roll = 0;
+    float* ring_out = nullptr; int n_roll = 0;
     bool rollout = false;
     int per_sample = 0;
     float out_T = 1.f;
 };
 
-RolloutState make_state(tante_handle_s* h, int B, int n_roll, float* rts_out, int* ns_out) {
+RolloutState make_state(tante_handle_s* h, int B, int n_roll) {
     RolloutState rs;
     int* s = reinterpret_cast<int*>(h->state.p);
     const int mb = h->max_batch;
     rs.cum = s; rs.fcount = s + mb; rs.steps = s + 2 * mb; rs.n_cur = s + 3 * mb; rs.remaining = s + 4 * mb;
-    rs.rts_out = rts_out; rs.ns_out = ns_out; rs.n_roll = n_roll; rs.max_steps = n_roll;
+    rs.iter = s + 4 * mb + 1;
+    rs.ptrs = reinterpret_cast<const RolloutPtrs*>(s + 4 * mb + 8);   // 32-byte aligned slot after the counters
+    rs.n_roll = n_roll; rs.max_steps = n_roll;
     return rs;
 }
 
@@ -391,7 +401,7 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
     hp.fcount = io.fcount;
     hp.n_arr = io.rollout ? rs.n_cur : reinterpret_cast<int*>(h->nbuf.p);
     hp.frames = io.frames; hp.n_cap = io.n_cap;
-    hp.y_out = io.y_out; hp.ring_out = io.ring_out; hp.cum = io.rollout ? rs.cum : nullptr; hp.n_roll = io.n_roll;
+    hp.ptrs = io.rollout ? rs.ptrs : nullptr; hp.ring_out = io.ring_out; hp.cum = io.rollout ? rs.cum : nullptr; hp.n_roll = io.n_roll;
     hp.deriv_dbg = deriv_dbg;
     const long long rows = (long long)B * h->L * h->geom.R1;
     const int NO = h->geom.k0 * h->geom.k0 * h->D;
@@ -514,7 +524,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
     h->launches++;
     launch_head<TA>(h, io, B, rs, nullptr, st);
     if (io.rollout) {
-        advance_state_kernel<<<1, 256, 0, st>>>(rs, B);
+        advance_state_kernel<<<1, 256, 0, st>>>(rs, B, h->cond_handle, h->use_cond);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -536,8 +546,12 @@ void set_smem_attrs() {
     HEADATTR(float, 1); HEADATTR(float, 2); HEADATTR(float, 3); HEADATTR(float, 4);
     HEADATTR(__nv_bfloat16, 1); HEADATTR(__nv_bfloat16, 2); HEADATTR(__nv_bfloat16, 3); HEADATTR(__nv_bfloat16, 4);
 #undef HEADATTR
+    CK(tc_set_attrs());
+    att_set_attrs();
     done = true;
 }
+
+void destroy_graphs(tante_handle_s* h);
 
 template <typename F>
 int guarded(F&& f) {
@@ -555,6 +569,60 @@ int guarded(F&& f) {
 
 }  // namespace
 
+namespace {
+void destroy_graphs(tante_handle_s* h) {
+    for (auto& kv : h->graphs) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    h->graphs.clear();
+}
+
+template <typename TA>
+void build_roll_graph(tante_handle_s* h, tante_handle_s::RollGraph& rg, const StepIO& io, int B,
+                             const RolloutState& rs, bool while_node) {
+    if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t launches0 = h->launches;
+    if (while_node) {
+        CK(cudaGraphCreate(&rg.graph, 0));
+        CK(cudaGraphConditionalHandleCreate(&h->cond_handle, rg.graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.conditional.handle = h->cond_handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        CK(cudaGraphAddNode(&node, rg.graph, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        h->use_cond = 1;
+        CK(cudaStreamBeginCaptureToGraph(h->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        try {
+            run_step<TA>(h, io, B, rs, h->cap_stream);
+        } catch (...) {
+            cudaGraph_t dummy = nullptr;
+            cudaStreamEndCapture(h->cap_stream, &dummy);
+            h->use_cond = 0;
+            throw;
+        }
+        CK(cudaStreamEndCapture(h->cap_stream, nullptr));
+        h->use_cond = 0;
+    } else {
+        CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            run_step<TA>(h, io, B, rs, h->cap_stream);
+        } catch (...) {
+            cudaGraph_t dummy = nullptr;
+            cudaStreamEndCapture(h->cap_stream, &dummy);
+            throw;
+        }
+        CK(cudaStreamEndCapture(h->cap_stream, &rg.graph));
+    }
+    CK(cudaGraphInstantiate(&rg.exec, rg.graph, 0));
+    rg.while_node = while_node;
+    rg.launches_per_step = h->launches - launches0;
+    h->launches = launches0;      // capture enqueued nothing
+}
+}  // namespace
+
 // ================================================================================================
 extern "C" {
 
@@ -568,6 +636,7 @@ int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out) {
         h->cfg = *cfg;
         h->device = device;
         build_plan(h.get());
+        if (const char* m = getenv("TANTE_ROLLOUT_MODE")) h->rollout_mode = std::max(0, std::min(2, atoi(m)));
         int sms = 0;   // stays at the B200 default when no device is visible (CPU-side plan checks)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
         else (void)cudaGetLastError();
@@ -587,6 +656,8 @@ int tante_destroy(tante_handle_t h) {
         if (h->h_flag) cudaFreeHost(h->h_flag);
         for (auto& e : h->ev) if (e) cudaEventDestroy(e);
         for (auto& e : h->prof_ev) cudaEventDestroy(e);
+        destroy_graphs(h);
+        if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
         delete h;
     });
 }
@@ -669,6 +740,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         (void)training;
         CK(cudaSetDevice(h->device));
         if (max_batch <= h->max_batch && max_roll <= h->max_roll) return;
+        destroy_graphs(h);        // workspace pointers are baked into captured kernel arguments
         max_batch = std::max(max_batch, h->max_batch);
         max_roll = std::max(max_roll, h->max_roll);
         const size_t es = h->cfg.precision == TANTE_PREC_BF16 ? 2 : 4;
@@ -695,7 +767,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         dev_alloc(h, h->nbuf, (size_t)max_batch * 4);
         dev_alloc(h, h->filmbuf, (size_t)max_batch * 2 * C * 4);
         dev_alloc(h, h->ring, (size_t)max_batch * h->T * h->D * h->cfg.H * h->cfg.W * 4);
-        dev_alloc(h, h->state, ((size_t)4 * max_batch + 16) * 4);
+        dev_alloc(h, h->state, ((size_t)4 * max_batch + 64) * 4);
         if (h->debug) dev_alloc(h, h->dbg_in, tokens * C * 4);
         if (!h->h_flag) {
             CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flag), 64));
@@ -738,37 +810,72 @@ int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_ro
     return guarded([&] {
         REQUIRE(h && window && y_out, "null argument");
         REQUIRE(n_roll >= 1, "n_roll must be >= 1");
-        REQUIRE(h->cfg.deg || (rts_out && ns_out), "rts_out/ns_out required for the adaptive model");
+        REQUIRE(rts_out && ns_out, "rts_out/ns_out are required");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        const bool f32 = h->cfg.precision == TANTE_PREC_FP32;
         const size_t wbytes = (size_t)B * h->T * h->D * h->cfg.H * h->cfg.W * 4;
         CK(cudaMemcpyAsync(h->ring.p, window, wbytes, cudaMemcpyDeviceToDevice, st));
-        RolloutState rs = make_state(h, B, n_roll, rts_out, ns_out);
+        RolloutState rs = make_state(h, B, n_roll);
         init_state_kernel<<<(B + 127) / 128, 128, 0, st>>>(rs, B, h->T);
         CK(cudaGetLastError());
-        h->launches++;
+        set_rollout_ptrs_kernel<<<1, 1, 0, st>>>(const_cast<RolloutPtrs*>(rs.ptrs), y_out, rts_out, ns_out);
+        CK(cudaGetLastError());
+        h->launches += 2;
         StepIO io;
         io.input = reinterpret_cast<const float*>(h->ring.p);
         io.fcount = rs.fcount;
-        io.y_out = y_out; io.ring_out = reinterpret_cast<float*>(h->ring.p); io.n_roll = n_roll;
+        io.ring_out = reinterpret_cast<float*>(h->ring.p); io.n_roll = n_roll;
         io.rollout = true; io.per_sample = per_sample; io.out_T = out_T;
-        // Every step emits >= 1 frame per running sample, so n_roll steps always suffice.  The host
-        // checks the device's `remaining` counter with a one-step lag (flag copy + event per step),
-        // so an adaptive rollout stops at most one step late and never stalls the stream.
-        int pending[2] = {0, 0};
-        for (int s = 0; s < n_roll; ++s) {
-            const int slot = s & 1;
-            if (pending[slot]) {
-                CK(cudaEventSynchronize(h->ev[slot]));
-                pending[slot] = 0;
-                if (h->h_flag[slot] == 0) break;
+
+        int mode = h->prof_on || h->debug ? 0 : h->rollout_mode;
+        tante_handle_s::RollGraph* rg = nullptr;
+        if (mode > 0) {
+            char key[96];
+            snprintf(key, sizeof(key), "%d/%d/%d/%.9g/%d", B, n_roll, per_sample, (double)out_T, mode);
+            auto it = h->graphs.find(key);
+            if (it == h->graphs.end()) {
+                tante_handle_s::RollGraph g;
+                try {
+                    if (f32) build_roll_graph<float>(h, g, io, B, rs, mode == 2);
+                    else build_roll_graph<__nv_bfloat16>(h, g, io, B, rs, mode == 2);
+                } catch (const Error& e) {
+                    if (mode != 2) throw;
+                    // conditional nodes unavailable: fall back to per-step graphs for this handle
+                    (void)cudaGetLastError();
+                    h->rollout_mode = mode = 1;
+                    snprintf(key, sizeof(key), "%d/%d/%d/%.9g/%d", B, n_roll, per_sample, (double)out_T, mode);
+                    if (f32) build_roll_graph<float>(h, g, io, B, rs, false);
+                    else build_roll_graph<__nv_bfloat16>(h, g, io, B, rs, false);
+                }
+                it = h->graphs.emplace(key, g).first;
             }
-            if (h->cfg.precision == TANTE_PREC_FP32) run_step<float>(h, io, B, rs, st);
-            else run_step<__nv_bfloat16>(h, io, B, rs, st);
-            CK(cudaMemcpyAsync(h->h_flag + slot, rs.remaining, 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(h->ev[slot], st));
-            pending[slot] = 1;
+            rg = &it->second;
+        }
+        if (mode == 2) {
+            // the whole `while cumulative_length < n_steps_rollout` loop (r_evaler.py:94) is ONE graph launch:
+            // a WHILE node re-runs the step body until the device-side counter of unfinished trajectories is 0
+            CK(cudaGraphLaunch(rg->exec, st));
+            h->launches += rg->launches_per_step;      // lower bound: the body runs >= 1 time (device decides)
+            h->last_graph_steps = -1;
+        } else {
+            // host loop with a one-step-lagged look at the device's `remaining` counter (never stalls the stream)
+            int pending[2] = {0, 0};
+            for (int s = 0; s < n_roll; ++s) {
+                const int slot = s & 1;
+                if (pending[slot]) {
+                    CK(cudaEventSynchronize(h->ev[slot]));
+                    pending[slot] = 0;
+                    if (h->h_flag[slot] == 0) break;
+                }
+                if (mode == 1) { CK(cudaGraphLaunch(rg->exec, st)); h->launches += rg->launches_per_step; }
+                else if (f32) run_step<float>(h, io, B, rs, st);
+                else run_step<__nv_bfloat16>(h, io, B, rs, st);
+                CK(cudaMemcpyAsync(h->h_flag + slot, rs.remaining, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(h->ev[slot], st));
+                pending[slot] = 1;
+            }
         }
         if (steps_out) CK(cudaMemcpyAsync(steps_out, rs.steps, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
         h->last_B = B;

@@ -142,10 +142,11 @@ TANTE_API int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm
 /* Test hook: run one GEMM of the library stand-alone, C[M,N] = epi(A[M,K] * W[N,K]^T + bias).
  * use_tc = 1: tcgen05 bf16 kernel (A, W bf16; C bf16 when out_bf16 else f32);
  * use_tc = 0: FFMA fp32 kernel (A, W, C f32).  epi: 0 bias, 1 +relu, 2 +gelu(erf), 3 +gelu(tanh),
- * 4 + resid (f32 [M,N], may alias C).  iters > 1 repeats the launch (timing from the caller's events). */
+ * 4 + resid (f32 [M,N], may alias C), 6 = 4 plus LayerNorm(gamma, beta, eps 1e-5) of the updated row into
+ * ln_out (bf16 [M,N]; tcgen05 kernel only, N == 256).  iters > 1 repeats the launch. */
 TANTE_API int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const void* W, const float* bias,
                     const float* resid, void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K,
-                    int32_t iters, void* stream);
+                    int32_t iters, const float* ln_gamma, const float* ln_beta, void* ln_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,7 @@ enum Epilogue : int {
     EPI_BIAS_GELU_TANH = 3,
     EPI_BIAS_RESID = 4,  // C = resid + acc + bias   (fp32 residual stream, may alias C)
     EPI_EMBED = 5,       // encoder tail: v=acc+bias; v += v*scale[t]+shift[t]; v += s_emb[hw]; v += t_emb[t]
+    EPI_BIAS_RESID_LN = 6,  // EPI_BIAS_RESID + LayerNorm of the updated row written to a second (bf16) output
 };
 
 struct EpiParams {
@@ -98,6 +99,10 @@ struct EpiParams {
     const float* s_emb = nullptr;   // [L][N]
     const float* t_emb = nullptr;   // [T][N]
     int T = 0, L = 0;
+    // EPI_BIAS_RESID_LN (tensor GEMM only, N == 256): next LayerNorm's affine + its bf16 output
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    void* ln_out = nullptr;         // bf16 [M, N]
 };
 
 template <int EPI>

@@ -25,8 +25,8 @@ constexpr int kTcBlockK = 64;                       // 64 bf16 = one 128-byte sw
 constexpr int kTcStageBytes = kTcBlockM * 128;      // 16 KB
 constexpr int kTcMaxStages = 8;
 constexpr int kTcEpiBuf = 32 * 128;                 // one staging buffer: 32 rows x 128 B (SWIZZLE_128B)
-constexpr int kTcEpiBytes = 4 * 2 * kTcEpiBuf;      // 4 warps x 2 buffers
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 8;                      // 2 warps per TMEM lane quarter, interleaved column chunks
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
     const float k = 0.79788456080286535588f;
@@ -46,25 +46,31 @@ __device__ __forceinline__ float act_rt(int epi, float v) {
 // byte offset of 16-byte chunk `c` of row `r` inside a SWIZZLE_128B staging buffer (1024-B aligned)
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M, int N, int nkb,
-               int nstage, int epi, int out_bf16, EpiParams ep) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmL, int M, int N, int nkb, int nstage, int nebuf, int epi,
+               int out_bf16, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;                                   // [nkb][BN rows][128 B]
     uint8_t* sA = sW + (size_t)nkb * BN * 128;            // [nstage][128 rows][128 B]
-    uint8_t* sEpi = sA + (size_t)nstage * kTcStageBytes;  // [4 warps][2][4 KB]
-    float* sBias = reinterpret_cast<float*>(sEpi + kTcEpiBytes);   // [BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+    uint8_t* sEpi = sA + (size_t)nstage * kTcStageBytes;  // [8 warps][nebuf][4 KB]
+    float* sBias = reinterpret_cast<float*>(sEpi + (size_t)kTcEpiWarps * nebuf * kTcEpiBuf);   // bias, LN gamma, LN beta
+    float* sStat = sBias + 3 * BN;                        // [4 quarters][2 halves][32 rows][2] partial sum / sumsq
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 4 * 2 * 32 * 2);
     uint64_t* full = bars;                    // [kTcMaxStages]
     uint64_t* empty = bars + kTcMaxStages;    // [kTcMaxStages]
     uint64_t* w_full = bars + 2 * kTcMaxStages;
     uint64_t* tmem_full = w_full + 1;         // [2]
     uint64_t* tmem_empty = tmem_full + 2;     // [2]
-    uint64_t* rbar = tmem_empty + 2;          // [4 warps][2] residual-chunk barriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
+    uint64_t* rbar = tmem_empty + 2;          // [8 warps][2] residual-chunk barriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * kTcEpiWarps);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int n_slices = N / BN;
@@ -73,17 +79,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int per_slice = gridDim.x / n_slices;
     const int m_tiles = (M + kTcBlockM - 1) / kTcBlockM;
     const int n0 = slice * BN;
+    const bool has_ln = epi == EPI_BIAS_RESID_LN;          // requires BN == N (whole row in this CTA)
+    const bool has_res = epi == EPI_BIAS_RESID || has_ln;
 
-    for (int i = threadIdx.x; i < BN; i += kTcThreads) sBias[i] = ep.bias[n0 + i];
+    for (int i = threadIdx.x; i < BN; i += kTcThreads) {
+        sBias[i] = ep.bias[n0 + i];
+        if (has_ln) { sBias[BN + i] = ep.ln_gamma[n0 + i]; sBias[2 * BN + i] = ep.ln_beta[n0 + i]; }
+    }
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmW);
         ptx::prefetch_tmap(&tmC);
-        if (epi == EPI_BIAS_RESID) ptx::prefetch_tmap(&tmR);
+        if (has_res) ptx::prefetch_tmap(&tmR);
+        if (has_ln) ptx::prefetch_tmap(&tmL);
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(w_full, 1);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
-        for (int i = 0; i < 8; ++i) ptx::mbar_init(&rbar[i], 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], kTcEpiWarps); }
+        for (int i = 0; i < 2 * kTcEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -103,6 +115,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = rank; mt < m_tiles; mt += per_slice) {
+                if (has_res) {
+                    // pull this tile's residual rows (128 x BN fp32) into L2 now: the epilogue's TMA loads of the
+                    // chunks, one tile-time later, then see L2 latency instead of HBM latency
+                    for (int c = 0; c < BN / 32; ++c)
+                        for (int r = 0; r < kTcBlockM / 32; ++r)
+                            ptx::tma_prefetch_l2_2d(&tmR, n0 + c * 32, mt * kTcBlockM + r * 32);
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
@@ -140,12 +159,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4, thread = one output row =====
+        // ===== epilogue warps (2..9): TMEM lane quarter q = warp % 4, column chunks interleaved between the two
+        //       warps of a quarter (half = 0/1); thread = one output row =====
+        const int ew = warp - 2;
         const int q = warp & 3;
-        uint8_t* ebuf = sEpi + q * 2 * kTcEpiBuf;
-        uint64_t* rb = rbar + q * 2;
-        uint32_t rphase[2] = {0, 0};
-        int nbuf = 0;        // staging buffer the next chunk uses (alternates every chunk, across tiles)
+        const int half = ew >> 2;
+        uint8_t* ebuf = sEpi + (size_t)ew * nebuf * kTcEpiBuf;
+        uint64_t* rb = rbar + ew * 2;
+        uint32_t rphase0 = 0;
+        int nbuf = 0;        // staging buffer the next chunk uses (bf16 path with nebuf == 2 only)
         int t = 0;
         for (int mt = rank; mt < m_tiles; mt += per_slice, ++t) {
             const int acc = t & 1;
@@ -155,11 +177,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 64; ++ch) {
+                for (int ch = half; ch < BN / 64; ch += 2) {
                     uint32_t r0[32], r1[32];
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64), r0);
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64 + 32), r1);
-                    if (lane == 0) ptx::bulk_wait_read<1>();      // the store that last used this buffer has drained
+                    if (lane == 0) { if (nebuf > 1) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
                     __syncwarp();
                     ptx::tc_wait_ld();
                     uint8_t* buf = ebuf + nbuf * kTcEpiBuf;
@@ -183,38 +205,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::tma_store_2d(&tmC, buf, n0 + ch * 64, row0);
                         ptx::bulk_commit();
                     }
-                    nbuf ^= 1;
+                    if (nebuf > 1) nbuf ^= 1;
                 }
             } else {
-                // fp32 output in 32-column chunks; EPI_BIAS_RESID prefetches the residual chunk by TMA
-                const bool has_res = epi == EPI_BIAS_RESID;
-                if (has_res && lane == 0) {
-                    ptx::bulk_wait_read<0>();
-                    ptx::mbar_arrive_expect_tx(&rb[nbuf], kTcEpiBuf);
-                    ptx::tma_load_2d(ebuf + nbuf * kTcEpiBuf, &tmR, &rb[nbuf], n0, row0);
-                }
+                // fp32 output in 32-column chunks, one staging buffer per warp.  The residual variants TMA-load the
+                // residual chunk into the buffer (8 warps x 4 KB of loads in flight per SM cover the HBM latency),
+                // add in place and TMA-store it back.
                 ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
                 ptx::tc_fence_after();
                 const int m = row0 + lane;
+                float rsum = 0.f, rsq = 0.f;
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
+                for (int ch = half; ch < BN / 32; ch += 2) {
                     uint32_t r0[32];
-                    ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 32), r0);
-                    uint8_t* buf = ebuf + nbuf * kTcEpiBuf;
+                    uint8_t* buf = ebuf;
                     if (lane == 0) {
-                        // buffer nbuf^1 was last read by the store of the previous chunk: drain, then prefetch into it
+                        ptx::bulk_wait_read<0>();       // the previous store has finished reading the buffer
                         if (has_res) {
-                            ptx::bulk_wait_read<0>();
-                            if (ch + 1 < BN / 32) {
-                                ptx::mbar_arrive_expect_tx(&rb[nbuf ^ 1], kTcEpiBuf);
-                                ptx::tma_load_2d(ebuf + (nbuf ^ 1) * kTcEpiBuf, &tmR, &rb[nbuf ^ 1], n0 + (ch + 1) * 32, row0);
-                            }
-                        } else {
-                            ptx::bulk_wait_read<1>();
+                            ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                            ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 32, row0);
                         }
                     }
+                    ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 32), r0);
                     __syncwarp();
-                    if (has_res) { ptx::mbar_wait(&rb[nbuf], rphase[nbuf]); rphase[nbuf] ^= 1; }
+                    if (has_res) { ptx::mbar_wait(&rb[0], rphase0); rphase0 ^= 1; }
                     ptx::tc_wait_ld();
                     const float* bsm = sBias + ch * 32;
                     const int ncol = n0 + ch * 32;
@@ -229,6 +243,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (has_res) {
                             const float4 x = *p;
                             o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                            if (has_ln) {       // keep the updated row in TMEM (over the accumulator) for the LN pass
+                                r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
+                                r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
+                                rsum += (o.x + o.y) + (o.z + o.w);
+                                rsq = fmaf(o.x, o.x, rsq); rsq = fmaf(o.y, o.y, rsq);
+                                rsq = fmaf(o.z, o.z, rsq); rsq = fmaf(o.w, o.w, rsq);
+                            }
                         } else if (epi == EPI_EMBED) {
                             if (m < M) {
                                 const int hw = m % ep.L, tt = (m / ep.L) % ep.T;
@@ -247,13 +268,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         *p = o;
                     }
+                    if (has_ln) ptx::tmem_st_32x32(tm + (uint32_t)(ch * 32), r0);
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
                         ptx::tma_store_2d(&tmC, buf, ncol, row0);
                         ptx::bulk_commit();
                     }
-                    nbuf ^= 1;
+                }
+                if (has_ln) {
+                    // LayerNorm of the updated row: the two warps of this lane quarter exchange their partial row
+                    // statistics through shared memory, then each normalises its share of the row straight out of
+                    // TMEM (-> affine -> bf16 -> staging -> TMA store into the next GEMM's A operand).
+                    float* st = sStat + ((q * 2 + half) * 32 + lane) * 2;
+                    st[0] = rsum; st[1] = rsq;
+                    ptx::tc_wait_st();
+                    ptx::tc_fence_before();
+                    named_bar_sync(1 + q, 64);
+                    ptx::tc_fence_after();
+                    const float* so = sStat + ((q * 2 + (half ^ 1)) * 32 + lane) * 2;
+                    const float mean = (rsum + so[0]) * (1.0f / BN);
+                    const float var = fmaxf((rsq + so[1]) * (1.0f / BN) - mean * mean, 0.f);
+                    const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll 1
+                    for (int ch = half; ch < BN / 64; ch += 2) {
+                        uint32_t r0[32], r1[32];
+                        ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64), r0);
+                        ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64 + 32), r1);
+                        if (lane == 0) ptx::bulk_wait_read<0>();
+                        __syncwarp();
+                        ptx::tc_wait_ld();
+                        uint8_t* buf = ebuf;
+                        const float* gsm = sBias + BN + ch * 64;
+                        const float* bsm2 = sBias + 2 * BN + ch * 64;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int col = c * 8 + j * 2;
+                                const float a = (__uint_as_float(col < 32 ? r0[col] : r1[col - 32]) - mean) * rstd * gsm[col] + bsm2[col];
+                                const float b = (__uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) - mean) * rstd * gsm[col + 1] + bsm2[col + 1];
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            *reinterpret_cast<uint4*>(buf + sw128_off(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&tmL, buf, n0 + ch * 64, row0);
+                            ptx::bulk_commit();
+                        }
+                    }
+                    // sStat is reused by the next tile: make sure the partner has read it
+                    named_bar_sync(1 + q, 64);
                 }
             }
             ptx::tc_fence_before();
@@ -298,14 +367,18 @@ static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, cons
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct TcPlan { int BN, nkb, nstage, grid; size_t smem; };
+struct TcPlan { int BN, nkb, nstage, nebuf, grid; size_t smem; };
 
-static bool tc_plan(int M, int N, int K, int num_sms, TcPlan* p) {
+static bool tc_plan(int M, int N, int K, int num_sms, int out_bf16, TcPlan* p) {
     if (K % kTcBlockK != 0 || K > 512 || N % 64 != 0) return false;
     const int nkb = K / kTcBlockK;
     int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
     while ((size_t)nkb * BN * 128 > 128 * 1024 && BN > 64) BN /= 2;   // keep the resident slice <= 128 KB
-    const size_t fixed = (size_t)nkb * BN * 128 + kTcEpiBytes + BN * 4 + 512 + 1024;
+    // one 4 KB staging buffer per epilogue warp (8 warps keep enough TMA traffic in flight without double buffering)
+    (void)out_bf16;
+    const int nebuf = 1;
+    const size_t fixed = (size_t)nkb * BN * 128 + (size_t)kTcEpiWarps * nebuf * kTcEpiBuf + 3 * BN * 4 + 4 * 2 * 32 * 2 * 4 +
+                         512 + 1024;
     const size_t budget = 227 * 1024;
     int nstage = (int)((budget - fixed) / kTcStageBytes);
     nstage = nstage > 6 ? 6 : nstage;
@@ -315,7 +388,7 @@ static bool tc_plan(int M, int N, int K, int num_sms, TcPlan* p) {
     int per_slice = num_sms / n_slices;
     if (per_slice < 1) per_slice = 1;
     if (per_slice > m_tiles) per_slice = m_tiles;
-    p->BN = BN; p->nkb = nkb; p->nstage = nstage; p->grid = per_slice * n_slices;
+    p->BN = BN; p->nkb = nkb; p->nstage = nstage; p->nebuf = nebuf; p->grid = per_slice * n_slices;
     p->smem = fixed + (size_t)nstage * kTcStageBytes;
     return true;
 }
@@ -337,9 +410,11 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
                                   cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
     TcPlan p;
-    if (!tc_plan(M, N, K, num_sms, &p)) return cudaErrorInvalidValue;
+    if (!tc_plan(M, N, K, num_sms, out_bf16, &p)) return cudaErrorInvalidValue;
     if (!out_bf16 && N % 32 != 0) return cudaErrorInvalidValue;
-    CUtensorMap tmA, tmW, tmC, tmR;
+    CUtensorMap tmA, tmW, tmC, tmR, tmL;
+    const bool is_ln = epi == EPI_BIAS_RESID_LN;
+    if (is_ln && (out_bf16 || p.BN != N || !ep.ln_out || !ep.ln_gamma || !ep.ln_beta)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kTcBlockK, kTcBlockM)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kTcBlockK, p.BN)) return cudaErrorInvalidValue;
     if (out_bf16) {
@@ -348,15 +423,17 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
         if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, M, N, ldc, 32, 32)) return cudaErrorInvalidValue;
     }
     tmR = tmC;
-    if (epi == EPI_BIAS_RESID) {
+    tmL = tmC;
+    if (is_ln && !make_tmap_2d(&tmL, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.ln_out, M, N, N, 64, 32)) return cudaErrorInvalidValue;
+    if (epi == EPI_BIAS_RESID || is_ln) {
         if (out_bf16) return cudaErrorInvalidValue;
         if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.resid, M, N, ep.ldr, 32, 32)) return cudaErrorInvalidValue;
     }
     { cudaError_t e = tc_set_attrs(); if (e != cudaSuccess) return e; }
     switch (p.BN) {
-        case 256: gemm_tc_kernel<256><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
-        case 128: gemm_tc_kernel<128><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
-        default: gemm_tc_kernel<64><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, M, N, p.nkb, p.nstage, epi, out_bf16, ep); break;
+        case 256: gemm_tc_kernel<256><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
+        case 128: gemm_tc_kernel<128><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
+        default: gemm_tc_kernel<64><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
     }
     return cudaGetLastError();
 }

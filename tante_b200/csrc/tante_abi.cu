@@ -18,6 +18,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "attention_mma.cuh"
+#include "propagator_mma.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
 
@@ -376,6 +377,15 @@ void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
+    if (h->cfg.precision == TANTE_PREC_BF16 && S > 8) {    // tiny axes (T = 4) stay on the FFMA kernel
+        cudaError_t e = cudaSuccess;
+        if (launch_propagator_mma(x, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]),
+                                  AF(h, op.prop[axis][3]), st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
     const int S4 = (S + 3) & ~3;
     const size_t smem = (size_t)(2 * S4 * 128 + 2 * S4 * S4 + 2 * S4) * sizeof(float);
     dim3 grid((unsigned)outer, (unsigned)((IC + 127) / 128));
@@ -464,18 +474,36 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         launch_propagator(h, x, B, 0, op, st);
         launch_propagator(h, x, B, 1, op, st);
         launch_propagator(h, x, B, 2, op, st);
-        for (const LayerPlan& lp : op.layers) {
-            launch_layernorm<TA>(h, x, lp.ln1w, lp.ln1b, ln, tokens, st);
+        // In tensor mode every LayerNorm except the first one of an order is folded into the epilogue of the
+        // residual GEMM that produces its input (EPI_BIAS_RESID_LN): the row is still on chip there.
+        constexpr bool kFuseLN = sizeof(TA) == 2;
+        bool ln_ready = false;
+        for (size_t li = 0; li < op.layers.size(); ++li) {
+            const LayerPlan& lp = op.layers[li];
+            if (!ln_ready) launch_layernorm<TA>(h, x, lp.ln1w, lp.ln1b, ln, tokens, st);
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, qkv, att, B, lp.axis, st);
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x; eo.ldr = C;
-            gemm<TA>(h, EPI_BIAS_RESID, att, C, lp.outw, x, C, true, tokens, C, C, eo, st);
-            launch_layernorm<TA>(h, x, lp.ln2w, lp.ln2b, ln, tokens, st);
+            if (kFuseLN) {
+                eo.ln_gamma = AF(h, lp.ln2w); eo.ln_beta = AF(h, lp.ln2b); eo.ln_out = ln;
+                gemm<TA>(h, EPI_BIAS_RESID_LN, att, C, lp.outw, x, C, true, tokens, C, C, eo, st);
+            } else {
+                gemm<TA>(h, EPI_BIAS_RESID, att, C, lp.outw, x, C, true, tokens, C, C, eo, st);
+                launch_layernorm<TA>(h, x, lp.ln2w, lp.ln2b, ln, tokens, st);
+            }
             EpiParams e0; e0.bias = AF(h, lp.m0b);
             gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, C, false, tokens, C, C, e0, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x; e2.ldr = C;
-            gemm<TA>(h, EPI_BIAS_RESID, hid, C, lp.m2w, x, C, true, tokens, C, C, e2, st);
+            if (kFuseLN && li + 1 < op.layers.size()) {
+                const LayerPlan& nx = op.layers[li + 1];
+                e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ln;
+                gemm<TA>(h, EPI_BIAS_RESID_LN, hid, C, lp.m2w, x, C, true, tokens, C, C, e2, st);
+                ln_ready = true;
+            } else {
+                gemm<TA>(h, EPI_BIAS_RESID, hid, C, lp.m2w, x, C, true, tokens, C, C, e2, st);
+                ln_ready = false;
+            }
         }
         // --- head of order o (tante.py:147-154) ---
         float* d32 = reinterpret_cast<float*>(h->d32.p);
@@ -548,6 +576,7 @@ void set_smem_attrs() {
 #undef HEADATTR
     CK(tc_set_attrs());
     att_set_attrs();
+    prop_set_attrs();
     done = true;
 }
 
@@ -957,13 +986,15 @@ int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm_flops, in
 }
 
 int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const void* W, const float* bias, const float* resid,
-                    void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K, int32_t iters, void* stream) {
+                    void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K, int32_t iters, const float* ln_gamma,
+                    const float* ln_beta, void* ln_out, void* stream) {
     return guarded([&] {
         REQUIRE(A && W && bias && C, "null argument");
-        REQUIRE(epi >= EPI_BIAS && epi <= EPI_BIAS_RESID, "unsupported epilogue for the test hook");
+        REQUIRE((epi >= EPI_BIAS && epi <= EPI_BIAS_RESID) || epi == EPI_BIAS_RESID_LN, "unsupported epilogue for the test hook");
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
         EpiParams ep;
         ep.bias = bias; ep.resid = resid; ep.ldr = N;
+        ep.ln_gamma = ln_gamma; ep.ln_beta = ln_beta; ep.ln_out = ln_out;
         int dev = 0, sms = 148;
         CK(cudaGetDevice(&dev));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

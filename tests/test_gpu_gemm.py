@@ -32,7 +32,7 @@ def _run(use_tc, epi, A, W, bias, resid, out_bf16):
         r = None
     _abi.check(lib.tante_test_gemm(use_tc, epi, A.data_ptr(), W.data_ptr(), bias.data_ptr(),
                                    None if r is None else r.data_ptr(), C.data_ptr(), int(out_bf16), M, N, K, 1,
-                                   torch.cuda.current_stream().cuda_stream))
+                                   None, None, None, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return C
 
@@ -75,3 +75,28 @@ def test_ffma_gemm_matches_torch(M, N, K, epi):
     out = _run(0, epi, A, W, bias, resid, out_bf16=False)
     err = float((out.double() - ref).norm() / ref.norm())
     assert err < 1e-6, err
+
+
+@pytest.mark.parametrize("M,K", [(128, 256), (1000, 256), (4096, 128), (40000, 256), (333, 64)])
+def test_tcgen05_gemm_residual_layernorm_epilogue(M, K):
+    """x += A W^T + b fused with the next LayerNorm (EPI_BIAS_RESID_LN): both outputs vs torch."""
+    lib = _abi.load()
+    N = 256
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.3
+    gamma = 1 + 0.1 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    x_ref = x + A.float() @ W.float().t() + bias
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (N,), gamma, beta, 1e-5)
+    xc = x.clone()
+    ln = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _abi.check(lib.tante_test_gemm(1, 6, A.data_ptr(), W.data_ptr(), bias.data_ptr(), xc.data_ptr(), xc.data_ptr(), 0,
+                                   M, N, K, 1, gamma.data_ptr(), beta.data_ptr(), ln.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert float((xc - x_ref).norm() / x_ref.norm()) < 2e-6
+    assert float((ln.float() - ln_ref).norm() / ln_ref.norm()) < 4e-3      # one bf16 rounding
+    assert float((ln.float() - ln_ref).abs().max()) < 0.05

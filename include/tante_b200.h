@@ -127,10 +127,12 @@ TANTE_API int tante_debug_stage(tante_handle_t h, const char* stage, float* dst,
 /* Number of kernel launches enqueued by this handle since creation (bench.py's gpu_launches). */
 TANTE_API int64_t tante_launch_count(tante_handle_t h);
 
-/* Stand-alone launch of the fused Taylor head (K decoded stage-2 activations -> n frames),
- * for the K x patch-size microbenchmark (BASELINE.json configs[4]). */
-TANTE_API int tante_bench_head(tante_handle_t h, int32_t B, int32_t n_frames, int32_t iters, float* ms_out,
-                     void* stream);
+/* Stand-alone launches of the fused Taylor head (K stage-1 activation matrices -> n_frames frames per
+ * sample) for the K x patch-size microbenchmark (BASELINE.json configs[4]).  Uses the handle's own
+ * stage-1 buffers (whatever they hold), `u` = f32[B,T,D,H,W] window, `frames` = f32[B,n_frames,D,H,W].
+ * Runs `iters` launches between two CUDA events and returns the average in *ms_out (synchronises). */
+TANTE_API int tante_bench_head(tante_handle_t h, const float* u, float* frames, int32_t B, int32_t n_frames,
+                     int32_t iters, float* ms_out, void* stream);
 
 /* Live per-kernel-class timing for bench.py's roofline: while enabled, every GEMM launch of this handle
  * is bracketed by CUDA events on the launching stream (un-graphed launches).  tante_profile_read

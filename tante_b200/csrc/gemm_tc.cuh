@@ -37,7 +37,7 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 __device__ __forceinline__ float act_rt(int epi, float v) {
     switch (epi) {
         case EPI_BIAS_RELU: return fmaxf(v, 0.0f);
-        case EPI_BIAS_GELU_ERF: return gelu_erf(v);
+        case EPI_BIAS_GELU_ERF: return gelu_erf_fast(v);
         case EPI_BIAS_GELU_TANH: return gelu_tanh_fast(v);
         default: return v;
     }
@@ -115,13 +115,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = rank; mt < m_tiles; mt += per_slice) {
-                if (has_res) {
-                    // pull this tile's residual rows (128 x BN fp32) into L2 now: the epilogue's TMA loads of the
-                    // chunks, one tile-time later, then see L2 latency instead of HBM latency
-                    for (int c = 0; c < BN / 32; ++c)
-                        for (int r = 0; r < kTcBlockM / 32; ++r)
-                            ptx::tma_prefetch_l2_2d(&tmR, n0 + c * 32, mt * kTcBlockM + r * 32);
-                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], kTcStageBytes);

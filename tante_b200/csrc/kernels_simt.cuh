@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) patch_embed_conv1_kernel(const float* __r
         for (int c4 = 0; c4 < C1 / 4; ++c4) {
             float v4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v4[j] = gelu_erf(acc[c4 * 4 + j]);
+            for (int j = 0; j < 4; ++j) v4[j] = gelu_erf_for<TOut>(acc[c4 * 4 + j]);
             const int chunk = (c4 * 4) / CH, within = (c4 * 4) % CH;
             Vec4<TOut>::store(s_out + (size_t)rr * C1 + ((chunk + rr) % NCH) * CH + within, v4);
         }

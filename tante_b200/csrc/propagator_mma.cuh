@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(float* __restrict__
                 for (int nb = 0; nb < 4; ++nb) {
                     const int chunk = warp * 4 + nb;
                     *reinterpret_cast<uint32_t*>(sH + slab_off(j0, chunk) + t * 4) =
-                        pack_bf16x2(gelu_erf(acc[mb][nb][0] + bb0), gelu_erf(acc[mb][nb][1] + bb0));
+                        pack_bf16x2(gelu_erf_fast(acc[mb][nb][0] + bb0), gelu_erf_fast(acc[mb][nb][1] + bb0));
                     *reinterpret_cast<uint32_t*>(sH + slab_off(j1, chunk) + t * 4) =
-                        pack_bf16x2(gelu_erf(acc[mb][nb][2] + bb1), gelu_erf(acc[mb][nb][3] + bb1));
+                        pack_bf16x2(gelu_erf_fast(acc[mb][nb][2] + bb1), gelu_erf_fast(acc[mb][nb][3] + bb1));
                 }
             }
             __syncwarp();     // the hidden columns of a warp are consumed only by the same warp

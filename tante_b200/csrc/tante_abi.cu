@@ -19,6 +19,7 @@
 #include "gemm_tc.cuh"
 #include "attention_mma.cuh"
 #include "propagator_mma.cuh"
+#include "head_mma.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
 
@@ -414,6 +415,14 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
     hp.ptrs = io.rollout ? rs.ptrs : nullptr; hp.ring_out = io.ring_out; hp.cum = io.rollout ? rs.cum : nullptr; hp.n_roll = io.n_roll;
     hp.deriv_dbg = deriv_dbg;
     const long long rows = (long long)B * h->L * h->geom.R1;
+    if (sizeof(TA) == 2) {
+        cudaError_t e = cudaSuccess;
+        if (launch_head_mma(hp, h->geom, h->C1, rows, B, st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
     const int NO = h->geom.k0 * h->geom.k0 * h->D;
     const size_t smem = (size_t)(h->K * h->C1 * NO + h->K * h->D) * sizeof(float);
     const int blocks = (int)((rows + 127) / 128);
@@ -950,10 +959,37 @@ int tante_debug_stage(tante_handle_t h, const char* stage, float* dst, int64_t c
 
 int64_t tante_launch_count(tante_handle_t h) { return h ? h->launches : -1; }
 
-int tante_bench_head(tante_handle_t h, int32_t B, int32_t n_frames, int32_t iters, float* ms_out, void* stream) {
+int tante_bench_head(tante_handle_t h, const float* u, float* frames, int32_t B, int32_t n_frames, int32_t iters,
+                     float* ms_out, void* stream) {
     return guarded([&] {
-        (void)h; (void)B; (void)n_frames; (void)iters; (void)ms_out; (void)stream;
-        throw Error(TANTE_ERR_INVALID, "tante_bench_head: not built yet");
+        REQUIRE(h && u && frames && ms_out && n_frames >= 1 && iters >= 1, "bad argument");
+        CK(cudaSetDevice(h->device));
+        ensure_ready(h, B);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        std::vector<int> n(B, n_frames);
+        CK(cudaMemcpyAsync(h->nbuf.p, n.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        StepIO io;
+        io.input = u; io.frames = frames; io.n_cap = n_frames;
+        RolloutState rs{};
+        auto run = [&] {
+            if (h->cfg.precision == TANTE_PREC_FP32) launch_head<float>(h, io, B, rs, nullptr, st);
+            else launch_head<__nv_bfloat16>(h, io, B, rs, nullptr, st);
+        };
+        for (int i = 0; i < 3; ++i) run();
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) run();
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_out = ms / iters;
+        h->last_B = B;
     });
 }
 

@@ -384,6 +384,19 @@ class TANTE(nn.Module):
                                              torch.cuda.current_stream(dev).cuda_stream))
         return out[:got.value]
 
+    @torch.no_grad()
+    def bench_head(self, window: torch.Tensor, n_frames: int, iters: int = 20) -> float:
+        """Average device time (ms) of one stand-alone fused-head launch emitting `n_frames` frames per sample."""
+        x = self._prep_input(window)
+        eng = self._engine(x.device)
+        B = x.shape[0]
+        eng.reserve(B)
+        frames = torch.empty((B, n_frames, self.n_channel, *self.shape), device=x.device, dtype=torch.float32)
+        ms = ctypes.c_float(0)
+        _abi.check(eng.lib.tante_bench_head(eng.handle, x.data_ptr(), frames.data_ptr(), B, int(n_frames), int(iters),
+                                            ctypes.byref(ms), torch.cuda.current_stream(x.device).cuda_stream))
+        return float(ms.value)
+
     def profile_gemms(self, enable: bool):
         for e in self._engines.values():
             _abi.check(e.lib.tante_profile(e.handle, 1 if enable else 0))

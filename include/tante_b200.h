@@ -118,6 +118,31 @@ TANTE_API int tante_rollout(tante_handle_t h, const float* window, int32_t B, in
                   int32_t per_sample, float* y_out, float* rts_out, int32_t* ns_out,
                   int32_t* steps_out, int32_t sync, void* stream);
 
+/* ---- training: taped forward + backward ---------------------------------------------
+ * The reference trains through torch autograd over the same module (trainer/r_trainer.py:145-155:
+ * rollout_model -> loss -> loss.backward(); fixed-step twin trainer/trainer.py:178-193).  Here one
+ * model call in grad mode = tante_train_forward (keeps the activations in tape slot `slot`), and
+ * its autograd node's backward = tante_backward on the same slot.  Slots are reserved with
+ * tante_reserve(.., training = number of slots); a chained rollout with BPTT through the window
+ * (r_trainer.py:126) holds one slot per model call until its backward ran.
+ *
+ * tante_train_forward: same contract as tante_forward with per_sample = 0 (sample 0's R_t governs
+ *   n, tante.py:163); n_host (nullable) = the reference's host sync for floor(R_t[0]).
+ * tante_backward:
+ *   input       : the f32[B,T,D,H,W] tensor the forward saw (the first conv's weight gradient reads it)
+ *   grad_frames : f32[B, n_frames, D, H, W] gradient of the emitted frames (n_frames <= the forward's n)
+ *   grad_Rt     : f32[B] gradient of R_t (adaptive models; NULL = zero)
+ *   grad_input  : f32[B,T,D,H,W], written (may be NULL when the input needs no gradient)
+ *   grad_params : f32[tante_grad_numel()], written: parameter i's gradient in its state_dict layout
+ *                 at tante_param_grad_offset(i) (the caller hands these views to autograd, which
+ *                 accumulates into .grad -- so gradient accumulation and BPTT just work). */
+TANTE_API int64_t tante_grad_numel(tante_handle_t h);
+TANTE_API int64_t tante_param_grad_offset(tante_handle_t h, int32_t i);
+TANTE_API int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int32_t B, float out_T,
+                        int32_t n_cap, float* frames, float* R_t, int32_t* n_host, void* stream);
+TANTE_API int tante_backward(tante_handle_t h, int32_t slot, const float* input, const float* grad_frames,
+                   int32_t n_frames, const float* grad_Rt, float* grad_input, float* grad_params, void* stream);
+
 /* ---- introspection for tests / profiling ------------------------------------------ */
 /* Copy an internal stage tensor of the last tante_forward into `dst` (f32, device).
  * stage: "latent_in" (after embed), "latent" (after the last backbone), "deriv<k>"
@@ -149,6 +174,12 @@ TANTE_API int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm
 TANTE_API int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const void* W, const float* bias,
                     const float* resid, void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K,
                     int32_t iters, const float* ln_gamma, const float* ln_beta, void* ln_out, void* stream);
+
+/* Test hook: weight-gradient GEMM stand-alone, C[N,K] += A[M,N]^T * B[M,K] (C is accumulated into).
+ * use_tc = 1: tcgen05 kernel (bf16 MN-major operands, TMA reduce-add), 2: SIMT kernel on bf16 operands,
+ * 0: SIMT kernel on f32 operands. */
+TANTE_API int tante_test_wgrad(int32_t use_tc, const void* A, const void* B, float* C, int64_t M, int32_t N, int32_t K,
+                     int32_t iters, void* stream);
 
 #ifdef __cplusplus
 }

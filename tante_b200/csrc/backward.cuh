@@ -1,0 +1,894 @@
+// Backward (training) kernels of the TANTE hot path that are not GEMMs: activation derivatives, LayerNorm
+// backward, axial attention backward, propagator backward, the Taylor-head backward, FiLM / interprator
+// backward, embedding backward, the first patch conv's backward, a generic split-M weight-gradient kernel for
+// the exact fp32 mode (and for shapes the tcgen05 wgrad kernel does not cover) and the gradient un-packer.
+// Templated on the activation element type TA (float: exact mode, bf16: tensor mode) like the forward kernels.
+//
+// What they differentiate (reference, all through torch autograd there):
+//   TransformerBlock.forward attn_backbone.py:59-83, Attn_Backbone.forward :134-191, enc_CNN/dec_CNN.forward
+//   enc_dec_cnn.py:217-229,263-277, film/interprator tante.py:178-230, Taylor sum tante.py:156-171.
+#pragma once
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "pack.cuh"
+
+namespace tante {
+
+enum ActKind : int { ACT_GELU_ERF = 2, ACT_GELU_TANH = 3, ACT_RELU = 1 };
+
+// ---- elementwise: act = f(pre) -------------------------------------------------------------------
+template <typename TA, int ACT>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const TA* __restrict__ pre, TA* __restrict__ out, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float v[4], o[4];
+    Vec4<TA>::load(pre + i * 4, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = ACT == ACT_GELU_ERF ? gelu_erf(v[j]) : (ACT == ACT_GELU_TANH ? gelu_tanh(v[j]) : fmaxf(v[j], 0.f));
+    Vec4<TA>::store(out + i * 4, o);
+}
+
+// ---- elementwise: g <- g * f'(pre)   (ACT_RELU: `pre` may be the post-ReLU activation) --------------
+template <typename TA, int ACT>
+__global__ void __launch_bounds__(256) act_bwd_kernel(TA* __restrict__ g, const TA* __restrict__ pre, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float v[4], d[4];
+    Vec4<TA>::load(pre + i * 4, v);
+    Vec4<TA>::load(g + i * 4, d);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        d[j] *= ACT == ACT_GELU_ERF ? gelu_erf_grad(v[j]) : (ACT == ACT_GELU_TANH ? gelu_tanh_grad(v[j]) : (v[j] > 0.f ? 1.f : 0.f));
+    Vec4<TA>::store(g + i * 4, d);
+}
+
+// fp32 -> TA copy (gradient stream -> GEMM operand)
+template <typename TA>
+__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float v[4];
+    Vec4<float>::load(src + i * 4, v);
+    Vec4<TA>::store(dst + i * 4, v);
+}
+
+// ---- column sums: out[n] += sum_m x[m][n]  (bias gradients) ----------------------------------------
+// block (32, 8): 32 column groups of 4 columns, 8 row lanes; grid (ceil(N/128), row chunks).
+template <typename TA>
+__global__ void __launch_bounds__(256) colsum_kernel(const TA* __restrict__ x, int ld, long long M, int N,
+                                                     float* __restrict__ out) {
+    __shared__ float red[8][128];
+    const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+    const int c0 = blockIdx.x * 128 + cx * 4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < N) {
+        for (long long m = (long long)blockIdx.y * 8 + ry; m < M; m += (long long)gridDim.y * 8) {
+            float v[4];
+            Vec4<TA>::load(x + (size_t)m * ld + c0, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ry][cx * 4 + j] = s[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+        const int c = blockIdx.x * 128 + threadIdx.x;
+        if (c < N) atomicAdd(out + c, t);
+    }
+}
+
+// ---- embed forward (training mode: the encoder tail's FiLM + embeddings as its own pass so that the conv
+//      output v stays available for the backward): x0 = v + (v*scale_t + shift_t) + s_emb + t_emb ------
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ v, const float* __restrict__ film,
+                                                        const float* __restrict__ s_emb, const float* __restrict__ t_emb,
+                                                        float* __restrict__ x0, long long tokens, int T, int L, int C) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= tokens * C) return;
+    const long long m = i4 / C;
+    const int c = (int)(i4 % C);
+    const int hw = (int)(m % L), t = (int)((m / L) % T);
+    float a[4], sc[4], sh[4], se[4], te[4], o[4];
+    Vec4<float>::load(v + i4, a);
+    Vec4<float>::load(film + (size_t)(t * 2 + 0) * C + c, sc);
+    Vec4<float>::load(film + (size_t)(t * 2 + 1) * C + c, sh);
+    Vec4<float>::load(s_emb + (size_t)hw * C + c, se);
+    Vec4<float>::load(t_emb + (size_t)t * C + c, te);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = a[j] + (a[j] * sc[j] + sh[j]) + se[j] + te[j];
+    Vec4<float>::store(x0 + i4, o);
+}
+
+// ---- embed backward: dv = g*(1+scale_t); dscale[t] += g*v; dshift[t] += g; ds_emb[hw] += g; dt_emb[t] += g ----
+// grid = L (one CTA per latent position hw), 256 threads over channels (C <= 1024, C % 4 == 0 not needed).
+template <typename TA>
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                                                        const float* __restrict__ film, TA* __restrict__ dv,
+                                                        float* __restrict__ dfilm /* [T][2][C] */,
+                                                        float* __restrict__ ds_emb, float* __restrict__ dt_emb, int B,
+                                                        int T, int L, int C) {
+    const int hw = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float semb = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float sc = film[(size_t)(t * 2) * C + c];
+            float dsc = 0.f, dsh = 0.f;
+            for (int b = 0; b < B; ++b) {
+                const size_t m = ((size_t)(b * T + t) * L + hw) * C + c;
+                const float gg = g[m];
+                dv[m] = from_f32<TA>(gg * (1.0f + sc));
+                dsc = fmaf(gg, v[m], dsc);
+                dsh += gg;
+            }
+            semb += dsh;
+            atomicAdd(dfilm + (size_t)(t * 2) * C + c, dsc);
+            atomicAdd(dfilm + (size_t)(t * 2 + 1) * C + c, dsh);
+            atomicAdd(dt_emb + (size_t)t * C + c, dsh);
+        }
+        ds_emb[(size_t)hw * C + c] += semb;
+    }
+}
+
+// ---- FiLM generator backward (tante.py:206-220): for each condition n, given dscale/dshift [n][2][C] -----
+// grads of the two 2-layer MLPs (atomics into the packed-gradient arena) and d cond[n].
+__global__ void __launch_bounds__(256) film_bwd_kernel(const float* __restrict__ cond, const float* __restrict__ dfilm,
+                                                       const float* __restrict__ w0s, const float* __restrict__ b0s,
+                                                       const float* __restrict__ w2s, const float* __restrict__ w0h,
+                                                       const float* __restrict__ b0h, const float* __restrict__ w2h,
+                                                       float* __restrict__ gw0s, float* __restrict__ gb0s,
+                                                       float* __restrict__ gw2s, float* __restrict__ gb2s,
+                                                       float* __restrict__ gw0h, float* __restrict__ gb0h,
+                                                       float* __restrict__ gw2h, float* __restrict__ gb2h, int C,
+                                                       float* __restrict__ dcond /* nullable [n] */) {
+    extern __shared__ float smem[];
+    const int Ch = C / 2;
+    float* hs = smem;            // [Ch] hidden of the scale branch
+    float* hh = hs + Ch;         // [Ch]
+    float* ds = hh + Ch;         // [C] dscale
+    float* dh = ds + C;          // [C] dshift
+    __shared__ float red[256];
+    const int n = blockIdx.x;
+    const float t = cond[n];
+    for (int i = threadIdx.x; i < Ch; i += blockDim.x) {
+        hs[i] = fmaxf(fmaf(w0s[i], t, b0s[i]), 0.f);
+        hh[i] = fmaxf(fmaf(w0h[i], t, b0h[i]), 0.f);
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        ds[c] = dfilm[((size_t)n * 2 + 0) * C + c];
+        dh[c] = dfilm[((size_t)n * 2 + 1) * C + c];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(gb2s + c, ds[c]);
+        atomicAdd(gb2h + c, dh[c]);
+    }
+    for (int i = threadIdx.x; i < C * Ch; i += blockDim.x) {
+        const int c = i / Ch, j = i % Ch;
+        if (hs[j] != 0.f) atomicAdd(gw2s + i, ds[c] * hs[j]);
+        if (hh[j] != 0.f) atomicAdd(gw2h + i, dh[c] * hh[j]);
+    }
+    float dt = 0.f;
+    for (int j = threadIdx.x; j < Ch; j += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < C; ++c) {
+            a = fmaf(ds[c], w2s[(size_t)c * Ch + j], a);
+            b = fmaf(dh[c], w2h[(size_t)c * Ch + j], b);
+        }
+        if (hs[j] <= 0.f) a = 0.f;
+        if (hh[j] <= 0.f) b = 0.f;
+        atomicAdd(gw0s + j, a * t);
+        atomicAdd(gb0s + j, a);
+        atomicAdd(gw0h + j, b * t);
+        atomicAdd(gb0h + j, b);
+        dt += a * w0s[j] + b * w0h[j];
+    }
+    red[threadIdx.x] = dt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && dcond) dcond[n] = red[0];
+}
+
+// ---- FiLM application backward on the (B, L, C) derivative latent (tante.py:222-230) --------------------
+// dmod = d + d*s_b + h_b:  dx_last[b,l,c] += g*(1+s_b[c]);  dfilm[b][0][c] += sum_l g*d;  dfilm[b][1][c] += sum_l g.
+// grid (B, chunks of L), block = C threads (C <= 1024).  dx_last is the gradient stream's last-frame slice.
+template <typename TA>
+__global__ void film_apply_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ d32,
+                                      const float* __restrict__ film, float* __restrict__ dxs, float* __restrict__ dfilm,
+                                      int T, int L, int C) {
+    const int b = blockIdx.x;
+    const int c = threadIdx.x;
+    const int per = (L + gridDim.y - 1) / gridDim.y;
+    const int l0 = blockIdx.y * per, l1 = min(L, l0 + per);
+    const float sc = film[((size_t)b * 2 + 0) * C + c];
+    float dsc = 0.f, dsh = 0.f;
+    for (int l = l0; l < l1; ++l) {
+        const size_t i = ((size_t)b * L + l) * C + c;
+        const float gg = to_f32<TA>(g[i]);
+        dsc = fmaf(gg, d32[i], dsc);
+        dsh += gg;
+        dxs[((size_t)(b * T + T - 1) * L + l) * C + c] += gg * (1.0f + sc);
+    }
+    atomicAdd(dfilm + ((size_t)b * 2 + 0) * C + c, dsc);
+    atomicAdd(dfilm + ((size_t)b * 2 + 1) * C + c, dsh);
+}
+
+// dxs[:, T-1] += src   (src: [B*L, C] TA)
+template <typename TA>
+__global__ void __launch_bounds__(256) add_last_frame_kernel(const TA* __restrict__ src, float* __restrict__ dxs, int B,
+                                                             int T, long long LC) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= (long long)B * LC) return;
+    const long long b = i4 / LC, r = i4 % LC;
+    float v[4], a[4];
+    Vec4<TA>::load(src + i4, v);
+    float* dst = dxs + ((size_t)(b * T + T - 1)) * LC + r;
+    Vec4<float>::load(dst, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] += v[j];
+    Vec4<float>::store(dst, a);
+}
+
+// ---- interprator tail backward (tante.py:191-201).  rt_b = mean_l clampST(w3.h2 + b3) + 1.001; the straight-
+// through clamp has unit gradient everywhere, so d t_l = drt_b / L for every token.
+//   drt_b = gRt[b]/K (R_t = mean_k rt_k, tante.py:159-160) + dcond[b] (FiLM modifier path)
+//   dh2[b,l,j] = drt_b/L * w3[j] * (h2 > 0);  gw3[j] += sum drt_b/L * h2;  gb3 += sum_b drt_b.     grid = B.
+template <typename TA>
+__global__ void __launch_bounds__(256) interp_tail_bwd_kernel(const TA* __restrict__ h2, const float* __restrict__ w3,
+                                                              const float* __restrict__ gRt, float inv_K,
+                                                              const float* __restrict__ dcond, int L, int C4,
+                                                              TA* __restrict__ dh2, float* __restrict__ gw3,
+                                                              float* __restrict__ gb3) {
+    extern __shared__ float sacc[];     // [C4] per-block accumulators of gw3
+    const int b = blockIdx.x;
+    const float drt = (gRt ? gRt[b] * inv_K : 0.f) + (dcond ? dcond[b] : 0.f);
+    const float dt = drt / (float)L;
+    for (int j = threadIdx.x; j < C4; j += blockDim.x) sacc[j] = 0.f;
+    __syncthreads();
+    const long long n = (long long)L * C4;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const int j = (int)(i % C4);
+        const size_t idx = (size_t)b * n + i;
+        const float hv = to_f32<TA>(h2[idx]);
+        dh2[idx] = from_f32<TA>(hv > 0.f ? dt * w3[j] : 0.f);
+        if (hv != 0.f) atomicAdd(&sacc[j], dt * hv);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < C4; j += blockDim.x) atomicAdd(gw3 + j, sacc[j]);
+    if (threadIdx.x == 0) atomicAdd(gb3, drt);
+}
+
+// ---- LayerNorm backward (one warp per row, C == 128*MAXV... C <= 128*MAXV) ------------------------------
+//   xhat = (x-mean)*rstd; gy = dy*gamma; dx_ln = rstd*(gy - mean(gy) - xhat*mean(gy*xhat))
+//   dxs (fp32 gradient stream, in place) += dx_ln; optional TA copy of the updated row (next GEMM operand);
+//   dgamma += dy*xhat, dbeta += dy (per-warp registers -> shared -> atomics).
+template <typename TA, int MAXV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TA* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ gamma, float* __restrict__ dxs,
+                                                     TA* __restrict__ dxb, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, long long rows, int C, float eps) {
+    __shared__ float sg[128 * MAXV * 4], sb[128 * MAXV * 4];
+    const int lane = threadIdx.x % kWarp;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    float ag[MAXV][4], ab[MAXV][4], gm[MAXV][4];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * kWarp + lane) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { ag[i][j] = 0.f; ab[i][j] = 0.f; gm[i][j] = 0.f; }
+        if (c < C) Vec4<float>::load(gamma + c, gm[i]);
+    }
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const long long nwarps = (long long)gridDim.x * blockDim.x / kWarp;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        float xv[MAXV][4], dv[MAXV][4];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (i * kWarp + lane) * 4;
+            if (c < C) {
+                Vec4<float>::load(x + (size_t)r * C + c, xv[i]);
+                Vec4<TA>::load(dy + (size_t)r * C + c, dv[i]);
+                s += (xv[i][0] + xv[i][1]) + (xv[i][2] + xv[i][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { xv[i][j] = 0.f; dv[i][j] = 0.f; }
+            }
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (i * kWarp + lane) * 4;
+            if (c < C) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float d = xv[i][j] - mean; q = fmaf(d, d, q); }
+            }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (i * kWarp + lane) * 4;
+            if (c < C) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (xv[i][j] - mean) * rstd;
+                    const float gy = dv[i][j] * gm[i][j];
+                    s1 += gy;
+                    s2 = fmaf(gy, xh, s2);
+                    ag[i][j] = fmaf(dv[i][j], xh, ag[i][j]);
+                    ab[i][j] += dv[i][j];
+                    xv[i][j] = xh;          // keep xhat
+                    dv[i][j] = gy;          // keep gy
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)C;
+        s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (i * kWarp + lane) * 4;
+            if (c < C) {
+                float o[4];
+                Vec4<float>::load(dxs + (size_t)r * C + c, o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] += rstd * (dv[i][j] - s1 - xv[i][j] * s2);
+                Vec4<float>::store(dxs + (size_t)r * C + c, o);
+                if (dxb) Vec4<TA>::store(dxb + (size_t)r * C + c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * kWarp + lane) * 4;
+        if (c < C) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { atomicAdd(&sg[c + j], ag[i][j]); atomicAdd(&sb[c + j], ab[i][j]); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(dgamma + i, sg[i]); atomicAdd(dbeta + i, sb[i]); }
+}
+
+// ---- axial attention backward (exact SIMT version) ---------------------------------------------------
+// One CTA = one head x G packed sequences (R = G*S <= 64 rows, block-diagonal).  Recomputes P = softmax(QK^T*scale
+// [+causal]) from the saved qkv, then dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dP o P)), dQ = scale dS K,
+// dK = scale dS^T Q.  Token addressing as in the forward (attn_backbone.py:149-162, no rearrange copies).
+template <typename TA, int HD>
+__global__ void __launch_bounds__(128) attention_bwd_kernel(const TA* __restrict__ qkv, const TA* __restrict__ dout,
+                                                            TA* __restrict__ dqkv, long long n_seq, int S, int inner_sz,
+                                                            int n_head, int C, int causal, float scale, int G) {
+    extern __shared__ float smem[];
+    constexpr int P = HD + 1;
+    const int R = G * S;
+    float* sQ = smem;             // [R][P]
+    float* sK = sQ + R * P;
+    float* sV = sK + R * P;
+    float* sO = sV + R * P;       // dO
+    float* sP = sO + R * P;       // [R][S+1]
+    float* sD = sP + R * (S + 1); // [R][S+1]  dP -> dS
+    const int head = blockIdx.y;
+    const long long seq0 = (long long)blockIdx.x * G;
+    const int ld = 3 * C;
+    const int SP = S + 1;
+    // ---- load
+    for (int i = threadIdx.x; i < R * (HD / 4); i += blockDim.x) {
+        const int r = i / (HD / 4), d4 = (i % (HD / 4)) * 4;
+        const long long seq = seq0 + r / S;
+        float q4[4] = {0, 0, 0, 0}, k4[4] = {0, 0, 0, 0}, v4[4] = {0, 0, 0, 0}, o4[4] = {0, 0, 0, 0};
+        if (seq < n_seq) {
+            const long long outer = seq / inner_sz, inner = seq % inner_sz;
+            const size_t tok = (size_t)outer * S * inner_sz + (size_t)(r % S) * inner_sz + inner;
+            const TA* base = qkv + tok * ld + head * HD + d4;
+            Vec4<TA>::load(base, q4);
+            Vec4<TA>::load(base + C, k4);
+            Vec4<TA>::load(base + 2 * C, v4);
+            Vec4<TA>::load(dout + tok * C + head * HD + d4, o4);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sQ[r * P + d4 + j] = q4[j]; sK[r * P + d4 + j] = k4[j]; sV[r * P + d4 + j] = v4[j]; sO[r * P + d4 + j] = o4[j];
+        }
+    }
+    __syncthreads();
+    // ---- scores and dP
+    for (int i = threadIdx.x; i < R * S; i += blockDim.x) {
+        const int r = i / S, j = i % S;
+        const int kr = (r / S) * S + j;
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            s = fmaf(sQ[r * P + d], sK[kr * P + d], s);
+            dp = fmaf(sO[r * P + d], sV[kr * P + d], dp);
+        }
+        s *= scale;
+        if (causal && j > (r % S)) s = -INFINITY;
+        sP[r * SP + j] = s;
+        sD[r * SP + j] = dp;
+    }
+    __syncthreads();
+    // ---- softmax rows + dS
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float m = -INFINITY;
+        for (int j = 0; j < S; ++j) m = fmaxf(m, sP[r * SP + j]);
+        float l = 0.f;
+        for (int j = 0; j < S; ++j) { const float p = expf(sP[r * SP + j] - m); sP[r * SP + j] = p; l += p; }
+        const float inv = 1.0f / l;
+        float dot = 0.f;
+        for (int j = 0; j < S; ++j) { const float p = sP[r * SP + j] * inv; sP[r * SP + j] = p; dot = fmaf(p, sD[r * SP + j], dot); }
+        for (int j = 0; j < S; ++j) sD[r * SP + j] = sP[r * SP + j] * (sD[r * SP + j] - dot) * scale;
+    }
+    __syncthreads();
+    // ---- dQ, dK, dV  (thread per (row, 4 channels))
+    for (int i = threadIdx.x; i < R * (HD / 4); i += blockDim.x) {
+        const int r = i / (HD / 4), d4 = (i % (HD / 4)) * 4;
+        const int g0 = (r / S) * S, p = r % S;
+        float dq[4] = {0, 0, 0, 0}, dk[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
+        for (int j = 0; j < S; ++j) {
+            const float ds_rj = sD[r * SP + j];             // dS[r][j]
+            const float ds_jr = sD[(g0 + j) * SP + p];      // dS[j][r]
+            const float p_jr = sP[(g0 + j) * SP + p];       // P[j][r]
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                dq[e] = fmaf(ds_rj, sK[(g0 + j) * P + d4 + e], dq[e]);
+                dk[e] = fmaf(ds_jr, sQ[(g0 + j) * P + d4 + e], dk[e]);
+                dv[e] = fmaf(p_jr, sO[(g0 + j) * P + d4 + e], dv[e]);
+            }
+        }
+        const long long seq = seq0 + r / S;
+        if (seq < n_seq) {
+            const long long outer = seq / inner_sz, inner = seq % inner_sz;
+            const size_t tok = (size_t)outer * S * inner_sz + (size_t)p * inner_sz + inner;
+            TA* base = dqkv + tok * ld + head * HD + d4;
+            Vec4<TA>::store(base, dq);
+            Vec4<TA>::store(base + C, dk);
+            Vec4<TA>::store(base + 2 * C, dv);
+        }
+    }
+}
+
+// ---- propagator backward (attn_backbone.py:111-119,140-146):  y = x + W2 gelu(W1 x + b1) + b2 along an axis ----
+// In place on the gradient stream: dx = dy + W1^T (gelu'(pre) o (W2^T dy)); weight gradients accumulated in
+// registers across the slabs of a persistent CTA and flushed with atomics.  Slab = one `outer` x 64 columns.
+constexpr int kPropBwdCols = 64;
+__global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __restrict__ xin, float* __restrict__ dy,
+                                                             int S, long long IC, long long n_outer,
+                                                             const float* __restrict__ W1, const float* __restrict__ b1,
+                                                             const float* __restrict__ W2, float* __restrict__ gW1,
+                                                             float* __restrict__ gb1, float* __restrict__ gW2,
+                                                             float* __restrict__ gb2) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int CW = kPropBwdCols;
+    const int S4 = (S + 3) & ~3;
+    float* sx = smem;                 // [S4][CW]  x
+    float* sp = sx + S4 * CW;         // [S4][CW]  pre -> dpre
+    float* sh = sp + S4 * CW;         // [S4][CW]  h
+    float* sd = sh + S4 * CW;         // [S4][CW]  dy
+    float* w1 = sd + S4 * CW;         // [S4][S4]  W1[j][i]
+    float* w1t = w1 + S4 * S4;        // [S4][S4]  W1^T: w1t[i][j] = W1[j][i]
+    float* w2 = w1t + S4 * S4;        // [S4][S4]  W2[j][i]
+    float* sb1 = w2 + S4 * S4;        // [S4]
+    for (int i = threadIdx.x; i < S4 * S4; i += blockDim.x) {
+        const int a = i / S4, b = i % S4;
+        const bool ok = a < S && b < S;
+        w1[i] = ok ? W1[a * S + b] : 0.f;
+        w1t[i] = ok ? W1[b * S + a] : 0.f;
+        w2[i] = ok ? W2[a * S + b] : 0.f;
+    }
+    for (int i = threadIdx.x; i < S4; i += blockDim.x) sb1[i] = i < S ? b1[i] : 0.f;
+    const int cg = threadIdx.x % 16, rg = threadIdx.x / 16;      // 4 columns x 4 rows per thread, 16 row groups
+    // weight-gradient tiles owned by this thread: entries (j = rj*4+a, i = ci*4+b) with (rj, ci) = (tid/16, tid%16)
+    float aw1[4][4], aw2[4][4], ab1[4], ab2[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        ab1[a] = ab2[a] = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) aw1[a][b] = aw2[a][b] = 0.f;
+    }
+    const long long ncb = (IC + CW - 1) / CW;
+    const long long nslab = n_outer * ncb;
+    // out[o][c] = sum_k wt[k][o] * src[k][c]   (4x4 register tile)
+    auto mm = [&](const float* wt, const float* src, int jt, float (&acc)[4][4]) {
+#pragma unroll 4
+        for (int k = 0; k < S4; ++k) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + k * S4 + jt * 4);
+            const float4 v4 = *reinterpret_cast<const float4*>(src + k * CW + cg * 4);
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(w[a], v[c], acc[a][c]);
+        }
+    };
+    for (long long slab = blockIdx.x; slab < nslab; slab += gridDim.x) {
+        const long long outer = slab / ncb;
+        const long long col0 = (slab % ncb) * CW;
+        const int ncol = (int)min((long long)CW, IC - col0);
+        const float* xb = xin + (size_t)outer * S * IC + col0;
+        float* db = dy + (size_t)outer * S * IC + col0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < S4 * (CW / 4); i += blockDim.x) {
+            const int p = i / (CW / 4), c4 = (i % (CW / 4)) * 4;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = xv;
+            if (p < S && c4 < ncol) {
+                xv = *reinterpret_cast<const float4*>(xb + (size_t)p * IC + c4);
+                dv = *reinterpret_cast<const float4*>(db + (size_t)p * IC + c4);
+            }
+            *reinterpret_cast<float4*>(sx + p * CW + c4) = xv;
+            *reinterpret_cast<float4*>(sd + p * CW + c4) = dv;
+        }
+        __syncthreads();
+        // pass A: pre = W1 x + b1, h = gelu(pre)
+        for (int jt = rg; jt < S4 / 4; jt += 16) {
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = sb1[jt * 4 + a];
+            mm(w1t, sx, jt, acc);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                *reinterpret_cast<float4*>(sp + (jt * 4 + a) * CW + cg * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                *reinterpret_cast<float4*>(sh + (jt * 4 + a) * CW + cg * 4) =
+                    make_float4(gelu_erf(acc[a][0]), gelu_erf(acc[a][1]), gelu_erf(acc[a][2]), gelu_erf(acc[a][3]));
+            }
+        }
+        __syncthreads();
+        // pass B: dh[i] = sum_j W2[j][i] dy[j];  dpre = dh * gelu'(pre)   (overwrites sp)
+        for (int it = rg; it < S4 / 4; it += 16) {
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+            mm(w2, sd, it, acc);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                float4* pp = reinterpret_cast<float4*>(sp + (it * 4 + a) * CW + cg * 4);
+                const float4 pr = *pp;
+                *pp = make_float4(acc[a][0] * gelu_erf_grad(pr.x), acc[a][1] * gelu_erf_grad(pr.y),
+                                  acc[a][2] * gelu_erf_grad(pr.z), acc[a][3] * gelu_erf_grad(pr.w));
+            }
+        }
+        __syncthreads();
+        // pass C: dx[i] = dy[i] + sum_j W1[j][i] dpre[j]
+        for (int it = rg; it < S4 / 4; it += 16) {
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+            mm(w1, sp, it, acc);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int p = it * 4 + a;
+                if (p < S && cg * 4 < ncol) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(sd + p * CW + cg * 4);
+                    *reinterpret_cast<float4*>(db + (size_t)p * IC + cg * 4) =
+                        make_float4(d4.x + acc[a][0], d4.y + acc[a][1], d4.z + acc[a][2], d4.w + acc[a][3]);
+                }
+            }
+        }
+        // weight gradients: gW2[j][i] += sum_c dy[j][c] h[i][c];  gW1[j][i] += sum_c dpre[j][c] x[i][c]
+        {
+            const int rj = threadIdx.x / 16, ci = threadIdx.x % 16;
+            if (rj * 4 < S4 && ci * 4 < S4) {
+                for (int c = 0; c < CW; ++c) {
+                    float dyv[4], dpv[4], hv[4], xv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        dyv[a] = sd[(rj * 4 + a) * CW + c];
+                        dpv[a] = sp[(rj * 4 + a) * CW + c];
+                        hv[a] = sh[(ci * 4 + a) * CW + c];
+                        xv[a] = sx[(ci * 4 + a) * CW + c];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            aw2[a][b] = fmaf(dyv[a], hv[b], aw2[a][b]);
+                            aw1[a][b] = fmaf(dpv[a], xv[b], aw1[a][b]);
+                        }
+                    if (ci == 0) {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) { ab2[a] += dyv[a]; ab1[a] += dpv[a]; }
+                    }
+                }
+            }
+        }
+    }
+    {
+        const int rj = threadIdx.x / 16, ci = threadIdx.x % 16;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int j = rj * 4 + a;
+            if (j >= S) continue;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int i = ci * 4 + b;
+                if (i >= S) continue;
+                atomicAdd(gW1 + j * S + i, aw1[a][b]);
+                atomicAdd(gW2 + j * S + i, aw2[a][b]);
+            }
+            if (ci == 0) { atomicAdd(gb1 + j, ab1[a]); atomicAdd(gb2 + j, ab2[a]); }
+        }
+    }
+}
+
+// ---- Taylor head backward (tante.py:156-171 + dec_conv_3, enc_dec_cnn.py:273) ---------------------------
+// frames_i = u0 + sum_k d_k c_ik, c_ik = (i*fi)^k/k!.  One thread per stage-1 row (k0 x k0 x D outputs):
+//   Gk[o]     = sum_{i<=n_b} gframes_i[o] * c_ik          -> Gbuf[k][row][NO]  (fp32; feeds the dW3 / db3 wgrad)
+//   du0[o]    = sum_{i<=n_b} gframes_i[o]                 -> grad_input[b, T-1] (nullable)
+//   dz_k[c]   = gelu_erf'(zpre_k[row][c]) * sum_o Gk[o] W3_k[c][o]   -> dz[k][row][C1]  (TA)
+struct HeadBwdParams {
+    const void* zpre[kMaxOrder];    // [rows][C1] pre-activation of the stage-1 rows (deconv2 output)
+    const float* w3[kMaxOrder];     // packed [C1][NO]
+    void* dz[kMaxOrder];            // [rows][C1]
+    float* G[kMaxOrder];            // [rows][NO]
+    int K;
+    float fi;
+    const float* gframes;           // (B, n_cap, D, H, W)
+    int n_cap;
+    const int* n_arr;               // [B]
+    float* grad_input;              // (B, T, D, H, W) or null
+};
+
+template <typename TA>
+__global__ void __launch_bounds__(128) head_bwd_kernel(HeadBwdParams hp, PatchGeom g, int C1, long long rows_total) {
+    extern __shared__ __align__(16) float smem[];
+    const int NO = g.k0 * g.k0 * g.D;
+    float* sw = smem;                       // [K][C1][NO]
+    for (int k = 0; k < hp.K; ++k)
+        for (int i = threadIdx.x; i < C1 * NO; i += blockDim.x) sw[k * C1 * NO + i] = hp.w3[k][i];
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_total) return;
+    long long tkn = row / g.R1;
+    const int r = (int)(row % g.R1);
+    const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
+    const int hpp = (int)(tkn % g.Hp);
+    const int b = (int)(tkn / g.Hp);
+    int h1, w1;
+    stage1_row_to_hw(g, hpp, wp, r, h1, w1);
+    const int n = min(hp.n_arr[b], hp.n_cap);
+    const size_t HW = (size_t)g.H * g.W;
+    // process the NO outputs in groups of 4 to bound registers; dz accumulates across groups in local memory
+    float dzacc[kMaxOrder > 4 ? 4 : kMaxOrder][64];     // K <= 4, C1 <= 64
+    for (int k = 0; k < hp.K; ++k)
+        for (int c = 0; c < C1; ++c) dzacc[k][c] = 0.f;
+    for (int oo = 0; oo < NO; ++oo) {
+        const int d = oo % g.D;
+        const int cp = (oo / g.D) % g.k0;
+        const int c = oo / (g.D * g.k0);
+        const int hh = h1 * g.k0 + c, ww = w1 * g.k0 + cp;
+        const size_t pix = (size_t)hh * g.W + ww;
+        float Gk[4] = {0.f, 0.f, 0.f, 0.f};
+        float du = 0.f;
+        for (int i = 1; i <= n; ++i) {
+            const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
+            du += gv;
+            const float dt = (float)i * hp.fi;
+            float coef = 1.f;
+            for (int k = 0; k < hp.K; ++k) {
+                coef *= dt / (float)(k + 1);
+                Gk[k] = fmaf(gv, coef, Gk[k]);
+            }
+        }
+        if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
+        for (int k = 0; k < hp.K; ++k) {
+            hp.G[k][(size_t)row * NO + oo] = Gk[k];
+            const float* wk = sw + k * C1 * NO + oo;
+            for (int cc = 0; cc < C1; ++cc) dzacc[k][cc] = fmaf(Gk[k], wk[cc * NO], dzacc[k][cc]);
+        }
+    }
+    for (int k = 0; k < hp.K; ++k) {
+        const TA* zp = reinterpret_cast<const TA*>(hp.zpre[k]) + (size_t)row * C1;
+        TA* dzp = reinterpret_cast<TA*>(hp.dz[k]) + (size_t)row * C1;
+        for (int cc = 0; cc < C1; cc += 4) {
+            float z4[4], o[4];
+            Vec4<TA>::load(zp + cc, z4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = dzacc[k][cc + j] * gelu_erf_grad(z4[j]);
+            Vec4<TA>::store(dzp + cc, o);
+        }
+    }
+}
+
+// ---- first patch conv backward (enc_conv_1, enc_dec_cnn.py:220-221) ----------------------------------------
+// im2col of the input patches (fp32 [rows][K1], K1 = k0*k0*D, column order (c, c', d) as the packed conv weight):
+// the dW1 operand of the generic wgrad kernel.
+__global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
+                                                           float* __restrict__ cols, long long rows_total) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_total) return;
+    long long tkn = row / g.R1;
+    const int r = (int)(row % g.R1);
+    const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
+    const int hpp = (int)(tkn % g.Hp);
+    const long long bt = tkn / g.Hp;
+    int h1, w1;
+    stage1_row_to_hw(g, hpp, wp, r, h1, w1);
+    const size_t HW = (size_t)g.H * g.W;
+    const float* xin = x + (size_t)bt * g.D * HW;
+    const int K1 = g.k0 * g.k0 * g.D;
+    int kk = 0;
+    for (int c = 0; c < g.k0; ++c)
+        for (int cp = 0; cp < g.k0; ++cp)
+            for (int d = 0; d < g.D; ++d, ++kk)
+                cols[(size_t)row * K1 + kk] = xin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)];
+}
+
+// grad_input[patch] += sum_c da1[row][c] * W1[c][kk]   (one thread per stage-1 row; patches do not overlap)
+template <typename TA>
+__global__ void __launch_bounds__(128) conv1_dinput_kernel(const TA* __restrict__ da1, PatchGeom g,
+                                                           const float* __restrict__ w1p /* [C1][K1] */, int C1,
+                                                           float* __restrict__ grad_input, long long rows_total) {
+    extern __shared__ __align__(16) float smem[];
+    const int K1 = g.k0 * g.k0 * g.D;
+    for (int i = threadIdx.x; i < C1 * K1; i += blockDim.x) smem[i] = w1p[i];
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows_total) return;
+    long long tkn = row / g.R1;
+    const int r = (int)(row % g.R1);
+    const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
+    const int hpp = (int)(tkn % g.Hp);
+    const long long bt = tkn / g.Hp;
+    int h1, w1;
+    stage1_row_to_hw(g, hpp, wp, r, h1, w1);
+    const size_t HW = (size_t)g.H * g.W;
+    float* gin = grad_input + (size_t)bt * g.D * HW;
+    float acc[64];       // K1 <= 64
+    for (int kk = 0; kk < K1; ++kk) acc[kk] = 0.f;
+    const TA* dr = da1 + (size_t)row * C1;
+    for (int c = 0; c < C1; c += 4) {
+        float d4[4];
+        Vec4<TA>::load(dr + c, d4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* wr = smem + (c + j) * K1;
+            for (int kk = 0; kk < K1; ++kk) acc[kk] = fmaf(d4[j], wr[kk], acc[kk]);
+        }
+    }
+    int kk = 0;
+    for (int c = 0; c < g.k0; ++c)
+        for (int cp = 0; cp < g.k0; ++cp)
+            for (int d = 0; d < g.D; ++d, ++kk)
+                gin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)] += acc[kk];
+}
+
+// ---- generic weight gradient: C[N][K] += A[M][N]^T * B[M][K]  (split over M, fp32 atomics) -------------------
+// 64 x 64 output tile per CTA, 256 threads x (4 x 4); rows of A and B are contiguous -> coalesced staging.
+template <typename TAa, typename TBb>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const TAa* __restrict__ A, int lda, const TBb* __restrict__ Bm,
+                                                         int ldb, float* __restrict__ Cout, int ldc, long long M, int N,
+                                                         int K, long long m_per_cta) {
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const long long m_begin = (long long)blockIdx.z * m_per_cta;
+    const long long m_end = min(M, m_begin + m_per_cta);
+    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+    const int lr = threadIdx.x / 16, lc = (threadIdx.x % 16) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (long long m0 = m_begin; m0 < m_end; m0 += 16) {
+        const long long m = m0 + lr;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = n0 + lc + e, k = k0 + lc + e;
+            As[lr][lc + e] = (m < m_end && n < N) ? to_f32<TAa>(A[(size_t)m * lda + n]) : 0.f;
+            Bs[lr][lc + e] = (m < m_end && k < K) ? to_f32<TBb>(Bm[(size_t)m * ldb + k]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int mm = 0; mm < 16; ++mm) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[mm][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[mm][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < K) atomicAdd(Cout + (size_t)n * ldc + k, acc[i][j]);
+        }
+    }
+}
+
+template <typename TAa, typename TBb>
+static cudaError_t launch_wgrad_simt(const TAa* A, int lda, const TBb* Bm, int ldb, float* Cout, int ldc, long long M,
+                                     int N, int K, int num_sms, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    const int gx = (N + 63) / 64, gy = (K + 63) / 64;
+    long long splits = std::max<long long>(1, (2LL * num_sms) / (gx * gy));
+    long long per = (M + splits - 1) / splits;
+    per = std::max<long long>(256, (per + 15) / 16 * 16);
+    splits = (M + per - 1) / per;
+    dim3 grid(gx, gy, (unsigned)splits);
+    wgrad_simt_kernel<TAa, TBb><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, Cout, ldc, M, N, K, per);
+    return cudaGetLastError();
+}
+
+// ---- gradient un-packer: packed-layout gradient arena -> flat caller buffer in state_dict layout ------------
+struct UnpackDesc {
+    long long src_off;   // into the gradient arena
+    long long dst_off;   // into the flat gradient buffer
+    long long numel;     // parameter elements
+    int mode;            // PackMode of the gradient entry
+    int d0, d1, k;
+};
+
+__global__ void __launch_bounds__(256) unpack_grads_kernel(const UnpackDesc* __restrict__ descs,
+                                                           const float* __restrict__ garena, float* __restrict__ flat) {
+    const UnpackDesc d = descs[blockIdx.y];
+    const int kk = d.k * d.k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < d.numel;
+         i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the PACKED layout for the permutation modes (a bijection), the parameter for BIAS_REP
+        if (d.mode == PACK_BIAS_REP) {
+            float s = 0.f;
+            for (int r = 0; r < kk; ++r) s += garena[d.src_off + (long long)r * d.d0 + i];
+            flat[d.dst_off + i] = s;
+            continue;
+        }
+        long long s = i;
+        if (d.mode == PACK_CONV) {
+            const int Ci = d.d1;
+            const int ci = (int)(i % Ci);
+            const int dd = (int)((i / Ci) % kk);
+            const int co = (int)(i / ((long long)Ci * kk));
+            s = ((long long)co * Ci + ci) * kk + dd;
+        } else if (d.mode == PACK_DECONV_NK) {
+            const int Ci = d.d0, Co = d.d1;
+            const int ci = (int)(i % Ci);
+            const int n = (int)(i / Ci);
+            const int co = n % Co, dd = n / Co;
+            s = ((long long)ci * Co + co) * kk + dd;
+        } else if (d.mode == PACK_DECONV_KN) {
+            const int Co = d.d1;
+            const int n = (int)(i % ((long long)kk * Co));
+            const int ci = (int)(i / ((long long)kk * Co));
+            const int co = n % Co, dd = n / Co;
+            s = ((long long)ci * Co + co) * kk + dd;
+        }
+        flat[d.dst_off + s] = garena[d.src_off + i];
+    }
+}
+
+// transposed copies of the packed GEMM weights for the input-gradient GEMMs:  dst[k][n] = src[n][k]
+struct TransDesc { long long src_off, dst_off; int rows, cols; };
+__global__ void __launch_bounds__(256) transpose_packed_kernel(const TransDesc* __restrict__ descs, float* __restrict__ arena,
+                                                               __nv_bfloat16* __restrict__ arena_bf16) {
+    const TransDesc d = descs[blockIdx.y];
+    const long long n = (long long)d.rows * d.cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / d.rows), r = (int)(i % d.rows);      // dst index i = k*rows + r
+        const float v = arena[d.src_off + (long long)r * d.cols + k];
+        arena[d.dst_off + i] = v;
+        if (arena_bf16) arena_bf16[d.dst_off + i] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace tante

@@ -363,7 +363,8 @@ static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, cons
 struct TcPlan { int BN, nkb, nstage, nebuf, grid; size_t smem; };
 
 static bool tc_plan(int M, int N, int K, int num_sms, int out_bf16, TcPlan* p) {
-    if (K % kTcBlockK != 0 || K > 512 || N % 64 != 0) return false;
+    if (K % kTcBlockK != 0 || K > 1024 || N % 64 != 0) return false;
+    if ((size_t)(K / kTcBlockK) * 64 * 128 > 128 * 1024) return false;
     const int nkb = K / kTcBlockK;
     int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
     while ((size_t)nkb * BN * 128 > 128 * 1024 && BN > 64) BN /= 2;   // keep the resident slice <= 128 KB

@@ -40,7 +40,7 @@ __device__ __forceinline__ void stage1_row_to_hw(const PatchGeom& g, int hp, int
 // `fcount` (nullable) makes the input a ring buffer of T slots per sample: logical frame t of sample b
 // lives in slot (fcount[b] + t) % T (rollout window, see rollout.cuh).
 // ------------------------------------------------------------------------------------------------
-template <typename TOut>
+template <typename TOut, bool ACT = true /* false: write the pre-activation (training tape) */>
 __global__ void __launch_bounds__(128) patch_embed_conv1_kernel(const float* __restrict__ x,
                                                                 const int* __restrict__ fcount, PatchGeom g,
                                                                 const float* __restrict__ w1p,  // [C1][k0*k0*D]
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128) patch_embed_conv1_kernel(const float* __r
         for (int c4 = 0; c4 < C1 / 4; ++c4) {
             float v4[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v4[j] = gelu_erf_for<TOut>(acc[c4 * 4 + j]);
+            for (int j = 0; j < 4; ++j) v4[j] = ACT ? gelu_erf_for<TOut>(acc[c4 * 4 + j]) : acc[c4 * 4 + j];
             const int chunk = (c4 * 4) / CH, within = (c4 * 4) % CH;
             Vec4<TOut>::store(s_out + (size_t)rr * C1 + ((chunk + rr) % NCH) * CH + within, v4);
         }
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const TIn* __restr
 // (outer, pos, col) lives at (outer*S + pos)*IC + col, IC = inner_sz*C contiguous floats.
 // One CTA = one `outer` x 64 columns; the S x 64 slab and both S x S matrices sit in shared memory.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) propagator_kernel(float* __restrict__ x, int S, long long IC,
+__global__ void __launch_bounds__(256) propagator_kernel(const float* xin, float* x, int S, long long IC,
                                                          const float* __restrict__ W1, const float* __restrict__ b1,
                                                          const float* __restrict__ W2, const float* __restrict__ b2) {
     // Register-tiled: each thread owns a 4 (axis positions) x 4 (columns) output tile; per reduction step it
@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(256) propagator_kernel(float* __restrict__ x, 
     const long long col0 = (long long)blockIdx.y * 128;
     const long long outer = blockIdx.x;
     float* base = x + (size_t)outer * S * IC + col0;
+    const float* ibase = xin + (size_t)outer * S * IC + col0;     // xin == x: in place (inference); else out of place
     for (int i = threadIdx.x; i < S4 * S4; i += blockDim.x) {
         const int ii = i / S4, jj = i % S4;            // sw[ii][jj] = W[jj][ii]
         const bool ok = ii < S && jj < S;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256) propagator_kernel(float* __restrict__ x, 
     for (int i = threadIdx.x; i < S4 * 32; i += blockDim.x) {
         const int p = i / 32, c4 = (i % 32) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < S && c4 < ncol) v = *reinterpret_cast<const float4*>(base + (size_t)p * IC + c4);
+        if (p < S && c4 < ncol) v = *reinterpret_cast<const float4*>(ibase + (size_t)p * IC + c4);
         *reinterpret_cast<float4*>(sv + p * 128 + c4) = v;
     }
     __syncthreads();

@@ -13,7 +13,7 @@ namespace tante {
 __device__ __forceinline__ uint32_t slab_off(int r, int chunk) { return (uint32_t)(r * 256 + (((chunk & 8) | ((chunk ^ r) & 7)) << 4)); }
 
 template <int MB /* S_pad / 16 */>
-__global__ void __launch_bounds__(128) propagator_mma_kernel(float* __restrict__ x, int S, long long IC,
+__global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, float* x, int S, long long IC,
                                                              const float* __restrict__ W1, const float* __restrict__ b1,
                                                              const float* __restrict__ W2, const float* __restrict__ b2) {
     constexpr int SP = MB * 16;
@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(float* __restrict__
     const long long col0 = (long long)blockIdx.y * 128;
     const long long outer = blockIdx.x;
     float* base = x + (size_t)outer * S * IC + col0;
+    const float* ibase = xin + (size_t)outer * S * IC + col0;    // xin == x: in place; else out of place (training)
     const int ncol = (int)min((long long)128, IC - col0);     // multiple of 4
 
     for (int i = tid; i < SP * SP; i += 128) {
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(float* __restrict__
     for (int i = tid; i < SP * 32; i += 128) {
         const int p = i / 32, c4 = (i % 32) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < S && c4 < ncol) v = *reinterpret_cast<const float4*>(base + (size_t)p * IC + c4);
+        if (p < S && c4 < ncol) v = *reinterpret_cast<const float4*>(ibase + (size_t)p * IC + c4);
         uint2 pk;
         pk.x = pack_bf16x2(v.x, v.y);
         pk.y = pack_bf16x2(v.z, v.w);
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(float* __restrict__
                         const int c = warp * 32 + nb * 8 + 2 * t;
                         if (c < ncol) {
                             float2* px = reinterpret_cast<float2*>(base + (size_t)p * IC + c);
-                            float2 xv = *px;
+                            float2 xv = *reinterpret_cast<const float2*>(ibase + (size_t)p * IC + c);
                             xv.x += acc[mb][nb][2 * hh + 0] + bb;
                             xv.y += acc[mb][nb][2 * hh + 1] + bb;
                             *px = xv;
@@ -126,7 +127,7 @@ static void prop_set_attrs() {
     done = true;
 }
 
-static bool launch_propagator_mma(float* x, int S, long long IC, long long outer, const float* W1, const float* b1,
+static bool launch_propagator_mma(const float* xin, float* x, int S, long long IC, long long outer, const float* W1, const float* b1,
                                   const float* W2, const float* b2, cudaStream_t st, cudaError_t* err) {
     if (S < 1 || S > 64 || (IC + 127) / 128 > 65535 || outer > 0x7fffffffLL) return false;
     dim3 grid((unsigned)outer, (unsigned)((IC + 127) / 128));
@@ -135,10 +136,10 @@ static bool launch_propagator_mma(float* x, int S, long long IC, long long outer
     const size_t smem = (size_t)2 * SP * 256 + (size_t)2 * SP * (SP * 2 + 16) + 2 * SP * sizeof(float);
     prop_set_attrs();
     switch (MB) {
-        case 1: propagator_mma_kernel<1><<<grid, 128, smem, st>>>(x, S, IC, W1, b1, W2, b2); break;
-        case 2: propagator_mma_kernel<2><<<grid, 128, smem, st>>>(x, S, IC, W1, b1, W2, b2); break;
-        case 3: propagator_mma_kernel<3><<<grid, 128, smem, st>>>(x, S, IC, W1, b1, W2, b2); break;
-        default: propagator_mma_kernel<4><<<grid, 128, smem, st>>>(x, S, IC, W1, b1, W2, b2); break;
+        case 1: propagator_mma_kernel<1><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
+        case 2: propagator_mma_kernel<2><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
+        case 3: propagator_mma_kernel<3><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
+        default: propagator_mma_kernel<4><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
     }
     *err = cudaGetLastError();
     return true;

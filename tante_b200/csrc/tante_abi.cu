@@ -22,6 +22,8 @@
 #include "head_mma.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
+#include "backward.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace tante;
 
@@ -57,6 +59,9 @@ struct Param {
     int d0 = 0, d1 = 0, k = 1;
     int64_t packed_numel = 0;
     int64_t off = -1;  // arena offset (elements)
+    // gradient arena entry (packed layout, see unpack_grads_kernel) and position in the flat gradient buffer
+    int64_t goff = -1, gnumel = 0, flat_off = 0;
+    int gmode = PACK_COPY, gd0 = 0, gd1 = 0, gk = 1;
 };
 
 struct DevBuf {
@@ -72,6 +77,7 @@ struct DevBuf {
 struct LayerPlan {
     char axis;
     int64_t ln1w, ln1b, inw, inb, outw, outb, ln2w, ln2b, m0w, m0b, m2w, m2b;
+    int64_t inwT, outwT, m0wT, m2wT;      // [K][N] copies for the input-gradient GEMMs
 };
 struct OrderPlan {
     std::vector<LayerPlan> layers;
@@ -79,9 +85,26 @@ struct OrderPlan {
     int64_t decw[3], decb[3];   // packed deconv 1,2 (GEMM NK + replicated bias), deconv 3 (KN + raw bias)
     int64_t intw[3], intb[3];
     int64_t mod[8];       // scale{0.w,0.b,2.w,2.b}, shift{...}
+    int64_t decwT[2], intwT[2];
 };
 
 }  // namespace
+
+// Saved activations of one training forward (one autograd node): everything the backward reads.
+struct OrderTape {
+    DevBuf P[3];                        // fp32 inputs of the H / W / T propagators (P[0] only for order 0)
+    std::vector<DevBuf> X;              // fp32 residual stream: X[0] after the propagators, X[2i+1] mid, X[2i+2] out of layer i
+    std::vector<DevBuf> ln1, qkv, att, ln2, hpre, hact;
+    DevBuf dl, d32, dmod, i1, i2, rt, film, z1pre, z1act, z2pre, z2act;
+};
+struct Tape {
+    DevBuf a1pre, a1act, a2pre, a2act, v, n_arr;
+    std::vector<OrderTape> ord;
+    int B = 0;          // allocated batch
+    int B_used = 0;     // batch of the taped forward
+    float out_T = 1.f;
+    bool valid = false;
+};
 
 struct tante_handle_s {
     tante_config_t cfg{};
@@ -124,6 +147,17 @@ struct tante_handle_s {
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     double prof_flops = 0;
+    // ---- training ----
+    int64_t enc_wT[3] = {0, 0, 0};
+    int64_t zero_off = 0;                      // 4096 zeros (bias of the input-gradient GEMMs)
+    int64_t garena_elems = 0, flat_elems = 0;
+    std::vector<TransDesc> tdescs;
+    std::vector<char> desc_cache;
+    std::map<int64_t, int64_t> goff_of;        // arena offset of a parameter -> gradient arena offset
+    DevBuf garena, tdesc_dev, udesc_dev;
+    std::vector<std::unique_ptr<Tape>> tapes;
+    int bw_batch = 0;
+    DevBuf dxs, dxb, g1, g2, gq, ga1, cols, hz, hG, hz1, hd, hi1, hi2, dfilm, dcond;
 };
 
 namespace {
@@ -141,9 +175,24 @@ int64_t add_param(tante_handle_s* h, const std::string& name, std::vector<int64_
     p.packed_numel = (mode == PACK_BIAS_REP) ? (int64_t)d0 * k * k : p.numel;
     p.off = h->arena_elems;
     h->arena_elems += (p.packed_numel + 63) / 64 * 64;   // 256-byte aligned tensors
+    p.goff = h->garena_elems;
+    p.gnumel = p.packed_numel; p.gmode = mode; p.gd0 = d0; p.gd1 = d1; p.gk = k;
+    h->garena_elems += (p.gnumel + 63) / 64 * 64;
+    p.flat_off = h->flat_elems;
+    h->flat_elems += p.numel;
+    h->goff_of[p.off] = p.goff;
     h->pindex[name] = (int)h->params.size();
     h->params.push_back(p);
     return p.off;
+}
+
+// [cols][rows] copy of the packed [rows][cols] GEMM weight at `src` (filled by transpose_packed_kernel at pack time)
+int64_t add_trans(tante_handle_s* h, int64_t src, int rows, int cols) {
+    TransDesc d;
+    d.src_off = src; d.dst_off = h->arena_elems; d.rows = rows; d.cols = cols;
+    h->arena_elems += ((int64_t)rows * cols + 63) / 64 * 64;
+    h->tdescs.push_back(d);
+    return d.dst_off;
 }
 
 void patch_kernels(int P, int k[3]) {
@@ -189,6 +238,7 @@ void build_plan(tante_handle_s* h) {
         const std::string p = "encoder.enc_conv_" + std::to_string(i + 1) + ".conv.";
         h->enc_w[i] = add_param(h, p + "weight", {ech[i + 1], ech[i], k[i], k[i]}, PACK_CONV, ech[i + 1], ech[i], k[i]);
         h->enc_b[i] = add_param(h, p + "bias", {ech[i + 1]});
+        if (i > 0) h->enc_wT[i] = add_trans(h, h->enc_w[i], ech[i + 1], ech[i] * k[i] * k[i]);
     }
     const char* fn[2] = {"condition_to_scale", "condition_to_shift"};
     auto add_film = [&](const std::string& pre, int64_t* out) {
@@ -225,6 +275,10 @@ void build_plan(tante_handle_s* h) {
             lp.m0b = add_param(h, p + "mlp.0.bias", {C});
             lp.m2w = add_param(h, p + "mlp.2.weight", {C, C});
             lp.m2b = add_param(h, p + "mlp.2.bias", {C});
+            lp.inwT = add_trans(h, lp.inw, 3 * C, C);
+            lp.outwT = add_trans(h, lp.outw, C, C);
+            lp.m0wT = add_trans(h, lp.m0w, C, C);
+            lp.m2wT = add_trans(h, lp.m2w, C, C);
             op.layers.push_back(lp);
         }
         const char* pn[3] = {"vertical", "horizontal", "temporal"};
@@ -242,8 +296,17 @@ void build_plan(tante_handle_s* h) {
             const std::string p = "decoders." + std::to_string(o) + ".dec_conv_" + std::to_string(i + 1) + ".deconv.";
             op.decw[i] = add_param(h, p + "weight", {dch[i], dch[i + 1], kk, kk},
                                    i < 2 ? PACK_DECONV_NK : PACK_DECONV_KN, dch[i], dch[i + 1], kk);
-            if (i < 2) op.decb[i] = add_param(h, p + "bias", {dch[i + 1]}, PACK_BIAS_REP, dch[i + 1], 0, kk);
-            else op.decb[i] = add_param(h, p + "bias", {dch[i + 1]});
+            if (i < 2) {
+                op.decb[i] = add_param(h, p + "bias", {dch[i + 1]}, PACK_BIAS_REP, dch[i + 1], 0, kk);
+                op.decwT[i] = add_trans(h, op.decw[i], kk * kk * dch[i + 1], dch[i]);
+            } else {
+                op.decb[i] = add_param(h, p + "bias", {dch[i + 1]});
+                // its gradient arrives as column sums over the k0*k0*D outputs of the fused head: folded at unpack
+                Param& bp3 = h->params.back();
+                h->garena_elems -= (bp3.gnumel + 63) / 64 * 64;
+                bp3.gnumel = (int64_t)kk * kk * dch[i + 1]; bp3.gmode = PACK_BIAS_REP; bp3.gd0 = dch[i + 1]; bp3.gk = kk;
+                h->garena_elems += (bp3.gnumel + 63) / 64 * 64;
+            }
         }
         if (!c.deg) {
             const std::string p = "interprators." + std::to_string(o) + ".interprete.";
@@ -251,6 +314,7 @@ void build_plan(tante_handle_s* h) {
             for (int i = 0; i < 3; ++i) {
                 op.intw[i] = add_param(h, p + std::to_string(2 * i) + ".weight", {ich[i + 1], ich[i]});
                 op.intb[i] = add_param(h, p + std::to_string(2 * i) + ".bias", {ich[i + 1]});
+                if (i < 2) op.intwT[i] = add_trans(h, op.intw[i], ich[i + 1], ich[i]);
             }
             add_film("modifiers." + std::to_string(o) + ".", op.mod);
         }
@@ -258,9 +322,16 @@ void build_plan(tante_handle_s* h) {
     // derived tensors
     h->film_t_off = h->arena_elems; h->arena_elems += (int64_t)T * 2 * C;
     h->tseq_off = h->arena_elems;   h->arena_elems += 64;
+    h->zero_off = h->arena_elems;   h->arena_elems += 4096;
 }
 
 inline float* AF(tante_handle_s* h, int64_t off) { return reinterpret_cast<float*>(h->arena.p) + off; }
+// gradient-arena pointer of the parameter whose ARENA offset is `off` (plans store arena offsets)
+inline float* GA(tante_handle_s* h, int64_t off) {
+    auto it = h->goff_of.find(off);
+    if (it == h->goff_of.end()) throw Error(TANTE_ERR_STATE, "no gradient entry for arena offset " + std::to_string(off));
+    return reinterpret_cast<float*>(h->garena.p) + it->second;
+}
 
 void dev_alloc(tante_handle_s* h, DevBuf& b, size_t bytes) {
     bytes = (bytes + 255) / 256 * 256;
@@ -371,8 +442,8 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
     h->launches++;
 }
 
-void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=T*/, const OrderPlan& op,
-                       cudaStream_t st) {
+void launch_propagator(tante_handle_s* h, const float* xin, float* x, int B, int axis /*0=H,1=W,2=T*/,
+                       const OrderPlan& op, cudaStream_t st) {
     int S; long long IC, outer;
     const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp, C = h->C;
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
@@ -380,7 +451,7 @@ void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=
     else { S = T; IC = (long long)L * C; outer = B; }
     if (h->cfg.precision == TANTE_PREC_BF16 && S > 8) {    // tiny axes (T = 4) stay on the FFMA kernel
         cudaError_t e = cudaSuccess;
-        if (launch_propagator_mma(x, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]),
+        if (launch_propagator_mma(xin, x, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]),
                                   AF(h, op.prop[axis][3]), st, &e)) {
             CK(e);
             h->launches++;
@@ -392,7 +463,7 @@ void launch_propagator(tante_handle_s* h, float* x, int B, int axis /*0=H,1=W,2=
     dim3 grid((unsigned)outer, (unsigned)((IC + 127) / 128));
     REQUIRE((IC + 127) / 128 <= 65535, "latent too large for the propagator grid");
     const int threads = 32 * std::min(8, S4 / 4);
-    propagator_kernel<<<grid, threads, smem, st>>>(x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+    propagator_kernel<<<grid, threads, smem, st>>>(xin, x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
                                                AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]));
     CK(cudaGetLastError());
     h->launches++;
@@ -480,9 +551,9 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
     for (int o = 0; o < K; ++o) {
         const OrderPlan& op = h->orders[o];
         // --- Attn_Backbone.forward (attn_backbone.py:134-191) ---
-        launch_propagator(h, x, B, 0, op, st);
-        launch_propagator(h, x, B, 1, op, st);
-        launch_propagator(h, x, B, 2, op, st);
+        launch_propagator(h, x, x, B, 0, op, st);
+        launch_propagator(h, x, x, B, 1, op, st);
+        launch_propagator(h, x, x, B, 2, op, st);
         // In tensor mode every LayerNorm except the first one of an order is folded into the epilogue of the
         // residual GEMM that produces its input (EPI_BIAS_RESID_LN): the row is still on chip there.
         constexpr bool kFuseLN = sizeof(TA) == 2;
@@ -567,6 +638,535 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
     }
 }
 
+// ================================================================================================
+// Training: forward with an activation tape + full backward (what torch autograd does for the reference:
+// trainer/r_trainer.py:145-155, trainer/trainer.py:178-193).
+// ================================================================================================
+template <typename TA> inline TA* TP(DevBuf& b) { return reinterpret_cast<TA*>(b.p); }
+inline float* FP(DevBuf& b) { return reinterpret_cast<float*>(b.p); }
+
+inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+template <typename TA, int ACT>
+void launch_act_fwd(tante_handle_s* h, const TA* pre, TA* out, long long n, cudaStream_t st) {
+    act_fwd_kernel<TA, ACT><<<blocks_for(n / 4, 256), 256, 0, st>>>(pre, out, n / 4);
+    CK(cudaGetLastError());
+    h->launches++;
+}
+template <typename TA, int ACT>
+void launch_act_bwd(tante_handle_s* h, TA* g, const TA* pre, long long n, cudaStream_t st) {
+    act_bwd_kernel<TA, ACT><<<blocks_for(n / 4, 256), 256, 0, st>>>(g, pre, n / 4);
+    CK(cudaGetLastError());
+    h->launches++;
+}
+template <typename TA>
+void launch_colsum(tante_handle_s* h, const TA* x, int ld, long long M, int N, float* out, cudaStream_t st) {
+    const unsigned gx = (unsigned)((N + 127) / 128);
+    unsigned gy = (unsigned)std::max<long long>(1, std::min<long long>((M + 255) / 256, (4LL * h->num_sms + gx - 1) / gx));
+    colsum_kernel<TA><<<dim3(gx, gy), 256, 0, st>>>(x, ld, M, N, out);
+    CK(cudaGetLastError());
+    h->launches++;
+}
+// dW[N][K] (+)= A[M][N]^T B[M][K] into the gradient arena
+template <typename TA>
+void wgrad(tante_handle_s* h, const TA* A, int lda, const TA* Bm, int ldb, float* out, long long M, int N, int K,
+           cudaStream_t st) {
+    ProfScope ps(h, st, 2.0 * (double)M * N * K);
+    if constexpr (sizeof(TA) == 2) {
+        if (wgrad_tc_supported(M, N, K, lda, ldb)) {
+            CK(launch_wgrad_tc(A, lda, Bm, ldb, out, K, M, N, K, h->num_sms, st));
+            h->launches++;
+            return;
+        }
+    }
+    CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, K, M, N, K, h->num_sms, st)));
+    h->launches++;
+}
+// dX = dY * W via the transposed packed weight (no bias)
+template <typename TA>
+void gemm_dx(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* out, int ldc, int M, int N, int K, cudaStream_t st) {
+    EpiParams ep; ep.bias = AF(h, h->zero_off);
+    REQUIRE(N <= 4096, "input-gradient GEMM wider than the zero-bias vector");
+    gemm<TA>(h, EPI_BIAS, A, lda, wT_off, out, ldc, sizeof(TA) == 4, M, N, K, ep, st);
+}
+
+template <typename TA>
+void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamma, float* dxs, TA* dxb, float* dg, float* db,
+                   long long rows, cudaStream_t st) {
+    const int C = h->C;
+    const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 8LL * h->num_sms);
+    if (C <= 256) ln_bwd_kernel<TA, 2><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f);
+    else ln_bwd_kernel<TA, 4><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f);
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+template <typename TA>
+void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* dqkv, int B, char axis, cudaStream_t st) {
+    int S, inner; long long nseq;
+    const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp;
+    if (axis == 'T') { S = T; inner = L; nseq = (long long)B * L; }
+    else if (axis == 'H') { S = Hp; inner = Wp; nseq = (long long)B * T * Wp; }
+    else { S = Wp; inner = 1; nseq = (long long)B * T * Hp; }
+    const int G = std::max(1, 64 / S);
+    const int R = G * S;
+    const float scale = 1.0f / sqrtf((float)h->HD);
+    dim3 grid((unsigned)((nseq + G - 1) / G), (unsigned)h->cfg.n_head);
+#define ATTB(HDv)                                                                                              \
+    do {                                                                                                       \
+        const size_t smem = (size_t)(4 * R * (HDv + 1) + 2 * R * (S + 1)) * sizeof(float);                     \
+        attention_bwd_kernel<TA, HDv><<<grid, 128, smem, st>>>(qkv, dout, dqkv, nseq, S, inner, h->cfg.n_head, \
+                                                               h->C, axis == 'T', scale, G);                   \
+    } while (0)
+    if (h->HD == 32) ATTB(32); else if (h->HD == 64) ATTB(64); else ATTB(16);
+#undef ATTB
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B, int axis, const OrderPlan& op, cudaStream_t st) {
+    int S; long long IC, outer;
+    const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp, C = h->C;
+    if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
+    else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
+    else { S = T; IC = (long long)L * C; outer = B; }
+    const int S4 = (S + 3) & ~3;
+    const size_t smem = (size_t)(4 * S4 * kPropBwdCols + 3 * S4 * S4 + S4) * sizeof(float);
+    const long long nslab = outer * ((IC + kPropBwdCols - 1) / kPropBwdCols);
+    const unsigned grid = (unsigned)std::min<long long>(nslab, (S4 <= 32 ? 2LL : 1LL) * h->num_sms);
+    propagator_bwd_kernel<<<grid, 256, smem, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                                 AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
+                                                 GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
+void free_tape(Tape& tp) {
+    DevBuf* bufs[] = {&tp.a1pre, &tp.a1act, &tp.a2pre, &tp.a2act, &tp.v, &tp.n_arr};
+    for (DevBuf* b : bufs) b->free();
+    for (OrderTape& ot : tp.ord) {
+        DevBuf* ob[] = {&ot.P[0], &ot.P[1], &ot.P[2], &ot.dl, &ot.d32, &ot.dmod, &ot.i1, &ot.i2, &ot.rt, &ot.film, &ot.z1pre,
+                        &ot.z1act, &ot.z2pre, &ot.z2act};
+        for (DevBuf* b : ob) b->free();
+        for (auto* v : {&ot.X, &ot.ln1, &ot.qkv, &ot.att, &ot.ln2, &ot.hpre, &ot.hact})
+            for (auto& b : *v) b.free();
+    }
+    tp.ord.clear();
+    tp.B = 0;
+    tp.valid = false;
+}
+
+void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
+    if (tp.B >= B && !tp.ord.empty()) return;
+    const size_t es = h->cfg.precision == TANTE_PREC_BF16 ? 2 : 4;
+    const size_t tokens = (size_t)B * h->T * h->L;
+    const size_t BL = (size_t)B * h->L;
+    const int C = h->C, C1 = h->C1, C2 = h->C2;
+    const PatchGeom& g = h->geom;
+    dev_alloc(h, tp.a1pre, tokens * g.R1 * C1 * es);
+    dev_alloc(h, tp.a1act, tokens * g.R1 * C1 * es);
+    dev_alloc(h, tp.a2pre, tokens * g.R2 * C2 * es);
+    dev_alloc(h, tp.a2act, tokens * g.R2 * C2 * es);
+    dev_alloc(h, tp.v, tokens * C * 4);
+    dev_alloc(h, tp.n_arr, (size_t)B * 4);
+    tp.ord.resize(h->K);
+    for (int o = 0; o < h->K; ++o) {
+        OrderTape& ot = tp.ord[o];
+        const size_t nl = h->orders[o].layers.size();
+        for (int a = (o == 0 ? 0 : 1); a < 3; ++a) dev_alloc(h, ot.P[a], tokens * C * 4);
+        ot.X.resize(2 * nl + 1);
+        for (auto& b : ot.X) dev_alloc(h, b, tokens * C * 4);
+        ot.ln1.resize(nl); ot.qkv.resize(nl); ot.att.resize(nl); ot.ln2.resize(nl); ot.hpre.resize(nl); ot.hact.resize(nl);
+        for (size_t i = 0; i < nl; ++i) {
+            dev_alloc(h, ot.ln1[i], tokens * C * es);
+            dev_alloc(h, ot.qkv[i], tokens * 3 * C * es);
+            dev_alloc(h, ot.att[i], tokens * C * es);
+            dev_alloc(h, ot.ln2[i], tokens * C * es);
+            dev_alloc(h, ot.hpre[i], tokens * C * es);
+            dev_alloc(h, ot.hact[i], tokens * C * es);
+        }
+        dev_alloc(h, ot.dl, BL * C * es);
+        dev_alloc(h, ot.d32, BL * C * 4);
+        if (!h->cfg.deg) {
+            dev_alloc(h, ot.dmod, BL * C * es);
+            dev_alloc(h, ot.i1, BL * (C / 2) * es);
+            dev_alloc(h, ot.i2, BL * (C / 4) * es);
+            dev_alloc(h, ot.rt, (size_t)B * 4);
+            dev_alloc(h, ot.film, (size_t)B * 2 * C * 4);
+        }
+        dev_alloc(h, ot.z1pre, BL * g.R2 * C2 * es);
+        dev_alloc(h, ot.z1act, BL * g.R2 * C2 * es);
+        dev_alloc(h, ot.z2pre, BL * g.R1 * C1 * es);
+        dev_alloc(h, ot.z2act, BL * g.R1 * C1 * es);
+    }
+    tp.B = B;
+}
+
+void backward_alloc(tante_handle_s* h, int B) {
+    if (h->bw_batch >= B) return;
+    const size_t es = h->cfg.precision == TANTE_PREC_BF16 ? 2 : 4;
+    const size_t tokens = (size_t)B * h->T * h->L;
+    const size_t BL = (size_t)B * h->L;
+    const int C = h->C, C1 = h->C1, C2 = h->C2;
+    const PatchGeom& g = h->geom;
+    const int NO = g.k0 * g.k0 * h->D;
+    dev_alloc(h, h->garena, (size_t)h->garena_elems * 4);
+    dev_alloc(h, h->dxs, tokens * C * 4);
+    if (es == 2) dev_alloc(h, h->dxb, tokens * C * es);
+    dev_alloc(h, h->g1, tokens * C * es);
+    dev_alloc(h, h->g2, tokens * C * es);
+    dev_alloc(h, h->gq, tokens * std::max(3 * C, g.R2 * C2) * es);
+    dev_alloc(h, h->ga1, tokens * g.R1 * C1 * es);
+    dev_alloc(h, h->cols, tokens * g.R1 * NO * 4);
+    dev_alloc(h, h->hz, (size_t)h->K * BL * g.R1 * C1 * es);
+    dev_alloc(h, h->hG, (size_t)h->K * BL * g.R1 * NO * 4);
+    dev_alloc(h, h->hz1, BL * g.R2 * C2 * es);
+    dev_alloc(h, h->hd, BL * C * es);
+    dev_alloc(h, h->hi1, BL * (C / 2) * es);
+    dev_alloc(h, h->hi2, BL * (C / 4) * es);
+    dev_alloc(h, h->dfilm, (size_t)std::max(B, h->T) * 2 * C * 4);
+    dev_alloc(h, h->dcond, (size_t)B * 4);
+    if (!h->udesc_dev.p) {
+        std::vector<UnpackDesc> ud;
+        for (const Param& p : h->params) {
+            UnpackDesc d;
+            d.src_off = p.goff; d.dst_off = p.flat_off; d.numel = p.numel; d.mode = p.gmode; d.d0 = p.gd0; d.d1 = p.gd1; d.k = p.gk;
+            ud.push_back(d);
+        }
+        dev_alloc(h, h->udesc_dev, ud.size() * sizeof(UnpackDesc));
+        CK(cudaMemcpy(h->udesc_dev.p, ud.data(), ud.size() * sizeof(UnpackDesc), cudaMemcpyHostToDevice));
+    }
+    h->bw_batch = B;
+}
+
+// One TANTE step in training mode: same arithmetic as run_step, every activation the backward needs is kept.
+template <typename TA>
+void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, float out_T, int n_cap, float* frames,
+                    float* R_t, cudaStream_t st) {
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K;
+    const PatchGeom& g = h->geom;
+    const int tokens = B * T * L;
+    constexpr bool kTensor = sizeof(TA) == 2;
+    // --- encoder ---
+    {
+        const int P = g.k0 * g.k1 * g.k2;
+        int WC = std::max(1, 128 / g.R1);
+        WC = std::min(WC, g.Wp);
+        const int K1 = g.k0 * g.k0 * g.D;
+        REQUIRE(C1 == 64, "patch embed kernel is specialised for embed_dim 256 (C/4 = 64)");
+        const size_t smem = (size_t)(((g.D * P * (P * WC + 1) + 3) & ~3) + C1 * K1 + C1) * sizeof(float) +
+                            (size_t)WC * g.R1 * C1 * sizeof(TA);
+        dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
+        patch_embed_conv1_kernel<TA, false><<<grid, 128, smem, st>>>(input, nullptr, g, AF(h, h->enc_w[0]),
+                                                                     AF(h, h->enc_b[0]), WC, TP<TA>(tp.a1pre));
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), (long long)tokens * g.R1 * C1, st);
+        EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
+        gemm<TA>(h, EPI_BIAS, TP<TA>(tp.a1act), g.k1 * g.k1 * C1, h->enc_w[1], tp.a2pre.p, C2, false, tokens * g.R2, C2,
+                 g.k1 * g.k1 * C1, e2, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a2pre), TP<TA>(tp.a2act), (long long)tokens * g.R2 * C2, st);
+        EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
+        gemm<TA>(h, EPI_BIAS, TP<TA>(tp.a2act), g.k2 * g.k2 * C2, h->enc_w[2], tp.v.p, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
+        embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(
+            FP(tp.v), AF(h, h->film_t_off), AF(h, h->s_emb), AF(h, h->t_emb), FP(tp.ord[0].P[0]), tokens, T, L, C);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    float* rt = reinterpret_cast<float*>(h->rt.p);
+    for (int o = 0; o < K; ++o) {
+        const OrderPlan& op = h->orders[o];
+        OrderTape& ot = tp.ord[o];
+        const float* pin = o == 0 ? FP(ot.P[0]) : FP(tp.ord[o - 1].X.back());
+        launch_propagator(h, pin, FP(ot.P[1]), B, 0, op, st);
+        launch_propagator(h, FP(ot.P[1]), FP(ot.P[2]), B, 1, op, st);
+        launch_propagator(h, FP(ot.P[2]), FP(ot.X[0]), B, 2, op, st);
+        bool ln_ready = false;
+        const size_t nl = op.layers.size();
+        for (size_t li = 0; li < nl; ++li) {
+            const LayerPlan& lp = op.layers[li];
+            float* x_in = FP(ot.X[2 * li]);
+            float* x_mid = FP(ot.X[2 * li + 1]);
+            float* x_out = FP(ot.X[2 * li + 2]);
+            if (!ln_ready) launch_layernorm<TA>(h, x_in, lp.ln1w, lp.ln1b, TP<TA>(ot.ln1[li]), tokens, st);
+            EpiParams eq; eq.bias = AF(h, lp.inb);
+            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln1[li]), C, lp.inw, ot.qkv[li].p, 3 * C, false, tokens, 3 * C, C, eq, st);
+            launch_attention<TA>(h, TP<TA>(ot.qkv[li]), TP<TA>(ot.att[li]), B, lp.axis, st);
+            EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x_in; eo.ldr = C;
+            if (kTensor) {
+                eo.ln_gamma = AF(h, lp.ln2w); eo.ln_beta = AF(h, lp.ln2b); eo.ln_out = ot.ln2[li].p;
+                gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.att[li]), C, lp.outw, x_mid, C, true, tokens, C, C, eo, st);
+            } else {
+                gemm<TA>(h, EPI_BIAS_RESID, TP<TA>(ot.att[li]), C, lp.outw, x_mid, C, true, tokens, C, C, eo, st);
+                launch_layernorm<TA>(h, x_mid, lp.ln2w, lp.ln2b, TP<TA>(ot.ln2[li]), tokens, st);
+            }
+            EpiParams e0; e0.bias = AF(h, lp.m0b);
+            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln2[li]), C, lp.m0w, ot.hpre[li].p, C, false, tokens, C, C, e0, st);
+            launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * C, st);
+            EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x_mid; e2.ldr = C;
+            if (kTensor && li + 1 < nl) {
+                const LayerPlan& nx = op.layers[li + 1];
+                e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ot.ln1[li + 1].p;
+                gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.hact[li]), C, lp.m2w, x_out, C, true, tokens, C, C, e2, st);
+                ln_ready = true;
+            } else {
+                gemm<TA>(h, EPI_BIAS_RESID, TP<TA>(ot.hact[li]), C, lp.m2w, x_out, C, true, tokens, C, C, e2, st);
+                ln_ready = false;
+            }
+        }
+        // --- head of order o ---
+        const long long LC = (long long)L * C;
+        const long long tot = (long long)B * LC;
+        const int eb = (int)((tot / 4 + 255) / 256);
+        last_frame_kernel<TA><<<eb, 256, 0, st>>>(FP(ot.X.back()), TP<TA>(ot.dl), FP(ot.d32), B, T, LC);
+        CK(cudaGetLastError());
+        h->launches++;
+        TA* dmod = TP<TA>(ot.dl);
+        if (!h->cfg.deg) {
+            EpiParams ei; ei.bias = AF(h, op.intb[0]);
+            gemm<TA>(h, EPI_BIAS_RELU, TP<TA>(ot.dl), C, op.intw[0], ot.i1.p, C / 2, false, B * L, C / 2, C, ei, st);
+            ei.bias = AF(h, op.intb[1]);
+            gemm<TA>(h, EPI_BIAS_RELU, TP<TA>(ot.i1), C / 2, op.intw[1], ot.i2.p, C / 4, false, B * L, C / 4, C / 2, ei, st);
+            rt_reduce_kernel<TA><<<B, 256, 0, st>>>(TP<TA>(ot.i2), AF(h, op.intw[2]), AF(h, op.intb[2]), L, C / 4, out_T,
+                                                    rt + (size_t)o * h->max_batch);
+            CK(cudaGetLastError());
+            h->launches++;
+            CK(cudaMemcpyAsync(ot.rt.p, rt + (size_t)o * h->max_batch, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+            film_params_kernel<<<B, 256, C * sizeof(float), st>>>(
+                FP(ot.rt), 1.0f, AF(h, op.mod[0]), AF(h, op.mod[1]), AF(h, op.mod[2]), AF(h, op.mod[3]), AF(h, op.mod[4]),
+                AF(h, op.mod[5]), AF(h, op.mod[6]), AF(h, op.mod[7]), C, FP(ot.film));
+            CK(cudaGetLastError());
+            h->launches++;
+            film_apply_kernel<TA><<<eb, 256, 0, st>>>(FP(ot.d32), FP(ot.film), TP<TA>(ot.dmod), LC, C, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            dmod = TP<TA>(ot.dmod);
+        }
+        EpiParams ed; ed.bias = AF(h, op.decb[0]);
+        gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], ot.z1pre.p, g.k2 * g.k2 * C2, false, B * L, g.k2 * g.k2 * C2, C, ed, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z1pre), TP<TA>(ot.z1act), (long long)B * L * g.R2 * C2, st);
+        ed.bias = AF(h, op.decb[1]);
+        gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z1act), C2, op.decw[1], ot.z2pre.p, g.k1 * g.k1 * C1, false, B * L * g.R2,
+                 g.k1 * g.k1 * C1, C2, ed, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z2pre), TP<TA>(ot.z2act), (long long)B * L * g.R1 * C1, st);
+    }
+    RolloutState rs{};
+    select_step_kernel<<<(B + 127) / 128, 128, 0, st>>>(rt, K, h->max_batch, B, h->cfg.deg, h->cfg.output_length, 0, n_cap,
+                                                        R_t, reinterpret_cast<int*>(h->nbuf.p), rs, 0);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaMemcpyAsync(tp.n_arr.p, h->nbuf.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    // fused Taylor head on the kept stage-1 activations
+    {
+        HeadParams hp{};
+        for (int k = 0; k < K; ++k) {
+            hp.z[k] = tp.ord[k].z2act.p;
+            hp.w3[k] = AF(h, h->orders[k].decw[2]);
+            hp.b3[k] = AF(h, h->orders[k].decb[2]);
+        }
+        hp.K = K; hp.fi = h->cfg.frame_interval; hp.u_ring = input; hp.fcount = nullptr;
+        hp.n_arr = reinterpret_cast<int*>(h->nbuf.p); hp.frames = frames; hp.n_cap = n_cap;
+        const long long rows = (long long)B * L * g.R1;
+        bool done = false;
+        if (kTensor) {
+            cudaError_t e = cudaSuccess;
+            if (launch_head_mma(hp, g, C1, rows, B, st, &e)) { CK(e); done = true; }
+        }
+        if (!done) {
+            const int NO = g.k0 * g.k0 * h->D;
+            const size_t smem = (size_t)(K * C1 * NO + K * h->D) * sizeof(float);
+            const int blocks = (int)((rows + 127) / 128);
+#define HEAD(KO) taylor_head_kernel<TA, 8, KO><<<blocks, 128, smem, st>>>(hp, g, C1, rows, B)
+            switch (K) { case 1: HEAD(1); break; case 2: HEAD(2); break; case 3: HEAD(3); break; default: HEAD(4); break; }
+#undef HEAD
+            CK(cudaGetLastError());
+        }
+        h->launches++;
+    }
+    tp.out_T = out_T;
+    tp.B_used = B;
+    tp.valid = true;
+}
+
+// Backward of one taped step.  gframes: f32 (B, n_g, D, H, W) gradient of the emitted frames; gRt: f32 [B] or null;
+// grad_input: f32 (B, T, D, H, W) or null (written, not accumulated); flat: f32 [sum numel] parameter gradients in
+// tante_param order (written, not accumulated).
+template <typename TA>
+void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* gframes, int n_g, const float* gRt,
+                  float* grad_input, float* flat, cudaStream_t st) {
+    const int B = tp.B_used;
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K, D = h->D;
+    const PatchGeom& g = h->geom;
+    const int tokens = B * T * L;
+    const int BL = B * L;
+    const int NO = g.k0 * g.k0 * D;
+    constexpr bool kTensor = sizeof(TA) == 2;
+    const long long rows1 = (long long)BL * g.R1;       // stage-1 rows of the last frame (head)
+    float* dxs = FP(h->dxs);
+    TA* dxb = kTensor ? TP<TA>(h->dxb) : reinterpret_cast<TA*>(dxs);
+    TA* g1 = TP<TA>(h->g1);
+    TA* g2 = TP<TA>(h->g2);
+    TA* gq = TP<TA>(h->gq);
+    CK(cudaMemsetAsync(h->garena.p, 0, (size_t)h->garena_elems * 4, st));
+    CK(cudaMemsetAsync(dxs, 0, (size_t)tokens * C * 4, st));
+    const size_t in_elems = (size_t)B * T * D * h->cfg.H * h->cfg.W;
+    if (grad_input) CK(cudaMemsetAsync(grad_input, 0, in_elems * 4, st));
+
+    // ---- Taylor head: all orders in one pass over the frame gradients ----
+    {
+        HeadBwdParams hp{};
+        for (int k = 0; k < K; ++k) {
+            hp.zpre[k] = tp.ord[k].z2pre.p;
+            hp.w3[k] = AF(h, h->orders[k].decw[2]);
+            hp.dz[k] = TP<TA>(h->hz) + (size_t)k * rows1 * C1;
+            hp.G[k] = FP(h->hG) + (size_t)k * rows1 * NO;
+        }
+        hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
+        hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); hp.grad_input = grad_input;
+        const size_t smem = (size_t)K * C1 * NO * sizeof(float);
+        head_bwd_kernel<TA><<<blocks_for(rows1, 128), 128, smem, st>>>(hp, g, C1, rows1);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    for (int o = K - 1; o >= 0; --o) {
+        const OrderPlan& op = h->orders[o];
+        OrderTape& ot = tp.ord[o];
+        TA* dz = TP<TA>(h->hz) + (size_t)o * rows1 * C1;
+        float* G = FP(h->hG) + (size_t)o * rows1 * NO;
+        // dec_conv_3: d_k = z2act * W3 + b3
+        CK((launch_wgrad_simt<TA, float>(TP<TA>(ot.z2act), C1, G, NO, GA(h, op.decw[2]), NO, rows1, C1, NO, h->num_sms, st)));
+        h->launches++;
+        launch_colsum<float>(h, G, NO, rows1, NO, GA(h, op.decb[2]), st);
+        // dec_conv_2: z2pre[M2, N2] = z1act[M2, C2] * Wd2^T + b
+        const int M2 = BL * g.R2, N2 = g.k1 * g.k1 * C1;
+        wgrad<TA>(h, dz, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st);
+        launch_colsum<TA>(h, dz, N2, M2, N2, GA(h, op.decb[1]), st);
+        TA* dz1 = TP<TA>(h->hz1);
+        gemm_dx<TA>(h, dz, N2, op.decwT[1], dz1, C2, M2, C2, N2, st);
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, dz1, TP<TA>(ot.z1pre), (long long)M2 * C2, st);
+        // dec_conv_1: z1pre[BL, N1] = dmod[BL, C] * Wd1^T + b
+        const int N1 = g.k2 * g.k2 * C2;
+        TA* dmod = h->cfg.deg ? TP<TA>(ot.dl) : TP<TA>(ot.dmod);
+        wgrad<TA>(h, dz1, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st);
+        launch_colsum<TA>(h, dz1, N1, BL, N1, GA(h, op.decb[0]), st);
+        TA* hd = TP<TA>(h->hd);
+        gemm_dx<TA>(h, dz1, N1, op.decwT[0], hd, C, BL, C, N1, st);
+        if (!h->cfg.deg) {
+            // FiLM modifier (tante.py:151) and interprator (tante.py:149)
+            CK(cudaMemsetAsync(h->dfilm.p, 0, (size_t)B * 2 * C * 4, st));
+            {
+                const int chunks = std::max(1, std::min(L, (2 * h->num_sms + B - 1) / B));
+                film_apply_bwd_kernel<TA><<<dim3(B, chunks), C, 0, st>>>(hd, FP(ot.d32), FP(ot.film), dxs, FP(h->dfilm), T, L, C);
+                CK(cudaGetLastError());
+                h->launches++;
+            }
+            film_bwd_kernel<<<B, 256, 3 * C * sizeof(float), st>>>(
+                FP(ot.rt), FP(h->dfilm), AF(h, op.mod[0]), AF(h, op.mod[1]), AF(h, op.mod[2]), AF(h, op.mod[4]),
+                AF(h, op.mod[5]), AF(h, op.mod[6]), GA(h, op.mod[0]), GA(h, op.mod[1]), GA(h, op.mod[2]), GA(h, op.mod[3]),
+                GA(h, op.mod[4]), GA(h, op.mod[5]), GA(h, op.mod[6]), GA(h, op.mod[7]), C, FP(h->dcond));
+            CK(cudaGetLastError());
+            h->launches++;
+            TA* hi2 = TP<TA>(h->hi2);
+            TA* hi1 = TP<TA>(h->hi1);
+            interp_tail_bwd_kernel<TA><<<B, 256, (C / 4) * sizeof(float), st>>>(
+                TP<TA>(ot.i2), AF(h, op.intw[2]), gRt, 1.0f / (float)K, FP(h->dcond), L, C / 4, hi2, GA(h, op.intw[2]),
+                GA(h, op.intb[2]));
+            CK(cudaGetLastError());
+            h->launches++;
+            wgrad<TA>(h, hi2, C / 4, TP<TA>(ot.i1), C / 2, GA(h, op.intw[1]), BL, C / 4, C / 2, st);
+            launch_colsum<TA>(h, hi2, C / 4, BL, C / 4, GA(h, op.intb[1]), st);
+            gemm_dx<TA>(h, hi2, C / 4, op.intwT[1], hi1, C / 2, BL, C / 2, C / 4, st);
+            launch_act_bwd<TA, ACT_RELU>(h, hi1, TP<TA>(ot.i1), (long long)BL * (C / 2), st);
+            wgrad<TA>(h, hi1, C / 2, TP<TA>(ot.dl), C, GA(h, op.intw[0]), BL, C / 2, C, st);
+            launch_colsum<TA>(h, hi1, C / 2, BL, C / 2, GA(h, op.intb[0]), st);
+            gemm_dx<TA>(h, hi1, C / 2, op.intwT[0], hd, C, BL, C, C / 2, st);
+        }
+        add_last_frame_kernel<TA><<<blocks_for((long long)BL * C / 4, 256), 256, 0, st>>>(hd, dxs, B, T, (long long)L * C);
+        CK(cudaGetLastError());
+        h->launches++;
+        // ---- backbone of order o ----
+        if (kTensor) {
+            convert_kernel<TA><<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(dxs, dxb, (long long)tokens * C / 4);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+        TA* dxb_out = kTensor ? dxb : nullptr;
+        for (int li = (int)op.layers.size() - 1; li >= 0; --li) {
+            const LayerPlan& lp = op.layers[li];
+            const float* x_in = FP(ot.X[2 * li]);
+            const float* x_mid = FP(ot.X[2 * li + 1]);
+            // MLP half: x_out = x_mid + W2 gelu_tanh(W0 ln2(x_mid) + b0) + b2
+            launch_colsum<TA>(h, dxb, C, tokens, C, GA(h, lp.m2b), st);
+            wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), C, GA(h, lp.m2w), tokens, C, C, st);
+            gemm_dx<TA>(h, dxb, C, lp.m2wT, g1, C, tokens, C, C, st);
+            launch_act_bwd<TA, ACT_GELU_TANH>(h, g1, TP<TA>(ot.hpre[li]), (long long)tokens * C, st);
+            launch_colsum<TA>(h, g1, C, tokens, C, GA(h, lp.m0b), st);
+            wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st);
+            gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
+            launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st);
+            // attention half: x_mid = x_in + Wo att(ln1(x_in)) + bo
+            launch_colsum<TA>(h, dxb, C, tokens, C, GA(h, lp.outb), st);
+            wgrad<TA>(h, dxb, C, TP<TA>(ot.att[li]), C, GA(h, lp.outw), tokens, C, C, st);
+            gemm_dx<TA>(h, dxb, C, lp.outwT, g2, C, tokens, C, C, st);
+            launch_attention_bwd<TA>(h, TP<TA>(ot.qkv[li]), g2, gq, B, lp.axis, st);
+            launch_colsum<TA>(h, gq, 3 * C, tokens, 3 * C, GA(h, lp.inb), st);
+            wgrad<TA>(h, gq, 3 * C, TP<TA>(ot.ln1[li]), C, GA(h, lp.inw), tokens, 3 * C, C, st);
+            gemm_dx<TA>(h, gq, 3 * C, lp.inwT, g2, C, tokens, C, 3 * C, st);
+            launch_ln_bwd<TA>(h, g2, x_in, lp.ln1w, dxs, dxb_out, GA(h, lp.ln1w), GA(h, lp.ln1b), tokens, st);
+        }
+        const float* pin = o == 0 ? FP(ot.P[0]) : FP(tp.ord[o - 1].X.back());
+        launch_propagator_bwd(h, FP(ot.P[2]), dxs, B, 2, op, st);
+        launch_propagator_bwd(h, FP(ot.P[1]), dxs, B, 1, op, st);
+        launch_propagator_bwd(h, pin, dxs, B, 0, op, st);
+    }
+    // ---- embeddings + t_encode FiLM (tante.py:136-141) ----
+    CK(cudaMemsetAsync(h->dfilm.p, 0, (size_t)T * 2 * C * 4, st));
+    embed_bwd_kernel<TA><<<L, 256, 0, st>>>(dxs, FP(tp.v), AF(h, h->film_t_off), g2, FP(h->dfilm), GA(h, h->s_emb),
+                                          GA(h, h->t_emb), B, T, L, C);
+    CK(cudaGetLastError());
+    h->launches++;
+    film_bwd_kernel<<<T, 256, 3 * C * sizeof(float), st>>>(
+        AF(h, h->tseq_off), FP(h->dfilm), AF(h, h->tenc[0]), AF(h, h->tenc[1]), AF(h, h->tenc[2]), AF(h, h->tenc[4]),
+        AF(h, h->tenc[5]), AF(h, h->tenc[6]), GA(h, h->tenc[0]), GA(h, h->tenc[1]), GA(h, h->tenc[2]), GA(h, h->tenc[3]),
+        GA(h, h->tenc[4]), GA(h, h->tenc[5]), GA(h, h->tenc[6]), GA(h, h->tenc[7]), C, nullptr);
+    CK(cudaGetLastError());
+    h->launches++;
+    // ---- encoder (enc_dec_cnn.py:217-229) ----
+    const int K3 = g.k2 * g.k2 * C2, K2 = g.k1 * g.k1 * C1;
+    const int M2 = tokens * g.R2;
+    const long long rows_in = (long long)tokens * g.R1;
+    launch_colsum<TA>(h, g2, C, tokens, C, GA(h, h->enc_b[2]), st);
+    wgrad<TA>(h, g2, C, TP<TA>(tp.a2act), K3, GA(h, h->enc_w[2]), tokens, C, K3, st);
+    gemm_dx<TA>(h, g2, C, h->enc_wT[2], gq, K3, tokens, K3, C, st);
+    launch_act_bwd<TA, ACT_GELU_ERF>(h, gq, TP<TA>(tp.a2pre), (long long)M2 * C2, st);
+    launch_colsum<TA>(h, gq, C2, M2, C2, GA(h, h->enc_b[1]), st);
+    wgrad<TA>(h, gq, C2, TP<TA>(tp.a1act), K2, GA(h, h->enc_w[1]), M2, C2, K2, st);
+    TA* ga1 = TP<TA>(h->ga1);
+    gemm_dx<TA>(h, gq, C2, h->enc_wT[1], ga1, K2, M2, K2, C2, st);
+    launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), rows_in * C1, st);
+    launch_colsum<TA>(h, ga1, C1, rows_in, C1, GA(h, h->enc_b[0]), st);
+    conv1_im2col_kernel<<<blocks_for(rows_in, 128), 128, 0, st>>>(input, g, FP(h->cols), rows_in);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK((launch_wgrad_simt<TA, float>(ga1, C1, FP(h->cols), NO, GA(h, h->enc_w[0]), NO, rows_in, C1, NO, h->num_sms, st)));
+    h->launches++;
+    if (grad_input) {
+        conv1_dinput_kernel<TA><<<blocks_for(rows_in, 128), 128, (size_t)C1 * NO * sizeof(float), st>>>(
+            ga1, g, AF(h, h->enc_w[0]), C1, grad_input, rows_in);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    // ---- packed gradient arena -> flat state_dict-layout buffer ----
+    {
+        int64_t max_numel = 0;
+        for (const Param& p : h->params) max_numel = std::max(max_numel, p.numel);
+        dim3 grid((unsigned)std::min<int64_t>((max_numel + 255) / 256, 64), (unsigned)h->params.size());
+        unpack_grads_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const UnpackDesc*>(h->udesc_dev.p), FP(h->garena), flat);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+}
+
 void ensure_ready(tante_handle_s* h, int B) {
     if (!h->packed) throw Error(TANTE_ERR_STATE, "parameters not packed: call tante_bind_param for every parameter, then tante_pack_params");
     if (B < 1 || B > h->max_batch) throw Error(TANTE_ERR_STATE, "batch exceeds tante_reserve(max_batch)");
@@ -583,7 +1183,17 @@ void set_smem_attrs() {
     HEADATTR(float, 1); HEADATTR(float, 2); HEADATTR(float, 3); HEADATTR(float, 4);
     HEADATTR(__nv_bfloat16, 1); HEADATTR(__nv_bfloat16, 2); HEADATTR(__nv_bfloat16, 3); HEADATTR(__nv_bfloat16, 4);
 #undef HEADATTR
+    CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(propagator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(head_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    CK(cudaFuncSetAttribute(head_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+#define ATTBATTR(TA, HDv) CK(cudaFuncSetAttribute(attention_bwd_kernel<TA, HDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024))
+    ATTBATTR(float, 16); ATTBATTR(float, 32); ATTBATTR(float, 64);
+    ATTBATTR(__nv_bfloat16, 16); ATTBATTR(__nv_bfloat16, 32); ATTBATTR(__nv_bfloat16, 64);
+#undef ATTBATTR
     CK(tc_set_attrs());
+    CK(wg_set_attrs());
     att_set_attrs();
     prop_set_attrs();
     done = true;
@@ -691,6 +1301,10 @@ int tante_destroy(tante_handle_t h) {
                           &h->state, &h->dbg_in};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
+        DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
+                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond};
+        for (DevBuf* b : tb) b->free();
+        for (auto& tp : h->tapes) free_tape(*tp);
         if (h->h_flag) cudaFreeHost(h->h_flag);
         for (auto& e : h->ev) if (e) cudaEventDestroy(e);
         for (auto& e : h->prof_ev) cudaEventDestroy(e);
@@ -744,14 +1358,36 @@ int tante_pack_params(tante_handle_t h, void* stream) {
             max_numel = std::max(max_numel, p.packed_numel);
         }
         dev_alloc(h, h->descs, descs.size() * sizeof(PackDesc));
-        // pageable H2D copy of a small table: synchronous w.r.t. the host buffer, ordered on `st`
-        CK(cudaMemcpyAsync(h->descs.p, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        // the descriptor tables only change when a parameter is re-bound: upload them once (pageable H2D copy of a
+        // small table: synchronous w.r.t. the host buffer, ordered on `st`), so that the per-optimizer-step repack
+        // of a training loop is two kernel launches and no host sync
+        const bool first = h->desc_cache.size() != descs.size() * sizeof(PackDesc) ||
+                           memcmp(h->desc_cache.data(), descs.data(), h->desc_cache.size()) != 0;
+        if (first) {
+            CK(cudaMemcpyAsync(h->descs.p, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            h->desc_cache.assign(reinterpret_cast<const char*>(descs.data()),
+                                 reinterpret_cast<const char*>(descs.data()) + descs.size() * sizeof(PackDesc));
+            if (!h->tdescs.empty()) {
+                dev_alloc(h, h->tdesc_dev, h->tdescs.size() * sizeof(TransDesc));
+                CK(cudaMemcpyAsync(h->tdesc_dev.p, h->tdescs.data(), h->tdescs.size() * sizeof(TransDesc),
+                                   cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));
+            }
+            CK(cudaMemsetAsync(AF(h, h->zero_off), 0, 4096 * sizeof(float), st));
+        }
         dim3 grid((unsigned)std::min<int64_t>((max_numel + 255) / 256, 64), (unsigned)descs.size());
         pack_params_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const PackDesc*>(h->descs.p), AF(h, 0),
                                                  reinterpret_cast<__nv_bfloat16*>(h->arena_bf16.p));
         CK(cudaGetLastError());
         h->launches++;
+        if (!h->tdescs.empty()) {
+            dim3 tgrid(64, (unsigned)h->tdescs.size());
+            transpose_packed_kernel<<<tgrid, 256, 0, st>>>(reinterpret_cast<const TransDesc*>(h->tdesc_dev.p), AF(h, 0),
+                                                           reinterpret_cast<__nv_bfloat16*>(h->arena_bf16.p));
+            CK(cudaGetLastError());
+            h->launches++;
+        }
         // derived: t_seq (tante.py:279-285: [-(T-2)..-1,-0,0]*fi) and the t_encode FiLM table
         std::vector<float> tseq(64, 0.f);
         {
@@ -761,8 +1397,10 @@ int tante_pack_params(tante_handle_t h, void* stream) {
             std::reverse(s.begin(), s.end());
             for (int i = 0; i < h->T; ++i) tseq[i] = s[i];
         }
-        CK(cudaMemcpyAsync(AF(h, h->tseq_off), tseq.data(), 64 * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        if (first) {
+            CK(cudaMemcpyAsync(AF(h, h->tseq_off), tseq.data(), 64 * sizeof(float), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
         film_params_kernel<<<h->T, 256, h->C * sizeof(float), st>>>(
             AF(h, h->tseq_off), 1.0f, AF(h, h->tenc[0]), AF(h, h->tenc[1]), AF(h, h->tenc[2]), AF(h, h->tenc[3]),
             AF(h, h->tenc[4]), AF(h, h->tenc[5]), AF(h, h->tenc[6]), AF(h, h->tenc[7]), h->C, AF(h, h->film_t_off));
@@ -775,8 +1413,9 @@ int tante_pack_params(tante_handle_t h, void* stream) {
 int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t training) {
     return guarded([&] {
         REQUIRE(h && max_batch >= 1, "bad argument");
-        (void)training;
+        REQUIRE(training >= 0 && training <= 64, "training (tape slots) must be in 0..64");
         CK(cudaSetDevice(h->device));
+        while ((int)h->tapes.size() < training) h->tapes.emplace_back(new Tape());
         if (max_batch <= h->max_batch && max_roll <= h->max_roll) return;
         destroy_graphs(h);        // workspace pointers are baked into captured kernel arguments
         max_batch = std::max(max_batch, h->max_batch);
@@ -918,6 +1557,79 @@ int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_ro
         if (steps_out) CK(cudaMemcpyAsync(steps_out, rs.steps, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
         h->last_B = B;
         if (sync) CK(cudaStreamSynchronize(st));
+    });
+}
+
+int64_t tante_grad_numel(tante_handle_t h) { return h ? h->flat_elems : -1; }
+int64_t tante_param_grad_offset(tante_handle_t h, int32_t i) {
+    if (!h || i < 0 || i >= (int32_t)h->params.size()) return -1;
+    return h->params[i].flat_off;
+}
+
+int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int32_t B, float out_T, int32_t n_cap,
+                        float* frames, float* R_t, int32_t* n_host, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && input && frames, "null argument");
+        REQUIRE(n_cap >= 1, "n_cap must be >= 1");
+        REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
+        REQUIRE(h->T <= 16, "training supports in_T <= 16");
+        CK(cudaSetDevice(h->device));
+        ensure_ready(h, B);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        Tape& tp = *h->tapes[slot];
+        tape_alloc(h, tp, B);
+        if (h->cfg.precision == TANTE_PREC_FP32) run_step_train<float>(h, tp, input, B, out_T, n_cap, frames, R_t, st);
+        else run_step_train<__nv_bfloat16>(h, tp, input, B, out_T, n_cap, frames, R_t, st);
+        h->last_B = B;
+        if (n_host) {
+            CK(cudaMemcpyAsync(h->h_flag + 8, h->nbuf.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            *n_host = h->h_flag[8];
+        }
+    });
+}
+
+int tante_backward(tante_handle_t h, int32_t slot, const float* input, const float* grad_frames, int32_t n_frames,
+                   const float* grad_Rt, float* grad_input, float* grad_params, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && input && grad_frames && grad_params, "null argument");
+        REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range");
+        REQUIRE(n_frames >= 1, "n_frames must be >= 1");
+        Tape& tp = *h->tapes[slot];
+        if (!tp.valid) throw Error(TANTE_ERR_STATE, "tape slot holds no forward (or was already consumed)");
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        backward_alloc(h, tp.B_used);
+        if (h->cfg.precision == TANTE_PREC_FP32)
+            run_backward<float>(h, tp, input, grad_frames, n_frames, grad_Rt, grad_input, grad_params, st);
+        else
+            run_backward<__nv_bfloat16>(h, tp, input, grad_frames, n_frames, grad_Rt, grad_input, grad_params, st);
+        tp.valid = false;
+    });
+}
+
+int tante_test_wgrad(int32_t use_tc, const void* A, const void* Bm, float* C, int64_t M, int32_t N, int32_t K,
+                     int32_t iters, void* stream) {
+    return guarded([&] {
+        REQUIRE(A && Bm && C, "null argument");
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        for (int i = 0; i < std::max(1, iters); ++i) {
+            if (use_tc == 1) {
+                REQUIRE(wgrad_tc_supported(M, N, K, N, K), "shape not covered by the tcgen05 wgrad kernel");
+                CK(launch_wgrad_tc(reinterpret_cast<const __nv_bfloat16*>(A), N, reinterpret_cast<const __nv_bfloat16*>(Bm), K,
+                                   C, K, M, N, K, sms, st));
+            } else if (use_tc == 2) {
+                CK((launch_wgrad_simt<__nv_bfloat16, __nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(A), N,
+                                                                    reinterpret_cast<const __nv_bfloat16*>(Bm), K, C, K, M, N,
+                                                                    K, sms, st)));
+            } else {
+                CK((launch_wgrad_simt<float, float>(reinterpret_cast<const float*>(A), N, reinterpret_cast<const float*>(Bm), K,
+                                                    C, K, M, N, K, sms, st)));
+            }
+        }
     });
 }
 

@@ -172,6 +172,11 @@ class _Engine:
         self.bound_sig = None
         self.max_batch = 0
         self.max_roll = 0
+        # training: tape slots (one per live autograd node) and the flat gradient layout
+        self.grad_numel = int(self.lib.tante_grad_numel(self.handle))
+        self.grad_offsets = [int(self.lib.tante_param_grad_offset(self.handle, i)) for i in range(len(self.names))]
+        self.n_slots = 0
+        self.free_slots: List[int] = []
 
     def close(self):
         if self.handle:
@@ -208,7 +213,100 @@ class _Engine:
         if B > self.max_batch or n_roll > self.max_roll:
             self.max_batch = max(B, self.max_batch)
             self.max_roll = max(n_roll, self.max_roll)
-            _abi.check(self.lib.tante_reserve(self.handle, self.max_batch, self.max_roll, 0))
+            _abi.check(self.lib.tante_reserve(self.handle, self.max_batch, self.max_roll, self.n_slots))
+
+    MAX_SLOTS = 64
+
+    def acquire_slot(self) -> int:
+        """Tape slot for one model call in grad mode; released by its backward (or when the autograd node dies)."""
+        if not self.free_slots:
+            if self.n_slots >= self.MAX_SLOTS:
+                raise RuntimeError(
+                    f"tante_b200: {self.MAX_SLOTS} taped forwards are alive without a backward; run validation under "
+                    "torch.no_grad()/inference_mode() as the reference trainers do (r_trainer.py:181)")
+            self.n_slots += 1
+            _abi.check(self.lib.tante_reserve(self.handle, max(self.max_batch, 1), self.max_roll, self.n_slots))
+            self.max_batch = max(self.max_batch, 1)
+            self.free_slots.append(self.n_slots - 1)
+        return self.free_slots.pop()
+
+    def release_slot(self, slot: int):
+        if slot not in self.free_slots:
+            self.free_slots.append(slot)
+
+
+class _SlotGuard:
+    """Returns a tape slot to its engine when the autograd node that owns it is freed without a backward."""
+
+    def __init__(self, eng: _Engine, slot: int):
+        self.eng, self.slot, self.released = eng, slot, False
+
+    def release(self):
+        if not self.released:
+            self.released = True
+            self.eng.release_slot(self.slot)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class _TanteStep(torch.autograd.Function):
+    """One differentiable model call: tante_train_forward / tante_backward on a tape slot.  The parameters are
+    passed as inputs so that autograd routes their gradients into `.grad` exactly as for the reference module
+    (accumulation over the chained BPTT rollout of r_trainer.py:122-126 included)."""
+
+    @staticmethod
+    def forward(ctx, model, x, out_T, n_cap, *params):
+        eng = model._engine(x.device)
+        B = x.shape[0]
+        eng.reserve(B)
+        slot = eng.acquire_slot()
+        frames = torch.empty((B, n_cap, model.n_channel, *model.shape), device=x.device, dtype=torch.float32)
+        R_t = torch.zeros((B,), device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        n_host = ctypes.c_int32(n_cap)
+        try:
+            _abi.check(eng.lib.tante_train_forward(eng.handle, slot, x.data_ptr(), B, float(out_T), n_cap,
+                                                   frames.data_ptr(), R_t.data_ptr(),
+                                                   None if model.deg else ctypes.byref(n_host), stream))
+        except Exception:
+            eng.release_slot(slot)
+            raise
+        n = n_host.value
+        ctx.eng, ctx.slot, ctx.n, ctx.model = eng, slot, n, model
+        ctx.guard = _SlotGuard(eng, slot)
+        ctx.save_for_backward(x)
+        out = frames if n == n_cap else frames[:, :n].contiguous()
+        if model.deg:
+            ctx.mark_non_differentiable(R_t)
+        return out, R_t
+
+    @staticmethod
+    def backward(ctx, g_frames, g_rt):
+        (x,) = ctx.saved_tensors
+        eng, model = ctx.eng, ctx.model
+        dev = x.device
+        g_frames = g_frames.to(torch.float32).contiguous()
+        g_rt_ptr = None
+        if not model.deg and g_rt is not None:
+            g_rt = g_rt.to(torch.float32).contiguous()
+            g_rt_ptr = g_rt.data_ptr()
+        flat = torch.empty((eng.grad_numel,), device=dev, dtype=torch.float32)
+        g_in = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _abi.check(eng.lib.tante_backward(eng.handle, ctx.slot, x.data_ptr(), g_frames.data_ptr(), int(g_frames.shape[1]),
+                                          g_rt_ptr, None if g_in is None else g_in.data_ptr(), flat.data_ptr(), stream))
+        ctx.guard.release()
+        grads = []
+        for (name, shape), off in zip(ctx.model._param_shapes(eng), eng.grad_offsets):
+            n = 1
+            for d in shape:
+                n *= d
+            grads.append(flat[off:off + n].view(shape))
+        return (None, g_in, None, None, *grads)
 
 
 class TANTE(nn.Module):
@@ -307,13 +405,20 @@ class TANTE(nn.Module):
         eng.sync_params(self, torch.cuda.current_stream(device).cuda_stream)
         return eng
 
-    def _check_inference(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "tante_b200.TANTE: the differentiable (training) path is not built yet; call under "
-                "torch.inference_mode()/no_grad() as the reference evaluators do (r_evaler.py:117)")
+    def _param_shapes(self, eng: _Engine):
+        params = dict(self.named_parameters())
+        return [(n, tuple(params[n].shape)) for n in eng.names]
+
+    def _needs_grad(self, input) -> bool:
+        return torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
+
+    def _forward_train(self, x, out_T, n_cap):
         if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not supported")
+            raise NotImplementedError("dropout > 0 in training mode is not supported by the CUDA backward; "
+                                      "construct the model with dropout=0.0")
+        eng = self._engine(x.device)
+        params = dict(self.named_parameters())
+        return _TanteStep.apply(self, x, float(out_T), int(n_cap), *[params[n] for n in eng.names])
 
     def _prep_input(self, input: torch.Tensor) -> torch.Tensor:
         if input.dim() != 5:
@@ -329,13 +434,15 @@ class TANTE(nn.Module):
     # ------------------------------------------------------------------ reference API
     def forward(self, input, out_T=1):
         """(B,>=T,D,H,W) -> frames (B,n,D,H,W) [and R_t (B,) when deg=False] (tante.py:125-176)."""
-        self._check_inference()
         x = self._prep_input(input)
-        eng = self._engine(x.device)
-        B = x.shape[0]
         if not self.deg and out_T < 1:
             raise ValueError("out_T must be >= 1")
         n_cap = int(self.output_length) if self.deg else max(1, int(math.floor(out_T + 0.001)))
+        if self._needs_grad(x):
+            frames, R_t = self._forward_train(x, out_T, n_cap)
+            return frames if self.deg else (frames, R_t)
+        eng = self._engine(x.device)
+        B = x.shape[0]
         eng.reserve(B)
         frames = torch.empty((B, n_cap, self.n_channel, *self.shape), device=x.device, dtype=torch.float32)
         R_t = None if self.deg else torch.empty((B,), device=x.device, dtype=torch.float32)

@@ -1,0 +1,238 @@
+"""GPU parity of the training path (taped forward + hand-written backward, through the C ABI and the autograd
+Function) against the reference's own loss/gradient goldens and against autograd over the CPU oracle.
+
+The drivers below are the reference trainers' rollouts restated around the drop-in module:
+R_Trainer.rollout_model (trainer/r_trainer.py:112-133: per-sample B=1 loops, out_T=1.5, window NOT detached => BPTT)
+and Trainer.rollout_model (trainer/trainer.py:144-159: whole batch, fixed step), loss = trainer/metrics.py MSE.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cfg, load_golden, rel_l2
+from oracle import tante_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_GRAD_TOL = 2e-4       # fp32 CUDA vs fp32 CPU reference gradients (different summation orders, atomics)
+BF16_GRAD_TOL = 6e-2       # bf16 tensor mode: per-tensor gradient rel-L2 (activations/gradients rounded to bf16)
+
+
+def _rollout_train(model, cfg, x, n_steps, out_T):
+    """The reference trainers' rollout around `model` (channels-first in, channels-last out)."""
+    def roll(win):
+        moving, ys, rts, cum = win, [], [], 0
+        while cum < n_steps:
+            if cfg.deg:
+                y, rt = model(moving), None
+            else:
+                y, rt = model(moving, out_T)
+            cum += y.shape[1]
+            if cum < n_steps:
+                moving = torch.cat([moving[:, y.shape[1]:], y], dim=1)
+            ys.append(y.permute(0, 1, 3, 4, 2))
+            if rt is not None:
+                rts.append(rt)
+        return torch.cat(ys, 1)[:, :n_steps], (torch.cat(rts, 0) if rts else None)
+    if cfg.deg:
+        return roll(x)
+    outs, rts = [], []
+    for b in range(x.shape[0]):
+        y, r = roll(x[b:b + 1])
+        outs.append(y)
+        rts.append(r)
+    return torch.cat(outs, 0), torch.cat(rts, 0)
+
+
+def _loss(y, y_ref, rts):
+    l = torch.mean((y - y_ref) ** 2, dim=(-3, -2)).mean()
+    if rts is None:
+        return l
+    avg = rts.mean()
+    pen = 0.0
+    if float(avg) < 1.5:
+        pen = pen + 5e-3 * (1.5 - avg) ** 2
+    if float(avg) > 4:
+        pen = pen + 1e-1 * (avg - 4) ** 2
+    return l + pen
+
+
+def _train_case(name, precision):
+    from gpu_util import make_model
+    z, meta = load_golden(name)
+    cfg = golden_cfg(meta)
+    sd = O.make_state_dict(cfg, meta["seed"], meta["rt_bias"])
+    model = make_model(cfg, sd, precision).train()
+    x = O.make_input(cfg, meta["B"], meta["input_seed"]).cuda().requires_grad_(True)
+    g = torch.Generator().manual_seed(meta["target_seed"])
+    y_ref = torch.randn(meta["B"], meta["n_steps"], cfg.H, cfg.W, cfg.n_fields, generator=g).cuda()
+    y, rts = _rollout_train(model, cfg, x, meta["n_steps"], 1.5)
+    loss = _loss(y, y_ref, rts)
+    loss.backward()
+    return z, meta, cfg, model, x, y, loss
+
+
+def _report(model, z, meta, tol):
+    bad, worst = [], 0.0
+    for name_, gn in zip(meta["param_names"], z["grad_norms"]):
+        gp = dict(model.named_parameters())[name_].grad
+        got = 0.0 if gp is None else float(gp.norm())
+        nerr = abs(got - gn) / max(gn, 1e-12)
+        err = nerr
+        key = "grad::" + name_
+        s = meta["stride"]
+        if gn > 0 and gp is not None:
+            if key in z:
+                err = max(err, rel_l2(gp.cpu().numpy(), z[key]))
+            elif "gradsub::" + name_ in z:
+                err = max(err, rel_l2(gp.cpu().reshape(-1)[::s].numpy(), z["gradsub::" + name_]))
+        worst = max(worst, err)
+        if err > tol:
+            bad.append(f"{name_}: rel {err:.3e} (norm got {got:.4e} ref {gn:.4e})")
+    return bad, worst
+
+
+@pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2"])
+def test_training_step_fp32_matches_reference_golden(name):
+    z, meta, cfg, model, x, y, loss = _train_case(name, "fp32")
+    assert abs(float(loss) - float(z["loss"])) < 2e-6 * max(1.0, abs(float(z["loss"])))
+    s = meta["stride"]
+    assert rel_l2(y.detach().cpu().reshape(-1)[::s].numpy(), z["y_pred"]) < 1e-5
+    bad, worst = _report(model, z, meta, FP32_GRAD_TOL)
+    assert not bad, "parameter gradients differ from the reference:\n" + "\n".join(bad)
+    assert rel_l2(x.grad.cpu().reshape(-1)[::s].numpy(), z["grad_input"]) < FP32_GRAD_TOL
+    assert abs(float(x.grad.norm()) - float(z["grad_input_norm"])) < FP32_GRAD_TOL * float(z["grad_input_norm"])
+
+
+@pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2"])
+def test_training_step_bf16_close_to_reference_golden(name):
+    z, meta, cfg, model, x, y, loss = _train_case(name, "bf16")
+    assert abs(float(loss) - float(z["loss"])) < 2e-2 * max(1.0, abs(float(z["loss"])))
+    bad, worst = _report(model, z, meta, BF16_GRAD_TOL)
+    assert not bad, "parameter gradients differ from the reference:\n" + "\n".join(bad)
+    s = meta["stride"]
+    assert rel_l2(x.grad.cpu().reshape(-1)[::s].numpy(), z["grad_input"]) < BF16_GRAD_TOL
+
+
+def _oracle_grads(cfg, sd, x, gy, grt, out_T):
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xg = x.clone().requires_grad_(True)
+    if cfg.deg:
+        y = O.forward(sdg, cfg, xg)
+        (y * gy).sum().backward()
+    else:
+        y, rt = O.forward(sdg, cfg, xg, out_T)
+        ((y * gy).sum() + (rt * grt).sum()).backward()
+    return y.detach(), sdg, xg.grad
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_GRAD_TOL), ("bf16", BF16_GRAD_TOL)])
+@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2"])
+def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
+    """One model call with a random cotangent on the frames AND on R_t, multi-frame emit (n = 3) included:
+    every parameter gradient and the input gradient against torch autograd over the CPU oracle."""
+    from gpu_util import make_model
+    if case == "adp_k2_n3":
+        cfg = O.OracleConfig(n_fields=3, H=32, W=64, taylor_order=2, attn_axes="THW-WHT", deg=False)
+        rt_bias, out_T = 2.7, 8
+    elif case == "deg_k1_p4":
+        cfg = O.OracleConfig(n_fields=5, H=32, W=48, taylor_order=1, attn_axes="HWT", deg=True, patch_scale=4,
+                             output_length=2, frame_interval=0.5)
+        rt_bias, out_T = 0.0, 1
+    else:
+        cfg = O.OracleConfig(n_fields=2, H=16, W=24, taylor_order=3, attn_axes="T-H-W", deg=False, patch_scale=2)
+        rt_bias, out_T = 1.3, 4
+    sd = O.make_state_dict(cfg, 311, rt_bias)
+    B = 3
+    x = O.make_input(cfg, B, 312)
+    with torch.no_grad():
+        y0 = O.forward(sd, cfg, x, out_T)
+        y0 = y0 if cfg.deg else y0[0]
+    g = torch.Generator().manual_seed(313)
+    gy = torch.randn(y0.shape, generator=g)
+    grt = torch.randn(B, generator=g)
+    y_ref, sdg, gx_ref = _oracle_grads(cfg, sd, x, gy, grt, out_T)
+
+    model = make_model(cfg, sd, prec).train()
+    xc = x.cuda().requires_grad_(True)
+    if cfg.deg:
+        y = model(xc)
+        (y * gy.cuda()).sum().backward()
+    else:
+        y, rt = model(xc, out_T)
+        ((y * gy.cuda()).sum() + (rt * grt.cuda()).sum()).backward()
+    assert y.shape == y_ref.shape
+    assert rel_l2(y.detach().cpu().numpy(), y_ref.numpy()) < (1e-5 if prec == "fp32" else 2e-2)
+    bad = []
+    for n, p in model.named_parameters():
+        ref = sdg[n].grad
+        refn = 0.0 if ref is None else float(ref.norm())
+        if p.grad is None:
+            if refn > 0:
+                bad.append(f"{n}: no gradient (ref norm {refn:.3e})")
+            continue
+        if refn == 0.0:
+            if float(p.grad.norm()) > 1e-6:
+                bad.append(f"{n}: got {float(p.grad.norm()):.3e}, reference gradient is zero")
+            continue
+        e = rel_l2(p.grad.cpu().numpy(), ref.numpy())
+        if e > tol:
+            bad.append(f"{n}: rel {e:.3e} (norm got {float(p.grad.norm()):.4e} ref {refn:.4e})")
+    assert not bad, "gradients differ from oracle autograd:\n" + "\n".join(bad)
+    assert rel_l2(xc.grad.cpu().numpy(), gx_ref.numpy()) < tol
+
+
+@pytest.mark.parametrize("shape", [(4096, 256, 256), (8192 + 64, 768, 256), (5000, 256, 512), (3000, 128, 256),
+                                   (2048, 512, 256), (1024, 256, 128), (777, 256, 64)])
+def test_wgrad_tcgen05_matches_torch(shape):
+    """dW[N,K] += A[M,N]^T B[M,K] on tcgen05 with MN-major operands + TMA reduce-add, accumulating into C."""
+    import ctypes
+    from tante_b200 import _abi
+    lib = _abi.load()
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    Bm = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    C0 = torch.randn(N, K, device="cuda", generator=g)
+    C = C0.clone()
+    _abi.check(lib.tante_test_wgrad(1, A.data_ptr(), Bm.data_ptr(), C.data_ptr(), M, N, K, 1,
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double().t() @ Bm.double()
+    assert rel_l2(C.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_wgrad_simt_matches_torch(mode):
+    from tante_b200 import _abi
+    lib = _abi.load()
+    M, N, K = 3001, 64, 44
+    g = torch.Generator(device="cuda").manual_seed(6)
+    dt = torch.float32 if mode == 0 else torch.bfloat16
+    A = torch.randn(M, N, device="cuda", generator=g).to(dt)
+    Bm = torch.randn(M, K, device="cuda", generator=g).to(dt)
+    C = torch.zeros(N, K, device="cuda")
+    _abi.check(lib.tante_test_wgrad(mode, A.data_ptr(), Bm.data_ptr(), C.data_ptr(), M, N, K, 1,
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = A.double().t() @ Bm.double()
+    assert rel_l2(C.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+
+
+def test_grad_accumulation_and_slot_reuse():
+    """Two backward passes accumulate into .grad like the reference module; tape slots are recycled."""
+    from gpu_util import make_model
+    cfg = O.OracleConfig(n_fields=2, H=16, W=16, taylor_order=1, attn_axes="TH", deg=True)
+    sd = O.make_state_dict(cfg, 11)
+    model = make_model(cfg, sd, "fp32").train()
+    x = O.make_input(cfg, 2, 12).cuda()
+    model(x).square().mean().backward()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model(x).square().mean().backward()
+    for n, p in model.named_parameters():
+        assert rel_l2(p.grad.cpu().numpy(), (2 * g1[n]).cpu().numpy()) < 1e-4, n
+    for _ in range(5):
+        model.zero_grad()
+        model(x).square().mean().backward()
+    eng = next(iter(model._engines.values()))
+    assert eng.n_slots <= 2

@@ -114,15 +114,23 @@ def test_training_step_bf16_close_to_reference_golden(name):
     assert rel_l2(x.grad.cpu().reshape(-1)[::s].numpy(), z["grad_input"]) < BF16_GRAD_TOL
 
 
-def _oracle_grads(cfg, sd, x, gy, grt, out_T):
+def _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=False):
+    """autocast=True: the oracle under torch.autocast(bf16) -- the reference's own amp mode (r_trainer.py:71-74,145);
+    its deviation from fp32 is the yardstick for the bf16 tensor mode on cancellation-dominated gradients."""
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     xg = x.clone().requires_grad_(True)
-    if cfg.deg:
-        y = O.forward(sdg, cfg, xg)
-        (y * gy).sum().backward()
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+        if cfg.deg:
+            y = O.forward(sdg, cfg, xg)
+            rt = None
+        else:
+            y, rt = O.forward(sdg, cfg, xg, out_T)
+    if y.shape != gy.shape:
+        return None, None, None
+    if rt is None:
+        (y.float() * gy).sum().backward()
     else:
-        y, rt = O.forward(sdg, cfg, xg, out_T)
-        ((y * gy).sum() + (rt * grt).sum()).backward()
+        ((y.float() * gy).sum() + (rt.float() * grt).sum()).backward()
     return y.detach(), sdg, xg.grad
 
 
@@ -152,6 +160,9 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
     gy = torch.randn(y0.shape, generator=g)
     grt = torch.randn(B, generator=g)
     y_ref, sdg, gx_ref = _oracle_grads(cfg, sd, x, gy, grt, out_T)
+    amp = None
+    if prec == "bf16":
+        _, amp, _ = _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=True)
 
     model = make_model(cfg, sd, prec).train()
     xc = x.cuda().requires_grad_(True)
@@ -176,8 +187,13 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
                 bad.append(f"{n}: got {float(p.grad.norm()):.3e}, reference gradient is zero")
             continue
         e = rel_l2(p.grad.cpu().numpy(), ref.numpy())
-        if e > tol:
-            bad.append(f"{n}: rel {e:.3e} (norm got {float(p.grad.norm()):.4e} ref {refn:.4e})")
+        lim = tol
+        if amp is not None and amp[n].grad is not None:
+            # bf16 mode: allow what the reference's own bf16 autocast deviates by on this tensor (sums with heavy
+            # cancellation -- bias / LayerNorm gradients, the tiny interprator -- amplify rounding noise)
+            lim = max(tol, 3.0 * rel_l2(amp[n].grad.numpy(), ref.numpy()))
+        if e > lim:
+            bad.append(f"{n}: rel {e:.3e} > {lim:.3e} (norm got {float(p.grad.norm()):.4e} ref {refn:.4e})")
     assert not bad, "gradients differ from oracle autograd:\n" + "\n".join(bad)
     assert rel_l2(xc.grad.cpu().numpy(), gx_ref.numpy()) < tol
 

@@ -456,8 +456,10 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const TA* __restrict
 
 // ---- propagator backward (attn_backbone.py:111-119,140-146):  y = x + W2 gelu(W1 x + b1) + b2 along an axis ----
 // In place on the gradient stream: dx = dy + W1^T (gelu'(pre) o (W2^T dy)); weight gradients accumulated in
-// registers across the slabs of a persistent CTA and flushed with atomics.  Slab = one `outer` x 64 columns.
-constexpr int kPropBwdCols = 64;
+// registers across the slabs of a persistent CTA, reduced in shared memory and flushed with one atomic per entry.
+// Slab = one `outer` x CW columns with S4*CW = 4096 (short axes get wide slabs, so all 256 threads work for
+// the T axis, S = 4, as well as for S = 64): threads = (CW/4 column groups) x (S4/4 row groups) of 4 x 4 tiles.
+constexpr int kPropBwdSlab = 4096;      // floats per slab array
 __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __restrict__ xin, float* __restrict__ dy,
                                                              int S, long long IC, long long n_outer,
                                                              const float* __restrict__ W1, const float* __restrict__ b1,
@@ -465,13 +467,17 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
                                                              float* __restrict__ gb1, float* __restrict__ gW2,
                                                              float* __restrict__ gb2) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int CW = kPropBwdCols;
-    const int S4 = (S + 3) & ~3;
+    int S4 = (S + 3) & ~3;
+    if (S4 > 4 && (S4 & (S4 - 1))) { int p2 = 8; while (p2 < S4) p2 <<= 1; S4 = p2; }   // power of two: 4, 8, 16, 32, 64
+    const int CW = kPropBwdSlab / S4;   // 1024 .. 64 columns
+    const int CWP = CW + 4;             // padded row pitch (bank spread for the row-strided weight-gradient reads)
+    const int ncg = CW / 4;             // column groups of 4
+    const int nrg = 256 / ncg;          // row groups working in parallel (== S4/4)
     float* sx = smem;                 // [S4][CW]  x
-    float* sp = sx + S4 * CW;         // [S4][CW]  pre -> dpre
-    float* sh = sp + S4 * CW;         // [S4][CW]  h
-    float* sd = sh + S4 * CW;         // [S4][CW]  dy
-    float* w1 = sd + S4 * CW;         // [S4][S4]  W1[j][i]
+    float* sp = sx + S4 * CWP;        // [S4][CW]  pre -> dpre
+    float* sh = sp + S4 * CWP;        // [S4][CW]  h
+    float* sd = sh + S4 * CWP;        // [S4][CW]  dy
+    float* w1 = sd + S4 * CWP;        // [S4][S4]  W1[j][i]
     float* w1t = w1 + S4 * S4;        // [S4][S4]  W1^T: w1t[i][j] = W1[j][i]
     float* w2 = w1t + S4 * S4;        // [S4][S4]  W2[j][i]
     float* sb1 = w2 + S4 * S4;        // [S4]
@@ -483,8 +489,11 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
         w2[i] = ok ? W2[a * S + b] : 0.f;
     }
     for (int i = threadIdx.x; i < S4; i += blockDim.x) sb1[i] = i < S ? b1[i] : 0.f;
-    const int cg = threadIdx.x % 16, rg = threadIdx.x / 16;      // 4 columns x 4 rows per thread, 16 row groups
-    // weight-gradient tiles owned by this thread: entries (j = rj*4+a, i = ci*4+b) with (rj, ci) = (tid/16, tid%16)
+    const int cg = threadIdx.x % ncg, rg = threadIdx.x / ncg;
+    // weight-gradient work split: (S4/4)^2 tiles of 4x4 entries x ncp column partitions
+    const int nt1 = S4 / 4, ntile = nt1 * nt1, ncp = 256 / ntile;
+    const int tile = threadIdx.x % ntile, cpart = threadIdx.x / ntile;
+    const int rj = tile / nt1, ci = tile % nt1;
     float aw1[4][4], aw2[4][4], ab1[4], ab2[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -499,7 +508,7 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
 #pragma unroll 4
         for (int k = 0; k < S4; ++k) {
             const float4 w4 = *reinterpret_cast<const float4*>(wt + k * S4 + jt * 4);
-            const float4 v4 = *reinterpret_cast<const float4*>(src + k * CW + cg * 4);
+            const float4 v4 = *reinterpret_cast<const float4*>(src + k * CWP + cg * 4);
             const float w[4] = {w4.x, w4.y, w4.z, w4.w};
             const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -515,19 +524,19 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
         const float* xb = xin + (size_t)outer * S * IC + col0;
         float* db = dy + (size_t)outer * S * IC + col0;
         __syncthreads();
-        for (int i = threadIdx.x; i < S4 * (CW / 4); i += blockDim.x) {
-            const int p = i / (CW / 4), c4 = (i % (CW / 4)) * 4;
+        for (int i = threadIdx.x; i < S4 * ncg; i += blockDim.x) {
+            const int p = i / ncg, c4 = (i % ncg) * 4;
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = xv;
             if (p < S && c4 < ncol) {
                 xv = *reinterpret_cast<const float4*>(xb + (size_t)p * IC + c4);
                 dv = *reinterpret_cast<const float4*>(db + (size_t)p * IC + c4);
             }
-            *reinterpret_cast<float4*>(sx + p * CW + c4) = xv;
-            *reinterpret_cast<float4*>(sd + p * CW + c4) = dv;
+            *reinterpret_cast<float4*>(sx + p * CWP + c4) = xv;
+            *reinterpret_cast<float4*>(sd + p * CWP + c4) = dv;
         }
         __syncthreads();
         // pass A: pre = W1 x + b1, h = gelu(pre)
-        for (int jt = rg; jt < S4 / 4; jt += 16) {
+        for (int jt = rg; jt < nt1; jt += nrg) {
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -536,14 +545,14 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
             mm(w1t, sx, jt, acc);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                *reinterpret_cast<float4*>(sp + (jt * 4 + a) * CW + cg * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-                *reinterpret_cast<float4*>(sh + (jt * 4 + a) * CW + cg * 4) =
+                *reinterpret_cast<float4*>(sp + (jt * 4 + a) * CWP + cg * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                *reinterpret_cast<float4*>(sh + (jt * 4 + a) * CWP + cg * 4) =
                     make_float4(gelu_erf(acc[a][0]), gelu_erf(acc[a][1]), gelu_erf(acc[a][2]), gelu_erf(acc[a][3]));
             }
         }
         __syncthreads();
         // pass B: dh[i] = sum_j W2[j][i] dy[j];  dpre = dh * gelu'(pre)   (overwrites sp)
-        for (int it = rg; it < S4 / 4; it += 16) {
+        for (int it = rg; it < nt1; it += nrg) {
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
             mm(w2, sd, it, acc);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                float4* pp = reinterpret_cast<float4*>(sp + (it * 4 + a) * CW + cg * 4);
+                float4* pp = reinterpret_cast<float4*>(sp + (it * 4 + a) * CWP + cg * 4);
                 const float4 pr = *pp;
                 *pp = make_float4(acc[a][0] * gelu_erf_grad(pr.x), acc[a][1] * gelu_erf_grad(pr.y),
                                   acc[a][2] * gelu_erf_grad(pr.z), acc[a][3] * gelu_erf_grad(pr.w));
@@ -560,7 +569,7 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
         }
         __syncthreads();
         // pass C: dx[i] = dy[i] + sum_j W1[j][i] dpre[j]
-        for (int it = rg; it < S4 / 4; it += 16) {
+        for (int it = rg; it < nt1; it += nrg) {
             float acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -571,56 +580,60 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
             for (int a = 0; a < 4; ++a) {
                 const int p = it * 4 + a;
                 if (p < S && cg * 4 < ncol) {
-                    const float4 d4 = *reinterpret_cast<const float4*>(sd + p * CW + cg * 4);
+                    const float4 d4 = *reinterpret_cast<const float4*>(sd + p * CWP + cg * 4);
                     *reinterpret_cast<float4*>(db + (size_t)p * IC + cg * 4) =
                         make_float4(d4.x + acc[a][0], d4.y + acc[a][1], d4.z + acc[a][2], d4.w + acc[a][3]);
                 }
             }
         }
         // weight gradients: gW2[j][i] += sum_c dy[j][c] h[i][c];  gW1[j][i] += sum_c dpre[j][c] x[i][c]
-        {
-            const int rj = threadIdx.x / 16, ci = threadIdx.x % 16;
-            if (rj * 4 < S4 && ci * 4 < S4) {
-                for (int c = 0; c < CW; ++c) {
-                    float dyv[4], dpv[4], hv[4], xv[4];
+        for (int c = cpart; c < CW; c += ncp) {
+            float dyv[4], dpv[4], hv[4], xv[4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        dyv[a] = sd[(rj * 4 + a) * CW + c];
-                        dpv[a] = sp[(rj * 4 + a) * CW + c];
-                        hv[a] = sh[(ci * 4 + a) * CW + c];
-                        xv[a] = sx[(ci * 4 + a) * CW + c];
-                    }
+            for (int a = 0; a < 4; ++a) {
+                dyv[a] = sd[(rj * 4 + a) * CWP + c];
+                dpv[a] = sp[(rj * 4 + a) * CWP + c];
+                hv[a] = sh[(ci * 4 + a) * CWP + c];
+                xv[a] = sx[(ci * 4 + a) * CWP + c];
+            }
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            aw2[a][b] = fmaf(dyv[a], hv[b], aw2[a][b]);
-                            aw1[a][b] = fmaf(dpv[a], xv[b], aw1[a][b]);
-                        }
-                    if (ci == 0) {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) { ab2[a] += dyv[a]; ab1[a] += dpv[a]; }
-                    }
+                for (int b = 0; b < 4; ++b) {
+                    aw2[a][b] = fmaf(dyv[a], hv[b], aw2[a][b]);
+                    aw1[a][b] = fmaf(dpv[a], xv[b], aw1[a][b]);
                 }
+            if (ci == 0) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { ab2[a] += dyv[a]; ab1[a] += dpv[a]; }
             }
         }
     }
-    {
-        const int rj = threadIdx.x / 16, ci = threadIdx.x % 16;
+    // reduce the column partitions in shared memory, then one global atomic per entry and CTA
+    __syncthreads();
+    float* r1 = sx;                    // [S4][S4]
+    float* r2 = r1 + S4 * S4;          // [S4][S4]
+    float* rb = r2 + S4 * S4;          // [2][S4]
+    for (int i = threadIdx.x; i < 2 * S4 * S4 + 2 * S4; i += blockDim.x) r1[i] = 0.f;
+    __syncthreads();
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int j = rj * 4 + a;
-            if (j >= S) continue;
+    for (int a = 0; a < 4; ++a) {
+        const int j = rj * 4 + a;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int i = ci * 4 + b;
-                if (i >= S) continue;
-                atomicAdd(gW1 + j * S + i, aw1[a][b]);
-                atomicAdd(gW2 + j * S + i, aw2[a][b]);
-            }
-            if (ci == 0) { atomicAdd(gb1 + j, ab1[a]); atomicAdd(gb2 + j, ab2[a]); }
+        for (int b = 0; b < 4; ++b) {
+            const int i = ci * 4 + b;
+            atomicAdd(&r1[j * S4 + i], aw1[a][b]);
+            atomicAdd(&r2[j * S4 + i], aw2[a][b]);
         }
+        if (ci == 0) { atomicAdd(&rb[j], ab1[a]); atomicAdd(&rb[S4 + j], ab2[a]); }
     }
+    __syncthreads();
+    for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+        const int j = e / S, i = e % S;
+        atomicAdd(gW1 + e, r1[j * S4 + i]);
+        atomicAdd(gW2 + e, r2[j * S4 + i]);
+    }
+    for (int j = threadIdx.x; j < S; j += blockDim.x) { atomicAdd(gb1 + j, rb[j]); atomicAdd(gb2 + j, rb[S4 + j]); }
 }
 
 // ---- Taylor head backward (tante.py:156-171 + dec_conv_3, enc_dec_cnn.py:273) ---------------------------

@@ -23,6 +23,7 @@
 #include "kernels_simt.cuh"
 #include "pack.cuh"
 #include "backward.cuh"
+#include "attention_bwd_mma.cuh"
 #include "wgrad_tc.cuh"
 
 using namespace tante;
@@ -708,6 +709,14 @@ void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* 
     if (axis == 'T') { S = T; inner = L; nseq = (long long)B * L; }
     else if (axis == 'H') { S = Hp; inner = Wp; nseq = (long long)B * T * Wp; }
     else { S = Wp; inner = 1; nseq = (long long)B * T * Hp; }
+    if constexpr (sizeof(TA) == 2) {
+        cudaError_t e = cudaSuccess;
+        if (launch_attention_bwd_mma(qkv, dout, dqkv, nseq, S, inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
     const int G = std::max(1, 64 / S);
     const int R = G * S;
     const float scale = 1.0f / sqrtf((float)h->HD);
@@ -730,10 +739,12 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
-    const int S4 = (S + 3) & ~3;
-    const size_t smem = (size_t)(4 * S4 * kPropBwdCols + 3 * S4 * S4 + S4) * sizeof(float);
-    const long long nslab = outer * ((IC + kPropBwdCols - 1) / kPropBwdCols);
-    const unsigned grid = (unsigned)std::min<long long>(nslab, (S4 <= 32 ? 2LL : 1LL) * h->num_sms);
+    int S4 = (S + 3) & ~3;
+    if (S4 > 4 && (S4 & (S4 - 1))) { int p2 = 8; while (p2 < S4) p2 <<= 1; S4 = p2; }
+    const int CW = kPropBwdSlab / S4;
+    const size_t smem = (size_t)(4 * (kPropBwdSlab + 4 * S4) + 3 * S4 * S4 + S4) * sizeof(float);
+    const long long nslab = outer * ((IC + CW - 1) / CW);
+    const unsigned grid = (unsigned)std::min<long long>(nslab, 2LL * h->num_sms);
     propagator_bwd_kernel<<<grid, 256, smem, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
                                                  AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
                                                  GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));

@@ -4,6 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            # the B200-native arm
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
 
+Workload `train` (default; BASELINE.json configs[1], the configuration the metric is quoted on): one bf16
+training step of TANTE (configs/tante.yaml: fixed-step, K=1, THWTHWTHW, patch 8) on the synthetic Active Matter
+shape (11 fields, 256x256), batch 16 per GPU: 4 chained model calls with BPTT through the window
+(trainer/trainer.py:144-159), MSE, backward, clip_grad_norm_(1.0), AdamW(lr 5e-5, wd 1e-5).  N > 1: data parallel,
+one NCCL all-reduce of the flat gradient bucket per step (weak scaling).  value = training samples/s (whole job).
+
 Workload `rollout` (BASELINE.json configs[2]): adaptive-step rollout inference on the synthetic
 Rayleigh-Benard shape (4 fields, 512x128), n_steps_rollout frames per trajectory, trajectories sharded
 over the ranks with NO data-path collective (weak scaling: fixed trajectories per GPU).
@@ -39,16 +45,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="rollout", choices=["rollout"])
-    ap.add_argument("--shape", default="rayleigh_benard", choices=sorted(SHAPES))
-    ap.add_argument("--batch", type=int, default=64, help="trajectories per GPU per step")
+    ap.add_argument("--workload", default="train", choices=["train", "rollout"])
+    ap.add_argument("--shape", default=None, choices=sorted(SHAPES))
+    ap.add_argument("--batch", type=int, default=None, help="samples (train) / trajectories (rollout) per GPU per step")
+    ap.add_argument("--n-steps-output", type=int, default=4, help="chained model calls per training sample")
     ap.add_argument("--n-roll", type=int, default=8)
     ap.add_argument("--taylor-order", type=int, default=1)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--rt-bias", type=float, default=0.0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.shape is None:
+        a.shape = "active_matter" if a.workload == "train" else "rayleigh_benard"
+    if a.batch is None:
+        a.batch = 16 if a.workload == "train" else 64
+    return a
 
 
 def model_axes(K):
@@ -322,9 +334,262 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# =====================================================================================================
+# workload `train` (BASELINE.json configs[1])
+# =====================================================================================================
+def train_config(args, batch):
+    D, H, W = SHAPES[args.shape]
+    return {"workload": f"TANTE training step, synthetic {args.shape} shape ({D} fields, {H}x{W}), batch {batch}/GPU "
+                        f"(BASELINE.json configs[1])",
+            "samples_per_gpu_per_step": batch, "n_steps_output": args.n_steps_output,
+            "step": "4 chained forwards with BPTT + MSE + backward + clip_grad_norm_(1.0) + AdamW(lr 5e-5, wd 1e-5)",
+            "taylor_order": 1, "attn_axes": "THWTHWTHW", "patch_scale": 8, "embed_dim": 256, "deg": True,
+            "dropout": 0.0, "weights": "random init, torch.manual_seed(211), reference initialisers",
+            "l2_hygiene": "per-step working set (saved activations ~4 GB per model call) >> 126 MB L2; no explicit flush",
+            "parallelism": (f"dp{args.gpus}: one NCCL all-reduce of the flat fp32 gradient bucket per step" if args.gpus > 1
+                            else "single GPU, no collective")}
+
+
+def oracle_train_setup(args):
+    import torch
+    from oracle import tante_oracle as O
+    D, H, W = SHAPES[args.shape]
+    cfg = O.OracleConfig(n_fields=D, H=H, W=W, taylor_order=1, attn_axes="THWTHWTHW", deg=True)
+    return O, cfg
+
+
+def cpu_train_leg(args, seconds, max_steps=8, state_dict=None):
+    """The reference's CPU training step (oracle port of models/tante.py + trainer/trainer.py:178-198 with torch
+    autograd and torch AdamW) on all host threads, on a bounded sample of the workload: batches of ONE sample."""
+    import torch
+    O, cfg = oracle_train_setup(args)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = state_dict if state_dict is not None else O.make_state_dict(cfg, 211)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(sd.values()), lr=5e-5, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(212)
+    D, H, W = SHAPES[args.shape]
+    x = torch.randn(1, 4, D, H, W, generator=g)
+    y_ref = torch.randn(1, args.n_steps_output, H, W, D, generator=g)
+
+    def step():
+        y, _, _ = O.rollout_eval(sd, cfg, x, args.n_steps_output)
+        loss = O.train_loss(y, y_ref, None)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), 1.0)
+        opt.step()
+        return float(loss)
+
+    step()                                                  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if el > seconds or n >= max_steps:
+            break
+    return {"value": n / el, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} training steps of batch 1 ({args.n_steps_output} chained forwards + backward + clip + AdamW, "
+                      f"{args.shape} shape, fp32, torch {torch.__version__} CPU autograd) in {el:.1f}s"}
+
+
+def run_reference_train(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    steps = max(args.steps, 1)
+    warm = max(args.warmup, 1)
+    O, cfg = oracle_train_setup(args)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.make_state_dict(cfg, 211).items()}
+    opt = torch.optim.AdamW(list(sd.values()), lr=5e-5, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(212)
+    D, H, W = SHAPES[args.shape]
+    x = torch.randn(1, 4, D, H, W, generator=g)
+    y_ref = torch.randn(1, args.n_steps_output, H, W, D, generator=g)
+
+    def step():
+        y, _, _ = O.rollout_eval(sd, cfg, x, args.n_steps_output)
+        loss = O.train_loss(y, y_ref, None)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), 1.0)
+        opt.step()
+
+    for _ in range(min(warm, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    el = time.perf_counter() - t0
+    val = steps / el
+    line = {
+        "impl": "reference", "metric": "training_samples_per_s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} training steps of batch 1, one per bench step (the b200 arm does "
+                                   f"{args.batch} samples per step)"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_train(args):
+    import torch
+    import torch.distributed as dist
+    from tante_b200 import TANTE, TanteMetadata
+    from tante_b200.trainer import GradBucket, train_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D, H, W = SHAPES[args.shape]
+    B, n_out = args.batch, args.n_steps_output
+
+    torch.manual_seed(211)                                 # configs/tante.yaml:1 -- identical weights on every rank
+    model = TANTE(4, TanteMetadata(spatial_resolution=(H, W), n_fields=D), taylor_order=1, attn_axes="THWTHWTHW",
+                  patch_scale=8, deg=True, dropout=0.0, precision=args.precision)
+    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-5)    # tante.yaml:38-41
+    bucket = GradBucket(model)
+
+    g = torch.Generator().manual_seed(212 + rank)
+    host_x = torch.randn(B, 4, D, H, W, generator=g).pin_memory()
+    host_y = torch.randn(B, n_out, H, W, D, generator=g).pin_memory()
+    host_loss = torch.zeros(1).pin_memory()
+    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    W_, K_ = max(args.warmup, 3), max(args.steps, 1)
+    for _ in range(W_):
+        train_step(model, opt, dev_x, dev_y, n_out, bucket)
+    barrier()
+    # ---- timed region 1: inputs resident in HBM (value) ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K_):
+        loss = train_step(model, opt, dev_x, dev_y, n_out, bucket)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.launch_count() - l0
+    clocks = sampler.stop()
+    final_loss = float(loss)
+
+    # ---- timed region 2: end to end with HOST batches (H2D of inputs+targets, D2H of the loss every step) ----
+    def e2e_step():
+        x = host_x.to(dev, non_blocking=True)
+        y = host_y.to(dev, non_blocking=True)
+        ls = train_step(model, opt, x, y, n_out, bucket)
+        host_loss.copy_(ls.reshape(1), non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(K_):
+        e2e_step()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+    # ---- live per-kernel timing of the dominant kernel class (forward/input-gradient/weight-gradient GEMMs) ----
+    model.profile_gemms(True)
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for _ in range(K_):
+        train_step(model, opt, dev_x, dev_y, n_out, bucket)
+    e5.record()
+    torch.cuda.synchronize(dev)
+    gemm_ms, gemm_flops, gemm_n = model.profile_read()
+    model.profile_gemms(False)
+    ms_prof = e4.elapsed_time(e5)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_mode = args.precision == "bf16"
+    if tensor_mode:
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks
+                    else "fallback 1.4 PFLOP/s sustained (of fallback)")
+    else:
+        peak = 72.0
+        peak_src = "nominal fp32 FFMA 72 TFLOP/s (no measured fp32 peak in MEASURED_PEAKS.json)"
+    achieved = (gemm_flops / (gemm_ms * 1e-3)) / 1e12 if gemm_ms > 0 else None
+    samples = B * world
+    grad_bytes = bucket.flat.numel() * 4
+    line = {
+        "metric": "training_samples_per_s", "value": samples * K_ / (ms_total * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_total / K_, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
+        "config": train_config(args, B),
+        "final_loss": final_loss,
+        "model_calls_per_step": n_out,
+        "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+        "e2e": {"value": samples * K_ / (ms_e2e * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": (host_x.numel() + host_y.numel()) * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K_},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "kernel": ("gemm_tc_kernel + wgrad_tc_kernel (tcgen05 bf16: every forward, input-gradient and "
+                       "weight-gradient GEMM of the step)" if tensor_mode
+                       else "gemm_simt_kernel + wgrad_simt_kernel (FFMA fp32)"),
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+            "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / K_, "gemm_share_of_step": gemm_ms / ms_prof,
+            "algorithmic_flops_per_step": gemm_flops / K_,
+            "note": "achieved = sum(2*M*N*K) / sum(CUDA-event time) over every GEMM launch of K steps, events on the launch stream",
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_train_leg(args, args.cpu_seconds, state_dict=cpu_sd)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "train":
+        if args.impl == "reference":
+            run_reference_train(args)
+        else:
+            run_b200_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

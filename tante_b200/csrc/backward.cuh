@@ -637,15 +637,14 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
 }
 
 // ---- Taylor head backward (tante.py:156-171 + dec_conv_3, enc_dec_cnn.py:273) ---------------------------
-// frames_i = u0 + sum_k d_k c_ik, c_ik = (i*fi)^k/k!.  One thread per stage-1 row (k0 x k0 x D outputs):
-//   Gk[o]     = sum_{i<=n_b} gframes_i[o] * c_ik          -> Gbuf[k][row][NO]  (fp32; feeds the dW3 / db3 wgrad)
-//   du0[o]    = sum_{i<=n_b} gframes_i[o]                 -> grad_input[b, T-1] (nullable)
-//   dz_k[c]   = gelu_erf'(zpre_k[row][c]) * sum_o Gk[o] W3_k[c][o]   -> dz[k][row][C1]  (TA)
+// frames_i = u0 + sum_k d_k c_ik, c_ik = (i*fi)^k/k!.  One thread per stage-1 row (k0 x k0 x D outputs) gathers
+//   Gk[o]  = sum_{i<=n_b} gframes_i[o] * c_ik   -> G[k][row][kHeadPad]  (TA, zero-padded to 64 columns)
+//   du0[o] = sum_{i<=n_b} gframes_i[o]          -> grad_input[b, T-1] (nullable)
+// The two contractions that follow -- dz_k = G_k W3_k^T and dW3_k = z_k^T G_k -- are thin GEMMs on the padded
+// matrices (tensor cores in bf16 mode), the bias gradient is a column sum of G_k.
+constexpr int kHeadPad = 64;        // k0*k0*D <= 64 (D <= 16)
 struct HeadBwdParams {
-    const void* zpre[kMaxOrder];    // [rows][C1] pre-activation of the stage-1 rows (deconv2 output)
-    const float* w3[kMaxOrder];     // packed [C1][NO]
-    void* dz[kMaxOrder];            // [rows][C1]
-    float* G[kMaxOrder];            // [rows][NO]
+    void* G[kMaxOrder];             // [rows][kHeadPad]
     int K;
     float fi;
     const float* gframes;           // (B, n_cap, D, H, W)
@@ -655,15 +654,10 @@ struct HeadBwdParams {
 };
 
 template <typename TA>
-__global__ void __launch_bounds__(128) head_bwd_kernel(HeadBwdParams hp, PatchGeom g, int C1, long long rows_total) {
-    extern __shared__ __align__(16) float smem[];
-    const int NO = g.k0 * g.k0 * g.D;
-    float* sw = smem;                       // [K][C1][NO]
-    for (int k = 0; k < hp.K; ++k)
-        for (int i = threadIdx.x; i < C1 * NO; i += blockDim.x) sw[k * C1 * NO + i] = hp.w3[k][i];
-    __syncthreads();
+__global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_total) return;
+    const int NO = g.k0 * g.k0 * g.D;
     long long tkn = row / g.R1;
     const int r = (int)(row % g.R1);
     const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
@@ -673,53 +667,44 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(HeadBwdParams hp, PatchGe
     stage1_row_to_hw(g, hpp, wp, r, h1, w1);
     const int n = min(hp.n_arr[b], hp.n_cap);
     const size_t HW = (size_t)g.H * g.W;
-    // process the NO outputs in groups of 4 to bound registers; dz accumulates across groups in local memory
-    float dzacc[kMaxOrder > 4 ? 4 : kMaxOrder][64];     // K <= 4, C1 <= 64
-    for (int k = 0; k < hp.K; ++k)
-        for (int c = 0; c < C1; ++c) dzacc[k][c] = 0.f;
-    for (int oo = 0; oo < NO; ++oo) {
-        const int d = oo % g.D;
-        const int cp = (oo / g.D) % g.k0;
-        const int c = oo / (g.D * g.k0);
-        const int hh = h1 * g.k0 + c, ww = w1 * g.k0 + cp;
-        const size_t pix = (size_t)hh * g.W + ww;
-        float Gk[4] = {0.f, 0.f, 0.f, 0.f};
-        float du = 0.f;
-        for (int i = 1; i <= n; ++i) {
-            const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
-            du += gv;
-            const float dt = (float)i * hp.fi;
-            float coef = 1.f;
-            for (int k = 0; k < hp.K; ++k) {
-                coef *= dt / (float)(k + 1);
-                Gk[k] = fmaf(gv, coef, Gk[k]);
-            }
-        }
-        if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
-        for (int k = 0; k < hp.K; ++k) {
-            hp.G[k][(size_t)row * NO + oo] = Gk[k];
-            const float* wk = sw + k * C1 * NO + oo;
-            for (int cc = 0; cc < C1; ++cc) dzacc[k][cc] = fmaf(Gk[k], wk[cc * NO], dzacc[k][cc]);
-        }
-    }
-    for (int k = 0; k < hp.K; ++k) {
-        const TA* zp = reinterpret_cast<const TA*>(hp.zpre[k]) + (size_t)row * C1;
-        TA* dzp = reinterpret_cast<TA*>(hp.dz[k]) + (size_t)row * C1;
-        for (int cc = 0; cc < C1; cc += 4) {
-            float z4[4], o[4];
-            Vec4<TA>::load(zp + cc, z4);
+    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
+        float Gk[4][4];                 // [order][4 consecutive outputs]
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = dzacc[k][cc + j] * gelu_erf_grad(z4[j]);
-            Vec4<TA>::store(dzp + cc, o);
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) Gk[k][e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int oo = o4 + e;
+            if (oo >= NO) continue;
+            const int d = oo % g.D;
+            const int cp = (oo / g.D) % g.k0;
+            const int c = oo / (g.D * g.k0);
+            const size_t pix = (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp);
+            float du = 0.f;
+            for (int i = 1; i <= n; ++i) {
+                const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
+                du += gv;
+                const float dt = (float)i * hp.fi;
+                float coef = 1.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    coef *= dt / (float)(k + 1);
+                    Gk[k][e] = fmaf(gv, coef, Gk[k][e]);
+                }
+            }
+            if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
         }
+        for (int k = 0; k < hp.K; ++k) Vec4<TA>::store(reinterpret_cast<TA*>(hp.G[k]) + (size_t)row * kHeadPad + o4, Gk[k]);
     }
 }
 
 // ---- first patch conv backward (enc_conv_1, enc_dec_cnn.py:220-221) ----------------------------------------
-// im2col of the input patches (fp32 [rows][K1], K1 = k0*k0*D, column order (c, c', d) as the packed conv weight):
-// the dW1 operand of the generic wgrad kernel.
+// im2col of the input patches, TA [rows][kHeadPad] zero-padded (K1 = k0*k0*D columns in the packed conv-weight
+// order (c, c', d)): the B operand of the dW1 weight-gradient GEMM.
+template <typename TA>
 __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
-                                                           float* __restrict__ cols, long long rows_total) {
+                                                           TA* __restrict__ cols, long long rows_total) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_total) return;
     long long tkn = row / g.R1;
@@ -732,22 +717,25 @@ __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restri
     const size_t HW = (size_t)g.H * g.W;
     const float* xin = x + (size_t)bt * g.D * HW;
     const int K1 = g.k0 * g.k0 * g.D;
-    int kk = 0;
-    for (int c = 0; c < g.k0; ++c)
-        for (int cp = 0; cp < g.k0; ++cp)
-            for (int d = 0; d < g.D; ++d, ++kk)
-                cols[(size_t)row * K1 + kk] = xin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)];
+    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int kk = o4 + e;
+            if (kk >= K1) continue;
+            const int d = kk % g.D;
+            const int cp = (kk / g.D) % g.k0;
+            const int c = kk / (g.D * g.k0);
+            v[e] = xin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)];
+        }
+        Vec4<TA>::store(cols + (size_t)row * kHeadPad + o4, v);
+    }
 }
 
-// grad_input[patch] += sum_c da1[row][c] * W1[c][kk]   (one thread per stage-1 row; patches do not overlap)
+// grad_input[patch] += dpatch[row][kk]   (dpatch = da1 * W1, a thin GEMM; patches do not overlap)
 template <typename TA>
-__global__ void __launch_bounds__(128) conv1_dinput_kernel(const TA* __restrict__ da1, PatchGeom g,
-                                                           const float* __restrict__ w1p /* [C1][K1] */, int C1,
+__global__ void __launch_bounds__(128) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
                                                            float* __restrict__ grad_input, long long rows_total) {
-    extern __shared__ __align__(16) float smem[];
-    const int K1 = g.k0 * g.k0 * g.D;
-    for (int i = threadIdx.x; i < C1 * K1; i += blockDim.x) smem[i] = w1p[i];
-    __syncthreads();
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_total) return;
     long long tkn = row / g.R1;
@@ -759,23 +747,20 @@ __global__ void __launch_bounds__(128) conv1_dinput_kernel(const TA* __restrict_
     stage1_row_to_hw(g, hpp, wp, r, h1, w1);
     const size_t HW = (size_t)g.H * g.W;
     float* gin = grad_input + (size_t)bt * g.D * HW;
-    float acc[64];       // K1 <= 64
-    for (int kk = 0; kk < K1; ++kk) acc[kk] = 0.f;
-    const TA* dr = da1 + (size_t)row * C1;
-    for (int c = 0; c < C1; c += 4) {
-        float d4[4];
-        Vec4<TA>::load(dr + c, d4);
+    const int K1 = g.k0 * g.k0 * g.D;
+    for (int o4 = 0; o4 < K1; o4 += 4) {
+        float v[4];
+        Vec4<TA>::load(dpatch + (size_t)row * kHeadPad + o4, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float* wr = smem + (c + j) * K1;
-            for (int kk = 0; kk < K1; ++kk) acc[kk] = fmaf(d4[j], wr[kk], acc[kk]);
+        for (int e = 0; e < 4; ++e) {
+            const int kk = o4 + e;
+            if (kk >= K1) continue;
+            const int d = kk % g.D;
+            const int cp = (kk / g.D) % g.k0;
+            const int c = kk / (g.D * g.k0);
+            gin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)] += v[e];
         }
     }
-    int kk = 0;
-    for (int c = 0; c < g.k0; ++c)
-        for (int cp = 0; cp < g.k0; ++cp)
-            for (int d = 0; d < g.D; ++d, ++kk)
-                gin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)] += acc[kk];
 }
 
 // ---- generic weight gradient: C[N][K] += A[M][N]^T * B[M][K]  (split over M, fp32 atomics) -------------------
@@ -890,15 +875,18 @@ __global__ void __launch_bounds__(256) unpack_grads_kernel(const UnpackDesc* __r
     }
 }
 
-// transposed copies of the packed GEMM weights for the input-gradient GEMMs:  dst[k][n] = src[n][k]
-struct TransDesc { long long src_off, dst_off; int rows, cols; };
+// derived copies of the packed GEMM weights for the backward GEMMs, zero-padded to [dst_rows][dst_ld]:
+//   transpose = 1:  dst[k][r] = src[r][k]   (input-gradient GEMMs: dX = dY W)
+//   transpose = 0:  dst[r][k] = src[r][k]   (padding only)
+struct TransDesc { long long src_off, dst_off; int rows, cols, dst_rows, dst_ld, transpose; };
 __global__ void __launch_bounds__(256) transpose_packed_kernel(const TransDesc* __restrict__ descs, float* __restrict__ arena,
                                                                __nv_bfloat16* __restrict__ arena_bf16) {
     const TransDesc d = descs[blockIdx.y];
-    const long long n = (long long)d.rows * d.cols;
+    const long long n = (long long)d.dst_rows * d.dst_ld;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i / d.rows), r = (int)(i % d.rows);      // dst index i = k*rows + r
-        const float v = arena[d.src_off + (long long)r * d.cols + k];
+        const int a = (int)(i / d.dst_ld), b = (int)(i % d.dst_ld);      // dst[a][b]
+        const int r = d.transpose ? b : a, k = d.transpose ? a : b;      // src[r][k]
+        const float v = (r < d.rows && k < d.cols) ? arena[d.src_off + (long long)r * d.cols + k] : 0.f;
         arena[d.dst_off + i] = v;
         if (arena_bf16) arena_bf16[d.dst_off + i] = __float2bfloat16_rn(v);
     }

@@ -87,6 +87,7 @@ struct OrderPlan {
     int64_t intw[3], intb[3];
     int64_t mod[8];       // scale{0.w,0.b,2.w,2.b}, shift{...}
     int64_t decwT[2], intwT[2];
+    int64_t w3pad = 0;
 };
 
 }  // namespace
@@ -187,11 +188,14 @@ int64_t add_param(tante_handle_s* h, const std::string& name, std::vector<int64_
     return p.off;
 }
 
-// [cols][rows] copy of the packed [rows][cols] GEMM weight at `src` (filled by transpose_packed_kernel at pack time)
-int64_t add_trans(tante_handle_s* h, int64_t src, int rows, int cols) {
+// derived copy of the packed [rows][cols] GEMM weight at `src` (filled by transpose_packed_kernel at pack time):
+// transposed [cols][rows] by default; dst_rows / dst_ld > 0 zero-pad the destination.
+int64_t add_trans(tante_handle_s* h, int64_t src, int rows, int cols, int transpose = 1, int dst_rows = 0, int dst_ld = 0) {
     TransDesc d;
-    d.src_off = src; d.dst_off = h->arena_elems; d.rows = rows; d.cols = cols;
-    h->arena_elems += ((int64_t)rows * cols + 63) / 64 * 64;
+    d.src_off = src; d.dst_off = h->arena_elems; d.rows = rows; d.cols = cols; d.transpose = transpose;
+    d.dst_rows = dst_rows > 0 ? dst_rows : (transpose ? cols : rows);
+    d.dst_ld = dst_ld > 0 ? dst_ld : (transpose ? rows : cols);
+    h->arena_elems += ((int64_t)d.dst_rows * d.dst_ld + 63) / 64 * 64;
     h->tdescs.push_back(d);
     return d.dst_off;
 }
@@ -240,6 +244,10 @@ void build_plan(tante_handle_s* h) {
         h->enc_w[i] = add_param(h, p + "weight", {ech[i + 1], ech[i], k[i], k[i]}, PACK_CONV, ech[i + 1], ech[i], k[i]);
         h->enc_b[i] = add_param(h, p + "bias", {ech[i + 1]});
         if (i > 0) h->enc_wT[i] = add_trans(h, h->enc_w[i], ech[i + 1], ech[i] * k[i] * k[i]);
+        else {
+            REQUIRE(k[0] * k[0] * D <= kHeadPad, "n_fields too large for the padded first-conv backward (k0*k0*D <= 64)");
+            h->enc_wT[0] = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 1, kHeadPad, ech[1]);   // [64 (K1 pad)][C1]
+        }
     }
     const char* fn[2] = {"condition_to_scale", "condition_to_shift"};
     auto add_film = [&](const std::string& pre, int64_t* out) {
@@ -307,6 +315,8 @@ void build_plan(tante_handle_s* h) {
                 h->garena_elems -= (bp3.gnumel + 63) / 64 * 64;
                 bp3.gnumel = (int64_t)kk * kk * dch[i + 1]; bp3.gmode = PACK_BIAS_REP; bp3.gd0 = dch[i + 1]; bp3.gk = kk;
                 h->garena_elems += (bp3.gnumel + 63) / 64 * 64;
+                // [C1][64]: the packed [C1][k0*k0*D] weight zero-padded along its columns (dz = G * W3^T as a GEMM)
+                op.w3pad = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 0, dch[i], kHeadPad);
             }
         }
         if (!c.deg) {
@@ -674,13 +684,28 @@ void wgrad(tante_handle_s* h, const TA* A, int lda, const TA* Bm, int ldb, float
            cudaStream_t st) {
     ProfScope ps(h, st, 2.0 * (double)M * N * K);
     if constexpr (sizeof(TA) == 2) {
-        if (wgrad_tc_supported(M, N, K, lda, ldb)) {
-            CK(launch_wgrad_tc(A, lda, Bm, ldb, out, K, M, N, K, h->num_sms, st));
+        if (wgrad_tc_supported(M, N, K, K, lda, ldb, K)) {
+            CK(launch_wgrad_tc(A, lda, Bm, ldb, out, K, M, N, K, K, h->num_sms, st));
             h->launches++;
             return;
         }
     }
     CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, K, M, N, K, h->num_sms, st)));
+    h->launches++;
+}
+// same with a zero-padded B operand: B is stored [M][Kb] (Kb % 64 == 0), only the first Kc columns of dW are kept
+template <typename TA>
+void wgrad_pad(tante_handle_s* h, const TA* A, int lda, int N, const TA* Bm, int ldb, int Kb, float* out, int ldc, int Kc,
+               long long M, cudaStream_t st) {
+    ProfScope ps(h, st, 2.0 * (double)M * N * Kc);
+    if constexpr (sizeof(TA) == 2) {
+        if (wgrad_tc_supported(M, N, Kb, Kc, lda, ldb, ldc)) {
+            CK(launch_wgrad_tc(A, lda, Bm, ldb, out, ldc, M, N, Kb, Kc, h->num_sms, st));
+            h->launches++;
+            return;
+        }
+    }
+    CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, ldc, M, N, Kc, h->num_sms, st)));
     h->launches++;
 }
 // dX = dY * W via the transposed packed weight (no bias)
@@ -828,9 +853,10 @@ void backward_alloc(tante_handle_s* h, int B) {
     dev_alloc(h, h->g2, tokens * C * es);
     dev_alloc(h, h->gq, tokens * std::max(3 * C, g.R2 * C2) * es);
     dev_alloc(h, h->ga1, tokens * g.R1 * C1 * es);
-    dev_alloc(h, h->cols, tokens * g.R1 * NO * 4);
+    (void)NO;
+    dev_alloc(h, h->cols, tokens * g.R1 * kHeadPad * es);
     dev_alloc(h, h->hz, (size_t)h->K * BL * g.R1 * C1 * es);
-    dev_alloc(h, h->hG, (size_t)h->K * BL * g.R1 * NO * 4);
+    dev_alloc(h, h->hG, (size_t)h->K * BL * g.R1 * kHeadPad * es);
     dev_alloc(h, h->hz1, BL * g.R2 * C2 * es);
     dev_alloc(h, h->hd, BL * C * es);
     dev_alloc(h, h->hi1, BL * (C / 2) * es);
@@ -1026,16 +1052,10 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     // ---- Taylor head: all orders in one pass over the frame gradients ----
     {
         HeadBwdParams hp{};
-        for (int k = 0; k < K; ++k) {
-            hp.zpre[k] = tp.ord[k].z2pre.p;
-            hp.w3[k] = AF(h, h->orders[k].decw[2]);
-            hp.dz[k] = TP<TA>(h->hz) + (size_t)k * rows1 * C1;
-            hp.G[k] = FP(h->hG) + (size_t)k * rows1 * NO;
-        }
+        for (int k = 0; k < K; ++k) hp.G[k] = TP<TA>(h->hG) + (size_t)k * rows1 * kHeadPad;
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
         hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); hp.grad_input = grad_input;
-        const size_t smem = (size_t)K * C1 * NO * sizeof(float);
-        head_bwd_kernel<TA><<<blocks_for(rows1, 128), 128, smem, st>>>(hp, g, C1, rows1);
+        head_gather_kernel<TA><<<blocks_for(rows1, 128), 128, 0, st>>>(hp, g, rows1);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1043,11 +1063,12 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         const OrderPlan& op = h->orders[o];
         OrderTape& ot = tp.ord[o];
         TA* dz = TP<TA>(h->hz) + (size_t)o * rows1 * C1;
-        float* G = FP(h->hG) + (size_t)o * rows1 * NO;
-        // dec_conv_3: d_k = z2act * W3 + b3
-        CK((launch_wgrad_simt<TA, float>(TP<TA>(ot.z2act), C1, G, NO, GA(h, op.decw[2]), NO, rows1, C1, NO, h->num_sms, st)));
-        h->launches++;
-        launch_colsum<float>(h, G, NO, rows1, NO, GA(h, op.decb[2]), st);
+        TA* G = TP<TA>(h->hG) + (size_t)o * rows1 * kHeadPad;
+        // dec_conv_3: d_k = z2act * W3 + b3  ->  dW3 = z2act^T G, db3 = colsum(G), dz2 = (G W3^T) o gelu'(z2pre)
+        wgrad_pad<TA>(h, TP<TA>(ot.z2act), C1, C1, G, kHeadPad, kHeadPad, GA(h, op.decw[2]), NO, NO, rows1, st);
+        launch_colsum<TA>(h, G, kHeadPad, rows1, NO, GA(h, op.decb[2]), st);
+        gemm_dx<TA>(h, G, kHeadPad, op.w3pad, dz, C1, (int)rows1, C1, kHeadPad, st);
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, dz, TP<TA>(ot.z2pre), rows1 * C1, st);
         // dec_conv_2: z2pre[M2, N2] = z1act[M2, C2] * Wd2^T + b
         const int M2 = BL * g.R2, N2 = g.k1 * g.k1 * C1;
         wgrad<TA>(h, dz, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st);
@@ -1156,14 +1177,16 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     gemm_dx<TA>(h, gq, C2, h->enc_wT[1], ga1, K2, M2, K2, C2, st);
     launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), rows_in * C1, st);
     launch_colsum<TA>(h, ga1, C1, rows_in, C1, GA(h, h->enc_b[0]), st);
-    conv1_im2col_kernel<<<blocks_for(rows_in, 128), 128, 0, st>>>(input, g, FP(h->cols), rows_in);
+    TA* cols = TP<TA>(h->cols);
+    conv1_im2col_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(input, g, cols, rows_in);
     CK(cudaGetLastError());
     h->launches++;
-    CK((launch_wgrad_simt<TA, float>(ga1, C1, FP(h->cols), NO, GA(h, h->enc_w[0]), NO, rows_in, C1, NO, h->num_sms, st)));
-    h->launches++;
+    wgrad_pad<TA>(h, ga1, C1, C1, cols, kHeadPad, kHeadPad, GA(h, h->enc_w[0]), NO, NO, rows_in, st);
     if (grad_input) {
-        conv1_dinput_kernel<TA><<<blocks_for(rows_in, 128), 128, (size_t)C1 * NO * sizeof(float), st>>>(
-            ga1, g, AF(h, h->enc_w[0]), C1, grad_input, rows_in);
+        // dpatch[rows, 64 (K1 padded)] = da1[rows, C1] * W1[C1][K1]  (thin GEMM), then scatter-add into the pixels
+        REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
+        gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], cols, kHeadPad, (int)rows_in, kHeadPad, C1, st);
+        conv1_col2im_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(cols, g, grad_input, rows_in);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1197,8 +1220,6 @@ void set_smem_attrs() {
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(propagator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-    CK(cudaFuncSetAttribute(head_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-    CK(cudaFuncSetAttribute(head_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
 #define ATTBATTR(TA, HDv) CK(cudaFuncSetAttribute(attention_bwd_kernel<TA, HDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024))
     ATTBATTR(float, 16); ATTBATTR(float, 32); ATTBATTR(float, 64);
     ATTBATTR(__nv_bfloat16, 16); ATTBATTR(__nv_bfloat16, 32); ATTBATTR(__nv_bfloat16, 64);
@@ -1629,9 +1650,11 @@ int tante_test_wgrad(int32_t use_tc, const void* A, const void* Bm, float* C, in
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         for (int i = 0; i < std::max(1, iters); ++i) {
             if (use_tc == 1) {
-                REQUIRE(wgrad_tc_supported(M, N, K, N, K), "shape not covered by the tcgen05 wgrad kernel");
-                CK(launch_wgrad_tc(reinterpret_cast<const __nv_bfloat16*>(A), N, reinterpret_cast<const __nv_bfloat16*>(Bm), K,
-                                   C, K, M, N, K, sms, st));
+                // B is stored zero-padded to a multiple of 64 columns by the caller when K % 64 != 0
+                const int Kb = (K + 63) / 64 * 64;
+                REQUIRE(wgrad_tc_supported(M, N, Kb, K, N, Kb, K), "shape not covered by the tcgen05 wgrad kernel");
+                CK(launch_wgrad_tc(reinterpret_cast<const __nv_bfloat16*>(A), N, reinterpret_cast<const __nv_bfloat16*>(Bm), Kb,
+                                   C, K, M, N, Kb, K, sms, st));
             } else if (use_tc == 2) {
                 CK((launch_wgrad_simt<__nv_bfloat16, __nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(A), N,
                                                                     reinterpret_cast<const __nv_bfloat16*>(Bm), K, C, K, M, N,

@@ -156,31 +156,36 @@ static cudaError_t wg_set_attrs() {
     return cudaSuccess;
 }
 
-// true when the shape is covered by the tensor-core kernel (otherwise the caller uses wgrad_simt)
-static bool wgrad_tc_supported(long long M, int N, int K, int lda, int ldb) {
-    return M >= 64 && M < (1LL << 31) && N % 128 == 0 && K % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0;
+// true when the shape is covered by the tensor-core kernel (otherwise the caller uses wgrad_simt).
+// N (columns of A = rows of dW) must be a multiple of 64: an odd 64-column half-tile is zero-filled by TMA on load
+// and clipped on the reduce-store.  Kb = columns of B as stored (multiple of 64, zero-padded by the producer),
+// Kc <= Kb = columns of dW actually kept (the rest is clipped by the output tensor map).
+static bool wgrad_tc_supported(long long M, int N, int Kb, int Kc, int lda, int ldb, int ldc) {
+    return M >= 64 && M < (1LL << 31) && N % 64 == 0 && Kb % 64 == 0 && Kc <= Kb && Kc >= 1 && lda % 8 == 0 &&
+           ldb % 8 == 0 && ldc % 4 == 0;
 }
 
 static cudaError_t launch_wgrad_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm, int ldb, float* Cout,
-                                   int ldc, long long M, int N, int K, int num_sms, cudaStream_t st) {
-    if (!wgrad_tc_supported(M, N, K, lda, ldb)) return cudaErrorInvalidValue;
-    const int BN = (K % 256 == 0) ? 256 : (K % 128 == 0 ? 128 : 64);
+                                   int ldc, long long M, int N, int Kb, int Kc, int num_sms, cudaStream_t st) {
+    if (!wgrad_tc_supported(M, N, Kb, Kc, lda, ldb, ldc)) return cudaErrorInvalidValue;
+    const int BN = (Kb % 256 == 0) ? 256 : (Kb % 128 == 0 ? 128 : 64);
     const int stage_bytes = (2 + BN / 64) * kWgBox;
     int nstage = (int)((227 * 1024 - 2048) / stage_bytes);
     nstage = nstage > 6 ? 6 : nstage;
     const size_t smem = (size_t)nstage * stage_bytes + 256 + 1024;
     const int m_tiles = (int)((M + kWgRows - 1) / kWgRows);
-    const int tiles_xy = (N / 128) * (K / BN);
+    const int n_tiles = (N + 127) / 128;
+    const int tiles_xy = n_tiles * (Kb / BN);
     int splits = std::max(1, num_sms / tiles_xy);
     splits = std::min(splits, m_tiles);
     const int per = (m_tiles + splits - 1) / splits;
     splits = (m_tiles + per - 1) / per;
     CUtensorMap tmA, tmB, tmC;
     if (!make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (int)M, N, lda, 64, kWgRows)) return cudaErrorInvalidValue;
-    if (!make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bm, (int)M, K, ldb, 64, kWgRows)) return cudaErrorInvalidValue;
-    if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, K, ldc, 32, 32)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bm, (int)M, Kb, ldb, 64, kWgRows)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, Kc, ldc, 32, 32)) return cudaErrorInvalidValue;
     { cudaError_t e = wg_set_attrs(); if (e != cudaSuccess) return e; }
-    dim3 grid(N / 128, K / BN, splits);
+    dim3 grid(n_tiles, Kb / BN, splits);
     switch (BN) {
         case 256: wgrad_tc_kernel<256><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage); break;
         case 128: wgrad_tc_kernel<128><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage); break;

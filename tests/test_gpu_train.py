@@ -199,7 +199,7 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
 
 
 @pytest.mark.parametrize("shape", [(4096, 256, 256), (8192 + 64, 768, 256), (5000, 256, 512), (3000, 128, 256),
-                                   (2048, 512, 256), (1024, 256, 128), (777, 256, 64)])
+                                   (2048, 512, 256), (1024, 256, 128), (777, 256, 64), (4100, 64, 44), (999, 64, 64)])
 def test_wgrad_tcgen05_matches_torch(shape):
     """dW[N,K] += A[M,N]^T B[M,K] on tcgen05 with MN-major operands + TMA reduce-add, accumulating into C."""
     import ctypes
@@ -211,7 +211,11 @@ def test_wgrad_tcgen05_matches_torch(shape):
     Bm = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     C0 = torch.randn(N, K, device="cuda", generator=g)
     C = C0.clone()
-    _abi.check(lib.tante_test_wgrad(1, A.data_ptr(), Bm.data_ptr(), C.data_ptr(), M, N, K, 1,
+    Bp = Bm
+    if K % 64:      # the producer zero-pads B to a multiple of 64 columns; only the first K columns of dW are kept
+        Bp = torch.zeros(M, (K + 63) // 64 * 64, device="cuda", dtype=torch.bfloat16)
+        Bp[:, :K] = Bm
+    _abi.check(lib.tante_test_wgrad(1, A.data_ptr(), Bp.data_ptr(), C.data_ptr(), M, N, K, 1,
                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = C0.double() + A.double().t() @ Bm.double()

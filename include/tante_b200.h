@@ -177,9 +177,9 @@ TANTE_API int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const 
 
 /* Test hook: weight-gradient GEMM stand-alone, C[N,K] += A[M,N]^T * B[M,K] (C is accumulated into).
  * use_tc = 1: tcgen05 kernel (bf16 MN-major operands, TMA reduce-add), 2: SIMT kernel on bf16 operands,
- * 0: SIMT kernel on f32 operands. */
-TANTE_API int tante_test_wgrad(int32_t use_tc, const void* A, const void* B, float* C, int64_t M, int32_t N, int32_t K,
-                     int32_t iters, void* stream);
+ * 0: SIMT kernel on f32 operands.  `bias` (nullable, tcgen05 kernel only): f32[N] += column sums of A. */
+TANTE_API int tante_test_wgrad(int32_t use_tc, const void* A, const void* B, float* C, float* bias, int64_t M, int32_t N,
+                     int32_t K, int32_t iters, void* stream);
 
 #ifdef __cplusplus
 }

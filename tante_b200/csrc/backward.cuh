@@ -286,62 +286,72 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TA* __restrict__ dy, 
     }
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const long long nwarps = (long long)gridDim.x * blockDim.x / kWarp;
-    for (long long r = warp0; r < rows; r += nwarps) {
-        float xv[MAXV][4], dv[MAXV][4];
-        float s = 0.f;
+    constexpr int RPI = 2;       // rows in flight per warp iteration (memory-level parallelism: the kernel is HBM-bound)
+    for (long long rb = warp0; rb < rows; rb += nwarps * RPI) {
+        float xv[RPI][MAXV][4], dv[RPI][MAXV][4], ov[RPI][MAXV][4];
+        long long rr[RPI];
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = (i * kWarp + lane) * 4;
-            if (c < C) {
-                Vec4<float>::load(x + (size_t)r * C + c, xv[i]);
-                Vec4<TA>::load(dy + (size_t)r * C + c, dv[i]);
-                s += (xv[i][0] + xv[i][1]) + (xv[i][2] + xv[i][3]);
-            } else {
+        for (int u = 0; u < RPI; ++u) {
+            rr[u] = rb + u * nwarps;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { xv[i][j] = 0.f; dv[i][j] = 0.f; }
-            }
-        }
-        const float mean = warp_sum(s) / (float)C;
-        float q = 0.f;
+            for (int i = 0; i < MAXV; ++i) {
+                const int c = (i * kWarp + lane) * 4;
+                if (c < C && rr[u] < rows) {
+                    Vec4<float>::load(x + (size_t)rr[u] * C + c, xv[u][i]);
+                    Vec4<TA>::load(dy + (size_t)rr[u] * C + c, dv[u][i]);
+                    Vec4<float>::load(dxs + (size_t)rr[u] * C + c, ov[u][i]);
+                } else {
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = (i * kWarp + lane) * 4;
-            if (c < C) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float d = xv[i][j] - mean; q = fmaf(d, d, q); }
-            }
-        }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = (i * kWarp + lane) * 4;
-            if (c < C) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float xh = (xv[i][j] - mean) * rstd;
-                    const float gy = dv[i][j] * gm[i][j];
-                    s1 += gy;
-                    s2 = fmaf(gy, xh, s2);
-                    ag[i][j] = fmaf(dv[i][j], xh, ag[i][j]);
-                    ab[i][j] += dv[i][j];
-                    xv[i][j] = xh;          // keep xhat
-                    dv[i][j] = gy;          // keep gy
+                    for (int j = 0; j < 4; ++j) { xv[u][i][j] = 0.f; dv[u][i][j] = 0.f; ov[u][i][j] = 0.f; }
                 }
             }
         }
-        s1 = warp_sum(s1) / (float)C;
-        s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int c = (i * kWarp + lane) * 4;
-            if (c < C) {
-                float o[4];
-                Vec4<float>::load(dxs + (size_t)r * C + c, o);
+        for (int u = 0; u < RPI; ++u) {
+            if (rr[u] >= rows) continue;        // warp-uniform
+            float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) o[j] += rstd * (dv[i][j] - s1 - xv[i][j] * s2);
-                Vec4<float>::store(dxs + (size_t)r * C + c, o);
-                if (dxb) Vec4<TA>::store(dxb + (size_t)r * C + c, o);
+            for (int i = 0; i < MAXV; ++i) s += (xv[u][i][0] + xv[u][i][1]) + (xv[u][i][2] + xv[u][i][3]);
+            const float mean = warp_sum(s) / (float)C;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int c = (i * kWarp + lane) * 4;
+                if (c < C) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float d = xv[u][i][j] - mean; q = fmaf(d, d, q); }
+                }
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int c = (i * kWarp + lane) * 4;
+                if (c < C) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float xh = (xv[u][i][j] - mean) * rstd;
+                        const float gy = dv[u][i][j] * gm[i][j];
+                        s1 += gy;
+                        s2 = fmaf(gy, xh, s2);
+                        ag[i][j] = fmaf(dv[u][i][j], xh, ag[i][j]);
+                        ab[i][j] += dv[u][i][j];
+                        xv[u][i][j] = xh;          // keep xhat
+                        dv[u][i][j] = gy;          // keep gy
+                    }
+                }
+            }
+            s1 = warp_sum(s1) / (float)C;
+            s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const int c = (i * kWarp + lane) * 4;
+                if (c < C) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ov[u][i][j] += rstd * (dv[u][i][j] - s1 - xv[u][i][j] * s2);
+                    Vec4<float>::store(dxs + (size_t)rr[u] * C + c, ov[u][i]);
+                    if (dxb) Vec4<TA>::store(dxb + (size_t)rr[u] * C + c, ov[u][i]);
+                }
             }
         }
     }
@@ -653,113 +663,114 @@ struct HeadBwdParams {
     float* grad_input;              // (B, T, D, H, W) or null
 };
 
-template <typename TA>
-__global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows_total) return;
-    const int NO = g.k0 * g.k0 * g.D;
+// thread = (stage-1 row, group of 4 consecutive outputs): 16 threads per row, coalesced 128-byte row writes
+__device__ __forceinline__ void patch_pixel(const PatchGeom& g, int h1, int w1, int oo, int& d, size_t& pix) {
+    d = oo % g.D;
+    const int cp = (oo / g.D) % g.k0;
+    const int c = oo / (g.D * g.k0);
+    pix = (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp);
+}
+__device__ __forceinline__ void row_coords(const PatchGeom& g, long long row, long long& bt, int& h1, int& w1) {
     long long tkn = row / g.R1;
     const int r = (int)(row % g.R1);
     const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
     const int hpp = (int)(tkn % g.Hp);
-    const int b = (int)(tkn / g.Hp);
-    int h1, w1;
+    bt = tkn / g.Hp;
     stage1_row_to_hw(g, hpp, wp, r, h1, w1);
-    const int n = min(hp.n_arr[b], hp.n_cap);
-    const size_t HW = (size_t)g.H * g.W;
-    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
-        float Gk[4][4];                 // [order][4 consecutive outputs]
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) Gk[k][e] = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int oo = o4 + e;
-            if (oo >= NO) continue;
-            const int d = oo % g.D;
-            const int cp = (oo / g.D) % g.k0;
-            const int c = oo / (g.D * g.k0);
-            const size_t pix = (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp);
-            float du = 0.f;
-            for (int i = 1; i <= n; ++i) {
-                const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
-                du += gv;
-                const float dt = (float)i * hp.fi;
-                float coef = 1.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    coef *= dt / (float)(k + 1);
-                    Gk[k][e] = fmaf(gv, coef, Gk[k][e]);
-                }
-            }
-            if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
-        }
-        for (int k = 0; k < hp.K; ++k) Vec4<TA>::store(reinterpret_cast<TA*>(hp.G[k]) + (size_t)row * kHeadPad + o4, Gk[k]);
-    }
 }
 
-// ---- first patch conv backward (enc_conv_1, enc_dec_cnn.py:220-221) ----------------------------------------
-// im2col of the input patches, TA [rows][kHeadPad] zero-padded (K1 = k0*k0*D columns in the packed conv-weight
-// order (c, c', d)): the B operand of the dW1 weight-gradient GEMM.
 template <typename TA>
-__global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
-                                                           TA* __restrict__ cols, long long rows_total) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = gid / (kHeadPad / 4);
+    const int o4 = (int)(gid % (kHeadPad / 4)) * 4;
     if (row >= rows_total) return;
-    long long tkn = row / g.R1;
-    const int r = (int)(row % g.R1);
-    const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
-    const int hpp = (int)(tkn % g.Hp);
-    const long long bt = tkn / g.Hp;
+    const int NO = g.k0 * g.k0 * g.D;
+    long long b;
     int h1, w1;
-    stage1_row_to_hw(g, hpp, wp, r, h1, w1);
+    row_coords(g, row, b, h1, w1);          // here rows are (b, hp, wp, r): "bt" is the sample index
+    const int n = min(hp.n_arr[b], hp.n_cap);
+    const size_t HW = (size_t)g.H * g.W;
+    float Gk[4][4];                 // [order][4 consecutive outputs]
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gk[k][e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int oo = o4 + e;
+        if (oo >= NO) continue;
+        int d; size_t pix;
+        patch_pixel(g, h1, w1, oo, d, pix);
+        float du = 0.f;
+        for (int i = 1; i <= n; ++i) {
+            const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
+            du += gv;
+            const float dt = (float)i * hp.fi;
+            float coef = 1.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                coef *= dt / (float)(k + 1);
+                Gk[k][e] = fmaf(gv, coef, Gk[k][e]);
+            }
+        }
+        if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
+    }
+    for (int k = 0; k < hp.K; ++k) Vec4<TA>::store(reinterpret_cast<TA*>(hp.G[k]) + (size_t)row * kHeadPad + o4, Gk[k]);
+}
+
+// ---- first patch conv (enc_conv_1, enc_dec_cnn.py:220-221) as im2col + GEMM in training ----------------------
+// im2col of the input patches, TA [rows][kHeadPad] zero-padded (K1 = k0*k0*D columns in the packed conv-weight
+// order (c, c', d)): the A operand of the forward conv GEMM and the B operand of its weight-gradient GEMM.
+template <typename TA>
+__global__ void __launch_bounds__(256) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
+                                                           TA* __restrict__ cols, long long rows_total) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = gid / (kHeadPad / 4);
+    const int o4 = (int)(gid % (kHeadPad / 4)) * 4;
+    if (row >= rows_total) return;
+    long long bt;
+    int h1, w1;
+    row_coords(g, row, bt, h1, w1);
     const size_t HW = (size_t)g.H * g.W;
     const float* xin = x + (size_t)bt * g.D * HW;
     const int K1 = g.k0 * g.k0 * g.D;
-    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int kk = o4 + e;
-            if (kk >= K1) continue;
-            const int d = kk % g.D;
-            const int cp = (kk / g.D) % g.k0;
-            const int c = kk / (g.D * g.k0);
-            v[e] = xin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)];
-        }
-        Vec4<TA>::store(cols + (size_t)row * kHeadPad + o4, v);
+    for (int e = 0; e < 4; ++e) {
+        const int kk = o4 + e;
+        if (kk >= K1) continue;
+        int d; size_t pix;
+        patch_pixel(g, h1, w1, kk, d, pix);
+        v[e] = xin[(size_t)d * HW + pix];
     }
+    Vec4<TA>::store(cols + (size_t)row * kHeadPad + o4, v);
 }
 
 // grad_input[patch] += dpatch[row][kk]   (dpatch = da1 * W1, a thin GEMM; patches do not overlap)
 template <typename TA>
-__global__ void __launch_bounds__(128) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
+__global__ void __launch_bounds__(256) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
                                                            float* __restrict__ grad_input, long long rows_total) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = gid / (kHeadPad / 4);
+    const int o4 = (int)(gid % (kHeadPad / 4)) * 4;
     if (row >= rows_total) return;
-    long long tkn = row / g.R1;
-    const int r = (int)(row % g.R1);
-    const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
-    const int hpp = (int)(tkn % g.Hp);
-    const long long bt = tkn / g.Hp;
+    const int K1 = g.k0 * g.k0 * g.D;
+    if (o4 >= K1) return;
+    long long bt;
     int h1, w1;
-    stage1_row_to_hw(g, hpp, wp, r, h1, w1);
+    row_coords(g, row, bt, h1, w1);
     const size_t HW = (size_t)g.H * g.W;
     float* gin = grad_input + (size_t)bt * g.D * HW;
-    const int K1 = g.k0 * g.k0 * g.D;
-    for (int o4 = 0; o4 < K1; o4 += 4) {
-        float v[4];
-        Vec4<TA>::load(dpatch + (size_t)row * kHeadPad + o4, v);
+    float v[4];
+    Vec4<TA>::load(dpatch + (size_t)row * kHeadPad + o4, v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int kk = o4 + e;
-            if (kk >= K1) continue;
-            const int d = kk % g.D;
-            const int cp = (kk / g.D) % g.k0;
-            const int c = kk / (g.D * g.k0);
-            gin[(size_t)d * HW + (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp)] += v[e];
-        }
+    for (int e = 0; e < 4; ++e) {
+        const int kk = o4 + e;
+        if (kk >= K1) continue;
+        int d; size_t pix;
+        patch_pixel(g, h1, w1, kk, d, pix);
+        gin[(size_t)d * HW + pix] += v[e];
     }
 }
 

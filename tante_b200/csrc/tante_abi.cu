@@ -100,7 +100,7 @@ struct OrderTape {
     DevBuf dl, d32, dmod, i1, i2, rt, film, z1pre, z1act, z2pre, z2act;
 };
 struct Tape {
-    DevBuf a1pre, a1act, a2pre, a2act, v, n_arr;
+    DevBuf cols, a1pre, a1act, a2pre, a2act, v, n_arr;
     std::vector<OrderTape> ord;
     int B = 0;          // allocated batch
     int B_used = 0;     // batch of the taped forward
@@ -151,6 +151,7 @@ struct tante_handle_s {
     double prof_flops = 0;
     // ---- training ----
     int64_t enc_wT[3] = {0, 0, 0};
+    int64_t enc_w1pad = 0;                     // [C1][64]: first conv weight zero-padded along K (im2col GEMM)
     int64_t zero_off = 0;                      // 4096 zeros (bias of the input-gradient GEMMs)
     int64_t garena_elems = 0, flat_elems = 0;
     std::vector<TransDesc> tdescs;
@@ -247,6 +248,7 @@ void build_plan(tante_handle_s* h) {
         else {
             REQUIRE(k[0] * k[0] * D <= kHeadPad, "n_fields too large for the padded first-conv backward (k0*k0*D <= 64)");
             h->enc_wT[0] = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 1, kHeadPad, ech[1]);   // [64 (K1 pad)][C1]
+            h->enc_w1pad = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 0, ech[1], kHeadPad);  // [C1][64]
         }
     }
     const char* fn[2] = {"condition_to_scale", "condition_to_shift"};
@@ -679,34 +681,41 @@ void launch_colsum(tante_handle_s* h, const TA* x, int ld, long long M, int N, f
     h->launches++;
 }
 // dW[N][K] (+)= A[M][N]^T B[M][K] into the gradient arena
+// `bias_out` (nullable): also db[N] += column sums of A (fused into the tensor-core kernel, else a colsum launch)
 template <typename TA>
 void wgrad(tante_handle_s* h, const TA* A, int lda, const TA* Bm, int ldb, float* out, long long M, int N, int K,
-           cudaStream_t st) {
-    ProfScope ps(h, st, 2.0 * (double)M * N * K);
-    if constexpr (sizeof(TA) == 2) {
-        if (wgrad_tc_supported(M, N, K, K, lda, ldb, K)) {
-            CK(launch_wgrad_tc(A, lda, Bm, ldb, out, K, M, N, K, K, h->num_sms, st));
-            h->launches++;
-            return;
+           cudaStream_t st, float* bias_out = nullptr) {
+    {
+        ProfScope ps(h, st, 2.0 * (double)M * N * K);
+        if constexpr (sizeof(TA) == 2) {
+            if (wgrad_tc_supported(M, N, K, K, lda, ldb, K)) {
+                CK(launch_wgrad_tc(A, lda, Bm, ldb, out, K, M, N, K, K, h->num_sms, st, bias_out));
+                h->launches++;
+                return;
+            }
         }
+        CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, K, M, N, K, h->num_sms, st)));
+        h->launches++;
     }
-    CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, K, M, N, K, h->num_sms, st)));
-    h->launches++;
+    if (bias_out) launch_colsum<TA>(h, A, lda, M, N, bias_out, st);
 }
 // same with a zero-padded B operand: B is stored [M][Kb] (Kb % 64 == 0), only the first Kc columns of dW are kept
 template <typename TA>
 void wgrad_pad(tante_handle_s* h, const TA* A, int lda, int N, const TA* Bm, int ldb, int Kb, float* out, int ldc, int Kc,
-               long long M, cudaStream_t st) {
-    ProfScope ps(h, st, 2.0 * (double)M * N * Kc);
-    if constexpr (sizeof(TA) == 2) {
-        if (wgrad_tc_supported(M, N, Kb, Kc, lda, ldb, ldc)) {
-            CK(launch_wgrad_tc(A, lda, Bm, ldb, out, ldc, M, N, Kb, Kc, h->num_sms, st));
-            h->launches++;
-            return;
+               long long M, cudaStream_t st, float* bias_out = nullptr) {
+    {
+        ProfScope ps(h, st, 2.0 * (double)M * N * Kc);
+        if constexpr (sizeof(TA) == 2) {
+            if (wgrad_tc_supported(M, N, Kb, Kc, lda, ldb, ldc)) {
+                CK(launch_wgrad_tc(A, lda, Bm, ldb, out, ldc, M, N, Kb, Kc, h->num_sms, st, bias_out));
+                h->launches++;
+                return;
+            }
         }
+        CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, ldc, M, N, Kc, h->num_sms, st)));
+        h->launches++;
     }
-    CK((launch_wgrad_simt<TA, TA>(A, lda, Bm, ldb, out, ldc, M, N, Kc, h->num_sms, st)));
-    h->launches++;
+    if (bias_out) launch_colsum<TA>(h, A, lda, M, N, bias_out, st);
 }
 // dX = dY * W via the transposed packed weight (no bias)
 template <typename TA>
@@ -778,7 +787,7 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
 }
 
 void free_tape(Tape& tp) {
-    DevBuf* bufs[] = {&tp.a1pre, &tp.a1act, &tp.a2pre, &tp.a2act, &tp.v, &tp.n_arr};
+    DevBuf* bufs[] = {&tp.cols, &tp.a1pre, &tp.a1act, &tp.a2pre, &tp.a2act, &tp.v, &tp.n_arr};
     for (DevBuf* b : bufs) b->free();
     for (OrderTape& ot : tp.ord) {
         DevBuf* ob[] = {&ot.P[0], &ot.P[1], &ot.P[2], &ot.dl, &ot.d32, &ot.dmod, &ot.i1, &ot.i2, &ot.rt, &ot.film, &ot.z1pre,
@@ -799,6 +808,7 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
     const size_t BL = (size_t)B * h->L;
     const int C = h->C, C1 = h->C1, C2 = h->C2;
     const PatchGeom& g = h->geom;
+    dev_alloc(h, tp.cols, tokens * g.R1 * kHeadPad * es);
     dev_alloc(h, tp.a1pre, tokens * g.R1 * C1 * es);
     dev_alloc(h, tp.a1act, tokens * g.R1 * C1 * es);
     dev_alloc(h, tp.a2pre, tokens * g.R2 * C2 * es);
@@ -886,18 +896,14 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     constexpr bool kTensor = sizeof(TA) == 2;
     // --- encoder ---
     {
-        const int P = g.k0 * g.k1 * g.k2;
-        int WC = std::max(1, 128 / g.R1);
-        WC = std::min(WC, g.Wp);
-        const int K1 = g.k0 * g.k0 * g.D;
-        REQUIRE(C1 == 64, "patch embed kernel is specialised for embed_dim 256 (C/4 = 64)");
-        const size_t smem = (size_t)(((g.D * P * (P * WC + 1) + 3) & ~3) + C1 * K1 + C1) * sizeof(float) +
-                            (size_t)WC * g.R1 * C1 * sizeof(TA);
-        dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
-        patch_embed_conv1_kernel<TA, false><<<grid, 128, smem, st>>>(input, nullptr, g, AF(h, h->enc_w[0]),
-                                                                     AF(h, h->enc_b[0]), WC, TP<TA>(tp.a1pre));
+        // enc_conv_1 as im2col (kept for the weight gradient) + GEMM over the zero-padded patch matrix
+        const long long rows_in = (long long)tokens * g.R1;
+        REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv GEMM");
+        conv1_im2col_kernel<TA><<<blocks_for(rows_in * (kHeadPad / 4), 256), 256, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
         CK(cudaGetLastError());
         h->launches++;
+        EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
+        gemm<TA>(h, EPI_BIAS, TP<TA>(tp.cols), kHeadPad, h->enc_w1pad, tp.a1pre.p, C1, false, (int)rows_in, C1, kHeadPad, e1, st);
         launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), (long long)tokens * g.R1 * C1, st);
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
         gemm<TA>(h, EPI_BIAS, TP<TA>(tp.a1act), g.k1 * g.k1 * C1, h->enc_w[1], tp.a2pre.p, C2, false, tokens * g.R2, C2,
@@ -1055,7 +1061,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         for (int k = 0; k < K; ++k) hp.G[k] = TP<TA>(h->hG) + (size_t)k * rows1 * kHeadPad;
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
         hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); hp.grad_input = grad_input;
-        head_gather_kernel<TA><<<blocks_for(rows1, 128), 128, 0, st>>>(hp, g, rows1);
+        head_gather_kernel<TA><<<blocks_for(rows1 * (kHeadPad / 4), 256), 256, 0, st>>>(hp, g, rows1);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1071,16 +1077,14 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         launch_act_bwd<TA, ACT_GELU_ERF>(h, dz, TP<TA>(ot.z2pre), rows1 * C1, st);
         // dec_conv_2: z2pre[M2, N2] = z1act[M2, C2] * Wd2^T + b
         const int M2 = BL * g.R2, N2 = g.k1 * g.k1 * C1;
-        wgrad<TA>(h, dz, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st);
-        launch_colsum<TA>(h, dz, N2, M2, N2, GA(h, op.decb[1]), st);
+        wgrad<TA>(h, dz, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st, GA(h, op.decb[1]));
         TA* dz1 = TP<TA>(h->hz1);
         gemm_dx<TA>(h, dz, N2, op.decwT[1], dz1, C2, M2, C2, N2, st);
         launch_act_bwd<TA, ACT_GELU_ERF>(h, dz1, TP<TA>(ot.z1pre), (long long)M2 * C2, st);
         // dec_conv_1: z1pre[BL, N1] = dmod[BL, C] * Wd1^T + b
         const int N1 = g.k2 * g.k2 * C2;
         TA* dmod = h->cfg.deg ? TP<TA>(ot.dl) : TP<TA>(ot.dmod);
-        wgrad<TA>(h, dz1, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st);
-        launch_colsum<TA>(h, dz1, N1, BL, N1, GA(h, op.decb[0]), st);
+        wgrad<TA>(h, dz1, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st, GA(h, op.decb[0]));
         TA* hd = TP<TA>(h->hd);
         gemm_dx<TA>(h, dz1, N1, op.decwT[0], hd, C, BL, C, N1, st);
         if (!h->cfg.deg) {
@@ -1105,12 +1109,10 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
                 GA(h, op.intb[2]));
             CK(cudaGetLastError());
             h->launches++;
-            wgrad<TA>(h, hi2, C / 4, TP<TA>(ot.i1), C / 2, GA(h, op.intw[1]), BL, C / 4, C / 2, st);
-            launch_colsum<TA>(h, hi2, C / 4, BL, C / 4, GA(h, op.intb[1]), st);
+            wgrad<TA>(h, hi2, C / 4, TP<TA>(ot.i1), C / 2, GA(h, op.intw[1]), BL, C / 4, C / 2, st, GA(h, op.intb[1]));
             gemm_dx<TA>(h, hi2, C / 4, op.intwT[1], hi1, C / 2, BL, C / 2, C / 4, st);
             launch_act_bwd<TA, ACT_RELU>(h, hi1, TP<TA>(ot.i1), (long long)BL * (C / 2), st);
-            wgrad<TA>(h, hi1, C / 2, TP<TA>(ot.dl), C, GA(h, op.intw[0]), BL, C / 2, C, st);
-            launch_colsum<TA>(h, hi1, C / 2, BL, C / 2, GA(h, op.intb[0]), st);
+            wgrad<TA>(h, hi1, C / 2, TP<TA>(ot.dl), C, GA(h, op.intw[0]), BL, C / 2, C, st, GA(h, op.intb[0]));
             gemm_dx<TA>(h, hi1, C / 2, op.intwT[0], hd, C, BL, C, C / 2, st);
         }
         add_last_frame_kernel<TA><<<blocks_for((long long)BL * C / 4, 256), 256, 0, st>>>(hd, dxs, B, T, (long long)L * C);
@@ -1128,21 +1130,17 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             const float* x_in = FP(ot.X[2 * li]);
             const float* x_mid = FP(ot.X[2 * li + 1]);
             // MLP half: x_out = x_mid + W2 gelu_tanh(W0 ln2(x_mid) + b0) + b2
-            launch_colsum<TA>(h, dxb, C, tokens, C, GA(h, lp.m2b), st);
-            wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), C, GA(h, lp.m2w), tokens, C, C, st);
+            wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), C, GA(h, lp.m2w), tokens, C, C, st, GA(h, lp.m2b));
             gemm_dx<TA>(h, dxb, C, lp.m2wT, g1, C, tokens, C, C, st);
             launch_act_bwd<TA, ACT_GELU_TANH>(h, g1, TP<TA>(ot.hpre[li]), (long long)tokens * C, st);
-            launch_colsum<TA>(h, g1, C, tokens, C, GA(h, lp.m0b), st);
-            wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st);
+            wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
             gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
             launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st);
             // attention half: x_mid = x_in + Wo att(ln1(x_in)) + bo
-            launch_colsum<TA>(h, dxb, C, tokens, C, GA(h, lp.outb), st);
-            wgrad<TA>(h, dxb, C, TP<TA>(ot.att[li]), C, GA(h, lp.outw), tokens, C, C, st);
+            wgrad<TA>(h, dxb, C, TP<TA>(ot.att[li]), C, GA(h, lp.outw), tokens, C, C, st, GA(h, lp.outb));
             gemm_dx<TA>(h, dxb, C, lp.outwT, g2, C, tokens, C, C, st);
             launch_attention_bwd<TA>(h, TP<TA>(ot.qkv[li]), g2, gq, B, lp.axis, st);
-            launch_colsum<TA>(h, gq, 3 * C, tokens, 3 * C, GA(h, lp.inb), st);
-            wgrad<TA>(h, gq, 3 * C, TP<TA>(ot.ln1[li]), C, GA(h, lp.inw), tokens, 3 * C, C, st);
+            wgrad<TA>(h, gq, 3 * C, TP<TA>(ot.ln1[li]), C, GA(h, lp.inw), tokens, 3 * C, C, st, GA(h, lp.inb));
             gemm_dx<TA>(h, gq, 3 * C, lp.inwT, g2, C, tokens, C, 3 * C, st);
             launch_ln_bwd<TA>(h, g2, x_in, lp.ln1w, dxs, dxb_out, GA(h, lp.ln1w), GA(h, lp.ln1b), tokens, st);
         }
@@ -1167,26 +1165,21 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     const int K3 = g.k2 * g.k2 * C2, K2 = g.k1 * g.k1 * C1;
     const int M2 = tokens * g.R2;
     const long long rows_in = (long long)tokens * g.R1;
-    launch_colsum<TA>(h, g2, C, tokens, C, GA(h, h->enc_b[2]), st);
-    wgrad<TA>(h, g2, C, TP<TA>(tp.a2act), K3, GA(h, h->enc_w[2]), tokens, C, K3, st);
+    wgrad<TA>(h, g2, C, TP<TA>(tp.a2act), K3, GA(h, h->enc_w[2]), tokens, C, K3, st, GA(h, h->enc_b[2]));
     gemm_dx<TA>(h, g2, C, h->enc_wT[2], gq, K3, tokens, K3, C, st);
     launch_act_bwd<TA, ACT_GELU_ERF>(h, gq, TP<TA>(tp.a2pre), (long long)M2 * C2, st);
-    launch_colsum<TA>(h, gq, C2, M2, C2, GA(h, h->enc_b[1]), st);
-    wgrad<TA>(h, gq, C2, TP<TA>(tp.a1act), K2, GA(h, h->enc_w[1]), M2, C2, K2, st);
+    wgrad<TA>(h, gq, C2, TP<TA>(tp.a1act), K2, GA(h, h->enc_w[1]), M2, C2, K2, st, GA(h, h->enc_b[1]));
     TA* ga1 = TP<TA>(h->ga1);
     gemm_dx<TA>(h, gq, C2, h->enc_wT[1], ga1, K2, M2, K2, C2, st);
     launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), rows_in * C1, st);
-    launch_colsum<TA>(h, ga1, C1, rows_in, C1, GA(h, h->enc_b[0]), st);
+    (void)input;      // the patches were kept by the forward (tape im2col)
     TA* cols = TP<TA>(h->cols);
-    conv1_im2col_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(input, g, cols, rows_in);
-    CK(cudaGetLastError());
-    h->launches++;
-    wgrad_pad<TA>(h, ga1, C1, C1, cols, kHeadPad, kHeadPad, GA(h, h->enc_w[0]), NO, NO, rows_in, st);
+    wgrad_pad<TA>(h, ga1, C1, C1, TP<TA>(tp.cols), kHeadPad, kHeadPad, GA(h, h->enc_w[0]), NO, NO, rows_in, st, GA(h, h->enc_b[0]));
     if (grad_input) {
         // dpatch[rows, 64 (K1 padded)] = da1[rows, C1] * W1[C1][K1]  (thin GEMM), then scatter-add into the pixels
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
         gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], cols, kHeadPad, (int)rows_in, kHeadPad, C1, st);
-        conv1_col2im_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(cols, g, grad_input, rows_in);
+        conv1_col2im_kernel<TA><<<blocks_for(rows_in * (kHeadPad / 4), 256), 256, 0, st>>>(cols, g, grad_input, rows_in);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1217,8 +1210,6 @@ void set_smem_attrs() {
     HEADATTR(float, 1); HEADATTR(float, 2); HEADATTR(float, 3); HEADATTR(float, 4);
     HEADATTR(__nv_bfloat16, 1); HEADATTR(__nv_bfloat16, 2); HEADATTR(__nv_bfloat16, 3); HEADATTR(__nv_bfloat16, 4);
 #undef HEADATTR
-    CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(propagator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
 #define ATTBATTR(TA, HDv) CK(cudaFuncSetAttribute(attention_bwd_kernel<TA, HDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024))
     ATTBATTR(float, 16); ATTBATTR(float, 32); ATTBATTR(float, 64);
@@ -1640,7 +1631,7 @@ int tante_backward(tante_handle_t h, int32_t slot, const float* input, const flo
     });
 }
 
-int tante_test_wgrad(int32_t use_tc, const void* A, const void* Bm, float* C, int64_t M, int32_t N, int32_t K,
+int tante_test_wgrad(int32_t use_tc, const void* A, const void* Bm, float* C, float* bias, int64_t M, int32_t N, int32_t K,
                      int32_t iters, void* stream) {
     return guarded([&] {
         REQUIRE(A && Bm && C, "null argument");
@@ -1654,7 +1645,7 @@ int tante_test_wgrad(int32_t use_tc, const void* A, const void* Bm, float* C, in
                 const int Kb = (K + 63) / 64 * 64;
                 REQUIRE(wgrad_tc_supported(M, N, Kb, K, N, Kb, K), "shape not covered by the tcgen05 wgrad kernel");
                 CK(launch_wgrad_tc(reinterpret_cast<const __nv_bfloat16*>(A), N, reinterpret_cast<const __nv_bfloat16*>(Bm), Kb,
-                                   C, K, M, N, Kb, K, sms, st));
+                                   C, K, M, N, Kb, K, sms, st, bias));
             } else if (use_tc == 2) {
                 CK((launch_wgrad_simt<__nv_bfloat16, __nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(A), N,
                                                                     reinterpret_cast<const __nv_bfloat16*>(Bm), K, C, K, M, N,

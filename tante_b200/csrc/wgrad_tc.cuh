@@ -27,6 +27,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
     return umma_idesc_bf16(M, N) | (1u << 15) | (1u << 16);     // a_major = b_major = MN
 }
+// 1-D bulk copy global -> shared (async proxy), completion on an mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
@@ -37,16 +43,23 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 template <int BN>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, int m_tiles, int tiles_per_split, int nstage) {
+                const __grid_constant__ CUtensorMap tmC, int m_tiles, int tiles_per_split, int nstage,
+                float* __restrict__ bias_grad, int n_total, const __nv_bfloat16* __restrict__ ones_g) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int kStage = (2 + BN / 64) * kWgBox;
-    uint8_t* sStage = smem;                                           // [nstage][A: 2 boxes][B: BN/64 boxes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nstage * kStage);
+    uint8_t* sStage = smem + kWgBox;                                  // [nstage][A: 2 boxes][B: BN/64 boxes]
+    // bias gradient db[n] = sum_m dY[m][n] rides along as one extra N = 64 MMA per k-step against a tile of ones
+    // (accumulated in TMEM columns [BN, BN+64)): no separate column-sum pass over dY
+    uint8_t* sOnes = smem;                                            // 64 rows x 128 B of bf16 1.0
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + (size_t)nstage * kStage);
+    constexpr int kTmemCols = BN >= 256 ? 512 : (BN >= 128 ? 256 : 128);
+    const bool do_bias = bias_grad != nullptr && blockIdx.y == 0;
     uint64_t* full = bars;
     uint64_t* empty = bars + 8;
     uint64_t* tmem_full = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* ones_full = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int n0 = blockIdx.x * 128, k0 = blockIdx.y * BN;
@@ -60,10 +73,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         ptx::prefetch_tmap(&tmC);
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(tmem_full, 1);
+        ptx::mbar_init(ones_full, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -74,6 +88,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (ntile > 0) {
         if (warp == 0) {
             if (lane == 0) {
+                if (do_bias) {
+                    // the tile of ones arrives like every other operand: through the async proxy (a bulk copy from a
+                    // small global buffer), so the tensor core sees it without any generic->async proxy hand-over
+                    ptx::mbar_arrive_expect_tx(ones_full, kWgBox);
+                    ptx::bulk_load_1d(sOnes, ones_g, kWgBox, ones_full);
+                }
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int t = t_begin; t < t_end; ++t) {
@@ -91,8 +111,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         } else if (warp == 1) {
             constexpr uint32_t idesc = ptx::umma_idesc_bf16_mn(128, BN);
+            constexpr uint32_t idesc_b = ptx::umma_idesc_bf16_mn(128, 64);     // one full 64-column SW128 atom (N < 64 is not a valid MN-major SW128 tile)
+            const uint32_t sones = ptx::smem_u32(sOnes);
             int stage = 0;
             uint32_t phase = 0;
+            if (do_bias) ptx::mbar_wait(ones_full, 0);
             for (int t = 0; t < ntile; ++t) {
                 ptx::mbar_wait(&full[stage], phase);
                 ptx::tc_fence_after();
@@ -104,6 +127,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint64_t da = ptx::umma_desc_mn_sw128(sa + k * 2048, kWgBox, 1024);
                         const uint64_t db = ptx::umma_desc_mn_sw128(sb + k * 2048, kWgBox, 1024);
                         ptx::umma_bf16(tmem_base, da, db, idesc, (t | k) != 0);
+                        if (do_bias) {
+                            // the descriptor is rebuilt per MMA from an opaque register copy: a loop-invariant 64-bit
+                            // descriptor hoisted out of the elected-lane block gets a predicated R2UR from ptxas 12.9 that
+                            // is skipped at run time (stale uniform registers -> the MMA reads a garbage address)
+                            uint32_t so;
+                            asm volatile("mov.u32 %0, %1;" : "=r"(so) : "r"(sones));
+                            ptx::umma_bf16(tmem_base + (uint32_t)BN, da, ptx::umma_desc_mn_sw128(so, kWgBox, 1024), idesc_b, (t | k) != 0);
+                        }
                     }
                     ptx::umma_commit(&empty[stage]);
                     if (t == ntile - 1) ptx::umma_commit(tmem_full);
@@ -137,12 +168,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     ptx::bulk_commit();
                 }
             }
+            if (do_bias) {
+                uint32_t r0[32];
+                ptx::tmem_ld_32x32(tm + (uint32_t)BN, r0);
+                ptx::tc_wait_ld();
+                const int n = n0 + q * 32 + lane;
+                if (n < n_total) atomicAdd(bias_grad + n, __uint_as_float(r0[0]));
+            }
             if (lane == 0) ptx::bulk_wait_all<0>();
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 static cudaError_t wg_set_attrs() {
@@ -156,6 +194,23 @@ static cudaError_t wg_set_attrs() {
     return cudaSuccess;
 }
 
+// 8 KB of bf16 1.0 per device (the B operand of the fused bias-gradient MMA)
+static const __nv_bfloat16* wg_ones(cudaError_t* err) {
+    static void* ptr[64] = {nullptr};
+    int dev = 0;
+    if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return nullptr;
+    if (dev < 0 || dev >= 64) { *err = cudaErrorInvalidDevice; return nullptr; }
+    if (!ptr[dev]) {
+        uint16_t host[kWgBox / 2];
+        for (int i = 0; i < kWgBox / 2; ++i) host[i] = 0x3F80;
+        void* p = nullptr;
+        if ((*err = cudaMalloc(&p, kWgBox)) != cudaSuccess) return nullptr;
+        if ((*err = cudaMemcpy(p, host, kWgBox, cudaMemcpyHostToDevice)) != cudaSuccess) return nullptr;
+        ptr[dev] = p;
+    }
+    return reinterpret_cast<const __nv_bfloat16*>(ptr[dev]);
+}
+
 // true when the shape is covered by the tensor-core kernel (otherwise the caller uses wgrad_simt).
 // N (columns of A = rows of dW) must be a multiple of 64: an odd 64-column half-tile is zero-filled by TMA on load
 // and clipped on the reduce-store.  Kb = columns of B as stored (multiple of 64, zero-padded by the producer),
@@ -166,13 +221,14 @@ static bool wgrad_tc_supported(long long M, int N, int Kb, int Kc, int lda, int 
 }
 
 static cudaError_t launch_wgrad_tc(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Bm, int ldb, float* Cout,
-                                   int ldc, long long M, int N, int Kb, int Kc, int num_sms, cudaStream_t st) {
+                                   int ldc, long long M, int N, int Kb, int Kc, int num_sms, cudaStream_t st,
+                                   float* bias_grad = nullptr) {
     if (!wgrad_tc_supported(M, N, Kb, Kc, lda, ldb, ldc)) return cudaErrorInvalidValue;
     const int BN = (Kb % 256 == 0) ? 256 : (Kb % 128 == 0 ? 128 : 64);
     const int stage_bytes = (2 + BN / 64) * kWgBox;
-    int nstage = (int)((227 * 1024 - 2048) / stage_bytes);
+    int nstage = (int)((227 * 1024 - 2048 - kWgBox) / stage_bytes);
     nstage = nstage > 6 ? 6 : nstage;
-    const size_t smem = (size_t)nstage * stage_bytes + 256 + 1024;
+    const size_t smem = (size_t)nstage * stage_bytes + kWgBox + 256 + 1024;
     const int m_tiles = (int)((M + kWgRows - 1) / kWgRows);
     const int n_tiles = (N + 127) / 128;
     const int tiles_xy = n_tiles * (Kb / BN);
@@ -185,11 +241,13 @@ static cudaError_t launch_wgrad_tc(const __nv_bfloat16* A, int lda, const __nv_b
     if (!make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Bm, (int)M, Kb, ldb, 64, kWgRows)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, Kc, ldc, 32, 32)) return cudaErrorInvalidValue;
     { cudaError_t e = wg_set_attrs(); if (e != cudaSuccess) return e; }
+    const __nv_bfloat16* ones = nullptr;
+    if (bias_grad) { cudaError_t e = cudaSuccess; ones = wg_ones(&e); if (e != cudaSuccess) return e; }
     dim3 grid(n_tiles, Kb / BN, splits);
     switch (BN) {
-        case 256: wgrad_tc_kernel<256><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage); break;
-        case 128: wgrad_tc_kernel<128><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage); break;
-        default: wgrad_tc_kernel<64><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage); break;
+        case 256: wgrad_tc_kernel<256><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones); break;
+        case 128: wgrad_tc_kernel<128><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones); break;
+        default: wgrad_tc_kernel<64><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones); break;
     }
     return cudaGetLastError();
 }

@@ -215,11 +215,16 @@ def test_wgrad_tcgen05_matches_torch(shape):
     if K % 64:      # the producer zero-pads B to a multiple of 64 columns; only the first K columns of dW are kept
         Bp = torch.zeros(M, (K + 63) // 64 * 64, device="cuda", dtype=torch.bfloat16)
         Bp[:, :K] = Bm
-    _abi.check(lib.tante_test_wgrad(1, A.data_ptr(), Bp.data_ptr(), C.data_ptr(), M, N, K, 1,
+    bias0 = torch.randn(N, device="cuda", generator=g)
+    bias = bias0.clone()
+    _abi.check(lib.tante_test_wgrad(1, A.data_ptr(), Bp.data_ptr(), C.data_ptr(), bias.data_ptr(), M, N, K, 1,
                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = C0.double() + A.double().t() @ Bm.double()
     assert rel_l2(C.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    # fused bias gradient: column sums of A ride along as an N = 16 MMA against a tile of ones
+    bref = bias0.double() + A.double().sum(0)
+    assert rel_l2(bias.cpu().numpy(), bref.cpu().numpy()) < 2e-5
 
 
 @pytest.mark.parametrize("mode", [0, 2])
@@ -232,7 +237,7 @@ def test_wgrad_simt_matches_torch(mode):
     A = torch.randn(M, N, device="cuda", generator=g).to(dt)
     Bm = torch.randn(M, K, device="cuda", generator=g).to(dt)
     C = torch.zeros(N, K, device="cuda")
-    _abi.check(lib.tante_test_wgrad(mode, A.data_ptr(), Bm.data_ptr(), C.data_ptr(), M, N, K, 1,
+    _abi.check(lib.tante_test_wgrad(mode, A.data_ptr(), Bm.data_ptr(), C.data_ptr(), None, M, N, K, 1,
                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = A.double().t() @ Bm.double()

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TA* __restrict__ dy, 
     }
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const long long nwarps = (long long)gridDim.x * blockDim.x / kWarp;
-    constexpr int RPI = 2;       // rows in flight per warp iteration (memory-level parallelism: the kernel is HBM-bound)
+    constexpr int RPI = 1;       // rows in flight per warp iteration (2 measured slower on B200: register pressure)
     for (long long rb = warp0; rb < rows; rb += nwarps * RPI) {
         float xv[RPI][MAXV][4], dv[RPI][MAXV][4], ov[RPI][MAXV][4];
         long long rr[RPI];
@@ -679,11 +679,10 @@ __device__ __forceinline__ void row_coords(const PatchGeom& g, long long row, lo
     stage1_row_to_hw(g, hpp, wp, r, h1, w1);
 }
 
+// One thread per stage-1 row (adjacent threads = adjacent pixels, so the per-(c, c', d) reads coalesce).
 template <typename TA>
-__global__ void __launch_bounds__(256) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long row = gid / (kHeadPad / 4);
-    const int o4 = (int)(gid % (kHeadPad / 4)) * 4;
+__global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_total) return;
     const int NO = g.k0 * g.k0 * g.D;
     long long b;
@@ -691,43 +690,44 @@ __global__ void __launch_bounds__(256) head_gather_kernel(HeadBwdParams hp, Patc
     row_coords(g, row, b, h1, w1);          // here rows are (b, hp, wp, r): "bt" is the sample index
     const int n = min(hp.n_arr[b], hp.n_cap);
     const size_t HW = (size_t)g.H * g.W;
-    float Gk[4][4];                 // [order][4 consecutive outputs]
+    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
+        float Gk[4][4];                 // [order][4 consecutive outputs]
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) Gk[k][e] = 0.f;
+            for (int e = 0; e < 4; ++e) Gk[k][e] = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int oo = o4 + e;
-        if (oo >= NO) continue;
-        int d; size_t pix;
-        patch_pixel(g, h1, w1, oo, d, pix);
-        float du = 0.f;
-        for (int i = 1; i <= n; ++i) {
-            const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
-            du += gv;
-            const float dt = (float)i * hp.fi;
-            float coef = 1.f;
+        for (int e = 0; e < 4; ++e) {
+            const int oo = o4 + e;
+            if (oo >= NO) continue;
+            int d; size_t pix;
+            patch_pixel(g, h1, w1, oo, d, pix);
+            float du = 0.f;
+            for (int i = 1; i <= n; ++i) {
+                const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
+                du += gv;
+                const float dt = (float)i * hp.fi;
+                float coef = 1.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                coef *= dt / (float)(k + 1);
-                Gk[k][e] = fmaf(gv, coef, Gk[k][e]);
+                for (int k = 0; k < 4; ++k) {
+                    coef *= dt / (float)(k + 1);
+                    Gk[k][e] = fmaf(gv, coef, Gk[k][e]);
+                }
             }
+            if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
         }
-        if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
+        for (int k = 0; k < hp.K; ++k) Vec4<TA>::store(reinterpret_cast<TA*>(hp.G[k]) + (size_t)row * kHeadPad + o4, Gk[k]);
     }
-    for (int k = 0; k < hp.K; ++k) Vec4<TA>::store(reinterpret_cast<TA*>(hp.G[k]) + (size_t)row * kHeadPad + o4, Gk[k]);
 }
 
 // ---- first patch conv (enc_conv_1, enc_dec_cnn.py:220-221) as im2col + GEMM in training ----------------------
 // im2col of the input patches, TA [rows][kHeadPad] zero-padded (K1 = k0*k0*D columns in the packed conv-weight
 // order (c, c', d)): the A operand of the forward conv GEMM and the B operand of its weight-gradient GEMM.
+// One thread per stage-1 row (adjacent threads = adjacent pixels, so the per-(c, c', d) reads coalesce).
 template <typename TA>
-__global__ void __launch_bounds__(256) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
+__global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
                                                            TA* __restrict__ cols, long long rows_total) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long row = gid / (kHeadPad / 4);
-    const int o4 = (int)(gid % (kHeadPad / 4)) * 4;
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_total) return;
     long long bt;
     int h1, w1;
@@ -735,42 +735,43 @@ __global__ void __launch_bounds__(256) conv1_im2col_kernel(const float* __restri
     const size_t HW = (size_t)g.H * g.W;
     const float* xin = x + (size_t)bt * g.D * HW;
     const int K1 = g.k0 * g.k0 * g.D;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int kk = o4 + e;
-        if (kk >= K1) continue;
-        int d; size_t pix;
-        patch_pixel(g, h1, w1, kk, d, pix);
-        v[e] = xin[(size_t)d * HW + pix];
+        for (int e = 0; e < 4; ++e) {
+            const int kk = o4 + e;
+            if (kk >= K1) continue;
+            int d; size_t pix;
+            patch_pixel(g, h1, w1, kk, d, pix);
+            v[e] = xin[(size_t)d * HW + pix];
+        }
+        Vec4<TA>::store(cols + (size_t)row * kHeadPad + o4, v);
     }
-    Vec4<TA>::store(cols + (size_t)row * kHeadPad + o4, v);
 }
 
 // grad_input[patch] += dpatch[row][kk]   (dpatch = da1 * W1, a thin GEMM; patches do not overlap)
 template <typename TA>
-__global__ void __launch_bounds__(256) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
+__global__ void __launch_bounds__(128) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
                                                            float* __restrict__ grad_input, long long rows_total) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long row = gid / (kHeadPad / 4);
-    const int o4 = (int)(gid % (kHeadPad / 4)) * 4;
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_total) return;
     const int K1 = g.k0 * g.k0 * g.D;
-    if (o4 >= K1) return;
     long long bt;
     int h1, w1;
     row_coords(g, row, bt, h1, w1);
     const size_t HW = (size_t)g.H * g.W;
     float* gin = grad_input + (size_t)bt * g.D * HW;
-    float v[4];
-    Vec4<TA>::load(dpatch + (size_t)row * kHeadPad + o4, v);
+    for (int o4 = 0; o4 < K1; o4 += 4) {
+        float v[4];
+        Vec4<TA>::load(dpatch + (size_t)row * kHeadPad + o4, v);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int kk = o4 + e;
-        if (kk >= K1) continue;
-        int d; size_t pix;
-        patch_pixel(g, h1, w1, kk, d, pix);
-        gin[(size_t)d * HW + pix] += v[e];
+        for (int e = 0; e < 4; ++e) {
+            const int kk = o4 + e;
+            if (kk >= K1) continue;
+            int d; size_t pix;
+            patch_pixel(g, h1, w1, kk, d, pix);
+            gin[(size_t)d * HW + pix] += v[e];
+        }
     }
 }
 

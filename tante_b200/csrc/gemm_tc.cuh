@@ -115,11 +115,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = rank; mt < m_tiles; mt += per_slice) {
-                if (has_res) {
-                    // warm L2 with this tile's residual rows: the epilogue reads them a few microseconds later
-                    for (int rr = 0; rr < kTcBlockM; rr += 32)
-                        for (int cc = 0; cc < BN; cc += 32) ptx::tma_prefetch_l2_2d(&tmR, n0 + cc, mt * kTcBlockM + rr);
-                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
@@ -163,6 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int half = ew >> 2;
         uint8_t* ebuf = sEpi + (size_t)ew * nebuf * kTcEpiBuf;
+        uint64_t* rb = rbar + ew * 2;
+        uint32_t rphase0 = 0;
         int nbuf = 0;        // staging buffer the next chunk uses (bf16 path with nebuf == 2 only)
         int t = 0;
         for (int mt = rank; mt < m_tiles; mt += per_slice, ++t) {
@@ -204,18 +201,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (nebuf > 1) nbuf ^= 1;
                 }
             } else {
-                // fp32 output in 32-column chunks, one staging buffer per warp.  The residual variants read the
-                // residual chunk (this thread's row: one full 128-byte line) straight into registers, ONE CHUNK AHEAD
-                // (the first one before the accumulator is even ready), so the HBM/L2 latency overlaps the previous
-                // chunk's math and store; the producer warp L2-prefetches the tile's residual rows with the A tile.
+                // fp32 output in 32-column chunks, one staging buffer per warp.  The residual variants TMA-load the
+                // residual chunk into the buffer (8 warps x 4 KB of loads in flight per SM), add in place and TMA-store it back.  The
+                // first chunk's load is issued before the accumulator is ready, so it overlaps the MMAs.
                 const int m = row0 + lane;
-                float4 xn[8];
-                auto load_res = [&](int chn) {
-                    const float4* p = reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldr + n0 + chn * 32);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) xn[c] = m < M ? p[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-                };
-                if (has_res) load_res(half);
+                if (has_res && lane == 0) {
+                    ptx::bulk_wait_read<0>();
+                    ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                    ptx::tma_load_2d(ebuf, &tmR, &rb[0], n0 + half * 32, row0);
+                }
                 ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
                 ptx::tc_fence_after();
                 float rsum = 0.f, rsq = 0.f;
@@ -223,15 +217,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int ch = half; ch < BN / 32; ch += 2) {
                     uint32_t r0[32];
                     uint8_t* buf = ebuf;
-                    float4 xc[8];
-                    if (has_res) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) xc[c] = xn[c];
-                        if (ch + 2 < BN / 32) load_res(ch + 2);
+                    if (lane == 0 && (ch != half || !has_res)) {
+                        ptx::bulk_wait_read<0>();       // the previous store has finished reading the buffer
+                        if (has_res) {
+                            ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                            ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 32, row0);
+                        }
                     }
-                    if (lane == 0) ptx::bulk_wait_read<0>();       // the previous store has finished reading the buffer
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 32), r0);
                     __syncwarp();
+                    if (has_res) { ptx::mbar_wait(&rb[0], rphase0); rphase0 ^= 1; }
                     ptx::tc_wait_ld();
                     const float* bsm = sBias + ch * 32;
                     const int ncol = n0 + ch * 32;
@@ -244,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         o.z = __uint_as_float(r0[c * 4 + 2]) + bsm[c * 4 + 2];
                         o.w = __uint_as_float(r0[c * 4 + 3]) + bsm[c * 4 + 3];
                         if (has_res) {
-                            const float4 x = xc[c];
+                            const float4 x = *p;
                             o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
                             if (has_ln) {       // keep the updated row in TMEM (over the accumulator) for the LN pass
                                 r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);

@@ -899,7 +899,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         // enc_conv_1 as im2col (kept for the weight gradient) + GEMM over the zero-padded patch matrix
         const long long rows_in = (long long)tokens * g.R1;
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv GEMM");
-        conv1_im2col_kernel<TA><<<blocks_for(rows_in * (kHeadPad / 4), 256), 256, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
+        conv1_im2col_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
@@ -1061,7 +1061,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         for (int k = 0; k < K; ++k) hp.G[k] = TP<TA>(h->hG) + (size_t)k * rows1 * kHeadPad;
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
         hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); hp.grad_input = grad_input;
-        head_gather_kernel<TA><<<blocks_for(rows1 * (kHeadPad / 4), 256), 256, 0, st>>>(hp, g, rows1);
+        head_gather_kernel<TA><<<blocks_for(rows1, 128), 128, 0, st>>>(hp, g, rows1);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1179,7 +1179,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         // dpatch[rows, 64 (K1 padded)] = da1[rows, C1] * W1[C1][K1]  (thin GEMM), then scatter-add into the pixels
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
         gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], cols, kHeadPad, (int)rows_in, kHeadPad, C1, st);
-        conv1_col2im_kernel<TA><<<blocks_for(rows_in * (kHeadPad / 4), 256), 256, 0, st>>>(cols, g, grad_input, rows_in);
+        conv1_col2im_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(cols, g, grad_input, rows_in);
         CK(cudaGetLastError());
         h->launches++;
     }

@@ -679,99 +679,215 @@ __device__ __forceinline__ void row_coords(const PatchGeom& g, long long row, lo
     stage1_row_to_hw(g, hpp, wp, r, h1, w1);
 }
 
-// One thread per stage-1 row (adjacent threads = adjacent pixels, so the per-(c, c', d) reads coalesce).
-template <typename TA>
-__global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows_total) return;
-    const int NO = g.k0 * g.k0 * g.D;
-    long long b;
-    int h1, w1;
-    row_coords(g, row, b, h1, w1);          // here rows are (b, hp, wp, r): "bt" is the sample index
-    const int n = min(hp.n_arr[b], hp.n_cap);
-    const size_t HW = (size_t)g.H * g.W;
-    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
-        float Gk[4][4];                 // [order][4 consecutive outputs]
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) Gk[k][e] = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int oo = o4 + e;
-            if (oo >= NO) continue;
-            int d; size_t pix;
-            patch_pixel(g, h1, w1, oo, d, pix);
-            float du = 0.f;
-            for (int i = 1; i <= n; ++i) {
-                const float gv = hp.gframes[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix];
-                du += gv;
-                const float dt = (float)i * hp.fi;
-                float coef = 1.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    coef *= dt / (float)(k + 1);
-                    Gk[k][e] = fmaf(gv, coef, Gk[k][e]);
-                }
-            }
-            if (hp.grad_input) hp.grad_input[((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix] += du;
-        }
-        for (int k = 0; k < hp.K; ++k) Vec4<TA>::store(reinterpret_cast<TA*>(hp.G[k]) + (size_t)row * kHeadPad + o4, Gk[k]);
+// ---- pixel planes <-> padded stage-1 row matrices, one 64-row tile per CTA -------------------------------------
+// The row matrices are [rows][kHeadPad] with rows in the nested (image, hp, wp, a, a', b, b') order and columns
+// (c, c', d); the pixel side is channels-first (image, d, H, W).  Both sides are touched with full-width accesses:
+// pixel side = thread per VEC-pixel run along W of one (token, field, pixel row), consecutive threads walk along W;
+// row side = thread per 16-byte chunk of a row.  A shared-memory tile S[row][kPatchPitch] sits in between.
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+constexpr int kPatchRows = 64;
+constexpr int kPatchPitch = kHeadPad + 4;     // floats; rows 16 B aligned, row stride = 4 banks
+struct PatchTile {
+    int P, NT, lP, lNT;
+    int stab[32];                             // RH[8], RW[8], OH[8], OW[8]   (see taylor_head_mma_kernel)
+    long long pix0[kPatchRows];               // per token: pixel offset of its top-left corner in a plane
+    long long img[kPatchRows];                // per token: image index (-1 = past the end)
+};
+__device__ __forceinline__ void patch_tile_init(PatchTile& pt, const PatchGeom& g, long long row0, long long rows_total) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        pt.P = g.k0 * g.k1 * g.k2;
+        pt.NT = kPatchRows / g.R1;
+        pt.lP = 31 - __clz(pt.P);
+        pt.lNT = 31 - __clz(pt.NT);
     }
+    const int P = g.k0 * g.k1 * g.k2;
+    if (tid < P) {
+        const int c = tid % g.k0, b = (tid / g.k0) % g.k1, a = tid / (g.k0 * g.k1);
+        pt.stab[tid] = a * g.k2 * g.k1 * g.k1 + b * g.k1;
+        pt.stab[8 + tid] = a * g.k1 * g.k1 + b;
+        pt.stab[16 + tid] = c * g.k0 * g.D;
+        pt.stab[24 + tid] = c * g.D;
+    }
+    if (tid < kPatchRows / g.R1) {
+        long long tkn = row0 / g.R1 + tid;
+        if (tkn < rows_total / g.R1) {
+            const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
+            const int hpp = (int)(tkn % g.Hp);
+            pt.img[tid] = tkn / g.Hp;
+            pt.pix0[tid] = (long long)hpp * P * g.W + (long long)wp * P;
+        } else {
+            pt.img[tid] = -1; pt.pix0[tid] = 0;
+        }
+    }
+}
+// pixel-side work item -> (token, field, pixel row, run) ; returns false past the end
+template <int VEC>
+__device__ __forceinline__ bool patch_item(const PatchTile& pt, const PatchGeom& g, int item, int& tok, int& d, size_t& pix,
+                                           int (&soff)[VEC]) {
+    const int lPQ = pt.lP - (VEC == 4 ? 2 : 1);
+    const int wq = item & ((1 << lPQ) - 1);
+    tok = (item >> lPQ) & (pt.NT - 1);
+    const int rest = item >> (lPQ + pt.lNT);
+    const int hr = rest & (pt.P - 1);
+    d = rest >> pt.lP;
+    if (pt.img[tok] < 0) return false;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const int wl = wq * VEC + e;
+        soff[e] = (tok * g.R1 + pt.stab[hr] + pt.stab[8 + wl]) * kPatchPitch + pt.stab[16 + hr] + pt.stab[24 + wl] + d;
+    }
+    pix = (size_t)pt.pix0[tok] + (size_t)hr * g.W + wq * VEC;
+    return true;
+}
+// row side: S tile -> [rows][kHeadPad] TA (columns >= ncols_valid come out as the zeros the tile was cleared to)
+template <typename TA>
+__device__ __forceinline__ void patch_rows_store(const float* S, TA* __restrict__ dst, long long row0, long long rows_total) {
+    constexpr int CH = (int)(16 / sizeof(TA));       // elements per 16-byte chunk
+    constexpr int NCH = kHeadPad / CH;
+    for (int i = threadIdx.x; i < kPatchRows * NCH; i += blockDim.x) {
+        const int r = i / NCH, ch = i % NCH;
+        if (row0 + r >= rows_total) continue;
+        const float* sp = S + r * kPatchPitch + ch * CH;
+        TA* dp = dst + (size_t)(row0 + r) * kHeadPad + ch * CH;
+        const float4 lo = *reinterpret_cast<const float4*>(sp);
+        if constexpr (CH == 4) {
+            *reinterpret_cast<float4*>(dp) = lo;
+        } else {
+            const float4 hi = *reinterpret_cast<const float4*>(sp + 4);
+            uint4 u;
+            u.x = bf16x2_bits(lo.x, lo.y); u.y = bf16x2_bits(lo.z, lo.w);
+            u.z = bf16x2_bits(hi.x, hi.y); u.w = bf16x2_bits(hi.z, hi.w);
+            *reinterpret_cast<uint4*>(dp) = u;
+        }
+    }
+}
+template <typename TA>
+__device__ __forceinline__ void patch_rows_load(float* S, const TA* __restrict__ src, long long row0, long long rows_total) {
+    constexpr int CH = (int)(16 / sizeof(TA));
+    constexpr int NCH = kHeadPad / CH;
+    for (int i = threadIdx.x; i < kPatchRows * NCH; i += blockDim.x) {
+        const int r = i / NCH, ch = i % NCH;
+        if (row0 + r >= rows_total) continue;
+        const TA* gp = src + (size_t)(row0 + r) * kHeadPad + ch * CH;
+        float* sp = S + r * kPatchPitch + ch * CH;
+        float v[4];
+        Vec4<TA>::load(gp, v);
+        sp[0] = v[0]; sp[1] = v[1]; sp[2] = v[2]; sp[3] = v[3];
+        if (CH == 8) {
+            Vec4<TA>::load(gp + 4, v);
+            sp[4] = v[0]; sp[5] = v[1]; sp[6] = v[2]; sp[7] = v[3];
+        }
+    }
+}
+
+template <typename TA, int VEC>
+__global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, PatchGeom g, long long rows_total) {
+    extern __shared__ __align__(16) float hg_smem[];          // [K][64][kPatchPitch]
+    __shared__ PatchTile pt;
+    const long long row0 = (long long)blockIdx.x * kPatchRows;
+    patch_tile_init(pt, g, row0, rows_total);                 // rows are (b, hp, wp, r): the "image" is the sample
+    for (int i = threadIdx.x; i < hp.K * kPatchRows * kPatchPitch; i += blockDim.x) hg_smem[i] = 0.f;
+    __syncthreads();
+    const size_t HW = (size_t)g.H * g.W;
+    const int nitems = (g.D * pt.P * pt.NT) << (pt.lP - (VEC == 4 ? 2 : 1));
+    for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+        int tok, d, soff[VEC];
+        size_t pix;
+        if (!patch_item<VEC>(pt, g, item, tok, d, pix, soff)) continue;
+        const long long b = pt.img[tok];
+        const int n = min(hp.n_arr[b], hp.n_cap);
+        float Gk[4][VEC], du[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { du[e] = 0.f; Gk[0][e] = Gk[1][e] = Gk[2][e] = Gk[3][e] = 0.f; }
+        for (int i = 1; i <= n; ++i) {
+            float gv[VEC];
+            VecN<VEC>::load(hp.gframes + (((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix, gv);
+            const float dt = (float)i * hp.fi;
+            float coef = 1.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                coef *= dt / (float)(k + 1);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) Gk[k][e] = fmaf(gv[e], coef, Gk[k][e]);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) du[e] += gv[e];
+        }
+        if (hp.grad_input && n > 0) {
+            float* gp = hp.grad_input + ((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix;
+            float cur[VEC];
+            VecN<VEC>::load(gp, cur);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) cur[e] += du[e];
+            VecN<VEC>::store(gp, cur);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < hp.K) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) hg_smem[k * kPatchRows * kPatchPitch + soff[e]] = Gk[k][e];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < hp.K) patch_rows_store<TA>(hg_smem + k * kPatchRows * kPatchPitch, reinterpret_cast<TA*>(hp.G[k]), row0, rows_total);
 }
 
 // ---- first patch conv (enc_conv_1, enc_dec_cnn.py:220-221) as im2col + GEMM in training ----------------------
 // im2col of the input patches, TA [rows][kHeadPad] zero-padded (K1 = k0*k0*D columns in the packed conv-weight
 // order (c, c', d)): the A operand of the forward conv GEMM and the B operand of its weight-gradient GEMM.
-// One thread per stage-1 row (adjacent threads = adjacent pixels, so the per-(c, c', d) reads coalesce).
-template <typename TA>
+template <typename TA, int VEC>
 __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
                                                            TA* __restrict__ cols, long long rows_total) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows_total) return;
-    long long bt;
-    int h1, w1;
-    row_coords(g, row, bt, h1, w1);
+    __shared__ __align__(16) float S[kPatchRows * kPatchPitch];
+    __shared__ PatchTile pt;
+    const long long row0 = (long long)blockIdx.x * kPatchRows;
+    patch_tile_init(pt, g, row0, rows_total);
+    for (int i = threadIdx.x; i < kPatchRows * kPatchPitch; i += blockDim.x) S[i] = 0.f;
+    __syncthreads();
     const size_t HW = (size_t)g.H * g.W;
-    const float* xin = x + (size_t)bt * g.D * HW;
-    const int K1 = g.k0 * g.k0 * g.D;
-    for (int o4 = 0; o4 < kHeadPad; o4 += 4) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nitems = (g.D * pt.P * pt.NT) << (pt.lP - (VEC == 4 ? 2 : 1));
+    for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+        int tok, d, soff[VEC];
+        size_t pix;
+        if (!patch_item<VEC>(pt, g, item, tok, d, pix, soff)) continue;
+        float v[VEC];
+        VecN<VEC>::load(x + ((size_t)pt.img[tok] * g.D + d) * HW + pix, v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int kk = o4 + e;
-            if (kk >= K1) continue;
-            int d; size_t pix;
-            patch_pixel(g, h1, w1, kk, d, pix);
-            v[e] = xin[(size_t)d * HW + pix];
-        }
-        Vec4<TA>::store(cols + (size_t)row * kHeadPad + o4, v);
+        for (int e = 0; e < VEC; ++e) S[soff[e]] = v[e];
     }
+    __syncthreads();
+    patch_rows_store<TA>(S, cols, row0, rows_total);
 }
 
 // grad_input[patch] += dpatch[row][kk]   (dpatch = da1 * W1, a thin GEMM; patches do not overlap)
-template <typename TA>
+template <typename TA, int VEC>
 __global__ void __launch_bounds__(128) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
                                                            float* __restrict__ grad_input, long long rows_total) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows_total) return;
-    const int K1 = g.k0 * g.k0 * g.D;
-    long long bt;
-    int h1, w1;
-    row_coords(g, row, bt, h1, w1);
+    __shared__ __align__(16) float S[kPatchRows * kPatchPitch];
+    __shared__ PatchTile pt;
+    const long long row0 = (long long)blockIdx.x * kPatchRows;
+    patch_tile_init(pt, g, row0, rows_total);
+    patch_rows_load<TA>(S, dpatch, row0, rows_total);
+    __syncthreads();
     const size_t HW = (size_t)g.H * g.W;
-    float* gin = grad_input + (size_t)bt * g.D * HW;
-    for (int o4 = 0; o4 < K1; o4 += 4) {
-        float v[4];
-        Vec4<TA>::load(dpatch + (size_t)row * kHeadPad + o4, v);
+    const int nitems = (g.D * pt.P * pt.NT) << (pt.lP - (VEC == 4 ? 2 : 1));
+    for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+        int tok, d, soff[VEC];
+        size_t pix;
+        if (!patch_item<VEC>(pt, g, item, tok, d, pix, soff)) continue;
+        float* gp = grad_input + ((size_t)pt.img[tok] * g.D + d) * HW + pix;
+        float cur[VEC];
+        VecN<VEC>::load(gp, cur);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int kk = o4 + e;
-            if (kk >= K1) continue;
-            int d; size_t pix;
-            patch_pixel(g, h1, w1, kk, d, pix);
-            gin[(size_t)d * HW + pix] += v[e];
-        }
+        for (int e = 0; e < VEC; ++e) cur[e] += S[soff[e]];
+        VecN<VEC>::store(gp, cur);
     }
 }
 

@@ -46,6 +46,22 @@ template <> struct Vec4<__nv_bfloat16> {
     }
 };
 
+// fp32 runs of 2 or 4 elements (64- / 128-bit accesses)
+template <int N> struct VecN;
+template <> struct VecN<4> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { Vec4<float>::load(p, v); }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { Vec4<float>::store(p, v); }
+};
+template <> struct VecN<2> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[2]) {
+        float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[2]) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
+
 // ---- activations (accurate versions: the fp32 parity mode is compiled without fast-math) --
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -106,6 +122,10 @@ enum Epilogue : int {
     EPI_BIAS_RESID = 4,  // C = resid + acc + bias   (fp32 residual stream, may alias C)
     EPI_EMBED = 5,       // encoder tail: v=acc+bias; v += v*scale[t]+shift[t]; v += s_emb[hw]; v += t_emb[t]
     EPI_BIAS_RESID_LN = 6,  // EPI_BIAS_RESID + LayerNorm of the updated row written to a second (bf16) output
+    // input-gradient GEMMs (tensor GEMM, bf16 output only): C = (acc + bias) * f'(pre[m][n]), pre = EpiParams::mul_pre
+    EPI_MULGRAD_RELU = 7,
+    EPI_MULGRAD_GELU_ERF = 8,
+    EPI_MULGRAD_GELU_TANH = 9,
 };
 
 struct EpiParams {
@@ -121,6 +141,9 @@ struct EpiParams {
     const float* ln_gamma = nullptr;
     const float* ln_beta = nullptr;
     void* ln_out = nullptr;         // bf16 [M, N]
+    // EPI_MULGRAD_*: saved pre-activation (post-activation for ReLU), bf16 [M, ld_pre]
+    const void* mul_pre = nullptr;
+    int ld_pre = 0;
 };
 
 template <int EPI>

@@ -43,6 +43,21 @@ __device__ __forceinline__ float act_rt(int epi, float v) {
     }
 }
 
+// derivative of the activation for the EPI_MULGRAD_* epilogues (bf16 mode: approximate transcendental units)
+__device__ __forceinline__ float act_grad_rt(int epi, float x) {
+    if (epi == EPI_MULGRAD_RELU) return x > 0.f ? 1.f : 0.f;
+    if (epi == EPI_MULGRAD_GELU_TANH) {
+        const float k = 0.79788456080286535588f;
+        const float x2 = x * x;
+        const float t = ptx::tanh_approx(k * fmaf(0.044715f * x, x2, x));
+        const float du = k * fmaf(3.0f * 0.044715f, x2, 1.0f);
+        return fmaf(0.5f * x * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+    }
+    const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752440f), 0.5f);
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return fmaf(x, pdf, cdf);
+}
+
 // byte offset of 16-byte chunk `c` of row `r` inside a SWIZZLE_128B staging buffer (1024-B aligned)
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -81,6 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = slice * BN;
     const bool has_ln = epi == EPI_BIAS_RESID_LN;          // requires BN == N (whole row in this CTA)
     const bool has_res = epi == EPI_BIAS_RESID || has_ln;
+    const bool has_mul = epi >= EPI_MULGRAD_RELU && epi <= EPI_MULGRAD_GELU_TANH;   // bf16 output only
 
     for (int i = threadIdx.x; i < BN; i += kTcThreads) {
         sBias[i] = ep.bias[n0 + i];
@@ -90,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmW);
         ptx::prefetch_tmap(&tmC);
-        if (has_res) ptx::prefetch_tmap(&tmR);
+        if (has_res || has_mul) ptx::prefetch_tmap(&tmR);
         if (has_ln) ptx::prefetch_tmap(&tmL);
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(w_full, 1);
@@ -167,6 +183,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row0 = mt * kTcBlockM + q * 32;
             const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             if (out_bf16) {
+                // EPI_MULGRAD_*: the saved pre-activation tile is TMA-loaded into the staging buffer (first chunk
+                // before the accumulator is ready), multiplied in place and TMA-stored -- like the residual path.
+                if (has_mul && lane == 0 && half < BN / 64) {
+                    ptx::bulk_wait_read<0>();
+                    ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                    ptx::tma_load_2d(ebuf, &tmR, &rb[0], n0 + half * 64, row0);
+                }
                 ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
                 ptx::tc_fence_after();
 #pragma unroll 1
@@ -174,20 +197,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r0[32], r1[32];
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64), r0);
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64 + 32), r1);
-                    if (lane == 0) { if (nebuf > 1) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>(); }
-                    __syncwarp();
-                    ptx::tc_wait_ld();
                     uint8_t* buf = ebuf + nbuf * kTcEpiBuf;
+                    if (lane == 0 && !(has_mul && ch == half)) {
+                        if (nebuf > 1) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+                        if (has_mul) {
+                            ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                            ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 64, row0);
+                        }
+                    }
+                    __syncwarp();
+                    if (has_mul) { ptx::mbar_wait(&rb[0], rphase0); rphase0 ^= 1; }
+                    ptx::tc_wait_ld();
                     const float* bsm = sBias + ch * 64;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {                 // 8 x 16 B chunks = 64 bf16 columns
                         uint32_t pk[4];
+                        uint4 pre4 = make_uint4(0u, 0u, 0u, 0u);
+                        if (has_mul) pre4 = *reinterpret_cast<const uint4*>(buf + sw128_off(lane, c));
+                        const uint32_t prew[4] = {pre4.x, pre4.y, pre4.z, pre4.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int col = c * 8 + j * 2;
-                            const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bsm[col];
-                            const float b = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + bsm[col + 1];
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(act_rt(epi, a), act_rt(epi, b));
+                            float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bsm[col];
+                            float b = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + bsm[col + 1];
+                            if (has_mul) {
+                                const float2 pv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&prew[j]));
+                                a *= act_grad_rt(epi, pv.x);
+                                b *= act_grad_rt(epi, pv.y);
+                            } else {
+                                a = act_rt(epi, a);
+                                b = act_rt(epi, b);
+                            }
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
                             pk[j] = *reinterpret_cast<uint32_t*>(&h2);
                         }
                         *reinterpret_cast<uint4*>(buf + sw128_off(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -424,6 +465,10 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
     tmR = tmC;
     tmL = tmC;
     if (is_ln && !make_tmap_2d(&tmL, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.ln_out, M, N, N, 64, 32)) return cudaErrorInvalidValue;
+    if (epi >= EPI_MULGRAD_RELU && epi <= EPI_MULGRAD_GELU_TANH) {
+        if (!out_bf16 || !ep.mul_pre || p.nebuf != 1) return cudaErrorInvalidValue;
+        if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.mul_pre, M, N, ep.ld_pre, 64, 32)) return cudaErrorInvalidValue;
+    }
     if (epi == EPI_BIAS_RESID || is_ln) {
         if (out_bf16) return cudaErrorInvalidValue;
         if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.resid, M, N, ep.ldr, 32, 32)) return cudaErrorInvalidValue;

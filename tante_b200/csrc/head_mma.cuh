@@ -14,155 +14,279 @@
 
 namespace tante {
 
-constexpr int kHeadRows = 64;          // rows per CTA: 4 warps x one 16-row m-block
 constexpr int kHeadWPitch = 144;       // bytes per weight row (64 bf16 + 16 B pad): conflict-free 32-bit B-fragment loads
 
-template <int KORD, int NB>
+// Persistent CTA; tile = ROWS stage-1 rows = NT consecutive latent tokens of ONE latent row (b, hp), i.e. a pixel
+// rectangle of P rows x XW = NT*P columns per field.  Per tile:
+//   loads    z tile (K x ROWS x 128 B, contiguous in HBM) by cp.async, requested while the previous tile is emitted;
+//            the u0 pixels of the tile as 128-bit register loads issued BEFORE phase 1, so they land under the MMAs
+//   phase 1  z tile x resident bf16 weights on mma.sync; derivative values (+ bias) scattered into shared memory in
+//            PIXEL-MAJOR planes S[k][d][pixel row][pixel column] (the MMA row/column -> pixel map is tile-invariant and
+//            lives in registers)
+//   phase 2  channels-first emit: thread = 4 consecutive pixels of one (field, pixel row): one 128-bit shared-memory
+//            read per order, Horner, one 128-bit store per emitted frame; consecutive threads walk along W, so every
+//            store instruction of a warp fills whole lines (frames / ring window / debug derivatives)
+//   phase 3  (rollout only) channels-last history, thread = one (pixel, field) with the field fastest, u0 from the
+//            copy phase 2 parked in shared memory (the ring slot may be overwritten by then)
+// All per-tile quantities (sample, frames to emit, ring position) are CTA-uniform.
+template <int KORD, int NB, int ROWS>
 __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) {
     extern __shared__ __align__(1024) uint8_t hsm[];
     const int NO = g.k0 * g.k0 * g.D;
-    uint8_t* sZ = hsm;                                              // [KORD][64 rows][128 B] swizzled
-    uint8_t* sW = sZ + KORD * kHeadRows * 128;                      // [KORD][NB*8][144 B]
-    float* sb = reinterpret_cast<float*>(sW + KORD * NB * 8 * kHeadWPitch);   // [KORD][D]
+    const int P = g.k0 * g.k1 * g.k2;
+    const int NT = ROWS / g.R1;                                      // tokens per tile (power of two)
+    const int XW = NT * P;                                           // pixel columns per tile (power of two, >= 16)
+    const int PS = P * XW + 4;                                       // floats per field plane (+4: bank spread for phase 3)
+    const int lXQ = 31 - __clz(XW / 4), lP = 31 - __clz(P), lXW = 31 - __clz(XW);
+    uint8_t* sZ = hsm;                                              // [KORD][ROWS][128 B] swizzled
+    uint8_t* sW = sZ + KORD * ROWS * 128;                           // [KORD][NB*8][144 B]
+    int* sOoff = reinterpret_cast<int*>(sW + KORD * NB * 8 * kHeadWPitch);    // [NB*8] MMA column -> plane offset (-1: padding)
+    float* sOb = reinterpret_cast<float*>(sOoff + NB * 8);                      // [KORD][NB*8] bias of the column's field
+    float* sS = sOb + KORD * NB * 8;                                            // [KORD (+1: u0, rollout)][D][PS]
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-    const long long row0 = (long long)blockIdx.x * kHeadRows;
+    const size_t HW = (size_t)g.H * g.W;
+    const int tpr = (g.Wp + NT - 1) / NT;                            // tiles per latent row
+    const long long ntiles = (long long)B * g.Hp * tpr;
+    const uint32_t zb = (uint32_t)__cvta_generic_to_shared(sZ);
+    float* y_out = hp.ptrs ? hp.ptrs->y_out : nullptr;
+    float* sU = sS + KORD * g.D * PS;                                // u0 planes (rollout only)
 
-    // ---- stage: z tiles by cp.async (coalesced 16-B chunks), weights converted to bf16 [o][c] ----
-    {
-        const uint32_t zb = (uint32_t)__cvta_generic_to_shared(sZ);
+    // the z tile is one contiguous run of 16-byte chunks: chunk i of the tile -> row i/8, swizzled column chunk
+    auto load_z = [&](long long tile) {
+        const long long bh = tile / tpr;
+        const int wpc = (int)(tile % tpr);
+        const long long row0 = (bh * g.Wp + (long long)wpc * NT) * g.R1;
+        const long long row_end = min(rows_total, (bh + 1) * g.Wp * g.R1);   // rows of the next latent row are not ours
 #pragma unroll
         for (int k = 0; k < KORD; ++k) {
-            const __nv_bfloat16* zk = reinterpret_cast<const __nv_bfloat16*>(hp.z[k]);
-            for (int i = tid; i < kHeadRows * 8; i += 128) {
-                const int r = i / 8, c = i % 8;
-                const bool ok = row0 + r < rows_total;
-                const __nv_bfloat16* src = zk + (ok ? (size_t)(row0 + r) * 64 + c * 8 : 0);
-                const uint32_t dst = zb + (uint32_t)(k * kHeadRows * 128 + r * 128 + ((c ^ (r & 7)) << 4));
-                const int nbytes = ok ? 16 : 0;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            const uint4* zk = reinterpret_cast<const uint4*>(hp.z[k]) + row0 * 8;
+#pragma unroll
+            for (int j = 0; j < ROWS * 8 / 128; ++j) {
+                const int i = tid + j * 128;
+                const int r = i >> 3, c = i & 7;
+                const int nbytes = row0 + r < row_end ? 16 : 0;
+                const uint32_t dst = zb + (uint32_t)(k * ROWS * 128 + r * 128 + ((c ^ (r & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(zk + (nbytes ? i : 0)), "r"(nbytes) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < KORD; ++k) {
-            for (int i = tid; i < NB * 8 * 64; i += 128) {
-                const int o = i / 64, c = i % 64;
-                const float w = o < NO ? hp.w3[k][(size_t)c * NO + o] : 0.f;
-                *reinterpret_cast<__nv_bfloat16*>(sW + (k * NB * 8 + o) * kHeadWPitch + c * 2) = __float2bfloat16_rn(w);
-            }
-            for (int i = tid; i < g.D; i += 128) sb[k * g.D + i] = hp.b3[k][i];
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
+    };
 
-    const int gq = lane >> 2, t = lane & 3;
-    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lchk = lane >> 4;
-    const uint32_t zb = (uint32_t)__cvta_generic_to_shared(sZ);
-
-    // ---- last deconv as [16 x 64] x [64 x NB*8] per order ----
-    float acc[KORD][NB][4];
+    // ---- once per CTA: first z tile in flight, weights -> bf16 [o][c] ----
+    if ((long long)blockIdx.x < ntiles) load_z(blockIdx.x);
 #pragma unroll
     for (int k = 0; k < KORD; ++k) {
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) acc[k][nb][0] = acc[k][nb][1] = acc[k][nb][2] = acc[k][nb][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            uint32_t a[4];
-            const int r = warp * 16 + lrow, c = ks * 2 + lchk;
-            ldsm_x4(zb + (uint32_t)(k * kHeadRows * 128 + r * 128 + ((c ^ (r & 7)) << 4)), a[0], a[1], a[2], a[3]);
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                const uint8_t* wr = sW + (k * NB * 8 + nb * 8 + gq) * kHeadWPitch + (ks * 16 + 2 * t) * 2;
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 16);
-                mma_bf16_16816(acc[k][nb], a, b0, b1);
-            }
+        for (int i = tid; i < NB * 8 * 64; i += 128) {
+            const int c = i / (NB * 8), o = i % (NB * 8);            // consecutive threads read consecutive o: coalesced
+            const float w = o < NO ? hp.w3[k][(size_t)c * NO + o] : 0.f;
+            *reinterpret_cast<__nv_bfloat16*>(sW + (k * NB * 8 + o) * kHeadWPitch + c * 2) = __float2bfloat16_rn(w);
         }
     }
 
-    // ---- Horner + emit; this thread owns rows (gq, gq+8) of its m-block, columns nb*8 + 2t + {0,1} ----
-    const size_t HW = (size_t)g.H * g.W;
-    float* y_out = hp.ptrs ? hp.ptrs->y_out : nullptr;
+    // ---- tile-invariant maps (registers) ----
+    const int gq = lane >> 2, t = lane & 3;
+    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1), lchk = lane >> 4;
+    // MMA fragment rows (gq, gq+8 of this warp's m-block) -> pixel (row, column) of the stage-1 pixel block:
+    // stage-1 row r1 = ((a*k2 + a')*k1 + b)*k1 + b'  ->  pixel row (a*k1 + b)*k0, pixel column tok*P + (a'*k1 + b')*k0
+    int rowbase[2];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-        const long long row = row0 + warp * 16 + gq + 8 * hh;
-        if (row >= rows_total) continue;
-        long long tkn = row / g.R1;
-        const int r1 = (int)(row % g.R1);
-        const int wp = (int)(tkn % g.Wp); tkn /= g.Wp;
-        const int hpp = (int)(tkn % g.Hp);
-        const int b = (int)(tkn / g.Hp);
-        int h1, w1;
-        stage1_row_to_hw(g, hpp, wp, r1, h1, w1);
+        const int r = warp * 16 + gq + 8 * hh;
+        const int tok = r / g.R1;
+        int r1 = r % g.R1;
+        const int bp = r1 % g.k1; r1 /= g.k1;
+        const int bq = r1 % g.k1; r1 /= g.k1;
+        const int ap = r1 % g.k2;
+        const int a = r1 / g.k2;
+        rowbase[hh] = ((a * g.k1 + bq) * g.k0) * XW + tok * P + (ap * g.k1 + bp) * g.k0;
+    }
+    // MMA fragment columns o = (c*k0 + c')*D + d  ->  plane d, pixel (+c, +c'); bias of field d  (shared-memory tables)
+    for (int o = tid; o < NB * 8; o += 128) {
+        const int d = o % g.D, cp = (o / g.D) % g.k0, c = o / (g.D * g.k0);
+        sOoff[o] = o < NO ? d * PS + c * XW + cp : -1;
+#pragma unroll
+        for (int k = 0; k < KORD; ++k) sOb[k * NB * 8 + o] = o < NO ? hp.b3[k][d] : 0.f;
+    }
+    // emit items of this thread: item = tid + 128*j -> (field, pixel row, 4-pixel run), all tile-invariant:
+    // shared-memory float offset inside the planes / global float offset inside a frame
+    const int nitems = g.D * P * (XW / 4);
+    auto item_soff = [&](int item) {
+        return (item >> (lXQ + lP)) * PS + ((item >> lXQ) & (P - 1)) * XW + ((item & ((1 << lXQ) - 1)) << 2);
+    };
+    auto item_goff = [&](int item) {
+        return (size_t)(item >> (lXQ + lP)) * HW + (size_t)(((item >> lXQ) & (P - 1)) * g.W + ((item & ((1 << lXQ) - 1)) << 2));
+    };
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long bh = tile / tpr;
+        const int wpc = (int)(tile % tpr);
+        const int b = (int)(bh / g.Hp), hpp = (int)(bh % g.Hp);
+        const int xvalid = min(NT, g.Wp - wpc * NT) * P;             // pixel columns of this tile that exist
         const int n = hp.n_arr[b];
-        if (n <= 0 && !hp.deriv_dbg) continue;
         const int fc = hp.fcount ? hp.fcount[b] : g.T;
-        const int u_slot = (fc + g.T - 1) % g.T;
-        const float* u0p = hp.u_ring + ((size_t)(b * g.T + u_slot) * g.D) * HW;
-        const int cum = hp.cum ? hp.cum[b] : 0;
+        const size_t pix0 = (size_t)hpp * P * g.W + (size_t)wpc * XW;
+        // u0 of this thread's items: in flight during phase 1
+        float4 u0r[NB];
+        {
+            const float* u0p = hp.u_ring + (size_t)(b * g.T + (fc + g.T - 1) % g.T) * g.D * HW + pix0;
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
+            for (int j = 0; j < NB; ++j) {
+                u0r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int item = tid + 128 * j;
+                if (n > 0 && item < nitems && ((item & ((1 << lXQ) - 1)) << 2) < xvalid)
+                    u0r[j] = *reinterpret_cast<const float4*>(u0p + item_goff(item));
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                             // z tile visible; previous emit is done with S
+
+        // ---- phase 1: last deconv as [16 x 64] x [64 x NB*8] per order, + bias, scattered into the pixel planes ----
+        if (warp * 16 < ROWS) {                                      // 32-row tiles: two MMA warps, four emit warps
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int o = nb * 8 + 2 * t + j;
-                if (o >= NO) continue;
-                const int d = o % g.D;
-                const int cp = (o / g.D) % g.k0;
-                const int c = o / (g.D * g.k0);
-                const size_t pix = (size_t)(h1 * g.k0 + c) * g.W + (w1 * g.k0 + cp);
-                float dk[KORD];
+            for (int k = 0; k < KORD; ++k) {
+                float acc[NB][4];
 #pragma unroll
-                for (int k = 0; k < KORD; ++k) dk[k] = acc[k][nb][2 * hh + j] + sb[k * g.D + d];
-                if (hp.deriv_dbg) {
+                for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
 #pragma unroll
-                    for (int k = 0; k < KORD; ++k) hp.deriv_dbg[(((size_t)k * B + b) * g.D + d) * HW + pix] = dk[k];
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t a[4];
+                    const int r = warp * 16 + lrow, c = ks * 2 + lchk;
+                    ldsm_x4(zb + (uint32_t)(k * ROWS * 128 + r * 128 + ((c ^ (r & 7)) << 4)), a[0], a[1], a[2], a[3]);
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const uint8_t* wr = sW + (k * NB * 8 + nb * 8 + gq) * kHeadWPitch + (ks * 16 + 2 * t) * 2;
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 16);
+                        mma_bf16_16816(acc[nb], a, b0, b1);
+                    }
                 }
-                if (n <= 0) continue;
-                const float u0 = u0p[(size_t)d * HW + pix];
-                for (int i = 1; i <= n; ++i) {
-                    const float dt = (float)i * hp.fi;
-                    float v = 0.f;
+                float* Sk = sS + k * g.D * PS;
 #pragma unroll
-                    for (int k = KORD; k >= 1; --k) v = (dk[k - 1] + v) * (dt / (float)k);
-                    const float val = v + u0;
-                    if (hp.frames) hp.frames[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix] = val;
-                    if (y_out) {
-                        const int fidx = cum + i - 1;
-                        if (fidx < hp.n_roll) y_out[(((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D + d] = val;
-                        if (i > n - g.T) {
-                            const int slot = (fc + i - 1) % g.T;
-                            hp.ring_out[((size_t)(b * g.T + slot) * g.D + d) * HW + pix] = val;
-                        }
+                for (int nb = 0; nb < NB; ++nb) {
+                    const int2 oo = *reinterpret_cast<const int2*>(sOoff + nb * 8 + 2 * t);
+                    const float2 ob = *reinterpret_cast<const float2*>(sOb + k * NB * 8 + nb * 8 + 2 * t);
+                    if (oo.x >= 0) {
+                        Sk[rowbase[0] + oo.x] = acc[nb][0] + ob.x;
+                        Sk[rowbase[1] + oo.x] = acc[nb][2] + ob.x;
+                    }
+                    if (oo.y >= 0) {
+                        Sk[rowbase[0] + oo.y] = acc[nb][1] + ob.y;
+                        Sk[rowbase[1] + oo.y] = acc[nb][3] + ob.y;
                     }
                 }
             }
         }
+        __syncthreads();                                             // S complete, z tile consumed
+        if (tile + gridDim.x < ntiles) load_z(tile + gridDim.x);     // overlaps the emit below
+        if (n <= 0 && !hp.deriv_dbg) continue;
+
+        // ---- phase 2: channels-first emit ----
+        const int cum = hp.cum ? hp.cum[b] : 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const int item = tid + 128 * j;
+            if (item >= nitems || ((item & ((1 << lXQ) - 1)) << 2) >= xvalid) continue;
+            const int soff = item_soff(item);
+            float4 dk[KORD];
+#pragma unroll
+            for (int k = 0; k < KORD; ++k) dk[k] = *reinterpret_cast<const float4*>(sS + k * g.D * PS + soff);
+            const size_t goff = pix0 + item_goff(item);
+            if (hp.deriv_dbg) {
+#pragma unroll
+                for (int k = 0; k < KORD; ++k)
+                    *reinterpret_cast<float4*>(hp.deriv_dbg + ((size_t)k * B + b) * g.D * HW + goff) = dk[k];
+            }
+            if (n <= 0) continue;
+            const float4 u0 = u0r[j];
+            if (y_out) *reinterpret_cast<float4*>(sU + soff) = u0;
+            for (int i = 1; i <= n; ++i) {
+                const float dt = (float)i * hp.fi;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = KORD; k >= 1; --k) {
+                    const float sc = dt / (float)k;
+                    v.x = (dk[k - 1].x + v.x) * sc; v.y = (dk[k - 1].y + v.y) * sc;
+                    v.z = (dk[k - 1].z + v.z) * sc; v.w = (dk[k - 1].w + v.w) * sc;
+                }
+                v.x += u0.x; v.y += u0.y; v.z += u0.z; v.w += u0.w;
+                if (hp.frames) *reinterpret_cast<float4*>(hp.frames + ((size_t)b * hp.n_cap + (i - 1)) * g.D * HW + goff) = v;
+                if (y_out && i > n - g.T) {
+                    const int slot = (fc + i - 1) % g.T;
+                    *reinterpret_cast<float4*>(hp.ring_out + (size_t)(b * g.T + slot) * g.D * HW + goff) = v;
+                }
+            }
+        }
+        if (!y_out || n <= 0) continue;
+        __syncthreads();                                             // u0 planes visible
+
+        // ---- phase 3: channels-last history, thread = (pixel row, pixel column, field), field fastest ----
+        const int nitemsB = P * xvalid * g.D;
+        const int xd = xvalid * g.D;
+        for (int item = tid; item < nitemsB; item += 128) {
+            const int hr = item / xd;
+            const int rem = item - hr * xd;
+            const int x = rem / g.D, d = rem - x * g.D;
+            const int so = d * PS + hr * XW + x;
+            float dk[KORD];
+#pragma unroll
+            for (int k = 0; k < KORD; ++k) dk[k] = sS[k * g.D * PS + so];
+            const float u0 = sU[so];
+            const size_t pix = pix0 + (size_t)hr * g.W + x;
+            for (int i = 1; i <= n; ++i) {
+                const int fidx = cum + i - 1;
+                if (fidx >= hp.n_roll) break;
+                const float dt = (float)i * hp.fi;
+                float v = 0.f;
+#pragma unroll
+                for (int k = KORD; k >= 1; --k) v = (dk[k - 1] + v) * (dt / (float)k);
+                y_out[(((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D + d] = v + u0;
+            }
+        }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int KORD, int NB>
-static cudaError_t launch_head_mma_inst(const HeadParams& hp, const PatchGeom& g, long long rows, int B, cudaStream_t st) {
-    const size_t smem = (size_t)KORD * kHeadRows * 128 + (size_t)KORD * NB * 8 * kHeadWPitch + (size_t)KORD * g.D * 4;
-    // (largest instantiation needs 42 KB of dynamic shared memory: below the 48 KB default limit)
-    const unsigned blocks = (unsigned)((rows + kHeadRows - 1) / kHeadRows);
-    taylor_head_mma_kernel<KORD, NB><<<blocks, 128, smem, st>>>(hp, g, rows, B);
+static cudaError_t launch_head_mma_inst(const HeadParams& hp, const PatchGeom& g, long long rows, int B, int num_sms,
+                                        cudaStream_t st) {
+    constexpr int ROWS = 64;     // (32-row tiles for the high orders were measured slower: two idle MMA warps, 64-B runs)
+    const int P = g.k0 * g.k1 * g.k2;
+    const int NT = ROWS / g.R1;
+    const int PS = P * NT * P + 4;
+    const size_t smem = (size_t)KORD * ROWS * 128 + (size_t)KORD * NB * 8 * kHeadWPitch + (size_t)(KORD + 1) * NB * 8 * 4 +
+                        (size_t)(KORD + (hp.ptrs ? 1 : 0)) * g.D * PS * 4;
+    const long long tiles = (long long)B * g.Hp * ((g.Wp + NT - 1) / NT);
+    static size_t attr_smem = 0, occ_smem = ~(size_t)0;      // per instantiation
+    static int occ_cache = 1;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(taylor_head_mma_kernel<KORD, NB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
+    if (smem != occ_smem) {
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, taylor_head_mma_kernel<KORD, NB, ROWS>, 128, smem) != cudaSuccess) occ = 1;
+        occ_cache = std::max(1, occ);
+        occ_smem = smem;
+    }
+    const unsigned blocks = (unsigned)std::min<long long>(tiles, (long long)num_sms * occ_cache);
+    taylor_head_mma_kernel<KORD, NB, ROWS><<<blocks, 128, smem, st>>>(hp, g, rows, B);
     return cudaGetLastError();
 }
 
 // Returns false when (K, D) is outside the instantiated set (caller falls back to the FFMA kernel).
-static bool launch_head_mma(const HeadParams& hp, const PatchGeom& g, int C1, long long rows, int B, cudaStream_t st,
-                            cudaError_t* err) {
-    if (C1 != 64) return false;
+static bool launch_head_mma(const HeadParams& hp, const PatchGeom& g, int C1, long long rows, int B, int num_sms,
+                            cudaStream_t st, cudaError_t* err) {
+    if (C1 != 64 || 32 % g.R1 != 0 || rows % g.R1 != 0 || (g.W & 3)) return false;
     const int NO = g.k0 * g.k0 * g.D;
     const int nb = (NO + 7) / 8;
     const int K = hp.K;
 #define TANTE_HEAD(KO, NBv) \
-    if (K == KO && nb <= NBv) { *err = launch_head_mma_inst<KO, NBv>(hp, g, rows, B, st); return true; }
+    if (K == KO && nb <= NBv) { *err = launch_head_mma_inst<KO, NBv>(hp, g, rows, B, num_sms, st); return true; }
     TANTE_HEAD(1, 2) TANTE_HEAD(2, 2) TANTE_HEAD(3, 2) TANTE_HEAD(4, 2)
     TANTE_HEAD(1, 4) TANTE_HEAD(2, 4) TANTE_HEAD(3, 4)
-    TANTE_HEAD(1, 6) TANTE_HEAD(2, 6)
-    TANTE_HEAD(1, 8)
+    TANTE_HEAD(1, 6) TANTE_HEAD(2, 6) TANTE_HEAD(3, 6) TANTE_HEAD(4, 6)
+    TANTE_HEAD(1, 8) TANTE_HEAD(2, 8) TANTE_HEAD(3, 8) TANTE_HEAD(4, 8)
 #undef TANTE_HEAD
     return false;
 }

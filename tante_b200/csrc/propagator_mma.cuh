@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
         *reinterpret_cast<__nv_bfloat16*>(sW2 + j * WPITCH + k * 2) = __float2bfloat16_rn(ok ? W2[j * S + k] : 0.f);
     }
     for (int i = tid; i < SP; i += 128) { sb1[i] = i < S ? b1[i] : 0.f; sb2[i] = i < S ? b2[i] : 0.f; }
+#pragma unroll 4
     for (int i = tid; i < SP * 32; i += 128) {
         const int p = i / 32, c4 = (i % 32) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -96,23 +97,35 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
             }
             __syncwarp();     // the hidden columns of a warp are consumed only by the same warp
         } else {
+            // residual add in two sweeps: all loads first (x may alias the output, so a load cannot be hoisted over
+            // an earlier store and an interleaved loop would serialise 8*MB L2 round trips per thread)
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int p = mb * 16 + g + 8 * hh;
-                    if (p >= S) continue;
-                    const float bb = sb2[p];
+                    const float bb = p < S ? sb2[p] : 0.f;
 #pragma unroll
                     for (int nb = 0; nb < 4; ++nb) {
                         const int c = warp * 32 + nb * 8 + 2 * t;
-                        if (c < ncol) {
-                            float2* px = reinterpret_cast<float2*>(base + (size_t)p * IC + c);
-                            float2 xv = *reinterpret_cast<const float2*>(ibase + (size_t)p * IC + c);
-                            xv.x += acc[mb][nb][2 * hh + 0] + bb;
-                            xv.y += acc[mb][nb][2 * hh + 1] + bb;
-                            *px = xv;
+                        if (p < S && c < ncol) {
+                            const float2 xv = *reinterpret_cast<const float2*>(ibase + (size_t)p * IC + c);
+                            acc[mb][nb][2 * hh + 0] += xv.x + bb;
+                            acc[mb][nb][2 * hh + 1] += xv.y + bb;
                         }
+                    }
+                }
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int p = mb * 16 + g + 8 * hh;
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        const int c = warp * 32 + nb * 8 + 2 * t;
+                        if (p < S && c < ncol)
+                            *reinterpret_cast<float2*>(base + (size_t)p * IC + c) = make_float2(acc[mb][nb][2 * hh], acc[mb][nb][2 * hh + 1]);
                     }
                 }
             }

@@ -19,6 +19,7 @@
 #include "gemm_tc.cuh"
 #include "attention_mma.cuh"
 #include "propagator_mma.cuh"
+#include "propagator_bwd_mma.cuh"
 #include "head_mma.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
@@ -124,6 +125,7 @@ struct tante_handle_s {
     int64_t arena_elems = 0;
     DevBuf arena, arena_bf16, descs;
     bool packed = false;
+    bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
 
     // workspace
     int max_batch = 0, max_roll = 0;
@@ -229,7 +231,8 @@ void build_plan(tante_handle_s* h) {
     h->C = c.embed_dim; h->C1 = h->C / 4; h->C2 = h->C / 2;
     h->Hp = c.H / c.patch_scale; h->Wp = c.W / c.patch_scale; h->L = h->Hp * h->Wp;
     h->T = c.in_T; h->D = c.n_fields; h->K = c.taylor_order; h->HD = hd;
-    REQUIRE(h->Hp <= 64 && h->Wp <= 64 && h->T <= 64, "axis length > 64 is not supported by the axial kernels yet");
+    // checked by the model entry points, not here: the head microbenchmark (tante_bench_head) needs no backbone
+    h->axes_ok = h->Hp <= 64 && h->Wp <= 64 && h->T <= 64;
     PatchGeom& g = h->geom;
     g.k0 = k[0]; g.k1 = k[1]; g.k2 = k[2];
     g.D = h->D; g.H = c.H; g.W = c.W; g.Hp = h->Hp; g.Wp = h->Wp; g.T = h->T;
@@ -501,7 +504,7 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
     const long long rows = (long long)B * h->L * h->geom.R1;
     if (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
-        if (launch_head_mma(hp, h->geom, h->C1, rows, B, st, &e)) {
+        if (launch_head_mma(hp, h->geom, h->C1, rows, B, h->num_sms, st, &e)) {
             CK(e);
             h->launches++;
             return;
@@ -725,6 +728,27 @@ void gemm_dx(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* out, i
     gemm<TA>(h, EPI_BIAS, A, lda, wT_off, out, ldc, sizeof(TA) == 4, M, N, K, ep, st);
 }
 
+// dX = (dY * W) o f'(pre): in tensor mode the activation derivative is applied in the GEMM epilogue (the saved
+// pre-activation tile is TMA-loaded next to the accumulator); in the exact mode it is a separate elementwise pass.
+// `out` and `pre` are both [M][N] contiguous.
+template <typename TA, int ACT>
+void gemm_dx_act(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* out, const TA* pre, int M, int N, int K,
+                 cudaStream_t st) {
+    // measured on B200 (Active Matter, M = 65536): fused epilogue 60 us vs 17 us GEMM + 26 us elementwise pass -- the
+    // single 4 KB staging buffer per epilogue warp keeps too few bytes in flight, so the fusion is opt-in for now
+    static const bool fuse = getenv("TANTE_FUSE_ACTGRAD") && atoi(getenv("TANTE_FUSE_ACTGRAD")) != 0;
+    if (sizeof(TA) == 2 && fuse) {
+        EpiParams ep; ep.bias = AF(h, h->zero_off);
+        REQUIRE(N <= 4096, "input-gradient GEMM wider than the zero-bias vector");
+        ep.mul_pre = pre; ep.ld_pre = N;
+        const int epi = ACT == ACT_RELU ? EPI_MULGRAD_RELU : (ACT == ACT_GELU_ERF ? EPI_MULGRAD_GELU_ERF : EPI_MULGRAD_GELU_TANH);
+        gemm<TA>(h, epi, A, lda, wT_off, out, N, false, M, N, K, ep, st);
+    } else {
+        gemm_dx<TA>(h, A, lda, wT_off, out, N, M, N, K, st);
+        launch_act_bwd<TA, ACT>(h, out, pre, (long long)M * N, st);
+    }
+}
+
 template <typename TA>
 void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamma, float* dxs, TA* dxb, float* dg, float* db,
                    long long rows, cudaStream_t st) {
@@ -773,6 +797,16 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
+    if (h->cfg.precision == TANTE_PREC_BF16) {
+        cudaError_t e = cudaSuccess;
+        if (launch_propagator_bwd_mma(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                      AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
+                                      GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]), h->num_sms, st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
     int S4 = (S + 3) & ~3;
     if (S4 > 4 && (S4 & (S4 - 1))) { int p2 = 8; while (p2 < S4) p2 <<= 1; S4 = p2; }
     const int CW = kPropBwdSlab / S4;
@@ -899,7 +933,8 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         // enc_conv_1 as im2col (kept for the weight gradient) + GEMM over the zero-padded patch matrix
         const long long rows_in = (long long)tokens * g.R1;
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv GEMM");
-        conv1_im2col_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
+        if (g.k0 * g.k1 * g.k2 >= 4) conv1_im2col_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
+        else conv1_im2col_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
@@ -1013,7 +1048,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         bool done = false;
         if (kTensor) {
             cudaError_t e = cudaSuccess;
-            if (launch_head_mma(hp, g, C1, rows, B, st, &e)) { CK(e); done = true; }
+            if (launch_head_mma(hp, g, C1, rows, B, h->num_sms, st, &e)) { CK(e); done = true; }
         }
         if (!done) {
             const int NO = g.k0 * g.k0 * h->D;
@@ -1061,7 +1096,9 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         for (int k = 0; k < K; ++k) hp.G[k] = TP<TA>(h->hG) + (size_t)k * rows1 * kHeadPad;
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
         hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); hp.grad_input = grad_input;
-        head_gather_kernel<TA><<<blocks_for(rows1, 128), 128, 0, st>>>(hp, g, rows1);
+        const size_t hsmem = (size_t)K * kPatchRows * kPatchPitch * sizeof(float);
+        if (g.k0 * g.k1 * g.k2 >= 4) head_gather_kernel<TA, 4><<<blocks_for(rows1, kPatchRows), 128, hsmem, st>>>(hp, g, rows1);
+        else head_gather_kernel<TA, 2><<<blocks_for(rows1, kPatchRows), 128, hsmem, st>>>(hp, g, rows1);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1073,14 +1110,12 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         // dec_conv_3: d_k = z2act * W3 + b3  ->  dW3 = z2act^T G, db3 = colsum(G), dz2 = (G W3^T) o gelu'(z2pre)
         wgrad_pad<TA>(h, TP<TA>(ot.z2act), C1, C1, G, kHeadPad, kHeadPad, GA(h, op.decw[2]), NO, NO, rows1, st);
         launch_colsum<TA>(h, G, kHeadPad, rows1, NO, GA(h, op.decb[2]), st);
-        gemm_dx<TA>(h, G, kHeadPad, op.w3pad, dz, C1, (int)rows1, C1, kHeadPad, st);
-        launch_act_bwd<TA, ACT_GELU_ERF>(h, dz, TP<TA>(ot.z2pre), rows1 * C1, st);
+        gemm_dx_act<TA, ACT_GELU_ERF>(h, G, kHeadPad, op.w3pad, dz, TP<TA>(ot.z2pre), (int)rows1, C1, kHeadPad, st);
         // dec_conv_2: z2pre[M2, N2] = z1act[M2, C2] * Wd2^T + b
         const int M2 = BL * g.R2, N2 = g.k1 * g.k1 * C1;
         wgrad<TA>(h, dz, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st, GA(h, op.decb[1]));
         TA* dz1 = TP<TA>(h->hz1);
-        gemm_dx<TA>(h, dz, N2, op.decwT[1], dz1, C2, M2, C2, N2, st);
-        launch_act_bwd<TA, ACT_GELU_ERF>(h, dz1, TP<TA>(ot.z1pre), (long long)M2 * C2, st);
+        gemm_dx_act<TA, ACT_GELU_ERF>(h, dz, N2, op.decwT[1], dz1, TP<TA>(ot.z1pre), M2, C2, N2, st);
         // dec_conv_1: z1pre[BL, N1] = dmod[BL, C] * Wd1^T + b
         const int N1 = g.k2 * g.k2 * C2;
         TA* dmod = h->cfg.deg ? TP<TA>(ot.dl) : TP<TA>(ot.dmod);
@@ -1110,8 +1145,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             CK(cudaGetLastError());
             h->launches++;
             wgrad<TA>(h, hi2, C / 4, TP<TA>(ot.i1), C / 2, GA(h, op.intw[1]), BL, C / 4, C / 2, st, GA(h, op.intb[1]));
-            gemm_dx<TA>(h, hi2, C / 4, op.intwT[1], hi1, C / 2, BL, C / 2, C / 4, st);
-            launch_act_bwd<TA, ACT_RELU>(h, hi1, TP<TA>(ot.i1), (long long)BL * (C / 2), st);
+            gemm_dx_act<TA, ACT_RELU>(h, hi2, C / 4, op.intwT[1], hi1, TP<TA>(ot.i1), BL, C / 2, C / 4, st);
             wgrad<TA>(h, hi1, C / 2, TP<TA>(ot.dl), C, GA(h, op.intw[0]), BL, C / 2, C, st, GA(h, op.intb[0]));
             gemm_dx<TA>(h, hi1, C / 2, op.intwT[0], hd, C, BL, C, C / 2, st);
         }
@@ -1131,8 +1165,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             const float* x_mid = FP(ot.X[2 * li + 1]);
             // MLP half: x_out = x_mid + W2 gelu_tanh(W0 ln2(x_mid) + b0) + b2
             wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), C, GA(h, lp.m2w), tokens, C, C, st, GA(h, lp.m2b));
-            gemm_dx<TA>(h, dxb, C, lp.m2wT, g1, C, tokens, C, C, st);
-            launch_act_bwd<TA, ACT_GELU_TANH>(h, g1, TP<TA>(ot.hpre[li]), (long long)tokens * C, st);
+            gemm_dx_act<TA, ACT_GELU_TANH>(h, dxb, C, lp.m2wT, g1, TP<TA>(ot.hpre[li]), tokens, C, C, st);
             wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
             gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
             launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st);
@@ -1166,12 +1199,10 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     const int M2 = tokens * g.R2;
     const long long rows_in = (long long)tokens * g.R1;
     wgrad<TA>(h, g2, C, TP<TA>(tp.a2act), K3, GA(h, h->enc_w[2]), tokens, C, K3, st, GA(h, h->enc_b[2]));
-    gemm_dx<TA>(h, g2, C, h->enc_wT[2], gq, K3, tokens, K3, C, st);
-    launch_act_bwd<TA, ACT_GELU_ERF>(h, gq, TP<TA>(tp.a2pre), (long long)M2 * C2, st);
+    gemm_dx_act<TA, ACT_GELU_ERF>(h, g2, C, h->enc_wT[2], gq, TP<TA>(tp.a2pre), tokens, K3, C, st);
     wgrad<TA>(h, gq, C2, TP<TA>(tp.a1act), K2, GA(h, h->enc_w[1]), M2, C2, K2, st, GA(h, h->enc_b[1]));
     TA* ga1 = TP<TA>(h->ga1);
-    gemm_dx<TA>(h, gq, C2, h->enc_wT[1], ga1, K2, M2, K2, C2, st);
-    launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), rows_in * C1, st);
+    gemm_dx_act<TA, ACT_GELU_ERF>(h, gq, C2, h->enc_wT[1], ga1, TP<TA>(tp.a1pre), M2, K2, C2, st);
     (void)input;      // the patches were kept by the forward (tape im2col)
     TA* cols = TP<TA>(h->cols);
     wgrad_pad<TA>(h, ga1, C1, C1, TP<TA>(tp.cols), kHeadPad, kHeadPad, GA(h, h->enc_w[0]), NO, NO, rows_in, st, GA(h, h->enc_b[0]));
@@ -1179,7 +1210,8 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         // dpatch[rows, 64 (K1 padded)] = da1[rows, C1] * W1[C1][K1]  (thin GEMM), then scatter-add into the pixels
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
         gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], cols, kHeadPad, (int)rows_in, kHeadPad, C1, st);
-        conv1_col2im_kernel<TA><<<blocks_for(rows_in, 128), 128, 0, st>>>(cols, g, grad_input, rows_in);
+        if (g.k0 * g.k1 * g.k2 >= 4) conv1_col2im_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in);
+        else conv1_col2im_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1194,7 +1226,9 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     }
 }
 
-void ensure_ready(tante_handle_s* h, int B) {
+void ensure_ready(tante_handle_s* h, int B, bool need_backbone = true) {
+    if (need_backbone && !h->axes_ok)
+        throw Error(TANTE_ERR_INVALID, "axis length > 64 is not supported by the axial kernels yet");
     if (!h->packed) throw Error(TANTE_ERR_STATE, "parameters not packed: call tante_bind_param for every parameter, then tante_pack_params");
     if (B < 1 || B > h->max_batch) throw Error(TANTE_ERR_STATE, "batch exceeds tante_reserve(max_batch)");
 }
@@ -1211,6 +1245,10 @@ void set_smem_attrs() {
     HEADATTR(__nv_bfloat16, 1); HEADATTR(__nv_bfloat16, 2); HEADATTR(__nv_bfloat16, 3); HEADATTR(__nv_bfloat16, 4);
 #undef HEADATTR
     CK(cudaFuncSetAttribute(propagator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK((cudaFuncSetAttribute(head_gather_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));
+    CK((cudaFuncSetAttribute(head_gather_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));
+    CK((cudaFuncSetAttribute(head_gather_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));
+    CK((cudaFuncSetAttribute(head_gather_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));
 #define ATTBATTR(TA, HDv) CK(cudaFuncSetAttribute(attention_bwd_kernel<TA, HDv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024))
     ATTBATTR(float, 16); ATTBATTR(float, 32); ATTBATTR(float, 64);
     ATTBATTR(__nv_bfloat16, 16); ATTBATTR(__nv_bfloat16, 32); ATTBATTR(__nv_bfloat16, 64);
@@ -1701,7 +1739,7 @@ int tante_bench_head(tante_handle_t h, const float* u, float* frames, int32_t B,
     return guarded([&] {
         REQUIRE(h && u && frames && ms_out && n_frames >= 1 && iters >= 1, "bad argument");
         CK(cudaSetDevice(h->device));
-        ensure_ready(h, B);
+        ensure_ready(h, B, false);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
         std::vector<int> n(B, n_frames);
         CK(cudaMemcpyAsync(h->nbuf.p, n.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));

@@ -135,7 +135,7 @@ def _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=False):
 
 
 @pytest.mark.parametrize("prec,tol", [("fp32", FP32_GRAD_TOL), ("bf16", BF16_GRAD_TOL)])
-@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2"])
+@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48"])
 def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
     """One model call with a random cotangent on the frames AND on R_t, multi-frame emit (n = 3) included:
     every parameter gradient and the input gradient against torch autograd over the CPU oracle."""
@@ -147,11 +147,19 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         cfg = O.OracleConfig(n_fields=5, H=32, W=48, taylor_order=1, attn_axes="HWT", deg=True, patch_scale=4,
                              output_length=2, frame_interval=0.5)
         rt_bias, out_T = 0.0, 1
+    elif case == "deg_k1_axes32":
+        # axis lengths 32 / 16 and 11 fields (the Active Matter geometry): tensor-core propagator backward, K1 = 44
+        cfg = O.OracleConfig(n_fields=11, H=256, W=128, taylor_order=1, attn_axes="HWT", deg=True)
+        rt_bias, out_T = 0.0, 1
+    elif case == "adp_k1_axes48":
+        # TRL geometry: axis length 48 (padded to 64 in the tensor-core propagator kernels)
+        cfg = O.OracleConfig(n_fields=4, H=128, W=384, taylor_order=1, attn_axes="WHT", deg=False)
+        rt_bias, out_T = 1.3, 4
     else:
         cfg = O.OracleConfig(n_fields=2, H=16, W=24, taylor_order=3, attn_axes="T-H-W", deg=False, patch_scale=2)
         rt_bias, out_T = 1.3, 4
     sd = O.make_state_dict(cfg, 311, rt_bias)
-    B = 3
+    B = 2 if "axes" in case else 3
     x = O.make_input(cfg, B, 312)
     with torch.no_grad():
         y0 = O.forward(sd, cfg, x, out_T)

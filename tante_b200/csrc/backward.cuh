@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TA* __restrict__ pre
     float v[4], o[4];
     Vec4<TA>::load(pre + i * 4, v);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = ACT == ACT_GELU_ERF ? gelu_erf(v[j]) : (ACT == ACT_GELU_TANH ? gelu_tanh(v[j]) : fmaxf(v[j], 0.f));
+    for (int j = 0; j < 4; ++j)
+        o[j] = ACT == ACT_GELU_ERF ? ActMath<TA>::gelu_erf_f(v[j]) : (ACT == ACT_GELU_TANH ? ActMath<TA>::gelu_tanh_f(v[j]) : fmaxf(v[j], 0.f));
     Vec4<TA>::store(out + i * 4, o);
 }
 
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(TA* __restrict__ g, const 
     Vec4<TA>::load(g + i * 4, d);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-        d[j] *= ACT == ACT_GELU_ERF ? gelu_erf_grad(v[j]) : (ACT == ACT_GELU_TANH ? gelu_tanh_grad(v[j]) : (v[j] > 0.f ? 1.f : 0.f));
+        d[j] *= ACT == ACT_GELU_ERF ? ActMath<TA>::gelu_erf_g(v[j]) : (ACT == ACT_GELU_TANH ? ActMath<TA>::gelu_tanh_g(v[j]) : (v[j] > 0.f ? 1.f : 0.f));
     Vec4<TA>::store(g + i * 4, d);
 }
 
@@ -470,6 +471,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const TA* __restrict
 // Slab = one `outer` x CW columns with S4*CW = 4096 (short axes get wide slabs, so all 256 threads work for
 // the T axis, S = 4, as well as for S = 64): threads = (CW/4 column groups) x (S4/4 row groups) of 4 x 4 tiles.
 constexpr int kPropBwdSlab = 4096;      // floats per slab array
+template <typename TM /* float: accurate erf/exp; bf16: the approximate versions the tensor-mode forward uses */>
 __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __restrict__ xin, float* __restrict__ dy,
                                                              int S, long long IC, long long n_outer,
                                                              const float* __restrict__ W1, const float* __restrict__ b1,
@@ -557,7 +559,8 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
             for (int a = 0; a < 4; ++a) {
                 *reinterpret_cast<float4*>(sp + (jt * 4 + a) * CWP + cg * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
                 *reinterpret_cast<float4*>(sh + (jt * 4 + a) * CWP + cg * 4) =
-                    make_float4(gelu_erf(acc[a][0]), gelu_erf(acc[a][1]), gelu_erf(acc[a][2]), gelu_erf(acc[a][3]));
+                    make_float4(ActMath<TM>::gelu_erf_f(acc[a][0]), ActMath<TM>::gelu_erf_f(acc[a][1]), ActMath<TM>::gelu_erf_f(acc[a][2]),
+                                ActMath<TM>::gelu_erf_f(acc[a][3]));
             }
         }
         __syncthreads();
@@ -573,8 +576,8 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
             for (int a = 0; a < 4; ++a) {
                 float4* pp = reinterpret_cast<float4*>(sp + (it * 4 + a) * CWP + cg * 4);
                 const float4 pr = *pp;
-                *pp = make_float4(acc[a][0] * gelu_erf_grad(pr.x), acc[a][1] * gelu_erf_grad(pr.y),
-                                  acc[a][2] * gelu_erf_grad(pr.z), acc[a][3] * gelu_erf_grad(pr.w));
+                *pp = make_float4(acc[a][0] * ActMath<TM>::gelu_erf_g(pr.x), acc[a][1] * ActMath<TM>::gelu_erf_g(pr.y),
+                                  acc[a][2] * ActMath<TM>::gelu_erf_g(pr.z), acc[a][3] * ActMath<TM>::gelu_erf_g(pr.w));
             }
         }
         __syncthreads();

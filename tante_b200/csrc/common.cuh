@@ -102,6 +102,42 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// bf16-mode variants of the activations and their derivatives (approximate transcendental units; the errors are far
+// below bf16 resolution).  Selected by the activation element type: float keeps the accurate versions.
+__device__ __forceinline__ float tanh_approx_f(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast_f(float x) {
+    const float k = 0.79788456080286535588f;
+    return 0.5f * x * (1.0f + tanh_approx_f(k * fmaf(0.044715f * x, x * x, x)));
+}
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+    const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752440f), 0.5f);
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return fmaf(x, pdf, cdf);
+}
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+    const float k = 0.79788456080286535588f;
+    const float x2 = x * x;
+    const float t = tanh_approx_f(k * fmaf(0.044715f * x, x2, x));
+    const float du = k * fmaf(3.0f * 0.044715f, x2, 1.0f);
+    return fmaf(0.5f * x * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+}
+template <typename T> struct ActMath {     // accurate (exact fp32 mode)
+    static __device__ __forceinline__ float gelu_erf_f(float x) { return gelu_erf(x); }
+    static __device__ __forceinline__ float gelu_tanh_f(float x) { return gelu_tanh(x); }
+    static __device__ __forceinline__ float gelu_erf_g(float x) { return gelu_erf_grad(x); }
+    static __device__ __forceinline__ float gelu_tanh_g(float x) { return gelu_tanh_grad(x); }
+};
+template <> struct ActMath<__nv_bfloat16> {
+    static __device__ __forceinline__ float gelu_erf_f(float x) { return gelu_erf_fast(x); }
+    static __device__ __forceinline__ float gelu_tanh_f(float x) { return gelu_tanh_fast_f(x); }
+    static __device__ __forceinline__ float gelu_erf_g(float x) { return gelu_erf_grad_fast(x); }
+    static __device__ __forceinline__ float gelu_tanh_g(float x) { return gelu_tanh_grad_fast(x); }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const TIn* __restr
 // (outer, pos, col) lives at (outer*S + pos)*IC + col, IC = inner_sz*C contiguous floats.
 // One CTA = one `outer` x 64 columns; the S x 64 slab and both S x S matrices sit in shared memory.
 // ------------------------------------------------------------------------------------------------
+template <typename TM /* float: accurate erf; bf16: erf_fast, as every other tensor-mode kernel */>
 __global__ void __launch_bounds__(256) propagator_kernel(const float* xin, float* x, int S, long long IC,
                                                          const float* __restrict__ W1, const float* __restrict__ b1,
                                                          const float* __restrict__ W2, const float* __restrict__ b2) {
@@ -321,7 +322,8 @@ __global__ void __launch_bounds__(256) propagator_kernel(const float* xin, float
                 const int p = jt * 4 + a;
                 if (pass == 0) {
                     *reinterpret_cast<float4*>(sh + p * 128 + cg * 4) =
-                        make_float4(gelu_erf(acc[a][0]), gelu_erf(acc[a][1]), gelu_erf(acc[a][2]), gelu_erf(acc[a][3]));
+                        make_float4(ActMath<TM>::gelu_erf_f(acc[a][0]), ActMath<TM>::gelu_erf_f(acc[a][1]),
+                                    ActMath<TM>::gelu_erf_f(acc[a][2]), ActMath<TM>::gelu_erf_f(acc[a][3]));
                 } else if (p < S && cg * 4 < ncol) {
                     const float4 x4 = *reinterpret_cast<const float4*>(sv + p * 128 + cg * 4);
                     *reinterpret_cast<float4*>(base + (size_t)p * IC + cg * 4) =

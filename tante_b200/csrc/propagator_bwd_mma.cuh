@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(128) propagator_bwd_mma_kernel(const float* __
                 *reinterpret_cast<uint32_t*>(sH + slab_off(j0, chunk) + t * 4) = pack_bf16x2(gelu_erf_fast(p0), gelu_erf_fast(p1));
                 *reinterpret_cast<uint32_t*>(sH + slab_off(j1, chunk) + t * 4) = pack_bf16x2(gelu_erf_fast(p2), gelu_erf_fast(p3));
                 *reinterpret_cast<uint32_t*>(sP + slab_off(j0, chunk) + t * 4) =
-                    pack_bf16x2(acch[nb][0] * gelu_erf_grad(p0), acch[nb][1] * gelu_erf_grad(p1));
+                    pack_bf16x2(acch[nb][0] * gelu_erf_grad_fast(p0), acch[nb][1] * gelu_erf_grad_fast(p1));
                 *reinterpret_cast<uint32_t*>(sP + slab_off(j1, chunk) + t * 4) =
-                    pack_bf16x2(acch[nb][2] * gelu_erf_grad(p2), acch[nb][3] * gelu_erf_grad(p3));
+                    pack_bf16x2(acch[nb][2] * gelu_erf_grad_fast(p2), acch[nb][3] * gelu_erf_grad_fast(p3));
             }
         }
         __syncwarp();       // dpre columns of a warp are consumed by the same warp below

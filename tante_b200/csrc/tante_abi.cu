@@ -20,6 +20,7 @@
 #include "attention_mma.cuh"
 #include "propagator_mma.cuh"
 #include "propagator_bwd_mma.cuh"
+#include "propagator_small.cuh"
 #include "head_mma.cuh"
 #include "kernels_simt.cuh"
 #include "pack.cuh"
@@ -465,7 +466,19 @@ void launch_propagator(tante_handle_s* h, const float* xin, float* x, int B, int
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
-    if (h->cfg.precision == TANTE_PREC_BF16 && S > 8) {    // tiny axes (T = 4) stay on the FFMA kernel
+    if (S <= 4 && (IC & 3) == 0) {      // short axes (T = 4): per-column register mat-vecs, one pass over the latent
+        const long long total = outer * (IC / 4);
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 16LL * h->num_sms);
+        const bool fast = h->cfg.precision == TANTE_PREC_BF16;
+#define PSMALL(TM, SM) propagator_small_kernel<TM, SM><<<grid, 256, 0, st>>>(xin, x, S, IC, outer, AF(h, op.prop[axis][0]), \
+            AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]))
+        if (fast) PSMALL(__nv_bfloat16, 4); else PSMALL(float, 4);
+#undef PSMALL
+        CK(cudaGetLastError());
+        h->launches++;
+        return;
+    }
+    if (h->cfg.precision == TANTE_PREC_BF16 && S > 8) {
         cudaError_t e = cudaSuccess;
         if (launch_propagator_mma(xin, x, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]),
                                   AF(h, op.prop[axis][3]), st, &e)) {
@@ -479,7 +492,9 @@ void launch_propagator(tante_handle_s* h, const float* xin, float* x, int B, int
     dim3 grid((unsigned)outer, (unsigned)((IC + 127) / 128));
     REQUIRE((IC + 127) / 128 <= 65535, "latent too large for the propagator grid");
     const int threads = 32 * std::min(8, S4 / 4);
-    propagator_kernel<<<grid, threads, smem, st>>>(xin, x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+    if (h->cfg.precision == TANTE_PREC_BF16) propagator_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(xin, x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                               AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]));
+    else propagator_kernel<float><<<grid, threads, smem, st>>>(xin, x, S, IC, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
                                                AF(h, op.prop[axis][2]), AF(h, op.prop[axis][3]));
     CK(cudaGetLastError());
     h->launches++;
@@ -797,6 +812,19 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
     if (axis == 0) { S = Hp; IC = (long long)Wp * C; outer = (long long)B * T; }
     else if (axis == 1) { S = Wp; IC = C; outer = (long long)B * T * Hp; }
     else { S = T; IC = (long long)L * C; outer = B; }
+    if (S <= 4 && (IC & 3) == 0) {
+        const long long total = outer * (IC / 4);
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 2LL * h->num_sms);
+        const bool fast = h->cfg.precision == TANTE_PREC_BF16;
+#define PSMALLB(TM, SM) propagator_small_bwd_kernel<TM, SM><<<grid, 256, 0, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), \
+            AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),                \
+            GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]))
+        if (fast) PSMALLB(__nv_bfloat16, 4); else PSMALLB(float, 4);
+#undef PSMALLB
+        CK(cudaGetLastError());
+        h->launches++;
+        return;
+    }
     if (h->cfg.precision == TANTE_PREC_BF16) {
         cudaError_t e = cudaSuccess;
         if (launch_propagator_bwd_mma(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
@@ -813,9 +841,14 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
     const size_t smem = (size_t)(4 * (kPropBwdSlab + 4 * S4) + 3 * S4 * S4 + S4) * sizeof(float);
     const long long nslab = outer * ((IC + CW - 1) / CW);
     const unsigned grid = (unsigned)std::min<long long>(nslab, 2LL * h->num_sms);
-    propagator_bwd_kernel<<<grid, 256, smem, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
-                                                 AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
-                                                 GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));
+    if (h->cfg.precision == TANTE_PREC_BF16)
+        propagator_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                                                     AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
+                                                                     GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));
+    else
+        propagator_bwd_kernel<float><<<grid, 256, smem, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                                             AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
+                                                             GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));
     CK(cudaGetLastError());
     h->launches++;
 }
@@ -1237,14 +1270,16 @@ void set_smem_attrs() {
     static bool done = false;
     if (done) return;
     const int big = 160 * 1024;
-    CK(cudaFuncSetAttribute(propagator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(propagator_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(propagator_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 #define HEADATTR(TA, KO) CK(cudaFuncSetAttribute(taylor_head_kernel<TA, 8, KO>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
     HEADATTR(float, 1); HEADATTR(float, 2); HEADATTR(float, 3); HEADATTR(float, 4);
     HEADATTR(__nv_bfloat16, 1); HEADATTR(__nv_bfloat16, 2); HEADATTR(__nv_bfloat16, 3); HEADATTR(__nv_bfloat16, 4);
 #undef HEADATTR
-    CK(cudaFuncSetAttribute(propagator_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(propagator_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(propagator_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     CK((cudaFuncSetAttribute(head_gather_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));
     CK((cudaFuncSetAttribute(head_gather_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));
     CK((cudaFuncSetAttribute(head_gather_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)));

@@ -300,6 +300,14 @@ class _TanteStep(torch.autograd.Function):
         _abi.check(eng.lib.tante_backward(eng.handle, ctx.slot, x.data_ptr(), g_frames.data_ptr(), int(g_frames.shape[1]),
                                           g_rt_ptr, None if g_in is None else g_in.data_ptr(), flat.data_ptr(), stream))
         ctx.guard.release()
+        # Fast path: every `p.grad` already is a view into ONE flat buffer laid out like the library's gradient
+        # (tante_b200.trainer.GradBucket): accumulate with a single add instead of one AccumulateGrad launch per
+        # parameter and model call (142 x 4 tiny kernels per BPTT step at tante.yaml).
+        if all(ctx.needs_input_grad[4:]):
+            acc = model._flat_grad_view(eng)
+            if acc is not None:
+                acc.add_(flat)
+                return (None, g_in, None, None, *([None] * len(eng.names)))
         grads = []
         for (name, shape), off in zip(ctx.model._param_shapes(eng), eng.grad_offsets):
             n = 1
@@ -404,6 +412,29 @@ class TANTE(nn.Module):
             self._engines[key] = eng
         eng.sync_params(self, torch.cuda.current_stream(device).cuda_stream)
         return eng
+
+    def grad_layout(self, device):
+        """(parameter names, element offsets, total elements) of the library's flat gradient on `device`."""
+        eng = self._engine(torch.device(device))
+        return list(eng.names), list(eng.grad_offsets), int(eng.grad_numel)
+
+    def _flat_grad_view(self, eng: _Engine):
+        """The flat fp32 tensor all `p.grad` are views of, if they are laid out like the library's gradient
+        (same storage, element offset = base + grad_offsets[i]); else None."""
+        params = dict(self.named_parameters())
+        g0 = params[eng.names[0]].grad
+        if g0 is None or g0.dtype != torch.float32 or not g0.is_contiguous():
+            return None
+        base = g0.data_ptr() - 4 * eng.grad_offsets[0]
+        for n, off in zip(eng.names, eng.grad_offsets):
+            g = params[n].grad
+            if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != base + 4 * off:
+                return None
+        st = g0.untyped_storage()
+        first = g0.storage_offset() - eng.grad_offsets[0]
+        if first < 0 or (first + eng.grad_numel) * 4 > st.nbytes():
+            return None
+        return torch.as_strided(g0, (eng.grad_numel,), (1,), first)
 
     def _param_shapes(self, eng: _Engine):
         params = dict(self.named_parameters())

@@ -65,8 +65,17 @@ class GradBucket:
 
     def __init__(self, model: torch.nn.Module):
         self.params = [p for p in model.parameters() if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
+        named = dict(model.named_parameters())
+        if hasattr(model, "grad_layout") and dev.type == "cuda" and all(p.requires_grad for p in named.values()):
+            # the library's own flat layout: the backward then accumulates with ONE add per model call
+            names, offsets, n = model.grad_layout(dev)
+            self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+            for name, off in zip(names, offsets):
+                p = named[name]
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+            return
+        n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for p in self.params:

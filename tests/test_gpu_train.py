@@ -269,3 +269,30 @@ def test_grad_accumulation_and_slot_reuse():
         model(x).square().mean().backward()
     eng = next(iter(model._engines.values()))
     assert eng.n_slots <= 2
+
+
+def test_grad_bucket_direct_accumulation_matches_autograd_path():
+    """GradBucket lays `p.grad` out like the library's flat gradient, so the backward accumulates with one add per
+    model call and returns no per-parameter gradients: the result must equal the plain autograd path, also when the
+    same parameters are used by several chained calls (BPTT) and after the bucket is zeroed."""
+    from gpu_util import make_model
+    from tante_b200.trainer import GradBucket, rollout_train
+    cfg = O.OracleConfig(n_fields=3, H=32, W=48, taylor_order=1, attn_axes="THW", deg=True)
+    sd = O.make_state_dict(cfg, 411, 0.0)
+    x = O.make_input(cfg, 2, 412).cuda()
+    ref = make_model(cfg, sd, "fp32").train()
+    y, _ = rollout_train(ref, x, 3)
+    y.square().mean().backward()
+    want = {n: p.grad.clone() for n, p in ref.named_parameters()}
+
+    model = make_model(cfg, sd, "fp32").train()
+    bucket = GradBucket(model)
+    eng = next(iter(model._engines.values()))
+    assert model._flat_grad_view(eng) is not None, "GradBucket layout is not the library's flat layout"
+    for rep in range(2):
+        bucket.zero()
+        y, _ = rollout_train(model, x, 3)
+        y.square().mean().backward()
+        for n, p in model.named_parameters():
+            assert p.grad.data_ptr() >= bucket.flat.data_ptr(), n
+            assert rel_l2(p.grad.cpu().numpy(), want[n].cpu().numpy()) < 1e-5, (rep, n)

@@ -177,10 +177,19 @@ struct EpiParams {
     const float* ln_gamma = nullptr;
     const float* ln_beta = nullptr;
     void* ln_out = nullptr;         // bf16 [M, N]
+    // optional device-side row count (rollout encoder cache): effective M = min(M, *m_dev * m_rows)
+    const int* m_dev = nullptr;
+    int m_rows = 0;
     // EPI_MULGRAD_*: saved pre-activation (post-activation for ReLU), bf16 [M, ld_pre]
     const void* mul_pre = nullptr;
     int ld_pre = 0;
 };
+
+// encoder tail (t_encode FiLM + s_emb + t_emb, tante.py:132-141) with explicit roundings: the GEMM epilogues
+// (EPI_EMBED, both GEMM kernels) and the rollout's embed_cached_kernel must agree bit for bit
+__device__ __forceinline__ float embed_value(float v, float sc, float sh, float se, float te) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(v, __fmaf_rn(v, sc, sh)), se), te);
+}
 
 template <int EPI>
 __device__ __forceinline__ float apply_epilogue(float acc, int m, int n, const EpiParams& p) {
@@ -192,9 +201,8 @@ __device__ __forceinline__ float apply_epilogue(float acc, int m, int n, const E
     if (EPI == EPI_EMBED) {
         const int hw = m % p.L;
         const int t = (m / p.L) % p.T;
-        v = v + (v * p.film[(size_t)(t * 2 + 0) * p.ldr + n] + p.film[(size_t)(t * 2 + 1) * p.ldr + n]);
-        v = v + p.s_emb[(size_t)hw * p.ldr + n];
-        v = v + p.t_emb[(size_t)t * p.ldr + n];
+        v = embed_value(v, p.film[(size_t)(t * 2 + 0) * p.ldr + n], p.film[(size_t)(t * 2 + 1) * p.ldr + n],
+                        p.s_emb[(size_t)hw * p.ldr + n], p.t_emb[(size_t)t * p.ldr + n]);
     }
     return v;
 }

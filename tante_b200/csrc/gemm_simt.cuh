@@ -16,9 +16,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Ws[2][BK][BN + 4];
 
+    if (ep.m_dev) M = min(M, *ep.m_dev * ep.m_rows);      // device-side row count (rollout encoder cache)
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM;
     const int n0 = blockIdx.x * BN;
+    if (m0 >= M) return;
     const int ty = tid / 16, tx = tid % 16;
 
     // global->smem mapping: each thread moves float4s along K.

@@ -87,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* rbar = tmem_empty + 2;          // [8 warps][2] residual-chunk barriers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * kTcEpiWarps);
 
+    if (ep.m_dev) M = min(M, *ep.m_dev * ep.m_rows);      // device-side row count (rollout encoder cache)
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int n_slices = N / BN;
     const int slice = blockIdx.x % n_slices;
@@ -297,10 +298,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const float4 sh = *reinterpret_cast<const float4*>(ep.film + (size_t)(tt * 2 + 1) * ep.ldr + n);
                                 const float4 se = *reinterpret_cast<const float4*>(ep.s_emb + (size_t)hw * ep.ldr + n);
                                 const float4 te = *reinterpret_cast<const float4*>(ep.t_emb + (size_t)tt * ep.ldr + n);
-                                o.x = o.x + (o.x * sc.x + sh.x) + se.x + te.x;
-                                o.y = o.y + (o.y * sc.y + sh.y) + se.y + te.y;
-                                o.z = o.z + (o.z * sc.z + sh.z) + se.z + te.z;
-                                o.w = o.w + (o.w * sc.w + sh.w) + se.w + te.w;
+                                o.x = embed_value(o.x, sc.x, sh.x, se.x, te.x);
+                                o.y = embed_value(o.y, sc.y, sh.y, se.y, te.y);
+                                o.z = embed_value(o.z, sc.z, sh.z, se.z, te.z);
+                                o.w = embed_value(o.w, sc.w, sh.w, se.w, te.w);
                             }
                         } else {
                             o.x = act_rt(epi, o.x); o.y = act_rt(epi, o.y); o.z = act_rt(epi, o.z); o.w = act_rt(epi, o.w);

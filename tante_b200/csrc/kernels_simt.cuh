@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(128) patch_embed_conv1_kernel(const float* __r
                                                                 const int* __restrict__ fcount, PatchGeom g,
                                                                 const float* __restrict__ w1p,  // [C1][k0*k0*D]
                                                                 const float* __restrict__ b1, int WC,
-                                                                TOut* __restrict__ out) {
+                                                                TOut* __restrict__ out,
+                                                                const int* __restrict__ enc_list = nullptr,
+                                                                const int* __restrict__ enc_count = nullptr) {
     constexpr int C1 = 64;
     extern __shared__ __align__(16) float smem[];
     const int P = g.k0 * g.k1 * g.k2;
@@ -59,8 +61,15 @@ __global__ void __launch_bounds__(128) patch_embed_conv1_kernel(const float* __r
     const int bt = blockIdx.x / g.Hp, hp = blockIdx.x % g.Hp;
     const int wp0 = blockIdx.y * WC;
     const int nwp = min(WC, g.Wp - wp0);
-    const int b = bt / g.T, t = bt % g.T;
-    const int slot = fcount ? (fcount[b] + t) % g.T : t;
+    // `enc_list` (rollout with the encoder cache): CTA row bt encodes the frame in ring slot enc_list[bt] and writes
+    // compact rows; frames past *enc_count are not encoded at all.
+    int b = bt / g.T, t = bt % g.T;
+    int slot = fcount ? (fcount[b] + t) % g.T : t;
+    if (enc_list) {
+        if (bt >= *enc_count) return;
+        b = enc_list[bt] / g.T;
+        slot = enc_list[bt] % g.T;
+    }
     const float* xin = x + ((size_t)(b * g.T + slot) * g.D) * g.H * g.W;
 
     for (int i = threadIdx.x; i < C1 * K1; i += blockDim.x) s_w[(i % K1) * C1 + (i / K1)] = w1p[i];
@@ -431,6 +440,46 @@ __global__ void __launch_bounds__(256) film_apply_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// Encoder tail on cached encoder outputs (rollout): x[b, t] = embed(enc[b, slot(t)], t) with
+// embed = t_encode FiLM + s_emb + t_emb (tante.py:132-141).  The encoder output of a frame does not depend on its
+// position in the window, so a rollout step only encodes the frames that entered the window (`cnew`, compact, in
+// enc_list order) and takes the others from `cache` (per ring slot); new outputs are copied into the cache here.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_cached_kernel(const float* __restrict__ cnew, float* __restrict__ cache,
+                                                           const int* __restrict__ enc_map, const int* __restrict__ fcount,
+                                                           const float* __restrict__ film, const float* __restrict__ s_emb,
+                                                           const float* __restrict__ t_emb, float* __restrict__ x, int B, int T,
+                                                           int L, int C) {
+    const int c4n = C / 4;
+    const long long total = (long long)B * T * L * c4n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        long long tok = i / c4n;
+        const int l = (int)(tok % L); tok /= L;
+        const int t = (int)(tok % T);
+        const int b = (int)(tok / T);
+        const int slot = (fcount[b] + t) % T;
+        const int e = enc_map[b * T + slot];
+        float* cp = cache + ((size_t)(b * T + slot) * L + l) * C + c;
+        float4 v;
+        if (e >= 0) {
+            v = *reinterpret_cast<const float4*>(cnew + ((size_t)e * L + l) * C + c);
+            *reinterpret_cast<float4*>(cp) = v;
+        } else {
+            v = *reinterpret_cast<const float4*>(cp);
+        }
+        const float4 sc = *reinterpret_cast<const float4*>(film + (size_t)(t * 2 + 0) * C + c);
+        const float4 sh = *reinterpret_cast<const float4*>(film + (size_t)(t * 2 + 1) * C + c);
+        const float4 se = *reinterpret_cast<const float4*>(s_emb + (size_t)l * C + c);
+        const float4 te = *reinterpret_cast<const float4*>(t_emb + (size_t)t * C + c);
+        float4 o;
+        o.x = embed_value(v.x, sc.x, sh.x, se.x, te.x); o.y = embed_value(v.y, sc.y, sh.y, se.y, te.y);
+        o.z = embed_value(v.z, sc.z, sh.z, se.z, te.z); o.w = embed_value(v.w, sc.w, sh.w, se.w, te.w);
+        *reinterpret_cast<float4*>(x + ((size_t)(b * T + t) * L + l) * C + c) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Step-size selection (reference tante.py:156-163): R_t = mean_k rt_k, n = floor(R_t[gov]) with
 // gov = b (per-sample) or 0 (reference batch semantics).  Also the rollout bookkeeping.
 // ------------------------------------------------------------------------------------------------
@@ -447,6 +496,11 @@ struct RolloutState {
     int* n_cur;     // [B] frames to emit this step (0 = sample finished)
     int* remaining; // [1] samples still running (written at the end of each step)
     int* iter;      // [1] model calls issued in this rollout
+    // encoder cache: frames whose ring slot changed since the previous model call (all B*T before the first one)
+    int* enc_count; // [1] number of entries of enc_list (null: no cache, every frame is encoded every call)
+    int* enc_list;  // [B*T] b*T + slot, compact
+    int* enc_map;   // [B*T] ring slot -> index into enc_list, or -1 (encoder output is in the cache)
+    int T;
     const RolloutPtrs* ptrs;
     int n_roll;
     int max_steps;
@@ -496,20 +550,33 @@ __global__ void select_step_kernel(const float* __restrict__ rt /* [K][Bstride] 
 __global__ void advance_state_kernel(RolloutState rs, int B, cudaGraphConditionalHandle cond, int use_cond) {
     // single CTA; after the head kernel of a step.  When the step runs as the body of a CUDA-graph WHILE
     // node, the loop condition (any trajectory still short of n_roll frames) is set here, on the device.
-    __shared__ int rem;
-    if (threadIdx.x == 0) rem = 0;
+    __shared__ int rem, cnt;
+    if (threadIdx.x == 0) { rem = 0; cnt = 0; }
+    if (rs.enc_count)
+        for (int i = threadIdx.x; i < B * rs.T; i += blockDim.x) rs.enc_map[i] = -1;
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const int n = rs.n_cur[b];
         if (n > 0) {
             rs.cum[b] += n;
-            rs.fcount[b] += n;
+            const int fc = rs.fcount[b] + n;
+            rs.fcount[b] = fc;
             rs.steps[b] += 1;
+            if (rs.enc_count) {      // the min(n, T) newest frames of the window sit in slots (fc - 1 - j) % T
+                const int m = min(n, rs.T);
+                const int e0 = atomicAdd(&cnt, m);
+                for (int j = 0; j < m; ++j) {
+                    const int slot = (fc - 1 - j) % rs.T;
+                    rs.enc_list[e0 + j] = b * rs.T + slot;
+                    rs.enc_map[b * rs.T + slot] = e0 + j;
+                }
+            }
         }
         if (rs.cum[b] < rs.n_roll) atomicAdd(&rem, 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (rs.enc_count) *rs.enc_count = cnt;
         *rs.remaining = rem;
         const int it = *rs.iter + 1;
         *rs.iter = it;
@@ -519,8 +586,12 @@ __global__ void advance_state_kernel(RolloutState rs, int B, cudaGraphConditiona
 
 __global__ void init_state_kernel(RolloutState rs, int B, int T) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) { rs.cum[b] = 0; rs.fcount[b] = T; rs.steps[b] = 0; rs.n_cur[b] = 0; }
-    if (b == 0) { *rs.remaining = B; *rs.iter = 0; }
+    if (b < B) {
+        rs.cum[b] = 0; rs.fcount[b] = T; rs.steps[b] = 0; rs.n_cur[b] = 0;
+        if (rs.enc_count)
+            for (int t = 0; t < T; ++t) { rs.enc_list[b * T + t] = b * T + t; rs.enc_map[b * T + t] = b * T + t; }
+    }
+    if (b == 0) { *rs.remaining = B; *rs.iter = 0; if (rs.enc_count) *rs.enc_count = B * T; }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -126,6 +126,9 @@ struct tante_handle_s {
     int64_t arena_elems = 0;
     DevBuf arena, arena_bf16, descs;
     bool packed = false;
+    DevBuf enc_cache;                   // rollout: encoder output per ring slot, fp32 [B*T*L][C]
+    DevBuf enc_state;                   // rollout: [8] count, [B*T] list, [B*T] map
+    bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
     bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
 
     // workspace
@@ -379,6 +382,12 @@ RolloutState make_state(tante_handle_s* h, int B, int n_roll) {
     rs.iter = s + 4 * mb + 1;
     rs.ptrs = reinterpret_cast<const RolloutPtrs*>(s + 4 * mb + 8);   // 32-byte aligned slot after the counters
     rs.n_roll = n_roll; rs.max_steps = n_roll;
+    rs.T = h->T;
+    rs.enc_count = nullptr; rs.enc_list = nullptr; rs.enc_map = nullptr;
+    if (h->enc_cache.p && h->use_enc_cache) {
+        int* e = reinterpret_cast<int*>(h->enc_state.p);
+        rs.enc_count = e; rs.enc_list = e + 8; rs.enc_map = e + 8 + (size_t)mb * h->T;
+    }
     return rs;
 }
 
@@ -564,17 +573,36 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         const size_t smem = (size_t)(((g.D * P * (P * WC + 1) + 3) & ~3) + C1 * K1 + C1) * sizeof(float) +
                             (size_t)WC * g.R1 * C1 * sizeof(TA);
         dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
+        const bool cached = io.rollout && rs.enc_count != nullptr;
         patch_embed_conv1_kernel<TA><<<grid, 128, smem, st>>>(io.input, io.fcount, g, AF(h, h->enc_w[0]),
-                                                              AF(h, h->enc_b[0]), WC, a1);
+                                                              AF(h, h->enc_b[0]), WC, a1, cached ? rs.enc_list : nullptr,
+                                                              cached ? rs.enc_count : nullptr);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
-        gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, false, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
         EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
-        e3.film = AF(h, h->film_t_off); e3.s_emb = AF(h, h->s_emb); e3.t_emb = AF(h, h->t_emb);
-        e3.T = T; e3.L = L; e3.ldr = C;
-        // the embed epilogue writes the fp32 residual stream directly
-        gemm<TA>(h, EPI_EMBED, a2, g.k2 * g.k2 * C2, h->enc_w[2], x, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
+        if (cached) {
+            // Rollout: only the frames that entered the window are encoded (their count lives on the device: the
+            // GEMMs clip M to it); everything else comes out of the per-slot cache.  The encoder output of a frame
+            // does not depend on its window position -- FiLM(t) and the embeddings are applied afterwards.
+            e2.m_dev = rs.enc_count; e2.m_rows = L * g.R2;
+            e3.m_dev = rs.enc_count; e3.m_rows = L;
+            float* cnew = reinterpret_cast<float*>(h->qkv.p);       // scratch: free until the first QKV GEMM
+            gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, false, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
+            gemm<TA>(h, EPI_BIAS, a2, g.k2 * g.k2 * C2, h->enc_w[2], cnew, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
+            const long long tot4 = (long long)tokens * (C / 4);
+            embed_cached_kernel<<<(unsigned)std::min<long long>((tot4 + 255) / 256, 32LL * h->num_sms), 256, 0, st>>>(
+                cnew, reinterpret_cast<float*>(h->enc_cache.p), rs.enc_map, io.fcount, AF(h, h->film_t_off), AF(h, h->s_emb),
+                AF(h, h->t_emb), x, B, T, L, C);
+            CK(cudaGetLastError());
+            h->launches++;
+        } else {
+            gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, false, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
+            e3.film = AF(h, h->film_t_off); e3.s_emb = AF(h, h->s_emb); e3.t_emb = AF(h, h->t_emb);
+            e3.T = T; e3.L = L; e3.ldr = C;
+            // the embed epilogue writes the fp32 residual stream directly
+            gemm<TA>(h, EPI_EMBED, a2, g.k2 * g.k2 * C2, h->enc_w[2], x, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
+        }
     }
     if (h->debug) CK(cudaMemcpyAsync(h->dbg_in.p, x, (size_t)tokens * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
@@ -1381,6 +1409,7 @@ int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out) {
         h->device = device;
         build_plan(h.get());
         if (const char* m = getenv("TANTE_ROLLOUT_MODE")) h->rollout_mode = std::max(0, std::min(2, atoi(m)));
+        if (const char* m = getenv("TANTE_ENC_CACHE")) h->use_enc_cache = atoi(m) != 0;
         int sms = 0;   // stays at the B200 default when no device is visible (CPU-side plan checks)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
         else (void)cudaGetLastError();
@@ -1394,7 +1423,7 @@ int tante_destroy(tante_handle_t h) {
         cudaSetDevice(h->device);
         DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
                           &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
-                          &h->state, &h->dbg_in};
+                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
@@ -1541,6 +1570,10 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         dev_alloc(h, h->filmbuf, (size_t)max_batch * 2 * C * 4);
         dev_alloc(h, h->ring, (size_t)max_batch * h->T * h->D * h->cfg.H * h->cfg.W * 4);
         dev_alloc(h, h->state, ((size_t)4 * max_batch + 64) * 4);
+        if (max_roll > 0 && h->use_enc_cache) {
+            dev_alloc(h, h->enc_cache, tokens * C * 4);
+            dev_alloc(h, h->enc_state, ((size_t)2 * max_batch * h->T + 8) * 4);
+        }
         if (h->debug) dev_alloc(h, h->dbg_in, tokens * C * 4);
         if (!h->h_flag) {
             CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flag), 64));

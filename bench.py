@@ -258,17 +258,28 @@ def run_b200(args):
         model_calls = int(steps.max().item())
 
         # ---- timed region 2: end to end through the public API with host buffers ----
-        for _ in range(2):
-            d = host_in.to(dev, non_blocking=True)
-            y, *_ = model.rollout(d, n_roll, per_sample=True, sync=False)
-            host_out.copy_(y, non_blocking=True)
+        # Every step copies its pinned HOST window to the device and the whole predicted history back;
+        # tante_b200.pipeline.HostPrefetcher (the repo's staging API) runs those copies on dedicated streams, so window
+        # i+1 travels in and history i-1 travels out while rollout i is computed.  Two host output buffers alternate.
+        from tante_b200.pipeline import HostPrefetcher
+        pf = HostPrefetcher(dev)
+        host_out2 = torch.empty_like(host_out).pin_memory()
+
+        def e2e_run(n):
+            pf.put(host_in)
+            for i in range(n):
+                (d,) = pf.get()
+                if i + 1 < n:
+                    pf.put(host_in)
+                y, *_ = model.rollout(d, n_roll, per_sample=True, sync=False)
+                pf.done()
+                pf.download(y, host_out if i % 2 == 0 else host_out2)
+            pf.join()
+        e2e_run(2)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for _ in range(K_):
-            d = host_in.to(dev, non_blocking=True)
-            y, *_ = model.rollout(d, n_roll, per_sample=True, sync=False)
-            host_out.copy_(y, non_blocking=True)
+        e2e_run(K_)
         e3.record()
         barrier()
         ms_e2e = max_over_ranks(e2.elapsed_time(e3))
@@ -503,18 +514,26 @@ def run_b200_train(args):
     final_loss = float(loss)
 
     # ---- timed region 2: end to end with HOST batches (H2D of inputs+targets, D2H of the loss every step) ----
-    def e2e_step():
-        x = host_x.to(dev, non_blocking=True)
-        y = host_y.to(dev, non_blocking=True)
-        ls = train_step(model, opt, x, y, n_out, bucket)
-        host_loss.copy_(ls.reshape(1), non_blocking=True)
-    for _ in range(2):
-        e2e_step()
+    # Every step copies its pinned HOST batch to the device and its loss back; tante_b200.pipeline.HostPrefetcher (the
+    # repo's staging API) runs those copies on dedicated streams, so batch i+1 travels while batch i is computed.
+    from tante_b200.pipeline import HostPrefetcher
+    pf = HostPrefetcher(dev)
+
+    def e2e_run(n):
+        pf.put(host_x, host_y)
+        for i in range(n):
+            x, y = pf.get()
+            if i + 1 < n:
+                pf.put(host_x, host_y)
+            ls = train_step(model, opt, x, y, n_out, bucket)
+            pf.done()
+            pf.download(ls.reshape(1), host_loss)
+        pf.join()
+    e2e_run(2)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for _ in range(K_):
-        e2e_step()
+    e2e_run(K_)
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))

@@ -588,8 +588,11 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             e2.m_dev = rs.enc_count; e2.m_rows = L * g.R2;
             e3.m_dev = rs.enc_count; e3.m_rows = L;
             float* cnew = reinterpret_cast<float*>(h->qkv.p);       // scratch: free until the first QKV GEMM
+            const bool prof = h->prof_on;
+            h->prof_on = false;      // the row count of these two GEMMs lives on the device: keep them out of the FLOP tally
             gemm<TA>(h, EPI_BIAS_GELU_ERF, a1, g.k1 * g.k1 * C1, h->enc_w[1], a2, C2, false, tokens * g.R2, C2, g.k1 * g.k1 * C1, e2, st);
             gemm<TA>(h, EPI_BIAS, a2, g.k2 * g.k2 * C2, h->enc_w[2], cnew, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
+            h->prof_on = prof;
             const long long tot4 = (long long)tokens * (C / 4);
             embed_cached_kernel<<<(unsigned)std::min<long long>((tot4 + 255) / 256, 32LL * h->num_sms), 256, 0, st>>>(
                 cnew, reinterpret_cast<float*>(h->enc_cache.p), rs.enc_map, io.fcount, AF(h, h->film_t_off), AF(h, h->s_emb),

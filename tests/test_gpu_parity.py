@@ -225,3 +225,30 @@ def test_autocast_selects_bf16_engine():
     assert len(model._engines) == 2
     assert not torch.equal(y32, y16)
     assert float((y32 - y16).norm() / y32.norm()) < BF16_FIELD_TOL
+
+
+def test_host_prefetcher_pipeline_matches_direct_calls():
+    """tante_b200.pipeline.HostPrefetcher (copy streams + two-slot device buffers) must not change results: a
+    pipelined sequence of rollouts over DIFFERENT pinned host windows equals the same rollouts done one by one."""
+    from gpu_util import make_model
+    from tante_b200.pipeline import HostPrefetcher
+    cfg = O.OracleConfig(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="THW", deg=False)
+    sd = O.make_state_dict(cfg, 9, rt_bias=1.3)
+    model = make_model(cfg, sd)
+    wins = [O.make_input(cfg, 2, 20 + i).pin_memory() for i in range(5)]
+    with torch.inference_mode():
+        want = [model.rollout(w.cuda(), 5, per_sample=True)[0].cpu() for w in wins]
+        pf = HostPrefetcher(torch.device("cuda:0"))
+        outs = [torch.empty_like(want[0]).pin_memory() for _ in wins]
+        pf.put(wins[0])
+        for i in range(len(wins)):
+            (d,) = pf.get()
+            if i + 1 < len(wins):
+                pf.put(wins[i + 1])
+            y, *_ = model.rollout(d, 5, per_sample=True, sync=False)
+            pf.done()
+            pf.download(y, outs[i])
+        pf.join()
+        torch.cuda.synchronize()
+    for i in range(len(wins)):
+        assert torch.equal(outs[i], want[i]), i

@@ -165,6 +165,20 @@ TANTE_API int tante_bench_head(tante_handle_t h, const float* u, float* frames, 
  * launch count since enabling, and clears the counters. */
 TANTE_API int tante_profile(tante_handle_t h, int32_t enable);
 TANTE_API int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+/* Same tally split by roofline class (call BEFORE tante_profile_read, which resets it): cls 0 = GEMMs with a plain
+ * bf16 / activation epilogue (tensor-bound), 1 = GEMMs with an fp32 residual / LayerNorm / embedding epilogue
+ * (HBM-bound), 2 = weight-gradient GEMMs (HBM-bound).  bytes = algorithmic HBM bytes (operands + outputs once). */
+TANTE_API int tante_profile_read_class(tante_handle_t h, int32_t cls, double* ms, double* flops, double* bytes,
+                                       int64_t* launches);
+
+/* Training loss of the rollout drivers (reference trainer/metrics.py:53-80, MSE.eval(...).mean(), as called from
+ * trainer/trainer.py:188-190 and trainer/r_trainer.py:150-152) between the module's channels-first predictions
+ * y = f32[B,nf,D,H*W] and the channels-last targets ref = f32[B,n_ref,H*W,D], frames f0 .. f0+n_use-1 (n_use <= nf: the
+ * rollout drivers truncate an overshooting last call).  loss_sum (nullable, f32[1]) += sum of squared differences;
+ * grad_y (nullable, f32 like y) = scale * (*gout, or 1 when gout is null) * (y - ref), zero for frames >= n_use.
+ * No handle: a pure function of its arguments, launched on `stream`. */
+TANTE_API int tante_mse_cl(const float* y, const float* ref, int32_t B, int32_t nf, int32_t n_use, int32_t D, int64_t HW,
+                 int32_t n_ref, int32_t f0, float scale, const float* gout, float* loss_sum, float* grad_y, void* stream);
 
 /* Test hook: run one GEMM of the library stand-alone, C[M,N] = epi(A[M,K] * W[N,K]^T + bias).
  * use_tc = 1: tcgen05 bf16 kernel (A, W bf16; C bf16 when out_bf16 else f32);

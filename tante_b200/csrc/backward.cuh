@@ -43,6 +43,51 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(TA* __restrict__ g, const 
     Vec4<TA>::store(g + i * 4, d);
 }
 
+// ---- training loss of the rollout drivers (trainer/metrics.py:53-80: MSE.eval(...).mean()) -------------------------
+// sum over (b, j < n_use, d, pixel) of (y - ref)^2 between channels-FIRST predictions y (B, nf, D, HW) -- the module's
+// output layout -- and the channels-LAST targets ref (B, n_ref, HW, D), frames f0 .. f0+n_use-1; and/or its gradient
+// grad_y = scale * gout * (y - ref) (frames >= n_use get zero).  One pass; replaces the formatter permute, the cat over
+// model calls, sub, pow, the two means and their five autograd kernels.  thread = pixel, loop over the fields:
+// y accesses coalesce across the warp, a warp's ref accesses cover 32*D consecutive floats.
+__global__ void __launch_bounds__(256) mse_cf_cl_kernel(const float* __restrict__ y, const float* __restrict__ ref, int B, int nf,
+                                                        int n_use, int D, long long HW, int n_ref, int f0, float scale,
+                                                        const float* __restrict__ gout, float* __restrict__ loss_sum,
+                                                        float* __restrict__ grad_y) {
+    const long long total = (long long)B * nf * HW;
+    const float gs = grad_y ? scale * (gout ? *gout : 1.f) : 0.f;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i % HW;
+        const long long bj = i / HW;
+        const int j = (int)(bj % nf);
+        const long long b = bj / nf;
+        const float* yp = y + (size_t)bj * D * HW + p;
+        float* gp = grad_y ? grad_y + (size_t)bj * D * HW + p : nullptr;
+        if (j >= n_use) {
+            if (gp) for (int d = 0; d < D; ++d) gp[(size_t)d * HW] = 0.f;
+            continue;
+        }
+        const float* rp = ref + (((size_t)b * n_ref + f0 + j) * HW + p) * D;
+        for (int d = 0; d < D; ++d) {
+            const float df = yp[(size_t)d * HW] - rp[d];
+            acc = fmaf(df, df, acc);
+            if (gp) gp[(size_t)d * HW] = gs * df;
+        }
+    }
+    if (loss_sum) {
+        __shared__ float red[8];
+        acc = warp_sum(acc);
+        if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float v = red[threadIdx.x];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+            if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+        }
+    }
+}
+
 // fp32 -> TA copy (gradient stream -> GEMM operand)
 template <typename TA>
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4) {

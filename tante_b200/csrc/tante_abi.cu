@@ -155,6 +155,8 @@ struct tante_handle_s {
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     double prof_flops = 0;
+    struct ProfRec { int cls; double flops, bytes; };
+    std::vector<ProfRec> prof_rec;      // one per bracketed launch (same order as the event pairs)
     // ---- training ----
     int64_t enc_wT[3] = {0, 0, 0};
     int64_t enc_w1pad = 0;                     // [C1][64]: first conv weight zero-padded along K (im2col GEMM)
@@ -400,8 +402,11 @@ void gemm(tante_handle_s* h, int epi, const TA* A, int lda, int64_t w_off, void*
 
 struct ProfScope {
     tante_handle_s* h; cudaStream_t st; bool on;
-    ProfScope(tante_handle_s* h_, cudaStream_t st_, double flops) : h(h_), st(st_), on(h_->prof_on) {
+    // cls: 0 = GEMM with a plain (bf16 / activation) epilogue: tensor-bound; 1 = GEMM with an fp32 residual / LayerNorm /
+    // embedding epilogue: HBM-bound; 2 = weight-gradient GEMM: HBM-bound.  bytes = algorithmic HBM bytes of the launch.
+    ProfScope(tante_handle_s* h_, cudaStream_t st_, double flops, int cls = 0, double bytes = 0) : h(h_), st(st_), on(h_->prof_on) {
         if (!on) return;
+        h->prof_rec.push_back({cls, flops, bytes});
         if (h->prof_used + 2 > h->prof_ev.size()) {
             for (int i = 0; i < 2; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->prof_ev.push_back(e); }
         }
@@ -418,7 +423,8 @@ struct ProfScope {
 template <>
 void gemm<float>(tante_handle_s* h, int epi, const float* A, int lda, int64_t w_off, void* Cout, int ldc, bool, int M,
                  int N, int K, const EpiParams& ep, cudaStream_t st) {
-    ProfScope ps(h, st, 2.0 * M * N * K);
+    const bool res = epi == EPI_BIAS_RESID || epi == EPI_EMBED;
+    ProfScope ps(h, st, 2.0 * M * N * K, res ? 1 : 0, (double)M * (4.0 * K + 4.0 * N * (epi == EPI_BIAS_RESID ? 2 : 1)));
     CK(launch_gemm_simt(epi, A, lda, AF(h, w_off), K, reinterpret_cast<float*>(Cout), ldc, M, N, K, ep, st));
     h->launches++;
 }
@@ -426,7 +432,9 @@ void gemm<float>(tante_handle_s* h, int epi, const float* A, int lda, int64_t w_
 template <>
 void gemm<__nv_bfloat16>(tante_handle_s* h, int epi, const __nv_bfloat16* A, int lda, int64_t w_off, void* Cout, int ldc,
                          bool out_f32, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
-    ProfScope ps(h, st, 2.0 * M * N * K);
+    const bool res = epi == EPI_BIAS_RESID || epi == EPI_BIAS_RESID_LN;
+    const double out_b = out_f32 ? 4.0 * N * (res ? 2 : 1) + (epi == EPI_BIAS_RESID_LN ? 2.0 * N : 0.0) : 2.0 * N;
+    ProfScope ps(h, st, 2.0 * M * N * K, out_f32 ? 1 : 0, (double)M * (2.0 * K + out_b));
     CK(launch_gemm_tc(epi, A, lda, AH(h, w_off), K, Cout, ldc, out_f32 ? 0 : 1, M, N, K, ep, h->num_sms, st));
     h->launches++;
 }
@@ -735,7 +743,7 @@ template <typename TA>
 void wgrad(tante_handle_s* h, const TA* A, int lda, const TA* Bm, int ldb, float* out, long long M, int N, int K,
            cudaStream_t st, float* bias_out = nullptr) {
     {
-        ProfScope ps(h, st, 2.0 * (double)M * N * K);
+        ProfScope ps(h, st, 2.0 * (double)M * N * K, 2, (double)M * (N + K) * sizeof(TA));
         if constexpr (sizeof(TA) == 2) {
             if (wgrad_tc_supported(M, N, K, K, lda, ldb, K)) {
                 CK(launch_wgrad_tc(A, lda, Bm, ldb, out, K, M, N, K, K, h->num_sms, st, bias_out));
@@ -753,7 +761,7 @@ template <typename TA>
 void wgrad_pad(tante_handle_s* h, const TA* A, int lda, int N, const TA* Bm, int ldb, int Kb, float* out, int ldc, int Kc,
                long long M, cudaStream_t st, float* bias_out = nullptr) {
     {
-        ProfScope ps(h, st, 2.0 * (double)M * N * Kc);
+        ProfScope ps(h, st, 2.0 * (double)M * N * Kc, 2, (double)M * (N + Kb) * sizeof(TA));
         if constexpr (sizeof(TA) == 2) {
             if (wgrad_tc_supported(M, N, Kb, Kc, lda, ldb, ldc)) {
                 CK(launch_wgrad_tc(A, lda, Bm, ldb, out, ldc, M, N, Kb, Kc, h->num_sms, st, bias_out));
@@ -1845,6 +1853,24 @@ int tante_profile(tante_handle_t h, int32_t enable) {
         h->prof_on = enable != 0;
         h->prof_used = 0;
         h->prof_flops = 0;
+        h->prof_rec.clear();
+    });
+}
+
+int tante_profile_read_class(tante_handle_t h, int32_t cls, double* ms_out, double* flops, double* bytes, int64_t* launches) {
+    return guarded([&] {
+        REQUIRE(h && ms_out && flops && bytes && launches, "null argument");
+        CK(cudaSetDevice(h->device));
+        double ms = 0, fl = 0, by = 0;
+        int64_t n = 0;
+        for (size_t i = 0; i + 1 < h->prof_used && i / 2 < h->prof_rec.size(); i += 2) {
+            if (h->prof_rec[i / 2].cls != cls) continue;
+            CK(cudaEventSynchronize(h->prof_ev[i + 1]));
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+            ms += t; fl += h->prof_rec[i / 2].flops; by += h->prof_rec[i / 2].bytes; ++n;
+        }
+        *ms_out = ms; *flops = fl; *bytes = by; *launches = n;
     });
 }
 
@@ -1864,6 +1890,24 @@ int tante_profile_read(tante_handle_t h, double* gemm_ms, double* gemm_flops, in
         *gemm_launches = (int64_t)(h->prof_used / 2);
         h->prof_used = 0;
         h->prof_flops = 0;
+        h->prof_rec.clear();
+    });
+}
+
+int tante_mse_cl(const float* y, const float* ref, int32_t B, int32_t nf, int32_t n_use, int32_t D, int64_t HW, int32_t n_ref,
+                 int32_t f0, float scale, const float* gout, float* loss_sum, float* grad_y, void* stream) {
+    return guarded([&] {
+        REQUIRE(y && ref && B >= 1 && nf >= 1 && n_use >= 0 && n_use <= nf && D >= 1 && HW >= 1, "bad argument");
+        REQUIRE(f0 >= 0 && f0 + n_use <= n_ref, "target frames out of range");
+        REQUIRE(loss_sum || grad_y, "nothing to compute");
+        const long long total = (long long)B * nf * HW;
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 16LL * sms);
+        mse_cf_cl_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, ref, B, nf, n_use, D, HW, n_ref, f0, scale,
+                                                                                 gout, loss_sum, grad_y);
+        CK(cudaGetLastError());
     });
 }
 

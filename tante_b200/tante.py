@@ -539,6 +539,21 @@ class TANTE(nn.Module):
         for e in self._engines.values():
             _abi.check(e.lib.tante_profile(e.handle, 1 if enable else 0))
 
+    def profile_read_classes(self):
+        """{class: (ms, flops, bytes, launches)} of the bracketed GEMM launches since profile_gemms(True); call before
+        profile_read().  0 = plain-epilogue GEMMs, 1 = fp32 residual/LayerNorm/embedding epilogues, 2 = weight gradients."""
+        out = {}
+        for cls in (0, 1, 2):
+            ms = fl = by = 0.0
+            n = 0
+            for e in self._engines.values():
+                a, b, c, d = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0), ctypes.c_int64(0)
+                _abi.check(e.lib.tante_profile_read_class(e.handle, cls, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                                                          ctypes.byref(d)))
+                ms += a.value; fl += b.value; by += c.value; n += d.value
+            out[cls] = (ms, fl, by, n)
+        return out
+
     def profile_read(self):
         """(gemm_ms, gemm_flops, gemm_launches) accumulated since profile_gemms(True)."""
         ms = fl = 0.0

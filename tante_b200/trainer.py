@@ -31,6 +31,72 @@ def mse_loss(y_pred, y_ref, rts=None, eps: float = 0.5, n: int = 2):
     return loss
 
 
+class _FusedMSE(torch.autograd.Function):
+    """mean((y_pred - y_ref)^2) over every element -- what `MSE.eval(...).mean()` (trainer/metrics.py:53-80) computes
+    on the concatenated, channels-last predictions -- evaluated directly on the per-call channels-first frame tensors
+    by libtante_b200's `tante_mse_cl`: one pass for the loss, one for the gradients; no permute / cat / sub / pow / mean
+    kernels and none of their autograd counterparts."""
+
+    @staticmethod
+    def forward(ctx, y_ref, n_steps, *frames):
+        from . import _abi
+        lib = _abi.load()
+        dev = frames[0].device
+        y_ref = y_ref.to(torch.float32).contiguous()
+        B, n_ref, H, W, D = y_ref.shape
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        acc = torch.zeros(1, device=dev, dtype=torch.float32)
+        plan, f0 = [], 0
+        for f in frames:
+            if f.dtype != torch.float32 or not f.is_contiguous() or f.shape[0] != B or tuple(f.shape[2:]) != (D, H, W):
+                raise ValueError("fused MSE expects contiguous fp32 frames (B, n, D, H, W) matching y_ref (B, n, H, W, D)")
+            use = max(0, min(int(f.shape[1]), n_steps - f0))
+            plan.append((f0, use))
+            if use > 0:
+                _abi.check(lib.tante_mse_cl(f.data_ptr(), y_ref.data_ptr(), B, int(f.shape[1]), use, D, H * W, n_ref, f0,
+                                            0.0, None, acc.data_ptr(), None, stream))
+            f0 += use
+        ctx.numel = float(B) * n_steps * H * W * D
+        ctx.plan, ctx.n_ref = plan, n_ref
+        ctx.save_for_backward(y_ref, *frames)
+        return (acc / ctx.numel).reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        from . import _abi
+        lib = _abi.load()
+        y_ref, *frames = ctx.saved_tensors
+        B, n_ref, H, W, D = y_ref.shape
+        dev = y_ref.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        g = gout.to(torch.float32).contiguous()
+        grads = []
+        for f, (f0, use) in zip(frames, ctx.plan):
+            gf = torch.empty_like(f)
+            _abi.check(lib.tante_mse_cl(f.data_ptr(), y_ref.data_ptr(), B, int(f.shape[1]), use, D, H * W, n_ref, f0,
+                                        2.0 / ctx.numel, g.data_ptr(), None, gf.data_ptr(), stream))
+            grads.append(gf)
+        return (None, None, *grads)
+
+
+def mse_loss_frames(frames, y_ref, n_steps: int):
+    """MSE.eval(...).mean() on the per-call channels-first predictions (list of (B, n_i, D, H, W)) against the
+    channels-last targets y_ref (B, >= n_steps, H, W, D); frames beyond n_steps are ignored (r_trainer.py:130)."""
+    return _FusedMSE.apply(y_ref, int(n_steps), *frames)
+
+
+def _roll_frames(model, window, n_steps: int):
+    """`_roll` for the fixed-step model without the formatter permute and the cat over calls."""
+    moving, ys, cum = window, [], 0
+    while cum < n_steps:
+        y = model(moving)
+        cum += y.shape[1]
+        if cum < n_steps:
+            moving = torch.cat([moving[:, y.shape[1]:], y], dim=1)      # window NOT detached (BPTT)
+        ys.append(y)
+    return ys
+
+
 def _roll(model, window, n_steps: int, out_T):
     moving, ys, rts, cum = window, [], [], 0
     while cum < n_steps:
@@ -95,8 +161,12 @@ def train_step(model, optimizer, x, y_ref, n_steps: int = 4, bucket: Optional[Gr
                clip: str = "norm", rt_eps: float = 0.5, rt_n: int = 2):
     """One optimizer step.  clip = "norm": clip_grad_norm_(1.0) (trainer.py:192-193); "value": clip_grad_value_(1.0)
     (r_trainer.py:155).  Returns the (device) loss tensor."""
-    y_pred, rts = rollout_train(model, x, n_steps)
-    loss = mse_loss(y_pred, y_ref, rts, rt_eps, rt_n)
+    if getattr(model, "deg", False) and x.is_cuda and hasattr(model, "grad_layout"):
+        # fixed-step model on the CUDA path: loss and its gradient straight from the per-call frames (tante_mse_cl)
+        loss = mse_loss_frames(_roll_frames(model, x, n_steps), y_ref, n_steps)
+    else:
+        y_pred, rts = rollout_train(model, x, n_steps)
+        loss = mse_loss(y_pred, y_ref, rts, rt_eps, rt_n)
     if bucket is not None:
         bucket.zero()
     else:

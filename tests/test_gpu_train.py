@@ -296,3 +296,22 @@ def test_grad_bucket_direct_accumulation_matches_autograd_path():
         for n, p in model.named_parameters():
             assert p.grad.data_ptr() >= bucket.flat.data_ptr(), n
             assert rel_l2(p.grad.cpu().numpy(), want[n].cpu().numpy()) < 1e-5, (rep, n)
+
+
+@pytest.mark.parametrize("n_steps", [3, 4])
+def test_fused_mse_matches_reference_loss_and_gradient(n_steps):
+    """tante_mse_cl (loss of the per-call channels-first frames vs channels-last targets) == the reference's
+    MSE.eval(...).mean() on the permuted, concatenated, truncated predictions -- value and gradients."""
+    from tante_b200.trainer import mse_loss, mse_loss_frames
+    g = torch.Generator().manual_seed(5)
+    B, D, H, W = 3, 5, 16, 24
+    frames = [torch.randn(B, n, D, H, W, generator=g).cuda().requires_grad_(True) for n in (1, 2, 1)]
+    y_ref = torch.randn(B, 4, H, W, D, generator=g).cuda()
+    y_cat = torch.cat([f.permute(0, 1, 3, 4, 2) for f in frames], dim=1)[:, :n_steps]
+    want = mse_loss(y_cat, y_ref[:, :n_steps])
+    gw = torch.autograd.grad(want * 1.7, frames)
+    got = mse_loss_frames(frames, y_ref, n_steps)
+    gg = torch.autograd.grad(got * 1.7, frames)
+    assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
+    for a, b in zip(gg, gw):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-5

@@ -193,7 +193,7 @@ def bench_config(args, batch):
             "parallelism": f"trajectory-sharded x{args.gpus}, no collective"}
 
 
-CLASS_NAMES = {0: "gemm_tc_kernel, bf16/activation epilogue (QKV, MLP-in, convs, input gradients)",
+CLASS_NAMES = {0: "gemm_tc_kernel, bf16/activation epilogue (QKV, MLP-in, convs, input gradients; K=64..768: below the ridge)",
                1: "gemm_tc_kernel, fp32 residual + LayerNorm / embedding epilogue (out-proj, MLP-out, conv3)",
                2: "wgrad_tc_kernel (weight gradients)"}
 
@@ -216,13 +216,16 @@ def roofline_object(classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, te
             continue
         tf = fl / (ms * 1e-3) / 1e12
         gb = by / (ms * 1e-3) / 1e9
-        hbm_bound = cls != 0
+        # classes 1 and 2 are HBM-bound by construction; class 0 (K = 64..768 GEMMs streaming their operands from HBM)
+        # is HBM-bound too whenever its arithmetic intensity is below the ridge point of the measured peaks
+        hbm_bound = cls != 0 or (by > 0 and fl / by < (tpeak * 1e12) / (hpeak * 1e9))
         out_cls[cls] = {
             "kernel": CLASS_NAMES[cls] if tensor_mode else CLASS_NAMES[cls].replace("_tc_", "_simt_"),
             "bound": "hbm" if hbm_bound else "tensor",
             "achieved": gb if hbm_bound else tf, "peak": hpeak if hbm_bound else tpeak,
             "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": (gb / hpeak) if hbm_bound else (tf / tpeak),
-            "tflops": tf, "algorithmic_GBps": gb, "launches": int(n), "avg_us_per_launch": 1e3 * ms / n,
+            "tflops": tf, "algorithmic_GBps": gb, "flop_per_byte": (fl / by) if by > 0 else None,
+            "frac_of_tensor_peak": tf / tpeak, "frac_of_hbm_peak": gb / hpeak, "launches": int(n), "avg_us_per_launch": 1e3 * ms / n,
             "ms_per_step": ms / K_, "share_of_step": ms / ms_prof,
         }
     all_tf = (gemm_flops / (gemm_ms * 1e-3)) / 1e12 if gemm_ms > 0 else None

@@ -65,7 +65,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN>
+// NCTA = 2: the CTA pair of a 2-cluster (one TPC) runs ONE tcgen05.mma.cta_group::2 of M = 256 per k-step -- each CTA
+// streams its own 128 activation rows and keeps only HALF of the weight slice (BN/2 rows) resident, which frees 64 KB of
+// shared memory per CTA for activation stages / epilogue staging at N = K = 256 and makes 128-wide tiles fit at K = 768.
+// The leader (cluster rank 0) issues every MMA; its `full` barriers collect the TMA bytes of both CTAs, its commits are
+// multicast to the `empty` / `tmem_full` barriers of both, and both epilogues release the accumulator on the leader.
+template <int BN, int NCTA>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -74,7 +79,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;                                   // [nkb][BN rows][128 B]
-    uint8_t* sA = sW + (size_t)nkb * BN * 128;            // [nstage][128 rows][128 B]
+    constexpr int BNC = BN / NCTA;                        // weight rows resident in THIS CTA
+    uint8_t* sA = sW + (size_t)nkb * BNC * 128;           // [nstage][128 rows][128 B]
     uint8_t* sEpi = sA + (size_t)nstage * kTcStageBytes;  // [8 warps][nebuf][4 KB]
     float* sBias = reinterpret_cast<float*>(sEpi + (size_t)kTcEpiWarps * nebuf * kTcEpiBuf);   // bias, LN gamma, LN beta
     float* sStat = sBias + 3 * BN;                        // [4 quarters][2 halves][32 rows][2] partial sum / sumsq
@@ -85,15 +91,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = w_full + 1;         // [2]
     uint64_t* tmem_empty = tmem_full + 2;     // [2]
     uint64_t* rbar = tmem_empty + 2;          // [8 warps][2] residual-chunk barriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * kTcEpiWarps);
+    uint64_t* w_pair = rbar + 2 * kTcEpiWarps;   // leader: the peer's weight half is resident
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_pair + 1);
 
     if (ep.m_dev) M = min(M, *ep.m_dev * ep.m_rows);      // device-side row count (rollout encoder cache)
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int crank = NCTA == 2 ? (int)ptx::cluster_ctarank() : 0;     // rank inside the CTA pair
+    const int cid = blockIdx.x / NCTA;                                // cluster (= work unit) index
     const int n_slices = N / BN;
-    const int slice = blockIdx.x % n_slices;
-    const int rank = blockIdx.x / n_slices;
-    const int per_slice = gridDim.x / n_slices;
-    const int m_tiles = (M + kTcBlockM - 1) / kTcBlockM;
+    const int slice = cid % n_slices;
+    const int rank = cid / n_slices;
+    const int per_slice = (gridDim.x / NCTA) / n_slices;
+    const int m_tiles = (M + kTcBlockM * NCTA - 1) / (kTcBlockM * NCTA);   // tiles of 128 rows per CTA of the unit
     const int n0 = slice * BN;
     const bool has_ln = epi == EPI_BIAS_RESID_LN;          // requires BN == N (whole row in this CTA)
     const bool has_res = epi == EPI_BIAS_RESID || has_ln;
@@ -111,43 +120,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (has_ln) ptx::prefetch_tmap(&tmL);
         for (int s = 0; s < nstage; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         ptx::mbar_init(w_full, 1);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], kTcEpiWarps); }
+        // accumulator release: the 8 local epilogue warps (+ in a pair, on the leader, one forwarded arrival of the peer)
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full[i], 1);
+            ptx::mbar_init(&tmem_empty[i], kTcEpiWarps + ((NCTA == 2 && ptx::cluster_ctarank() == 0) ? 1 : 0));
+        }
         for (int i = 0; i < 2 * kTcEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
+        ptx::mbar_init(w_pair, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 2 * BN);
-        ptx::tmem_relinquish();
+        if (NCTA == 2) { ptx::tmem_alloc_pair(tmem_slot, 2 * BN); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc(tmem_slot, 2 * BN); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) ptx::cluster_sync_all();     // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(w_full, (uint32_t)nkb * BN * 128);
-            for (int kb = 0; kb < nkb; ++kb) ptx::tma_load_2d(sW + (size_t)kb * BN * 128, &tmW, w_full, kb * kTcBlockK, n0);
+            ptx::mbar_arrive_expect_tx(w_full, (uint32_t)nkb * BNC * 128);
+            for (int kb = 0; kb < nkb; ++kb)
+                ptx::tma_load_2d(sW + (size_t)kb * BNC * 128, &tmW, w_full, kb * kTcBlockK, n0 + crank * BNC);
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = rank; mt < m_tiles; mt += per_slice) {
                 for (int kb = 0; kb < nkb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
-                    ptx::tma_load_2d(sA + (size_t)stage * kTcStageBytes, &tmA, &full[stage], kb * kTcBlockK, mt * kTcBlockM);
+                    if (NCTA == 2) {
+                        // the leader's barrier counts the bytes of both CTAs' tiles (one arrival: the leader's)
+                        if (crank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * kTcStageBytes);
+                        ptx::tma_load_2d_pair(sA + (size_t)stage * kTcStageBytes, &tmA, &full[stage], kb * kTcBlockK,
+                                              (mt * 2 + crank) * kTcBlockM);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
+                        ptx::tma_load_2d(sA + (size_t)stage * kTcStageBytes, &tmA, &full[stage], kb * kTcBlockK, mt * kTcBlockM);
+                    }
                     if (++stage == nstage) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTcBlockM, BN);
+        // ===== MMA issuer (CTA pair: the leader only; the peer just reports its weight half) =====
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTcBlockM * NCTA, BN);
         ptx::mbar_wait(w_full, 0);
+        if (NCTA == 2) {
+            if (crank == 1) {
+                if (lane == 0) ptx::mbar_arrive_leader(w_pair);
+                // The peer's otherwise idle warp forwards "all 8 local epilogue warps released the accumulator" to the
+                // leader: the cluster-scope release (MEMBAR + ERRBAR) stays off the epilogue warps' critical path.
+                int tt = 0;
+                for (int mt = rank; mt < m_tiles; mt += per_slice, ++tt) {
+                    ptx::mbar_wait(&tmem_empty[tt & 1], (tt >> 1) & 1);
+                    if (lane == 0) ptx::mbar_arrive_leader(&tmem_empty[tt & 1]);
+                    __syncwarp();
+                }
+            } else {
+                ptx::mbar_wait(w_pair, 0);
+            }
+        }
         int stage = 0;
         uint32_t phase = 0;
         int t = 0;
-        for (int mt = rank; mt < m_tiles; mt += per_slice, ++t) {
+        for (int mt = rank; mt < m_tiles && crank == 0; mt += per_slice, ++t) {
             const int acc = t & 1;
             ptx::mbar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1);
             ptx::tc_fence_after();
@@ -157,12 +195,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + (size_t)stage * kTcStageBytes));
-                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sW + (size_t)kb * BN * 128));
+                    const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sW + (size_t)kb * BNC * 128));
 #pragma unroll
-                    for (int k = 0; k < kTcBlockK / 16; ++k)
-                        ptx::umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    ptx::umma_commit(&empty[stage]);          // frees the smem stage when the MMAs retire
-                    if (kb == nkb - 1) ptx::umma_commit(&tmem_full[acc]);
+                    for (int k = 0; k < kTcBlockK / 16; ++k) {
+                        if (NCTA == 2) ptx::umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else ptx::umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when the MMAs retire
+                    if (NCTA == 2) ptx::umma_commit_pair(&empty[stage]); else ptx::umma_commit(&empty[stage]);
+                    if (kb == nkb - 1) { if (NCTA == 2) ptx::umma_commit_pair(&tmem_full[acc]); else ptx::umma_commit(&tmem_full[acc]); }
                 }
                 __syncwarp();
                 if (++stage == nstage) { stage = 0; phase ^= 1; }
@@ -176,12 +217,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half = ew >> 2;
         uint8_t* ebuf = sEpi + (size_t)ew * nebuf * kTcEpiBuf;
         uint64_t* rb = rbar + ew * 2;
-        uint32_t rphase0 = 0;
+        uint32_t rphase0 = 0, rphase1 = 0;
         int nbuf = 0;        // staging buffer the next chunk uses (bf16 path with nebuf == 2 only)
         int t = 0;
         for (int mt = rank; mt < m_tiles; mt += per_slice, ++t) {
             const int acc = t & 1;
-            const int row0 = mt * kTcBlockM + q * 32;
+            const int row0 = (mt * NCTA + crank) * kTcBlockM + q * 32;
             const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             if (out_bf16) {
                 // EPI_MULGRAD_*: the saved pre-activation tile is TMA-loaded into the staging buffer (first chunk
@@ -198,9 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r0[32], r1[32];
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64), r0);
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 64 + 32), r1);
-                    uint8_t* buf = ebuf + nbuf * kTcEpiBuf;
+                    const bool alt = nebuf > 1 && !has_mul;      // alternate the two staging buffers (plain epilogues only)
+                    uint8_t* buf = ebuf + (alt ? nbuf : 0) * kTcEpiBuf;
                     if (lane == 0 && !(has_mul && ch == half)) {
-                        if (nebuf > 1) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+                        if (alt) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
                         if (has_mul) {
                             ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
                             ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 64, row0);
@@ -240,35 +282,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::tma_store_2d(&tmC, buf, n0 + ch * 64, row0);
                         ptx::bulk_commit();
                     }
-                    if (nebuf > 1) nbuf ^= 1;
+                    if (alt) nbuf ^= 1;
                 }
             } else {
                 // fp32 output in 32-column chunks, one staging buffer per warp.  The residual variants TMA-load the
                 // residual chunk into the buffer (8 warps x 4 KB of loads in flight per SM), add in place and TMA-store it back.  The
                 // first chunk's load is issued before the accumulator is ready, so it overlaps the MMAs.
                 const int m = row0 + lane;
-                if (has_res && lane == 0) {
+                // nebuf == 2 (CTA pairs: the halved weight slice pays for a second staging buffer per warp): the residual
+                // chunk AFTER the next one is requested as soon as the store of the current chunk has drained its buffer,
+                // so two residual loads per warp (16 per SM pair... 64 KB per SM) are in flight instead of one.
+                const bool dbl = nebuf > 1;
+                if (lane == 0 && (has_res || dbl)) {
                     ptx::bulk_wait_read<0>();
-                    ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
-                    ptx::tma_load_2d(ebuf, &tmR, &rb[0], n0 + half * 32, row0);
+                    if (has_res) {
+                        ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                        ptx::tma_load_2d(ebuf, &tmR, &rb[0], n0 + half * 32, row0);
+                        if (dbl && half + 2 < BN / 32) {
+                            ptx::mbar_arrive_expect_tx(&rb[1], kTcEpiBuf);
+                            ptx::tma_load_2d(ebuf + kTcEpiBuf, &tmR, &rb[1], n0 + (half + 2) * 32, row0);
+                        }
+                    }
                 }
                 ptx::mbar_wait(&tmem_full[acc], (t >> 1) & 1);
                 ptx::tc_fence_after();
                 float rsum = 0.f, rsq = 0.f;
+                int jc = 0;
 #pragma unroll 1
-                for (int ch = half; ch < BN / 32; ch += 2) {
+                for (int ch = half; ch < BN / 32; ch += 2, ++jc) {
                     uint32_t r0[32];
-                    uint8_t* buf = ebuf;
-                    if (lane == 0 && (ch != half || !has_res)) {
-                        ptx::bulk_wait_read<0>();       // the previous store has finished reading the buffer
-                        if (has_res) {
-                            ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
-                            ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 32, row0);
+                    const int bsel = dbl ? (jc & 1) : 0;
+                    uint8_t* buf = ebuf + bsel * kTcEpiBuf;
+                    if (!dbl) {
+                        if (lane == 0 && (ch != half || !has_res)) {
+                            ptx::bulk_wait_read<0>();       // the previous store has finished reading the buffer
+                            if (has_res) {
+                                ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
+                                ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 32, row0);
+                            }
                         }
+                    } else if (!has_res && lane == 0 && jc >= 2) {
+                        ptx::bulk_wait_read<1>();           // this buffer's store of two chunks ago has drained
                     }
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 32), r0);
                     __syncwarp();
-                    if (has_res) { ptx::mbar_wait(&rb[0], rphase0); rphase0 ^= 1; }
+                    if (has_res) {
+                        if (bsel == 0) { ptx::mbar_wait(&rb[0], rphase0); rphase0 ^= 1; }
+                        else { ptx::mbar_wait(&rb[1], rphase1); rphase1 ^= 1; }
+                    }
                     ptx::tc_wait_ld();
                     const float* bsm = sBias + ch * 32;
                     const int ncol = n0 + ch * 32;
@@ -314,6 +375,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (lane == 0) {
                         ptx::tma_store_2d(&tmC, buf, ncol, row0);
                         ptx::bulk_commit();
+                        if (dbl && has_res && ch + 4 < BN / 32) {
+                            ptx::bulk_wait_read<0>();       // the store just issued has drained this buffer: refill it
+                            ptx::mbar_arrive_expect_tx(&rb[bsel], kTcEpiBuf);
+                            ptx::tma_load_2d(buf, &tmR, &rb[bsel], n0 + (ch + 4) * 32, row0);
+                        }
                     }
                 }
                 if (has_ln) {
@@ -371,8 +437,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) ptx::bulk_wait_all<0>();
     }
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+    if (NCTA == 2) ptx::cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair's MMAs may still touch it
+    else __syncthreads();
+    if (warp == 1) { if (NCTA == 2) ptx::tmem_dealloc_pair(tmem_base, 2 * BN); else ptx::tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -407,29 +474,49 @@ static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, cons
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct TcPlan { int BN, nkb, nstage, nebuf, grid; size_t smem; };
+struct TcPlan { int BN, ncta, nkb, nstage, nebuf, grid; size_t smem; };
+
+// CTA pairs (cta_group::2): TANTE_GEMM_2CTA = 0 never, 1 (default) where they pay off, 2 everywhere they fit (tests).
+// Measured on B200 (tools/gemm_probe.py, M = 262144 / 65536, N = K = 256): the fp32 residual (+LayerNorm) epilogues gain
+// 16-19 % / 11-14 % from the second staging buffer the halved weight slice pays for (156.6 -> 126.9 us, 188.7 -> 158.2 us);
+// plain bf16 epilogues lose 4-19 % to the lock-step of the pair, so they stay on single CTAs unless the reduction is so
+// long (K = 768) that a single CTA could only keep a 64-wide weight slice resident.
+static int tc_pair_mode() {
+    static const int mode = getenv("TANTE_GEMM_2CTA") ? atoi(getenv("TANTE_GEMM_2CTA")) : 1;
+    return mode;
+}
 
 static bool tc_plan(int M, int N, int K, int num_sms, int out_bf16, TcPlan* p) {
     if (K % kTcBlockK != 0 || K > 1024 || N % 64 != 0) return false;
     if ((size_t)(K / kTcBlockK) * 64 * 128 > 128 * 1024) return false;
     const int nkb = K / kTcBlockK;
     int BN = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
-    while ((size_t)nkb * BN * 128 > 128 * 1024 && BN > 64) BN /= 2;   // keep the resident slice <= 128 KB
-    // one 4 KB staging buffer per epilogue warp (8 warps keep enough TMA traffic in flight without double buffering)
-    (void)out_bf16;
-    const int nebuf = 1;
-    const size_t fixed = (size_t)nkb * BN * 128 + (size_t)kTcEpiWarps * nebuf * kTcEpiBuf + 3 * BN * 4 + 4 * 2 * 32 * 2 * 4 +
-                         512 + 1024;
+    // pairs need >= 128 columns (64 per CTA) and enough 256-row tiles to fill the machine
+    const bool narrow_single = (size_t)nkb * 128 * 128 > 128 * 1024;        // a single CTA would be down to 64-wide slices
+    const bool pays = !out_bf16 || (narrow_single && N >= 128);
+    const int ncta = (tc_pair_mode() == 2 && N % 128 == 0) ? 2
+                     : (tc_pair_mode() == 1 && pays && N % 128 == 0 && M >= 256 * (num_sms / 2)) ? 2 : 1;
+    while ((size_t)nkb * (BN / ncta) * 128 > 128 * 1024 && BN > 64 * ncta) BN /= 2;   // keep the resident slice <= 128 KB
+    if ((size_t)nkb * (BN / ncta) * 128 > 128 * 1024) return false;
+    // pairs: the halved weight slice pays for a second staging buffer per epilogue warp (if >= 3 activation stages remain)
+    int nebuf = ncta == 2 ? 2 : 1;
     const size_t budget = 227 * 1024;
-    int nstage = (int)((budget - fixed) / kTcStageBytes);
-    nstage = nstage > 6 ? 6 : nstage;
+    size_t fixed = 0;
+    int nstage = 0;
+    for (;; --nebuf) {
+        fixed = (size_t)nkb * (BN / ncta) * 128 + (size_t)kTcEpiWarps * nebuf * kTcEpiBuf + 3 * BN * 4 + 4 * 2 * 32 * 2 * 4 + 512 + 1024;
+        nstage = fixed < budget ? (int)((budget - fixed) / kTcStageBytes) : 0;
+        if (nstage >= 3 || nebuf == 1) break;
+    }
+    nstage = nstage > kTcMaxStages ? kTcMaxStages : nstage;
+    if (ncta == 1 && nstage > 6) nstage = 6;
     if (nstage < 2) return false;
     const int n_slices = N / BN;
-    const int m_tiles = (M + kTcBlockM - 1) / kTcBlockM;
-    int per_slice = num_sms / n_slices;
+    const int m_tiles = (M + kTcBlockM * ncta - 1) / (kTcBlockM * ncta);
+    int per_slice = (num_sms / ncta) / n_slices;
     if (per_slice < 1) per_slice = 1;
     if (per_slice > m_tiles) per_slice = m_tiles;
-    p->BN = BN; p->nkb = nkb; p->nstage = nstage; p->nebuf = nebuf; p->grid = per_slice * n_slices;
+    p->BN = BN; p->ncta = ncta; p->nkb = nkb; p->nstage = nstage; p->nebuf = nebuf; p->grid = per_slice * n_slices * ncta;
     p->smem = fixed + (size_t)nstage * kTcStageBytes;
     return true;
 }
@@ -438,9 +525,11 @@ static cudaError_t tc_set_attrs() {
     static bool attr_done = false;
     if (attr_done) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if (!get_encode_tiled()) return cudaErrorNotSupported;
     attr_done = true;
     return cudaSuccess;
@@ -457,7 +546,7 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
     const bool is_ln = epi == EPI_BIAS_RESID_LN;
     if (is_ln && (out_bf16 || p.BN != N || !ep.ln_out || !ep.ln_gamma || !ep.ln_beta)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kTcBlockK, kTcBlockM)) return cudaErrorInvalidValue;
-    if (!make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kTcBlockK, p.BN)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kTcBlockK, p.BN / p.ncta)) return cudaErrorInvalidValue;
     if (out_bf16) {
         if (!make_tmap_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, M, N, ldc, 64, 32)) return cudaErrorInvalidValue;
     } else {
@@ -467,7 +556,7 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
     tmL = tmC;
     if (is_ln && !make_tmap_2d(&tmL, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.ln_out, M, N, N, 64, 32)) return cudaErrorInvalidValue;
     if (epi >= EPI_MULGRAD_RELU && epi <= EPI_MULGRAD_GELU_TANH) {
-        if (!out_bf16 || !ep.mul_pre || p.nebuf != 1) return cudaErrorInvalidValue;
+        if (!out_bf16 || !ep.mul_pre) return cudaErrorInvalidValue;
         if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep.mul_pre, M, N, ep.ld_pre, 64, 32)) return cudaErrorInvalidValue;
     }
     if (epi == EPI_BIAS_RESID || is_ln) {
@@ -475,10 +564,21 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
         if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.resid, M, N, ep.ldr, 32, 32)) return cudaErrorInvalidValue;
     }
     { cudaError_t e = tc_set_attrs(); if (e != cudaSuccess) return e; }
+    if (p.ncta == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)p.grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (p.BN == 256)
+            return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, 2>, tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep);
+        return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, 2>, tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep);
+    }
     switch (p.BN) {
-        case 256: gemm_tc_kernel<256><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
-        case 128: gemm_tc_kernel<128><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
-        default: gemm_tc_kernel<64><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
+        case 256: gemm_tc_kernel<256, 1><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
+        case 128: gemm_tc_kernel<128, 1><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
+        default: gemm_tc_kernel<64, 1><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
     }
     return cudaGetLastError();
 }

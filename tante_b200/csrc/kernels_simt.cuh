@@ -450,14 +450,15 @@ __global__ void __launch_bounds__(256) embed_cached_kernel(const float* __restri
                                                            const float* __restrict__ film, const float* __restrict__ s_emb,
                                                            const float* __restrict__ t_emb, float* __restrict__ x, int B, int T,
                                                            int L, int C) {
-    const int c4n = C / 4;
-    const long long total = (long long)B * T * L * c4n;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // 32-bit index arithmetic (B*T*L*C/4 < 2^31 is checked by the launcher): the 64-bit div/mod chain cost more than the copy
+    const unsigned c4n = (unsigned)C / 4;
+    const unsigned total = (unsigned)B * T * L * c4n;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = (int)(i % c4n) * 4;
-        long long tok = i / c4n;
-        const int l = (int)(tok % L); tok /= L;
-        const int t = (int)(tok % T);
-        const int b = (int)(tok / T);
+        unsigned tok = i / c4n;
+        const int l = (int)(tok % (unsigned)L); tok /= (unsigned)L;
+        const int t = (int)(tok % (unsigned)T);
+        const int b = (int)(tok / (unsigned)T);
         const int slot = (fcount[b] + t) % T;
         const int e = enc_map[b * T + slot];
         float* cp = cache + ((size_t)(b * T + slot) * L + l) * C + c;

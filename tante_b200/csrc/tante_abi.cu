@@ -602,6 +602,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             gemm<TA>(h, EPI_BIAS, a2, g.k2 * g.k2 * C2, h->enc_w[2], cnew, C, true, tokens, C, g.k2 * g.k2 * C2, e3, st);
             h->prof_on = prof;
             const long long tot4 = (long long)tokens * (C / 4);
+            REQUIRE(tot4 < (1LL << 31), "latent too large for the 32-bit indexing of the cached embed pass");
             embed_cached_kernel<<<(unsigned)std::min<long long>((tot4 + 255) / 256, 32LL * h->num_sms), 256, 0, st>>>(
                 cnew, reinterpret_cast<float*>(h->enc_cache.p), rs.enc_map, io.fcount, AF(h, h->film_t_off), AF(h, h->s_emb),
                 AF(h, h->t_emb), x, B, T, L, C);

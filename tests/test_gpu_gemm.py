@@ -100,3 +100,14 @@ def test_tcgen05_gemm_residual_layernorm_epilogue(M, K):
     assert float((xc - x_ref).norm() / x_ref.norm()) < 2e-6
     assert float((ln.float() - ln_ref).norm() / ln_ref.norm()) < 4e-3      # one bf16 rounding
     assert float((ln.float() - ln_ref).abs().max()) < 0.05
+
+
+def test_cta_pair_gemm_on_every_shape_in_a_subprocess():
+    """The CTA-pair (cta_group::2) variant is only chosen where it pays off (fp32 epilogues / K = 768 at large M); force it
+    wherever it fits (TANTE_GEMM_2CTA=2, read once per process) and run this file's tcgen05 parity tests again."""
+    import os, subprocess, sys
+    env = dict(os.environ, TANTE_GEMM_2CTA="2")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-k", "tcgen05 and not subprocess"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(here)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -46,36 +46,47 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
     constexpr int R = NKB * 8;
     extern __shared__ __align__(128) uint8_t att_smem[];
     __shared__ long long s_tok[R];
+    __shared__ int s_gp[R];              // row -> (group << 8) | position, -1 for padding rows
     // tiles: [mat q,k,v][head 0..3][R rows][64 B]
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int blk = blockIdx.x, hq = blockIdx.y;
     const int Gv = min(G, n_groups - blk * G);           // sequences actually present in this block
     const int rows_valid = Gv * S;
 
+    // (the kernel is issue-bound: every division below is done once per ROW by one thread, the per-thread loops further
+    //  down only add constants to what these tables hold)
     if (tid < R) {
         long long tok = -1;
+        int gp = -1;
         if (tid < rows_valid) {
-            const int i = tid / S, p = tid % S;
+            const int i = tid / S, p = tid - i * S;
             const long long gid = (long long)blk * G + i;
-            const long long outer = gid / inner_sz, inner = gid % inner_sz;
+            const long long outer = gid / inner_sz, inner = gid - outer * inner_sz;
             tok = outer * S * inner_sz + (long long)p * inner_sz + inner;
+            gp = (i << 8) | p;
         }
         s_tok[tid] = tok;
+        s_gp[tid] = gp;
     }
     __syncthreads();
     // ---- stage Q/K/V slices of 4 heads: per row 3 x 256 contiguous bytes ----
+    // thread = (16-byte chunk ch of the 256-byte head-group slice, row group): 16 consecutive threads fetch one slice;
     // (cp.async: all 16-byte requests of a thread are in flight at once, no register staging; src-size 0 zero-fills)
+    const int ch = tid & 15, rg = tid >> 4;              // ch = head(2 bits) | part(2 bits); 8 row groups
+    const int hh_l = ch >> 2, part_l = ch & 3;
+    const int col_l = (hq * 4 + hh_l) * 32 + part_l * 8; // element offset of this thread's chunk inside a C-wide row
     {
         const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(att_smem);
-#pragma unroll 4
-        for (int idx = tid; idx < R * 48; idx += 128) {
-            const int r = idx / 48, c = idx % 48;
-            const int mat = c / 16, hh = (c % 16) / 4, part = c % 4;
+#pragma unroll
+        for (int r = rg; r < R; r += 8) {
             const long long tok = s_tok[r];
-            const __nv_bfloat16* src = qkv + (tok >= 0 ? (size_t)tok * 3 * C + (size_t)mat * C + (hq * 4 + hh) * 32 + part * 8 : 0);
-            const uint32_t dst = sbase + (uint32_t)((mat * 4 + hh) * R) * 64 + att_off(r, part);
+            const __nv_bfloat16* src = qkv + (tok >= 0 ? (size_t)tok * 3 * C + col_l : 0);
+            const uint32_t dst = sbase + (uint32_t)(hh_l * R) * 64 + att_off(r, part_l);
             const int nbytes = tok >= 0 ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+#pragma unroll
+            for (int mat = 0; mat < 3; ++mat)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(mat * 4 * R * 64)),
+                             "l"(src + (tok >= 0 ? mat * C : 0)), "r"(nbytes) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -96,9 +107,9 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
     for (int kb = 0; kb < NKB; ++kb)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int key = kb * 8 + 2 * t + j;
-            if (G == 1) { kgrp[kb][j] = key < rows_valid ? 0 : -1; kpos[kb][j] = key; }
-            else { kgrp[kb][j] = key < rows_valid ? key / S : -1; kpos[kb][j] = key % S; }
+            const int gp = s_gp[kb * 8 + 2 * t + j];
+            kgrp[kb][j] = gp < 0 ? -1 : (gp >> 8);
+            kpos[kb][j] = gp & 255;
         }
 
 #pragma unroll 1
@@ -119,8 +130,10 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
         }
         // ---- mask + softmax over the key axis (rows g and g+8 of this 16-row block) ----
         const int r0 = qb * 16 + g, r1 = r0 + 8;
-        const int g0 = G == 1 ? 0 : r0 / S, p0 = G == 1 ? r0 : r0 % S;
-        const int g1 = G == 1 ? 0 : r1 / S, p1 = G == 1 ? r1 : r1 % S;
+        // padding query rows get group -2: no key matches, the row stays fully masked (as before: zero output)
+        const int gp0 = s_gp[r0], gp1 = s_gp[r1];
+        const int g0 = gp0 < 0 ? -2 : (gp0 >> 8), p0 = gp0 & 255;
+        const int g1 = gp1 < 0 ? -2 : (gp1 >> 8), p1 = gp1 & 255;
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb) {
@@ -180,14 +193,13 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
         }
     }
     __syncthreads();
-    // ---- coalesced write-back: per row 4 heads x 64 B = 256 contiguous bytes ----
-    for (int idx = tid; idx < R * 16; idx += 128) {
-        const int r = idx / 16, c = idx % 16;
-        const int hh = c / 4, part = c % 4;
+    // ---- coalesced write-back: per row 4 heads x 64 B = 256 contiguous bytes (same thread map as the loads) ----
+#pragma unroll
+    for (int r = rg; r < R; r += 8) {
         const long long tok = s_tok[r];
         if (tok < 0) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(att_smem + (size_t)((0 * 4 + hh) * R) * 64 + att_off(r, part));
-        *reinterpret_cast<uint4*>(out + (size_t)tok * C + (hq * 4 + hh) * 32 + part * 8) = v;
+        const uint4 v = *reinterpret_cast<const uint4*>(att_smem + (size_t)(hh_l * R) * 64 + att_off(r, part_l));
+        *reinterpret_cast<uint4*>(out + (size_t)tok * C + col_l) = v;
     }
 }
 

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
     constexpr int R = NKB * 8;
     extern __shared__ __align__(128) uint8_t attb_smem[];
     __shared__ long long s_tok[R];
+    __shared__ int s_gp[R];              // row -> (group << 8) | position, -1 for padding rows (see attention_mma.cuh)
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int blk = blockIdx.x, hq = blockIdx.y;
     const int Gv = min(G, n_groups - blk * G);
@@ -33,28 +34,37 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
 
     if (tid < R) {
         long long tok = -1;
+        int gp = -1;
         if (tid < rows_valid) {
-            const int i = tid / S, p = tid % S;
+            const int i = tid / S, p = tid - i * S;
             const long long gid = (long long)blk * G + i;
-            const long long outer = gid / inner_sz, inner = gid % inner_sz;
+            const long long outer = gid / inner_sz, inner = gid - outer * inner_sz;
             tok = outer * S * inner_sz + (long long)p * inner_sz + inner;
+            gp = (i << 8) | p;
         }
         s_tok[tid] = tok;
+        s_gp[tid] = gp;
     }
     __syncthreads();
+    // thread = (16-byte chunk of the 256-byte head-group slice, row group), as in the forward kernel
+    const int ch = tid & 15, rg = tid >> 4;
+    const int hh_l = ch >> 2, part_l = ch & 3;
+    const int col_l = (hq * 4 + hh_l) * 32 + part_l * 8;
     {
         const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tiles);
-#pragma unroll 4
-        for (int idx = tid; idx < R * 64; idx += 128) {
-            const int r = idx / 64, c = idx % 64;
-            const int mat = c / 16, hh = (c % 16) / 4, part = c % 4;
+#pragma unroll
+        for (int r = rg; r < R; r += 8) {
             const long long tok = s_tok[r];
-            const __nv_bfloat16* src;
-            if (mat < 3) src = qkv + (tok >= 0 ? (size_t)tok * 3 * C + (size_t)mat * C + (hq * 4 + hh) * 32 + part * 8 : 0);
-            else src = dout + (tok >= 0 ? (size_t)tok * C + (hq * 4 + hh) * 32 + part * 8 : 0);
-            const uint32_t dst = sbase + (uint32_t)((mat * 4 + hh) * R) * 64 + att_off(r, part);
             const int nbytes = tok >= 0 ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            const __nv_bfloat16* src = qkv + (tok >= 0 ? (size_t)tok * 3 * C + col_l : 0);
+            const uint32_t dst = sbase + (uint32_t)(hh_l * R) * 64 + att_off(r, part_l);
+#pragma unroll
+            for (int mat = 0; mat < 3; ++mat)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(mat * 4 * R * 64)),
+                             "l"(src + (tok >= 0 ? mat * C : 0)), "r"(nbytes) : "memory");
+            const __nv_bfloat16* srco = dout + (tok >= 0 ? (size_t)tok * C + col_l : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(3 * 4 * R * 64)), "l"(srco),
+                         "r"(nbytes) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -81,9 +91,9 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
     for (int kb = 0; kb < NKB; ++kb)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int col = kb * 8 + 2 * t + j;
-            if (G == 1) { cgrp[kb][j] = col < rows_valid ? 0 : -1; cpos[kb][j] = col; }
-            else { cgrp[kb][j] = col < rows_valid ? col / S : -1; cpos[kb][j] = col % S; }
+            const int gp = s_gp[kb * 8 + 2 * t + j];
+            cgrp[kb][j] = gp < 0 ? -1 : (gp >> 8);
+            cpos[kb][j] = gp & 255;
         }
 
     // ================= pass 1: query-major =================
@@ -113,8 +123,9 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
             mma_bf16_16816(dp[kb], oa[1], k2, k3);
         }
         const int r0 = qb * 16 + g, r1 = r0 + 8;
-        const int g0 = G == 1 ? 0 : r0 / S, p0 = G == 1 ? r0 : r0 % S;
-        const int g1 = G == 1 ? 0 : r1 / S, p1 = G == 1 ? r1 : r1 % S;
+        const int gp0 = s_gp[r0], gp1 = s_gp[r1];
+        const int g0 = gp0 < 0 ? -2 : (gp0 >> 8), p0 = gp0 & 255;
+        const int g1 = gp1 < 0 ? -2 : (gp1 >> 8), p1 = gp1 & 255;
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb)
@@ -220,9 +231,9 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
             mma_bf16_16816(dp[qb], va[1], q2, q3);
         }
         const int r0 = kb16 * 16 + g, r1 = r0 + 8;        // key rows
-        const int g0 = G == 1 ? (r0 < rows_valid ? 0 : -2) : (r0 < rows_valid ? r0 / S : -2);
-        const int g1 = G == 1 ? (r1 < rows_valid ? 0 : -2) : (r1 < rows_valid ? r1 / S : -2);
-        const int p0 = G == 1 ? r0 : r0 % S, p1 = G == 1 ? r1 : r1 % S;
+        const int gp0 = s_gp[r0], gp1 = s_gp[r1];
+        const int g0 = gp0 < 0 ? -2 : (gp0 >> 8), p0 = gp0 & 255;
+        const int g1 = gp1 < 0 ? -2 : (gp1 >> 8), p1 = gp1 & 255;
 #pragma unroll
         for (int qb = 0; qb < NKB; ++qb)
 #pragma unroll
@@ -277,15 +288,16 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
         }
     }
     __syncthreads();
-    // ---- coalesced write-back of (dq, dk, dv): per row 3 x 4 heads x 64 B ----
-    for (int idx = tid; idx < R * 48; idx += 128) {
-        const int r = idx / 48, c = idx % 48;
-        const int mat = c / 16, hh = (c % 16) / 4, part = c % 4;
+    // ---- coalesced write-back of (dq, dk, dv): per row 3 x 4 heads x 64 B (same thread map as the loads) ----
+#pragma unroll
+    for (int r = rg; r < R; r += 8) {
         const long long tok = s_tok[r];
         if (tok < 0) continue;
-        const uint8_t* src = mat == 0 ? stage + (size_t)(hh * R) * 64 : tiles + (size_t)((mat * 4 + hh) * R) * 64;
-        const uint4 v = *reinterpret_cast<const uint4*>(src + att_off(r, part));
-        *reinterpret_cast<uint4*>(dqkv + (size_t)tok * 3 * C + (size_t)mat * C + (hq * 4 + hh) * 32 + part * 8) = v;
+        __nv_bfloat16* dst = dqkv + (size_t)tok * 3 * C + col_l;
+        const uint32_t so = (uint32_t)(hh_l * R) * 64 + att_off(r, part_l);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stage + so);
+        *reinterpret_cast<uint4*>(dst + C) = *reinterpret_cast<const uint4*>(tiles + (size_t)(1 * 4 * R) * 64 + so);
+        *reinterpret_cast<uint4*>(dst + 2 * C) = *reinterpret_cast<const uint4*>(tiles + (size_t)(2 * 4 * R) * 64 + so);
     }
 }
 

@@ -313,8 +313,9 @@ __global__ void __launch_bounds__(256) interp_tail_bwd_kernel(const TA* __restri
 //   xhat = (x-mean)*rstd; gy = dy*gamma; dx_ln = rstd*(gy - mean(gy) - xhat*mean(gy*xhat))
 //   dxs (fp32 gradient stream, in place) += dx_ln; optional TA copy of the updated row (next GEMM operand);
 //   dgamma += dy*xhat, dbeta += dy (per-warp registers -> shared -> atomics).
+// (occupancy: 3 blocks of 256 threads per SM -- at the natural 87 registers only 2 fit, and the kernel is latency-bound)
 template <typename TA, int MAXV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const TA* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ gamma, float* __restrict__ dxs,
                                                      TA* __restrict__ dxb, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, long long rows, int C, float eps) {

@@ -808,7 +808,8 @@ template <typename TA>
 void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamma, float* dxs, TA* dxb, float* dg, float* db,
                    long long rows, cudaStream_t st) {
     const int C = h->C;
-    const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, 8LL * h->num_sms);
+    // persistent grid = exactly the resident blocks (3 per SM for C <= 256): no partial last wave
+    const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, (C <= 256 ? 3LL : 2LL) * h->num_sms);
     if (C <= 256) ln_bwd_kernel<TA, 2><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f);
     else ln_bwd_kernel<TA, 4><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f);
     CK(cudaGetLastError());

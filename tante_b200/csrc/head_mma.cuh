@@ -219,27 +219,38 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         if (!y_out || n <= 0) continue;
         __syncthreads();                                             // u0 planes visible
 
-        // ---- phase 3: channels-last history, thread = (pixel row, pixel column, field), field fastest ----
-        const int nitemsB = P * xvalid * g.D;
-        const int xd = xvalid * g.D;
-        for (int item = tid; item < nitemsB; item += 128) {
-            const int hr = item / xd;
-            const int rem = item - hr * xd;
-            const int x = rem / g.D, d = rem - x * g.D;
-            const int so = d * PS + hr * XW + x;
-            float dk[KORD];
-#pragma unroll
-            for (int k = 0; k < KORD; ++k) dk[k] = sS[k * g.D * PS + so];
-            const float u0 = sU[so];
+        // ---- phase 3: channels-last history, thread = one pixel: its D fields are D consecutive floats of the output
+        //      (one 128-bit store when D == 4), adjacent threads = adjacent pixels ----
+        const int npix = P * xvalid;
+        const bool vec4 = g.D == 4 && (reinterpret_cast<uintptr_t>(y_out) & 15) == 0;
+        for (int pi = tid; pi < npix; pi += 128) {
+            const int hr = pi / xvalid;
+            const int x = pi - hr * xvalid;
+            const int so = hr * XW + x;
             const size_t pix = pix0 + (size_t)hr * g.W + x;
             for (int i = 1; i <= n; ++i) {
                 const int fidx = cum + i - 1;
                 if (fidx >= hp.n_roll) break;
                 const float dt = (float)i * hp.fi;
-                float v = 0.f;
+                float* yp = y_out + (((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D;
+                if (vec4) {
+                    float o[4];
 #pragma unroll
-                for (int k = KORD; k >= 1; --k) v = (dk[k - 1] + v) * (dt / (float)k);
-                y_out[(((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D + d] = v + u0;
+                    for (int d = 0; d < 4; ++d) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int k = KORD; k >= 1; --k) v = (sS[(k - 1) * g.D * PS + d * PS + so] + v) * (dt / (float)k);
+                        o[d] = v + sU[d * PS + so];
+                    }
+                    *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+                    for (int d = 0; d < g.D; ++d) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int k = KORD; k >= 1; --k) v = (sS[(k - 1) * g.D * PS + d * PS + so] + v) * (dt / (float)k);
+                        yp[d] = v + sU[d * PS + so];
+                    }
+                }
             }
         }
     }

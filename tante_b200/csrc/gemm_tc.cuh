@@ -90,8 +90,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* w_full = bars + 2 * kTcMaxStages;
     uint64_t* tmem_full = w_full + 1;         // [2]
     uint64_t* tmem_empty = tmem_full + 2;     // [2]
-    uint64_t* rbar = tmem_empty + 2;          // [8 warps][2] residual-chunk barriers
-    uint64_t* w_pair = rbar + 2 * kTcEpiWarps;   // leader: the peer's weight half is resident
+    uint64_t* rbar = tmem_empty + 2;          // [8 warps][3] residual-chunk barriers (one per staging buffer)
+    uint64_t* w_pair = rbar + 3 * kTcEpiWarps;   // leader: the peer's weight half is resident
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_pair + 1);
 
     if (ep.m_dev) M = min(M, *ep.m_dev * ep.m_rows);      // device-side row count (rollout encoder cache)
@@ -125,7 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tmem_full[i], 1);
             ptx::mbar_init(&tmem_empty[i], kTcEpiWarps + ((NCTA == 2 && ptx::cluster_ctarank() == 0) ? 1 : 0));
         }
-        for (int i = 0; i < 2 * kTcEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
+        for (int i = 0; i < 3 * kTcEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
         ptx::mbar_init(w_pair, 1);
         ptx::fence_barrier_init();
     }
@@ -216,8 +216,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int half = ew >> 2;
         uint8_t* ebuf = sEpi + (size_t)ew * nebuf * kTcEpiBuf;
-        uint64_t* rb = rbar + ew * 2;
-        uint32_t rphase0 = 0, rphase1 = 0;
+        uint64_t* rb = rbar + ew * 3;
+        uint32_t rphase0 = 0;       // bf16 (MULGRAD) path: phase of rb[0]
+        uint32_t rph = 0;           // fp32 path: bit b = phase of rb[b]
         int nbuf = 0;        // staging buffer the next chunk uses (bf16 path with nebuf == 2 only)
         int t = 0;
         for (int mt = rank; mt < m_tiles; mt += per_slice, ++t) {
@@ -289,18 +290,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // residual chunk into the buffer (8 warps x 4 KB of loads in flight per SM), add in place and TMA-store it back.  The
                 // first chunk's load is issued before the accumulator is ready, so it overlaps the MMAs.
                 const int m = row0 + lane;
-                // nebuf == 2 (CTA pairs: the halved weight slice pays for a second staging buffer per warp): the residual
-                // chunk AFTER the next one is requested as soon as the store of the current chunk has drained its buffer,
-                // so two residual loads per warp (16 per SM pair... 64 KB per SM) are in flight instead of one.
+                // nebuf >= 2 (CTA pairs: the halved weight slice pays for up to three staging buffers per warp): the first
+                // `nebuf` residual chunks of the tile are requested before the accumulator is even ready, and a buffer is
+                // refilled with chunk j + nebuf as soon as the store of chunk j has drained it -- up to 3 x 4 KB of residual
+                // loads in flight per warp (96 KB per SM) instead of 4 KB.
                 const bool dbl = nebuf > 1;
                 if (lane == 0 && (has_res || dbl)) {
                     ptx::bulk_wait_read<0>();
                     if (has_res) {
-                        ptx::mbar_arrive_expect_tx(&rb[0], kTcEpiBuf);
-                        ptx::tma_load_2d(ebuf, &tmR, &rb[0], n0 + half * 32, row0);
-                        if (dbl && half + 2 < BN / 32) {
-                            ptx::mbar_arrive_expect_tx(&rb[1], kTcEpiBuf);
-                            ptx::tma_load_2d(ebuf + kTcEpiBuf, &tmR, &rb[1], n0 + (half + 2) * 32, row0);
+                        for (int b = 0; b < nebuf && half + 2 * b < BN / 32; ++b) {
+                            ptx::mbar_arrive_expect_tx(&rb[b], kTcEpiBuf);
+                            ptx::tma_load_2d(ebuf + b * kTcEpiBuf, &tmR, &rb[b], n0 + (half + 2 * b) * 32, row0);
                         }
                     }
                 }
@@ -311,7 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int ch = half; ch < BN / 32; ch += 2, ++jc) {
                     uint32_t r0[32];
-                    const int bsel = dbl ? (jc & 1) : 0;
+                    const int bsel = dbl ? (jc >= nebuf ? jc - nebuf : jc) : 0;      // jc % nebuf for jc < 2 * nebuf
                     uint8_t* buf = ebuf + bsel * kTcEpiBuf;
                     if (!dbl) {
                         if (lane == 0 && (ch != half || !has_res)) {
@@ -321,15 +321,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 ptx::tma_load_2d(buf, &tmR, &rb[0], n0 + ch * 32, row0);
                             }
                         }
-                    } else if (!has_res && lane == 0 && jc >= 2) {
-                        ptx::bulk_wait_read<1>();           // this buffer's store of two chunks ago has drained
+                    } else if (!has_res && lane == 0 && jc >= nebuf) {
+                        // this buffer's store of `nebuf` chunks ago has drained (the nebuf - 1 newer ones may be pending)
+                        if (nebuf == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<2>();
                     }
                     ptx::tmem_ld_32x32(tm + (uint32_t)(ch * 32), r0);
                     __syncwarp();
-                    if (has_res) {
-                        if (bsel == 0) { ptx::mbar_wait(&rb[0], rphase0); rphase0 ^= 1; }
-                        else { ptx::mbar_wait(&rb[1], rphase1); rphase1 ^= 1; }
-                    }
+                    if (has_res) { ptx::mbar_wait(&rb[bsel], (rph >> bsel) & 1u); rph ^= 1u << bsel; }
                     ptx::tc_wait_ld();
                     const float* bsm = sBias + ch * 32;
                     const int ncol = n0 + ch * 32;
@@ -375,10 +373,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (lane == 0) {
                         ptx::tma_store_2d(&tmC, buf, ncol, row0);
                         ptx::bulk_commit();
-                        if (dbl && has_res && ch + 4 < BN / 32) {
+                        if (dbl && has_res && ch + 2 * nebuf < BN / 32) {
                             ptx::bulk_wait_read<0>();       // the store just issued has drained this buffer: refill it
                             ptx::mbar_arrive_expect_tx(&rb[bsel], kTcEpiBuf);
-                            ptx::tma_load_2d(buf, &tmR, &rb[bsel], n0 + (ch + 4) * 32, row0);
+                            ptx::tma_load_2d(buf, &tmR, &rb[bsel], n0 + (ch + 2 * nebuf) * 32, row0);
                         }
                     }
                 }
@@ -499,7 +497,7 @@ static bool tc_plan(int M, int N, int K, int num_sms, int out_bf16, TcPlan* p) {
     while ((size_t)nkb * (BN / ncta) * 128 > 128 * 1024 && BN > 64 * ncta) BN /= 2;   // keep the resident slice <= 128 KB
     if ((size_t)nkb * (BN / ncta) * 128 > 128 * 1024) return false;
     // pairs: the halved weight slice pays for a second staging buffer per epilogue warp (if >= 3 activation stages remain)
-    int nebuf = ncta == 2 ? 2 : 1;
+    int nebuf = ncta == 2 ? (out_bf16 ? 2 : 3) : 1;
     const size_t budget = 227 * 1024;
     size_t fixed = 0;
     int nstage = 0;

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
                                                                       __nv_bfloat16* __restrict__ dqkv, int n_groups,
                                                                       int S, int inner_sz, int C, int causal, int G,
                                                                       float scale, float scale_log2e) {
+    pdl_trigger();
     constexpr int R = NKB * 8;
     extern __shared__ __align__(128) uint8_t attb_smem[];
     __shared__ long long s_tok[R];

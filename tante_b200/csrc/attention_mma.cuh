@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
                                                                   __nv_bfloat16* __restrict__ out, int n_groups, int S,
                                                                   int inner_sz, int C, int causal, int G,
                                                                   float scale_log2e) {
+    pdl_trigger();
     constexpr int R = NKB * 8;
     extern __shared__ __align__(128) uint8_t att_smem[];
     __shared__ long long s_tok[R];

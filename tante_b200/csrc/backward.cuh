@@ -19,6 +19,7 @@ enum ActKind : int { ACT_GELU_ERF = 2, ACT_GELU_TANH = 3, ACT_RELU = 1 };
 // ---- elementwise: act = f(pre) -------------------------------------------------------------------
 template <typename TA, int ACT>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const TA* __restrict__ pre, TA* __restrict__ out, long long n4) {
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float v[4], o[4];
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(const TA* __restrict__ pre
 // ---- elementwise: g <- g * f'(pre)   (ACT_RELU: `pre` may be the post-ReLU activation) --------------
 template <typename TA, int ACT>
 __global__ void __launch_bounds__(256) act_bwd_kernel(TA* __restrict__ g, const TA* __restrict__ pre, long long n4) {
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float v[4], d[4];
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(256) mse_cf_cl_kernel(const float* __restrict_
 // fp32 -> TA copy (gradient stream -> GEMM operand)
 template <typename TA>
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4) {
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float v[4];
@@ -319,6 +322,7 @@ __global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA
                                                      const float* __restrict__ gamma, float* __restrict__ dxs,
                                                      TA* __restrict__ dxb, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta, long long rows, int C, float eps) {
+    pdl_trigger();
     __shared__ float sg[128 * MAXV * 4], sb[128 * MAXV * 4];
     const int lane = threadIdx.x % kWarp;
     for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }

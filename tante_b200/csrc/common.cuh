@@ -46,6 +46,15 @@ template <> struct Vec4<__nv_bfloat16> {
     }
 };
 
+// Programmatic dependent launch (PDL).  The tcgen05 GEMM / weight-gradient kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: their prologue (barrier init, TMEM allocation, the resident weight
+// slice -- parameters only, never data of a kernel in flight) may run while the PREVIOUS kernel of the stream drains, and they
+// execute griddepcontrol.wait before touching anything that kernel produced.  Every kernel that commonly precedes them calls
+// pdl_trigger() first thing, which allows that early start once all of ITS blocks have been scheduled.  Both instructions are
+// no-ops when the neighbouring launch is an ordinary one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // fp32 runs of 2 or 4 elements (64- / 128-bit accesses)
 template <int N> struct VecN;
 template <> struct VecN<4> {

@@ -94,7 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* w_pair = rbar + 3 * kTcEpiWarps;   // leader: the peer's weight half is resident
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_pair + 1);
 
-    if (ep.m_dev) M = min(M, *ep.m_dev * ep.m_rows);      // device-side row count (rollout encoder cache)
+    pdl_trigger();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int crank = NCTA == 2 ? (int)ptx::cluster_ctarank() : 0;     // rank inside the CTA pair
     const int cid = blockIdx.x / NCTA;                                // cluster (= work unit) index
@@ -102,7 +102,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int slice = cid % n_slices;
     const int rank = cid / n_slices;
     const int per_slice = (gridDim.x / NCTA) / n_slices;
-    const int m_tiles = (M + kTcBlockM * NCTA - 1) / (kTcBlockM * NCTA);   // tiles of 128 rows per CTA of the unit
     const int n0 = slice * BN;
     const bool has_ln = epi == EPI_BIAS_RESID_LN;          // requires BN == N (whole row in this CTA)
     const bool has_res = epi == EPI_BIAS_RESID || has_ln;
@@ -138,13 +137,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Everything above touched parameters only, and so does the resident weight slice the producer requests now.  After that
+    // every thread waits for the previous kernel of the stream (PDL; a no-op for an ordinary launch).
+    if (warp == 0 && lane == 0) {
+        ptx::mbar_arrive_expect_tx(w_full, (uint32_t)nkb * BNC * 128);
+        for (int kb = 0; kb < nkb; ++kb)
+            ptx::tma_load_2d(sW + (size_t)kb * BNC * 128, &tmW, w_full, kb * kTcBlockK, n0 + crank * BNC);
+    }
+    pdl_wait();
+    if (ep.m_dev) M = min(M, *ep.m_dev * ep.m_rows);      // device-side row count (rollout encoder cache)
+    const int m_tiles = (M + kTcBlockM * NCTA - 1) / (kTcBlockM * NCTA);   // tiles of 128 rows per CTA of the unit
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(w_full, (uint32_t)nkb * BNC * 128);
-            for (int kb = 0; kb < nkb; ++kb)
-                ptx::tma_load_2d(sW + (size_t)kb * BNC * 128, &tmW, w_full, kb * kTcBlockK, n0 + crank * BNC);
             int stage = 0;
             uint32_t phase = 0;
             for (int mt = rank; mt < m_tiles; mt += per_slice) {
@@ -533,6 +539,16 @@ static cudaError_t tc_set_attrs() {
     return cudaSuccess;
 }
 
+// Programmatic dependent launch for the tensor-core kernels (common.cuh): not inside stream capture (the rollout graphs keep
+// plain kernel nodes), TANTE_PDL=0 disables it.
+static bool pdl_enabled(cudaStream_t st) {
+    static const bool on = !(getenv("TANTE_PDL") && atoi(getenv("TANTE_PDL")) == 0);
+    if (!on) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return cs == cudaStreamCaptureStatusNone;
+}
+
 static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, void* C,
                                   int ldc, int out_bf16, int M, int N, int K, const EpiParams& ep, int num_sms,
                                   cudaStream_t st) {
@@ -562,23 +578,28 @@ static cudaError_t launch_gemm_tc(int epi, const __nv_bfloat16* A, int lda, cons
         if (!make_tmap_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep.resid, M, N, ep.ldr, 32, 32)) return cudaErrorInvalidValue;
     }
     { cudaError_t e = tc_set_attrs(); if (e != cudaSuccess) return e; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
     if (p.ncta == 2) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)p.grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (p.BN == 256)
-            return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, 2>, tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep);
-        return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, 2>, tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep);
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
     }
-    switch (p.BN) {
-        case 256: gemm_tc_kernel<256, 1><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
-        case 128: gemm_tc_kernel<128, 1><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
-        default: gemm_tc_kernel<64, 1><<<p.grid, kTcThreads, p.smem, st>>>(tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep); break;
+    if (pdl_enabled(st)) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
     }
-    return cudaGetLastError();
+    cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+#define TANTE_TC_LAUNCH(BNv, NC) \
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BNv, NC>, tmA, tmW, tmC, tmR, tmL, M, N, p.nkb, p.nstage, p.nebuf, epi, out_bf16, ep)
+    if (p.ncta == 2) { if (p.BN == 256) TANTE_TC_LAUNCH(256, 2); TANTE_TC_LAUNCH(128, 2); }
+    if (p.BN == 256) TANTE_TC_LAUNCH(256, 1);
+    if (p.BN == 128) TANTE_TC_LAUNCH(128, 1);
+    TANTE_TC_LAUNCH(64, 1);
+#undef TANTE_TC_LAUNCH
 }
 
 }  // namespace tante

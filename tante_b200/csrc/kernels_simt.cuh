@@ -148,6 +148,7 @@ template <typename TOut, int MAXV /* float4 per lane, C <= 128*MAXV */>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, TOut* __restrict__ y,
                                                         int rows, int C, float eps) {
+    pdl_trigger();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     const int lane = threadIdx.x % kWarp;
     if (warp >= rows) return;

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, int m_tiles, int tiles_per_split, int nstage,
                 float* __restrict__ bias_grad, int n_total, const __nv_bfloat16* __restrict__ ones_g) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int kStage = (2 + BN / 64) * kWgBox;
@@ -84,6 +85,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // PDL: barriers / TMEM above needed nothing from the previous kernel; the operands below do
 
     if (ntile > 0) {
         if (warp == 0) {
@@ -243,13 +245,21 @@ static cudaError_t launch_wgrad_tc(const __nv_bfloat16* A, int lda, const __nv_b
     { cudaError_t e = wg_set_attrs(); if (e != cudaSuccess) return e; }
     const __nv_bfloat16* ones = nullptr;
     if (bias_grad) { cudaError_t e = cudaSuccess; ones = wg_ones(&e); if (e != cudaSuccess) return e; }
-    dim3 grid(n_tiles, Kb / BN, splits);
-    switch (BN) {
-        case 256: wgrad_tc_kernel<256><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones); break;
-        case 128: wgrad_tc_kernel<128><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones); break;
-        default: wgrad_tc_kernel<64><<<grid, kWgThreads, smem, st>>>(tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones); break;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles, Kb / BN, splits); cfg.blockDim = dim3(kWgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    int na = 0;
+    if (pdl_enabled(st)) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
     }
-    return cudaGetLastError();
+    cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+    switch (BN) {
+        case 256: return cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<256>, tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones);
+        case 128: return cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<128>, tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones);
+        default: return cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<64>, tmA, tmB, tmC, m_tiles, per, nstage, bias_grad, N, ones);
+    }
 }
 
 }  // namespace tante

@@ -198,7 +198,21 @@ CLASS_NAMES = {0: "gemm_tc_kernel, bf16/activation epilogue (QKV, MLP-in, convs,
                2: "wgrad_tc_kernel (weight gradients)"}
 
 
-def roofline_object(classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, tensor_mode):
+def ncu_traffic(workload, cls):
+    """DRAM bytes of one representative launch of the class from the committed ncu capture (profiles/traffic_*.json)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+            e = d.get(workload, {}).get(str(cls))
+            if e:
+                return e["traffic"], f"{os.path.basename(path)}: {e['kernel']} (algorithmic {e['algorithmic_bytes']} B)"
+        except Exception:
+            pass
+    return None, None
+
+
+def roofline_object(classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, tensor_mode, workload="train"):
     """BASELINE roofline of the dominant kernel family.  The tcgen05 GEMM launches fall into classes with different
     bounds (tante_profile_read_class): the top-level numbers are those of the class with the largest share of the step;
     every class is listed under `classes` (tensor classes in TFLOP/s vs the measured bf16 peak, HBM classes in
@@ -232,8 +246,9 @@ def roofline_object(classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, te
     dom = max(out_cls, key=lambda c: out_cls[c]["ms_per_step"]) if out_cls else None
     top = dict(out_cls[dom]) if dom is not None else {"kernel": "gemm", "bound": "tensor", "achieved": all_tf, "peak": tpeak,
                                                         "unit": "TFLOP/s", "frac": (all_tf / tpeak) if all_tf else None}
+    traffic, traffic_src = ncu_traffic(workload, dom) if dom is not None else (None, None)
     top.update({
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": f"{hsrc}; {tsrc}",
         "all_gemm_launches": int(gemm_n), "all_gemm_ms_per_step": gemm_ms / K_, "all_gemm_share_of_step": gemm_ms / ms_prof,
         "all_gemm_tflops": all_tf, "all_gemm_frac_of_tensor_peak": (all_tf / tpeak) if all_tf else None,
@@ -381,7 +396,7 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / K_},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": roofline_object(prof_classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, tensor_mode),
+        "roofline": roofline_object(prof_classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, tensor_mode, "rollout"),
     }
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_leg(args, args.cpu_seconds, cpu_sd)

@@ -53,9 +53,7 @@ __device__ __forceinline__ float act_grad_rt(int epi, float x) {
         const float du = k * fmaf(3.0f * 0.044715f, x2, 1.0f);
         return fmaf(0.5f * x * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
     }
-    const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752440f), 0.5f);
-    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-    return fmaf(x, pdf, cdf);
+    return gelu_erf_grad_fast(x);
 }
 
 // byte offset of 16-byte chunk `c` of row `r` inside a SWIZZLE_128B staging buffer (1024-B aligned)

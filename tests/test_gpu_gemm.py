@@ -52,8 +52,14 @@ def test_tcgen05_gemm_matches_torch(M, N, K, epi):
     ref = _ref(epi, A, W, bias, resid)
     out = _run(1, epi, A, W, bias, resid, out_bf16=False)
     err = float((out - ref).norm() / ref.norm())
-    assert err < 2e-6, err                     # same bf16 inputs, fp32 accumulate: order-of-summation only
-    assert float((out - ref).abs().max()) < 1e-4
+    if epi == 2:
+        # the tensor-mode GELU is the tanh-form approximant of erf-GELU on tanh.approx (|err| ~ 3e-4 of the value, far below
+        # the bf16 resolution of the activations it produces): bound it, do not demand summation-order agreement
+        assert err < 5e-4, err
+        assert float((out - ref).abs().max()) < 3e-3
+    else:
+        assert err < 2e-6, err                 # same bf16 inputs, fp32 accumulate: order-of-summation only
+        assert float((out - ref).abs().max()) < 1e-4
     if epi != 4:
         outb = _run(1, epi, A, W, bias, resid, out_bf16=True)
         errb = float((outb.float() - ref).norm() / ref.norm())

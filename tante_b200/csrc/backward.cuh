@@ -897,15 +897,36 @@ __global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, Patc
 // order (c, c', d)): the A operand of the forward conv GEMM and the B operand of its weight-gradient GEMM.
 template <typename TA, int VEC>
 __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restrict__ x, PatchGeom g,
-                                                           TA* __restrict__ cols, long long rows_total) {
+                                                           TA* __restrict__ cols, long long rows_total,
+                                                           const int* __restrict__ enc_list = nullptr,
+                                                           const int* __restrict__ enc_count = nullptr,
+                                                           const int* __restrict__ fcount = nullptr) {
     __shared__ __align__(16) float S[kPatchRows * kPatchPitch];
     __shared__ PatchTile pt;
     const long long row0 = (long long)blockIdx.x * kPatchRows;
+    if (enc_list) {
+        // blocks are numbered by compact image: everything past the list leaves before touching shared memory
+        const long long first_img = row0 / ((long long)g.R1 * g.Hp * g.Wp);
+        if (first_img >= *enc_count) return;
+    }
     patch_tile_init(pt, g, row0, rows_total);
     for (int i = threadIdx.x; i < kPatchRows * kPatchPitch; i += blockDim.x) S[i] = 0.f;
     __syncthreads();
+    // Rollout: the image a row block reads is not the one it is numbered after.  `enc_list` (encoder cache): block image e is
+    // the frame in ring slot enc_list[e], images >= *enc_count are not encoded at all; `fcount` (ring window without the
+    // cache): logical frame t of sample b lives in slot (fcount[b] + t) % T.
+    if ((enc_list || fcount) && threadIdx.x < kPatchRows / g.R1) {
+        long long e = pt.img[threadIdx.x];
+        if (e >= 0) {
+            if (enc_list) e = e < *enc_count ? enc_list[e] : -1;
+            else { const long long b = e / g.T; e = b * g.T + (fcount[b] + (int)(e - b * g.T)) % g.T; }
+            pt.img[threadIdx.x] = e;
+        }
+    }
+    if (enc_list || fcount) __syncthreads();
     const size_t HW = (size_t)g.H * g.W;
     const int nitems = (g.D * pt.P * pt.NT) << (pt.lP - (VEC == 4 ? 2 : 1));
+    bool any = false;
     for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
         int tok, d, soff[VEC];
         size_t pix;
@@ -914,8 +935,10 @@ __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restri
         VecN<VEC>::load(x + ((size_t)pt.img[tok] * g.D + d) * HW + pix, v);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) S[soff[e]] = v[e];
+        any = true;
     }
-    __syncthreads();
+    if (!__syncthreads_or(any)) return;          // nothing of this block is encoded (frames past the list)
+    // rows of skipped tokens are written as zeros (harmless: past the GEMM's device-side row count or masked out)
     patch_rows_store<TA>(S, cols, row0, rows_total);
 }
 

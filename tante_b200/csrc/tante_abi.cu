@@ -126,6 +126,7 @@ struct tante_handle_s {
     int64_t arena_elems = 0;
     DevBuf arena, arena_bf16, descs;
     bool packed = false;
+    DevBuf icols;                       // tensor mode: im2col'ed input patches of the first conv, [B*T*L*R1][64] bf16
     DevBuf enc_cache;                   // rollout: encoder output per ring slot, fp32 [B*T*L][C]
     DevBuf enc_state;                   // rollout: [8] count, [B*T] list, [B*T] map
     bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
@@ -517,6 +518,8 @@ void launch_propagator(tante_handle_s* h, const float* xin, float* x, int B, int
     h->launches++;
 }
 
+inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
 template <typename TA>
 void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, float* deriv_dbg, cudaStream_t st) {
     HeadParams hp{};
@@ -582,11 +585,31 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
                             (size_t)WC * g.R1 * C1 * sizeof(TA);
         dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
         const bool cached = io.rollout && rs.enc_count != nullptr;
-        patch_embed_conv1_kernel<TA><<<grid, 128, smem, st>>>(io.input, io.fcount, g, AF(h, h->enc_w[0]),
-                                                              AF(h, h->enc_b[0]), WC, a1, cached ? rs.enc_list : nullptr,
-                                                              cached ? rs.enc_count : nullptr);
-        CK(cudaGetLastError());
-        h->launches++;
+        if constexpr (sizeof(TA) == 2) {
+            // tensor mode: enc_conv_1 as im2col (coalesced tiles, bf16 -- what the reference's autocast feeds its conv) + a
+            // thin tcgen05 GEMM with the GELU in its epilogue; the FFMA kernel below is 64 erf-GELUs + 1024 FMAs per row
+            const long long rows_in = (long long)tokens * g.R1;
+            REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv GEMM");
+            TA* icols = reinterpret_cast<TA*>(h->icols.p);
+            const int* el = cached ? rs.enc_list : nullptr;
+            const int* ec = cached ? rs.enc_count : nullptr;
+            const int* fc = cached ? nullptr : io.fcount;
+            if (P >= 4) conv1_im2col_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(io.input, g, icols, rows_in, el, ec, fc);
+            else conv1_im2col_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(io.input, g, icols, rows_in, el, ec, fc);
+            CK(cudaGetLastError());
+            h->launches++;
+            EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
+            const bool prof = h->prof_on;
+            if (cached) { e1.m_dev = rs.enc_count; e1.m_rows = L * g.R1; h->prof_on = false; }
+            gemm<TA>(h, EPI_BIAS_GELU_ERF, icols, kHeadPad, h->enc_w1pad, a1, C1, false, (int)rows_in, C1, kHeadPad, e1, st);
+            h->prof_on = prof;
+        } else {
+            patch_embed_conv1_kernel<TA><<<grid, 128, smem, st>>>(io.input, io.fcount, g, AF(h, h->enc_w[0]),
+                                                                  AF(h, h->enc_b[0]), WC, a1, cached ? rs.enc_list : nullptr,
+                                                                  cached ? rs.enc_count : nullptr);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
         EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
         if (cached) {
@@ -716,7 +739,6 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
 template <typename TA> inline TA* TP(DevBuf& b) { return reinterpret_cast<TA*>(b.p); }
 inline float* FP(DevBuf& b) { return reinterpret_cast<float*>(b.p); }
 
-inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
 template <typename TA, int ACT>
 void launch_act_fwd(tante_handle_s* h, const TA* pre, TA* out, long long n, cudaStream_t st) {
@@ -1436,7 +1458,7 @@ int tante_destroy(tante_handle_t h) {
         cudaSetDevice(h->device);
         DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
                           &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
-                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state};
+                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
@@ -1569,6 +1591,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         dev_alloc(h, h->att, tokens * C * es);
         dev_alloc(h, h->hid, tokens * C * es);
         dev_alloc(h, h->a1, tokens * g.R1 * C1 * es);
+        if (es == 2) dev_alloc(h, h->icols, tokens * g.R1 * kHeadPad * es);
         dev_alloc(h, h->a2, tokens * g.R2 * C2 * es);
         dev_alloc(h, h->d32, BL * C * 4);
         dev_alloc(h, h->dmod, BL * C * es);

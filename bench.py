@@ -451,7 +451,7 @@ def cpu_train_leg(args, seconds, max_steps=8, state_dict=None):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(list(sd.values()), 1.0)
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     step()                                                  # warm-up
     t0 = time.perf_counter()

@@ -83,7 +83,7 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // tanh.approx and two orders below bf16 resolution), folded into x (z = x / sqrt 2): 8 instructions + one MUFU per element
 // instead of ~20 + two MUFU for the A&S erf + exp form, which made the propagator / patch-embed / activation kernels issue-bound.
 // The odd polynomial is not monotone beyond |x| ~ 8.7 (c < 0), where tanh has long saturated: the argument is clamped.
-__device__ __forceinline__ float tanh_approx_c(float x) {
+__device__ __forceinline__ float tanh_approx_f(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
@@ -92,7 +92,7 @@ constexpr float kGeA = 0.7977190645145112f, kGeB = 0.036797175748107515f, kGeC =
 __device__ __forceinline__ float gelu_erf_fast(float x) {
     const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
     const float x2 = xc * xc;
-    const float t = tanh_approx_c(xc * fmaf(x2, fmaf(x2, kGeC, kGeB), kGeA));
+    const float t = tanh_approx_f(xc * fmaf(x2, fmaf(x2, kGeC, kGeB), kGeA));
     const float hx = 0.5f * x;
     return fmaf(hx, t, hx);
 }
@@ -116,11 +116,6 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 
 // bf16-mode variants of the activations and their derivatives (approximate transcendental units; the errors are far
 // below bf16 resolution).  Selected by the activation element type: float keeps the accurate versions.
-__device__ __forceinline__ float tanh_approx_f(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ float gelu_tanh_fast_f(float x) {
     const float k = 0.79788456080286535588f;
     return 0.5f * x * (1.0f + tanh_approx_f(k * fmaf(0.044715f * x, x * x, x)));
@@ -129,7 +124,7 @@ __device__ __forceinline__ float gelu_tanh_fast_f(float x) {
 __device__ __forceinline__ float gelu_erf_grad_fast(float x) {
     const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
     const float x2 = xc * xc;
-    const float t = tanh_approx_c(xc * fmaf(x2, fmaf(x2, kGeC, kGeB), kGeA));
+    const float t = tanh_approx_f(xc * fmaf(x2, fmaf(x2, kGeC, kGeB), kGeA));
     const float du = fmaf(x2, fmaf(x2, 5.0f * kGeC, 3.0f * kGeB), kGeA);
     return fmaf(0.5f * xc * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }

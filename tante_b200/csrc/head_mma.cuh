@@ -116,6 +116,18 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
     auto item_goff = [&](int item) {
         return (size_t)(item >> (lXQ + lP)) * HW + (size_t)(((item >> lXQ) & (P - 1)) * g.W + ((item & ((1 << lXQ) - 1)) << 2));
     };
+    // few fields (NB <= 2, e.g. the 4-field shapes): the per-item offsets of this thread stay in registers for all tiles
+    constexpr bool kItemRegs = NB <= 2;
+    int soffR[kItemRegs ? NB : 1], goffR[kItemRegs ? NB : 1], xcolR[kItemRegs ? NB : 1];
+    if (kItemRegs) {
+#pragma unroll
+        for (int j = 0; j < (kItemRegs ? NB : 1); ++j) {
+            const int item = tid + 128 * j;
+            soffR[j] = item < nitems ? item_soff(item) : -1;
+            goffR[j] = (int)item_goff(item);
+            xcolR[j] = (item & ((1 << lXQ) - 1)) << 2;
+        }
+    }
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long bh = tile / tpr;
@@ -133,8 +145,11 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
             for (int j = 0; j < NB; ++j) {
                 u0r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int item = tid + 128 * j;
-                if (n > 0 && item < nitems && ((item & ((1 << lXQ) - 1)) << 2) < xvalid)
+                if (kItemRegs) {
+                    if (n > 0 && soffR[j] >= 0 && xcolR[j] < xvalid) u0r[j] = *reinterpret_cast<const float4*>(u0p + goffR[j]);
+                } else if (n > 0 && item < nitems && ((item & ((1 << lXQ) - 1)) << 2) < xvalid) {
                     u0r[j] = *reinterpret_cast<const float4*>(u0p + item_goff(item));
+                }
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -185,12 +200,13 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const int item = tid + 128 * j;
-            if (item >= nitems || ((item & ((1 << lXQ) - 1)) << 2) >= xvalid) continue;
-            const int soff = item_soff(item);
+            if (kItemRegs) { if (soffR[j] < 0 || xcolR[j] >= xvalid) continue; }
+            else if (item >= nitems || ((item & ((1 << lXQ) - 1)) << 2) >= xvalid) continue;
+            const int soff = kItemRegs ? soffR[j] : item_soff(item);
             float4 dk[KORD];
 #pragma unroll
             for (int k = 0; k < KORD; ++k) dk[k] = *reinterpret_cast<const float4*>(sS + k * g.D * PS + soff);
-            const size_t goff = pix0 + item_goff(item);
+            const size_t goff = pix0 + (kItemRegs ? (size_t)goffR[j] : item_goff(item));
             if (hp.deriv_dbg) {
 #pragma unroll
                 for (int k = 0; k < KORD; ++k)

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
             kpos[kb][j] = gp & 255;
         }
 
+    const bool nomask = !causal && G == 1 && rows_valid == R;
 #pragma unroll 1
     for (int qb = 0; qb < R / 16; ++qb) {
         if (qb * 16 >= rows_valid) break;
@@ -136,17 +137,28 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
         const int g0 = gp0 < 0 ? -2 : (gp0 >> 8), p0 = gp0 & 255;
         const int g1 = gp1 < 0 ? -2 : (gp1 >> 8), p1 = gp1 & 255;
         float m0 = -INFINITY, m1 = -INFINITY;
+        if (nomask) {       // one full, non-causal sequence fills the block: every key is visible to every query
 #pragma unroll
-        for (int kb = 0; kb < NKB; ++kb) {
+            for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int kg = kgrp[kb][j], kp = kpos[kb][j];
-                const bool ok0 = kg == g0 && (!causal || kp <= p0);
-                const bool ok1 = kg == g1 && (!causal || kp <= p1);
-                s[kb][j] = ok0 ? s[kb][j] : -INFINITY;
-                s[kb][2 + j] = ok1 ? s[kb][2 + j] : -INFINITY;
-                m0 = fmaxf(m0, s[kb][j]);
-                m1 = fmaxf(m1, s[kb][2 + j]);
+                for (int j = 0; j < 2; ++j) {
+                    m0 = fmaxf(m0, s[kb][j]);
+                    m1 = fmaxf(m1, s[kb][2 + j]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int kg = kgrp[kb][j], kp = kpos[kb][j];
+                    const bool ok0 = kg == g0 && (!causal || kp <= p0);
+                    const bool ok1 = kg == g1 && (!causal || kp <= p1);
+                    s[kb][j] = ok0 ? s[kb][j] : -INFINITY;
+                    s[kb][2 + j] = ok1 ? s[kb][2 + j] : -INFINITY;
+                    m0 = fmaxf(m0, s[kb][j]);
+                    m1 = fmaxf(m1, s[kb][2 + j]);
+                }
             }
         }
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));

@@ -55,6 +55,11 @@ def parse():
     ap.add_argument("--rt-bias", type=float, default=0.0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline legs")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="default line only: skip the rollout / head_sweep sub-records of the default (train) run")
+    ap.add_argument("--amp-mix", action="store_true", help="rollout: per-trajectory input amplitudes (different step sequences)")
+    ap.add_argument("--dropout", type=float, default=0.0, help="train: dropout probability (configs/tante.yaml:29 uses 0.1)")
     a = ap.parse_args()
     if a.shape is None:
         a.shape = "active_matter" if a.workload == "train" else "rayleigh_benard"
@@ -173,7 +178,10 @@ def run_reference(args):
         "impl": "reference", "metric": "rollout_trajectories_per_s", "value": val, "unit": "trajectories/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(args, 1),
+        "config": dict(bench_config(args, 1), reference_arm=(
+            "CPU port (oracle/tante_oracle.py, pinned to the live reference) of R_Evaler.rollout_model, one trajectory per "
+            "step in fp32 as a bounded sample of the b200 arm's 64-trajectory bf16 workload (DESIGN.md 1); the same-GPU "
+            "stock-PyTorch number is the b200 line's gpu_eager_baseline.")),
         "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{steps} single-trajectory rollouts, one per step"},
         "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -206,7 +214,9 @@ def ncu_traffic(workload, cls):
             d = json.load(open(path))
             e = d.get(workload, {}).get(str(cls))
             if e:
-                return e["traffic"], f"{os.path.basename(path)}: {e['kernel']} (algorithmic {e['algorithmic_bytes']} B)"
+                return e["traffic"], (f"static ncu --set full capture committed as profiles/{os.path.basename(path)} "
+                                      f"({d.get('captured', 'round 1u')}; not measured in this run): {e['kernel']} "
+                                      f"(algorithmic {e['algorithmic_bytes']} B)")
         except Exception:
             pass
     return None, None
@@ -261,18 +271,41 @@ def roofline_object(classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, te
     return top
 
 
-def run_b200(args):
+def _dist_helpers(dev, world):
     import torch
     import torch.distributed as dist
-    from tante_b200 import TANTE, TanteMetadata
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+    return barrier, max_over_ranks
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+AMP_MIX = (0.25, 1.0, 2.0, 4.0)      # per-trajectory input amplitudes of the `adaptive` rollout record
+
+
+def rollout_measure(args, dev, world, rank, with_cpu_baseline=True):
+    """BASELINE configs[2]: per-sample adaptive rollout, `args.batch` trajectories per GPU per step.  Returns the JSON
+    record on rank 0 (None elsewhere).  args.rt_bias shifts the interprators' last bias; args.amp_mix scales
+    trajectory i's window by AMP_MIX[i % 4] so that trajectories of one batch take different step sequences."""
+    import torch
+    from tante_b200 import TANTE, TanteMetadata
+    barrier, max_over_ranks = _dist_helpers(dev, world)
     D, H, W = SHAPES[args.shape]
     B, n_roll = args.batch, args.n_roll
 
@@ -288,21 +321,12 @@ def run_b200(args):
     model = model.to(dev).eval()
 
     g = torch.Generator().manual_seed(212 + rank)
-    host_in = torch.randn(B, 4, D, H, W, generator=g).pin_memory()
+    host_in = torch.randn(B, 4, D, H, W, generator=g)
+    if getattr(args, "amp_mix", False):
+        host_in *= torch.tensor([AMP_MIX[i % len(AMP_MIX)] for i in range(B)]).view(B, 1, 1, 1, 1)
+    host_in = host_in.pin_memory()
     host_out = torch.empty(B, n_roll, H, W, D).pin_memory()
     dev_in = host_in.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
 
     W_, K_ = max(args.warmup, 3), max(args.steps, 1)
     with torch.inference_mode():
@@ -310,7 +334,7 @@ def run_b200(args):
             y, rts, ns, steps = model.rollout(dev_in, n_roll, per_sample=True, sync=False)
         barrier()
         # ---- timed region 1: device-resident inputs (value) ----
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(dev.index or 0)
         sampler.start()
         l0 = model.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,7 +347,11 @@ def run_b200(args):
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         launches = model.launch_count() - l0
         clocks = sampler.stop()
-        model_calls = int(steps.max().item())
+        steps_h = steps.tolist()
+        model_calls = int(max(steps_h))
+        if launches and model_calls > 1:
+            # the WHILE-graph body is counted once per rollout by the library (the device decides how often it runs)
+            launches = int(launches + (model_calls - 1) * K_ * (launches // K_ - 2))
 
         # ---- timed region 2: end to end through the public API with host buffers ----
         # Every step copies its pinned HOST window to the device and the whole predicted history back;
@@ -364,32 +392,19 @@ def run_b200(args):
         gemm_ms, gemm_flops, gemm_n = model.profile_read()
         model.profile_gemms(False)
         ms_prof = e4.elapsed_time(e5)
-
+    del model
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+        return None
+    peaks = load_peaks()
     tensor_mode = args.precision == "bf16"
-    if tensor_mode:
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    else:
-        peak = 72.0   # 148 SMs x 128 FFMA x 2 x ~1.9 GHz: fp32 FFMA peak; no measured figure exists for it
-        peak_src = "nominal fp32 FFMA 72 TFLOP/s (no measured fp32 peak in MEASURED_PEAKS.json)"
-    achieved = (gemm_flops / (gemm_ms * 1e-3)) / 1e12 if gemm_ms > 0 else None
     traj = B * world
     line = {
         "metric": "rollout_trajectories_per_s", "value": traj * K_ / (ms_total * 1e-3), "unit": "trajectories/s",
         "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_total / K_, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
         "config": bench_config(args, B),
-        "model_calls_per_trajectory": model_calls,
+        "model_calls_per_trajectory": {"max": model_calls, "min": int(min(steps_h)), "mean": sum(steps_h) / len(steps_h)},
         "frames_per_s": traj * n_roll * K_ / (ms_total * 1e-3),
         "e2e": {"value": traj * K_ / (ms_e2e * 1e-3), "unit": "trajectories/s",
                 "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
@@ -398,12 +413,204 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roofline_object(prof_classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, tensor_mode, "rollout"),
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and with_cpu_baseline and not args.no_cpu_baseline:
         cb, _ = cpu_leg(args, args.cpu_seconds, cpu_sd)
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = rollout_measure(args, dev, world, rank)
+    if rank == 0:
+        if world == 1 and not args.no_eager:
+            try:
+                line["gpu_eager_baseline"] = eager_rollout_leg(args, dev)
+            except Exception as e:   # the eager leg is a reported baseline; never lose the product's line to it
+                line["gpu_eager_baseline"] = {"error": repr(e)[:300]}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# =====================================================================================================
+# gpu_eager_baseline: the reference module's op sequence in stock PyTorch on the same GPU
+# =====================================================================================================
+class _RefCudaFlags:
+    """utils.set_seed_device on CUDA (utils.py:19-34): cudnn.benchmark, TF32 matmuls ("high")."""
+
+    def __enter__(self):
+        import torch
+        self.prev = (torch.backends.cudnn.benchmark, torch.get_float32_matmul_precision())
+        torch.backends.cudnn.benchmark = True
+        torch.set_float32_matmul_precision("high")
+
+    def __exit__(self, *a):
+        import torch
+        torch.backends.cudnn.benchmark = self.prev[0]
+        torch.set_float32_matmul_precision(self.prev[1])
+
+
+def _eager_model(cfg, dev, torch_seed=211, rt_bias=0.0):
+    import torch
+    from oracle.eager_module import EagerTANTE
+    torch.manual_seed(torch_seed)
+    m = EagerTANTE(cfg, dropout=0.0)
+    if rt_bias and not cfg.deg:
+        with torch.no_grad():
+            for ip in m.interprators:
+                ip.interprete[4].bias.add_(rt_bias)
+    return m.to(dev)
+
+
+def eager_rollout_leg(args, dev, steps=3):
+    """R_Evaler.rollout_model around the stock nn.Module (oracle/eager_module.py) on `dev`: inference_mode, bf16
+    autocast, TF32, whole batch per call with sample 0's R_t governing n -- the reference's own GPU path."""
+    import torch
+    from oracle import tante_oracle as O
+    from oracle.eager_module import eager_rollout
+    D, H, W = SHAPES[args.shape]
+    cfg = O.OracleConfig(n_fields=D, H=H, W=W, taylor_order=args.taylor_order, attn_axes=model_axes(args.taylor_order),
+                         deg=False)
+    B, n_roll = args.batch, args.n_roll
+    with _RefCudaFlags():
+        model = _eager_model(cfg, dev, rt_bias=args.rt_bias).eval()
+        g = torch.Generator().manual_seed(212)
+        x = torch.randn(B, 4, D, H, W, generator=g).to(dev)
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(2):
+                eager_rollout(model, x, n_roll)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                eager_rollout(model, x, n_roll)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+    del model, x
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms, "steps": steps,
+            "what": "oracle/eager_module.py (stock torch.nn restatement of the reference module, pinned to the reference "
+                    "goldens) on the same GPU: inference_mode + bf16 autocast + TF32 + cudnn.benchmark (utils.py:19-34), "
+                    f"R_Evaler loop, batch {B}, sample 0's R_t governs n (tante.py:163)"}
+
+
+def eager_train_leg(args, dev, steps=3):
+    """Trainer.train_one_epoch body (trainer.py:178-198) around the stock nn.Module on `dev`: bf16 autocast, TF32,
+    4 chained forwards with BPTT, MSE, backward, clip_grad_norm_(1.0), torch.optim.AdamW(lr 5e-5, wd 1e-5)."""
+    import torch
+    from einops import rearrange
+    from oracle import tante_oracle as O
+    D, H, W = SHAPES[args.shape]
+    cfg = O.OracleConfig(n_fields=D, H=H, W=W, taylor_order=1, attn_axes="THWTHWTHW", deg=True)
+    B, n_out = args.batch, args.n_steps_output
+    with _RefCudaFlags():
+        model = _eager_model(cfg, dev).train()
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-5)
+        g = torch.Generator().manual_seed(212)
+        x = torch.randn(B, 4, D, H, W, generator=g).to(dev)
+        y_ref = torch.randn(B, n_out, H, W, D, generator=g).to(dev)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                moving, ys, cum = x, [], 0
+                while cum < n_out:
+                    y = model(moving)
+                    cum += y.shape[1]
+                    if cum < n_out:
+                        moving = torch.cat([moving[:, y.shape[1]:], y], dim=1)
+                    ys.append(rearrange(y, "b t c h w -> b t h w c"))
+                y_pred = torch.cat(ys, dim=1)[:, :n_out]
+                loss = torch.mean((y_pred - y_ref) ** 2, dim=(-3, -2)).mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+            opt.step()
+            opt.zero_grad()
+            return loss
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        peak_mem = torch.cuda.max_memory_allocated(dev)
+    del model, opt, x, y_ref
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps, "final_loss": float(loss),
+            "peak_memory_bytes": int(peak_mem),
+            "what": "oracle/eager_module.py (stock torch.nn restatement of the reference module, pinned to the reference "
+                    "goldens) on the same GPU: bf16 autocast + TF32 + cudnn.benchmark (utils.py:19-34), Trainer step "
+                    f"(trainer.py:178-198) at batch {B}: {n_out} chained forwards with BPTT, MSE, clip_grad_norm_, AdamW"}
+
+
+# =====================================================================================================
+# head sweep (BASELINE.json configs[4]): K x patch x n of the fused Taylor head vs the measured HBM copy bandwidth
+# =====================================================================================================
+def head_sweep_leg(dev, precision="bf16", full=False):
+    import torch
+    from tante_b200 import TANTE, TanteMetadata
+    peaks = load_peaks()
+    peak = peaks.get("hbm_gbs") or 6650.0
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    cases = []
+    shapes = {"trl": (4, 128, 384, 64), "active_matter": (11, 256, 256, 32)}   # batch: > 2x the 126 MB L2 per launch
+    patches = (2, 4, 8, 16, 32) if full else (4, 8, 16)
+    for sname, (D, H, W, B) in shapes.items():
+        x = torch.randn(B, 4, D, H, W, device=dev)
+        for P in patches:
+            for K in (1, 2, 3, 4):
+                try:
+                    m = TANTE(4, TanteMetadata(spatial_resolution=(H, W), n_fields=D), taylor_order=K,
+                              attn_axes="-".join(["T"] * K), patch_scale=P, deg=False, precision=precision).to(dev).eval()
+                except Exception as e:
+                    cases.append({"shape": sname, "P": P, "K": K, "skipped": str(e)[:100]})
+                    continue
+                k0 = m.patch_kernels[0]
+                for n in (1, 4, 8):
+                    try:
+                        ms = m.bench_head(x, n, iters=10)
+                    except Exception as e:
+                        cases.append({"shape": sname, "P": P, "K": K, "n": n, "skipped": str(e)[:100]})
+                        continue
+                    s_act = 2 if precision == "bf16" else 4
+                    rows = B * H * W // (k0 * k0)
+                    by = rows * K * 64 * s_act + B * D * H * W * 4 * (1 + n)
+                    gbs = by / (ms * 1e-3) / 1e9
+                    cases.append({"shape": sname, "P": P, "K": K, "n": n, "us": 1e3 * ms, "bytes": by, "GBps": gbs,
+                                  "frac": gbs / peak})
+                del m
+        del x
+        torch.cuda.empty_cache()
+    clocks = sampler.stop()
+    ok = [c for c in cases if "frac" in c]
+    per_shape = {}
+    for sname in shapes:
+        fr = [c["frac"] for c in ok if c["shape"] == sname]
+        if fr:
+            worst = min((c for c in ok if c["shape"] == sname), key=lambda c: c["frac"])
+            per_shape[sname] = {"min": min(fr), "mean": sum(fr) / len(fr), "max": max(fr), "cells": len(fr),
+                                "cells_ge_0.70": sum(f >= 0.70 for f in fr),
+                                "worst_cell": {k: worst[k] for k in ("P", "K", "n", "us", "frac")}}
+    return {"what": "stand-alone fused Taylor head (tante_bench_head): last deconv + Horner sum + residual + emit; algorithmic "
+                    "bytes per launch = rows*K*64*s_act + B*D*H*W*4*(1+n) (boundary B of SURVEY.md 8(d)), rows = B*H*W/k0^2",
+            "boundary": "B", "bound": "hbm", "peak": peak, "unit": "GB/s",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+            "patch_scales": list(patches), "K": [1, 2, 3, 4], "n": [1, 4, 8], "per_shape": per_shape, "clocks": clocks,
+            "skipped": [c for c in cases if "skipped" in c][:8], "cases": ok}
 
 
 # =====================================================================================================
@@ -416,7 +623,7 @@ def train_config(args, batch):
             "samples_per_gpu_per_step": batch, "n_steps_output": args.n_steps_output,
             "step": "4 chained forwards with BPTT + MSE + backward + clip_grad_norm_(1.0) + AdamW(lr 5e-5, wd 1e-5)",
             "taylor_order": 1, "attn_axes": "THWTHWTHW", "patch_scale": 8, "embed_dim": 256, "deg": True,
-            "dropout": 0.0, "weights": "random init, torch.manual_seed(211), reference initialisers",
+            "dropout": args.dropout, "weights": "random init, torch.manual_seed(211), reference initialisers",
             "l2_hygiene": "per-step working set (saved activations ~4 GB per model call) >> 126 MB L2; no explicit flush",
             "parallelism": (f"dp{args.gpus}: one NCCL all-reduce of the flat fp32 gradient bucket per step" if args.gpus > 1
                             else "single GPU, no collective")}
@@ -502,7 +709,12 @@ def run_reference_train(args):
         "impl": "reference", "metric": "training_samples_per_s", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": train_config(args, 1),
+        "config": dict(train_config(args, 1), reference_arm=(
+            "CPU port (oracle/tante_oracle.py, pinned to the live reference) of the reference's training step: the reference is "
+            "pure Python with missing dependencies and cannot travel to the GPU box (DESIGN.md 1).  fp32 (the reference's CPU "
+            "path has no autocast), batch 1 per step as a bounded sample of the b200 arm's batch-16 bf16 workload; samples/s is "
+            "per-sample throughput, so the two values are comparable, the configs are not identical by construction.  The "
+            "same-GPU stock-PyTorch number is the b200 line's gpu_eager_baseline.")),
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{steps} training steps of batch 1, one per bench step (the b200 arm does "
                                    f"{args.batch} samples per step)"},
@@ -530,7 +742,7 @@ def run_b200_train(args):
 
     torch.manual_seed(211)                                 # configs/tante.yaml:1 -- identical weights on every rank
     model = TANTE(4, TanteMetadata(spatial_resolution=(H, W), n_fields=D), taylor_order=1, attn_axes="THWTHWTHW",
-                  patch_scale=8, deg=True, dropout=0.0, precision=args.precision)
+                  patch_scale=8, deg=True, dropout=args.dropout, precision=args.precision)
     cpu_sd = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev).train()
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)    # tante.yaml:38-41 (torch's fused kernel)
@@ -612,26 +824,47 @@ def run_b200_train(args):
     model.profile_gemms(False)
     ms_prof = e4.elapsed_time(e5)
 
+    grad_bytes = bucket.flat.numel() * 4
+    # free the training state before the sub-records run in the same process
+    del model, opt, bucket, dev_x, dev_y, pf
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- sub-records: every other BASELINE config, measured in the same driver run --------------------------------
+    extras = {}
+    if not args.no_extras:
+        import copy
+        ra = copy.copy(args)
+        ra.workload, ra.shape, ra.batch, ra.taylor_order = "rollout", "rayleigh_benard", 64, 1
+        ra.steps, ra.warmup = min(args.steps, 10), 3
+        for key, rt_bias, amp in (("rollout", 0.0, False), ("rollout_adaptive", 3.07, True)):
+            ra.rt_bias, ra.amp_mix = rt_bias, amp
+            try:
+                rec = rollout_measure(ra, dev, world, rank, with_cpu_baseline=False)
+            except Exception as e:      # a sub-record must never cost the headline line
+                rec = {"error": repr(e)[:300]}
+            if rank == 0:
+                if world == 1 and not args.no_eager and isinstance(rec, dict) and "error" not in rec:
+                    try:
+                        rec["gpu_eager_baseline"] = eager_rollout_leg(ra, dev)
+                        rec["vs_gpu_eager"] = rec["value"] / rec["gpu_eager_baseline"]["value"]
+                    except Exception as e:
+                        rec["gpu_eager_baseline"] = {"error": repr(e)[:300]}
+                extras[key] = rec
+        if rank == 0 and world == 1:
+            try:
+                extras["head_sweep"] = head_sweep_leg(dev, args.precision)
+            except Exception as e:
+                extras["head_sweep"] = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     tensor_mode = args.precision == "bf16"
-    if tensor_mode:
-        peak = peaks.get("bf16_tflops_sustained") or 1400.0
-        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks
-                    else "fallback 1.4 PFLOP/s sustained (of fallback)")
-    else:
-        peak = 72.0
-        peak_src = "nominal fp32 FFMA 72 TFLOP/s (no measured fp32 peak in MEASURED_PEAKS.json)"
-    achieved = (gemm_flops / (gemm_ms * 1e-3)) / 1e12 if gemm_ms > 0 else None
     samples = B * world
-    grad_bytes = bucket.flat.numel() * 4
     line = {
         "metric": "training_samples_per_s", "value": samples * K_ / (ms_total * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_total / K_, "higher_is_better": True,
@@ -647,6 +880,13 @@ def run_b200_train(args):
         "clocks": clocks,
         "roofline": roofline_object(prof_classes, gemm_ms, gemm_flops, gemm_n, K_, ms_prof, peaks, tensor_mode),
     }
+    if world == 1 and not args.no_eager:
+        try:
+            line["gpu_eager_baseline"] = eager_train_leg(args, dev)
+            line["vs_gpu_eager"] = line["value"] / line["gpu_eager_baseline"]["value"]
+        except Exception as e:
+            line["gpu_eager_baseline"] = {"error": repr(e)[:300]}
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_train_leg(args, args.cpu_seconds, state_dict=cpu_sd)
     print(json.dumps(line), flush=True)

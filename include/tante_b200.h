@@ -180,6 +180,14 @@ TANTE_API int tante_profile_read_class(tante_handle_t h, int32_t cls, double* ms
 TANTE_API int tante_mse_cl(const float* y, const float* ref, int32_t B, int32_t nf, int32_t n_use, int32_t D, int64_t HW,
                  int32_t n_ref, int32_t f0, float scale, const float* gout, float* loss_sum, float* grad_y, void* stream);
 
+/* Evaluation metrics of the rollout drivers (reference trainer/metrics.py:53-164: MSE, NMSE, L2RE, NNMSE, RMSE, NRMSE,
+ * VMSE, VRMSE as called from trainer/r_evaler.py:134-137, trainer/evaler.py:203-206): ONE pass over the channels-last
+ * prediction x and target y = f32[BT, HW, C] producing the three spatial moments every one of those metrics is built from,
+ * out = f64[BT, C, 3] = { sum (x-y)^2, sum y^2, sum y } over HW (written, not accumulated).  No handle: a pure function of
+ * its arguments, launched on `stream` on the device that owns x. */
+TANTE_API int tante_metric_moments(const float* x, const float* y, int64_t BT, int64_t HW, int32_t C, double* out,
+                                   void* stream);
+
 /* Test hook: run one GEMM of the library stand-alone, C[M,N] = epi(A[M,K] * W[N,K]^T + bias).
  * use_tc = 1: tcgen05 bf16 kernel (A, W bf16; C bf16 when out_bf16 else f32);
  * use_tc = 0: FFMA fp32 kernel (A, W, C f32).  epi: 0 bias, 1 +relu, 2 +gelu(erf), 3 +gelu(tanh),

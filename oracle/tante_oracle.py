@@ -423,6 +423,25 @@ def l2re_eval(x, y, eps=1e-7):
     return torch.linalg.vector_norm(xf - yf, dim=1) / (torch.linalg.vector_norm(yf, dim=1) + eps)
 
 
+def nmse_eval(x, y, eps=1e-7, norm_mode="norm"):
+    # NMSE.eval (metrics.py:82-98)
+    if norm_mode == "norm":
+        norm = torch.mean(y ** 2, dim=(-3, -2))
+    else:
+        norm = torch.std(y, dim=(-3, -2)) ** 2
+    return mse_eval(x, y) / (norm + eps)
+
+
+def nnmse_eval(x, y, eps=1e-7):
+    # NNMSE.eval (metrics.py:114-130), norm_mode="norm": normaliser over (H, W, C)
+    return torch.mean(mse_eval(x, y), dim=-1) / (torch.mean(y ** 2, dim=(-3, -2, -1)) + eps)
+
+
+def vrmse_eval(x, y):
+    # VRMSE.eval -> NRMSE.eval(norm_mode="std") -> sqrt(NMSE.eval(norm_mode="std")) (metrics.py:140-164)
+    return torch.sqrt(nmse_eval(x, y, norm_mode="std"))
+
+
 # --------------------------------------------------------------------------
 # deterministic synthetic weights (shared by goldens and parity tests)
 # --------------------------------------------------------------------------

@@ -303,12 +303,11 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
 }
 
 static void attb_set_attrs() {
-    static bool attr = false;
-    if (attr) return;
+    static unsigned long long attr = 0;
+    if (!attrs_needed(attr)) return;
     cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
 }
 
 // Host launcher.  Returns false when the configuration is outside this kernel (caller falls back to the SIMT kernel).

@@ -8,6 +8,17 @@ namespace tante {
 
 constexpr int kWarp = 32;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: every *_set_attrs() keeps one
+// "done" bit per device ordinal (a process may drive several GPUs through one engine each).
+static inline bool attrs_needed(unsigned long long& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 // ---- element conversion -------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -524,16 +524,15 @@ static bool tc_plan(int M, int N, int K, int num_sms, int out_bf16, TcPlan* p) {
 }
 
 static cudaError_t tc_set_attrs() {
-    static bool attr_done = false;
-    if (attr_done) return cudaSuccess;
+    static unsigned long long attr_done = 0;
+    if (!get_encode_tiled()) return cudaErrorNotSupported;
+    if (!attrs_needed(attr_done)) return cudaSuccess;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(gemm_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(gemm_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(gemm_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    if (!get_encode_tiled()) return cudaErrorNotSupported;
-    attr_done = true;
     return cudaSuccess;
 }
 

@@ -284,11 +284,15 @@ static cudaError_t launch_head_mma_inst(const HeadParams& hp, const PatchGeom& g
                         (size_t)(KORD + (hp.ptrs ? 1 : 0)) * g.D * PS * 4;
     const long long tiles = (long long)B * g.Hp * ((g.Wp + NT - 1) / NT);
     static size_t attr_smem = 0, occ_smem = ~(size_t)0;      // per instantiation
-    static int occ_cache = 1;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(taylor_head_mma_kernel<KORD, NB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static int occ_cache = 1, attr_dev = -1;
+    int cur_dev = 0;
+    if (cudaGetDevice(&cur_dev) != cudaSuccess) { (void)cudaGetLastError(); cur_dev = 0; }
+    if (smem > attr_smem || cur_dev != attr_dev) {      // the attribute is per device
+        const size_t want = std::max(smem, attr_smem);
+        cudaError_t e = cudaFuncSetAttribute(taylor_head_mma_kernel<KORD, NB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
         if (e != cudaSuccess) return e;
-        attr_smem = smem;
+        attr_smem = want;
+        attr_dev = cur_dev;
     }
     if (smem != occ_smem) {
         int occ = 1;

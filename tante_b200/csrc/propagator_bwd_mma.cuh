@@ -236,11 +236,10 @@ static cudaError_t launch_propagator_bwd_mma_inst(const float* xin, float* dy, i
                                                   float* gW2, float* gb2, int num_sms, cudaStream_t st) {
     constexpr int SP = MB * 16;
     const size_t smem = (size_t)4 * SP * 256 + (size_t)3 * SP * (SP * 2 + 16) + SP * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;
+    if (attrs_needed(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(propagator_bwd_mma_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     const long long nslab = outer * ((IC + 127) / 128);
     const unsigned grid = (unsigned)std::min<long long>(nslab, (long long)num_sms * (MB == 4 ? 2 : 4));

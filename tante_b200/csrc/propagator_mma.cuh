@@ -134,10 +134,9 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
 }
 
 static void prop_set_attrs() {
-    static bool done = false;
-    if (done) return;
+    static unsigned long long done = 0;
+    if (!attrs_needed(done)) return;
     cudaFuncSetAttribute(propagator_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    done = true;
 }
 
 static bool launch_propagator_mma(const float* xin, float* x, int S, long long IC, long long outer, const float* W1, const float* b1,

@@ -27,6 +27,7 @@
 #include "backward.cuh"
 #include "attention_bwd_mma.cuh"
 #include "wgrad_tc.cuh"
+#include "metrics.cuh"
 
 using namespace tante;
 
@@ -1330,8 +1331,8 @@ void ensure_ready(tante_handle_s* h, int B, bool need_backbone = true) {
 }
 
 void set_smem_attrs() {
-    static bool done = false;
-    if (done) return;
+    static unsigned long long done = 0;
+    if (!attrs_needed(done)) return;
     const int big = 160 * 1024;
     CK(cudaFuncSetAttribute(propagator_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(propagator_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1355,7 +1356,6 @@ void set_smem_attrs() {
     CK(wg_set_attrs());
     att_set_attrs();
     prop_set_attrs();
-    done = true;
 }
 
 void destroy_graphs(tante_handle_s* h);
@@ -1573,7 +1573,7 @@ int tante_pack_params(tante_handle_t h, void* stream) {
 int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t training) {
     return guarded([&] {
         REQUIRE(h && max_batch >= 1, "bad argument");
-        REQUIRE(training >= 0 && training <= 64, "training (tape slots) must be in 0..64");
+        REQUIRE(training >= 0 && training <= 65536, "training (tape slots) must be in 0..65536");
         CK(cudaSetDevice(h->device));
         while ((int)h->tapes.size() < training) h->tapes.emplace_back(new Tape());
         if (max_batch <= h->max_batch && max_roll <= h->max_roll) return;
@@ -1927,12 +1927,34 @@ int tante_mse_cl(const float* y, const float* ref, int32_t B, int32_t nf, int32_
         REQUIRE(loss_sum || grad_y, "nothing to compute");
         const long long total = (long long)B * nf * HW;
         int dev = 0, sms = 148;
+        {   // launch on the device that owns the prediction tensor, whatever the caller's current device is
+            cudaPointerAttributes pa{};
+            if (cudaPointerGetAttributes(&pa, y) == cudaSuccess && pa.type == cudaMemoryTypeDevice) CK(cudaSetDevice(pa.device));
+            else (void)cudaGetLastError();
+        }
         CK(cudaGetDevice(&dev));
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
         const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 16LL * sms);
         mse_cf_cl_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, ref, B, nf, n_use, D, HW, n_ref, f0, scale,
                                                                                  gout, loss_sum, grad_y);
         CK(cudaGetLastError());
+    });
+}
+
+int tante_metric_moments(const float* x, const float* y, int64_t BT, int64_t HW, int32_t C, double* out, void* stream) {
+    return guarded([&] {
+        REQUIRE(x && y && out, "null argument");
+        REQUIRE(C >= 1 && C <= kMetricMaxC, "metric kernels support 1..16 fields");
+        REQUIRE(BT >= 1 && BT <= 65535 && HW >= 1, "bad shape");
+        int dev = 0, sms = 148;
+        {
+            cudaPointerAttributes pa{};
+            if (cudaPointerGetAttributes(&pa, x) == cudaSuccess && pa.type == cudaMemoryTypeDevice) CK(cudaSetDevice(pa.device));
+            else (void)cudaGetLastError();
+        }
+        CK(cudaGetDevice(&dev));
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+        CK(launch_metric_moments(x, y, BT, HW, C, out, sms, reinterpret_cast<cudaStream_t>(stream)));
     });
 }
 

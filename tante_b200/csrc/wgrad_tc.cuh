@@ -186,13 +186,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 static cudaError_t wg_set_attrs() {
-    static bool done = false;
-    if (done) return cudaSuccess;
+    static unsigned long long done = 0;
+    if (!attrs_needed(done)) return cudaSuccess;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(wgrad_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-    done = true;
     return cudaSuccess;
 }
 

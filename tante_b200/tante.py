@@ -215,17 +215,20 @@ class _Engine:
             self.max_roll = max(n_roll, self.max_roll)
             _abi.check(self.lib.tante_reserve(self.handle, self.max_batch, self.max_roll, self.n_slots))
 
-    MAX_SLOTS = 64
-
     def acquire_slot(self) -> int:
-        """Tape slot for one model call in grad mode; released by its backward (or when the autograd node dies)."""
+        """Tape slot for one model call in grad mode; released by its backward (or when the autograd node dies).
+        The pool grows with the number of live model calls (R_Trainer's per-sample BPTT keeps batch_size x n_steps
+        tapes alive until loss.backward(), r_trainer.py:118-133); the only limit is device memory."""
         if not self.free_slots:
-            if self.n_slots >= self.MAX_SLOTS:
-                raise RuntimeError(
-                    f"tante_b200: {self.MAX_SLOTS} taped forwards are alive without a backward; run validation under "
-                    "torch.no_grad()/inference_mode() as the reference trainers do (r_trainer.py:181)")
             self.n_slots += 1
-            _abi.check(self.lib.tante_reserve(self.handle, max(self.max_batch, 1), self.max_roll, self.n_slots))
+            try:
+                _abi.check(self.lib.tante_reserve(self.handle, max(self.max_batch, 1), self.max_roll, self.n_slots))
+            except _abi.TanteError as e:
+                self.n_slots -= 1
+                raise RuntimeError(
+                    f"tante_b200: cannot grow the activation-tape pool beyond {self.n_slots} live model calls ({e.msg}); "
+                    "every model call made in grad mode keeps its tape until its backward runs -- call loss.backward() "
+                    "(or run evaluation under torch.no_grad()/inference_mode(), r_trainer.py:181)") from e
             self.max_batch = max(self.max_batch, 1)
             self.free_slots.append(self.n_slots - 1)
         return self.free_slots.pop()
@@ -373,6 +376,7 @@ class TANTE(nn.Module):
         if float(mlp_ratio) != 1.0:
             raise NotImplementedError("mlp_ratio != 1.0 is not supported yet")
         ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
+        self.patch_kernels = ks
 
         # parameter containers, created in the reference's order (tante.py:85-123)
         self.decoders = nn.ModuleList()

@@ -181,3 +181,273 @@ def train_step(model, optimizer, x, y_ref, n_steps: int = 4, bucket: Optional[Gr
         torch.nn.utils.clip_grad_value_(params, 1.0)
     optimizer.step()
     return loss.detach()
+
+
+# =====================================================================================================
+# Drop-ins for trainer.Trainer / trainer.R_Trainer (configs/tante.yaml:48 `trainer._target_`)
+# =====================================================================================================
+def _wandb_log(logs, step):
+    """wandb.log if a run is active (train.py:68-76 opens it); silently nothing otherwise."""
+    try:
+        import wandb
+        if getattr(wandb, "run", None) is not None:
+            wandb.log(logs, step=step)
+    except Exception:
+        pass
+
+
+class _TrainerBase:
+    """Shared body of the two reference trainers: constructor kwargs, `save_model` / `load_checkpoint` (checkpoint keys
+    incl. the reference's `optimizer_state_dit` spelling, trainer.py:112-137 / r_trainer.py:85-110), `train()` with
+    `recent.pt` every epoch and `best.pt` on improvement (trainer.py:232-255 / r_trainer.py:208-230)."""
+
+    adaptive = False
+
+    def _init_common(self, kw):
+        import logging
+        import os
+        from .rollout import DefaultChannelsFirstFormatter
+        for k, v in kw.items():
+            if k != "self" and not k.startswith("_"):
+                setattr(self, k, v)
+        self._log = logging.getLogger(__name__)
+        self._os = os
+        self.device = torch.device(self.device)
+        self.starting_epoch = 1
+        self.amp_type = torch.bfloat16 if self.amp_type == "bfloat16" else torch.float16
+        self.grad_scaler = torch.GradScaler(self.device.type, enabled=self.enable_amp and self.amp_type != torch.bfloat16)
+        self.best_val_loss = None
+        self.starting_val_loss = float("inf")
+        self.dset_metadata = getattr(getattr(self.datamodule, "train_dataset", None), "metadata", None)
+        if self.formatter != "channels_first_default":
+            raise NotImplementedError("only channels_first_default is wired to the CUDA model")
+        self.formatter = DefaultChannelsFirstFormatter(self.dset_metadata)
+        self._bucket = None
+        if self.checkpoint_path and len(self.checkpoint_path) > 0:
+            self.load_checkpoint(self.checkpoint_path)
+
+    def save_model(self, epoch: int, validation_loss: float, output_path: str):
+        torch.save({"epoch": epoch, "model_state_dict": self.model.state_dict(),
+                    "optimizer_state_dit": self.optimizer.state_dict(), "validation_loss": validation_loss,
+                    "best_validation_loss": self.best_val_loss}, output_path)
+
+    def load_checkpoint(self, checkpoint_path: str):
+        self._log.info(f"Loading checkpoint from {checkpoint_path}")
+        checkpoint = torch.load(checkpoint_path, weights_only=False)
+        if self.model is not None:
+            self.model.load_state_dict(checkpoint["model_state_dict"])
+        if self.optimizer is not None:
+            self.optimizer.load_state_dict(checkpoint["optimizer_state_dit"])
+        self.best_val_loss = checkpoint["best_validation_loss"]
+        self.starting_val_loss = checkpoint["validation_loss"]
+        self.starting_epoch = checkpoint["epoch"] + 1
+        if self.lr_scheduler:
+            for _ in range(self.starting_epoch - 1):
+                self.lr_scheduler.step()
+
+    def _grad_bucket(self):
+        """Data-parallel runs (is_distributed + an initialised process group) all-reduce ONE flat gradient bucket."""
+        if self._bucket is None and self.is_distributed and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size() > 1:
+            self._bucket = GradBucket(self.model)
+        return self._bucket
+
+    def train(self):
+        train_dataloader = self.datamodule.train_dataloader()
+        val_dataloader = self.datamodule.val_dataloader()
+        val_loss = self.starting_val_loss
+        join = self._os.path.join
+        for epoch in range(self.starting_epoch, self.max_epoch + 1):
+            if self.is_distributed and hasattr(getattr(train_dataloader, "sampler", None), "set_epoch"):
+                train_dataloader.sampler.set_epoch(epoch)
+            self._log.info(f"Epoch {epoch}/{self.max_epoch}: starting training")
+            train_loss, train_logs = self.train_one_epoch(epoch, train_dataloader)
+            self._log.info(f"Epoch {epoch}/{self.max_epoch}: avg training loss {train_loss}")
+            _wandb_log(train_logs, epoch)
+            self.save_model(epoch, val_loss, join(self.checkpoint_folder, "recent.pt"))
+            self._log.info(f"Epoch {epoch}/{self.max_epoch}: starting validation")
+            val_loss = self.validation_loop(val_dataloader, epoch=epoch)
+            self._log.info(f"Epoch {epoch}/{self.max_epoch}: avg validation loss {val_loss}")
+            _wandb_log({"valid": val_loss}, epoch)
+            if self.best_val_loss is None or val_loss < self.best_val_loss:
+                self.save_model(epoch, val_loss, join(self.checkpoint_folder, "best.pt"))
+                self.best_val_loss = val_loss
+
+
+class Trainer(_TrainerBase):
+    """Drop-in for trainer.Trainer (trainer.py:72-255): fixed-step model, whole-batch rollout with BPTT,
+    `clip_grad_norm_(1.0)`.  The CViT branch (trainer.py:161-172) belongs to another model."""
+
+    def __init__(self, checkpoint_folder: str = "", formatter: str = "channels_first_default", model=None, datamodule=None,
+                 optimizer=None, train_loss_fn=None, eval_loss_fn=None, max_epoch: int = 1, lr_scheduler=None,
+                 device=torch.device("cuda"), is_distributed: bool = False, enable_amp: bool = False,
+                 amp_type: str = "float16", checkpoint_path: str = "", n_steps_output: int = 1, n_steps_rollout: int = 8,
+                 rt_eps: float = 0.5, rt_n: int = 2, cvit: bool = False, num_query_points: int = 1024):
+        if cvit:
+            raise NotImplementedError("cvit=True selects the CViT query-point rollout (trainer.py:161-172), not TANTE")
+        self._init_common(dict(locals()))
+
+    def rollout_model(self, model, batch, formatter, mode="train"):
+        n_steps = self.n_steps_output if mode == "train" else self.n_steps_rollout
+        moving_batch, y_ref = formatter.process_input(batch)
+        moving_batch = moving_batch[0].to(self.device)
+        if mode != "train" and not torch.is_grad_enabled() and hasattr(model, "rollout"):
+            from .rollout import rollout_eval
+            y, _, _, _ = rollout_eval(model, moving_batch, n_steps)       # device-resident loop
+            return y, y_ref.to(self.device)
+        y_pred_out, _ = _roll(model, moving_batch, n_steps, 1.5)
+        return y_pred_out, y_ref.to(self.device)
+
+    def _fused_mse(self) -> bool:
+        return (type(self.train_loss_fn).__name__ == "MSE" and getattr(self.model, "deg", False)
+                and hasattr(self.model, "grad_layout") and self.device.type == "cuda")
+
+    def train_one_epoch(self, epoch: int, dataloader):
+        import time
+        self.model.train()
+        epoch_loss, train_logs = 0.0, {}
+        start_time = time.time()
+        bucket = self._grad_bucket()
+        for i, batch in enumerate(dataloader):
+            t0 = time.time()
+            with torch.autocast(self.device.type, enabled=self.enable_amp, dtype=self.amp_type):
+                if self._fused_mse():
+                    # MSE(...).mean() straight from the per-call channels-first frames (tante_mse_cl): no permute / cat
+                    moving, y_ref = self.formatter.process_input(batch)
+                    y_ref = y_ref.to(self.device)
+                    frames = _roll_frames(self.model, moving[0].to(self.device), self.n_steps_output)
+                    forward_time = time.time() - t0
+                    loss = mse_loss_frames(frames, y_ref, self.n_steps_output)
+                else:
+                    y_pred, y_ref = self.rollout_model(self.model, batch, self.formatter, "train")
+                    forward_time = time.time() - t0
+                    assert y_ref.shape == y_pred.shape, \
+                        f"Mismatching shapes between reference {y_ref.shape} and prediction {y_pred.shape}"
+                    loss = self.train_loss_fn(y_pred, y_ref, None).mean()
+            if bucket is not None:
+                bucket.zero()
+            self.grad_scaler.scale(loss).backward()
+            if bucket is not None:
+                bucket.all_reduce_mean()
+            self.grad_scaler.unscale_(self.optimizer)
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=1.0)
+            self.grad_scaler.step(self.optimizer)
+            self.grad_scaler.update()
+            if bucket is None:
+                self.optimizer.zero_grad()
+            epoch_loss += loss.item() / len(dataloader)
+            print(f"Epoch {epoch}, Batch {i+1}/{len(dataloader)}: loss {loss.item()}, forward time {forward_time}")
+        train_logs["time_per_train_iter"] = (time.time() - start_time) / len(dataloader)
+        train_logs["train_loss"] = epoch_loss
+        if self.lr_scheduler:
+            self.lr_scheduler.step()
+            train_logs["lr"] = self.lr_scheduler.get_last_lr()[-1]
+        return epoch_loss, train_logs
+
+    @torch.inference_mode()
+    def validation_loop(self, dataloader, epoch: int = 0) -> float:
+        self.model.eval()
+        seq_loss = 0.0
+        with torch.autocast(self.device.type, enabled=self.enable_amp, dtype=self.amp_type):
+            for batch in dataloader:
+                y_pred, y_ref = self.rollout_model(self.model, batch, self.formatter, "eval")
+                assert y_ref.shape == y_pred.shape, \
+                    f"Mismatching shapes between reference {y_ref.shape} and prediction {y_pred.shape}"
+                seq_loss += self.eval_loss_fn(y_pred, y_ref, None).mean().item()
+        validation_loss = seq_loss / len(dataloader)
+        with open(self.checkpoint_folder + "/saved_loss.txt", "a") as f:
+            f.write(str(validation_loss) + "\n")
+        return validation_loss
+
+
+def rt_analyse(rt):
+    """r_trainer.py:35-41."""
+    step = len(rt)
+    return torch.mean(rt).item(), step, (torch.std(rt, unbiased=True).item() if step > 1 else 0)
+
+
+class R_Trainer(_TrainerBase):
+    """Drop-in for trainer.R_Trainer (r_trainer.py:43-231): adaptive model, per-sample B=1 rollouts with out_T = 1.5 and
+    BPTT through the chained calls, MSE + rt penalty, `clip_grad_value_(1.0)`."""
+
+    adaptive = True
+
+    def __init__(self, checkpoint_folder: str = "", formatter: str = "channels_first_default", model=None, datamodule=None,
+                 optimizer=None, train_loss_fn=None, eval_loss_fn=None, max_epoch: int = 1, lr_scheduler=None,
+                 device=torch.device("cuda"), is_distributed: bool = False, enable_amp: bool = False,
+                 amp_type: str = "float16", checkpoint_path: str = "", n_steps_output: int = 4, n_steps_rollout: int = 8,
+                 rt_eps: float = 0.5, rt_n: int = 2):
+        self._init_common(dict(locals()))
+
+    def rollout_model(self, model, batch, formatter, mode="train"):
+        n_steps = self.n_steps_output if mode == "train" else self.n_steps_rollout
+        batch, y_ref = formatter.process_input(batch)
+        batch = batch[0].to(self.device)
+        if mode != "train" and not torch.is_grad_enabled() and hasattr(model, "rollout"):
+            # the per-sample B=1 loops of r_trainer.py:118-129 as ONE device-resident per-sample rollout
+            from .rollout import rollout_eval
+            y, Rts, _, _ = rollout_eval(model, batch, n_steps, out_T=1.5, per_sample=True)
+            return y, y_ref.to(self.device), Rts
+        y_pred_out, Rts = rollout_train(model, batch, n_steps, 1.5)
+        return y_pred_out, y_ref.to(self.device), Rts
+
+    def train_one_epoch(self, epoch: int, dataloader):
+        import time
+        self.model.train()
+        epoch_loss, train_logs = 0.0, {}
+        start_time = time.time()
+        rt_saved, rt_var_saved, steps = [], [], []
+        bucket = self._grad_bucket()
+        for i, batch in enumerate(dataloader):
+            t0 = time.time()
+            with torch.autocast(self.device.type, enabled=self.enable_amp, dtype=self.amp_type):
+                y_pred, y_ref, Rts = self.rollout_model(self.model, batch, self.formatter, "train")
+                forward_time = time.time() - t0
+                assert y_ref.shape == y_pred.shape, \
+                    f"Mismatching shapes between reference {y_ref.shape} and prediction {y_pred.shape}"
+                loss = self.train_loss_fn(y_pred, y_ref, Rts, self.rt_eps, self.rt_n)
+            rt_avg, step, var = rt_analyse(Rts)
+            if bucket is not None:
+                bucket.zero()
+            self.grad_scaler.scale(loss).backward()
+            if bucket is not None:
+                bucket.all_reduce_mean()
+            torch.nn.utils.clip_grad_value_(self.model.parameters(), 1.0)
+            self.grad_scaler.step(self.optimizer)
+            self.grad_scaler.update()
+            if bucket is None:
+                self.optimizer.zero_grad()
+            epoch_loss += loss.item() / len(dataloader)
+            print(f"Epoch {epoch}, Batch {i+1}/{len(dataloader)}: loss {loss.item()}, steps {step/4}, var {var}, "
+                  f"rt {rt_avg}, forward time {forward_time}")
+            rt_saved.append(rt_avg)
+            rt_var_saved.append(var)
+            steps.append(step / 4)
+        train_logs["time_per_train_iter"] = (time.time() - start_time) / len(dataloader)
+        train_logs["train_loss"] = epoch_loss
+        train_logs["rt"] = sum(rt_saved) / len(rt_saved)
+        train_logs["rt_var"] = sum(rt_var_saved) / len(rt_var_saved)
+        train_logs["steps"] = sum(steps) / len(steps)
+        if self.lr_scheduler:
+            self.lr_scheduler.step()
+            train_logs["lr"] = self.lr_scheduler.get_last_lr()[-1]
+        return epoch_loss, train_logs
+
+    @torch.inference_mode()
+    def validation_loop(self, dataloader, epoch: int = 0) -> float:
+        self.model.eval()
+        rt_list, seq_loss = [], 0.0
+        with torch.autocast(self.device.type, enabled=self.enable_amp, dtype=self.amp_type):
+            for batch in dataloader:
+                y_pred, y_ref, Rts = self.rollout_model(self.model, batch, self.formatter, "eval")
+                assert y_ref.shape == y_pred.shape, \
+                    f"Mismatching shapes between reference {y_ref.shape} and prediction {y_pred.shape}"
+                seq_loss += self.eval_loss_fn(y_pred, y_ref, None).mean().item()
+                rt_list += Rts.tolist()
+        validation_loss = seq_loss / len(dataloader)
+        with open(self.checkpoint_folder + "/saved_loss.txt", "a") as f:
+            f.write(str(validation_loss) + "\n")
+        RT = sum(rt_list) / len(rt_list)
+        with open(self.checkpoint_folder + "/saved_rt.txt", "a") as f:
+            f.write(str(RT) + "\n")
+        return validation_loss

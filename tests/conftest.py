@@ -15,6 +15,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not failed) where they cannot run: no CUDA device, or no built library."""
+    reason = None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            reason = "no CUDA device"
+    except Exception as e:  # pragma: no cover
+        reason = f"torch unavailable: {e}"
+    lib = os.path.join(ROOT, "tante_b200", "lib", "libtante_b200.so")
+    if reason is None and not os.path.exists(lib):
+        reason = "tante_b200/lib/libtante_b200.so is not built (python -m tante_b200.build)"
+    if reason is None:
+        return
+    skip = pytest.mark.skip(reason=reason)
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     meta = json.loads(bytes(z["meta_json"]).decode())

@@ -180,6 +180,19 @@ def test_full_size_shapes_vs_oracle_fp32(shape):
 BF16_FIELD_TOL = 2e-2
 
 
+def _prefix_rel(got, golden_flat, n_ref, stride, n_common, frame_axis_per):
+    """rel-L2 on the golden's strided subsample restricted to the first `n_common` frames of every sample.
+    got: (B, n_got, per) tensor; the golden holds flat[::stride] of the (B, n_ref, per) reference tensor."""
+    B, n_got, per = got.shape
+    assert per == frame_axis_per
+    idx = np.arange(0, B * n_ref * per, stride)
+    b, i, r = idx // (n_ref * per), (idx // per) % n_ref, idx % per
+    m = i < n_common
+    assert m.any()
+    g = got.numpy()[b[m], i[m], r[m]]
+    return rel_l2(g, golden_flat[m])
+
+
 @pytest.mark.parametrize("name", ["fwd_deg_k1_p8", "fwd_stages_k2_p8", "fwd_adp_k2_p8_b27", "fwd_adp_k3_p4",
                                   "fwd_adp_k1_p2", "trl_k1_b13", "trl_k2_b52"])
 def test_forward_bf16_matches_reference_golden(name):
@@ -192,14 +205,18 @@ def test_forward_bf16_matches_reference_golden(name):
         y, rt = out
         np.testing.assert_allclose(rt.cpu().numpy(), z["R_t"], rtol=0, atol=5e-2)
     assert abs(y.shape[1] - meta["n"]) <= 1
-    if y.shape[1] == meta["n"]:
-        s = meta["stride"]
-        yc = y.cpu()
-        assert rel_l2(yc.reshape(-1)[::s].numpy(), z["frames"]) < BF16_FIELD_TOL
-        u0 = x[:, -1:].expand_as(yc)
-        d_got = (yc - u0).reshape(-1)[::s].numpy()
-        d_ref = z["frames"] - u0.reshape(-1)[::s].numpy()
-        assert rel_l2(d_got, d_ref) < 5e-2      # derivative-only: bf16 noise floor measured 4.8e-3
+    # unconditional: when the bf16 run emits one frame more or fewer, the common prefix of frames is compared (frame i
+    # of a call does not depend on how many frames follow it, tante.py:165-169)
+    s = meta["stride"]
+    yc = y.cpu()
+    B, n_got = yc.shape[0], yc.shape[1]
+    per = yc[0, 0].numel()
+    n_common = min(n_got, meta["n"])
+    assert _prefix_rel(yc.reshape(B, n_got, per), z["frames"], meta["n"], s, n_common, per) < BF16_FIELD_TOL
+    d_got = (yc - x[:, -1:]).reshape(B, n_got, per)
+    u0_ref = x[:, -1:].expand(B, meta["n"], *x.shape[2:]).reshape(-1)[::s].numpy()
+    # derivative-only: bf16 noise floor measured 4.8e-3
+    assert _prefix_rel(d_got, z["frames"] - u0_ref, meta["n"], s, n_common, per) < 5e-2
 
 
 @pytest.mark.parametrize("name", ["fwd_stages_k2_p8", "trl_k1_b13", "fwd_deg_k1_p8"])
@@ -211,9 +228,50 @@ def test_rollout_bf16_matches_reference_golden(name):
         y, Rts, ns, steps = rollout_eval(model, x.cuda(), n_roll)
     st = int(steps[0])
     assert abs(st - len(z["roll_ns"])) <= 1, "number of rollout steps differs by more than 1"
-    if ns[:st, 0].tolist() == z["roll_ns"].tolist():
-        s = meta["stride"]
-        assert rel_l2(y.cpu().reshape(-1)[::s].numpy(), z["roll_frames"]) < BF16_FIELD_TOL
+    # unconditional: frames are compared up to the first call whose frame count differs from the reference's (the calls
+    # before it saw the same windows; inside it the first min(n) frames are the same Taylor evaluations)
+    got_ns, ref_ns = ns[:st, 0].tolist(), z["roll_ns"].tolist()
+    n_common = 0
+    for a, b in zip(got_ns, ref_ns):
+        n_common += min(a, b)
+        if a != b:
+            break
+    n_common = min(n_common, n_roll)
+    assert n_common >= 1
+    s = meta["stride"]
+    yc = y.cpu()
+    per = yc[0, 0].numel()
+    assert _prefix_rel(yc.reshape(meta["B"], n_roll, per), z["roll_frames"], n_roll, s, n_common, per) < BF16_FIELD_TOL
+
+
+def test_bf16_rollout_at_benchmarked_shape_vs_oracle():
+    """BASELINE configs[2] as bench.py runs it -- Rayleigh-Benard (4 fields, 512x128), K = 1 THWTHWTHW, per-sample adaptive
+    rollout in bf16 -- against the fp32 CPU oracle: every trajectory takes the oracle's number of model calls +-1 and the
+    frames up to the first differing call are within 2e-2 (north_star)."""
+    from gpu_util import make_model
+    from tante_b200 import rollout_eval
+    cfg = O.OracleConfig(n_fields=4, H=512, W=128, taylor_order=1, attn_axes="THWTHWTHW", deg=False)
+    sd = O.make_state_dict(cfg, 211, rt_bias=1.3)
+    B, n_roll = 4, 6
+    x = O.make_input(cfg, B, 212)
+    x = x * torch.tensor([0.25, 1.0, 2.0, 4.0]).view(B, 1, 1, 1, 1)
+    with torch.inference_mode():
+        y_ref, R_ref, ns_ref = O.rollout_per_sample(sd, cfg, x, n_roll, n_roll)
+        model = make_model(cfg, sd, "bf16")
+        y, R, ns, steps = rollout_eval(model, x.cuda(), n_roll, per_sample=True)
+    yc = y.cpu()
+    for b in range(B):
+        got = ns[: int(steps[b]), b].tolist()
+        assert abs(len(got) - len(ns_ref[b])) <= 1, (b, got, ns_ref[b])
+        n_common = 0
+        for a, r in zip(got, ns_ref[b]):
+            n_common += min(a, r)
+            if a != r:
+                break
+        n_common = min(n_common, n_roll)
+        assert n_common >= 1
+        e = float((yc[b, :n_common] - y_ref[b, :n_common]).norm() / y_ref[b, :n_common].norm())
+        assert e < BF16_FIELD_TOL, (b, e, got, ns_ref[b])
 
 
 def test_autocast_selects_bf16_engine():

@@ -114,6 +114,46 @@ def test_training_step_bf16_close_to_reference_golden(name):
     assert rel_l2(x.grad.cpu().reshape(-1)[::s].numpy(), z["grad_input"]) < BF16_GRAD_TOL
 
 
+def test_bf16_training_step_at_benchmarked_shape_vs_oracle():
+    """BASELINE configs[1] as bench.py runs it -- Active Matter (11 fields, 256x256), fixed step, K = 1 THWTHWTHW, four
+    chained model calls with BPTT, MSE -- in bf16 (batch 2) against fp32 autograd over the CPU oracle: loss, predictions and
+    every parameter gradient, the latter against 6e-2 or 3x what the reference's own bf16 autocast deviates by."""
+    from gpu_util import make_model
+    from tante_b200.trainer import mse_loss_frames, _roll_frames
+    cfg = O.OracleConfig(n_fields=11, H=256, W=256, taylor_order=1, attn_axes="THWTHWTHW", deg=True)
+    sd = O.make_state_dict(cfg, 211)
+    B, n_steps = 2, 4
+    x = O.make_input(cfg, B, 212)
+    g = torch.Generator().manual_seed(213)
+    y_ref = torch.randn(B, n_steps, cfg.H, cfg.W, cfg.n_fields, generator=g)
+
+    def oracle(autocast):
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            y, _, _ = O.rollout_eval(sdg, cfg, x, n_steps)
+        loss = O.train_loss(y.float(), y_ref, None)
+        loss.backward()
+        return float(loss), y.detach().float(), sdg
+    loss_ref, yp_ref, sdg = oracle(False)
+    _, _, amp = oracle(True)
+
+    model = make_model(cfg, sd, "bf16").train()
+    frames = _roll_frames(model, x.cuda(), n_steps)
+    loss = mse_loss_frames(frames, y_ref.cuda(), n_steps)
+    loss.backward()
+    assert abs(float(loss) - loss_ref) < 2e-2 * abs(loss_ref)
+    yp = torch.cat([f.detach().permute(0, 1, 3, 4, 2) for f in frames], dim=1).cpu()
+    assert rel_l2(yp.numpy(), yp_ref.numpy()) < 2e-2
+    bad = []
+    for n, p in model.named_parameters():
+        ref = sdg[n].grad
+        e = rel_l2(p.grad.cpu().numpy(), ref.numpy())
+        lim = max(BF16_GRAD_TOL, 3.0 * rel_l2(amp[n].grad.numpy(), ref.numpy()))
+        if e > lim:
+            bad.append(f"{n}: rel {e:.3e} > {lim:.3e}")
+    assert not bad, "bf16 gradients at the benchmarked shape differ from the oracle:\n" + "\n".join(bad)
+
+
 def _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=False):
     """autocast=True: the oracle under torch.autocast(bf16) -- the reference's own amp mode (r_trainer.py:71-74,145);
     its deviation from fp32 is the yardstick for the bf16 tensor mode on cancellation-dominated gradients."""

@@ -102,3 +102,26 @@ def test_training_step_grads_match_reference_golden(name):
         key = "grad::" + name_
         if key in z and gn > 0:
             assert rel_l2(gp.numpy(), z[key]) < 5e-5, name_
+
+
+@pytest.mark.parametrize("name", ["fwd_deg_k1_p8", "fwd_stages_k2_p8", "fwd_adp_k3_p4", "fwd_adp_k1_p2"])
+def test_eager_module_matches_reference_golden(name):
+    """oracle/eager_module.py (the stock-torch nn.Module bench.py times on the GPU as `gpu_eager_baseline`) loads the
+    reference state_dict unchanged and reproduces the reference's frames, R_t and rollout."""
+    from oracle.eager_module import EagerTANTE, eager_rollout
+    z, meta = load_golden(name)
+    cfg = golden_cfg(meta)
+    sd = O.make_state_dict(cfg, meta["seed"], meta["rt_bias"])
+    m = EagerTANTE(cfg).eval()
+    m.load_state_dict(sd, strict=True)
+    x = O.make_input(cfg, meta["B"], meta["input_seed"])
+    with torch.inference_mode():
+        out = m(x, meta["out_T"])
+        y = out if cfg.deg else out[0]
+        if not cfg.deg:
+            np.testing.assert_allclose(out[1].numpy(), z["R_t"], rtol=0, atol=5e-6)
+        yr = eager_rollout(m, x, meta["n_roll"])
+    s = meta["stride"]
+    assert list(y.shape) == meta["frames_shape"]
+    assert rel_l2(y.reshape(-1)[::s].numpy(), z["frames"]) < TOL
+    assert rel_l2(yr.reshape(-1)[::s].numpy(), z["roll_frames"]) < 5e-6

@@ -203,7 +203,8 @@ def bench_config(args, batch):
 
 CLASS_NAMES = {0: "gemm_tc_kernel, bf16/activation epilogue (QKV, MLP-in, convs, input gradients; K=64..768: below the ridge)",
                1: "gemm_tc_kernel, fp32 residual + LayerNorm / embedding epilogue (out-proj, MLP-out, conv3)",
-               2: "wgrad_tc_kernel (weight gradients)"}
+               2: "wgrad_tc_kernel (weight gradients)",
+               3: "block_tail_kernel (out-proj + residual + LN2 + MLP + residual + next LN1 fused: three chained tcgen05 GEMMs)"}
 
 
 def ncu_traffic(workload, cls):
@@ -317,7 +318,6 @@ def rollout_measure(args, dev, world, rank, with_cpu_baseline=True):
         with torch.no_grad():
             for ip in model.interprators:
                 ip.interprete[4].bias.add_(args.rt_bias)
-    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev).eval()
 
     g = torch.Generator().manual_seed(212 + rank)
@@ -327,6 +327,21 @@ def rollout_measure(args, dev, world, rank, with_cpu_baseline=True):
     host_in = host_in.pin_memory()
     host_out = torch.empty(B, n_roll, H, W, D).pin_memory()
     dev_in = host_in.to(dev)
+    calib = None
+    if getattr(args, "amp_mix", False):
+        # Random-init interprators give R_t = 1.0x for every trajectory, so a constant bias only moves all
+        # trajectories together.  Calibrate: shift the bias so that the MEDIAN first-call R_t of this batch sits exactly on an
+        # integer boundary (4.0) -- about half of the trajectories then emit 3 frames per call and half 4, each with its own
+        # step sequence, which is what per-sample adaptive stepping is for.
+        with torch.inference_mode():
+            _, rts0, _, _ = model.rollout(dev_in, n_roll, per_sample=True)
+        r0 = rts0[0].float().cpu()
+        shift = 4.0 - float(r0.median())
+        with torch.no_grad():
+            for ip in model.interprators:
+                ip.interprete[4].bias.add_(shift)
+        calib = {"first_call_Rt_before": [float(r0.min()), float(r0.median()), float(r0.max())], "bias_shift": shift}
+    cpu_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
 
     W_, K_ = max(args.warmup, 3), max(args.steps, 1)
     with torch.inference_mode():
@@ -349,6 +364,7 @@ def rollout_measure(args, dev, world, rank, with_cpu_baseline=True):
         clocks = sampler.stop()
         steps_h = steps.tolist()
         model_calls = int(max(steps_h))
+        ns_first = ns[0].tolist()
         if launches and model_calls > 1:
             # the WHILE-graph body is counted once per rollout by the library (the device decides how often it runs)
             launches = int(launches + (model_calls - 1) * K_ * (launches // K_ - 2))
@@ -405,6 +421,8 @@ def rollout_measure(args, dev, world, rank, with_cpu_baseline=True):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
         "config": bench_config(args, B),
         "model_calls_per_trajectory": {"max": model_calls, "min": int(min(steps_h)), "mean": sum(steps_h) / len(steps_h)},
+        "frames_first_call": {str(k): ns_first.count(k) for k in sorted(set(ns_first))},
+        "adaptive_calibration": calib,
         "frames_per_s": traj * n_roll * K_ / (ms_total * 1e-3),
         "e2e": {"value": traj * K_ / (ms_e2e * 1e-3), "unit": "trajectories/s",
                 "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
@@ -485,9 +503,18 @@ def eager_rollout_leg(args, dev, steps=3):
         model = _eager_model(cfg, dev, rt_bias=args.rt_bias).eval()
         g = torch.Generator().manual_seed(212)
         x = torch.randn(B, 4, D, H, W, generator=g).to(dev)
+        note = ""
         with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
-            for _ in range(2):
+            try:
                 eager_rollout(model, x, n_roll)
+                torch.cuda.synchronize(dev)
+            except RuntimeError as e:
+                # torch 2.11's cuDNN SDPA graph rejects the T-axis layer's 65536 x 8 sequences of length 4; the stock module
+                # then only runs with that backend switched off (flash / memory-efficient / math remain)
+                note = f"; cuDNN SDPA backend disabled after: {str(e)[:80]}"
+                torch.backends.cuda.enable_cudnn_sdp(False)
+                eager_rollout(model, x, n_roll)
+            eager_rollout(model, x, n_roll)
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -501,7 +528,7 @@ def eager_rollout_leg(args, dev, steps=3):
     return {"value": B / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms, "steps": steps,
             "what": "oracle/eager_module.py (stock torch.nn restatement of the reference module, pinned to the reference "
                     "goldens) on the same GPU: inference_mode + bf16 autocast + TF32 + cudnn.benchmark (utils.py:19-34), "
-                    f"R_Evaler loop, batch {B}, sample 0's R_t governs n (tante.py:163)"}
+                    f"R_Evaler loop, batch {B}, sample 0's R_t governs n (tante.py:163)" + note}
 
 
 def eager_train_leg(args, dev, steps=3):
@@ -838,7 +865,7 @@ def run_b200_train(args):
         ra = copy.copy(args)
         ra.workload, ra.shape, ra.batch, ra.taylor_order = "rollout", "rayleigh_benard", 64, 1
         ra.steps, ra.warmup = min(args.steps, 10), 3
-        for key, rt_bias, amp in (("rollout", 0.0, False), ("rollout_adaptive", 3.07, True)):
+        for key, rt_bias, amp in (("rollout", 0.0, False), ("rollout_adaptive", 0.0, True)):
             ra.rt_bias, ra.amp_mix = rt_bias, amp
             try:
                 rec = rollout_measure(ra, dev, world, rank, with_cpu_baseline=False)
@@ -847,6 +874,8 @@ def run_b200_train(args):
             if rank == 0:
                 if world == 1 and not args.no_eager and isinstance(rec, dict) and "error" not in rec:
                     try:
+                        if rec.get("adaptive_calibration"):
+                            ra.rt_bias = rec["adaptive_calibration"]["bias_shift"]     # same weights for the eager module
                         rec["gpu_eager_baseline"] = eager_rollout_leg(ra, dev)
                         rec["vs_gpu_eager"] = rec["value"] / rec["gpu_eager_baseline"]["value"]
                     except Exception as e:

@@ -197,6 +197,15 @@ TANTE_API int tante_test_gemm(int32_t use_tc, int32_t epi, const void* A, const 
                     const float* resid, void* C, int32_t out_bf16, int32_t M, int32_t N, int32_t K,
                     int32_t iters, const float* ln_gamma, const float* ln_beta, void* ln_out, void* stream);
 
+/* Test hook: the fused block tail (block_tail_tc.cuh; reference attn_backbone.py:81-83 + the next layer's LayerNorm) stand-alone:
+ *   x_mid = x_in + att Wo^T + bo;  h = gelu_tanh(LN(x_mid; g2, be2) W1^T + b1);  x_out = x_mid + h W2^T + b2;
+ *   ln_out = LN(x_out; gn, ben)   (skipped when ln_out is NULL).
+ * att bf16[M,256]; Wo, W1, W2 bf16[256,256] (nn.Linear layout); vec7 = f32[7][256] = bo, g2, be2, b1, b2, gn, ben; x_in / x_out
+ * f32[M,256] (may alias).  x_mid (f32) / ln2 / hpre / hact (bf16) all non-NULL select the training variant, which stores them. */
+TANTE_API int tante_test_block_tail(const void* att, const void* Wo, const void* W1, const void* W2, const float* vec7,
+                                    const float* x_in, float* x_out, void* ln_out, float* x_mid, void* ln2, void* hpre,
+                                    void* hact, int32_t M, int32_t iters, void* stream);
+
 /* Test hook: weight-gradient GEMM stand-alone, C[N,K] += A[M,N]^T * B[M,K] (C is accumulated into).
  * use_tc = 1: tcgen05 kernel (bf16 MN-major operands, TMA reduce-add), 2: SIMT kernel on bf16 operands,
  * 0: SIMT kernel on f32 operands.  `bias` (nullable, tcgen05 kernel only): f32[N] += column sums of A. */

@@ -61,6 +61,7 @@ SIGNATURES = {
                                            C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "tante_mse_cl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tante_test_block_tail": (C.c_int, [C.c_void_p] * 12 + [C.c_int32, C.c_int32, C.c_void_p]),
     "tante_metric_moments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "tante_test_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1,0 +1,501 @@
+// Fused "tail" of a TANTE transformer block on tcgen05 (reference models/attn_backbone.py:81-83 + the LayerNorm of the
+// next layer, :68): everything after the attention core of a TransformerBlock in ONE kernel --
+//
+//     x_mid = x + att * Wo^T + bo                          (attention out-projection + residual)
+//     h     = gelu_tanh( LN2(x_mid) * W1^T + b1 )          (MLP in)
+//     x_out = x_mid + h * W2^T + b2                        (MLP out + residual)
+//     ln    = LN1'(x_out)                                  (pre-LN of the NEXT layer, the A operand of its QKV GEMM)
+//
+// The un-fused path runs three GEMM launches for this (gemm_tc_kernel: out-proj + residual + LN2, MLP-in + GELU, MLP-out +
+// residual + LN1') and moves per token 512 + 1024 + 1024 + 512 | 512 + 512 | 512 + 1024 + 1024 + 512 = 7 KB through HBM; here the
+// LN2 output, the hidden activations and x_mid never leave the SM: 512 (att) + 1024 (x) in, 1024 (x) + 512 (ln) out = 3 KB.
+//
+// One CTA per SM, persistent over 128-token tiles.  Per tile three chained MMAs share one TMEM accumulator (256 columns) and
+// one 64 KB shared-memory A tile that is rewritten in place by the epilogue warps between the phases (att -> LN2 -> hidden, all
+// K-major SWIZZLE_128B, exactly the layout TMA would have produced); x_mid lives in the other 256 TMEM columns from the first
+// epilogue to the last.  The three 128 KB weight matrices do not fit next to that, so they STREAM from L2 through a ring of
+// 16 KB stages ([128 rows of N][64 of K]; 24 stages per tile = 384 KB per 128 tokens, L2-resident: 0.4 MB of weights in total).
+// The residual chunks arrive by TMA into per-warp staging buffers (two per warp, the first two requested before the
+// accumulator is ready), results leave by TMA stores from the same buffers.
+// TRAIN = true additionally stores what the backward needs (x_mid, LN2 output, MLP pre-activation, hidden).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two per TMEM lane quarter).
+#pragma once
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace tante {
+
+constexpr int kBtThreads = 64 + 32 * 8;
+constexpr int kBtC = 256;                   // embed_dim the kernel is specialised for
+constexpr int kBtKBlk = 128 * 128;          // one k-block of the A tile: [128 rows][64 bf16] = 16 KB
+constexpr int kBtWStage = 128 * 128;        // one weight stage: [128 rows of N][64 of K] bf16 = 16 KB
+constexpr int kBtWStages = 5;
+constexpr int kBtEbuf = 32 * 128;           // staging buffer: 32 rows x 128 B
+constexpr size_t kBtSmem = 1024 + 4 * kBtKBlk + kBtWStages * kBtWStage + 8 * 2 * kBtEbuf + 7 * kBtC * 4 + 2 * 4 * 2 * 32 * 2 * 4 + 256;
+
+struct BtParams {
+    const float* bo; const float* g2; const float* be2; const float* b1; const float* b2; const float* gn; const float* ben;
+    int M;
+    int has_ln_out;      // 0 for the last layer of a backbone (no next LayerNorm)
+};
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kBtThreads, 1)
+block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWo,
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmXin, const __grid_constant__ CUtensorMap tmXmid,
+                  const __grid_constant__ CUtensorMap tmXout, const __grid_constant__ CUtensorMap tmLn2,
+                  const __grid_constant__ CUtensorMap tmHpre, const __grid_constant__ CUtensorMap tmHact,
+                  const __grid_constant__ CUtensorMap tmLnOut, BtParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                        // [4 k-blocks][128 rows][128 B]
+    uint8_t* sW = sA + 4 * kBtKBlk;                            // [kBtWStages][128 rows][128 B]
+    uint8_t* sE = sW + kBtWStages * kBtWStage;                 // [8 warps][2][4 KB]
+    float* sP = reinterpret_cast<float*>(sE + 8 * 2 * kBtEbuf);    // bo, g2, be2, b1, b2, gn, ben
+    float* sStat = sP + 7 * kBtC;                              // [2 sets][4 quarters][2 halves][32 rows][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 4 * 2 * 32 * 2);
+    uint64_t* w_full = bars;                       // [kBtWStages]
+    uint64_t* w_empty = bars + kBtWStages;         // [kBtWStages]
+    uint64_t* a_full = bars + 2 * kBtWStages;      // att tile landed
+    uint64_t* a_empty = a_full + 1;                // the tile's last MMA has read the A tile
+    uint64_t* a_ready = a_full + 2;                // the epilogue warps rewrote the A tile (8 arrivals)
+    uint64_t* acc_full = a_full + 3;               // one MMA phase finished
+    uint64_t* acc_free = a_full + 4;               // the last epilogue has read the accumulator (8 arrivals)
+    uint64_t* rbar = a_full + 5;                   // [8 warps][2] residual-chunk barriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
+
+    pdl_trigger();
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int tiles = (p.M + 127) / 128;
+
+    for (int i = threadIdx.x; i < kBtC; i += kBtThreads) {
+        sP[i] = p.bo[i]; sP[kBtC + i] = p.g2[i]; sP[2 * kBtC + i] = p.be2[i]; sP[3 * kBtC + i] = p.b1[i];
+        sP[4 * kBtC + i] = p.b2[i];
+        sP[5 * kBtC + i] = p.has_ln_out ? p.gn[i] : 1.f; sP[6 * kBtC + i] = p.has_ln_out ? p.ben[i] : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA); ptx::prefetch_tmap(&tmWo); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
+        ptx::prefetch_tmap(&tmXin); ptx::prefetch_tmap(&tmXout);
+        if (p.has_ln_out) ptx::prefetch_tmap(&tmLnOut);
+        for (int s = 0; s < kBtWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+        ptx::mbar_init(a_full, 1);
+        ptx::mbar_init(a_empty, 1);
+        ptx::mbar_init(a_ready, 8);
+        ptx::mbar_init(acc_full, 1);
+        ptx::mbar_init(acc_free, 8);
+        for (int i = 0; i < 16; ++i) ptx::mbar_init(&rbar[i], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer: the tile's att rows, then its 24 weight stages =====
+        if (lane == 0) {
+            int ws = 0;
+            uint32_t wph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+                ptx::mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(a_full, 4 * kBtKBlk);
+                for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(sA + kb * kBtKBlk, &tmA, a_full, kb * 64, tile * 128);
+                for (int ph = 0; ph < 3; ++ph) {
+                    const CUtensorMap* wm = ph == 0 ? &tmWo : (ph == 1 ? &tmW1 : &tmW2);
+                    for (int kb = 0; kb < 4; ++kb) {
+                        for (int nh = 0; nh < 2; ++nh) {
+                            ptx::mbar_wait(&w_empty[ws], wph ^ 1u);
+                            ptx::mbar_arrive_expect_tx(&w_full[ws], kBtWStage);
+                            ptx::tma_load_2d(sW + ws * kBtWStage, wm, &w_full[ws], kb * 64, nh * 128);
+                            if (++ws == kBtWStages) { ws = 0; wph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: three chained GEMM phases per tile into the one accumulator =====
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+        int ws = 0;
+        uint32_t wph = 0, ar = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            for (int ph = 0; ph < 3; ++ph) {
+                if (ph == 0) {
+                    ptx::mbar_wait(acc_free, (uint32_t)(it & 1) ^ 1u);     // the previous tile's accumulator has been read
+                    ptx::mbar_wait(a_full, (uint32_t)(it & 1));
+                } else {
+                    ptx::mbar_wait(a_ready, ar & 1u);                       // the A tile was rewritten (and acc read) by the epilogue
+                    ++ar;
+                }
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    for (int nh = 0; nh < 2; ++nh) {
+                        ptx::mbar_wait(&w_full[ws], wph);
+                        ptx::tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + kb * kBtKBlk));
+                            const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sW + ws * kBtWStage));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_bf16(tmem_base + (uint32_t)(nh * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                               (kb | k) != 0);
+                            ptx::umma_commit(&w_empty[ws]);
+                        }
+                        __syncwarp();
+                        if (++ws == kBtWStages) { ws = 0; wph ^= 1u; }
+                    }
+                }
+                if (lane == 0) {
+                    ptx::umma_commit(acc_full);
+                    if (ph == 2) ptx::umma_commit(a_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quarter q = warp % 4, thread = one token row =====
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        uint8_t* ebuf = sE + (size_t)ew * 2 * kBtEbuf;
+        uint64_t* rb = rbar + ew * 2;
+        uint32_t rph = 0;             // bit b = phase of rb[b]
+        uint32_t af = 0;              // completed acc_full waits
+        int st_last = -1, st_prev = -1;      // staging buffers of the two most recent TMA-store groups of this warp
+        // a staging buffer may be rewritten once the TMA store that last read it has drained
+        auto buf_free = [&](int b) {
+            if (lane == 0) {
+                if (st_last == b) ptx::bulk_wait_read<0>();
+                else if (st_prev == b) ptx::bulk_wait_read<1>();
+            }
+            __syncwarp();
+        };
+        auto buf_stored = [&](int b) { st_prev = st_last; st_last = b; };
+        const int arow = q * 32 + lane;                 // row inside the A tile
+        const float* bo = sP; const float* g2 = sP + kBtC; const float* be2 = sP + 2 * kBtC; const float* b1 = sP + 3 * kBtC;
+        const float* b2 = sP + 4 * kBtC; const float* gn = sP + 5 * kBtC; const float* ben = sP + 6 * kBtC;
+
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int row0 = tile * 128 + q * 32;
+            const uint32_t tm_acc = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t tm_x = tm_acc + 256u;
+
+            // ---------------- phase 1: x_mid = x + acc + bo ; LN2 -> A tile ----------------
+            buf_free(0); buf_free(1);
+            if (lane == 0) {
+                for (int b = 0; b < 2; ++b) {
+                    ptx::mbar_arrive_expect_tx(&rb[b], kBtEbuf);
+                    ptx::tma_load_2d(ebuf + b * kBtEbuf, &tmXin, &rb[b], (half + 2 * b) * 32, row0);
+                }
+            }
+            st_last = st_prev = -1;
+            ptx::mbar_wait(acc_full, af & 1u); ++af;
+            ptx::tc_fence_after();
+            float rsum = 0.f, rsq = 0.f;
+#pragma unroll 1
+            for (int jc = 0; jc < 4; ++jc) {
+                const int ch = half + 2 * jc;
+                const int b = jc & 1;
+                uint8_t* buf = ebuf + b * kBtEbuf;
+                uint32_t r0[32];
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r0);
+                ptx::mbar_wait(&rb[b], (rph >> b) & 1u); rph ^= 1u << b;
+                ptx::tc_wait_ld();
+                const float* bs = bo + ch * 32;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4* pp = reinterpret_cast<float4*>(buf + sw128_off(lane, c));
+                    const float4 x = *pp;
+                    float4 o;
+                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0] + x.x;
+                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1] + x.y;
+                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2] + x.z;
+                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3] + x.w;
+                    r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
+                    r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
+                    rsum += (o.x + o.y) + (o.z + o.w);
+                    rsq = fmaf(o.x, o.x, rsq); rsq = fmaf(o.y, o.y, rsq); rsq = fmaf(o.z, o.z, rsq); rsq = fmaf(o.w, o.w, rsq);
+                    if (TRAIN) *pp = o;
+                }
+                ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r0);
+                if (TRAIN) {
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { ptx::tma_store_2d(&tmXmid, buf, ch * 32, row0); ptx::bulk_commit(); }
+                    buf_stored(b);
+                } else {
+                    __syncwarp();
+                }
+                if (jc + 2 < 4) {           // refill this buffer with the chunk two steps ahead
+                    if (TRAIN) buf_free(b);
+                    if (lane == 0) {
+                        ptx::mbar_arrive_expect_tx(&rb[b], kBtEbuf);
+                        ptx::tma_load_2d(buf, &tmXin, &rb[b], (ch + 4) * 32, row0);
+                    }
+                    if (TRAIN) { st_last = (st_last == b) ? -1 : st_last; st_prev = (st_prev == b) ? -1 : st_prev; }
+                }
+            }
+            {
+                float* st = sStat + ((q * 2 + half) * 32 + lane) * 2;
+                st[0] = rsum; st[1] = rsq;
+                ptx::tc_wait_st();
+                ptx::tc_fence_before();
+                named_bar_sync(1 + q, 64);          // the partner warp's x_mid chunks (TMEM) and row statistics are complete
+                ptx::tc_fence_after();
+                const float* so = sStat + ((q * 2 + (half ^ 1)) * 32 + lane) * 2;
+                const float mean = (rsum + so[0]) * (1.0f / kBtC);
+                const float var = fmaxf((rsq + so[1]) * (1.0f / kBtC) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll 1
+                for (int jc = 0; jc < 2; ++jc) {
+                    const int ch = half + 2 * jc;              // 64-column chunk = k-block of the A tile
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64), r0);
+                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64 + 32), r1);
+                    if (TRAIN) buf_free(jc);
+                    ptx::tc_wait_ld();
+                    const float* gs = g2 + ch * 64;
+                    const float* bs = be2 + ch * 64;
+                    uint8_t* abase = sA + ch * kBtKBlk;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = c * 8 + j * 2;
+                            const float a = (__uint_as_float(col < 32 ? r0[col] : r1[col - 32]) - mean) * rstd * gs[col] + bs[col];
+                            const float bb = (__uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) - mean) * rstd * gs[col + 1] + bs[col + 1];
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(abase + sw128_off(arow, c)) = v;
+                        if (TRAIN) *reinterpret_cast<uint4*>(ebuf + jc * kBtEbuf + sw128_off(lane, c)) = v;
+                    }
+                    if (TRAIN) {
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) { ptx::tma_store_2d(&tmLn2, ebuf + jc * kBtEbuf, ch * 64, row0); ptx::bulk_commit(); }
+                        buf_stored(jc);
+                    }
+                }
+            }
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a_ready);
+
+            // ---------------- phase 2: hidden = gelu_tanh(acc + b1) -> A tile ----------------
+            ptx::mbar_wait(acc_full, af & 1u); ++af;
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int jc = 0; jc < 2; ++jc) {
+                const int ch = half + 2 * jc;
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 64), r0);
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 64 + 32), r1);
+                if (TRAIN) { buf_free(0); buf_free(1); }
+                ptx::tc_wait_ld();
+                const float* bs = b1 + ch * 64;
+                uint8_t* abase = sA + ch * kBtKBlk;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t pk[4], pp[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = c * 8 + j * 2;
+                        float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bs[col];
+                        float bb = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + bs[col + 1];
+                        if (TRAIN) {
+                            // the backward differentiates the activation at the SAVED (bf16) pre-activation: use it here too
+                            __nv_bfloat162 pr = __floats2bfloat162_rn(a, bb);
+                            pp[j] = *reinterpret_cast<uint32_t*>(&pr);
+                            const float2 f = __bfloat1622float2(pr);
+                            a = f.x; bb = f.y;
+                        }
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(gelu_tanh_fast(a), gelu_tanh_fast(bb));
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(abase + sw128_off(arow, c)) = v;
+                    if (TRAIN) {
+                        *reinterpret_cast<uint4*>(ebuf + sw128_off(lane, c)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+                        *reinterpret_cast<uint4*>(ebuf + kBtEbuf + sw128_off(lane, c)) = v;
+                    }
+                }
+                if (TRAIN) {
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmHpre, ebuf, ch * 64, row0);
+                        ptx::bulk_commit();
+                        ptx::tma_store_2d(&tmHact, ebuf + kBtEbuf, ch * 64, row0);
+                        ptx::bulk_commit();
+                    }
+                    buf_stored(0); buf_stored(1);
+                }
+            }
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(a_ready);
+
+            // ---------------- phase 3: x_out = x_mid + acc + b2 ; LN1' ----------------
+            ptx::mbar_wait(acc_full, af & 1u); ++af;
+            ptx::tc_fence_after();
+            rsum = 0.f; rsq = 0.f;
+#pragma unroll 1
+            for (int jc = 0; jc < 4; ++jc) {
+                const int ch = half + 2 * jc;
+                const int b = jc & 1;
+                uint8_t* buf = ebuf + b * kBtEbuf;
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r0);
+                ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 32), r1);
+                buf_free(b);
+                ptx::tc_wait_ld();
+                const float* bs = b2 + ch * 32;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 o;
+                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0] + __uint_as_float(r1[c * 4 + 0]);
+                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1] + __uint_as_float(r1[c * 4 + 1]);
+                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2] + __uint_as_float(r1[c * 4 + 2]);
+                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3] + __uint_as_float(r1[c * 4 + 3]);
+                    *reinterpret_cast<float4*>(buf + sw128_off(lane, c)) = o;
+                    r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
+                    r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
+                    rsum += (o.x + o.y) + (o.z + o.w);
+                    rsq = fmaf(o.x, o.x, rsq); rsq = fmaf(o.y, o.y, rsq); rsq = fmaf(o.z, o.z, rsq); rsq = fmaf(o.w, o.w, rsq);
+                }
+                if (p.has_ln_out) ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r0);
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { ptx::tma_store_2d(&tmXout, buf, ch * 32, row0); ptx::bulk_commit(); }
+                buf_stored(b);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc_free);          // the next tile's first GEMM may overwrite the accumulator
+            if (p.has_ln_out) {
+                float* st = sStat + 4 * 2 * 32 * 2 + ((q * 2 + half) * 32 + lane) * 2;      // second set
+                st[0] = rsum; st[1] = rsq;
+                ptx::tc_wait_st();
+                ptx::tc_fence_before();
+                named_bar_sync(1 + q, 64);
+                ptx::tc_fence_after();
+                const float* so = sStat + 4 * 2 * 32 * 2 + ((q * 2 + (half ^ 1)) * 32 + lane) * 2;
+                const float mean = (rsum + so[0]) * (1.0f / kBtC);
+                const float var = fmaxf((rsq + so[1]) * (1.0f / kBtC) - mean * mean, 0.f);
+                const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll 1
+                for (int jc = 0; jc < 2; ++jc) {
+                    const int ch = half + 2 * jc;
+                    uint8_t* buf = ebuf + jc * kBtEbuf;
+                    uint32_t r0[32], r1[32];
+                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64), r0);
+                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64 + 32), r1);
+                    buf_free(jc);
+                    ptx::tc_wait_ld();
+                    const float* gs = gn + ch * 64;
+                    const float* bs = ben + ch * 64;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = c * 8 + j * 2;
+                            const float a = (__uint_as_float(col < 32 ? r0[col] : r1[col - 32]) - mean) * rstd * gs[col] + bs[col];
+                            const float bb = (__uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) - mean) * rstd * gs[col + 1] + bs[col + 1];
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        *reinterpret_cast<uint4*>(buf + sw128_off(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { ptx::tma_store_2d(&tmLnOut, buf, ch * 64, row0); ptx::bulk_commit(); }
+                    buf_stored(jc);
+                }
+                // the partner has read this warp's x_out chunks out of TMEM: the next tile may overwrite them with its x_mid
+                ptx::tc_fence_before();
+                named_bar_sync(1 + q, 64);
+                ptx::tc_fence_after();
+            }
+        }
+        if (lane == 0) ptx::bulk_wait_all<0>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+static cudaError_t bt_set_attrs() {
+    static unsigned long long done = 0;
+    if (!get_encode_tiled()) return cudaErrorNotSupported;
+    if (!attrs_needed(done)) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(block_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(block_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+struct BlockTailArgs {
+    const __nv_bfloat16* att;                 // [M][256]
+    const __nv_bfloat16 *Wo, *W1, *W2;        // [256][256] K-major (nn.Linear layout), bf16
+    const float *bo, *g2, *be2, *b1, *b2, *gn, *ben;
+    const float* x_in;                        // fp32 residual stream [M][256]
+    float* x_out;                             // may alias x_in (inference)
+    __nv_bfloat16* ln_out;                    // next layer's LN1 output, null for the last layer
+    // training only
+    float* x_mid = nullptr;
+    __nv_bfloat16 *ln2 = nullptr, *hpre = nullptr, *hact = nullptr;
+};
+
+static cudaError_t launch_block_tail(const BlockTailArgs& a, int M, bool train, int num_sms, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    { cudaError_t e = bt_set_attrs(); if (e != cudaSuccess) return e; }
+    if (train && (!a.x_mid || !a.ln2 || !a.hpre || !a.hact)) return cudaErrorInvalidValue;
+    CUtensorMap tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut;
+    const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    bool ok = make_tmap_2d(&tmA, BF, 2, a.att, M, kBtC, kBtC, 64, 128) &&
+              make_tmap_2d(&tmWo, BF, 2, a.Wo, kBtC, kBtC, kBtC, 64, 128) &&
+              make_tmap_2d(&tmW1, BF, 2, a.W1, kBtC, kBtC, kBtC, 64, 128) &&
+              make_tmap_2d(&tmW2, BF, 2, a.W2, kBtC, kBtC, kBtC, 64, 128) &&
+              make_tmap_2d(&tmXin, F32, 4, a.x_in, M, kBtC, kBtC, 32, 32) &&
+              make_tmap_2d(&tmXout, F32, 4, a.x_out, M, kBtC, kBtC, 32, 32);
+    if (!ok) return cudaErrorInvalidValue;
+    tmXmid = tmXout; tmLn2 = tmA; tmHpre = tmA; tmHact = tmA; tmLnOut = tmA;
+    if (a.ln_out && !make_tmap_2d(&tmLnOut, BF, 2, a.ln_out, M, kBtC, kBtC, 64, 32)) return cudaErrorInvalidValue;
+    if (train) {
+        ok = make_tmap_2d(&tmXmid, F32, 4, a.x_mid, M, kBtC, kBtC, 32, 32) &&
+             make_tmap_2d(&tmLn2, BF, 2, a.ln2, M, kBtC, kBtC, 64, 32) &&
+             make_tmap_2d(&tmHpre, BF, 2, a.hpre, M, kBtC, kBtC, 64, 32) &&
+             make_tmap_2d(&tmHact, BF, 2, a.hact, M, kBtC, kBtC, 64, 32);
+        if (!ok) return cudaErrorInvalidValue;
+    }
+    BtParams p;
+    p.bo = a.bo; p.g2 = a.g2; p.be2 = a.be2; p.b1 = a.b1; p.b2 = a.b2; p.gn = a.gn; p.ben = a.ben;
+    p.M = M; p.has_ln_out = a.ln_out != nullptr;
+    const int tiles = (M + 127) / 128;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min(tiles, num_sms)); cfg.blockDim = dim3(kBtThreads); cfg.dynamicSmemBytes = kBtSmem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    int na = 0;
+    if (pdl_enabled(st)) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+    if (train) return cudaLaunchKernelEx(&cfg, block_tail_kernel<true>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
+    return cudaLaunchKernelEx(&cfg, block_tail_kernel<false>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
+}
+
+}  // namespace tante

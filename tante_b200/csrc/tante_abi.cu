@@ -28,6 +28,7 @@
 #include "attention_bwd_mma.cuh"
 #include "wgrad_tc.cuh"
 #include "metrics.cuh"
+#include "block_tail_tc.cuh"
 
 using namespace tante;
 
@@ -132,6 +133,7 @@ struct tante_handle_s {
     DevBuf enc_state;                   // rollout: [8] count, [B*T] list, [B*T] map
     bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
     bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
+    bool fuse_tail = true;              // tensor mode: out-proj + LN2 + MLP + LN1' of a block as ONE kernel (TANTE_FUSE_TAIL=0: three GEMMs)
 
     // workspace
     int max_batch = 0, max_roll = 0;
@@ -451,6 +453,29 @@ void launch_layernorm(tante_handle_s* h, const float* x, int64_t w, int64_t b, T
     h->launches++;
 }
 
+// Fused tail of a transformer block (block_tail_tc.cuh): out-projection + residual + LN2 + MLP + residual + the next layer's
+// LN1 in one tcgen05 kernel.  `nx` = the next layer of the backbone (null for the last one: no LayerNorm output).
+// Training (x_mid != null) also stores x_mid, the LN2 output, the MLP pre-activation and the hidden activation.
+void launch_tail(tante_handle_s* h, const LayerPlan& lp, const LayerPlan* nx, const __nv_bfloat16* att, const float* x_in,
+                 float* x_out, __nv_bfloat16* ln_out, int tokens, cudaStream_t st, float* x_mid = nullptr,
+                 __nv_bfloat16* ln2 = nullptr, __nv_bfloat16* hpre = nullptr, __nv_bfloat16* hact = nullptr) {
+    const bool train = x_mid != nullptr;
+    const double C = h->C;
+    // class 3: HBM-bound by construction -- att (2C) + x in (4C) + x out (4C) [+ ln out (2C)] per token; training adds
+    // x_mid (4C) and the three saved bf16 activations (6C)
+    ProfScope ps(h, st, 3.0 * 2.0 * tokens * C * C, 3,
+                 (double)tokens * (2 * C + 4 * C + 4 * C + (nx ? 2 * C : 0) + (train ? 4 * C + 6 * C : 0)));
+    BlockTailArgs a;
+    a.att = att;
+    a.Wo = AH(h, lp.outw); a.W1 = AH(h, lp.m0w); a.W2 = AH(h, lp.m2w);
+    a.bo = AF(h, lp.outb); a.g2 = AF(h, lp.ln2w); a.be2 = AF(h, lp.ln2b); a.b1 = AF(h, lp.m0b); a.b2 = AF(h, lp.m2b);
+    a.gn = nx ? AF(h, nx->ln1w) : nullptr; a.ben = nx ? AF(h, nx->ln1b) : nullptr;
+    a.x_in = x_in; a.x_out = x_out; a.ln_out = nx ? ln_out : nullptr;
+    a.x_mid = x_mid; a.ln2 = ln2; a.hpre = hpre; a.hact = hact;
+    CK(launch_block_tail(a, tokens, train, h->num_sms, st));
+    h->launches++;
+}
+
 template <typename TA>
 void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axis, cudaStream_t st) {
     int S, inner, nseq;
@@ -659,6 +684,14 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, qkv, att, B, lp.axis, st);
+            if constexpr (kFuseLN) {
+                if (h->fuse_tail && C == kBtC) {
+                    const LayerPlan* nx = li + 1 < op.layers.size() ? &op.layers[li + 1] : nullptr;
+                    launch_tail(h, lp, nx, att, x, x, ln, tokens, st);
+                    ln_ready = nx != nullptr;
+                    continue;
+                }
+            }
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x; eo.ldr = C;
             if (kFuseLN) {
                 eo.ln_gamma = AF(h, lp.ln2w); eo.ln_beta = AF(h, lp.ln2b); eo.ln_out = ln;
@@ -1067,6 +1100,15 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln1[li]), C, lp.inw, ot.qkv[li].p, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, TP<TA>(ot.qkv[li]), TP<TA>(ot.att[li]), B, lp.axis, st);
+            if constexpr (kTensor) {
+                if (h->fuse_tail && C == kBtC) {
+                    const LayerPlan* nx = li + 1 < nl ? &op.layers[li + 1] : nullptr;
+                    launch_tail(h, lp, nx, TP<TA>(ot.att[li]), x_in, x_out, nx ? TP<TA>(ot.ln1[li + 1]) : nullptr, tokens, st,
+                                x_mid, TP<TA>(ot.ln2[li]), TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]));
+                    ln_ready = nx != nullptr;
+                    continue;
+                }
+            }
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x_in; eo.ldr = C;
             if (kTensor) {
                 eo.ln_gamma = AF(h, lp.ln2w); eo.ln_beta = AF(h, lp.ln2b); eo.ln_out = ot.ln2[li].p;
@@ -1353,6 +1395,7 @@ void set_smem_attrs() {
     ATTBATTR(__nv_bfloat16, 16); ATTBATTR(__nv_bfloat16, 32); ATTBATTR(__nv_bfloat16, 64);
 #undef ATTBATTR
     CK(tc_set_attrs());
+    CK(bt_set_attrs());
     CK(wg_set_attrs());
     att_set_attrs();
     prop_set_attrs();
@@ -1445,6 +1488,7 @@ int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out) {
         build_plan(h.get());
         if (const char* m = getenv("TANTE_ROLLOUT_MODE")) h->rollout_mode = std::max(0, std::min(2, atoi(m)));
         if (const char* m = getenv("TANTE_ENC_CACHE")) h->use_enc_cache = atoi(m) != 0;
+        if (const char* m = getenv("TANTE_FUSE_TAIL")) h->fuse_tail = atoi(m) != 0;
         int sms = 0;   // stays at the B200 default when no device is visible (CPU-side plan checks)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
         else (void)cudaGetLastError();
@@ -1938,6 +1982,28 @@ int tante_mse_cl(const float* y, const float* ref, int32_t B, int32_t nf, int32_
         mse_cf_cl_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, ref, B, nf, n_use, D, HW, n_ref, f0, scale,
                                                                                  gout, loss_sum, grad_y);
         CK(cudaGetLastError());
+    });
+}
+
+int tante_test_block_tail(const void* att, const void* Wo, const void* W1, const void* W2, const float* vec7, const float* x_in,
+                          float* x_out, void* ln_out, float* x_mid, void* ln2, void* hpre, void* hact, int32_t M, int32_t iters,
+                          void* stream) {
+    return guarded([&] {
+        REQUIRE(att && Wo && W1 && W2 && vec7 && x_in && x_out, "null argument");
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BlockTailArgs a;
+        a.att = reinterpret_cast<const __nv_bfloat16*>(att);
+        a.Wo = reinterpret_cast<const __nv_bfloat16*>(Wo); a.W1 = reinterpret_cast<const __nv_bfloat16*>(W1);
+        a.W2 = reinterpret_cast<const __nv_bfloat16*>(W2);
+        a.bo = vec7; a.g2 = vec7 + 256; a.be2 = vec7 + 512; a.b1 = vec7 + 768; a.b2 = vec7 + 1024; a.gn = vec7 + 1280;
+        a.ben = vec7 + 1536;
+        a.x_in = x_in; a.x_out = x_out; a.ln_out = reinterpret_cast<__nv_bfloat16*>(ln_out);
+        a.x_mid = x_mid; a.ln2 = reinterpret_cast<__nv_bfloat16*>(ln2); a.hpre = reinterpret_cast<__nv_bfloat16*>(hpre);
+        a.hact = reinterpret_cast<__nv_bfloat16*>(hact);
+        for (int i = 0; i < std::max(1, iters); ++i) CK(launch_block_tail(a, M, x_mid != nullptr, sms, st));
     });
 }
 

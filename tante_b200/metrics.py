@@ -32,7 +32,12 @@ def spatial_moments(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         return torch.stack([((xd - yd) ** 2).sum(dim=(2, 3)), (yd * yd).sum(dim=(2, 3)), yd.sum(dim=(2, 3))], dim=-1)
     x = x.detach().to(torch.float32).contiguous()
     y = y.detach().to(torch.float32).contiguous()
-    key = (x.data_ptr(), y.data_ptr(), tuple(x.shape), x._version, y._version)
+    def version(t):
+        try:
+            return t._version
+        except RuntimeError:          # inference tensors carry no version counter (immutable outside inference mode)
+            return -1
+    key = (x.data_ptr(), y.data_ptr(), tuple(x.shape), version(x), version(y))
     if _cache["key"] == key:
         return _cache["val"]
     B, T, H, W, C = x.shape

@@ -545,9 +545,10 @@ class TANTE(nn.Module):
 
     def profile_read_classes(self):
         """{class: (ms, flops, bytes, launches)} of the bracketed GEMM launches since profile_gemms(True); call before
-        profile_read().  0 = plain-epilogue GEMMs, 1 = fp32 residual/LayerNorm/embedding epilogues, 2 = weight gradients."""
+        profile_read().  0 = plain-epilogue GEMMs, 1 = fp32 residual/LayerNorm/embedding epilogues, 2 = weight gradients,
+        3 = fused block tail (out-proj + LN2 + MLP + LN1' in one kernel)."""
         out = {}
-        for cls in (0, 1, 2):
+        for cls in (0, 1, 2, 3):
             ms = fl = by = 0.0
             n = 0
             for e in self._engines.values():

@@ -491,44 +491,53 @@ def _eager_model(cfg, dev, torch_seed=211, rt_bias=0.0):
 
 def eager_rollout_leg(args, dev, steps=3):
     """R_Evaler.rollout_model around the stock nn.Module (oracle/eager_module.py) on `dev`: inference_mode, bf16
-    autocast, TF32, whole batch per call with sample 0's R_t governing n -- the reference's own GPU path."""
+    autocast, TF32, whole batch per call with sample 0's R_t governing n -- the reference's own GPU path.  torch 2.11's fused
+    attention kernels refuse the T-axis layer at the product's batch (64 x 1024 sequences x 8 heads of length 4: first the
+    cuDNN graph, then the grid limit of the flash / memory-efficient kernels), so the leg falls back to the largest batch the
+    stock module runs at and reports it -- trajectories/s is a per-trajectory rate either way."""
     import torch
     from oracle import tante_oracle as O
     from oracle.eager_module import eager_rollout
     D, H, W = SHAPES[args.shape]
     cfg = O.OracleConfig(n_fields=D, H=H, W=W, taylor_order=args.taylor_order, attn_axes=model_axes(args.taylor_order),
                          deg=False)
-    B, n_roll = args.batch, args.n_roll
+    n_roll = args.n_roll
+    notes = []
     with _RefCudaFlags():
         model = _eager_model(cfg, dev, rt_bias=args.rt_bias).eval()
         g = torch.Generator().manual_seed(212)
-        x = torch.randn(B, 4, D, H, W, generator=g).to(dev)
-        note = ""
-        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        x_all = torch.randn(args.batch, 4, D, H, W, generator=g).to(dev)
+        B, ms = args.batch, None
+        while B >= 1 and ms is None:
+            x = x_all[:B]
             try:
-                eager_rollout(model, x, n_roll)
-                torch.cuda.synchronize(dev)
+                with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    for _ in range(2):
+                        eager_rollout(model, x, n_roll)
+                    torch.cuda.synchronize(dev)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        eager_rollout(model, x, n_roll)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / steps
             except RuntimeError as e:
-                # torch 2.11's cuDNN SDPA graph rejects the T-axis layer's 65536 x 8 sequences of length 4; the stock module
-                # then only runs with that backend switched off (flash / memory-efficient / math remain)
-                note = f"; cuDNN SDPA backend disabled after: {str(e)[:80]}"
-                torch.backends.cuda.enable_cudnn_sdp(False)
-                eager_rollout(model, x, n_roll)
-            eager_rollout(model, x, n_roll)
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
-                eager_rollout(model, x, n_roll)
-            e1.record()
-            torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / steps
-    del model, x
+                notes.append(f"batch {B}: {str(e).splitlines()[0][:90]}")
+                try:
+                    torch.cuda.synchronize(dev)
+                except RuntimeError:
+                    pass
+                B //= 2
+    del model, x_all
     torch.cuda.empty_cache()
-    return {"value": B / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms, "steps": steps,
+    if ms is None:
+        raise RuntimeError("the stock module did not run at any batch size: " + "; ".join(notes))
+    return {"value": B / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms, "steps": steps, "batch": B,
+            "batches_refused_by_stock_torch": notes,
             "what": "oracle/eager_module.py (stock torch.nn restatement of the reference module, pinned to the reference "
                     "goldens) on the same GPU: inference_mode + bf16 autocast + TF32 + cudnn.benchmark (utils.py:19-34), "
-                    f"R_Evaler loop, batch {B}, sample 0's R_t governs n (tante.py:163)" + note}
+                    f"R_Evaler loop, batch {B}, sample 0's R_t governs n (tante.py:163)"}
 
 
 def eager_train_leg(args, dev, steps=3):

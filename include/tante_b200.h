@@ -136,6 +136,11 @@ TANTE_API int tante_rollout(tante_handle_t h, const float* window, int32_t B, in
  *   grad_params : f32[tante_grad_numel()], written: parameter i's gradient in its state_dict layout
  *                 at tante_param_grad_offset(i) (the caller hands these views to autograd, which
  *                 accumulates into .grad -- so gradient accumulation and BPTT just work). */
+/* Dropout of the NEXT taped forwards (nn.Dropout / nn.MultiheadAttention(dropout=p) inside TransformerBlock,
+ * models/attn_backbone.py:47-57,81-83; p = 0.1 in configs/tante.yaml:29): p = 0 disables it.  `seed` keys the counter-based
+ * mask generator for the call; the host draws a fresh one per model call (torch's generator), the tape remembers it and
+ * tante_backward regenerates the same masks.  tante_forward / tante_rollout never drop (model.eval() semantics). */
+TANTE_API int tante_set_dropout(tante_handle_t h, float p, uint64_t seed);
 TANTE_API int64_t tante_grad_numel(tante_handle_t h);
 TANTE_API int64_t tante_param_grad_offset(tante_handle_t h, int32_t i);
 TANTE_API int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int32_t B, float out_T,

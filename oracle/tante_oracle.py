@@ -202,8 +202,10 @@ def interprator(sd, k: int, d, out_T):
 # --------------------------------------------------------------------------
 # backbone (reference models/attn_backbone.py)
 # --------------------------------------------------------------------------
-def transformer_block(sd, p: str, x, n_head: int, causal: bool):
-    """TransformerBlock.forward (attn_backbone.py:59-83) on (N, S, C) sequences, dropout=0."""
+def transformer_block(sd, p: str, x, n_head: int, causal: bool, drop=None):
+    """TransformerBlock.forward (attn_backbone.py:59-83) on (N, S, C) sequences.  `drop` (train mode, dropout > 0): explicit
+    multipliers {0, 1/(1-p)} -- "attn" (N, heads, S, S) on the softmax probabilities (nn.MultiheadAttention(dropout=p), :47),
+    "res1" / "res2" (N, S, C) on the two residual branches (self.drop, :81-83)."""
     N, S, C = x.shape
     hd = C // n_head
     h = layer_norm(x, sd[p + "ln1.weight"], sd[p + "ln1.bias"])
@@ -216,22 +218,30 @@ def transformer_block(sd, p: str, x, n_head: int, causal: bool):
     if causal:  # causal_mask (attn_backbone.py:35-36): True above the diagonal = masked
         m = torch.triu(torch.ones(S, S, dtype=torch.bool), diagonal=1)
         s = s.masked_fill(m, float("-inf"))
-    a = torch.softmax(s, dim=-1) @ v
+    pr = torch.softmax(s, dim=-1)
+    if drop is not None:
+        pr = pr * drop["attn"]
+    a = pr @ v
     a = a.transpose(1, 2).reshape(N, S, C)
-    x = x + linear(a, sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"])
+    y = linear(a, sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"])
+    x = x + (y if drop is None else y * drop["res1"])
     h = layer_norm(x, sd[p + "ln2.weight"], sd[p + "ln2.bias"])
     h = gelu_tanh(linear(h, sd[p + "mlp.0.weight"], sd[p + "mlp.0.bias"]))
-    return x + linear(h, sd[p + "mlp.2.weight"], sd[p + "mlp.2.bias"])
+    y = linear(h, sd[p + "mlp.2.weight"], sd[p + "mlp.2.bias"])
+    return x + (y if drop is None else y * drop["res2"])
 
 
 def _axis_mlp(sd, p: str, v):
     return linear(gelu_erf(linear(v, sd[p + "0.weight"], sd[p + "0.bias"])), sd[p + "2.weight"], sd[p + "2.bias"])
 
 
-def backbone(sd, cfg: OracleConfig, k: int, axes: str, x):
-    """Attn_Backbone.forward (attn_backbone.py:134-191): x (B,T,Hp,Wp,C)."""
+def backbone(sd, cfg: OracleConfig, k: int, axes: str, x, drop_fn=None):
+    """Attn_Backbone.forward (attn_backbone.py:134-191): x (B,T,Hp,Wp,C).  `drop_fn(k, i, tok)` (tests of the training
+    dropout): returns the explicit dropout multipliers of layer i for sequences whose tokens are `tok` (N, S) -- indices
+    into the (B,T,Hp,Wp) token order -- see transformer_block."""
     B, T, H, W, C = x.shape
     p = f"blocks.{k}."
+    tok_all = torch.arange(B * T * H * W).reshape(B, T, H, W)
     # three residual axis MLPs, h then w then t (:140-146)
     v = x.permute(0, 1, 3, 4, 2)
     x = (v + _axis_mlp(sd, p + "vertical_propagator.", v)).permute(0, 1, 4, 2, 3)
@@ -243,27 +253,33 @@ def backbone(sd, cfg: OracleConfig, k: int, axes: str, x):
         bp = f"{p}blocks.{i}."
         if axis == "T":      # (b h w) t c, causal (:149-152)
             s = x.permute(0, 2, 3, 1, 4).reshape(B * H * W, T, C)
-            s = transformer_block(sd, bp, s, cfg.n_head, True)
+            dr = None if drop_fn is None else drop_fn(k, i, tok_all.permute(0, 2, 3, 1).reshape(B * H * W, T))
+            s = transformer_block(sd, bp, s, cfg.n_head, True, dr)
             x = s.reshape(B, H, W, T, C).permute(0, 3, 1, 2, 4)
         elif axis == "H":    # (b t w) h c (:154-157)
             s = x.permute(0, 1, 3, 2, 4).reshape(B * T * W, H, C)
-            s = transformer_block(sd, bp, s, cfg.n_head, False)
+            dr = None if drop_fn is None else drop_fn(k, i, tok_all.permute(0, 1, 3, 2).reshape(B * T * W, H))
+            s = transformer_block(sd, bp, s, cfg.n_head, False, dr)
             x = s.reshape(B, T, W, H, C).permute(0, 1, 3, 2, 4)
         elif axis == "W":    # (b t h) w c (:159-162)
             s = x.reshape(B * T * H, W, C)
-            s = transformer_block(sd, bp, s, cfg.n_head, False)
+            dr = None if drop_fn is None else drop_fn(k, i, tok_all.reshape(B * T * H, W))
+            s = transformer_block(sd, bp, s, cfg.n_head, False, dr)
             x = s.reshape(B, T, H, W, C)
         elif axis == "L":    # (b t) (h w) c (:164-167)
             s = x.reshape(B * T, H * W, C)
-            s = transformer_block(sd, bp, s, cfg.n_head, False)
+            dr = None if drop_fn is None else drop_fn(k, i, tok_all.reshape(B * T, H * W))
+            s = transformer_block(sd, bp, s, cfg.n_head, False, dr)
             x = s.reshape(B, T, H, W, C)
         elif axis == "Y":    # (b w) (t h) c (:169-172)
             s = x.permute(0, 3, 1, 2, 4).reshape(B * W, T * H, C)
-            s = transformer_block(sd, bp, s, cfg.n_head, False)
+            dr = None if drop_fn is None else drop_fn(k, i, tok_all.permute(0, 3, 1, 2).reshape(B * W, T * H))
+            s = transformer_block(sd, bp, s, cfg.n_head, False, dr)
             x = s.reshape(B, W, T, H, C).permute(0, 2, 3, 1, 4)
         elif axis == "A":    # b (t h w) c (:179-182)
             s = x.reshape(B, T * H * W, C)
-            s = transformer_block(sd, bp, s, cfg.n_head, False)
+            dr = None if drop_fn is None else drop_fn(k, i, tok_all.reshape(B, T * H * W))
+            s = transformer_block(sd, bp, s, cfg.n_head, False, dr)
             x = s.reshape(B, T, H, W, C)
         else:
             raise ValueError(f"axis {axis!r} not covered by the oracle")
@@ -292,7 +308,7 @@ def taylor_coefs(K: int, n: int, fi: float):
 
 
 def forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, inp: torch.Tensor, out_T=1,
-            per_sample: bool = False, return_parts: bool = False):
+            per_sample: bool = False, return_parts: bool = False, drop_fn=None):
     """One TANTE step.
 
     Returns frames (B,n,D,H,W) [and R_t (B,) when deg=False].  With `per_sample=False`
@@ -306,7 +322,7 @@ def forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, inp: torch.Tensor, o
     x = embed(sd, cfg, inp)
     derivs, rts = [], []
     for k, axes in enumerate(cfg.segments):
-        x = backbone(sd, cfg, k, axes, x)
+        x = backbone(sd, cfg, k, axes, x, drop_fn)
         d = x[:, -1]                                               # (B,Hp,Wp,C)
         if not cfg.deg:
             dl = d.reshape(B, -1, d.shape[-1])

@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
                                                                       const __nv_bfloat16* __restrict__ dout,
                                                                       __nv_bfloat16* __restrict__ dqkv, int n_groups,
                                                                       int S, int inner_sz, int C, int causal, int G,
-                                                                      float scale, float scale_log2e) {
+                                                                      float scale, float scale_log2e, DropCfg drop, uint32_t site,
+                                                                      int n_head) {
     pdl_trigger();
     constexpr int R = NKB * 8;
     extern __shared__ __align__(128) uint8_t attb_smem[];
@@ -157,6 +158,21 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+        if (drop.p > 0.f) {
+            // O = (P o Z) V with Z = mask / (1 - p): dP = (dO V^T) o Z; everything below uses the masked dP
+            const int head = hq * 4 + warp;
+            const long long t0 = s_tok[r0], t1 = s_tok[r1];
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+                const uint4 w0 = drop_words(drop, site, drop_attn_grp(t0, n_head, head, cpos[kb][0]));
+                const uint4 w1 = drop_words(drop, site, drop_attn_grp(t1, n_head, head, cpos[kb][0]));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dp[kb][j] *= drop_mul(drop, w0, cpos[kb][j] & 7);
+                    dp[kb][2 + j] *= drop_mul(drop, w1, cpos[kb][j] & 7);
+                }
+            }
+        }
         float D0 = 0.f, D1 = 0.f;
 #pragma unroll
         for (int kb = 0; kb < NKB; ++kb)
@@ -246,10 +262,17 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
                 const bool ok1 = qg == g1 && (!causal || p1 <= qp);
                 const float pt0 = ok0 ? exp2f((s[qb][j] - m) * scale_log2e) * il : 0.f;
                 const float pt1 = ok1 ? exp2f((s[qb][2 + j] - m) * scale_log2e) * il : 0.f;
-                s[qb][j] = pt0;
-                s[qb][2 + j] = pt1;
-                dp[qb][j] = ok0 ? pt0 * (dp[qb][j] - D) * scale : 0.f;           // dS^T (stats of padding queries are unset)
-                dp[qb][2 + j] = ok1 ? pt1 * (dp[qb][2 + j] - D) * scale : 0.f;
+                float z0 = 1.f, z1 = 1.f;
+                if (drop.p > 0.f) {       // Z of (query = this column, key = rows r0 / r1)
+                    const long long tq = s_tok[col];
+                    const int head = hq * 4 + warp;
+                    z0 = drop_mul(drop, drop_words(drop, site, drop_attn_grp(tq, n_head, head, p0)), p0 & 7);
+                    z1 = drop_mul(drop, drop_words(drop, site, drop_attn_grp(tq, n_head, head, p1)), p1 & 7);
+                }
+                s[qb][j] = pt0 * z0;                                              // (P o Z)^T: dV = (P o Z)^T dO
+                s[qb][2 + j] = pt1 * z1;
+                dp[qb][j] = ok0 ? pt0 * (dp[qb][j] * z0 - D) * scale : 0.f;       // dS^T (stats of padding queries are unset)
+                dp[qb][2 + j] = ok1 ? pt1 * (dp[qb][2 + j] * z1 - D) * scale : 0.f;
             }
         float ov[4][4], ok_[4][4];
 #pragma unroll
@@ -313,7 +336,7 @@ static void attb_set_attrs() {
 // Host launcher.  Returns false when the configuration is outside this kernel (caller falls back to the SIMT kernel).
 static bool launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat16* dout, __nv_bfloat16* dqkv,
                                      long long n_groups, int S, int inner_sz, int n_head, int C, int head_dim, int causal,
-                                     cudaStream_t st, cudaError_t* err) {
+                                     cudaStream_t st, cudaError_t* err, const DropCfg& drop = DropCfg(), uint32_t site = 0) {
     if (head_dim != 32 || n_head % 4 != 0 || S > 64 || S < 1) return false;
     const int G = S <= 16 ? 16 / S : 1;
     const int R = S <= 16 ? 16 : ((S + 15) / 16) * 16;
@@ -325,10 +348,10 @@ static bool launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat
     const float sl2 = scale * 1.4426950408889634f;
     attb_set_attrs();
     switch (R) {
-        case 16: axial_attention_bwd_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2); break;
-        case 32: axial_attention_bwd_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2); break;
-        case 48: axial_attention_bwd_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2); break;
-        default: axial_attention_bwd_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2); break;
+        case 16: axial_attention_bwd_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        case 32: axial_attention_bwd_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        case 48: axial_attention_bwd_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        default: axial_attention_bwd_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
     }
     *err = cudaGetLastError();
     return true;

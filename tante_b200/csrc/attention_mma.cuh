@@ -42,7 +42,7 @@ template <int NKB /* R_pad / 8 */>
 __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                   __nv_bfloat16* __restrict__ out, int n_groups, int S,
                                                                   int inner_sz, int C, int causal, int G,
-                                                                  float scale_log2e) {
+                                                                  float scale_log2e, DropCfg drop, uint32_t site, int n_head) {
     pdl_trigger();
     constexpr int R = NKB * 8;
     extern __shared__ __align__(128) uint8_t att_smem[];
@@ -178,6 +178,22 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        if (drop.p > 0.f) {
+            // training: dropout on the (normalised) probabilities -- the normaliser above saw every key.  The two keys this
+            // lane holds in a block are lanes (kpos & 7), (kpos & 7) + 1 of one Philox group of (query token, head)
+            const int head = hq * 4 + warp;
+            const long long t0 = s_tok[r0], t1 = s_tok[r1];
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+                const uint4 w0 = drop_words(drop, site, drop_attn_grp(t0, n_head, head, kpos[kb][0]));
+                const uint4 w1 = drop_words(drop, site, drop_attn_grp(t1, n_head, head, kpos[kb][0]));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    s[kb][j] *= drop_mul(drop, w0, kpos[kb][j] & 7);
+                    s[kb][2 + j] *= drop_mul(drop, w1, kpos[kb][j] & 7);
+                }
+            }
+        }
         // ---- O = P V ----
         float o[4][4];
 #pragma unroll
@@ -225,7 +241,8 @@ static void att_set_attrs() {
 
 // Host launcher.  Returns false when the configuration is outside this kernel (caller falls back).
 static bool launch_attention_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, long long n_groups, int S, int inner_sz,
-                                 int n_head, int C, int head_dim, int causal, cudaStream_t st, cudaError_t* err) {
+                                 int n_head, int C, int head_dim, int causal, cudaStream_t st, cudaError_t* err,
+                                 const DropCfg& drop = DropCfg(), uint32_t site = 0) {
     if (head_dim != 32 || n_head % 4 != 0 || S > 64 || S < 1) return false;
     const int G = S <= 16 ? 16 / S : 1;
     const int R = S <= 16 ? 16 : ((S + 15) / 16) * 16;
@@ -236,10 +253,10 @@ static bool launch_attention_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, l
     const float sl2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
     att_set_attrs();
     switch (R) {
-        case 16: axial_attention_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
-        case 32: axial_attention_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
-        case 48: axial_attention_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
-        default: axial_attention_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2); break;
+        case 16: axial_attention_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        case 32: axial_attention_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        case 48: axial_attention_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        default: axial_attention_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
     }
     *err = cudaGetLastError();
     return true;

@@ -92,12 +92,19 @@ __global__ void __launch_bounds__(256) mse_cf_cl_kernel(const float* __restrict_
 
 // fp32 -> TA copy (gradient stream -> GEMM operand)
 template <typename TA>
-__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4) {
+__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4,
+                                                      DropCfg drop = DropCfg(), uint32_t site = 0) {
     pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float v[4];
     Vec4<float>::load(src + i * 4, v);
+    if (drop.p > 0.f) {
+        // the copy is the dY operand of a residual BRANCH whose output went through dropout: dY = dx o mask / (1 - p)
+        const uint4 w = drop_words(drop, site, (unsigned long long)(i >> 1));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] *= drop_mul(drop, w, (int)((i & 1) * 4 + j));
+    }
     Vec4<TA>::store(dst + i * 4, v);
 }
 
@@ -321,7 +328,8 @@ template <typename TA, int MAXV>
 __global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ gamma, float* __restrict__ dxs,
                                                      TA* __restrict__ dxb, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, long long rows, int C, float eps) {
+                                                     float* __restrict__ dbeta, long long rows, int C, float eps,
+                                                     DropCfg drop = DropCfg(), uint32_t site = 0) {
     pdl_trigger();
     __shared__ float sg[128 * MAXV * 4], sb[128 * MAXV * 4];
     const int lane = threadIdx.x % kWarp;
@@ -401,7 +409,16 @@ __global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA
 #pragma unroll
                     for (int j = 0; j < 4; ++j) ov[u][i][j] += rstd * (dv[u][i][j] - s1 - xv[u][i][j] * s2);
                     Vec4<float>::store(dxs + (size_t)rr[u] * C + c, ov[u][i]);
-                    if (dxb) Vec4<TA>::store(dxb + (size_t)rr[u] * C + c, ov[u][i]);
+                    if (dxb) {
+                        if (drop.p > 0.f) {
+                            // the copy feeds the gradients of the residual branch below (its output went through dropout)
+                            const unsigned long long e = (unsigned long long)rr[u] * C + c;
+                            const uint4 w = drop_words(drop, site, e >> 3);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ov[u][i][j] *= drop_mul(drop, w, (int)(e & 7) + j);
+                        }
+                        Vec4<TA>::store(dxb + (size_t)rr[u] * C + c, ov[u][i]);
+                    }
                 }
             }
         }
@@ -425,7 +442,8 @@ __global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA
 template <typename TA, int HD>
 __global__ void __launch_bounds__(128) attention_bwd_kernel(const TA* __restrict__ qkv, const TA* __restrict__ dout,
                                                             TA* __restrict__ dqkv, long long n_seq, int S, int inner_sz,
-                                                            int n_head, int C, int causal, float scale, int G) {
+                                                            int n_head, int C, int causal, float scale, int G,
+                                                            DropCfg drop = DropCfg(), uint32_t site = 0) {
     extern __shared__ float smem[];
     constexpr int P = HD + 1;
     const int R = G * S;
@@ -471,6 +489,16 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const TA* __restrict
         }
         s *= scale;
         if (causal && j > (r % S)) s = -INFINITY;
+        if (drop.p > 0.f) {
+            // dP = (dO V^T) o Z with Z = mask / (1 - p) of (query token, head, key position), as the forward drew it
+            const long long seq = seq0 + r / S;
+            if (seq < n_seq) {
+                const long long outer = seq / inner_sz, inner = seq % inner_sz;
+                const long long tokq = outer * S * inner_sz + (long long)(r % S) * inner_sz + inner;
+                const uint4 w = drop_words(drop, site, drop_attn_grp(tokq, n_head, head, j));
+                dp *= drop_mul(drop, w, j & 7);
+            }
+        }
         sP[r * SP + j] = s;
         sD[r * SP + j] = dp;
     }
@@ -495,7 +523,16 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const TA* __restrict
         for (int j = 0; j < S; ++j) {
             const float ds_rj = sD[r * SP + j];             // dS[r][j]
             const float ds_jr = sD[(g0 + j) * SP + p];      // dS[j][r]
-            const float p_jr = sP[(g0 + j) * SP + p];       // P[j][r]
+            float p_jr = sP[(g0 + j) * SP + p];             // P[j][r] (o Z[j][r] with dropout: dV = (P o Z)^T dO)
+            if (drop.p > 0.f) {
+                const long long seqj = seq0 + r / S;
+                if (seqj < n_seq) {
+                    const long long outer = seqj / inner_sz, inner = seqj % inner_sz;
+                    const long long tokq = outer * S * inner_sz + (long long)j * inner_sz + inner;
+                    const uint4 w = drop_words(drop, site, drop_attn_grp(tokq, n_head, head, p));
+                    p_jr *= drop_mul(drop, w, p & 7);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 dq[e] = fmaf(ds_rj, sK[(g0 + j) * P + d4 + e], dq[e]);

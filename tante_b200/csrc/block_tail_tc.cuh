@@ -38,6 +38,8 @@ struct BtParams {
     const float* bo; const float* g2; const float* be2; const float* b1; const float* b2; const float* gn; const float* ben;
     int M;
     int has_ln_out;      // 0 for the last layer of a backbone (no next LayerNorm)
+    DropCfg drop;        // training with dropout (attn_backbone.py:81-83): both residual branches are masked
+    uint32_t site1, site2;
 };
 
 template <bool TRAIN>
@@ -208,15 +210,24 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ptx::mbar_wait(&rb[b], (rph >> b) & 1u); rph ^= 1u << b;
                 ptx::tc_wait_ld();
                 const float* bs = bo + ch * 32;
+                const bool dropping = TRAIN && p.drop.p > 0.f;
+                uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4* pp = reinterpret_cast<float4*>(buf + sw128_off(lane, c));
                     const float4 x = *pp;
                     float4 o;
-                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0] + x.x;
-                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1] + x.y;
-                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2] + x.z;
-                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3] + x.w;
+                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0];
+                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1];
+                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2];
+                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3];
+                    if (dropping) {       // x + drop(attention branch): 8 consecutive columns share one Philox group
+                        if ((c & 1) == 0) dw = drop_words(p.drop, p.site1, (unsigned long long)(row0 + lane) * (kBtC / 8) + ch * 4 + (c >> 1));
+                        const int l0 = (c & 1) * 4;
+                        o.x *= drop_mul(p.drop, dw, l0); o.y *= drop_mul(p.drop, dw, l0 + 1);
+                        o.z *= drop_mul(p.drop, dw, l0 + 2); o.w *= drop_mul(p.drop, dw, l0 + 3);
+                    }
+                    o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
                     r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
                     r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
                     rsum += (o.x + o.y) + (o.z + o.w);
@@ -361,13 +372,23 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 buf_free(b);
                 ptx::tc_wait_ld();
                 const float* bs = b2 + ch * 32;
+                const bool dropping = TRAIN && p.drop.p > 0.f;
+                uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4 o;
-                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0] + __uint_as_float(r1[c * 4 + 0]);
-                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1] + __uint_as_float(r1[c * 4 + 1]);
-                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2] + __uint_as_float(r1[c * 4 + 2]);
-                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3] + __uint_as_float(r1[c * 4 + 3]);
+                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0];
+                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1];
+                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2];
+                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3];
+                    if (dropping) {       // x_mid + drop(MLP branch)
+                        if ((c & 1) == 0) dw = drop_words(p.drop, p.site2, (unsigned long long)(row0 + lane) * (kBtC / 8) + ch * 4 + (c >> 1));
+                        const int l0 = (c & 1) * 4;
+                        o.x *= drop_mul(p.drop, dw, l0); o.y *= drop_mul(p.drop, dw, l0 + 1);
+                        o.z *= drop_mul(p.drop, dw, l0 + 2); o.w *= drop_mul(p.drop, dw, l0 + 3);
+                    }
+                    o.x += __uint_as_float(r1[c * 4 + 0]); o.y += __uint_as_float(r1[c * 4 + 1]);
+                    o.z += __uint_as_float(r1[c * 4 + 2]); o.w += __uint_as_float(r1[c * 4 + 3]);
                     *reinterpret_cast<float4*>(buf + sw128_off(lane, c)) = o;
                     r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
                     r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
@@ -456,6 +477,8 @@ struct BlockTailArgs {
     // training only
     float* x_mid = nullptr;
     __nv_bfloat16 *ln2 = nullptr, *hpre = nullptr, *hact = nullptr;
+    DropCfg drop;
+    uint32_t site1 = 0, site2 = 0;
 };
 
 static cudaError_t launch_block_tail(const BlockTailArgs& a, int M, bool train, int num_sms, cudaStream_t st) {
@@ -483,6 +506,7 @@ static cudaError_t launch_block_tail(const BlockTailArgs& a, int M, bool train, 
     BtParams p;
     p.bo = a.bo; p.g2 = a.g2; p.be2 = a.be2; p.b1 = a.b1; p.b2 = a.b2; p.gn = a.gn; p.ben = a.ben;
     p.M = M; p.has_ln_out = a.ln_out != nullptr;
+    p.drop = train ? a.drop : DropCfg(); p.site1 = a.site1; p.site2 = a.site2;
     const int tiles = (M + 127) / 128;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min(tiles, num_sms)); cfg.blockDim = dim3(kBtThreads); cfg.dynamicSmemBytes = kBtSmem; cfg.stream = st;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropout.cuh"
+
 namespace tante {
 
 constexpr int kWarp = 32;
@@ -204,6 +206,9 @@ struct EpiParams {
     // EPI_MULGRAD_*: saved pre-activation (post-activation for ReLU), bf16 [M, ld_pre]
     const void* mul_pre = nullptr;
     int ld_pre = 0;
+    // EPI_BIAS_RESID in training with dropout (SIMT GEMM): C = resid + drop(acc + bias), element index m * ldr + n
+    DropCfg drop;
+    uint32_t drop_site = 0;
 };
 
 // encoder tail (t_encode FiLM + s_emb + t_emb, tante.py:132-141) with explicit roundings: the GEMM epilogues
@@ -218,7 +223,10 @@ __device__ __forceinline__ float apply_epilogue(float acc, int m, int n, const E
     if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.0f);
     if (EPI == EPI_BIAS_GELU_ERF) v = gelu_erf(v);
     if (EPI == EPI_BIAS_GELU_TANH) v = gelu_tanh(v);
-    if (EPI == EPI_BIAS_RESID) v = p.resid[(size_t)m * p.ldr + n] + v;
+    if (EPI == EPI_BIAS_RESID) {
+        if (p.drop.p > 0.f) v *= drop_elem(p.drop, p.drop_site, (unsigned long long)m * p.ldr + n);
+        v = p.resid[(size_t)m * p.ldr + n] + v;
+    }
     if (EPI == EPI_EMBED) {
         const int hw = m % p.L;
         const int t = (m / p.L) % p.T;

@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <typename TIn, typename TOut, int HD>
 __global__ void __launch_bounds__(128) axial_attention_kernel(const TIn* __restrict__ qkv, TOut* __restrict__ out,
                                                               int n_seq, int S, int inner_sz, int n_head, int C,
-                                                              int causal, float scale) {
+                                                              int causal, float scale, DropCfg drop = DropCfg(),
+                                                              uint32_t site = 0) {
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n_seq * n_head * S;
     if (item >= total) return;
@@ -244,14 +245,20 @@ __global__ void __launch_bounds__(128) axial_attention_kernel(const TIn* __restr
         const float mn = fmaxf(m, s);
         const float corr = expf(m - mn);   // exp(-inf) = 0 on the first key
         const float p = expf(s - mn);
-        l = l * corr + p;
+        l = l * corr + p;                  // the softmax normaliser sees every key; dropout acts on the probabilities
+        float pz = p;
+        if (drop.p > 0.f) {
+            const long long tokq = (long long)tok0 + (long long)qpos * inner_sz;
+            const uint4 w = drop_words(drop, site, drop_attn_grp(tokq, n_head, head, j));
+            pz *= drop_mul(drop, w, j & 7);
+        }
         const TIn* vp = kp + C;
 #pragma unroll
         for (int d = 0; d < HD; d += 4) {
             float t4[4];
             Vec4<TIn>::load(vp + d, t4);
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[d + jj] = fmaf(acc[d + jj], corr, p * t4[jj]);
+            for (int jj = 0; jj < 4; ++jj) acc[d + jj] = fmaf(acc[d + jj], corr, pz * t4[jj]);
         }
         m = mn;
     }

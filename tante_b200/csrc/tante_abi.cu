@@ -110,6 +110,7 @@ struct Tape {
     int B_used = 0;     // batch of the taped forward
     float out_T = 1.f;
     bool valid = false;
+    DropCfg drop;       // dropout of this taped call (p = 0: none); the backward regenerates the forward's masks from it
 };
 
 struct tante_handle_s {
@@ -133,6 +134,8 @@ struct tante_handle_s {
     DevBuf enc_state;                   // rollout: [8] count, [B*T] list, [B*T] map
     bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
     bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
+    float drop_p = 0.f;                 // tante_set_dropout: applies to the NEXT tante_train_forward calls
+    unsigned long long drop_seed = 0;
     bool fuse_tail = true;              // tensor mode: out-proj + LN2 + MLP + LN1' of a block as ONE kernel (TANTE_FUSE_TAIL=0: three GEMMs)
 
     // workspace
@@ -458,7 +461,8 @@ void launch_layernorm(tante_handle_s* h, const float* x, int64_t w, int64_t b, T
 // Training (x_mid != null) also stores x_mid, the LN2 output, the MLP pre-activation and the hidden activation.
 void launch_tail(tante_handle_s* h, const LayerPlan& lp, const LayerPlan* nx, const __nv_bfloat16* att, const float* x_in,
                  float* x_out, __nv_bfloat16* ln_out, int tokens, cudaStream_t st, float* x_mid = nullptr,
-                 __nv_bfloat16* ln2 = nullptr, __nv_bfloat16* hpre = nullptr, __nv_bfloat16* hact = nullptr) {
+                 __nv_bfloat16* ln2 = nullptr, __nv_bfloat16* hpre = nullptr, __nv_bfloat16* hact = nullptr,
+                 const DropCfg& drop = DropCfg(), uint32_t site1 = 0, uint32_t site2 = 0) {
     const bool train = x_mid != nullptr;
     const double C = h->C;
     // class 3: HBM-bound by construction -- att (2C) + x in (4C) + x out (4C) [+ ln out (2C)] per token; training adds
@@ -472,12 +476,14 @@ void launch_tail(tante_handle_s* h, const LayerPlan& lp, const LayerPlan* nx, co
     a.gn = nx ? AF(h, nx->ln1w) : nullptr; a.ben = nx ? AF(h, nx->ln1b) : nullptr;
     a.x_in = x_in; a.x_out = x_out; a.ln_out = nx ? ln_out : nullptr;
     a.x_mid = x_mid; a.ln2 = ln2; a.hpre = hpre; a.hact = hact;
+    a.drop = drop; a.site1 = site1; a.site2 = site2;
     CK(launch_block_tail(a, tokens, train, h->num_sms, st));
     h->launches++;
 }
 
 template <typename TA>
-void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axis, cudaStream_t st) {
+void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axis, cudaStream_t st,
+                      const DropCfg& drop = DropCfg(), uint32_t site = 0) {
     int S, inner, nseq;
     const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp;
     if (axis == 'T') { S = T; inner = L; nseq = B * L; }
@@ -486,7 +492,7 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
     if (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
         if (launch_attention_mma(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
-                                 inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e)) {
+                                 inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e, drop, site)) {
             CK(e);
             h->launches++;
             return;
@@ -496,7 +502,7 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
     const int blocks = (int)((total + 127) / 128);
     const float scale = 1.0f / sqrtf((float)h->HD);
     const int causal = axis == 'T';
-#define ATT(HDv) axial_attention_kernel<TA, TA, HDv><<<blocks, 128, 0, st>>>(qkv, out, nseq, S, inner, h->cfg.n_head, h->C, causal, scale)
+#define ATT(HDv) axial_attention_kernel<TA, TA, HDv><<<blocks, 128, 0, st>>>(qkv, out, nseq, S, inner, h->cfg.n_head, h->C, causal, scale, drop, site)
     if (h->HD == 32) ATT(32); else if (h->HD == 64) ATT(64); else ATT(16);
 #undef ATT
     CK(cudaGetLastError());
@@ -862,18 +868,19 @@ void gemm_dx_act(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* ou
 
 template <typename TA>
 void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamma, float* dxs, TA* dxb, float* dg, float* db,
-                   long long rows, cudaStream_t st) {
+                   long long rows, cudaStream_t st, const DropCfg& drop = DropCfg(), uint32_t site = 0) {
     const int C = h->C;
     // persistent grid = exactly the resident blocks (3 per SM for C <= 256): no partial last wave
     const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, (C <= 256 ? 3LL : 2LL) * h->num_sms);
-    if (C <= 256) ln_bwd_kernel<TA, 2><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f);
-    else ln_bwd_kernel<TA, 4><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f);
+    if (C <= 256) ln_bwd_kernel<TA, 2><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
+    else ln_bwd_kernel<TA, 4><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
     CK(cudaGetLastError());
     h->launches++;
 }
 
 template <typename TA>
-void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* dqkv, int B, char axis, cudaStream_t st) {
+void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* dqkv, int B, char axis, cudaStream_t st,
+                          const DropCfg& drop = DropCfg(), uint32_t site = 0) {
     int S, inner; long long nseq;
     const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp;
     if (axis == 'T') { S = T; inner = L; nseq = (long long)B * L; }
@@ -881,7 +888,7 @@ void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* 
     else { S = Wp; inner = 1; nseq = (long long)B * T * Hp; }
     if constexpr (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
-        if (launch_attention_bwd_mma(qkv, dout, dqkv, nseq, S, inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e)) {
+        if (launch_attention_bwd_mma(qkv, dout, dqkv, nseq, S, inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e, drop, site)) {
             CK(e);
             h->launches++;
             return;
@@ -895,7 +902,7 @@ void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* 
     do {                                                                                                       \
         const size_t smem = (size_t)(4 * R * (HDv + 1) + 2 * R * (S + 1)) * sizeof(float);                     \
         attention_bwd_kernel<TA, HDv><<<grid, 128, smem, st>>>(qkv, dout, dqkv, nseq, S, inner, h->cfg.n_head, \
-                                                               h->C, axis == 'T', scale, G);                   \
+                                                               h->C, axis == 'T', scale, G, drop, site);       \
     } while (0)
     if (h->HD == 32) ATTB(32); else if (h->HD == 64) ATTB(64); else ATTB(16);
 #undef ATTB
@@ -1022,7 +1029,7 @@ void backward_alloc(tante_handle_s* h, int B) {
     const int NO = g.k0 * g.k0 * h->D;
     dev_alloc(h, h->garena, (size_t)h->garena_elems * 4);
     dev_alloc(h, h->dxs, tokens * C * 4);
-    if (es == 2) dev_alloc(h, h->dxb, tokens * C * es);
+    dev_alloc(h, h->dxb, tokens * C * es);      // bf16 mirror of the gradient stream; in the exact mode: its dropout-masked copy
     dev_alloc(h, h->g1, tokens * C * es);
     dev_alloc(h, h->g2, tokens * C * es);
     dev_alloc(h, h->gq, tokens * std::max(3 * C, g.R2 * C2) * es);
@@ -1058,6 +1065,10 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     const PatchGeom& g = h->geom;
     const int tokens = B * T * L;
     constexpr bool kTensor = sizeof(TA) == 2;
+    tp.drop = make_drop_cfg(h->drop_p, h->drop_seed);
+    const DropCfg& drop = tp.drop;
+    if (drop.p > 0.f && kTensor && !(h->fuse_tail && C == kBtC))
+        throw Error(TANTE_ERR_INVALID, "dropout in the tensor mode needs the fused block tail (TANTE_FUSE_TAIL=1, embed_dim 256)");
     // --- encoder ---
     {
         // enc_conv_1 as im2col (kept for the weight gradient) + GEMM over the zero-padded patch matrix
@@ -1099,17 +1110,19 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             if (!ln_ready) launch_layernorm<TA>(h, x_in, lp.ln1w, lp.ln1b, TP<TA>(ot.ln1[li]), tokens, st);
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln1[li]), C, lp.inw, ot.qkv[li].p, 3 * C, false, tokens, 3 * C, C, eq, st);
-            launch_attention<TA>(h, TP<TA>(ot.qkv[li]), TP<TA>(ot.att[li]), B, lp.axis, st);
+            launch_attention<TA>(h, TP<TA>(ot.qkv[li]), TP<TA>(ot.att[li]), B, lp.axis, st, drop, drop_site(o, (int)li, 0));
             if constexpr (kTensor) {
                 if (h->fuse_tail && C == kBtC) {
                     const LayerPlan* nx = li + 1 < nl ? &op.layers[li + 1] : nullptr;
                     launch_tail(h, lp, nx, TP<TA>(ot.att[li]), x_in, x_out, nx ? TP<TA>(ot.ln1[li + 1]) : nullptr, tokens, st,
-                                x_mid, TP<TA>(ot.ln2[li]), TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]));
+                                x_mid, TP<TA>(ot.ln2[li]), TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), drop,
+                                drop_site(o, (int)li, 1), drop_site(o, (int)li, 2));
                     ln_ready = nx != nullptr;
                     continue;
                 }
             }
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x_in; eo.ldr = C;
+            eo.drop = drop; eo.drop_site = drop_site(o, (int)li, 1);
             if (kTensor) {
                 eo.ln_gamma = AF(h, lp.ln2w); eo.ln_beta = AF(h, lp.ln2b); eo.ln_out = ot.ln2[li].p;
                 gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.att[li]), C, lp.outw, x_mid, C, true, tokens, C, C, eo, st);
@@ -1121,6 +1134,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln2[li]), C, lp.m0w, ot.hpre[li].p, C, false, tokens, C, C, e0, st);
             launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * C, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x_mid; e2.ldr = C;
+            e2.drop = drop; e2.drop_site = drop_site(o, (int)li, 2);
             if (kTensor && li + 1 < nl) {
                 const LayerPlan& nx = op.layers[li + 1];
                 e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ot.ln1[li + 1].p;
@@ -1220,7 +1234,11 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     constexpr bool kTensor = sizeof(TA) == 2;
     const long long rows1 = (long long)BL * g.R1;       // stage-1 rows of the last frame (head)
     float* dxs = FP(h->dxs);
-    TA* dxb = kTensor ? TP<TA>(h->dxb) : reinterpret_cast<TA*>(dxs);
+    const DropCfg& drop = tp.drop;
+    // dY operand of the residual-branch GEMMs: the bf16 copy of the gradient stream (tensor mode) and / or its
+    // dropout-masked copy; the exact mode without dropout reads the fp32 stream itself
+    const bool mirror = kTensor || drop.p > 0.f;
+    TA* dxb = mirror ? TP<TA>(h->dxb) : reinterpret_cast<TA*>(dxs);
     TA* g1 = TP<TA>(h->g1);
     TA* g2 = TP<TA>(h->g2);
     TA* gq = TP<TA>(h->gq);
@@ -1292,12 +1310,13 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         CK(cudaGetLastError());
         h->launches++;
         // ---- backbone of order o ----
-        if (kTensor) {
-            convert_kernel<TA><<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(dxs, dxb, (long long)tokens * C / 4);
+        if (mirror) {
+            convert_kernel<TA><<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(
+                dxs, dxb, (long long)tokens * C / 4, drop, drop_site(o, (int)op.layers.size() - 1, 2));
             CK(cudaGetLastError());
             h->launches++;
         }
-        TA* dxb_out = kTensor ? dxb : nullptr;
+        TA* dxb_out = mirror ? dxb : nullptr;
         for (int li = (int)op.layers.size() - 1; li >= 0; --li) {
             const LayerPlan& lp = op.layers[li];
             const float* x_in = FP(ot.X[2 * li]);
@@ -1307,14 +1326,17 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             gemm_dx_act<TA, ACT_GELU_TANH>(h, dxb, C, lp.m2wT, g1, TP<TA>(ot.hpre[li]), tokens, C, C, st);
             wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
             gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
-            launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st);
+            launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st, drop,
+                              drop_site(o, li, 1));
             // attention half: x_mid = x_in + Wo att(ln1(x_in)) + bo
             wgrad<TA>(h, dxb, C, TP<TA>(ot.att[li]), C, GA(h, lp.outw), tokens, C, C, st, GA(h, lp.outb));
             gemm_dx<TA>(h, dxb, C, lp.outwT, g2, C, tokens, C, C, st);
-            launch_attention_bwd<TA>(h, TP<TA>(ot.qkv[li]), g2, gq, B, lp.axis, st);
+            launch_attention_bwd<TA>(h, TP<TA>(ot.qkv[li]), g2, gq, B, lp.axis, st, drop, drop_site(o, li, 0));
             wgrad<TA>(h, gq, 3 * C, TP<TA>(ot.ln1[li]), C, GA(h, lp.inw), tokens, 3 * C, C, st, GA(h, lp.inb));
             gemm_dx<TA>(h, gq, 3 * C, lp.inwT, g2, C, tokens, C, 3 * C, st);
-            launch_ln_bwd<TA>(h, g2, x_in, lp.ln1w, dxs, dxb_out, GA(h, lp.ln1w), GA(h, lp.ln1b), tokens, st);
+            // the copy written here is the dY of the layer below's MLP branch
+            launch_ln_bwd<TA>(h, g2, x_in, lp.ln1w, dxs, dxb_out, GA(h, lp.ln1w), GA(h, lp.ln1b), tokens, st, drop,
+                              drop_site(o, std::max(li - 1, 0), 2));
         }
         const float* pin = o == 0 ? FP(ot.P[0]) : FP(tp.ord[o - 1].X.back());
         launch_propagator_bwd(h, FP(ot.P[2]), dxs, B, 2, op, st);
@@ -1766,6 +1788,15 @@ int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_ro
         if (steps_out) CK(cudaMemcpyAsync(steps_out, rs.steps, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
         h->last_B = B;
         if (sync) CK(cudaStreamSynchronize(st));
+    });
+}
+
+int tante_set_dropout(tante_handle_t h, float p, uint64_t seed) {
+    return guarded([&] {
+        REQUIRE(h, "null handle");
+        REQUIRE(p >= 0.f && p < 1.f, "dropout probability must be in [0, 1)");
+        h->drop_p = p;
+        h->drop_seed = seed;
     });
 }
 

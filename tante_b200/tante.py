@@ -448,10 +448,13 @@ class TANTE(nn.Module):
         return torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters()))
 
     def _forward_train(self, x, out_T, n_cap):
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not supported by the CUDA backward; "
-                                      "construct the model with dropout=0.0")
         eng = self._engine(x.device)
+        # nn.Dropout / MultiheadAttention(dropout=p) act in train() mode only (attn_backbone.py:47-57,81-83).  Every model
+        # call draws a fresh 64-bit key for the counter-based mask generator from torch's CPU generator (reproducible
+        # under torch.manual_seed); the tape keeps it so that the backward regenerates the same masks.
+        p = float(self.dropout) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+        _abi.check(eng.lib.tante_set_dropout(eng.handle, p, seed))
         params = dict(self.named_parameters())
         return _TanteStep.apply(self, x, float(out_T), int(n_cap), *[params[n] for n in eng.names])
 
@@ -473,7 +476,9 @@ class TANTE(nn.Module):
         if not self.deg and out_T < 1:
             raise ValueError("out_T must be >= 1")
         n_cap = int(self.output_length) if self.deg else max(1, int(math.floor(out_T + 0.001)))
-        if self._needs_grad(x):
+        if self._needs_grad(x) or (self.training and self.dropout > 0):
+            # (train() mode with dropout under no_grad still drops, like the reference module: same taped path, the tape
+            #  slot is returned as soon as the unused autograd context dies)
             frames, R_t = self._forward_train(x, out_T, n_cap)
             return frames if self.deg else (frames, R_t)
         eng = self._engine(x.device)

@@ -13,7 +13,7 @@
 
 namespace tante {
 
-template <int NKB /* R_pad / 8 */>
+template <int NKB /* R_pad / 8 */, bool DROP = false>
 __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                       const __nv_bfloat16* __restrict__ dout,
                                                                       __nv_bfloat16* __restrict__ dqkv, int n_groups,
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
-        if (drop.p > 0.f) {
+        if (DROP) {
             // O = (P o Z) V with Z = mask / (1 - p): dP = (dO V^T) o Z; everything below uses the masked dP
             const int head = hq * 4 + warp;
             const long long t0 = s_tok[r0], t1 = s_tok[r1];
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
                 const float pt0 = ok0 ? exp2f((s[qb][j] - m) * scale_log2e) * il : 0.f;
                 const float pt1 = ok1 ? exp2f((s[qb][2 + j] - m) * scale_log2e) * il : 0.f;
                 float z0 = 1.f, z1 = 1.f;
-                if (drop.p > 0.f) {       // Z of (query = this column, key = rows r0 / r1)
+                if (DROP) {       // Z of (query = this column, key = rows r0 / r1)
                     const long long tq = s_tok[col];
                     const int head = hq * 4 + warp;
                     z0 = drop_mul(drop, drop_words(drop, site, drop_attn_grp(tq, n_head, head, p0)), p0 & 7);
@@ -328,9 +328,12 @@ __global__ void __launch_bounds__(128) axial_attention_bwd_mma_kernel(const __nv
 static void attb_set_attrs() {
     static unsigned long long attr = 0;
     if (!attrs_needed(attr)) return;
-    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(axial_attention_bwd_mma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
 // Host launcher.  Returns false when the configuration is outside this kernel (caller falls back to the SIMT kernel).
@@ -347,11 +350,12 @@ static bool launch_attention_bwd_mma(const __nv_bfloat16* qkv, const __nv_bfloat
     const float scale = 1.0f / sqrtf((float)head_dim);
     const float sl2 = scale * 1.4426950408889634f;
     attb_set_attrs();
+    const bool dr = drop.p > 0.f;
     switch (R) {
-        case 16: axial_attention_bwd_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
-        case 32: axial_attention_bwd_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
-        case 48: axial_attention_bwd_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
-        default: axial_attention_bwd_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        case 16: if (dr) axial_attention_bwd_mma_kernel<2, true><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); else axial_attention_bwd_mma_kernel<2, false><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        case 32: if (dr) axial_attention_bwd_mma_kernel<4, true><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); else axial_attention_bwd_mma_kernel<4, false><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        case 48: if (dr) axial_attention_bwd_mma_kernel<6, true><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); else axial_attention_bwd_mma_kernel<6, false><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
+        default: if (dr) axial_attention_bwd_mma_kernel<8, true><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); else axial_attention_bwd_mma_kernel<8, false><<<grid, 128, smem, st>>>(qkv, dout, dqkv, (int)n_groups, S, inner_sz, C, causal, G, scale, sl2, drop, site, n_head); break;
     }
     *err = cudaGetLastError();
     return true;

@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // tile row = 64 B (32 bf16) = four 16-byte chunks, chunk index XOR-swizzled by (row >> 1) & 3
 __device__ __forceinline__ uint32_t att_off(int r, int chunk) { return (uint32_t)(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); }
 
-template <int NKB /* R_pad / 8 */>
+template <int NKB /* R_pad / 8 */, bool DROP = false>
 __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                   __nv_bfloat16* __restrict__ out, int n_groups, int S,
                                                                   int inner_sz, int C, int causal, int G,
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        if (drop.p > 0.f) {
+        if (DROP) {
             // training: dropout on the (normalised) probabilities -- the normaliser above saw every key.  The two keys this
             // lane holds in a block are lanes (kpos & 7), (kpos & 7) + 1 of one Philox group of (query token, head)
             const int head = hq * 4 + warp;
@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(128) axial_attention_mma_kernel(const __nv_bfl
 static void att_set_attrs() {
     static unsigned long long attr = 0;
     if (!attrs_needed(attr)) return;
-    cudaFuncSetAttribute(axial_attention_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(axial_attention_mma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(axial_attention_mma_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(axial_attention_mma_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(axial_attention_mma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(axial_attention_mma_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
 // Host launcher.  Returns false when the configuration is outside this kernel (caller falls back).
@@ -252,11 +254,12 @@ static bool launch_attention_mma(const __nv_bfloat16* qkv, __nv_bfloat16* out, l
     const size_t smem = (size_t)3 * 4 * R * 64;
     const float sl2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
     att_set_attrs();
+    const bool dr = drop.p > 0.f;
     switch (R) {
-        case 16: axial_attention_mma_kernel<2><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
-        case 32: axial_attention_mma_kernel<4><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
-        case 48: axial_attention_mma_kernel<6><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
-        default: axial_attention_mma_kernel<8><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        case 16: if (dr) axial_attention_mma_kernel<2, true><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); else axial_attention_mma_kernel<2, false><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        case 32: if (dr) axial_attention_mma_kernel<4, true><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); else axial_attention_mma_kernel<4, false><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        case 48: if (dr) axial_attention_mma_kernel<6, true><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); else axial_attention_mma_kernel<6, false><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
+        default: if (dr) axial_attention_mma_kernel<8, true><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); else axial_attention_mma_kernel<8, false><<<grid, 128, smem, st>>>(qkv, out, (int)n_groups, S, inner_sz, C, causal, G, sl2, drop, site, n_head); break;
     }
     *err = cudaGetLastError();
     return true;

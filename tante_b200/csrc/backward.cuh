@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) interp_tail_bwd_kernel(const TA* __restri
 //   dxs (fp32 gradient stream, in place) += dx_ln; optional TA copy of the updated row (next GEMM operand);
 //   dgamma += dy*xhat, dbeta += dy (per-warp registers -> shared -> atomics).
 // (occupancy: 3 blocks of 256 threads per SM -- at the natural 87 registers only 2 fit, and the kernel is latency-bound)
-template <typename TA, int MAXV>
+template <typename TA, int MAXV, bool DROP = false>
 __global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA* __restrict__ dy, const float* __restrict__ x,
                                                      const float* __restrict__ gamma, float* __restrict__ dxs,
                                                      TA* __restrict__ dxb, float* __restrict__ dgamma,
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256, MAXV <= 2 ? 3 : 1) ln_bwd_kernel(const TA
                     for (int j = 0; j < 4; ++j) ov[u][i][j] += rstd * (dv[u][i][j] - s1 - xv[u][i][j] * s2);
                     Vec4<float>::store(dxs + (size_t)rr[u] * C + c, ov[u][i]);
                     if (dxb) {
-                        if (drop.p > 0.f) {
+                        if (DROP) {
                             // the copy feeds the gradients of the residual branch below (its output went through dropout)
                             const unsigned long long e = (unsigned long long)rr[u] * C + c;
                             const uint4 w = drop_words(drop, site, e >> 3);

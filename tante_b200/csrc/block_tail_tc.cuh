@@ -42,7 +42,7 @@ struct BtParams {
     uint32_t site1, site2;
 };
 
-template <bool TRAIN>
+template <int MODE /* 0: inference, 1: training (stores the tape), 2: training with dropout */>
 __global__ void __launch_bounds__(kBtThreads, 1)
 block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWo,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -50,8 +50,11 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmXout, const __grid_constant__ CUtensorMap tmLn2,
                   const __grid_constant__ CUtensorMap tmHpre, const __grid_constant__ CUtensorMap tmHact,
                   const __grid_constant__ CUtensorMap tmLnOut, BtParams p) {
+    constexpr bool TRAIN = MODE != 0;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B) as an OFFSET into the shared array: a pointer -> integer -> pointer round trip would
+    // lose the address space and turn every shared-memory access of the epilogue into a generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                                        // [4 k-blocks][128 rows][128 B]
     uint8_t* sW = sA + 4 * kBtKBlk;                            // [kBtWStages][128 rows][128 B]
     uint8_t* sE = sW + kBtWStages * kBtWStage;                 // [8 warps][2][4 KB]
@@ -210,7 +213,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ptx::mbar_wait(&rb[b], (rph >> b) & 1u); rph ^= 1u << b;
                 ptx::tc_wait_ld();
                 const float* bs = bo + ch * 32;
-                const bool dropping = TRAIN && p.drop.p > 0.f;
+                constexpr bool dropping = MODE == 2;
                 uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -372,7 +375,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 buf_free(b);
                 ptx::tc_wait_ld();
                 const float* bs = b2 + ch * 32;
-                const bool dropping = TRAIN && p.drop.p > 0.f;
+                constexpr bool dropping = MODE == 2;
                 uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -462,8 +465,9 @@ static cudaError_t bt_set_attrs() {
     if (!get_encode_tiled()) return cudaErrorNotSupported;
     if (!attrs_needed(done)) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(block_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(block_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(block_tail_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(block_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(block_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -518,8 +522,9 @@ static cudaError_t launch_block_tail(const BlockTailArgs& a, int M, bool train, 
         ++na;
     }
     cfg.attrs = at; cfg.numAttrs = (unsigned)na;
-    if (train) return cudaLaunchKernelEx(&cfg, block_tail_kernel<true>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
-    return cudaLaunchKernelEx(&cfg, block_tail_kernel<false>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
+    if (train && p.drop.p > 0.f) return cudaLaunchKernelEx(&cfg, block_tail_kernel<2>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
+    if (train) return cudaLaunchKernelEx(&cfg, block_tail_kernel<1>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
+    return cudaLaunchKernelEx(&cfg, block_tail_kernel<0>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
 }
 
 }  // namespace tante

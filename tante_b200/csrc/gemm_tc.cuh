@@ -75,7 +75,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmL, int M, int N, int nkb, int nstage, int nebuf, int epi,
                int out_bf16, EpiParams ep) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B) as an OFFSET into the shared array: a pointer -> integer -> pointer round trip would
+    // lose the address space and turn every shared-memory access of the epilogue into a generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;                                   // [nkb][BN rows][128 B]
     constexpr int BNC = BN / NCTA;                        // weight rows resident in THIS CTA
     uint8_t* sA = sW + (size_t)nkb * BNC * 128;           // [nstage][128 rows][128 B]

@@ -29,8 +29,18 @@ constexpr int kHeadWPitch = 144;       // bytes per weight row (64 bf16 + 16 B p
 //   phase 3  (rollout only) channels-last history, thread = one (pixel, field) with the field fastest, u0 from the
 //            copy phase 2 parked in shared memory (the ring slot may be overwritten by then)
 // All per-tile quantities (sample, frames to emit, ring position) are CTA-uniform.
-template <int KORD, int NB, int ROWS>
-__global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) {
+// THREADS = 128: one warp per 16-row MMA block (NB <= 2: the 4-field shapes).  THREADS = 256 (wide outputs, e.g. the 11 fields
+// of Active Matter): two warps per MMA block, each owning half of the output columns, and half as many emit items per
+// thread -- the per-thread accumulators / item registers halve (200 -> < 128 registers), so the same two CTAs per SM the
+// shared memory allows for K >= 3 hold 16 warps instead of 8.
+template <int KORD, int NB, int ROWS, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
+taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) {
+    constexpr int MW = ROWS / 16;                 // warps covering the tile's rows
+    constexpr int CS = (THREADS / 32) / MW;       // column splits of the MMA phase (1 or 2)
+    constexpr int NBH = (NB + CS - 1) / CS;       // 8-column blocks per warp
+    constexpr int NJ = (NB * 128 + THREADS - 1) / THREADS;    // emit items per thread (nitems = 64 D <= 128 NB)
+    static_assert(THREADS == 32 * MW * CS, "THREADS must be a whole number of column splits");
     extern __shared__ __align__(1024) uint8_t hsm[];
     const int NO = g.k0 * g.k0 * g.D;
     const int P = g.k0 * g.k1 * g.k2;
@@ -61,8 +71,8 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         for (int k = 0; k < KORD; ++k) {
             const uint4* zk = reinterpret_cast<const uint4*>(hp.z[k]) + row0 * 8;
 #pragma unroll
-            for (int j = 0; j < ROWS * 8 / 128; ++j) {
-                const int i = tid + j * 128;
+            for (int j = 0; j < ROWS * 8 / THREADS; ++j) {
+                const int i = tid + j * THREADS;
                 const int r = i >> 3, c = i & 7;
                 const int nbytes = row0 + r < row_end ? 16 : 0;
                 const uint32_t dst = zb + (uint32_t)(k * ROWS * 128 + r * 128 + ((c ^ (r & 7)) << 4));
@@ -76,7 +86,7 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
     if ((long long)blockIdx.x < ntiles) load_z(blockIdx.x);
 #pragma unroll
     for (int k = 0; k < KORD; ++k) {
-        for (int i = tid; i < NB * 8 * 64; i += 128) {
+        for (int i = tid; i < NB * 8 * 64; i += THREADS) {
             const int c = i / (NB * 8), o = i % (NB * 8);            // consecutive threads read consecutive o: coalesced
             const float w = o < NO ? hp.w3[k][(size_t)c * NO + o] : 0.f;
             *reinterpret_cast<__nv_bfloat16*>(sW + (k * NB * 8 + o) * kHeadWPitch + c * 2) = __float2bfloat16_rn(w);
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
     int rowbase[2];
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-        const int r = warp * 16 + gq + 8 * hh;
+        const int r = (warp % MW) * 16 + gq + 8 * hh;
         const int tok = r / g.R1;
         int r1 = r % g.R1;
         const int bp = r1 % g.k1; r1 /= g.k1;
@@ -101,13 +111,13 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         rowbase[hh] = ((a * g.k1 + bq) * g.k0) * XW + tok * P + (ap * g.k1 + bp) * g.k0;
     }
     // MMA fragment columns o = (c*k0 + c')*D + d  ->  plane d, pixel (+c, +c'); bias of field d  (shared-memory tables)
-    for (int o = tid; o < NB * 8; o += 128) {
+    for (int o = tid; o < NB * 8; o += THREADS) {
         const int d = o % g.D, cp = (o / g.D) % g.k0, c = o / (g.D * g.k0);
         sOoff[o] = o < NO ? d * PS + c * XW + cp : -1;
 #pragma unroll
         for (int k = 0; k < KORD; ++k) sOb[k * NB * 8 + o] = o < NO ? hp.b3[k][d] : 0.f;
     }
-    // emit items of this thread: item = tid + 128*j -> (field, pixel row, 4-pixel run), all tile-invariant:
+    // emit items of this thread: item = tid + THREADS*j -> (field, pixel row, 4-pixel run), all tile-invariant:
     // shared-memory float offset inside the planes / global float offset inside a frame
     const int nitems = g.D * P * (XW / 4);
     auto item_soff = [&](int item) {
@@ -118,11 +128,11 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
     };
     // few fields (NB <= 2, e.g. the 4-field shapes): the per-item offsets of this thread stay in registers for all tiles
     constexpr bool kItemRegs = NB <= 2;
-    int soffR[kItemRegs ? NB : 1], goffR[kItemRegs ? NB : 1], xcolR[kItemRegs ? NB : 1];
+    int soffR[kItemRegs ? NJ : 1], goffR[kItemRegs ? NJ : 1], xcolR[kItemRegs ? NJ : 1];
     if (kItemRegs) {
 #pragma unroll
-        for (int j = 0; j < (kItemRegs ? NB : 1); ++j) {
-            const int item = tid + 128 * j;
+        for (int j = 0; j < (kItemRegs ? NJ : 1); ++j) {
+            const int item = tid + THREADS * j;
             soffR[j] = item < nitems ? item_soff(item) : -1;
             goffR[j] = (int)item_goff(item);
             xcolR[j] = (item & ((1 << lXQ) - 1)) << 2;
@@ -138,13 +148,13 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         const int fc = hp.fcount ? hp.fcount[b] : g.T;
         const size_t pix0 = (size_t)hpp * P * g.W + (size_t)wpc * XW;
         // u0 of this thread's items: in flight during phase 1
-        float4 u0r[NB];
+        float4 u0r[NJ];
         {
             const float* u0p = hp.u_ring + (size_t)(b * g.T + (fc + g.T - 1) % g.T) * g.D * HW + pix0;
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 u0r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int item = tid + 128 * j;
+                const int item = tid + THREADS * j;
                 if (kItemRegs) {
                     if (n > 0 && soffR[j] >= 0 && xcolR[j] < xvalid) u0r[j] = *reinterpret_cast<const float4*>(u0p + goffR[j]);
                 } else if (n > 0 && item < nitems && ((item & ((1 << lXQ) - 1)) << 2) < xvalid) {
@@ -156,20 +166,22 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         __syncthreads();                                             // z tile visible; previous emit is done with S
 
         // ---- phase 1: last deconv as [16 x 64] x [64 x NB*8] per order, + bias, scattered into the pixel planes ----
-        if (warp * 16 < ROWS) {                                      // 32-row tiles: two MMA warps, four emit warps
+        {
+            const int mw = warp % MW, nb0 = (warp / MW) * NBH;       // this warp's 16 rows and its first 8-column block
 #pragma unroll
             for (int k = 0; k < KORD; ++k) {
-                float acc[NB][4];
+                float acc[NBH][4];
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+                for (int nb = 0; nb < NBH; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     uint32_t a[4];
-                    const int r = warp * 16 + lrow, c = ks * 2 + lchk;
+                    const int r = mw * 16 + lrow, c = ks * 2 + lchk;
                     ldsm_x4(zb + (uint32_t)(k * ROWS * 128 + r * 128 + ((c ^ (r & 7)) << 4)), a[0], a[1], a[2], a[3]);
 #pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) {
-                        const uint8_t* wr = sW + (k * NB * 8 + nb * 8 + gq) * kHeadWPitch + (ks * 16 + 2 * t) * 2;
+                    for (int nb = 0; nb < NBH; ++nb) {
+                        if (CS > 1 && nb0 + nb >= NB) continue;
+                        const uint8_t* wr = sW + (k * NB * 8 + (nb0 + nb) * 8 + gq) * kHeadWPitch + (ks * 16 + 2 * t) * 2;
                         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
                         const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 16);
                         mma_bf16_16816(acc[nb], a, b0, b1);
@@ -177,9 +189,10 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
                 }
                 float* Sk = sS + k * g.D * PS;
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    const int2 oo = *reinterpret_cast<const int2*>(sOoff + nb * 8 + 2 * t);
-                    const float2 ob = *reinterpret_cast<const float2*>(sOb + k * NB * 8 + nb * 8 + 2 * t);
+                for (int nb = 0; nb < NBH; ++nb) {
+                    if (CS > 1 && nb0 + nb >= NB) continue;
+                    const int2 oo = *reinterpret_cast<const int2*>(sOoff + (nb0 + nb) * 8 + 2 * t);
+                    const float2 ob = *reinterpret_cast<const float2*>(sOb + k * NB * 8 + (nb0 + nb) * 8 + 2 * t);
                     if (oo.x >= 0) {
                         Sk[rowbase[0] + oo.x] = acc[nb][0] + ob.x;
                         Sk[rowbase[1] + oo.x] = acc[nb][2] + ob.x;
@@ -198,8 +211,8 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         // ---- phase 2: channels-first emit ----
         const int cum = hp.cum ? hp.cum[b] : 0;
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const int item = tid + 128 * j;
+        for (int j = 0; j < NJ; ++j) {
+            const int item = tid + THREADS * j;
             if (kItemRegs) { if (soffR[j] < 0 || xcolR[j] >= xvalid) continue; }
             else if (item >= nitems || ((item & ((1 << lXQ) - 1)) << 2) >= xvalid) continue;
             const int soff = kItemRegs ? soffR[j] : item_soff(item);
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(128) taylor_head_mma_kernel(HeadParams hp, Pat
         //      (one 128-bit store when D == 4), adjacent threads = adjacent pixels ----
         const int npix = P * xvalid;
         const bool vec4 = g.D == 4 && (reinterpret_cast<uintptr_t>(y_out) & 15) == 0;
-        for (int pi = tid; pi < npix; pi += 128) {
+        for (int pi = tid; pi < npix; pi += THREADS) {
             const int hr = pi / xvalid;
             const int x = pi - hr * xvalid;
             const int so = hr * XW + x;
@@ -277,6 +290,7 @@ template <int KORD, int NB>
 static cudaError_t launch_head_mma_inst(const HeadParams& hp, const PatchGeom& g, long long rows, int B, int num_sms,
                                         cudaStream_t st) {
     constexpr int ROWS = 64;     // (32-row tiles for the high orders were measured slower: two idle MMA warps, 64-B runs)
+    constexpr int THREADS = NB >= 4 ? 256 : 128;
     const int P = g.k0 * g.k1 * g.k2;
     const int NT = ROWS / g.R1;
     const int PS = P * NT * P + 4;
@@ -289,19 +303,19 @@ static cudaError_t launch_head_mma_inst(const HeadParams& hp, const PatchGeom& g
     if (cudaGetDevice(&cur_dev) != cudaSuccess) { (void)cudaGetLastError(); cur_dev = 0; }
     if (smem > attr_smem || cur_dev != attr_dev) {      // the attribute is per device
         const size_t want = std::max(smem, attr_smem);
-        cudaError_t e = cudaFuncSetAttribute(taylor_head_mma_kernel<KORD, NB, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+        cudaError_t e = cudaFuncSetAttribute(taylor_head_mma_kernel<KORD, NB, ROWS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
         if (e != cudaSuccess) return e;
         attr_smem = want;
         attr_dev = cur_dev;
     }
     if (smem != occ_smem) {
         int occ = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, taylor_head_mma_kernel<KORD, NB, ROWS>, 128, smem) != cudaSuccess) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, taylor_head_mma_kernel<KORD, NB, ROWS, THREADS>, THREADS, smem) != cudaSuccess) occ = 1;
         occ_cache = std::max(1, occ);
         occ_smem = smem;
     }
     const unsigned blocks = (unsigned)std::min<long long>(tiles, (long long)num_sms * occ_cache);
-    taylor_head_mma_kernel<KORD, NB, ROWS><<<blocks, 128, smem, st>>>(hp, g, rows, B);
+    taylor_head_mma_kernel<KORD, NB, ROWS, THREADS><<<blocks, THREADS, smem, st>>>(hp, g, rows, B);
     return cudaGetLastError();
 }
 

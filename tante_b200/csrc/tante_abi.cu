@@ -872,8 +872,13 @@ void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamm
     const int C = h->C;
     // persistent grid = exactly the resident blocks (3 per SM for C <= 256): no partial last wave
     const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, (C <= 256 ? 3LL : 2LL) * h->num_sms);
-    if (C <= 256) ln_bwd_kernel<TA, 2><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
-    else ln_bwd_kernel<TA, 4><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
+    if (drop.p > 0.f) {
+        if (C <= 256) ln_bwd_kernel<TA, 2, true><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
+        else ln_bwd_kernel<TA, 4, true><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
+    } else {
+        if (C <= 256) ln_bwd_kernel<TA, 2, false><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
+        else ln_bwd_kernel<TA, 4, false><<<blocks, 256, 0, st>>>(dy, x, AF(h, gamma), dxs, dxb, dg, db, rows, C, 1e-5f, drop, site);
+    }
     CK(cudaGetLastError());
     h->launches++;
 }

@@ -47,7 +47,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float* __restrict__ bias_grad, int n_total, const __nv_bfloat16* __restrict__ ones_g) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B) as an OFFSET into the shared array: a pointer -> integer -> pointer round trip would
+    // lose the address space and turn every shared-memory access of the epilogue into a generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int kStage = (2 + BN / 64) * kWgBox;
     uint8_t* sStage = smem + kWgBox;                                  // [nstage][A: 2 boxes][B: BN/64 boxes]
     // bias gradient db[n] = sum_m dY[m][n] rides along as one extra N = 64 MMA per k-step against a tile of ones

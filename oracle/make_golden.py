@@ -178,10 +178,32 @@ def case_train(ns, name, cfg, B, n_steps, rt_bias=0.0, seed=211, stride=17):
     save(name, cfg, meta, arrays)
 
 
+def main_round2(ns):
+    """Round-2 fixtures: patch_scale 16 / 32 / 64 (shifted 4x4 windows + bilinear resize, enc_dec_cnn.py:75-81,93-95,
+    176-184) and the long / composite attention axes L, Y, A (attn_backbone.py:164-182) -- written by the live reference."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_adp_k2_p16", C(n_fields=3, H=64, W=96, taylor_order=2, attn_axes="THW-WT", deg=False,
+                                          patch_scale=16), B=2, out_T=6, rt_bias=2.7, stages=True, n_roll=6, stride=5)
+    case_forward(ns, "fwd_deg_k1_p32", C(n_fields=4, H=128, W=192, taylor_order=1, attn_axes="THW", deg=True,
+                                          patch_scale=32), B=2, out_T=1, rt_bias=0.0, n_roll=3, stride=13)
+    case_forward(ns, "fwd_adp_k1_p64", C(n_fields=2, H=256, W=128, taylor_order=1, attn_axes="HWT", deg=False,
+                                          patch_scale=64), B=1, out_T=4, rt_bias=1.3, n_roll=4, stride=11)
+    case_forward(ns, "fwd_adp_k1_p16_d11", C(n_fields=11, H=64, W=64, taylor_order=1, attn_axes="TW", deg=False,
+                                              patch_scale=16), B=2, out_T=4, rt_bias=1.3, n_roll=4, stride=13)
+    # axes L / Y / A and an axis longer than 64 tokens (W_p = 96 at patch 4)
+    case_forward(ns, "fwd_adp_k2_axes_lya", C(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="LTY-AW", deg=False),
+                 B=2, out_T=6, rt_bias=2.7, stages=True, n_roll=6)
+    case_forward(ns, "fwd_deg_k1_w96", C(n_fields=2, H=32, W=384, taylor_order=1, attn_axes="WHT", deg=True,
+                                          patch_scale=4), B=2, out_T=1, rt_bias=0.0, n_roll=2)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ns = ref_shim.load_reference()
+    if "--round2" in sys.argv:
+        main_round2(ns)
+        return
     C = O.OracleConfig
     # 1. fixed-step (what configs/tante.yaml selects), full outputs on a small grid
     case_forward(ns, "fwd_deg_k1_p8", C(n_fields=4, H=64, W=96, taylor_order=1, deg=True), B=2, out_T=1,

@@ -29,6 +29,7 @@
 #include "wgrad_tc.cuh"
 #include "metrics.cuh"
 #include "block_tail_tc.cuh"
+#include "wide_patch.cuh"
 
 using namespace tante;
 
@@ -92,6 +93,7 @@ struct OrderPlan {
     int64_t mod[8];       // scale{0.w,0.b,2.w,2.b}, shift{...}
     int64_t decwT[2], intwT[2];
     int64_t w3pad = 0;
+    int64_t w3nk = 0;        // wide patches: last deconv as a GEMM weight [round_up(k0*k0*D, 64)][C1]
 };
 
 }  // namespace
@@ -134,6 +136,11 @@ struct tante_handle_s {
     DevBuf enc_state;                   // rollout: [8] count, [B*T] list, [B*T] map
     bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
     bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
+    bool long_axes = false;             // an L / Y / A layer or an axis longer than 64 tokens: inference / rollout only
+    bool wide = false;                  // patch_scale >= 16: natural-order stages with shifted 4x4 windows (wide_patch.cuh)
+    int K1pad = 0, NOpad = 0;           // wide: first-conv reduction / last-deconv output width rounded up to 64
+    int64_t enc_w1wide = 0;             // wide: first conv weight [C1][K1pad]
+    DevBuf wbuf, dfield;                // wide: patch / sub-pixel matrix scratch; decoded derivative fields [K][B][D][H][W]
     float drop_p = 0.f;                 // tante_set_dropout: applies to the NEXT tante_train_forward calls
     unsigned long long drop_seed = 0;
     bool fuse_tail = true;              // tensor mode: out-proj + LN2 + MLP + LN1' of a block as ONE kernel (TANTE_FUSE_TAIL=0: three GEMMs)
@@ -221,9 +228,9 @@ void patch_kernels(int P, int k[3]) {
         case 8: k[0] = 2; k[1] = 2; k[2] = 2; break;
         case 4: k[0] = 2; k[1] = 2; k[2] = 1; break;
         case 2: k[0] = 2; k[1] = 1; k[2] = 1; break;
-        case 16: case 32: case 64:
-            throw Error(TANTE_ERR_INVALID,
-                        "patch_scale 16/32/64 (4x4 kernels with padding 1 + bilinear resize) is not implemented yet");
+        case 16: k[0] = 4; k[1] = 2; k[2] = 2; break;      // 4x4 / pad-1 stages: wide_patch.cuh (inference / rollout)
+        case 32: k[0] = 4; k[1] = 4; k[2] = 2; break;
+        case 64: k[0] = 4; k[1] = 4; k[2] = 4; break;
         default: throw Error(TANTE_ERR_INVALID, "KeyError: patch_scale not in Patch_map");
     }
 }
@@ -241,11 +248,16 @@ void build_plan(tante_handle_s* h) {
     int k[3];
     patch_kernels(c.patch_scale, k);
     REQUIRE(c.H % c.patch_scale == 0 && c.W % c.patch_scale == 0, "H and W must be divisible by patch_scale");
+    h->wide = c.patch_scale >= 16;
+    h->K1pad = (k[0] * k[0] * c.n_fields + 63) / 64 * 64;
+    h->NOpad = h->K1pad;
+    if (h->wide) h->use_enc_cache = false;
     h->C = c.embed_dim; h->C1 = h->C / 4; h->C2 = h->C / 2;
     h->Hp = c.H / c.patch_scale; h->Wp = c.W / c.patch_scale; h->L = h->Hp * h->Wp;
     h->T = c.in_T; h->D = c.n_fields; h->K = c.taylor_order; h->HD = hd;
     // checked by the model entry points, not here: the head microbenchmark (tante_bench_head) needs no backbone
-    h->axes_ok = h->Hp <= 64 && h->Wp <= 64 && h->T <= 64;
+    h->axes_ok = h->Hp <= 96 && h->Wp <= 96 && h->T <= 64;      // propagator kernels: the S x S matrices + slab fit in shared memory
+    if (h->Hp > 64 || h->Wp > 64) h->long_axes = true;
     PatchGeom& g = h->geom;
     g.k0 = k[0]; g.k1 = k[1]; g.k2 = k[2];
     g.D = h->D; g.H = c.H; g.W = c.W; g.Hp = h->Hp; g.Wp = h->Wp; g.T = h->T;
@@ -261,7 +273,9 @@ void build_plan(tante_handle_s* h) {
         h->enc_w[i] = add_param(h, p + "weight", {ech[i + 1], ech[i], k[i], k[i]}, PACK_CONV, ech[i + 1], ech[i], k[i]);
         h->enc_b[i] = add_param(h, p + "bias", {ech[i + 1]});
         if (i > 0) h->enc_wT[i] = add_trans(h, h->enc_w[i], ech[i + 1], ech[i] * k[i] * k[i]);
-        else {
+        else if (h->wide) {
+            h->enc_w1wide = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 0, ech[1], h->K1pad);   // [C1][K1pad]
+        } else {
             REQUIRE(k[0] * k[0] * D <= kHeadPad, "n_fields too large for the padded first-conv backward (k0*k0*D <= 64)");
             h->enc_wT[0] = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 1, kHeadPad, ech[1]);   // [64 (K1 pad)][C1]
             h->enc_w1pad = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 0, ech[1], kHeadPad);  // [C1][64]
@@ -287,8 +301,12 @@ void build_plan(tante_handle_s* h) {
         for (int i = 0; i < nl; ++i) {
             LayerPlan lp;
             lp.axis = c.axes[o][i];
-            REQUIRE(lp.axis == 'T' || lp.axis == 'H' || lp.axis == 'W',
-                    std::string("attention axis '") + lp.axis + "' is not implemented (supported: T, H, W)");
+            // T / H / W: the axial layers of configs/tante.yaml; L / Y / A (attn_backbone.py:164-182): composite sequences,
+            // forward / rollout only.  'C' (channel attention with its 1 -> expanded_channel lift, :184-189) is not built;
+            // 'X' cannot be reached through TANTE's own validation (tante.py:76).
+            REQUIRE(lp.axis == 'T' || lp.axis == 'H' || lp.axis == 'W' || lp.axis == 'L' || lp.axis == 'Y' || lp.axis == 'A',
+                    std::string("attention axis '") + lp.axis + "' is not implemented (supported: T, H, W, L, Y, A)");
+            if (lp.axis == 'L' || lp.axis == 'Y' || lp.axis == 'A') h->long_axes = true;
             const std::string p = bp + "blocks." + std::to_string(i) + ".";
             lp.ln1w = add_param(h, p + "ln1.weight", {C});
             lp.ln1b = add_param(h, p + "ln1.bias", {C});
@@ -333,8 +351,12 @@ void build_plan(tante_handle_s* h) {
                 h->garena_elems -= (bp3.gnumel + 63) / 64 * 64;
                 bp3.gnumel = (int64_t)kk * kk * dch[i + 1]; bp3.gmode = PACK_BIAS_REP; bp3.gd0 = dch[i + 1]; bp3.gk = kk;
                 h->garena_elems += (bp3.gnumel + 63) / 64 * 64;
-                // [C1][64]: the packed [C1][k0*k0*D] weight zero-padded along its columns (dz = G * W3^T as a GEMM)
-                op.w3pad = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 0, dch[i], kHeadPad);
+                if (h->wide) {
+                    op.w3nk = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 1, h->NOpad, dch[i]);   // [NOpad][C1]
+                } else {
+                    // [C1][64]: the packed [C1][k0*k0*D] weight zero-padded along its columns (dz = G * W3^T as a GEMM)
+                    op.w3pad = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 0, dch[i], kHeadPad);
+                }
             }
         }
         if (!c.deg) {
@@ -405,7 +427,7 @@ inline __nv_bfloat16* AH(tante_handle_s* h, int64_t off) { return reinterpret_ca
 // C = epi(A * W^T): fp32 mode -> FFMA GEMM; bf16 mode -> tcgen05 GEMM (C is fp32 when out_f32, else bf16).
 template <typename TA>
 void gemm(tante_handle_s* h, int epi, const TA* A, int lda, int64_t w_off, void* Cout, int ldc, bool out_f32, int M, int N,
-          int K, const EpiParams& ep, cudaStream_t st);
+          int K, const EpiParams& ep, cudaStream_t st, int ldw = 0);
 
 struct ProfScope {
     tante_handle_s* h; cudaStream_t st; bool on;
@@ -429,20 +451,20 @@ struct ProfScope {
 
 template <>
 void gemm<float>(tante_handle_s* h, int epi, const float* A, int lda, int64_t w_off, void* Cout, int ldc, bool, int M,
-                 int N, int K, const EpiParams& ep, cudaStream_t st) {
+                 int N, int K, const EpiParams& ep, cudaStream_t st, int ldw) {
     const bool res = epi == EPI_BIAS_RESID || epi == EPI_EMBED;
     ProfScope ps(h, st, 2.0 * M * N * K, res ? 1 : 0, (double)M * (4.0 * K + 4.0 * N * (epi == EPI_BIAS_RESID ? 2 : 1)));
-    CK(launch_gemm_simt(epi, A, lda, AF(h, w_off), K, reinterpret_cast<float*>(Cout), ldc, M, N, K, ep, st));
+    CK(launch_gemm_simt(epi, A, lda, AF(h, w_off), ldw > 0 ? ldw : K, reinterpret_cast<float*>(Cout), ldc, M, N, K, ep, st));
     h->launches++;
 }
 
 template <>
 void gemm<__nv_bfloat16>(tante_handle_s* h, int epi, const __nv_bfloat16* A, int lda, int64_t w_off, void* Cout, int ldc,
-                         bool out_f32, int M, int N, int K, const EpiParams& ep, cudaStream_t st) {
+                         bool out_f32, int M, int N, int K, const EpiParams& ep, cudaStream_t st, int ldw) {
     const bool res = epi == EPI_BIAS_RESID || epi == EPI_BIAS_RESID_LN;
     const double out_b = out_f32 ? 4.0 * N * (res ? 2 : 1) + (epi == EPI_BIAS_RESID_LN ? 2.0 * N : 0.0) : 2.0 * N;
     ProfScope ps(h, st, 2.0 * M * N * K, out_f32 ? 1 : 0, (double)M * (2.0 * K + out_b));
-    CK(launch_gemm_tc(epi, A, lda, AH(h, w_off), K, Cout, ldc, out_f32 ? 0 : 1, M, N, K, ep, h->num_sms, st));
+    CK(launch_gemm_tc(epi, A, lda, AH(h, w_off), ldw > 0 ? ldw : K, Cout, ldc, out_f32 ? 0 : 1, M, N, K, ep, h->num_sms, st));
     h->launches++;
 }
 
@@ -486,9 +508,13 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
                       const DropCfg& drop = DropCfg(), uint32_t site = 0) {
     int S, inner, nseq;
     const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp;
+    // sequence gid = (outer, inner): token(pos) = (outer * S + pos) * inner_sz + inner   (attn_backbone.py:149-182)
     if (axis == 'T') { S = T; inner = L; nseq = B * L; }
     else if (axis == 'H') { S = Hp; inner = Wp; nseq = B * T * Wp; }
-    else { S = Wp; inner = 1; nseq = B * T * Hp; }
+    else if (axis == 'W') { S = Wp; inner = 1; nseq = B * T * Hp; }
+    else if (axis == 'L') { S = L; inner = 1; nseq = B * T; }               // (b t) (h w)
+    else if (axis == 'Y') { S = T * Hp; inner = Wp; nseq = B * Wp; }        // (b w) (t h)
+    else { S = T * L; inner = 1; nseq = B; }                                // 'A': b (t h w)
     if (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
         if (launch_attention_mma(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
@@ -592,6 +618,118 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
     h->launches++;
 }
 
+// ---- patch_scale >= 16 (wide_patch.cuh): encoder, decoder of one order, emit ----
+template <typename TA>
+void run_encoder_wide(tante_handle_s* h, const StepIO& io, int B, cudaStream_t st) {
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L;
+    const PatchGeom& g = h->geom;
+    const int tokens = B * T * L;
+    const int H = h->cfg.H, W = h->cfg.W, D = h->D;
+    TA* wb = reinterpret_cast<TA*>(h->wbuf.p);
+    TA* a1 = reinterpret_cast<TA*>(h->a1.p);
+    TA* a2 = reinterpret_cast<TA*>(h->a2.p);
+    float* x = reinterpret_cast<float*>(h->x.p);
+    const int H1 = H / g.k0, W1 = W / g.k0, H2 = H1 / g.k1, W2 = W1 / g.k1;
+    const long long rows1 = (long long)B * T * H1 * W1, rows2 = (long long)B * T * H2 * W2;
+    REQUIRE(rows1 * h->K1pad < (1LL << 40) && rows1 < (1LL << 31), "input too large for the wide first-conv GEMM");
+    // conv1: shifted (k0 = 4) windows of the ring frames -> [rows1][K1pad] -> GEMM + GELU -> grid [BT][H1][W1][C1]
+    {
+        const long long total = rows1 * h->K1pad;
+        wide_im2col_cf_kernel<TA><<<blocks_for(total, 256), 256, 0, st>>>(io.input, io.fcount, T, D, H, W, g.k0, (g.k0 - 1) / 2,
+                                                                         h->K1pad, wb, total);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, wb, h->K1pad, h->enc_w1wide, a1, C1, false, (int)rows1, C1, h->K1pad, e1, st);
+    }
+    // conv2
+    {
+        const int K2 = g.k1 * g.k1 * C1;
+        const long long total4 = rows2 * K2 / 4;
+        wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(a1, H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb, total4);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
+        gemm<TA>(h, EPI_BIAS_GELU_ERF, wb, K2, h->enc_w[1], a2, C2, false, (int)rows2, C2, K2, e2, st);
+    }
+    // conv3 + t_encode FiLM + embeddings -> residual stream
+    {
+        const int K3 = g.k2 * g.k2 * C2;
+        const long long total4 = (long long)tokens * K3 / 4;
+        wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(a2, H2, W2, C2, g.k2, (g.k2 - 1) / 2, wb, total4);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
+        if (sizeof(TA) == 2 && K3 > 1024) {
+            // K = 2048 (patch_scale 64) exceeds the resident weight slice of the tcgen05 GEMM: two K halves through an fp32
+            // scratch, then the embed pass
+            float* v = reinterpret_cast<float*>(h->qkv.p);
+            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], v, C, true, tokens, C, K3 / 2, e3, st, K3);
+            EpiParams e4; e4.bias = AF(h, h->zero_off); e4.resid = v; e4.ldr = C;
+            gemm<TA>(h, EPI_BIAS_RESID, wb + K3 / 2, K3, h->enc_w[2] + K3 / 2, v, C, true, tokens, C, K3 / 2, e4, st, K3);
+            embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(v, AF(h, h->film_t_off), AF(h, h->s_emb),
+                                                                                      AF(h, h->t_emb), x, tokens, T, L, C);
+            CK(cudaGetLastError());
+            h->launches++;
+        } else {
+            e3.film = AF(h, h->film_t_off); e3.s_emb = AF(h, h->s_emb); e3.t_emb = AF(h, h->t_emb);
+            e3.T = T; e3.L = L; e3.ldr = C;
+            gemm<TA>(h, EPI_EMBED, wb, K3, h->enc_w[2], x, C, true, tokens, C, K3, e3, st);
+        }
+    }
+}
+
+// decoder of order o on the (modified) last-frame latent dmod [B*L][C] -> derivative field dfield[o] (B, D, H, W)
+template <typename TA>
+void run_decoder_wide(tante_handle_s* h, int o, const TA* dmod, int B, cudaStream_t st) {
+    const OrderPlan& op = h->orders[o];
+    const int C = h->C, C1 = h->C1, C2 = h->C2, L = h->L, D = h->D, Hp = h->Hp, Wp = h->Wp;
+    const PatchGeom& g = h->geom;
+    const int H = h->cfg.H, W = h->cfg.W;
+    TA* wb = reinterpret_cast<TA*>(h->wbuf.p);
+    TA* z1 = reinterpret_cast<TA*>(h->z1.p);
+    TA* z2 = reinterpret_cast<TA*>(h->z2[o].p);
+    float* field = reinterpret_cast<float*>(h->dfield.p) + (size_t)o * B * D * H * W;
+    const int H2 = Hp * g.k2, W2 = Wp * g.k2, H1 = H2 * g.k1, W1 = W2 * g.k1;
+    auto post = [&](const TA* S, int ldS, int hi, int wi, int Cout, int k, const float* bias, TA* out, float* fld, bool act) {
+        const long long total = (long long)B * (hi * k) * (wi * k) * Cout;
+        const unsigned blocks = blocks_for(total, 256);
+        if (fld) wide_deconv_post_kernel<TA, false, true><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, nullptr, fld, total);
+        else if (act) wide_deconv_post_kernel<TA, true, false><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total);
+        else wide_deconv_post_kernel<TA, false, false><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total);
+        CK(cudaGetLastError());
+        h->launches++;
+    };
+    // dec_conv_1 (k2): [B*L][C] -> sub-pixel [B*L][k2*k2*C2] (+ replicated bias) -> resample + GELU -> grid [B][H2][W2][C2]
+    const int N1 = g.k2 * g.k2 * C2, N2 = g.k1 * g.k1 * C1;
+    EpiParams ed; ed.bias = AF(h, op.decb[0]);
+    gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ed, st);
+    post(wb, N1, Hp, Wp, C2, g.k2, nullptr, z1, nullptr, true);
+    // dec_conv_2 (k1)
+    ed.bias = AF(h, op.decb[1]);
+    gemm<TA>(h, EPI_BIAS, z1, C2, op.decw[1], wb, N2, false, B * H2 * W2, N2, C2, ed, st);
+    post(wb, N2, H2, W2, C1, g.k1, nullptr, z2, nullptr, true);
+    // dec_conv_3 (k0): output width k0*k0*D padded to NOpad, bias added after the resample (its weights sum to one)
+    EpiParams e3; e3.bias = AF(h, h->zero_off);
+    gemm<TA>(h, EPI_BIAS, z2, C1, op.w3nk, wb, h->NOpad, false, B * H1 * W1, h->NOpad, C1, e3, st);
+    post(wb, h->NOpad, H1, W1, D, g.k0, AF(h, op.decb[2]), nullptr, field, false);
+}
+
+void launch_emit_wide(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, cudaStream_t st) {
+    EmitParams ep{};
+    ep.dfield = reinterpret_cast<const float*>(h->dfield.p);
+    ep.K = h->K; ep.fi = h->cfg.frame_interval;
+    ep.u_ring = io.input; ep.fcount = io.fcount;
+    ep.n_arr = io.rollout ? rs.n_cur : reinterpret_cast<int*>(h->nbuf.p);
+    ep.frames = io.frames; ep.n_cap = io.n_cap;
+    ep.ptrs = io.rollout ? rs.ptrs : nullptr; ep.ring_out = io.ring_out; ep.cum = io.rollout ? rs.cum : nullptr; ep.n_roll = io.n_roll;
+    ep.B = B; ep.D = h->D; ep.T = h->T; ep.HW = (long long)h->cfg.H * h->cfg.W;
+    const long long total = (long long)B * h->D * ep.HW;
+    taylor_emit_kernel<<<blocks_for(total, 256), 256, 0, st>>>(ep);
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
 // One TANTE step (reference models/tante.py:125-176) as a launch sequence on `st`.
 template <typename TA>
 void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, cudaStream_t st) {
@@ -607,7 +745,9 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
     TA* a2 = reinterpret_cast<TA*>(h->a2.p);
 
     // --- encoder (enc_dec_cnn.py:217-229) + t_encode FiLM + s_emb + t_emb (tante.py:132-141) ---
-    {
+    if (h->wide) {
+        run_encoder_wide<TA>(h, io, B, st);
+    } else {
         const int P = g.k0 * g.k1 * g.k2;
         int WC = std::max(1, 128 / g.R1);
         WC = std::min(WC, g.Wp);
@@ -749,6 +889,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             CK(cudaGetLastError());
             h->launches++;
         }
+        if (h->wide) { run_decoder_wide<TA>(h, o, dmod, B, st); continue; }
         TA* z1 = reinterpret_cast<TA*>(h->z1.p);
         TA* z2 = reinterpret_cast<TA*>(h->z2[o].p);
         EpiParams ed; ed.bias = AF(h, op.decb[0]);
@@ -764,7 +905,8 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
                                                         io.rollout ? 1 : 0);
     CK(cudaGetLastError());
     h->launches++;
-    launch_head<TA>(h, io, B, rs, nullptr, st);
+    if (h->wide) launch_emit_wide(h, io, B, rs, st);
+    else launch_head<TA>(h, io, B, rs, nullptr, st);
     if (io.rollout) {
         advance_state_kernel<<<1, 256, 0, st>>>(rs, B, h->cond_handle, h->use_cond);
         CK(cudaGetLastError());
@@ -1394,7 +1536,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
 
 void ensure_ready(tante_handle_s* h, int B, bool need_backbone = true) {
     if (need_backbone && !h->axes_ok)
-        throw Error(TANTE_ERR_INVALID, "axis length > 64 is not supported by the axial kernels yet");
+        throw Error(TANTE_ERR_INVALID, "axis length > 96 (H_p, W_p) or in_T > 64 is not supported by the propagator kernels");
     if (!h->packed) throw Error(TANTE_ERR_STATE, "parameters not packed: call tante_bind_param for every parameter, then tante_pack_params");
     if (B < 1 || B > h->max_batch) throw Error(TANTE_ERR_STATE, "batch exceeds tante_reserve(max_batch)");
 }
@@ -1403,8 +1545,8 @@ void set_smem_attrs() {
     static unsigned long long done = 0;
     if (!attrs_needed(done)) return;
     const int big = 160 * 1024;
-    CK(cudaFuncSetAttribute(propagator_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CK(cudaFuncSetAttribute(propagator_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(propagator_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(propagator_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 #define HEADATTR(TA, KO) CK(cudaFuncSetAttribute(taylor_head_kernel<TA, 8, KO>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
@@ -1529,7 +1671,7 @@ int tante_destroy(tante_handle_t h) {
         cudaSetDevice(h->device);
         DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
                           &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
-                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols};
+                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols, &h->wbuf, &h->dfield};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
@@ -1682,6 +1824,17 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             dev_alloc(h, h->enc_state, ((size_t)2 * max_batch * h->T + 8) * 4);
         }
         if (h->debug) dev_alloc(h, h->dbg_in, tokens * C * 4);
+        if (h->wide) {
+            const size_t BLs = BL;
+            size_t m = tokens * g.R1 * (size_t)h->K1pad;                                  // conv1 windows
+            m = std::max(m, tokens * g.R2 * (size_t)(g.k1 * g.k1 * C1));                   // conv2 windows
+            m = std::max(m, tokens * (size_t)(g.k2 * g.k2 * C2));                          // conv3 windows
+            m = std::max(m, BLs * (size_t)(g.k2 * g.k2 * C2));                             // sub-pixel matrices of the decoder
+            m = std::max(m, BLs * g.R2 * (size_t)(g.k1 * g.k1 * C1));
+            m = std::max(m, BLs * g.R1 * (size_t)h->NOpad);
+            dev_alloc(h, h->wbuf, m * es);
+            dev_alloc(h, h->dfield, (size_t)h->K * max_batch * h->D * h->cfg.H * h->cfg.W * 4);
+        }
         if (!h->h_flag) {
             CK(cudaMallocHost(reinterpret_cast<void**>(&h->h_flag), 64));
             for (auto& e : h->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1818,6 +1971,9 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
+        REQUIRE(!h->wide, "training at patch_scale 16/32/64 is not implemented (inference / rollout only)");
+        REQUIRE(!h->long_axes, "training with attention axes L / Y / A or an axis longer than 64 tokens is not implemented "
+                               "(inference / rollout only)");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1900,6 +2056,11 @@ int tante_debug_stage(tante_handle_t h, const char* stage, float* dst, int64_t c
             // activations with every write but the debug one disabled
             n = (int64_t)h->K * B * h->D * h->cfg.H * h->cfg.W;
             REQUIRE(cap >= n, "destination too small");
+            if (h->wide) {       // the decoder already wrote the fields
+                CK(cudaMemcpyAsync(dst, h->dfield.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+                *numel = n;
+                return;
+            }
             CK(cudaMemsetAsync(h->nbuf.p, 0, (size_t)B * 4, st));
             StepIO io;
             io.input = reinterpret_cast<const float*>(h->ring.p);
@@ -1932,7 +2093,8 @@ int tante_bench_head(tante_handle_t h, const float* u, float* frames, int32_t B,
         io.input = u; io.frames = frames; io.n_cap = n_frames;
         RolloutState rs{};
         auto run = [&] {
-            if (h->cfg.precision == TANTE_PREC_FP32) launch_head<float>(h, io, B, rs, nullptr, st);
+            if (h->wide) launch_emit_wide(h, io, B, rs, st);       // boundary C: Horner emit over the decoded fields
+            else if (h->cfg.precision == TANTE_PREC_FP32) launch_head<float>(h, io, B, rs, nullptr, st);
             else launch_head<__nv_bfloat16>(h, io, B, rs, nullptr, st);
         };
         for (int i = 0; i < 3; ++i) run();

@@ -377,6 +377,22 @@ class TANTE(nn.Module):
             raise NotImplementedError("mlp_ratio != 1.0 is not supported yet")
         ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
         self.patch_kernels = ks
+        # what the CUDA library does not cover is refused HERE, not at the first forward
+        if "C" in self.attn_axes:
+            raise NotImplementedError("attention axis 'C' (channel attention with a 1 -> expanded_channel lift, "
+                                      "attn_backbone.py:126-130,184-189) is not implemented; supported: T, H, W, L, Y, A")
+        if embed_dim != 256:
+            raise NotImplementedError("the CUDA kernels are specialised for embed_dim = 256 (configs/tante.yaml:31)")
+        if n_head <= 0 or embed_dim % n_head or embed_dim // n_head not in (16, 32, 64):
+            raise NotImplementedError("head_dim = embed_dim / n_head must be 16, 32 or 64")
+        if not 1 <= self.n_channel <= 16:
+            raise NotImplementedError("1..16 fields are supported")
+        if self.shape[0] % patch_scale or self.shape[1] % patch_scale:
+            raise ValueError("the spatial resolution must be divisible by patch_scale")
+        if self.H_p > 96 or self.W_p > 96 or in_T > 64:
+            raise NotImplementedError("latent axes longer than 96 (H_p, W_p) / 64 (in_T) are not supported")
+        if not 1 <= taylor_order <= 4:
+            raise NotImplementedError("taylor_order must be in 1..4")
 
         # parameter containers, created in the reference's order (tante.py:85-123)
         self.decoders = nn.ModuleList()

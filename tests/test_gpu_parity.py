@@ -310,3 +310,56 @@ def test_host_prefetcher_pipeline_matches_direct_calls():
         torch.cuda.synchronize()
     for i in range(len(wins)):
         assert torch.equal(outs[i], want[i]), i
+
+
+# ------------------------------------------------------------------------------------------------
+# patch_scale 16 / 32 / 64 (shifted 4x4 windows + bilinear resize) and the attention axes L / Y / A,
+# axis lengths up to 96 -- against goldens written by the live reference (oracle/make_golden.py --round2)
+# ------------------------------------------------------------------------------------------------
+NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d11", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96"]
+
+
+@pytest.mark.parametrize("name", NEXT)
+def test_next_scope_forward_and_rollout_fp32(name):
+    from tante_b200 import rollout_eval
+    z, meta, cfg, sd, x, model = _setup(name)
+    with torch.inference_mode():
+        out = model(x.cuda(), meta["out_T"])
+        y, rt = (out, None) if cfg.deg else out
+        if rt is not None:
+            np.testing.assert_allclose(rt.cpu().numpy(), z["R_t"], rtol=0, atol=2e-5)
+        assert y.shape[1] == meta["n"] and list(y.shape) == meta["frames_shape"]
+        s = meta["stride"]
+        yc = y.cpu()
+        assert rel_l2(yc.reshape(-1)[::s].numpy(), z["frames"]) < FP32_FIELD_TOL
+        u0 = x[:, -1:].expand_as(yc)
+        assert rel_l2((yc - u0).reshape(-1)[::s].numpy(), z["frames"] - u0.reshape(-1)[::s].numpy()) < FP32_DERIV_TOL
+        yr, Rts, ns, steps = rollout_eval(model, x.cuda(), meta["n_roll"])
+    assert ns[: int(steps[0]), 0].tolist() == z["roll_ns"].tolist()
+    assert rel_l2(yr.cpu().reshape(-1)[::s].numpy(), z["roll_frames"]) < FP32_FIELD_TOL
+    if "stage_deriv0" in z.files:
+        B = meta["B"]
+        der = model.debug_stage("deriv", cfg.taylor_order * B * cfg.n_fields * cfg.H * cfg.W).cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96"])
+def test_next_scope_forward_bf16(name):
+    z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
+    with torch.inference_mode():
+        out = model(x.cuda(), meta["out_T"])
+    y = out if cfg.deg else out[0]
+    assert abs(y.shape[1] - meta["n"]) <= 1
+    s = meta["stride"]
+    yc = y.cpu()
+    B, n_got = yc.shape[0], yc.shape[1]
+    per = yc[0, 0].numel()
+    assert _prefix_rel(yc.reshape(B, n_got, per), z["frames"], meta["n"], s, min(n_got, meta["n"]), per) < BF16_FIELD_TOL
+
+
+def test_training_refused_for_inference_only_scopes():
+    from gpu_util import make_model
+    for kw in (dict(patch_scale=16, attn_axes="TH"), dict(attn_axes="LT")):
+        cfg = O.OracleConfig(n_fields=2, H=64, W=64, taylor_order=1, deg=True, **kw)
+        model = make_model(cfg, O.make_state_dict(cfg, 1)).train()
+        with pytest.raises(Exception, match="not implemented"):
+            model(O.make_input(cfg, 1, 2).cuda())

@@ -623,11 +623,16 @@ def head_sweep_leg(dev, precision="bf16", full=False):
                         cases.append({"shape": sname, "P": P, "K": K, "n": n, "skipped": str(e)[:100]})
                         continue
                     s_act = 2 if precision == "bf16" else 4
-                    rows = B * H * W // (k0 * k0)
-                    by = rows * K * 64 * s_act + B * D * H * W * 4 * (1 + n)
+                    if k0 == 4:
+                        # patch_scale >= 16: the bilinear resize after the last transposed conv blends neighbouring patches,
+                        # so the head is the Horner emit over the decoded derivative fields: boundary C of SURVEY.md 8(d)
+                        boundary, by = "C", (K + 1 + n) * B * D * H * W * 4
+                    else:
+                        rows = B * H * W // (k0 * k0)
+                        boundary, by = "B", rows * K * 64 * s_act + B * D * H * W * 4 * (1 + n)
                     gbs = by / (ms * 1e-3) / 1e9
-                    cases.append({"shape": sname, "P": P, "K": K, "n": n, "us": 1e3 * ms, "bytes": by, "GBps": gbs,
-                                  "frac": gbs / peak})
+                    cases.append({"shape": sname, "P": P, "K": K, "n": n, "boundary": boundary, "us": 1e3 * ms, "bytes": by,
+                                  "GBps": gbs, "frac": gbs / peak})
                 del m
         del x
         torch.cuda.empty_cache()
@@ -643,7 +648,8 @@ def head_sweep_leg(dev, precision="bf16", full=False):
                                 "worst_cell": {k: worst[k] for k in ("P", "K", "n", "us", "frac")}}
     return {"what": "stand-alone fused Taylor head (tante_bench_head): last deconv + Horner sum + residual + emit; algorithmic "
                     "bytes per launch = rows*K*64*s_act + B*D*H*W*4*(1+n) (boundary B of SURVEY.md 8(d)), rows = B*H*W/k0^2",
-            "boundary": "B", "bound": "hbm", "peak": peak, "unit": "GB/s",
+            "boundary": "B for patch_scale <= 8 (last deconv + Horner + emit fused), C for patch_scale >= 16 (Horner + emit over "
+                        "decoded fields, bytes = (K+1+n)*B*D*H*W*4)", "bound": "hbm", "peak": peak, "unit": "GB/s",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
             "patch_scales": list(patches), "K": [1, 2, 3, 4], "n": [1, 4, 8], "per_shape": per_shape, "clocks": clocks,
             "skipped": [c for c in cases if "skipped" in c][:8], "cases": ok}

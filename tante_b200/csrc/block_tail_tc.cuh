@@ -15,10 +15,11 @@
 // K-major SWIZZLE_128B, exactly the layout TMA would have produced); x_mid lives in the other 256 TMEM columns from the first
 // epilogue to the last.  The three 128 KB weight matrices do not fit next to that, so they STREAM from L2 through a ring of
 // 16 KB stages ([128 rows of N][64 of K]; 24 stages per tile = 384 KB per 128 tokens, L2-resident: 0.4 MB of weights in total).
-// The residual chunks arrive by TMA into per-warp staging buffers (two per warp, the first two requested before the
-// accumulator is ready), results leave by TMA stores from the same buffers.
+// The residual chunks arrive by TMA: the first of a warp's two into its staging buffer (requested before the accumulator
+// is ready), the second into a 4 KB slot of the A tile, which is idle between the first GEMM and the LayerNorm pass;
+// results leave by TMA stores from the staging buffers (training: LN2 / hidden straight from the A tile).
 // TRAIN = true additionally stores what the backward needs (x_mid, LN2 output, MLP pre-activation, hidden).
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two per TMEM lane quarter).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..17 = epilogue (four per TMEM lane quarter).
 #pragma once
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -26,13 +27,14 @@
 
 namespace tante {
 
-constexpr int kBtThreads = 64 + 32 * 8;
+constexpr int kBtEpiWarps = 16;
+constexpr int kBtThreads = 64 + 32 * kBtEpiWarps;
 constexpr int kBtC = 256;                   // embed_dim the kernel is specialised for
 constexpr int kBtKBlk = 128 * 128;          // one k-block of the A tile: [128 rows][64 bf16] = 16 KB
 constexpr int kBtWStage = 128 * 128;        // one weight stage: [128 rows of N][64 of K] bf16 = 16 KB
 constexpr int kBtWStages = 5;
 constexpr int kBtEbuf = 32 * 128;           // staging buffer: 32 rows x 128 B
-constexpr size_t kBtSmem = 1024 + 4 * kBtKBlk + kBtWStages * kBtWStage + 8 * 2 * kBtEbuf + 7 * kBtC * 4 + 2 * 4 * 2 * 32 * 2 * 4 + 256;
+constexpr size_t kBtSmem = 1024 + 4 * kBtKBlk + kBtWStages * kBtWStage + kBtEpiWarps * kBtEbuf + 7 * kBtC * 4 + 2 * 4 * 4 * 32 * 2 * 4 + 512;
 
 struct BtParams {
     const float* bo; const float* g2; const float* be2; const float* b1; const float* b2; const float* gn; const float* ben;
@@ -57,19 +59,19 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                                        // [4 k-blocks][128 rows][128 B]
     uint8_t* sW = sA + 4 * kBtKBlk;                            // [kBtWStages][128 rows][128 B]
-    uint8_t* sE = sW + kBtWStages * kBtWStage;                 // [8 warps][2][4 KB]
-    float* sP = reinterpret_cast<float*>(sE + 8 * 2 * kBtEbuf);    // bo, g2, be2, b1, b2, gn, ben
-    float* sStat = sP + 7 * kBtC;                              // [2 sets][4 quarters][2 halves][32 rows][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 4 * 2 * 32 * 2);
+    uint8_t* sE = sW + kBtWStages * kBtWStage;                 // [16 warps][4 KB]
+    float* sP = reinterpret_cast<float*>(sE + kBtEpiWarps * kBtEbuf);    // bo, g2, be2, b1, b2, gn, ben
+    float* sStat = sP + 7 * kBtC;                              // [2 sets][4 quarters][4 slices][32 rows][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 2 * 4 * 4 * 32 * 2);
     uint64_t* w_full = bars;                       // [kBtWStages]
     uint64_t* w_empty = bars + kBtWStages;         // [kBtWStages]
     uint64_t* a_full = bars + 2 * kBtWStages;      // att tile landed
     uint64_t* a_empty = a_full + 1;                // the tile's last MMA has read the A tile
-    uint64_t* a_ready = a_full + 2;                // the epilogue warps rewrote the A tile (8 arrivals)
+    uint64_t* a_ready = a_full + 2;                // the epilogue warps rewrote the A tile (16 arrivals)
     uint64_t* acc_full = a_full + 3;               // one MMA phase finished
-    uint64_t* acc_free = a_full + 4;               // the last epilogue has read the accumulator (8 arrivals)
-    uint64_t* rbar = a_full + 5;                   // [8 warps][2] residual-chunk barriers
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
+    uint64_t* acc_free = a_full + 4;               // the last epilogue has read the accumulator (16 arrivals)
+    uint64_t* rbar = a_full + 5;                   // [16 warps][2] residual-chunk barriers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * kBtEpiWarps);
 
     pdl_trigger();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -86,11 +88,11 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.has_ln_out) ptx::prefetch_tmap(&tmLnOut);
         for (int s = 0; s < kBtWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
         ptx::mbar_init(a_full, 1);
-        ptx::mbar_init(a_empty, 1);
-        ptx::mbar_init(a_ready, 8);
+        ptx::mbar_init(a_empty, TRAIN ? 1 + kBtEpiWarps : 1);     // the last GEMM's commit (+ training: the stores that read the A tile)
+        ptx::mbar_init(a_ready, kBtEpiWarps);
         ptx::mbar_init(acc_full, 1);
-        ptx::mbar_init(acc_free, 8);
-        for (int i = 0; i < 16; ++i) ptx::mbar_init(&rbar[i], 1);
+        ptx::mbar_init(acc_free, kBtEpiWarps);
+        for (int i = 0; i < 2 * kBtEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -164,56 +166,98 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quarter q = warp % 4, thread = one token row =====
+        // ===== 16 epilogue warps: TMEM lane quarter q = warp % 4 (thread = one token row), column slice cs = 0..3 =====
+        // fp32 passes: the warp owns the 32-column chunks cs and cs + 4 of its rows; bf16 passes: the 64-column k-block cs.
+        // (Four warps per scheduler: the epilogue is a chain of TMEM / shared-memory round trips per row, and with two
+        //  warps per scheduler -- the first version, 8 epilogue warps -- the issue slots were 30 % busy.)
         const int ew = warp - 2;
         const int q = warp & 3;
-        const int half = ew >> 2;
-        uint8_t* ebuf = sE + (size_t)ew * 2 * kBtEbuf;
+        const int cs = ew >> 2;
+        uint8_t* ebuf = sE + (size_t)ew * kBtEbuf;             // own staging buffer (4 KB)
+        uint8_t* aslot = sA + (size_t)ew * kBtEbuf;            // phase 1: landing zone of the second residual chunk (A tile is idle)
+        uint8_t* aown = sA + (size_t)cs * kBtKBlk + (size_t)q * 32 * 128;    // this warp's 32 rows of k-block cs inside the A tile
         uint64_t* rb = rbar + ew * 2;
         uint32_t rph = 0;             // bit b = phase of rb[b]
         uint32_t af = 0;              // completed acc_full waits
-        int st_last = -1, st_prev = -1;      // staging buffers of the two most recent TMA-store groups of this warp
-        // a staging buffer may be rewritten once the TMA store that last read it has drained
-        auto buf_free = [&](int b) {
-            if (lane == 0) {
-                if (st_last == b) ptx::bulk_wait_read<0>();
-                else if (st_prev == b) ptx::bulk_wait_read<1>();
-            }
+        bool st_pending = false;      // a TMA store of this warp may still be reading ebuf
+        auto ebuf_free = [&]() {
+            if (st_pending && lane == 0) ptx::bulk_wait_read<0>();
+            st_pending = false;
             __syncwarp();
         };
-        auto buf_stored = [&](int b) { st_prev = st_last; st_last = b; };
-        const int arow = q * 32 + lane;                 // row inside the A tile
         const float* bo = sP; const float* g2 = sP + kBtC; const float* be2 = sP + 2 * kBtC; const float* b1 = sP + 3 * kBtC;
         const float* b2 = sP + 4 * kBtC; const float* gn = sP + 5 * kBtC; const float* ben = sP + 6 * kBtC;
+        constexpr bool dropping = MODE == 2;
+
+        // row statistics of the four column slices of a quarter -> mean, 1 / std
+        auto row_stats = [&](int set, float rsum, float rsq, float& mean, float& rstd) {
+            float* st = sStat + (size_t)set * 4 * 4 * 32 * 2;
+            st[((q * 4 + cs) * 32 + lane) * 2 + 0] = rsum;
+            st[((q * 4 + cs) * 32 + lane) * 2 + 1] = rsq;
+            ptx::tc_wait_st();
+            ptx::tc_fence_before();
+            named_bar_sync(5, 16 * 32);             // every epilogue warp: statistics + TMEM rows written, A-tile slots consumed
+            ptx::tc_fence_after();
+            float s = 0.f, sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { s += st[((q * 4 + c) * 32 + lane) * 2]; sq += st[((q * 4 + c) * 32 + lane) * 2 + 1]; }
+            mean = s * (1.0f / kBtC);
+            const float var = fmaxf(sq * (1.0f / kBtC) - mean * mean, 0.f);
+            rstd = rsqrtf(var + 1e-5f);
+        };
+        // LayerNorm of this warp's k-block (64 columns out of the TMEM x region) -> bf16 -> 32 rows x 128 B at `dst` (SWIZZLE_128B)
+        auto ln_kblock = [&](uint32_t tm_x, float mean, float rstd, const float* gam, const float* bet, uint8_t* dst, int drow) {
+            const float mr = mean * rstd;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t r0[32];
+                ptx::tmem_ld_32x32(tm_x + (uint32_t)(cs * 64 + hh * 32), r0);
+                ptx::tc_wait_ld();
+                const float* gs = gam + cs * 64 + hh * 32;
+                const float* bs = bet + cs * 64 + hh * 32;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = c * 8 + j * 2;
+                        const float a = fmaf(fmaf(__uint_as_float(r0[col]), rstd, -mr), gs[col], bs[col]);
+                        const float bb = fmaf(fmaf(__uint_as_float(r0[col + 1]), rstd, -mr), gs[col + 1], bs[col + 1]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(dst + sw128_off(drow, hh * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        };
 
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int row0 = tile * 128 + q * 32;
             const uint32_t tm_acc = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t tm_x = tm_acc + 256u;
 
-            // ---------------- phase 1: x_mid = x + acc + bo ; LN2 -> A tile ----------------
-            buf_free(0); buf_free(1);
+            // ---------------- phase 1: x_mid = x + drop(acc + bo) ; LN2 -> A tile ----------------
+            ebuf_free();
             if (lane == 0) {
-                for (int b = 0; b < 2; ++b) {
-                    ptx::mbar_arrive_expect_tx(&rb[b], kBtEbuf);
-                    ptx::tma_load_2d(ebuf + b * kBtEbuf, &tmXin, &rb[b], (half + 2 * b) * 32, row0);
-                }
+                ptx::mbar_arrive_expect_tx(&rb[0], kBtEbuf);
+                ptx::tma_load_2d(ebuf, &tmXin, &rb[0], cs * 32, row0);
             }
-            st_last = st_prev = -1;
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
+            if (lane == 0) {      // the A tile has been consumed by the first GEMM: its 4 KB slot takes the second chunk
+                ptx::mbar_arrive_expect_tx(&rb[1], kBtEbuf);
+                ptx::tma_load_2d(aslot, &tmXin, &rb[1], (cs + 4) * 32, row0);
+            }
             float rsum = 0.f, rsq = 0.f;
 #pragma unroll 1
-            for (int jc = 0; jc < 4; ++jc) {
-                const int ch = half + 2 * jc;
-                const int b = jc & 1;
-                uint8_t* buf = ebuf + b * kBtEbuf;
+            for (int jc = 0; jc < 2; ++jc) {
+                const int ch = cs + 4 * jc;
+                uint8_t* buf = jc == 0 ? ebuf : aslot;
                 uint32_t r0[32];
                 ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r0);
-                ptx::mbar_wait(&rb[b], (rph >> b) & 1u); rph ^= 1u << b;
+                ptx::mbar_wait(&rb[jc], (rph >> jc) & 1u); rph ^= 1u << jc;
                 ptx::tc_wait_ld();
                 const float* bs = bo + ch * 32;
-                constexpr bool dropping = MODE == 2;
                 uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -234,7 +278,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
                     r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
                     rsum += (o.x + o.y) + (o.z + o.w);
-                    rsq = fmaf(o.x, o.x, rsq); rsq = fmaf(o.y, o.y, rsq); rsq = fmaf(o.z, o.z, rsq); rsq = fmaf(o.w, o.w, rsq);
+                    rsq += fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, o.w * o.w)));
                     if (TRAIN) *pp = o;
                 }
                 ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r0);
@@ -242,62 +286,20 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { ptx::tma_store_2d(&tmXmid, buf, ch * 32, row0); ptx::bulk_commit(); }
-                    buf_stored(b);
-                } else {
-                    __syncwarp();
-                }
-                if (jc + 2 < 4) {           // refill this buffer with the chunk two steps ahead
-                    if (TRAIN) buf_free(b);
-                    if (lane == 0) {
-                        ptx::mbar_arrive_expect_tx(&rb[b], kBtEbuf);
-                        ptx::tma_load_2d(buf, &tmXin, &rb[b], (ch + 4) * 32, row0);
-                    }
-                    if (TRAIN) { st_last = (st_last == b) ? -1 : st_last; st_prev = (st_prev == b) ? -1 : st_prev; }
                 }
             }
+            if (TRAIN) {      // both x_mid stores have drained: the slot is about to be overwritten by the LayerNorm output
+                if (lane == 0) ptx::bulk_wait_read<0>();
+                __syncwarp();
+            }
             {
-                float* st = sStat + ((q * 2 + half) * 32 + lane) * 2;
-                st[0] = rsum; st[1] = rsq;
-                ptx::tc_wait_st();
-                ptx::tc_fence_before();
-                named_bar_sync(1 + q, 64);          // the partner warp's x_mid chunks (TMEM) and row statistics are complete
-                ptx::tc_fence_after();
-                const float* so = sStat + ((q * 2 + (half ^ 1)) * 32 + lane) * 2;
-                const float mean = (rsum + so[0]) * (1.0f / kBtC);
-                const float var = fmaxf((rsq + so[1]) * (1.0f / kBtC) - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll 1
-                for (int jc = 0; jc < 2; ++jc) {
-                    const int ch = half + 2 * jc;              // 64-column chunk = k-block of the A tile
-                    uint32_t r0[32], r1[32];
-                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64), r0);
-                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64 + 32), r1);
-                    if (TRAIN) buf_free(jc);
-                    ptx::tc_wait_ld();
-                    const float* gs = g2 + ch * 64;
-                    const float* bs = be2 + ch * 64;
-                    uint8_t* abase = sA + ch * kBtKBlk;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int col = c * 8 + j * 2;
-                            const float a = (__uint_as_float(col < 32 ? r0[col] : r1[col - 32]) - mean) * rstd * gs[col] + bs[col];
-                            const float bb = (__uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) - mean) * rstd * gs[col + 1] + bs[col + 1];
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-                        }
-                        const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(abase + sw128_off(arow, c)) = v;
-                        if (TRAIN) *reinterpret_cast<uint4*>(ebuf + jc * kBtEbuf + sw128_off(lane, c)) = v;
-                    }
-                    if (TRAIN) {
-                        ptx::fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) { ptx::tma_store_2d(&tmLn2, ebuf + jc * kBtEbuf, ch * 64, row0); ptx::bulk_commit(); }
-                        buf_stored(jc);
-                    }
+                float mean, rstd;
+                row_stats(0, rsum, rsq, mean, rstd);
+                ln_kblock(tm_x, mean, rstd, g2, be2, aown, lane);
+                if (TRAIN) {      // the saved LN2 output leaves straight from the A tile (same 32-row x 128-B swizzled box)
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { ptx::tma_store_2d(&tmLn2, aown, cs * 64, row0); ptx::bulk_commit(); }
                 }
             }
             ptx::fence_proxy_async();
@@ -308,24 +310,24 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // ---------------- phase 2: hidden = gelu_tanh(acc + b1) -> A tile ----------------
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
+            if (TRAIN) {      // the LN2 store has finished reading this warp's rows of the A tile
+                if (lane == 0) ptx::bulk_wait_read<0>();
+                __syncwarp();
+            }
 #pragma unroll 1
-            for (int jc = 0; jc < 2; ++jc) {
-                const int ch = half + 2 * jc;
-                uint32_t r0[32], r1[32];
-                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 64), r0);
-                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 64 + 32), r1);
-                if (TRAIN) { buf_free(0); buf_free(1); }
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t r0[32];
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(cs * 64 + hh * 32), r0);
                 ptx::tc_wait_ld();
-                const float* bs = b1 + ch * 64;
-                uint8_t* abase = sA + ch * kBtKBlk;
+                const float* bs = b1 + cs * 64 + hh * 32;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint32_t pk[4], pp[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int col = c * 8 + j * 2;
-                        float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + bs[col];
-                        float bb = __uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) + bs[col + 1];
+                        float a = __uint_as_float(r0[col]) + bs[col];
+                        float bb = __uint_as_float(r0[col + 1]) + bs[col + 1];
                         if (TRAIN) {
                             // the backward differentiates the activation at the SAVED (bf16) pre-activation: use it here too
                             __nv_bfloat162 pr = __floats2bfloat162_rn(a, bb);
@@ -336,46 +338,42 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(gelu_tanh_fast(a), gelu_tanh_fast(bb));
                         pk[j] = *reinterpret_cast<uint32_t*>(&h2);
                     }
-                    const uint4 v = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(abase + sw128_off(arow, c)) = v;
-                    if (TRAIN) {
-                        *reinterpret_cast<uint4*>(ebuf + sw128_off(lane, c)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
-                        *reinterpret_cast<uint4*>(ebuf + kBtEbuf + sw128_off(lane, c)) = v;
-                    }
+                    *reinterpret_cast<uint4*>(aown + sw128_off(lane, hh * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (TRAIN) *reinterpret_cast<uint4*>(ebuf + sw128_off(lane, hh * 4 + c)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
                 }
-                if (TRAIN) {
-                    ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        ptx::tma_store_2d(&tmHpre, ebuf, ch * 64, row0);
-                        ptx::bulk_commit();
-                        ptx::tma_store_2d(&tmHact, ebuf + kBtEbuf, ch * 64, row0);
-                        ptx::bulk_commit();
-                    }
-                    buf_stored(0); buf_stored(1);
+            }
+            if (TRAIN) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmHpre, ebuf, cs * 64, row0);
+                    ptx::tma_store_2d(&tmHact, aown, cs * 64, row0);
+                    ptx::bulk_commit();
                 }
+                st_pending = true;
             }
             ptx::fence_proxy_async();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(a_ready);
 
-            // ---------------- phase 3: x_out = x_mid + acc + b2 ; LN1' ----------------
+            // ---------------- phase 3: x_out = x_mid + drop(acc + b2) ; LN1' ----------------
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
+            if (TRAIN) {      // hidden / pre-activation stores drained: the producer may refill the A tile
+                ebuf_free();
+                if (lane == 0) ptx::mbar_arrive(a_empty);
+            }
             rsum = 0.f; rsq = 0.f;
 #pragma unroll 1
-            for (int jc = 0; jc < 4; ++jc) {
-                const int ch = half + 2 * jc;
-                const int b = jc & 1;
-                uint8_t* buf = ebuf + b * kBtEbuf;
+            for (int jc = 0; jc < 2; ++jc) {
+                const int ch = cs + 4 * jc;
                 uint32_t r0[32], r1[32];
                 ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r0);
                 ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 32), r1);
-                buf_free(b);
+                ebuf_free();
                 ptx::tc_wait_ld();
                 const float* bs = b2 + ch * 32;
-                constexpr bool dropping = MODE == 2;
                 uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -392,64 +390,33 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     o.x += __uint_as_float(r1[c * 4 + 0]); o.y += __uint_as_float(r1[c * 4 + 1]);
                     o.z += __uint_as_float(r1[c * 4 + 2]); o.w += __uint_as_float(r1[c * 4 + 3]);
-                    *reinterpret_cast<float4*>(buf + sw128_off(lane, c)) = o;
+                    *reinterpret_cast<float4*>(ebuf + sw128_off(lane, c)) = o;
                     r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
                     r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
                     rsum += (o.x + o.y) + (o.z + o.w);
-                    rsq = fmaf(o.x, o.x, rsq); rsq = fmaf(o.y, o.y, rsq); rsq = fmaf(o.z, o.z, rsq); rsq = fmaf(o.w, o.w, rsq);
+                    rsq += fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, o.w * o.w)));
                 }
                 if (p.has_ln_out) ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r0);
                 ptx::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) { ptx::tma_store_2d(&tmXout, buf, ch * 32, row0); ptx::bulk_commit(); }
-                buf_stored(b);
+                if (lane == 0) { ptx::tma_store_2d(&tmXout, ebuf, ch * 32, row0); ptx::bulk_commit(); }
+                st_pending = true;
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc_free);          // the next tile's first GEMM may overwrite the accumulator
             if (p.has_ln_out) {
-                float* st = sStat + 4 * 2 * 32 * 2 + ((q * 2 + half) * 32 + lane) * 2;      // second set
-                st[0] = rsum; st[1] = rsq;
-                ptx::tc_wait_st();
+                float mean, rstd;
+                row_stats(1, rsum, rsq, mean, rstd);
+                ebuf_free();
+                ln_kblock(tm_x, mean, rstd, gn, ben, ebuf, lane);
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { ptx::tma_store_2d(&tmLnOut, ebuf, cs * 64, row0); ptx::bulk_commit(); }
+                st_pending = true;
+                // the other warps of the quarter have read this warp's x_out columns out of TMEM: the next tile may overwrite them
                 ptx::tc_fence_before();
-                named_bar_sync(1 + q, 64);
-                ptx::tc_fence_after();
-                const float* so = sStat + 4 * 2 * 32 * 2 + ((q * 2 + (half ^ 1)) * 32 + lane) * 2;
-                const float mean = (rsum + so[0]) * (1.0f / kBtC);
-                const float var = fmaxf((rsq + so[1]) * (1.0f / kBtC) - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll 1
-                for (int jc = 0; jc < 2; ++jc) {
-                    const int ch = half + 2 * jc;
-                    uint8_t* buf = ebuf + jc * kBtEbuf;
-                    uint32_t r0[32], r1[32];
-                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64), r0);
-                    ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 64 + 32), r1);
-                    buf_free(jc);
-                    ptx::tc_wait_ld();
-                    const float* gs = gn + ch * 64;
-                    const float* bs = ben + ch * 64;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int col = c * 8 + j * 2;
-                            const float a = (__uint_as_float(col < 32 ? r0[col] : r1[col - 32]) - mean) * rstd * gs[col] + bs[col];
-                            const float bb = (__uint_as_float(col + 1 < 32 ? r0[col + 1] : r1[col + 1 - 32]) - mean) * rstd * gs[col + 1] + bs[col + 1];
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-                        }
-                        *reinterpret_cast<uint4*>(buf + sw128_off(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
-                    ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { ptx::tma_store_2d(&tmLnOut, buf, ch * 64, row0); ptx::bulk_commit(); }
-                    buf_stored(jc);
-                }
-                // the partner has read this warp's x_out chunks out of TMEM: the next tile may overwrite them with its x_mid
-                ptx::tc_fence_before();
-                named_bar_sync(1 + q, 64);
+                named_bar_sync(1 + q, 4 * 32);
                 ptx::tc_fence_after();
             }
         }

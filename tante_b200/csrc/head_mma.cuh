@@ -139,34 +139,6 @@ taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) 
         }
     }
 
-    // u0 pixels of this thread's items for tile `t` (128-bit loads).  They are requested ONE TILE AHEAD (u0n, below): a
-    // tile's own u0 then never sits on its critical path (the previous version requested them at the top of the tile and
-    // waited for DRAM in the emit).  A tile only ever writes its own pixel rectangle, so reading the next tile's last
-    // frame before this tile's ring writes is safe.
-    auto load_u0 = [&](long long t, float4 (&u)[NJ]) {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) u[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= ntiles) return;
-        const long long bh = t / tpr;
-        const int wpc = (int)(t % tpr);
-        const int b = (int)(bh / g.Hp), hpp = (int)(bh % g.Hp);
-        if (hp.n_arr[b] <= 0) return;
-        const int xvalid = min(NT, g.Wp - wpc * NT) * P;
-        const int fc = hp.fcount ? hp.fcount[b] : g.T;
-        const float* u0p = hp.u_ring + (size_t)(b * g.T + (fc + g.T - 1) % g.T) * g.D * HW + (size_t)hpp * P * g.W + (size_t)wpc * XW;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int item = tid + THREADS * j;
-            if (kItemRegs) {
-                if (soffR[j] >= 0 && xcolR[j] < xvalid) u[j] = *reinterpret_cast<const float4*>(u0p + goffR[j]);
-            } else if (item < nitems && ((item & ((1 << lXQ) - 1)) << 2) < xvalid) {
-                u[j] = *reinterpret_cast<const float4*>(u0p + item_goff(item));
-            }
-        }
-    };
-    float4 u0n[NJ];
-    load_u0(blockIdx.x, u0n);
-
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long bh = tile / tpr;
         const int wpc = (int)(tile % tpr);
@@ -175,10 +147,22 @@ taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) 
         const int n = hp.n_arr[b];
         const int fc = hp.fcount ? hp.fcount[b] : g.T;
         const size_t pix0 = (size_t)hpp * P * g.W + (size_t)wpc * XW;
+        // u0 of this thread's items: in flight during phase 1  (requesting them one tile ahead was measured SLOWER on B200:
+        // K = 1, n = 1 on the TRL shape 45.7 -> 63 us -- the extra per-tile index chain costs more than the latency it hides)
         float4 u0r[NJ];
+        {
+            const float* u0p = hp.u_ring + (size_t)(b * g.T + (fc + g.T - 1) % g.T) * g.D * HW + pix0;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) u0r[j] = u0n[j];
-        load_u0(tile + gridDim.x, u0n);                              // next tile's u0: in flight during this whole tile
+            for (int j = 0; j < NJ; ++j) {
+                u0r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int item = tid + THREADS * j;
+                if (kItemRegs) {
+                    if (n > 0 && soffR[j] >= 0 && xcolR[j] < xvalid) u0r[j] = *reinterpret_cast<const float4*>(u0p + goffR[j]);
+                } else if (n > 0 && item < nitems && ((item & ((1 << lXQ) - 1)) << 2) < xvalid) {
+                    u0r[j] = *reinterpret_cast<const float4*>(u0p + item_goff(item));
+                }
+            }
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                             // z tile visible; previous emit is done with S
 

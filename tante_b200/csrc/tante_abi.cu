@@ -724,8 +724,8 @@ void launch_emit_wide(tante_handle_s* h, const StepIO& io, int B, const RolloutS
     ep.frames = io.frames; ep.n_cap = io.n_cap;
     ep.ptrs = io.rollout ? rs.ptrs : nullptr; ep.ring_out = io.ring_out; ep.cum = io.rollout ? rs.cum : nullptr; ep.n_roll = io.n_roll;
     ep.B = B; ep.D = h->D; ep.T = h->T; ep.HW = (long long)h->cfg.H * h->cfg.W;
-    const long long total = (long long)B * h->D * ep.HW;
-    taylor_emit_kernel<<<blocks_for(total, 256), 256, 0, st>>>(ep);
+    REQUIRE(ep.HW % 4 == 0, "H * W must be a multiple of 4");
+    taylor_emit_kernel<<<dim3(blocks_for(ep.HW / 4, 256), (unsigned)h->D, (unsigned)B), 256, 0, st>>>(ep);
     CK(cudaGetLastError());
     h->launches++;
 }

@@ -126,8 +126,8 @@ wide_deconv_post_kernel(const TA* __restrict__ S, int ldS, int hi, int wi, int C
     else out[idx] = from_f32<TA>(v);
 }
 
-// Taylor / Horner emit over decoded derivative fields (tante.py:165-171 + formatter transpose + window cat, as head_mma.cuh):
-// thread = one (sample, field, pixel); dfield = [K][B][D][HW] fp32.
+// Taylor / Horner emit over decoded derivative fields (tante.py:165-171 + formatter transpose + window cat, as head_mma.cuh);
+// dfield = [K][B][D][HW] fp32.
 struct EmitParams {
     const float* dfield;
     int K; float fi;
@@ -136,35 +136,43 @@ struct EmitParams {
     const RolloutPtrs* ptrs; float* ring_out; const int* cum; int n_roll;
     int B, D, T; long long HW;
 };
+// grid = (ceil(HW / 4 / 256), D, B): thread = 4 consecutive pixels of one (sample, field) plane -- no index divisions,
+// 128-bit loads / stores on the channels-first tensors
 __global__ void __launch_bounds__(256) taylor_emit_kernel(EmitParams p) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per = (long long)p.D * p.HW;
-    if (idx >= (long long)p.B * per) return;
-    const int b = (int)(idx / per);
-    const long long r = idx - (long long)b * per;
-    const int d = (int)(r / p.HW);
-    const long long pix = r - (long long)d * p.HW;
+    const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (pix >= p.HW) return;
+    const int d = blockIdx.y, b = blockIdx.z;
     const int n = p.n_arr[b];
     if (n <= 0) return;
     const int fc = p.fcount ? p.fcount[b] : p.T;
-    const float u0 = p.u_ring[((size_t)(b * p.T + (fc + p.T - 1) % p.T) * p.D + d) * p.HW + pix];
-    float dk[kMaxOrder];
+    const long long per = (long long)p.D * p.HW;
+    const size_t plane = (size_t)d * p.HW + pix;
+    const float4 u0 = *reinterpret_cast<const float4*>(p.u_ring + (size_t)(b * p.T + (fc + p.T - 1) % p.T) * per + plane);
+    float4 dk[kMaxOrder];
 #pragma unroll
-    for (int k = 0; k < kMaxOrder; ++k) dk[k] = k < p.K ? p.dfield[(size_t)k * p.B * per + idx] : 0.f;
+    for (int k = 0; k < kMaxOrder; ++k)
+        dk[k] = k < p.K ? *reinterpret_cast<const float4*>(p.dfield + ((size_t)k * p.B + b) * per + plane) : make_float4(0.f, 0.f, 0.f, 0.f);
     const int cum = p.cum ? p.cum[b] : 0;
     float* y_out = p.ptrs ? p.ptrs->y_out : nullptr;
     for (int i = 1; i <= n; ++i) {
         const float dt = (float)i * p.fi;
-        float v = 0.f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = kMaxOrder; k >= 1; --k)
-            if (k <= p.K) v = (dk[k - 1] + v) * (dt / (float)k);
-        const float val = v + u0;
-        if (p.frames) p.frames[(((size_t)b * p.n_cap + (i - 1)) * p.D + d) * p.HW + pix] = val;
+            if (k <= p.K) {
+                const float sc = dt / (float)k;
+                v.x = (dk[k - 1].x + v.x) * sc; v.y = (dk[k - 1].y + v.y) * sc;
+                v.z = (dk[k - 1].z + v.z) * sc; v.w = (dk[k - 1].w + v.w) * sc;
+            }
+        v.x += u0.x; v.y += u0.y; v.z += u0.z; v.w += u0.w;
+        if (p.frames) *reinterpret_cast<float4*>(p.frames + ((size_t)b * p.n_cap + (i - 1)) * per + plane) = v;
         if (y_out) {
             const int fidx = cum + i - 1;
-            if (fidx < p.n_roll) y_out[(((size_t)b * p.n_roll + fidx) * p.HW + pix) * p.D + d] = val;
-            if (i > n - p.T) p.ring_out[((size_t)(b * p.T + (fc + i - 1) % p.T) * p.D + d) * p.HW + pix] = val;
+            if (fidx < p.n_roll) {
+                float* yp = y_out + (((size_t)b * p.n_roll + fidx) * p.HW + pix) * p.D + d;
+                yp[0] = v.x; yp[p.D] = v.y; yp[2 * p.D] = v.z; yp[3 * p.D] = v.w;
+            }
+            if (i > n - p.T) *reinterpret_cast<float4*>(p.ring_out + (size_t)(b * p.T + (fc + i - 1) % p.T) * per + plane) = v;
         }
     }
 }

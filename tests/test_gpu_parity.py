@@ -339,7 +339,12 @@ def test_next_scope_forward_and_rollout_fp32(name):
     assert rel_l2(yr.cpu().reshape(-1)[::s].numpy(), z["roll_frames"]) < FP32_FIELD_TOL
     if "stage_deriv0" in z.files:
         B = meta["B"]
-        der = model.debug_stage("deriv", cfg.taylor_order * B * cfg.n_fields * cfg.H * cfg.W).cpu().numpy()
+        with torch.inference_mode():
+            model(x.cuda(), meta["out_T"])
+            der = model.debug_stage("deriv", cfg.taylor_order * B * cfg.n_fields * cfg.H * cfg.W).cpu().numpy()
+        der = der.reshape(cfg.taylor_order, B, cfg.n_fields, cfg.H, cfg.W)
+        for k in range(cfg.taylor_order):
+            assert rel_l2(der[k], z[f"stage_deriv{k}"][:, 0]) < FP32_DERIV_TOL, k
 
 
 @pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96"])

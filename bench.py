@@ -60,11 +60,20 @@ def parse():
                     help="default line only: skip the rollout / head_sweep sub-records of the default (train) run")
     ap.add_argument("--amp-mix", action="store_true", help="rollout: per-trajectory input amplitudes (different step sequences)")
     ap.add_argument("--dropout", type=float, default=0.0, help="train: dropout probability (configs/tante.yaml:29 uses 0.1)")
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="strong scaling: total samples / trajectories per step, split evenly over the ranks")
     a = ap.parse_args()
     if a.shape is None:
         a.shape = "active_matter" if a.workload == "train" else "rayleigh_benard"
     if a.batch is None:
         a.batch = 16 if a.workload == "train" else 64
+    a.scaling = "weak"
+    if a.global_batch:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if a.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of ranks")
+        a.batch = a.global_batch // world
+        a.scaling = "strong"
     return a
 
 
@@ -418,7 +427,7 @@ def rollout_measure(args, dev, world, rank, with_cpu_baseline=True):
     line = {
         "metric": "rollout_trajectories_per_s", "value": traj * K_ / (ms_total * 1e-3), "unit": "trajectories/s",
         "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_total / K_, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
+        "scaling": getattr(args, "scaling", "weak"), "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
         "config": bench_config(args, B),
         "model_calls_per_trajectory": {"max": model_calls, "min": int(min(steps_h)), "mean": sum(steps_h) / len(steps_h)},
         "frames_first_call": {str(k): ns_first.count(k) for k in sorted(set(ns_first))},
@@ -912,7 +921,7 @@ def run_b200_train(args):
     line = {
         "metric": "training_samples_per_s", "value": samples * K_ / (ms_total * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": K_, "warmup": W_, "ms_per_step": ms_total / K_, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
+        "scaling": getattr(args, "scaling", "weak"), "vs_baseline": None, "dtype": "bf16" if tensor_mode else "f32", "data": "synthetic",
         "config": train_config(args, B),
         "final_loss": final_loss,
         "model_calls_per_step": n_out,

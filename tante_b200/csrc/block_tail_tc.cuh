@@ -167,6 +167,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else {
         // ===== 16 epilogue warps: TMEM lane quarter q = warp % 4 (thread = one token row), column slice cs = 0..3 =====
+        // fp32 passes: the warp owns the 32-column chunks cs and cs + 4 of its rows; bf16 passes: the 64-column k-block cs.
         // (Four warps per scheduler: the epilogue is a chain of TMEM / shared-memory round trips per row, and with two
         //  warps per scheduler -- the first version, 8 epilogue warps -- the issue slots were 30 % busy.)
         const int ew = warp - 2;
@@ -204,27 +205,29 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const float var = fmaxf(sq * (1.0f / kBtC) - mean * mean, 0.f);
             rstd = rsqrtf(var + 1e-5f);
         };
-        // LayerNorm of this warp's k-block (its 64 columns of the row, still in registers: xa = columns 0..31, xb = 32..63 of
-        // the block) -> bf16 -> 32 rows x 128 B at `dst` (SWIZZLE_128B)
-        auto ln_kblock = [&](const uint32_t (&xa)[32], const uint32_t (&xb)[32], float mean, float rstd, const float* gam,
-                             const float* bet, uint8_t* dst) {
+        // LayerNorm of this warp's k-block (64 columns out of the TMEM x region) -> bf16 -> 32 rows x 128 B at `dst` (SWIZZLE_128B)
+        auto ln_kblock = [&](uint32_t tm_x, float mean, float rstd, const float* gam, const float* bet, uint8_t* dst, int drow) {
             const float mr = mean * rstd;
-            const float* gs = gam + cs * 64;
-            const float* bs = bet + cs * 64;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t r0[32];
+                ptx::tmem_ld_32x32(tm_x + (uint32_t)(cs * 64 + hh * 32), r0);
+                ptx::tc_wait_ld();
+                const float* gs = gam + cs * 64 + hh * 32;
+                const float* bs = bet + cs * 64 + hh * 32;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t pk[4];
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t pk[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = c * 8 + j * 2;
-                    const float v0 = __uint_as_float(col < 32 ? xa[col] : xb[col - 32]);
-                    const float v1 = __uint_as_float(col + 1 < 32 ? xa[col + 1] : xb[col + 1 - 32]);
-                    const float a = fmaf(fmaf(v0, rstd, -mr), gs[col], bs[col]);
-                    const float bb = fmaf(fmaf(v1, rstd, -mr), gs[col + 1], bs[col + 1]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-                    pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = c * 8 + j * 2;
+                        const float a = fmaf(fmaf(__uint_as_float(r0[col]), rstd, -mr), gs[col], bs[col]);
+                        const float bb = fmaf(fmaf(__uint_as_float(r0[col + 1]), rstd, -mr), gs[col + 1], bs[col + 1]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+                        pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(dst + sw128_off(drow, hh * 4 + c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
-                *reinterpret_cast<uint4*>(dst + sw128_off(lane, c)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         };
 
@@ -232,29 +235,27 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int row0 = tile * 128 + q * 32;
             const uint32_t tm_acc = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t tm_x = tm_acc + 256u;
-            // The warp owns the 64 columns [cs * 64, cs * 64 + 64) of its 32 rows in EVERY pass (32-column chunks 2 cs and
-            // 2 cs + 1 = k-block cs): x_mid / x_out stay in registers from the residual pass to the LayerNorm pass, and the
-            // TMEM copy of x_mid is written and later read by the same thread.  (The TMEM read port -- 64 B / cycle per SM --
-            // is what bounds these epilogues: every avoided re-read of a 128 KB tile is ~2k cycles.)
-            uint32_t xa[32], xb[32];
 
             // ---------------- phase 1: x_mid = x + drop(acc + bo) ; LN2 -> A tile ----------------
             ebuf_free();
             if (lane == 0) {
                 ptx::mbar_arrive_expect_tx(&rb[0], kBtEbuf);
-                ptx::tma_load_2d(ebuf, &tmXin, &rb[0], cs * 64, row0);
+                ptx::tma_load_2d(ebuf, &tmXin, &rb[0], cs * 32, row0);
             }
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
             if (lane == 0) {      // the A tile has been consumed by the first GEMM: its 4 KB slot takes the second chunk
                 ptx::mbar_arrive_expect_tx(&rb[1], kBtEbuf);
-                ptx::tma_load_2d(aslot, &tmXin, &rb[1], cs * 64 + 32, row0);
+                ptx::tma_load_2d(aslot, &tmXin, &rb[1], (cs + 4) * 32, row0);
             }
             float rsum = 0.f, rsq = 0.f;
-            // one 32-column chunk: r (accumulator in, x_mid out, in place), residual chunk in `buf`
-            auto resid_chunk = [&](uint32_t (&r)[32], int ch, uint8_t* buf, uint64_t* bar, int bit) {
-                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r);
-                ptx::mbar_wait(bar, (rph >> bit) & 1u); rph ^= 1u << bit;
+#pragma unroll 1
+            for (int jc = 0; jc < 2; ++jc) {
+                const int ch = cs + 4 * jc;
+                uint8_t* buf = jc == 0 ? ebuf : aslot;
+                uint32_t r0[32];
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r0);
+                ptx::mbar_wait(&rb[jc], (rph >> jc) & 1u); rph ^= 1u << jc;
                 ptx::tc_wait_ld();
                 const float* bs = bo + ch * 32;
                 uint4 dw = make_uint4(0u, 0u, 0u, 0u);
@@ -263,10 +264,10 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     float4* pp = reinterpret_cast<float4*>(buf + sw128_off(lane, c));
                     const float4 x = *pp;
                     float4 o;
-                    o.x = __uint_as_float(r[c * 4 + 0]) + bs[c * 4 + 0];
-                    o.y = __uint_as_float(r[c * 4 + 1]) + bs[c * 4 + 1];
-                    o.z = __uint_as_float(r[c * 4 + 2]) + bs[c * 4 + 2];
-                    o.w = __uint_as_float(r[c * 4 + 3]) + bs[c * 4 + 3];
+                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0];
+                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1];
+                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2];
+                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3];
                     if (dropping) {       // x + drop(attention branch): 8 consecutive columns share one Philox group
                         if ((c & 1) == 0) dw = drop_words(p.drop, p.site1, (unsigned long long)(row0 + lane) * (kBtC / 8) + ch * 4 + (c >> 1));
                         const int l0 = (c & 1) * 4;
@@ -274,21 +275,19 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         o.z *= drop_mul(p.drop, dw, l0 + 2); o.w *= drop_mul(p.drop, dw, l0 + 3);
                     }
                     o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                    r[c * 4 + 0] = __float_as_uint(o.x); r[c * 4 + 1] = __float_as_uint(o.y);
-                    r[c * 4 + 2] = __float_as_uint(o.z); r[c * 4 + 3] = __float_as_uint(o.w);
+                    r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
+                    r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
                     rsum += (o.x + o.y) + (o.z + o.w);
                     rsq += fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, o.w * o.w)));
                     if (TRAIN) *pp = o;
                 }
-                ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r);
+                ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r0);
                 if (TRAIN) {
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { ptx::tma_store_2d(&tmXmid, buf, ch * 32, row0); ptx::bulk_commit(); }
                 }
-            };
-            resid_chunk(xa, 2 * cs, ebuf, &rb[0], 0);
-            resid_chunk(xb, 2 * cs + 1, aslot, &rb[1], 1);
+            }
             if (TRAIN) {      // both x_mid stores have drained: the slot is about to be overwritten by the LayerNorm output
                 if (lane == 0) ptx::bulk_wait_read<0>();
                 __syncwarp();
@@ -296,7 +295,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             {
                 float mean, rstd;
                 row_stats(0, rsum, rsq, mean, rstd);
-                ln_kblock(xa, xb, mean, rstd, g2, be2, aown);
+                ln_kblock(tm_x, mean, rstd, g2, be2, aown, lane);
                 if (TRAIN) {      // the saved LN2 output leaves straight from the A tile (same 32-row x 128-B swizzled box)
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -366,48 +365,43 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lane == 0) ptx::mbar_arrive(a_empty);
             }
             rsum = 0.f; rsq = 0.f;
-            ptx::tc_wait_st();                  // this thread's x_mid columns (written in phase 1)
-            // one 32-column chunk: r = accumulator in, x_out out (in place); x_mid comes out of TMEM 16 columns at a time
-            auto out_chunk = [&](uint32_t (&r)[32], int ch) {
-                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r);
+#pragma unroll 1
+            for (int jc = 0; jc < 2; ++jc) {
+                const int ch = cs + 4 * jc;
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32(tm_acc + (uint32_t)(ch * 32), r0);
+                ptx::tmem_ld_32x32(tm_x + (uint32_t)(ch * 32), r1);
                 ebuf_free();
+                ptx::tc_wait_ld();
                 const float* bs = b2 + ch * 32;
                 uint4 dw = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int h16 = 0; h16 < 2; ++h16) {
-                    uint32_t xm[16];
-                    ptx::tmem_ld_32x16(tm_x + (uint32_t)(ch * 32 + h16 * 16), xm);
-                    ptx::tc_wait_ld();
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        const int c = h16 * 4 + c4;
-                        float4 o;
-                        o.x = __uint_as_float(r[c * 4 + 0]) + bs[c * 4 + 0];
-                        o.y = __uint_as_float(r[c * 4 + 1]) + bs[c * 4 + 1];
-                        o.z = __uint_as_float(r[c * 4 + 2]) + bs[c * 4 + 2];
-                        o.w = __uint_as_float(r[c * 4 + 3]) + bs[c * 4 + 3];
-                        if (dropping) {       // x_mid + drop(MLP branch)
-                            if ((c & 1) == 0) dw = drop_words(p.drop, p.site2, (unsigned long long)(row0 + lane) * (kBtC / 8) + ch * 4 + (c >> 1));
-                            const int l0 = (c & 1) * 4;
-                            o.x *= drop_mul(p.drop, dw, l0); o.y *= drop_mul(p.drop, dw, l0 + 1);
-                            o.z *= drop_mul(p.drop, dw, l0 + 2); o.w *= drop_mul(p.drop, dw, l0 + 3);
-                        }
-                        o.x += __uint_as_float(xm[c4 * 4 + 0]); o.y += __uint_as_float(xm[c4 * 4 + 1]);
-                        o.z += __uint_as_float(xm[c4 * 4 + 2]); o.w += __uint_as_float(xm[c4 * 4 + 3]);
-                        *reinterpret_cast<float4*>(ebuf + sw128_off(lane, c)) = o;
-                        r[c * 4 + 0] = __float_as_uint(o.x); r[c * 4 + 1] = __float_as_uint(o.y);
-                        r[c * 4 + 2] = __float_as_uint(o.z); r[c * 4 + 3] = __float_as_uint(o.w);
-                        rsum += (o.x + o.y) + (o.z + o.w);
-                        rsq += fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, o.w * o.w)));
+                for (int c = 0; c < 8; ++c) {
+                    float4 o;
+                    o.x = __uint_as_float(r0[c * 4 + 0]) + bs[c * 4 + 0];
+                    o.y = __uint_as_float(r0[c * 4 + 1]) + bs[c * 4 + 1];
+                    o.z = __uint_as_float(r0[c * 4 + 2]) + bs[c * 4 + 2];
+                    o.w = __uint_as_float(r0[c * 4 + 3]) + bs[c * 4 + 3];
+                    if (dropping) {       // x_mid + drop(MLP branch)
+                        if ((c & 1) == 0) dw = drop_words(p.drop, p.site2, (unsigned long long)(row0 + lane) * (kBtC / 8) + ch * 4 + (c >> 1));
+                        const int l0 = (c & 1) * 4;
+                        o.x *= drop_mul(p.drop, dw, l0); o.y *= drop_mul(p.drop, dw, l0 + 1);
+                        o.z *= drop_mul(p.drop, dw, l0 + 2); o.w *= drop_mul(p.drop, dw, l0 + 3);
                     }
+                    o.x += __uint_as_float(r1[c * 4 + 0]); o.y += __uint_as_float(r1[c * 4 + 1]);
+                    o.z += __uint_as_float(r1[c * 4 + 2]); o.w += __uint_as_float(r1[c * 4 + 3]);
+                    *reinterpret_cast<float4*>(ebuf + sw128_off(lane, c)) = o;
+                    r0[c * 4 + 0] = __float_as_uint(o.x); r0[c * 4 + 1] = __float_as_uint(o.y);
+                    r0[c * 4 + 2] = __float_as_uint(o.z); r0[c * 4 + 3] = __float_as_uint(o.w);
+                    rsum += (o.x + o.y) + (o.z + o.w);
+                    rsq += fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, o.w * o.w)));
                 }
+                if (p.has_ln_out) ptx::tmem_st_32x32(tm_x + (uint32_t)(ch * 32), r0);
                 ptx::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) { ptx::tma_store_2d(&tmXout, ebuf, ch * 32, row0); ptx::bulk_commit(); }
                 st_pending = true;
-            };
-            out_chunk(xa, 2 * cs);
-            out_chunk(xb, 2 * cs + 1);
+            }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc_free);          // the next tile's first GEMM may overwrite the accumulator
@@ -415,11 +409,15 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 float mean, rstd;
                 row_stats(1, rsum, rsq, mean, rstd);
                 ebuf_free();
-                ln_kblock(xa, xb, mean, rstd, gn, ben, ebuf);
+                ln_kblock(tm_x, mean, rstd, gn, ben, ebuf, lane);
                 ptx::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) { ptx::tma_store_2d(&tmLnOut, ebuf, cs * 64, row0); ptx::bulk_commit(); }
                 st_pending = true;
+                // the other warps of the quarter have read this warp's x_out columns out of TMEM: the next tile may overwrite them
+                ptx::tc_fence_before();
+                named_bar_sync(1 + q, 4 * 32);
+                ptx::tc_fence_after();
             }
         }
         if (lane == 0) ptx::bulk_wait_all<0>();

@@ -58,7 +58,9 @@ typedef struct tante_config {
     float frame_interval;
     int32_t precision;      /* TANTE_PREC_*                                         */
     int32_t n_layers[TANTE_MAX_ORDER];                 /* len(segment k) of attn_axes */
-    char axes[TANTE_MAX_ORDER][TANTE_MAX_LAYERS];      /* axis letter per layer: T/H/W */
+    char axes[TANTE_MAX_ORDER][TANTE_MAX_LAYERS];      /* axis letter per layer: T/H/W (L/Y/A: inference) */
+    int32_t enc_dec_fno;    /* 0: enc_dec_type='cnn' (enc_dec_cnn.py), 1: 'fno' (enc_dec_fno.py; inference / rollout) */
+    int32_t modes1, modes2; /* SpectralLayer modes of the fno encoder / decoder (models/tante.py:56-57)            */
 } tante_config_t;
 
 typedef struct tante_handle_s* tante_handle_t;

@@ -32,8 +32,8 @@ def build_ref(ns, cfg: O.OracleConfig, sd):
     m = ns.TANTE(in_T=cfg.in_T, dset_metadata=md, taylor_order=cfg.taylor_order,
                  frame_interval=cfg.frame_interval, output_length=cfg.output_length,
                  attn_axes=cfg.attn_axes, n_head=cfg.n_head, mlp_ratio=1.0, dropout=0.0,
-                 enc_dec_type="cnn", embed_dim=cfg.embed_dim, patch_scale=cfg.patch_scale,
-                 overlap_ratio=0.0, deg=cfg.deg)
+                 enc_dec_type=cfg.enc_dec_type, embed_dim=cfg.embed_dim, modes1=cfg.modes1, modes2=cfg.modes2,
+                 patch_scale=cfg.patch_scale, overlap_ratio=0.0, deg=cfg.deg)
     m.load_state_dict(sd)
     m.t_seq = m.t_seq.cpu()
     return m
@@ -195,6 +195,22 @@ def main_round2(ns):
                  B=2, out_T=6, rt_bias=2.7, stages=True, n_roll=6)
     case_forward(ns, "fwd_deg_k1_w96", C(n_fields=2, H=32, W=384, taylor_order=1, attn_axes="WHT", deg=True,
                                           patch_scale=4), B=2, out_T=1, rt_bias=0.0, n_roll=2)
+    if "--fno" in sys.argv:
+        main_fno(ns)
+
+
+def main_fno(ns):
+    """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_deg_k1_fno_p8", C(n_fields=3, H=64, W=96, taylor_order=1, attn_axes="THW", deg=True,
+                                             enc_dec_type="fno", patch_scale=8, modes1=16, modes2=16),
+                 B=2, out_T=1, rt_bias=0.0, n_roll=3, stride=7, stages=True)
+    case_forward(ns, "fwd_adp_k2_fno_p4", C(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="TH-W", deg=False,
+                                             enc_dec_type="fno", patch_scale=4, modes1=8, modes2=8),
+                 B=2, out_T=6, rt_bias=2.7, n_roll=6, stride=3)
+    case_forward(ns, "fwd_deg_k1_fno_p16", C(n_fields=4, H=64, W=128, taylor_order=1, attn_axes="WT", deg=True,
+                                              enc_dec_type="fno", patch_scale=16, modes1=12, modes2=20),
+                 B=1, out_T=1, rt_bias=0.0, n_roll=2, stride=5)
 
 
 def main():
@@ -203,6 +219,9 @@ def main():
     ns = ref_shim.load_reference()
     if "--round2" in sys.argv:
         main_round2(ns)
+        return
+    if "--fno" in sys.argv:
+        main_fno(ns)
         return
     C = O.OracleConfig
     # 1. fixed-step (what configs/tante.yaml selects), full outputs on a small grid

@@ -30,6 +30,8 @@ import torch
 
 # reference models/enc_dec_cnn.py:39-46
 PATCH_MAP = {64: (4, 4, 4), 32: (4, 4, 2), 16: (4, 2, 2), 8: (2, 2, 2), 4: (2, 2, 1), 2: (2, 1, 1)}
+# reference models/enc_dec_fno.py:39-46 (two patch stages, spectral layers in between)
+PATCH_MAP_FNO = {64: (8, 8), 32: (8, 4), 16: (4, 4), 8: (4, 2), 4: (2, 2), 2: (2, 1)}
 
 
 @dataclass
@@ -47,6 +49,9 @@ class OracleConfig:
     embed_dim: int = 256
     patch_scale: int = 8
     deg: bool = True
+    enc_dec_type: str = "cnn"      # 'cnn' (enc_dec_cnn.py) | 'fno' (enc_dec_fno.py)
+    modes1: int = 32
+    modes2: int = 32
 
     @property
     def Hp(self):
@@ -152,8 +157,50 @@ def _patch_deconv(x, w, b, k: int):
     return y
 
 
+def spectral_layer(sd, p: str, x, modes1: int, modes2: int):
+    """SpectralLayer.forward (enc_dec_fno.py:184-222): rfft2 (ortho) -> the low modes (top and bottom m1 rows, first m2
+    columns) mixed across channels by a complex weight -> irfft2, plus a 1x1 convolution.  x (N, Cin, H, W)."""
+    N, Cin, H, W = x.shape
+    w = sd[p + "weight"]                                            # complex (Cin, Cout, modes1, modes2)
+    x_ft = torch.fft.rfft2(x, dim=(-2, -1), norm="ortho")
+    Wf = x_ft.shape[-1]
+    m1, m2 = min(modes1, H), min(modes2, Wf)
+    out_ft = torch.zeros(N, w.shape[1], H, Wf, dtype=x_ft.dtype)
+    wc = w[:, :, :m1, :m2].to(x_ft.dtype)
+    out_ft[:, :, :m1, :m2] = torch.einsum("bcij,coij->boij", x_ft[:, :, :m1, :m2], wc)
+    out_ft[:, :, -m1:, :m2] = torch.einsum("bcij,coij->boij", x_ft[:, :, -m1:, :m2], wc)
+    y = torch.fft.irfft2(out_ft, s=(H, W), dim=(-2, -1), norm="ortho")
+    s = torch.einsum("bchw,oc->bohw", x, sd[p + "w0.weight"][:, :, 0, 0]) + sd[p + "w0.bias"][None, :, None, None]
+    return s + y
+
+
+def encoder_fno(sd, cfg: OracleConfig, x):
+    """enc_FNO.forward (enc_dec_fno.py:254-271)."""
+    B, T, D, H, W = x.shape
+    ps = PATCH_MAP_FNO[cfg.patch_scale]
+    z = x.reshape(B * T, D, H, W)
+    z = gelu_erf(spectral_layer(sd, "encoder.enc_spectral_1.", z, cfg.modes1, cfg.modes2))
+    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_1.conv.weight"], sd["encoder.enc_conv_1.conv.bias"], ps[0]))
+    z = gelu_erf(spectral_layer(sd, "encoder.enc_spectral_2.", z, cfg.modes1 // ps[0], cfg.modes2 // ps[0]))
+    z = _patch_conv(z, sd["encoder.enc_conv_2.conv.weight"], sd["encoder.enc_conv_2.conv.bias"], ps[1])
+    return z.reshape(B, T, z.shape[1], z.shape[2], z.shape[3]).permute(0, 1, 3, 4, 2).contiguous()
+
+
+def decoder_fno(sd, cfg: OracleConfig, k: int, d):
+    """dec_FNO.forward (enc_dec_fno.py:303-323) on the last-frame latent: (B,Hp,Wp,C) -> (B,D,H,W)."""
+    ps = PATCH_MAP_FNO[cfg.patch_scale]
+    p = f"decoders.{k}."
+    z = d.permute(0, 3, 1, 2)
+    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_1.deconv.weight"], sd[p + "dec_conv_1.deconv.bias"], ps[1]))
+    z = gelu_erf(spectral_layer(sd, p + "dec_spectral_1.", z, cfg.modes1 // ps[0], cfg.modes2 // ps[0]))
+    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_2.deconv.weight"], sd[p + "dec_conv_2.deconv.bias"], ps[0]))
+    return spectral_layer(sd, p + "dec_spectral_2.", z, cfg.modes1, cfg.modes2)
+
+
 def encoder(sd, cfg: OracleConfig, x):
     """enc_CNN.forward (enc_dec_cnn.py:217-229): (B,T,D,H,W) -> (B,T,Hp,Wp,C)."""
+    if cfg.enc_dec_type == "fno":
+        return encoder_fno(sd, cfg, x)
     B, T, D, H, W = x.shape
     ks = PATCH_MAP[cfg.patch_scale]
     z = x.reshape(B * T, D, H, W)
@@ -165,6 +212,8 @@ def encoder(sd, cfg: OracleConfig, x):
 
 def decoder(sd, cfg: OracleConfig, k: int, d):
     """dec_CNN.forward (enc_dec_cnn.py:263-277) on the last-frame latent: (B,Hp,Wp,C) -> (B,D,H,W)."""
+    if cfg.enc_dec_type == "fno":
+        return decoder_fno(sd, cfg, k, d)
     ks = PATCH_MAP[cfg.patch_scale]
     p = f"decoders.{k}."
     z = d.permute(0, 3, 1, 2)
@@ -468,16 +517,37 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     sh: Dict[str, Tuple[int, ...]] = {}
     sh["t_emb"] = (1, T, C)
     sh["s_emb"] = (1, Hp, Wp, C)
-    chans = [D, C // 4, C // 2, C]
-    for i in range(3):
-        sh[f"encoder.enc_conv_{i+1}.conv.weight"] = (chans[i + 1], chans[i], ks[i], ks[i])
-        sh[f"encoder.enc_conv_{i+1}.conv.bias"] = (chans[i + 1],)
-    for k, axes in enumerate(cfg.segments):
-        dch = [C, C // 2, C // 4, D]
+    fno = cfg.enc_dec_type == "fno"
+    if fno:
+        ps = PATCH_MAP_FNO[cfg.patch_scale]
+        m1, m2 = cfg.modes1, cfg.modes2
+
+        def spectral(pfx, ci, co, a, b):
+            sh[pfx + "weight"] = ("complex", ci, co, a, b)
+            sh[pfx + "w0.weight"] = (co, ci, 1, 1)
+            sh[pfx + "w0.bias"] = (co,)
+        spectral("encoder.enc_spectral_1.", D, C // 8, m1, m2)
+        sh["encoder.enc_conv_1.conv.weight"] = (C // 4, C // 8, ps[0], ps[0]); sh["encoder.enc_conv_1.conv.bias"] = (C // 4,)
+        spectral("encoder.enc_spectral_2.", C // 4, C // 2, m1 // ps[0], m2 // ps[0])
+        sh["encoder.enc_conv_2.conv.weight"] = (C, C // 2, ps[1], ps[1]); sh["encoder.enc_conv_2.conv.bias"] = (C,)
+    else:
+        chans = [D, C // 4, C // 2, C]
         for i in range(3):
-            kk = ks[2 - i]
-            sh[f"decoders.{k}.dec_conv_{i+1}.deconv.weight"] = (dch[i], dch[i + 1], kk, kk)
-            sh[f"decoders.{k}.dec_conv_{i+1}.deconv.bias"] = (dch[i + 1],)
+            sh[f"encoder.enc_conv_{i+1}.conv.weight"] = (chans[i + 1], chans[i], ks[i], ks[i])
+            sh[f"encoder.enc_conv_{i+1}.conv.bias"] = (chans[i + 1],)
+    for k, axes in enumerate(cfg.segments):
+        if fno:
+            p = f"decoders.{k}."
+            sh[p + "dec_conv_1.deconv.weight"] = (C, C // 2, ps[1], ps[1]); sh[p + "dec_conv_1.deconv.bias"] = (C // 2,)
+            spectral(p + "dec_spectral_1.", C // 2, C // 4, m1 // ps[0], m2 // ps[0])
+            sh[p + "dec_conv_2.deconv.weight"] = (C // 4, C // 8, ps[0], ps[0]); sh[p + "dec_conv_2.deconv.bias"] = (C // 8,)
+            spectral(p + "dec_spectral_2.", C // 8, D, m1, m2)
+        else:
+            dch = [C, C // 2, C // 4, D]
+            for i in range(3):
+                kk = ks[2 - i]
+                sh[f"decoders.{k}.dec_conv_{i+1}.deconv.weight"] = (dch[i], dch[i + 1], kk, kk)
+                sh[f"decoders.{k}.dec_conv_{i+1}.deconv.bias"] = (dch[i + 1],)
         for i, _ in enumerate(axes):
             p = f"blocks.{k}.blocks.{i}."
             sh[p + "ln1.weight"] = (C,); sh[p + "ln1.bias"] = (C,)
@@ -522,6 +592,11 @@ def make_state_dict(cfg: OracleConfig, seed: int = 211, rt_bias: float = 0.0,
     shapes = param_shapes(cfg)
     for name, shape in shapes.items():
         g = torch.Generator().manual_seed(_name_seed(name, seed))
+        if shape and shape[0] == "complex":       # SpectralLayer.weight (enc_dec_fno.py:190-193): cfloat, scale 1/sqrt(Cin*Cout)
+            cs = shape[1:]
+            v = torch.complex(torch.randn(cs, generator=g), torch.randn(cs, generator=g)) * (1.0 / math.sqrt(cs[0] * cs[1]))
+            sd[name] = v.to(torch.complex128 if dtype == torch.float64 else torch.complex64)
+            continue
         if name == "t_emb":
             v = t_emb_init(cfg.embed_dim, cfg.in_T) + 0.02 * torch.randn(shape, generator=g)
         elif name == "s_emb":

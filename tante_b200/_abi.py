@@ -26,6 +26,7 @@ class TanteConfig(C.Structure):
         ("frame_interval", C.c_float), ("precision", C.c_int32),
         ("n_layers", C.c_int32 * TANTE_MAX_ORDER),
         ("axes", (C.c_char * TANTE_MAX_LAYERS) * TANTE_MAX_ORDER),
+        ("enc_dec_fno", C.c_int32), ("modes1", C.c_int32), ("modes2", C.c_int32),
     ]
 
 

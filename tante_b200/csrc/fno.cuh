@@ -1,0 +1,151 @@
+// enc_dec_type = 'fno' (reference models/enc_dec_fno.py:184-323): SpectralLayer = rfft2 (ortho) -> the low modes (the first and
+// last m1 rows, the first m2 columns of the half spectrum) mixed across channels by a complex weight -> irfft2 (ortho), plus a
+// 1x1 convolution.  Only 2 m1 x m2 modes survive, so both transforms are TRUNCATED DFTs -- five small passes, no FFT:
+//     A[n,c,h,k2]  = sum_w x[n,c,h,w] e^{-2 pi i k2 w / W}                         (dft_w)
+//     X[n,c,j,k2]  = sum_h A[n,c,h,k2] e^{-2 pi i k1(j) h / H}                     (dft_h; k1(j) = j or H - 2 m1 + j)
+//     Y[n,o,j,k2]  = sum_c X[n,c,j,k2] Wt[c,o,j mod m1,k2]                         (mix)
+//     B[n,o,h,k2]  = sum_j Y[n,o,j,k2] e^{+2 pi i k1(j) h / H}                     (idft_h)
+//     y[n,o,h,w]   = (1 / HW) (Re B[..,0] + 2 sum_{k2>=1} Re(B[..,k2] e^{+2 pi i k2 w / W})) + sum_c w0[o,c] x[n,c,h,w] + b[o]
+// (the C2R half of irfft2 ignores the imaginary part of the k2 = 0 column).  All five in fp32 in both precision modes; the
+// patch convolutions between the spectral layers are the gather + GEMM stages of wide_patch.cuh.  Inference / rollout only.
+#pragma once
+#include "common.cuh"
+
+namespace tante {
+
+// where a spectral layer reads x[n, c, h, w] from / writes y[n, o, h, w] to
+struct SpecView {
+    const void* p;          // fp32 channels-first frames (mode 0) or TA channels-last grid [n][h][w][c] (mode 1)
+    int mode;
+    const int* fcount;      // mode 0: ring position per sample (nullable); frame t of sample b sits in slot (fcount[b] + t) % T
+    int T;
+};
+
+template <typename TA>
+__device__ __forceinline__ float spec_read(const SpecView& v, long long n, int c, int h, int w, int C, int H, int W) {
+    if (v.mode == 0) {
+        long long img = n;
+        if (v.fcount) { const long long b = n / v.T; const int t = (int)(n % v.T); img = b * v.T + (v.fcount[b] + t) % v.T; }
+        return reinterpret_cast<const float*>(v.p)[((size_t)img * C + c) * H * W + (size_t)h * W + w];
+    }
+    return to_f32(reinterpret_cast<const TA*>(v.p)[(((size_t)n * H + h) * W + w) * C + c]);
+}
+
+// twiddle table tw[j] = (cos, sin)(2 pi j / N), j < N (written once per axis length in double precision on the host)
+template <typename TA>
+__global__ void __launch_bounds__(128) spec_dft_w_kernel(SpecView in, int C, int H, int W, int m2, const float2* __restrict__ twW,
+                                                         float2* __restrict__ A, long long rows) {
+    // one warp per (n, c, h) row; lane = k2 (m2 <= 32 per pass, looped otherwise)
+    const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int h = (int)(row % H);
+    const int c = (int)((row / H) % C);
+    const long long n = row / ((long long)H * C);
+    for (int k2 = lane; k2 < m2; k2 += 32) {
+        float re = 0.f, im = 0.f;
+        int idx = 0;                                   // (k2 * w) mod W
+        for (int w = 0; w < W; ++w) {
+            const float v = spec_read<TA>(in, n, c, h, w, C, H, W);
+            const float2 t = twW[idx];
+            re = fmaf(v, t.x, re);
+            im = fmaf(-v, t.y, im);
+            idx += k2; if (idx >= W) idx -= W;
+        }
+        A[(size_t)row * m2 + k2] = make_float2(re, im);
+    }
+}
+
+__device__ __forceinline__ int spec_k1(int j, int m1, int H) { return j < m1 ? j : H - 2 * m1 + j; }
+
+__global__ void __launch_bounds__(256) spec_dft_h_kernel(const float2* __restrict__ A, int H, int m1, int m2,
+                                                         const float2* __restrict__ twH, float2* __restrict__ X, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((nc * 2 m1 + j) * m2 + k2)
+    if (idx >= total) return;
+    const int k2 = (int)(idx % m2);
+    const int j = (int)((idx / m2) % (2 * m1));
+    const long long nc = idx / ((long long)m2 * 2 * m1);
+    const int k1 = spec_k1(j, m1, H);
+    const float2* a = A + (size_t)nc * H * m2 + k2;
+    float re = 0.f, im = 0.f;
+    int t = 0;                                          // (k1 * h) mod H
+    for (int h = 0; h < H; ++h) {
+        const float2 v = a[(size_t)h * m2];
+        const float2 w = twH[t];                        // e^{-i theta} = (cos, -sin)
+        re = fmaf(v.x, w.x, fmaf(v.y, w.y, re));
+        im = fmaf(v.y, w.x, fmaf(-v.x, w.y, im));
+        t += k1; if (t >= H) t -= H;
+    }
+    X[idx] = make_float2(re, im);
+}
+
+__global__ void __launch_bounds__(256) spec_mix_kernel(const float2* __restrict__ X, const float2* __restrict__ Wt, int Cin, int Cout,
+                                                       int m1, int m2, int wm2 /* stored modes2 of the weight */, int wm1,
+                                                       float2* __restrict__ Y, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((n * Cout + o) * 2 m1 + j) * m2 + k2
+    if (idx >= total) return;
+    const int k2 = (int)(idx % m2);
+    const int j = (int)((idx / m2) % (2 * m1));
+    const int o = (int)((idx / ((long long)m2 * 2 * m1)) % Cout);
+    const long long n = idx / ((long long)m2 * 2 * m1 * Cout);
+    const int jw = j < m1 ? j : j - m1;
+    float re = 0.f, im = 0.f;
+    for (int c = 0; c < Cin; ++c) {
+        const float2 x = X[(((size_t)n * Cin + c) * 2 * m1 + j) * m2 + k2];
+        const float2 w = Wt[(((size_t)c * Cout + o) * wm1 + jw) * wm2 + k2];
+        re = fmaf(x.x, w.x, fmaf(-x.y, w.y, re));
+        im = fmaf(x.x, w.y, fmaf(x.y, w.x, im));
+    }
+    Y[idx] = make_float2(re, im);
+}
+
+__global__ void __launch_bounds__(256) spec_idft_h_kernel(const float2* __restrict__ Y, int H, int m1, int m2,
+                                                          const float2* __restrict__ twH, float2* __restrict__ Bh, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((no * H + h) * m2 + k2)
+    if (idx >= total) return;
+    const int k2 = (int)(idx % m2);
+    const int h = (int)((idx / m2) % H);
+    const long long no = idx / ((long long)m2 * H);
+    const float2* y = Y + (size_t)no * 2 * m1 * m2 + k2;
+    float re = 0.f, im = 0.f;
+    for (int j = 0; j < 2 * m1; ++j) {
+        const int k1 = spec_k1(j, m1, H);
+        const float2 w = twH[(int)(((long long)k1 * h) % H)];      // e^{+i theta}
+        const float2 v = y[(size_t)j * m2];
+        re = fmaf(v.x, w.x, fmaf(-v.y, w.y, re));
+        im = fmaf(v.x, w.y, fmaf(v.y, w.x, im));
+    }
+    Bh[idx] = make_float2(re, im);
+}
+
+// y = irfft-along-W of Bh (scaled 1 / HW) + w0 x + b, optional GELU; out: TA channels-last grid (o fastest) or fp32 channels-first
+template <typename TA, bool ACT, bool FIELD>
+__global__ void __launch_bounds__(256) spec_out_kernel(const float2* __restrict__ Bh, SpecView in, const float* __restrict__ w0,
+                                                       const float* __restrict__ b0, int Cin, int Cout, int H, int W, int m2,
+                                                       const float2* __restrict__ twW, TA* __restrict__ out, float* __restrict__ field,
+                                                       long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int o, w, h;
+    long long n;
+    if (FIELD) { long long r = idx; w = (int)(r % W); r /= W; h = (int)(r % H); r /= H; o = (int)(r % Cout); n = r / Cout; }
+    else { long long r = idx; o = (int)(r % Cout); r /= Cout; w = (int)(r % W); r /= W; h = (int)(r % H); n = r / H; }
+    const float2* bh = Bh + (((size_t)n * Cout + o) * H + h) * m2;
+    float acc = bh[0].x;
+    int t = 0;
+    for (int k2 = 1; k2 < m2; ++k2) {
+        t += w; if (t >= W) t -= W;                     // (k2 * w) mod W
+        const float2 tw = twW[t];
+        const float2 v = bh[k2];
+        acc = fmaf(2.f, fmaf(v.x, tw.x, -v.y * tw.y), acc);
+    }
+    float v = acc / ((float)H * (float)W);
+    float s = b0[o];
+    for (int c = 0; c < Cin; ++c) s = fmaf(w0[(size_t)o * Cin + c], spec_read<TA>(in, n, c, h, w, Cin, H, W), s);
+    v += s;
+    if (ACT) v = ActMath<TA>::gelu_erf_f(v);
+    if (FIELD) field[idx] = v;
+    else out[idx] = from_f32<TA>(v);
+}
+
+}  // namespace tante

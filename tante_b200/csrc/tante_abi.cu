@@ -30,6 +30,7 @@
 #include "metrics.cuh"
 #include "block_tail_tc.cuh"
 #include "wide_patch.cuh"
+#include "fno.cuh"
 
 using namespace tante;
 
@@ -85,8 +86,13 @@ struct LayerPlan {
     int64_t ln1w, ln1b, inw, inb, outw, outb, ln2w, ln2b, m0w, m0b, m2w, m2b;
     int64_t inwT, outwT, m0wT, m2wT;      // [K][N] copies for the input-gradient GEMMs
 };
+struct SpecPlan {            // one SpectralLayer (enc_dec_fno.py:184-222)
+    int64_t w = 0, w0 = 0, b0 = 0;      // complex weight [Cin][Cout][wm1][wm2] (as float pairs), 1x1 conv [Cout][Cin], bias [Cout]
+    int Cin = 0, Cout = 0, wm1 = 0, wm2 = 0;
+};
 struct OrderPlan {
     std::vector<LayerPlan> layers;
+    SpecPlan fs1, fs2;                  // fno decoder: dec_spectral_1 / dec_spectral_2
     int64_t prop[3][4];   // [H,W,T][w0,b0,w2,b2]
     int64_t decw[3], decb[3];   // packed deconv 1,2 (GEMM NK + replicated bias), deconv 3 (KN + raw bias)
     int64_t intw[3], intb[3];
@@ -137,6 +143,10 @@ struct tante_handle_s {
     bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
     bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
     bool long_axes = false;             // an L / Y / A layer or an axis longer than 64 tokens: inference / rollout only
+    bool fno = false;                   // enc_dec_type = 'fno' (fno.cuh): spectral layers between two patch stages; inference / rollout
+    int fp0 = 0, fp1 = 0;               // fno patch kernels (enc_dec_fno.py:39-46)
+    SpecPlan fes1, fes2;                // fno encoder: enc_spectral_1 / enc_spectral_2
+    DevBuf ftw, fA, fB, fg0, fg1, fg2;  // fno: twiddle tables, complex scratch x2, channels-last stage grids
     bool wide = false;                  // patch_scale >= 16: natural-order stages with shifted 4x4 windows (wide_patch.cuh)
     int K1pad = 0, NOpad = 0;           // wide: first-conv reduction / last-deconv output width rounded up to 64
     int64_t enc_w1wide = 0;             // wide: first conv weight [C1][K1pad]
@@ -246,9 +256,27 @@ void build_plan(tante_handle_s* h) {
     REQUIRE(c.n_fields >= 1 && c.n_fields <= 16, "n_fields must be in 1..16");
     REQUIRE(c.precision == TANTE_PREC_FP32 || c.precision == TANTE_PREC_BF16, "unknown precision");
     int k[3];
-    patch_kernels(c.patch_scale, k);
+    h->fno = c.enc_dec_fno != 0;
+    if (h->fno) {
+        // enc_dec_fno.py:39-46: two patch stages (p0 at full resolution, p1 after the second spectral layer)
+        switch (c.patch_scale) {
+            case 2: h->fp0 = 2; h->fp1 = 1; break;
+            case 4: h->fp0 = 2; h->fp1 = 2; break;
+            case 8: h->fp0 = 4; h->fp1 = 2; break;
+            case 16: h->fp0 = 4; h->fp1 = 4; break;
+            case 32: case 64: throw Error(TANTE_ERR_INVALID, "enc_dec_type='fno' at patch_scale 32 / 64 (8x8 stages) is not implemented");
+            default: throw Error(TANTE_ERR_INVALID, "KeyError: patch_scale not in Patch_map");
+        }
+        k[0] = h->fp0; k[1] = h->fp1; k[2] = 1;      // geometry bookkeeping only (rows per token of the two stage grids)
+        const int H1 = c.H / h->fp0, W1 = c.W / h->fp0;
+        REQUIRE(c.modes1 >= h->fp0 && c.modes2 >= h->fp0, "fno: modes1 / modes2 must be >= the first patch kernel");
+        REQUIRE(2 * c.modes1 <= c.H && c.modes2 <= c.W / 2 && 2 * (c.modes1 / h->fp0) <= H1 && (c.modes2 / h->fp0) <= W1 / 2,
+                "fno: the kept modes must fit the grid (2 * modes1 <= H, modes2 <= W / 2 at both resolutions)");
+    } else {
+        patch_kernels(c.patch_scale, k);
+    }
     REQUIRE(c.H % c.patch_scale == 0 && c.W % c.patch_scale == 0, "H and W must be divisible by patch_scale");
-    h->wide = c.patch_scale >= 16;
+    h->wide = c.patch_scale >= 16 || h->fno;
     h->K1pad = (k[0] * k[0] * c.n_fields + 63) / 64 * 64;
     h->NOpad = h->K1pad;
     if (h->wide) h->use_enc_cache = false;
@@ -267,8 +295,25 @@ void build_plan(tante_handle_s* h) {
 
     h->t_emb = add_param(h, "t_emb", {1, T, C});
     h->s_emb = add_param(h, "s_emb", {1, h->Hp, h->Wp, C});
+    auto add_spec = [&](const std::string& pre, int Cin, int Cout, int wm1, int wm2) {
+        SpecPlan sp;
+        sp.Cin = Cin; sp.Cout = Cout; sp.wm1 = wm1; sp.wm2 = wm2;
+        sp.w = add_param(h, pre + "weight", {Cin, Cout, wm1, wm2, 2});        // cfloat viewed as (..., 2) floats
+        sp.w0 = add_param(h, pre + "w0.weight", {Cout, Cin, 1, 1});
+        sp.b0 = add_param(h, pre + "w0.bias", {Cout});
+        return sp;
+    };
     const int ech[4] = {D, C1, C2, C};
-    for (int i = 0; i < 3; ++i) {
+    if (h->fno) {
+        const int p0 = h->fp0, p1 = h->fp1, C8 = C / 8;
+        h->fes1 = add_spec("encoder.enc_spectral_1.", D, C8, c.modes1, c.modes2);
+        h->enc_w[0] = add_param(h, "encoder.enc_conv_1.conv.weight", {C1, C8, p0, p0}, PACK_CONV, C1, C8, p0);
+        h->enc_b[0] = add_param(h, "encoder.enc_conv_1.conv.bias", {C1});
+        h->fes2 = add_spec("encoder.enc_spectral_2.", C1, C2, c.modes1 / p0, c.modes2 / p0);
+        h->enc_w[1] = add_param(h, "encoder.enc_conv_2.conv.weight", {C, C2, p1, p1}, PACK_CONV, C, C2, p1);
+        h->enc_b[1] = add_param(h, "encoder.enc_conv_2.conv.bias", {C});
+    }
+    for (int i = 0; i < 3 && !h->fno; ++i) {
         const std::string p = "encoder.enc_conv_" + std::to_string(i + 1) + ".conv.";
         h->enc_w[i] = add_param(h, p + "weight", {ech[i + 1], ech[i], k[i], k[i]}, PACK_CONV, ech[i + 1], ech[i], k[i]);
         h->enc_b[i] = add_param(h, p + "bias", {ech[i + 1]});
@@ -336,7 +381,17 @@ void build_plan(tante_handle_s* h) {
             op.prop[a][3] = add_param(h, p + "2.bias", {plen[a]});
         }
         const int dch[4] = {C, C2, C1, D};
-        for (int i = 0; i < 3; ++i) {
+        if (h->fno) {
+            const int p0 = h->fp0, p1 = h->fp1, C8 = C / 8;
+            const std::string p = "decoders." + std::to_string(o) + ".";
+            op.decw[0] = add_param(h, p + "dec_conv_1.deconv.weight", {C, C2, p1, p1}, PACK_DECONV_NK, C, C2, p1);
+            op.decb[0] = add_param(h, p + "dec_conv_1.deconv.bias", {C2}, PACK_BIAS_REP, C2, 0, p1);
+            op.fs1 = add_spec(p + "dec_spectral_1.", C2, C1, c.modes1 / p0, c.modes2 / p0);
+            op.decw[1] = add_param(h, p + "dec_conv_2.deconv.weight", {C1, C8, p0, p0}, PACK_DECONV_NK, C1, C8, p0);
+            op.decb[1] = add_param(h, p + "dec_conv_2.deconv.bias", {C8}, PACK_BIAS_REP, C8, 0, p0);
+            op.fs2 = add_spec(p + "dec_spectral_2.", C8, D, c.modes1, c.modes2);
+        }
+        for (int i = 0; i < 3 && !h->fno; ++i) {
             const int kk = k[2 - i];
             const std::string p = "decoders." + std::to_string(o) + ".dec_conv_" + std::to_string(i + 1) + ".deconv.";
             op.decw[i] = add_param(h, p + "weight", {dch[i], dch[i + 1], kk, kk},
@@ -715,6 +770,147 @@ void run_decoder_wide(tante_handle_s* h, int o, const TA* dmod, int B, cudaStrea
     post(wb, h->NOpad, H1, W1, D, g.k0, AF(h, op.decb[2]), nullptr, field, false);
 }
 
+// ---- enc_dec_type = 'fno' (fno.cuh) ----
+// twiddle tables of the four axis lengths, (cos, sin)(2 pi j / N) in double precision: [W | H | W1 | H1]
+void fno_twiddles(tante_handle_s* h) {
+    if (h->ftw.p) return;
+    const int W = h->cfg.W, H = h->cfg.H, W1 = W / h->fp0, H1 = H / h->fp0;
+    std::vector<float> tw((size_t)2 * (W + H + W1 + H1));
+    size_t o = 0;
+    for (int N : {W, H, W1, H1})
+        for (int j = 0; j < N; ++j) {
+            const double a = 2.0 * 3.14159265358979323846 * (double)j / (double)N;
+            tw[o++] = (float)cos(a); tw[o++] = (float)sin(a);
+        }
+    dev_alloc(h, h->ftw, tw.size() * sizeof(float));
+    CK(cudaMemcpy(h->ftw.p, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// one SpectralLayer: in (view) -> TA channels-last grid `out` (+ GELU) or the fp32 channels-first `field`
+template <typename TA>
+void run_spectral(tante_handle_s* h, const SpecPlan& sp, const SpecView& in, long long N, int H, int W, int level, bool act,
+                  TA* out, float* field, cudaStream_t st) {
+    const int W0 = h->cfg.W, H0 = h->cfg.H, W1 = W0 / h->fp0;
+    const float2* tw = reinterpret_cast<const float2*>(h->ftw.p);
+    const float2* twW = level == 0 ? tw : tw + W0 + H0;
+    const float2* twH = level == 0 ? tw + W0 : tw + W0 + H0 + W1;
+    const int m1 = sp.wm1, m2 = sp.wm2;
+    float2* A = reinterpret_cast<float2*>(h->fA.p);
+    float2* Bc = reinterpret_cast<float2*>(h->fB.p);
+    const long long rows = N * sp.Cin * H;
+    spec_dft_w_kernel<TA><<<blocks_for(rows, 4), 128, 0, st>>>(in, sp.Cin, H, W, m2, twW, A, rows);
+    CK(cudaGetLastError());
+    const long long tx = N * sp.Cin * 2 * m1 * m2;
+    spec_dft_h_kernel<<<blocks_for(tx, 256), 256, 0, st>>>(A, H, m1, m2, twH, Bc, tx);                 // X -> Bc
+    CK(cudaGetLastError());
+    const long long ty = N * sp.Cout * 2 * m1 * m2;
+    spec_mix_kernel<<<blocks_for(ty, 256), 256, 0, st>>>(Bc, reinterpret_cast<const float2*>(AF(h, sp.w)), sp.Cin, sp.Cout, m1, m2,
+                                                         sp.wm2, sp.wm1, A, ty);                        // Y -> A
+    CK(cudaGetLastError());
+    const long long tb = N * sp.Cout * H * m2;
+    spec_idft_h_kernel<<<blocks_for(tb, 256), 256, 0, st>>>(A, H, m1, m2, twH, Bc, tb);                // Bh -> Bc
+    CK(cudaGetLastError());
+    const long long to = N * sp.Cout * H * W;
+    const unsigned nb = blocks_for(to, 256);
+    if (field) spec_out_kernel<TA, false, true><<<nb, 256, 0, st>>>(Bc, in, AF(h, sp.w0), AF(h, sp.b0), sp.Cin, sp.Cout, H, W, m2, twW, nullptr, field, to);
+    else if (act) spec_out_kernel<TA, true, false><<<nb, 256, 0, st>>>(Bc, in, AF(h, sp.w0), AF(h, sp.b0), sp.Cin, sp.Cout, H, W, m2, twW, out, nullptr, to);
+    else spec_out_kernel<TA, false, false><<<nb, 256, 0, st>>>(Bc, in, AF(h, sp.w0), AF(h, sp.b0), sp.Cin, sp.Cout, H, W, m2, twW, out, nullptr, to);
+    CK(cudaGetLastError());
+    h->launches += 5;
+}
+
+// conv over a channels-last grid as gather + GEMM; K beyond the tcgen05 GEMM's resident slice (1024) runs as two K halves
+template <typename TA>
+void conv_cl_gemm(tante_handle_s* h, int epi, const TA* grid, int Hs, int Ws, int Cin, int k, int64_t w_off, void* out, int Cout,
+                  bool out_f32, long long n_img, EpiParams ep, cudaStream_t st) {
+    TA* wb = reinterpret_cast<TA*>(h->wbuf.p);
+    const int K = k * k * Cin;
+    const long long rows = n_img * (Hs / k) * (Ws / k);
+    REQUIRE(rows < (1LL << 31), "input too large for the gather GEMM");
+    const long long total4 = rows * K / 4;
+    wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(grid, Hs, Ws, Cin, k, (k - 1) / 2, wb, total4);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (sizeof(TA) == 2 && K > 1024) {
+        REQUIRE(epi == EPI_BIAS && out_f32, "the split-K path produces the fp32 pre-embedding only");
+        gemm<TA>(h, EPI_BIAS, wb, K, w_off, out, Cout, true, (int)rows, Cout, K / 2, ep, st, K);
+        EpiParams e2; e2.bias = AF(h, h->zero_off); e2.resid = reinterpret_cast<const float*>(out); e2.ldr = Cout;
+        gemm<TA>(h, EPI_BIAS_RESID, wb + K / 2, K, w_off + K / 2, out, Cout, true, (int)rows, Cout, K / 2, e2, st, K);
+    } else {
+        gemm<TA>(h, epi, wb, K, w_off, out, Cout, out_f32, (int)rows, Cout, K, ep, st);
+    }
+}
+
+template <typename TA>
+void run_encoder_fno(tante_handle_s* h, const StepIO& io, int B, cudaStream_t st) {
+    const int C = h->C, C1 = h->C1, C2 = h->C2, C8 = h->C / 8, T = h->T, L = h->L, D = h->D;
+    const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0;
+    const int tokens = B * T * L;
+    const long long NI = (long long)B * T;
+    float* x = reinterpret_cast<float*>(h->x.p);
+    TA* g0 = reinterpret_cast<TA*>(h->fg0.p);      // [NI][H][W][C8]
+    TA* g1 = reinterpret_cast<TA*>(h->fg1.p);      // [NI][H1][W1][C1]
+    TA* g2 = reinterpret_cast<TA*>(h->fg2.p);      // [NI][H1][W1][C2]
+    fno_twiddles(h);
+    // enc_spectral_1 + GELU on the (ring) frames  (enc_dec_fno.py:258-259)
+    SpecView v0{io.input, 0, io.fcount, T};
+    run_spectral<TA>(h, h->fes1, v0, NI, H, W, 0, true, g0, nullptr, st);
+    // enc_conv_1 + GELU (:260-261)
+    EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
+    conv_cl_gemm<TA>(h, EPI_BIAS_GELU_ERF, g0, H, W, C8, p0, h->enc_w[0], g1, C1, false, NI, e1, st);
+    // enc_spectral_2 + GELU (:263-264)
+    SpecView v1{g1, 1, nullptr, 1};
+    run_spectral<TA>(h, h->fes2, v1, NI, H1, W1, 1, true, g2, nullptr, st);
+    // enc_conv_2 (:265) + t_encode FiLM + embeddings -> residual stream
+    EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
+    if (sizeof(TA) == 2 && p1 * p1 * C2 > 1024) {
+        float* v = reinterpret_cast<float*>(h->qkv.p);
+        conv_cl_gemm<TA>(h, EPI_BIAS, g2, H1, W1, C2, p1, h->enc_w[1], v, C, true, NI, e2, st);
+        embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(v, AF(h, h->film_t_off), AF(h, h->s_emb),
+                                                                                  AF(h, h->t_emb), x, tokens, T, L, C);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
+        e2.film = AF(h, h->film_t_off); e2.s_emb = AF(h, h->s_emb); e2.t_emb = AF(h, h->t_emb);
+        e2.T = T; e2.L = L; e2.ldr = C;
+        conv_cl_gemm<TA>(h, EPI_EMBED, g2, H1, W1, C2, p1, h->enc_w[1], x, C, true, NI, e2, st);
+    }
+}
+
+// dec_FNO.forward (enc_dec_fno.py:303-323) of order o on the last-frame latent dmod [B*L][C] -> dfield[o] (B, D, H, W)
+template <typename TA>
+void run_decoder_fno(tante_handle_s* h, int o, const TA* dmod, int B, cudaStream_t st) {
+    const OrderPlan& op = h->orders[o];
+    const int C = h->C, C1 = h->C1, C2 = h->C2, C8 = h->C / 8, L = h->L, D = h->D, Hp = h->Hp, Wp = h->Wp;
+    const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0;
+    TA* wb = reinterpret_cast<TA*>(h->wbuf.p);
+    TA* g0 = reinterpret_cast<TA*>(h->fg0.p);      // [B][H][W][C8]
+    TA* g1 = reinterpret_cast<TA*>(h->fg1.p);      // [B][H1][W1][C1]
+    TA* g2 = reinterpret_cast<TA*>(h->fg2.p);      // [B][H1][W1][C2]
+    float* field = reinterpret_cast<float*>(h->dfield.p) + (size_t)o * B * D * H * W;
+    auto post = [&](const TA* S, int ldS, int hi, int wi, int Cout, int k, TA* out) {
+        const long long total = (long long)B * (hi * k) * (wi * k) * Cout;
+        wide_deconv_post_kernel<TA, true, false><<<blocks_for(total, 256), 256, 0, st>>>(S, ldS, hi, wi, Cout, k, nullptr, out, nullptr, total);
+        CK(cudaGetLastError());
+        h->launches++;
+    };
+    // dec_conv_1 (p1) + GELU
+    const int N1 = p1 * p1 * C2, N2 = p0 * p0 * C8;
+    EpiParams ed; ed.bias = AF(h, op.decb[0]);
+    gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ed, st);
+    post(wb, N1, Hp, Wp, C2, p1, g2);
+    // dec_spectral_1 + GELU
+    SpecView v2{g2, 1, nullptr, 1};
+    run_spectral<TA>(h, op.fs1, v2, B, H1, W1, 1, true, g1, nullptr, st);
+    // dec_conv_2 (p0) + GELU
+    ed.bias = AF(h, op.decb[1]);
+    gemm<TA>(h, EPI_BIAS, g1, C1, op.decw[1], wb, N2, false, B * H1 * W1, N2, C1, ed, st);
+    post(wb, N2, H1, W1, C8, p0, g0);
+    // dec_spectral_2 -> derivative field
+    SpecView v0{g0, 1, nullptr, 1};
+    run_spectral<TA>(h, op.fs2, v0, B, H, W, 0, false, nullptr, field, st);
+}
+
 void launch_emit_wide(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, cudaStream_t st) {
     EmitParams ep{};
     ep.dfield = reinterpret_cast<const float*>(h->dfield.p);
@@ -745,7 +941,9 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
     TA* a2 = reinterpret_cast<TA*>(h->a2.p);
 
     // --- encoder (enc_dec_cnn.py:217-229) + t_encode FiLM + s_emb + t_emb (tante.py:132-141) ---
-    if (h->wide) {
+    if (h->fno) {
+        run_encoder_fno<TA>(h, io, B, st);
+    } else if (h->wide) {
         run_encoder_wide<TA>(h, io, B, st);
     } else {
         const int P = g.k0 * g.k1 * g.k2;
@@ -889,6 +1087,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             CK(cudaGetLastError());
             h->launches++;
         }
+        if (h->fno) { run_decoder_fno<TA>(h, o, dmod, B, st); continue; }
         if (h->wide) { run_decoder_wide<TA>(h, o, dmod, B, st); continue; }
         TA* z1 = reinterpret_cast<TA*>(h->z1.p);
         TA* z2 = reinterpret_cast<TA*>(h->z2[o].p);
@@ -1671,7 +1870,8 @@ int tante_destroy(tante_handle_t h) {
         cudaSetDevice(h->device);
         DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
                           &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
-                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols, &h->wbuf, &h->dfield};
+                          &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols, &h->wbuf, &h->dfield, &h->ftw,
+                          &h->fA, &h->fB, &h->fg0, &h->fg1, &h->fg2};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
@@ -1824,7 +2024,26 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             dev_alloc(h, h->enc_state, ((size_t)2 * max_batch * h->T + 8) * 4);
         }
         if (h->debug) dev_alloc(h, h->dbg_in, tokens * C * 4);
-        if (h->wide) {
+        if (h->fno) {
+            const size_t NI = (size_t)max_batch * h->T, HW = (size_t)h->cfg.H * h->cfg.W, HW1 = HW / (h->fp0 * h->fp0);
+            const int C8 = C / 8;
+            dev_alloc(h, h->fg0, NI * HW * C8 * es);
+            dev_alloc(h, h->fg1, NI * HW1 * C1 * es);
+            dev_alloc(h, h->fg2, NI * HW1 * C2 * es);
+            // complex scratch: A holds dft_w output [N][Cin][H][m2] or the mixed modes; B holds X / Bh [N][Cout][H][m2]
+            const size_t m2a = h->cfg.modes2, m2b = h->cfg.modes2 / h->fp0, H0 = h->cfg.H, H1 = h->cfg.H / h->fp0;
+            size_t ca = NI * std::max<size_t>((size_t)h->D, C8) * H0 * m2a;          // level 0 (D or C/8 channels)
+            ca = std::max(ca, NI * (size_t)C2 * H1 * m2b);                            // level 1 (up to C/2 channels)
+            dev_alloc(h, h->fA, ca * 8);
+            dev_alloc(h, h->fB, ca * 8);
+            size_t m = NI * HW1 * (size_t)(h->fp0 * h->fp0 * C8);                     // conv_1 windows
+            m = std::max(m, NI * (HW1 / (h->fp1 * h->fp1)) * (size_t)(h->fp1 * h->fp1 * C2));      // conv_2 windows
+            m = std::max(m, (size_t)max_batch * h->L * (size_t)(h->fp1 * h->fp1 * C2));            // deconv_1 sub-pixel matrix
+            m = std::max(m, (size_t)max_batch * HW1 * (size_t)(h->fp0 * h->fp0 * C8));             // deconv_2 sub-pixel matrix
+            dev_alloc(h, h->wbuf, m * es);
+            dev_alloc(h, h->dfield, (size_t)h->K * max_batch * h->D * h->cfg.H * h->cfg.W * 4);
+            fno_twiddles(h);      // (a synchronous upload: here, never inside a stream capture)
+        } else if (h->wide) {
             const size_t BLs = BL;
             size_t m = tokens * g.R1 * (size_t)h->K1pad;                                  // conv1 windows
             m = std::max(m, tokens * g.R2 * (size_t)(g.k1 * g.k1 * C1));                   // conv2 windows

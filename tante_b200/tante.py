@@ -21,6 +21,8 @@ from . import _abi
 
 # reference models/enc_dec_cnn.py:39-46
 Patch_map = {64: (4, 4, 4), 32: (4, 4, 2), 16: (4, 2, 2), 8: (2, 2, 2), 4: (2, 2, 1), 2: (2, 1, 1)}
+# reference models/enc_dec_fno.py:39-46
+Patch_map_fno = {64: (8, 8), 32: (8, 4), 16: (4, 4), 8: (4, 2), 4: (2, 2), 2: (2, 1)}
 
 
 @dataclass
@@ -81,6 +83,31 @@ class _DecCNN(_ParamsOnly):          # dec_CNN (enc_dec_cnn.py:232-261)
         self.dec_conv_1 = _PatchDeconv(C, C // 2, ks[2])
         self.dec_conv_2 = _PatchDeconv(C // 2, C // 4, ks[1])
         self.dec_conv_3 = _PatchDeconv(C // 4, D, ks[0])
+
+
+class _Spectral(_ParamsOnly):        # SpectralLayer (enc_dec_fno.py:184-197)
+    def __init__(self, cin, cout, m1, m2):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(cin, cout, m1, m2, dtype=torch.cfloat) * (1.0 / (cin * cout) ** 0.5))
+        self.w0 = nn.Conv2d(cin, cout, kernel_size=1, bias=True)
+
+
+class _EncFNO(_ParamsOnly):          # enc_FNO (enc_dec_fno.py:224-252)
+    def __init__(self, D, C, ps, m1, m2):
+        super().__init__()
+        self.enc_spectral_1 = _Spectral(D, C // 8, m1, m2)
+        self.enc_conv_1 = _PatchConv(C // 8, C // 4, ps[0])
+        self.enc_spectral_2 = _Spectral(C // 4, C // 2, m1 // ps[0], m2 // ps[0])
+        self.enc_conv_2 = _PatchConv(C // 2, C, ps[1])
+
+
+class _DecFNO(_ParamsOnly):          # dec_FNO (enc_dec_fno.py:274-301)
+    def __init__(self, D, C, ps, m1, m2):
+        super().__init__()
+        self.dec_conv_1 = _PatchDeconv(C, C // 2, ps[1])
+        self.dec_spectral_1 = _Spectral(C // 2, C // 4, m1 // ps[0], m2 // ps[0])
+        self.dec_conv_2 = _PatchDeconv(C // 4, C // 8, ps[0])
+        self.dec_spectral_2 = _Spectral(C // 8, D, m1, m2)
 
 
 class _Block(_ParamsOnly):           # TransformerBlock (attn_backbone.py:38-57)
@@ -159,6 +186,8 @@ class _Engine:
         cfg.output_length = int(model.output_length)
         cfg.frame_interval = float(model.frame_interval)
         cfg.precision = precision
+        cfg.enc_dec_fno = 1 if model.enc_dec_type == "fno" else 0
+        cfg.modes1, cfg.modes2 = int(model.modes1), int(model.modes2)
         for k, seg in enumerate(model.blocks_axes):
             if len(seg) > _abi.TANTE_MAX_LAYERS:
                 raise ValueError("too many layers in one attn_axes segment")
@@ -203,9 +232,11 @@ class _Engine:
             return
         for n in self.names:
             p = params[n]
-            if p.device != self.device or p.dtype != torch.float32 or not p.is_contiguous():
-                raise RuntimeError(f"parameter {n} must be a contiguous float32 tensor on {self.device}")
-            _abi.check(self.lib.tante_bind_param(self.handle, n.encode(), p.data_ptr(), None, p.numel()))
+            ok_dtype = p.dtype == torch.float32 or p.dtype == torch.complex64     # SpectralLayer.weight is cfloat: bound as float pairs
+            if p.device != self.device or not ok_dtype or not p.is_contiguous():
+                raise RuntimeError(f"parameter {n} must be a contiguous float32 (or complex64) tensor on {self.device}")
+            numel = p.numel() * (2 if p.dtype == torch.complex64 else 1)
+            _abi.check(self.lib.tante_bind_param(self.handle, n.encode(), p.data_ptr(), None, numel))
         _abi.check(self.lib.tante_pack_params(self.handle, stream))
         self.bound_sig = sig
 
@@ -369,14 +400,25 @@ class TANTE(nn.Module):
             raise ValueError(
                 f"Block allocation doesn't match expansion order: expected {taylor_order} parts, "
                 f"got {len(self.blocks_axes)} (input='{self.attn_axes}').")
-        if enc_dec_type != "cnn":
-            raise NotImplementedError("enc_dec_type='fno' is outside the B200 hot path (SURVEY.md §8(f) rank 2)")
+        if enc_dec_type not in ("cnn", "fno"):
+            raise ValueError(f"unknown enc_dec_type {enc_dec_type!r}")
+        self.enc_dec_type, self.modes1, self.modes2 = enc_dec_type, modes1, modes2
         if overlap_ratio != 0.0:
             raise NotImplementedError("overlap_ratio != 0 is not supported by the patch-GEMM kernels")
         if float(mlp_ratio) != 1.0:
             raise NotImplementedError("mlp_ratio != 1.0 is not supported yet")
         ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
         self.patch_kernels = ks
+        if enc_dec_type == "fno":
+            ps = Patch_map_fno[patch_scale]
+            self.patch_kernels = ps
+            if patch_scale > 16:
+                raise NotImplementedError("enc_dec_type='fno' at patch_scale 32 / 64 (8x8 patch stages) is not implemented")
+            H1, W1 = self.shape[0] // ps[0], self.shape[1] // ps[0]
+            if (min(modes1, modes2) < ps[0] or 2 * modes1 > self.shape[0] or modes2 > self.shape[1] // 2
+                    or 2 * (modes1 // ps[0]) > H1 or modes2 // ps[0] > W1 // 2):
+                raise NotImplementedError("enc_dec_type='fno': the kept modes must fit the grid at both resolutions "
+                                          "(ps[0] <= modes, 2*modes1 <= H, modes2 <= W/2)")
         # what the CUDA library does not cover is refused HERE, not at the first forward
         if "C" in self.attn_axes:
             raise NotImplementedError("attention axis 'C' (channel attention with a 1 -> expanded_channel lift, "
@@ -396,9 +438,14 @@ class TANTE(nn.Module):
 
         # parameter containers, created in the reference's order (tante.py:85-123)
         self.decoders = nn.ModuleList()
-        self.encoder = _EncCNN(self.n_channel, embed_dim, ks)
-        for _ in range(taylor_order):
-            self.decoders.append(_DecCNN(self.n_channel, embed_dim, ks))
+        if enc_dec_type == "fno":             # enc_dec_fno.py:224-301 (inference / rollout only)
+            self.encoder = _EncFNO(self.n_channel, embed_dim, self.patch_kernels, modes1, modes2)
+            for _ in range(taylor_order):
+                self.decoders.append(_DecFNO(self.n_channel, embed_dim, self.patch_kernels, modes1, modes2))
+        else:
+            self.encoder = _EncCNN(self.n_channel, embed_dim, ks)
+            for _ in range(taylor_order):
+                self.decoders.append(_DecCNN(self.n_channel, embed_dim, ks))
         self.blocks = nn.ModuleList()
         for seg in self.blocks_axes:
             self.blocks.append(_Backbone(self.T, self.H_p, self.W_p, self.C, seg, n_head, mlp_ratio, dropout))

@@ -108,7 +108,8 @@ def test_default_init_and_state_dict_equal_the_reference():
         pytest.skip("upstream reference not mounted")
     ns = ref_shim.load_reference()
     md = ref_shim.make_metadata(3, 64, 96)
-    for kw in (dict(taylor_order=1, attn_axes="THWTHW", deg=True), dict(taylor_order=2, attn_axes="THW-HW", deg=False)):
+    for kw in (dict(taylor_order=1, attn_axes="THWTHW", deg=True), dict(taylor_order=2, attn_axes="THW-HW", deg=False),
+               dict(taylor_order=2, attn_axes="TH-W", deg=False, enc_dec_type="fno", modes1=16, modes2=16)):
         torch.manual_seed(211)
         ref = ns.TANTE(in_T=4, dset_metadata=md, patch_scale=8, dropout=0.1, **kw)
         torch.manual_seed(211)

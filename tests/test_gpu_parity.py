@@ -316,7 +316,9 @@ def test_host_prefetcher_pipeline_matches_direct_calls():
 # patch_scale 16 / 32 / 64 (shifted 4x4 windows + bilinear resize) and the attention axes L / Y / A,
 # axis lengths up to 96 -- against goldens written by the live reference (oracle/make_golden.py --round2)
 # ------------------------------------------------------------------------------------------------
-NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d11", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96"]
+NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d11", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
+        # enc_dec_type = 'fno' (enc_dec_fno.py): spectral layers as truncated DFTs (fno.cuh)
+        "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16"]
 
 
 @pytest.mark.parametrize("name", NEXT)
@@ -347,7 +349,8 @@ def test_next_scope_forward_and_rollout_fp32(name):
             assert rel_l2(der[k], z[f"stage_deriv{k}"][:, 0]) < FP32_DERIV_TOL, k
 
 
-@pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96"])
+@pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
+                                  "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16"])
 def test_next_scope_forward_bf16(name):
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
     with torch.inference_mode():
@@ -363,7 +366,7 @@ def test_next_scope_forward_bf16(name):
 
 def test_training_refused_for_inference_only_scopes():
     from gpu_util import make_model
-    for kw in (dict(patch_scale=16, attn_axes="TH"), dict(attn_axes="LT")):
+    for kw in (dict(patch_scale=16, attn_axes="TH"), dict(attn_axes="LT"), dict(attn_axes="TH", enc_dec_type="fno", modes1=8, modes2=8)):
         cfg = O.OracleConfig(n_fields=2, H=64, W=64, taylor_order=1, deg=True, **kw)
         model = make_model(cfg, O.make_state_dict(cfg, 1)).train()
         with pytest.raises(Exception, match="not implemented"):

@@ -464,9 +464,9 @@ static PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// 2-D row-major tensor map with a 128-byte-wide box (SWIZZLE_128B): dims {cols, rows}.
+// 2-D row-major tensor map, dims {cols, rows}; the box is one swizzle span wide (128 B for SWIZZLE_128B, 64 B for SWIZZLE_64B).
 static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, int rows, int cols,
-                         int ld_elems, int box_cols, int box_rows) {
+                         int ld_elems, int box_cols, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -474,7 +474,7 @@ static bool make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, int esize, cons
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -29,6 +29,7 @@
 #include "wgrad_tc.cuh"
 #include "metrics.cuh"
 #include "block_tail_tc.cuh"
+#include "block_tail2_tc.cuh"
 #include "wide_patch.cuh"
 #include "fno.cuh"
 
@@ -554,7 +555,7 @@ void launch_tail(tante_handle_s* h, const LayerPlan& lp, const LayerPlan* nx, co
     a.x_in = x_in; a.x_out = x_out; a.ln_out = nx ? ln_out : nullptr;
     a.x_mid = x_mid; a.ln2 = ln2; a.hpre = hpre; a.hact = hact;
     a.drop = drop; a.site1 = site1; a.site2 = site2;
-    CK(launch_block_tail(a, tokens, train, h->num_sms, st));
+    CK(launch_block_tail_any(a, tokens, train, h->num_sms, st));
     h->launches++;
 }
 
@@ -2420,7 +2421,7 @@ int tante_test_block_tail(const void* att, const void* Wo, const void* W1, const
         a.x_in = x_in; a.x_out = x_out; a.ln_out = reinterpret_cast<__nv_bfloat16*>(ln_out);
         a.x_mid = x_mid; a.ln2 = reinterpret_cast<__nv_bfloat16*>(ln2); a.hpre = reinterpret_cast<__nv_bfloat16*>(hpre);
         a.hact = reinterpret_cast<__nv_bfloat16*>(hact);
-        for (int i = 0; i < std::max(1, iters); ++i) CK(launch_block_tail(a, M, x_mid != nullptr, sms, st));
+        for (int i = 0; i < std::max(1, iters); ++i) CK(launch_block_tail_any(a, M, x_mid != nullptr, sms, st));
     });
 }
 

@@ -44,15 +44,25 @@ struct BtParams {
     uint32_t site1, site2;
 };
 
-template <int MODE /* 0: inference, 1: training (stores the tape), 2: training with dropout */>
+// NCTA = 2: the CTA pair of a 2-cluster runs every MMA as ONE tcgen05.mma.cta_group::2 of M = 256 (gemm_tc.cuh): each CTA owns
+// 128 token rows (its own A tile, accumulator, x_mid, epilogue) and streams only ITS HALF of every weight stage (128 of the
+// 256 output rows), so the weight traffic per token -- the L2 -> SM stream that bounds this kernel -- is halved and a ring
+// stage covers a whole k-block.  The leader (cluster rank 0) issues the MMAs; its barriers collect the TMA bytes of both
+// CTAs, its commits are multicast to both, and the peer's idle warp 1 forwards "A tile rewritten" / "accumulator free".
+template <int MODE /* 0: inference, 1: training (stores the tape), 2: training with dropout */, int NCTA>
 __global__ void __launch_bounds__(kBtThreads, 1)
 block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWo,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                   const __grid_constant__ CUtensorMap tmXin, const __grid_constant__ CUtensorMap tmXmid,
                   const __grid_constant__ CUtensorMap tmXout, const __grid_constant__ CUtensorMap tmLn2,
                   const __grid_constant__ CUtensorMap tmHpre, const __grid_constant__ CUtensorMap tmHact,
-                  const __grid_constant__ CUtensorMap tmLnOut, BtParams p) {
+                  const __grid_constant__ CUtensorMap tmLnOut, BtParams p, long long* trace) {
     constexpr bool TRAIN = MODE != 0;
+    // TANTE_TAIL_TRACE (debugging aid): CTA 0 records (event, clock64) pairs -- role 0 = MMA warp, 1 = first epilogue warp
+    int tr_n = 0;
+    auto TR = [&](int role, int ev) {
+        if (trace && blockIdx.x == 0 && tr_n < 1024) { trace[(role * 1024 + tr_n) * 2] = ev; trace[(role * 1024 + tr_n) * 2 + 1] = clock64(); ++tr_n; }
+    };
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B) as an OFFSET into the shared array: a pointer -> integer -> pointer round trip would
     // lose the address space and turn every shared-memory access of the epilogue into a generic LD / ST
@@ -75,7 +85,10 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     pdl_trigger();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int tiles = (p.M + 127) / 128;
+    const int crank = NCTA == 2 ? (int)ptx::cluster_ctarank() : 0;     // rank inside the CTA pair
+    const int cid = blockIdx.x / NCTA;                                // work-unit sequence of this CTA (pair)
+    const int ncl = gridDim.x / NCTA;
+    const int tiles = (p.M + 128 * NCTA - 1) / (128 * NCTA);          // units of 128 rows per CTA
 
     for (int i = threadIdx.x; i < kBtC; i += kBtThreads) {
         sP[i] = p.bo[i]; sP[kBtC + i] = p.g2[i]; sP[2 * kBtC + i] = p.be2[i]; sP[3 * kBtC + i] = p.b1[i];
@@ -89,15 +102,20 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int s = 0; s < kBtWStages; ++s) { ptx::mbar_init(&w_full[s], 1); ptx::mbar_init(&w_empty[s], 1); }
         ptx::mbar_init(a_full, 1);
         ptx::mbar_init(a_empty, TRAIN ? 1 + kBtEpiWarps : 1);     // the last GEMM's commit (+ training: the stores that read the A tile)
-        ptx::mbar_init(a_ready, kBtEpiWarps);
+        // pair: the leader's copies also take one forwarded arrival of the peer
+        ptx::mbar_init(a_ready, kBtEpiWarps + ((NCTA == 2 && crank == 0) ? 1 : 0));
         ptx::mbar_init(acc_full, 1);
-        ptx::mbar_init(acc_free, kBtEpiWarps);
+        ptx::mbar_init(acc_free, kBtEpiWarps + ((NCTA == 2 && crank == 0) ? 1 : 0));
         for (int i = 0; i < 2 * kBtEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    if (warp == 1) {
+        if (NCTA == 2) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+        else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) ptx::cluster_sync_all();     // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
@@ -108,17 +126,29 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int ws = 0;
             uint32_t wph = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            for (int tile = cid; tile < tiles; tile += ncl, ++it) {
                 ptx::mbar_wait(a_empty, (uint32_t)(it & 1) ^ 1u);
-                ptx::mbar_arrive_expect_tx(a_full, 4 * kBtKBlk);
-                for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(sA + kb * kBtKBlk, &tmA, a_full, kb * 64, tile * 128);
+                if (NCTA == 2) {
+                    // the leader's barrier counts the bytes of both CTAs' tiles (one arrival: the leader's)
+                    if (crank == 0) ptx::mbar_arrive_expect_tx(a_full, 2 * 4 * kBtKBlk);
+                    for (int kb = 0; kb < 4; ++kb)
+                        ptx::tma_load_2d_pair(sA + kb * kBtKBlk, &tmA, a_full, kb * 64, (tile * 2 + crank) * 128);
+                } else {
+                    ptx::mbar_arrive_expect_tx(a_full, 4 * kBtKBlk);
+                    for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(sA + kb * kBtKBlk, &tmA, a_full, kb * 64, tile * 128);
+                }
                 for (int ph = 0; ph < 3; ++ph) {
                     const CUtensorMap* wm = ph == 0 ? &tmWo : (ph == 1 ? &tmW1 : &tmW2);
                     for (int kb = 0; kb < 4; ++kb) {
-                        for (int nh = 0; nh < 2; ++nh) {
+                        for (int nh = 0; nh < 2 / NCTA; ++nh) {
                             ptx::mbar_wait(&w_empty[ws], wph ^ 1u);
-                            ptx::mbar_arrive_expect_tx(&w_full[ws], kBtWStage);
-                            ptx::tma_load_2d(sW + ws * kBtWStage, wm, &w_full[ws], kb * 64, nh * 128);
+                            if (NCTA == 2) {      // this CTA's half of the output rows of k-block kb
+                                if (crank == 0) ptx::mbar_arrive_expect_tx(&w_full[ws], 2 * kBtWStage);
+                                ptx::tma_load_2d_pair(sW + ws * kBtWStage, wm, &w_full[ws], kb * 64, crank * 128);
+                            } else {
+                                ptx::mbar_arrive_expect_tx(&w_full[ws], kBtWStage);
+                                ptx::tma_load_2d(sW + ws * kBtWStage, wm, &w_full[ws], kb * 64, nh * 128);
+                            }
                             if (++ws == kBtWStages) { ws = 0; wph ^= 1u; }
                         }
                     }
@@ -127,11 +157,26 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 1) {
         // ===== MMA issuer: three chained GEMM phases per tile into the one accumulator =====
-        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc = NCTA == 2 ? ptx::umma_idesc_bf16(256, 256) : ptx::umma_idesc_bf16(128, 128);
         int ws = 0;
         uint32_t wph = 0, ar = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        if (NCTA == 2 && crank == 1) {
+            // the peer's otherwise idle warp forwards its epilogue's "A tile rewritten" (twice per tile) and "accumulator
+            // free" to the leader's barriers
+            for (int tile = cid; tile < tiles; tile += ncl, ++it) {
+                for (int ph = 1; ph < 3; ++ph) {
+                    ptx::mbar_wait(a_ready, ar & 1u);
+                    ++ar;
+                    if (lane == 0) ptx::mbar_arrive_leader(a_ready);
+                    __syncwarp();
+                }
+                ptx::mbar_wait(acc_free, (uint32_t)(it & 1));
+                if (lane == 0) ptx::mbar_arrive_leader(acc_free);
+                __syncwarp();
+            }
+        }
+        for (int tile = cid; tile < tiles && crank == 0; tile += ncl, ++it) {
             for (int ph = 0; ph < 3; ++ph) {
                 if (ph == 0) {
                     ptx::mbar_wait(acc_free, (uint32_t)(it & 1) ^ 1u);     // the previous tile's accumulator has been read
@@ -141,26 +186,35 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     ++ar;
                 }
                 ptx::tc_fence_after();
+                if (lane == 0) TR(0, 100 + ph);
                 for (int kb = 0; kb < 4; ++kb) {
-                    for (int nh = 0; nh < 2; ++nh) {
+                    for (int nh = 0; nh < 2 / NCTA; ++nh) {
                         ptx::mbar_wait(&w_full[ws], wph);
                         ptx::tc_fence_after();
                         if (lane == 0) {
                             const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(sA + kb * kBtKBlk));
                             const uint64_t db = ptx::umma_desc_k_sw128(ptx::smem_u32(sW + ws * kBtWStage));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16(tmem_base + (uint32_t)(nh * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                               (kb | k) != 0);
-                            ptx::umma_commit(&w_empty[ws]);
+                            for (int k = 0; k < 4; ++k) {
+                                if (NCTA == 2) ptx::umma_bf16_pair(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                                else ptx::umma_bf16(tmem_base + (uint32_t)(nh * 128), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                                    (kb | k) != 0);
+                            }
+                            if (NCTA == 2) ptx::umma_commit_pair(&w_empty[ws]); else ptx::umma_commit(&w_empty[ws]);
                         }
                         __syncwarp();
                         if (++ws == kBtWStages) { ws = 0; wph ^= 1u; }
                     }
                 }
                 if (lane == 0) {
-                    ptx::umma_commit(acc_full);
-                    if (ph == 2) ptx::umma_commit(a_empty);
+                    TR(0, 200 + ph);
+                    if (NCTA == 2) {
+                        ptx::umma_commit_pair(acc_full);
+                        if (ph == 2) ptx::umma_commit_pair(a_empty);
+                    } else {
+                        ptx::umma_commit(acc_full);
+                        if (ph == 2) ptx::umma_commit(a_empty);
+                    }
                 }
                 __syncwarp();
             }
@@ -174,8 +228,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;
         const int cs = ew >> 2;
         uint8_t* ebuf = sE + (size_t)ew * kBtEbuf;             // own staging buffer (4 KB)
-        uint8_t* aslot = sA + (size_t)ew * kBtEbuf;            // phase 1: landing zone of the second residual chunk (A tile is idle)
         uint8_t* aown = sA + (size_t)cs * kBtKBlk + (size_t)q * 32 * 128;    // this warp's 32 rows of k-block cs inside the A tile
+        uint8_t* aslot = aown;     // phase 1: landing zone of the second residual chunk (the A tile is idle; no other warp touches this region)
         uint64_t* rb = rbar + ew * 2;
         uint32_t rph = 0;             // bit b = phase of rb[b]
         uint32_t af = 0;              // completed acc_full waits
@@ -196,7 +250,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             st[((q * 4 + cs) * 32 + lane) * 2 + 1] = rsq;
             ptx::tc_wait_st();
             ptx::tc_fence_before();
-            named_bar_sync(5, 16 * 32);             // every epilogue warp: statistics + TMEM rows written, A-tile slots consumed
+            named_bar_sync(5 + q, 4 * 32);          // the four warps of the quarter (same token rows): statistics + TMEM rows written
             ptx::tc_fence_after();
             float s = 0.f, sq = 0.f;
 #pragma unroll
@@ -231,8 +285,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         };
 
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int row0 = tile * 128 + q * 32;
+        for (int tile = cid; tile < tiles; tile += ncl) {
+            const int row0 = (tile * NCTA + crank) * 128 + q * 32;
             const uint32_t tm_acc = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t tm_x = tm_acc + 256u;
 
@@ -242,8 +296,10 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ptx::mbar_arrive_expect_tx(&rb[0], kBtEbuf);
                 ptx::tma_load_2d(ebuf, &tmXin, &rb[0], cs * 32, row0);
             }
+            if (ew == 0 && lane == 0) TR(1, 10);
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
+            if (ew == 0 && lane == 0) TR(1, 11);
             if (lane == 0) {      // the A tile has been consumed by the first GEMM: its 4 KB slot takes the second chunk
                 ptx::mbar_arrive_expect_tx(&rb[1], kBtEbuf);
                 ptx::tma_load_2d(aslot, &tmXin, &rb[1], (cs + 4) * 32, row0);
@@ -294,8 +350,11 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             {
                 float mean, rstd;
+                if (ew == 0 && lane == 0) TR(1, 12);
                 row_stats(0, rsum, rsq, mean, rstd);
+                if (ew == 0 && lane == 0) TR(1, 13);
                 ln_kblock(tm_x, mean, rstd, g2, be2, aown, lane);
+                if (ew == 0 && lane == 0) TR(1, 14);
                 if (TRAIN) {      // the saved LN2 output leaves straight from the A tile (same 32-row x 128-B swizzled box)
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -310,6 +369,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             // ---------------- phase 2: hidden = gelu_tanh(acc + b1) -> A tile ----------------
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
+            if (ew == 0 && lane == 0) TR(1, 21);
+            if (lane == 0 && tile + ncl < tiles) {      // pull the next tile's residual rows into L2 (the loads themselves are issued late)
+                const int nrow0 = ((tile + ncl) * NCTA + crank) * 128 + q * 32;
+                ptx::tma_prefetch_l2_2d(&tmXin, cs * 32, nrow0);
+                ptx::tma_prefetch_l2_2d(&tmXin, (cs + 4) * 32, nrow0);
+            }
             if (TRAIN) {      // the LN2 store has finished reading this warp's rows of the A tile
                 if (lane == 0) ptx::bulk_wait_read<0>();
                 __syncwarp();
@@ -358,8 +423,10 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) ptx::mbar_arrive(a_ready);
 
             // ---------------- phase 3: x_out = x_mid + drop(acc + b2) ; LN1' ----------------
+            if (ew == 0 && lane == 0) TR(1, 24);
             ptx::mbar_wait(acc_full, af & 1u); ++af;
             ptx::tc_fence_after();
+            if (ew == 0 && lane == 0) TR(1, 31);
             if (TRAIN) {      // hidden / pre-activation stores drained: the producer may refill the A tile
                 ebuf_free();
                 if (lane == 0) ptx::mbar_arrive(a_empty);
@@ -405,9 +472,11 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(acc_free);          // the next tile's first GEMM may overwrite the accumulator
+            if (ew == 0 && lane == 0) TR(1, 32);
             if (p.has_ln_out) {
                 float mean, rstd;
                 row_stats(1, rsum, rsq, mean, rstd);
+                if (ew == 0 && lane == 0) TR(1, 33);
                 ebuf_free();
                 ln_kblock(tm_x, mean, rstd, gn, ben, ebuf, lane);
                 ptx::fence_proxy_async();
@@ -419,12 +488,14 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 named_bar_sync(1 + q, 4 * 32);
                 ptx::tc_fence_after();
             }
+            if (ew == 0 && lane == 0) TR(1, 34);
         }
         if (lane == 0) ptx::bulk_wait_all<0>();
     }
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    if (NCTA == 2) ptx::cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair's MMAs may still touch it
+    else __syncthreads();
+    if (warp == 1) { if (NCTA == 2) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512); }
 }
 
 static cudaError_t bt_set_attrs() {
@@ -432,9 +503,10 @@ static cudaError_t bt_set_attrs() {
     if (!get_encode_tiled()) return cudaErrorNotSupported;
     if (!attrs_needed(done)) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(block_tail_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(block_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(block_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e;
+#define TANTE_BT_ATTR(MODE, NC) \
+    if ((e = cudaFuncSetAttribute(block_tail_kernel<MODE, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmem)) != cudaSuccess) return e
+    TANTE_BT_ATTR(0, 1); TANTE_BT_ATTR(1, 1); TANTE_BT_ATTR(2, 1); TANTE_BT_ATTR(0, 2); TANTE_BT_ATTR(1, 2); TANTE_BT_ATTR(2, 2);
+#undef TANTE_BT_ATTR
     return cudaSuccess;
 }
 
@@ -478,20 +550,46 @@ static cudaError_t launch_block_tail(const BlockTailArgs& a, int M, bool train, 
     p.bo = a.bo; p.g2 = a.g2; p.be2 = a.be2; p.b1 = a.b1; p.b2 = a.b2; p.gn = a.gn; p.ben = a.ben;
     p.M = M; p.has_ln_out = a.ln_out != nullptr;
     p.drop = train ? a.drop : DropCfg(); p.site1 = a.site1; p.site2 = a.site2;
-    const int tiles = (M + 127) / 128;
+    // CTA pairs (TANTE_TAIL_2CTA = 0 disables them) once there are enough 256-row units to fill the machine
+    static const int pair_mode = getenv("TANTE_TAIL_2CTA") ? atoi(getenv("TANTE_TAIL_2CTA")) : 1;
+    const int ncta = (pair_mode == 2 || (pair_mode == 1 && M >= 256 * (num_sms / 2))) ? 2 : 1;
+    const int tiles = (M + 128 * ncta - 1) / (128 * ncta);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)std::min(tiles, num_sms)); cfg.blockDim = dim3(kBtThreads); cfg.dynamicSmemBytes = kBtSmem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3((unsigned)(ncta * std::min(tiles, num_sms / ncta))); cfg.blockDim = dim3(kBtThreads); cfg.dynamicSmemBytes = kBtSmem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
     int na = 0;
+    if (ncta == 2) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
     if (pdl_enabled(st)) {
         at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
     cfg.attrs = at; cfg.numAttrs = (unsigned)na;
-    if (train && p.drop.p > 0.f) return cudaLaunchKernelEx(&cfg, block_tail_kernel<2>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
-    if (train) return cudaLaunchKernelEx(&cfg, block_tail_kernel<1>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
-    return cudaLaunchKernelEx(&cfg, block_tail_kernel<0>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p);
+    long long* trace = nullptr;
+    static const char* trace_path = getenv("TANTE_TAIL_TRACE");      // debugging aid: per-phase clock64 stamps of CTA 0
+    if (trace_path) {
+        if (cudaMalloc(&trace, 3 * 1024 * 2 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(trace, 0, 3 * 1024 * 2 * sizeof(long long), st);
+    }
+    cudaError_t e;
+#define TANTE_BT_LAUNCH(MODE, NC) \
+    e = cudaLaunchKernelEx(&cfg, block_tail_kernel<MODE, NC>, tmA, tmWo, tmW1, tmW2, tmXin, tmXmid, tmXout, tmLn2, tmHpre, tmHact, tmLnOut, p, trace)
+    const int mode = (train && p.drop.p > 0.f) ? 2 : (train ? 1 : 0);
+    if (ncta == 2) { if (mode == 2) TANTE_BT_LAUNCH(2, 2); else if (mode == 1) TANTE_BT_LAUNCH(1, 2); else TANTE_BT_LAUNCH(0, 2); }
+    else { if (mode == 2) TANTE_BT_LAUNCH(2, 1); else if (mode == 1) TANTE_BT_LAUNCH(1, 1); else TANTE_BT_LAUNCH(0, 1); }
+#undef TANTE_BT_LAUNCH
+    if (trace) {
+        std::vector<long long> hbuf(3 * 1024 * 2);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hbuf.data(), trace, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(trace);
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(hbuf.data(), sizeof(long long), hbuf.size(), f); fclose(f); }
+    }
+    return e;
 }
 
 }  // namespace tante

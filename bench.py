@@ -796,8 +796,15 @@ def run_b200_train(args):
                   patch_scale=8, deg=True, dropout=args.dropout, precision=args.precision)
     cpu_sd = {k: v.clone() for k, v in model.state_dict().items()}
     model = model.to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)    # tante.yaml:38-41 (torch's fused kernel)
     bucket = GradBucket(model)
+    if os.environ.get("TANTE_TORCH_OPTIMIZER", "0") != "0":
+        opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)    # tante.yaml:38-41 (torch's fused kernel)
+    else:
+        # same update rule, one launch over the flat gradient with the clip folded in (tante_optimizer_step); under
+        # torchrun the bucket is all-reduced by the library's own NCCL communicator (tante_allreduce_grads)
+        from tante_b200 import FusedAdamW
+        opt = FusedAdamW(model.parameters(), lr=5e-5, weight_decay=1e-5, model=model)
+        bucket.init_native_comm(model)
 
     g = torch.Generator().manual_seed(212 + rank)
     host_x = torch.randn(B, 4, D, H, W, generator=g).pin_memory()

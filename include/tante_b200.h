@@ -195,6 +195,27 @@ TANTE_API int tante_mse_cl(const float* y, const float* ref, int32_t B, int32_t 
 TANTE_API int tante_metric_moments(const float* x, const float* y, int64_t BT, int64_t HW, int32_t C, double* out,
                                    void* stream);
 
+/* ---- optimizer tail of a training step (SURVEY.md 8(b) `allreduce_grads`; reference trainer/trainer.py:192-198,
+ *      trainer/r_trainer.py:155-157: clip_grad_norm_ / clip_grad_value_ + torch.optim.AdamW.step) ------------------------
+ * All three work on the FLAT gradient of tante_backward (f32[tante_grad_numel()], parameter i at tante_param_grad_offset(i)).
+ *
+ * tante_comm_unique_id : rank 0 fills id128 (128 bytes, ncclGetUniqueId); the host side broadcasts it.
+ * tante_comm_init      : every rank, collectively: ncclCommInitRank on the handle's device; the communicator lives in the handle.
+ * tante_allreduce_grads: in-place SUM all-reduce of the flat gradient on `stream` over `comm` (an ncclComm_t; NULL = the
+ *                        handle's own).  NCCL is the copy already loaded in the process (dlopen, no link-time dependency).
+ * tante_optimizer_step : g = grad * grad_scale (1 / world size after the sum); clip_mode 1: g *= min(1, clip / (||g||_2 + 1e-6))
+ *                        over ALL parameters (clip_grad_norm_), 2: clamp to [-clip, clip] (clip_grad_value_), 0: none; then
+ *                        AdamW (decoupled weight decay, bias correction with `step` counted from 1) on every parameter
+ *                        through its bound master pointer, moments in the caller-owned flat buffers exp_avg / exp_avg_sq
+ *                        (laid out like the gradient).  The clipped gradient is written back to `grad`; grad_sumsq (nullable,
+ *                        f64[1], device) receives sum g^2 before clipping.  Follow with tante_pack_params. */
+TANTE_API int tante_comm_unique_id(void* id128);
+TANTE_API int tante_comm_init(tante_handle_t h, const void* id128, int32_t nranks, int32_t rank);
+TANTE_API int tante_allreduce_grads(tante_handle_t h, float* grad, void* comm, void* stream);
+TANTE_API int tante_optimizer_step(tante_handle_t h, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                                   float beta2, float eps, float weight_decay, int64_t step, int32_t clip_mode, float clip,
+                                   float grad_scale, double* grad_sumsq, void* stream);
+
 /* Test hook: run one GEMM of the library stand-alone, C[M,N] = epi(A[M,K] * W[N,K]^T + bias).
  * use_tc = 1: tcgen05 bf16 kernel (A, W bf16; C bf16 when out_bf16 else f32);
  * use_tc = 0: FFMA fp32 kernel (A, W, C f32).  epi: 0 bias, 1 +relu, 2 +gelu(erf), 3 +gelu(tanh),

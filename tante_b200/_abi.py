@@ -67,6 +67,12 @@ SIGNATURES = {
     "tante_test_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "tante_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "tante_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "tante_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tante_optimizer_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_int64, C.c_int32, C.c_float, C.c_float, C.c_void_p,
+                                       C.c_void_p]),
     "tante_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_uint64]),
     "tante_grad_numel": (C.c_int64, [C.c_void_p]),
     "tante_param_grad_offset": (C.c_int64, [C.c_void_p, C.c_int32]),

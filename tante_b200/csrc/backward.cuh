@@ -159,32 +159,69 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
 }
 
 // ---- embed backward: dv = g*(1+scale_t); dscale[t] += g*v; dshift[t] += g; ds_emb[hw] += g; dt_emb[t] += g ----
-// grid = L (one CTA per latent position hw), 256 threads over channels (C <= 1024, C % 4 == 0 not needed).
+// Thread = (latent position hw, 4 channels): 128-bit loads of g and v, the batch loop unrolled for loads in flight; the block's
+// positions are summed in shared memory before the atomics.  grid = ceil(L / (256 / (C / 4))), C % 4 == 0, C <= 1024.
 template <typename TA>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v,
                                                         const float* __restrict__ film, TA* __restrict__ dv,
                                                         float* __restrict__ dfilm /* [T][2][C] */,
                                                         float* __restrict__ ds_emb, float* __restrict__ dt_emb, int B,
                                                         int T, int L, int C) {
-    const int hw = blockIdx.x;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float semb = 0.f;
-        for (int t = 0; t < T; ++t) {
-            const float sc = film[(size_t)(t * 2) * C + c];
-            float dsc = 0.f, dsh = 0.f;
+    __shared__ float red[256 * 4];
+    const int c4n = C / 4;                       // threads per position
+    const int ppb = blockDim.x / c4n;            // positions per block
+    const int pl = threadIdx.x / c4n;            // local position
+    const int c = (threadIdx.x % c4n) * 4;
+    const int hw = blockIdx.x * ppb + pl;
+    const bool live = pl < ppb && hw < L;
+    float semb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < T; ++t) {
+        float sc[4], dsc[4] = {0.f, 0.f, 0.f, 0.f}, dsh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            Vec4<float>::load(film + (size_t)(t * 2) * C + c, sc);
+#pragma unroll 4
             for (int b = 0; b < B; ++b) {
                 const size_t m = ((size_t)(b * T + t) * L + hw) * C + c;
-                const float gg = g[m];
-                dv[m] = from_f32<TA>(gg * (1.0f + sc));
-                dsc = fmaf(gg, v[m], dsc);
-                dsh += gg;
+                float gg[4], vv[4], o[4];
+                Vec4<float>::load(g + m, gg);
+                Vec4<float>::load(v + m, vv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    o[j] = gg[j] * (1.0f + sc[j]);
+                    dsc[j] = fmaf(gg[j], vv[j], dsc[j]);
+                    dsh[j] += gg[j];
+                }
+                Vec4<TA>::store(dv + m, o);
             }
-            semb += dsh;
-            atomicAdd(dfilm + (size_t)(t * 2) * C + c, dsc);
-            atomicAdd(dfilm + (size_t)(t * 2 + 1) * C + c, dsh);
-            atomicAdd(dt_emb + (size_t)t * C + c, dsh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) semb[j] += dsh[j];
         }
-        ds_emb[(size_t)hw * C + c] += semb;
+        // sum the block's positions, then one atomic per (t, channel) and quantity
+        for (int k = 0; k < 2; ++k) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[threadIdx.x * 4 + j] = live ? (k == 0 ? dsc[j] : dsh[j]) : 0.f;
+            __syncthreads();
+            if (threadIdx.x < c4n) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float tot = 0.f;
+                    for (int q = 0; q < ppb; ++q) tot += red[(q * c4n + threadIdx.x) * 4 + j];
+                    if (k == 0) atomicAdd(dfilm + (size_t)(t * 2) * C + c + j, tot);
+                    else {
+                        atomicAdd(dfilm + (size_t)(t * 2 + 1) * C + c + j, tot);
+                        atomicAdd(dt_emb + (size_t)t * C + c + j, tot);
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+        float cur[4];
+        Vec4<float>::load(ds_emb + (size_t)hw * C + c, cur);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] += semb[j];
+        Vec4<float>::store(ds_emb + (size_t)hw * C + c, cur);
     }
 }
 
@@ -205,8 +242,11 @@ __global__ void __launch_bounds__(256) film_bwd_kernel(const float* __restrict__
     float* hh = hs + Ch;         // [Ch]
     float* ds = hh + Ch;         // [C] dscale
     float* dh = ds + C;          // [C] dshift
-    __shared__ float red[256];
-    const int n = blockIdx.x;
+    __shared__ float red[8];
+    // grid (n conditions, Y slices): a slice takes 1/Y of the outer-product atomics and 8 hidden units per pass (one warp
+    // each, lanes over the C outputs); dcond must be zeroed by the caller (slices add their partial sums)
+    const int n = blockIdx.x, y = blockIdx.y, Y = gridDim.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float t = cond[n];
     for (int i = threadIdx.x; i < Ch; i += blockDim.x) {
         hs[i] = fmaxf(fmaf(w0s[i], t, b0s[i]), 0.f);
@@ -217,37 +257,42 @@ __global__ void __launch_bounds__(256) film_bwd_kernel(const float* __restrict__
         dh[c] = dfilm[((size_t)n * 2 + 1) * C + c];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(gb2s + c, ds[c]);
-        atomicAdd(gb2h + c, dh[c]);
+    if (y == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            atomicAdd(gb2s + c, ds[c]);
+            atomicAdd(gb2h + c, dh[c]);
+        }
     }
-    for (int i = threadIdx.x; i < C * Ch; i += blockDim.x) {
+    for (int i = y * blockDim.x + threadIdx.x; i < C * Ch; i += Y * blockDim.x) {
         const int c = i / Ch, j = i % Ch;
         if (hs[j] != 0.f) atomicAdd(gw2s + i, ds[c] * hs[j]);
         if (hh[j] != 0.f) atomicAdd(gw2h + i, dh[c] * hh[j]);
     }
     float dt = 0.f;
-    for (int j = threadIdx.x; j < Ch; j += blockDim.x) {
+    for (int j = y * 8 + warp; j < Ch; j += Y * 8) {
         float a = 0.f, b = 0.f;
-        for (int c = 0; c < C; ++c) {
+        for (int c = lane; c < C; c += 32) {
             a = fmaf(ds[c], w2s[(size_t)c * Ch + j], a);
             b = fmaf(dh[c], w2h[(size_t)c * Ch + j], b);
         }
+        a = warp_sum(a); b = warp_sum(b);
         if (hs[j] <= 0.f) a = 0.f;
         if (hh[j] <= 0.f) b = 0.f;
-        atomicAdd(gw0s + j, a * t);
-        atomicAdd(gb0s + j, a);
-        atomicAdd(gw0h + j, b * t);
-        atomicAdd(gb0h + j, b);
-        dt += a * w0s[j] + b * w0h[j];
+        if (lane == 0) {
+            atomicAdd(gw0s + j, a * t);
+            atomicAdd(gb0s + j, a);
+            atomicAdd(gw0h + j, b * t);
+            atomicAdd(gb0h + j, b);
+            dt += a * w0s[j] + b * w0h[j];
+        }
     }
-    red[threadIdx.x] = dt;
+    if (lane == 0) red[warp] = dt;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
+    if (threadIdx.x == 0 && dcond) {
+        float tot = 0.f;
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        atomicAdd(dcond + n, tot);
     }
-    if (threadIdx.x == 0 && dcond) dcond[n] = red[0];
 }
 
 // ---- FiLM application backward on the (B, L, C) derivative latent (tante.py:222-230) --------------------

@@ -1,8 +1,10 @@
 // Residual axis MLP ("propagator") on tensor cores for the bf16 mode:
 //   x += W2 * gelu_erf(W1 * x_axis + b1) + b2   along one axis of length S <= 64, in place on the fp32 latent
 // (reference attn_backbone.py:111-119,140-146; under autocast the reference also runs these Linears in bf16).
-// Element (outer, p, col) lives at (outer*S + p)*IC + col.  One CTA = one `outer` x 128 columns, 4 warps x 32
-// columns.  Both S x S weight matrices (bf16, padded to 16) are the A operands, the S x 128 slab is the B
+// Element (outer, p, col) lives at (outer*S + p)*IC + col.  One tile = one `outer` x 128 columns, 4 warps x 32
+// columns; CTAs are persistent over tiles (column blocks fastest) so that the S x S weight matrices are fetched and
+// converted once per CTA, not once per 128-column slab (at S = 64 that prologue cost as much as the slab itself).
+// Both weight matrices (bf16, padded to 16) are the A operands, the S x 128 slab is the B
 // operand via ldmatrix.trans; the hidden tile never leaves shared memory.  HBM traffic: read x + write x.
 #pragma once
 #include "attention_mma.cuh"
@@ -13,7 +15,7 @@ namespace tante {
 __device__ __forceinline__ uint32_t slab_off(int r, int chunk) { return (uint32_t)(r * 256 + (((chunk & 8) | ((chunk ^ r) & 7)) << 4)); }
 
 template <int MB /* S_pad / 16 */>
-__global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, float* x, int S, long long IC,
+__global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, float* x, int S, long long IC, long long n_outer,
                                                              const float* __restrict__ W1, const float* __restrict__ b1,
                                                              const float* __restrict__ W2, const float* __restrict__ b2) {
     constexpr int SP = MB * 16;
@@ -27,11 +29,7 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
     float* sb2 = sb1 + SP;
 
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-    const long long col0 = (long long)blockIdx.y * 128;
-    const long long outer = blockIdx.x;
-    float* base = x + (size_t)outer * S * IC + col0;
-    const float* ibase = xin + (size_t)outer * S * IC + col0;    // xin == x: in place; else out of place (training)
-    const int ncol = (int)min((long long)128, IC - col0);     // multiple of 4
+    const long long ncb = (IC + 127) / 128;
 
     for (int i = tid; i < SP * SP; i += 128) {
         const int j = i / SP, k = i % SP;
@@ -40,6 +38,20 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
         *reinterpret_cast<__nv_bfloat16*>(sW2 + j * WPITCH + k * 2) = __float2bfloat16_rn(ok ? W2[j * S + k] : 0.f);
     }
     for (int i = tid; i < SP; i += 128) { sb1[i] = i < S ? b1[i] : 0.f; sb2[i] = i < S ? b2[i] : 0.f; }
+
+    const uint32_t aV = (uint32_t)__cvta_generic_to_shared(sV), aH = (uint32_t)__cvta_generic_to_shared(sH);
+    const uint32_t aW1 = (uint32_t)__cvta_generic_to_shared(sW1), aW2 = (uint32_t)__cvta_generic_to_shared(sW2);
+    const int g = lane >> 2, t = lane & 3;
+    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);
+    const int lchk = lane >> 4;
+
+  for (long long tile = blockIdx.x; tile < n_outer * ncb; tile += gridDim.x) {
+    const long long outer = tile / ncb;
+    const long long col0 = (tile % ncb) * 128;
+    float* base = x + (size_t)outer * S * IC + col0;
+    const float* ibase = xin + (size_t)outer * S * IC + col0;    // xin == x: in place; else out of place (training)
+    const int ncol = (int)min((long long)128, IC - col0);     // multiple of 4
+    __syncthreads();      // the previous tile's slab has been consumed (and, first pass, the weights are in place)
 #pragma unroll 4
     for (int i = tid; i < SP * 32; i += 128) {
         const int p = i / 32, c4 = (i % 32) * 4;
@@ -51,12 +63,6 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
         *reinterpret_cast<uint2*>(sV + slab_off(p, c4 / 8) + (c4 % 8) * 2) = pk;
     }
     __syncthreads();
-
-    const uint32_t aV = (uint32_t)__cvta_generic_to_shared(sV), aH = (uint32_t)__cvta_generic_to_shared(sH);
-    const uint32_t aW1 = (uint32_t)__cvta_generic_to_shared(sW1), aW2 = (uint32_t)__cvta_generic_to_shared(sW2);
-    const int g = lane >> 2, t = lane & 3;
-    const int lrow = (lane & 7) + 8 * ((lane >> 3) & 1);
-    const int lchk = lane >> 4;
 
     for (int pass = 0; pass < 2; ++pass) {
         const uint32_t aW = pass == 0 ? aW1 : aW2;
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
             }
         }
     }
+  }
 }
 
 static void prop_set_attrs() {
@@ -140,18 +147,21 @@ static void prop_set_attrs() {
 }
 
 static bool launch_propagator_mma(const float* xin, float* x, int S, long long IC, long long outer, const float* W1, const float* b1,
-                                  const float* W2, const float* b2, cudaStream_t st, cudaError_t* err) {
-    if (S < 1 || S > 64 || (IC + 127) / 128 > 65535 || outer > 0x7fffffffLL) return false;
-    dim3 grid((unsigned)outer, (unsigned)((IC + 127) / 128));
+                                  const float* W2, const float* b2, cudaStream_t st, cudaError_t* err, int num_sms = 148) {
+    if (S < 1 || S > 64 || outer > 0x7fffffffLL) return false;
     const int MB = (S + 15) / 16;
     const int SP = MB * 16;
     const size_t smem = (size_t)2 * SP * 256 + (size_t)2 * SP * (SP * 2 + 16) + 2 * SP * sizeof(float);
+    // persistent CTAs: as many as are resident (shared memory / 16 CTAs per SM), each walks over its share of the tiles
+    const long long tiles = outer * ((IC + 127) / 128);
+    const int per_sm = (int)std::min<size_t>(16, (227 * 1024) / (smem + 1024));
+    dim3 grid((unsigned)std::min<long long>(tiles, (long long)num_sms * per_sm));
     prop_set_attrs();
     switch (MB) {
-        case 1: propagator_mma_kernel<1><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
-        case 2: propagator_mma_kernel<2><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
-        case 3: propagator_mma_kernel<3><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
-        default: propagator_mma_kernel<4><<<grid, 128, smem, st>>>(xin, x, S, IC, W1, b1, W2, b2); break;
+        case 1: propagator_mma_kernel<1><<<grid, 128, smem, st>>>(xin, x, S, IC, outer, W1, b1, W2, b2); break;
+        case 2: propagator_mma_kernel<2><<<grid, 128, smem, st>>>(xin, x, S, IC, outer, W1, b1, W2, b2); break;
+        case 3: propagator_mma_kernel<3><<<grid, 128, smem, st>>>(xin, x, S, IC, outer, W1, b1, W2, b2); break;
+        default: propagator_mma_kernel<4><<<grid, 128, smem, st>>>(xin, x, S, IC, outer, W1, b1, W2, b2); break;
     }
     *err = cudaGetLastError();
     return true;

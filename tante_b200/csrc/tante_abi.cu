@@ -32,6 +32,7 @@
 #include "block_tail2_tc.cuh"
 #include "wide_patch.cuh"
 #include "fno.cuh"
+#include "optimizer.cuh"
 
 using namespace tante;
 
@@ -194,6 +195,11 @@ struct tante_handle_s {
     std::vector<std::unique_ptr<Tape>> tapes;
     int bw_batch = 0;
     DevBuf dxs, dxb, g1, g2, gq, ga1, cols, hz, hG, hz1, hd, hi1, hi2, dfilm, dcond;
+    // ---- optimizer tail (optimizer.cuh) ----
+    DevBuf opt_segs, opt_norm;                 // parameter segments of the flat gradient; f64 sum of squares
+    std::vector<char> opt_seg_cache;
+    void* nccl_comm = nullptr;                 // tante_comm_init
+    int nccl_nranks = 1;
 };
 
 namespace {
@@ -613,7 +619,7 @@ void launch_propagator(tante_handle_s* h, const float* xin, float* x, int B, int
     if (h->cfg.precision == TANTE_PREC_BF16 && S > 8) {
         cudaError_t e = cudaSuccess;
         if (launch_propagator_mma(xin, x, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]), AF(h, op.prop[axis][2]),
-                                  AF(h, op.prop[axis][3]), st, &e)) {
+                                  AF(h, op.prop[axis][3]), st, &e, h->num_sms)) {
             CK(e);
             h->launches++;
             return;
@@ -1635,7 +1641,8 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
                 CK(cudaGetLastError());
                 h->launches++;
             }
-            film_bwd_kernel<<<B, 256, 3 * C * sizeof(float), st>>>(
+            CK(cudaMemsetAsync(h->dcond.p, 0, (size_t)B * 4, st));
+            film_bwd_kernel<<<dim3(B, 16), 256, 3 * C * sizeof(float), st>>>(
                 FP(ot.rt), FP(h->dfilm), AF(h, op.mod[0]), AF(h, op.mod[1]), AF(h, op.mod[2]), AF(h, op.mod[4]),
                 AF(h, op.mod[5]), AF(h, op.mod[6]), GA(h, op.mod[0]), GA(h, op.mod[1]), GA(h, op.mod[2]), GA(h, op.mod[3]),
                 GA(h, op.mod[4]), GA(h, op.mod[5]), GA(h, op.mod[6]), GA(h, op.mod[7]), C, FP(h->dcond));
@@ -1692,11 +1699,11 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     }
     // ---- embeddings + t_encode FiLM (tante.py:136-141) ----
     CK(cudaMemsetAsync(h->dfilm.p, 0, (size_t)T * 2 * C * 4, st));
-    embed_bwd_kernel<TA><<<L, 256, 0, st>>>(dxs, FP(tp.v), AF(h, h->film_t_off), g2, FP(h->dfilm), GA(h, h->s_emb),
+    embed_bwd_kernel<TA><<<(L + (256 / (C / 4)) - 1) / (256 / (C / 4)), 256, 0, st>>>(dxs, FP(tp.v), AF(h, h->film_t_off), g2, FP(h->dfilm), GA(h, h->s_emb),
                                           GA(h, h->t_emb), B, T, L, C);
     CK(cudaGetLastError());
     h->launches++;
-    film_bwd_kernel<<<T, 256, 3 * C * sizeof(float), st>>>(
+    film_bwd_kernel<<<dim3(T, 16), 256, 3 * C * sizeof(float), st>>>(
         AF(h, h->tseq_off), FP(h->dfilm), AF(h, h->tenc[0]), AF(h, h->tenc[1]), AF(h, h->tenc[2]), AF(h, h->tenc[4]),
         AF(h, h->tenc[5]), AF(h, h->tenc[6]), GA(h, h->tenc[0]), GA(h, h->tenc[1]), GA(h, h->tenc[2]), GA(h, h->tenc[3]),
         GA(h, h->tenc[4]), GA(h, h->tenc[5]), GA(h, h->tenc[6]), GA(h, h->tenc[7]), C, nullptr);
@@ -1876,8 +1883,9 @@ int tante_destroy(tante_handle_t h) {
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
-                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond};
+                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->opt_segs, &h->opt_norm};
         for (DevBuf* b : tb) b->free();
+        if (h->nccl_comm && nccl_api().ok()) nccl_api().CommDestroy(h->nccl_comm);
         for (auto& tp : h->tapes) free_tape(*tp);
         if (h->h_flag) cudaFreeHost(h->h_flag);
         for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -2423,6 +2431,94 @@ int tante_test_block_tail(const void* att, const void* Wo, const void* W1, const
         a.hact = reinterpret_cast<__nv_bfloat16*>(hact);
         for (int i = 0; i < std::max(1, iters); ++i) CK(launch_block_tail_any(a, M, x_mid != nullptr, sms, st));
     });
+}
+
+int tante_comm_unique_id(void* id128) {
+    return guarded([&] {
+        REQUIRE(id128, "null argument");
+        NcclApi& n = nccl_api();
+        if (!n.ok()) throw Error(TANTE_ERR_STATE, "NCCL (libnccl.so.2) is not loadable in this process");
+        NcclId id;
+        const int r = n.GetUniqueId(&id);
+        if (r != 0) throw Error(TANTE_ERR_CUDA, std::string("ncclGetUniqueId: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+        memcpy(id128, id.b, sizeof(id.b));
+    });
+}
+
+int tante_comm_init(tante_handle_t h, const void* id128, int32_t nranks, int32_t rank) {
+    return guarded([&] {
+        REQUIRE(h && id128, "null argument");
+        REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / world size");
+        NcclApi& n = nccl_api();
+        if (!n.ok()) throw Error(TANTE_ERR_STATE, "NCCL (libnccl.so.2) is not loadable in this process");
+        CK(cudaSetDevice(h->device));
+        if (h->nccl_comm) { n.CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+        NcclId id;
+        memcpy(id.b, id128, sizeof(id.b));
+        const int r = n.CommInitRank(&h->nccl_comm, nranks, id, rank);
+        if (r != 0) throw Error(TANTE_ERR_CUDA, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+        h->nccl_nranks = nranks;
+    });
+}
+
+int tante_allreduce_grads(tante_handle_t h, float* grad, void* comm, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && grad, "null argument");
+        void* c = comm ? comm : h->nccl_comm;
+        if (!c) throw Error(TANTE_ERR_STATE, "no communicator: call tante_comm_init first (or pass an ncclComm_t)");
+        NcclApi& n = nccl_api();
+        if (!n.ok()) throw Error(TANTE_ERR_STATE, "NCCL (libnccl.so.2) is not loadable in this process");
+        CK(cudaSetDevice(h->device));
+        const int r = n.AllReduce(grad, grad, (size_t)h->flat_elems, /* ncclFloat32 */ 7, /* ncclSum */ 0, c,
+                                  reinterpret_cast<cudaStream_t>(stream));
+        if (r != 0) throw Error(TANTE_ERR_CUDA, std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+    });
+}
+
+int tante_optimizer_step(tante_handle_t h, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int64_t step, int32_t clip_mode, float clip, float grad_scale,
+                         double* grad_sumsq, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && grad && exp_avg && exp_avg_sq, "null argument");
+        REQUIRE(step >= 1, "step counts from 1");
+        REQUIRE(clip_mode >= 0 && clip_mode <= 2, "clip_mode: 0 none, 1 norm, 2 value");
+        REQUIRE(h->params.size() <= (size_t)kOptMaxSegs, "too many parameters");
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        std::vector<OptSeg> segs;
+        for (const Param& p : h->params) {
+            if (!p.data) throw Error(TANTE_ERR_STATE, "parameter not bound: " + p.name);
+            segs.push_back(OptSeg{(long long)p.flat_off, (long long)p.numel, const_cast<float*>(p.data)});
+        }
+        std::sort(segs.begin(), segs.end(), [](const OptSeg& a, const OptSeg& b) { return a.off < b.off; });
+        dev_alloc(h, h->opt_segs, segs.size() * sizeof(OptSeg));
+        dev_alloc(h, h->opt_norm, sizeof(double));
+        const size_t nb = segs.size() * sizeof(OptSeg);
+        if (h->opt_seg_cache.size() != nb || memcmp(h->opt_seg_cache.data(), segs.data(), nb) != 0) {
+            CK(cudaMemcpyAsync(h->opt_segs.p, segs.data(), nb, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            h->opt_seg_cache.assign(reinterpret_cast<const char*>(segs.data()), reinterpret_cast<const char*>(segs.data()) + nb);
+        }
+        double* norm = grad_sumsq ? grad_sumsq : reinterpret_cast<double*>(h->opt_norm.p);
+        const long long n = h->flat_elems;
+        const unsigned grid = (unsigned)std::min<long long>((n + 255) / 256, 8LL * h->num_sms);
+        if (clip_mode == 1 || grad_sumsq) {
+            CK(cudaMemsetAsync(norm, 0, sizeof(double), st));
+            grad_sumsq_kernel<<<grid, 256, 0, st>>>(grad, n, grad_scale, norm);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+        AdamWArgs a;
+        a.gscale = grad_scale; a.clip_mode = clip_mode; a.clip = clip;
+        a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+        a.bc1 = (float)(1.0 - std::pow((double)beta1, (double)step));
+        a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step));
+        adamw_flat_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const OptSeg*>(h->opt_segs.p), (int)segs.size(), grad, exp_avg,
+                                                exp_avg_sq, n, norm, a);
+        CK(cudaGetLastError());
+        h->launches++;
+    });
+    // the packed weights follow the masters: the caller runs tante_pack_params next (the host mirror does)
 }
 
 int tante_metric_moments(const float* x, const float* y, int64_t BT, int64_t HW, int32_t C, double* out, void* stream) {

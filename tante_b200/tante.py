@@ -218,16 +218,24 @@ class _Engine:
         except Exception:
             pass
 
-    def sync_params(self, model: "TANTE", stream: int):
-        """(Re)bind + repack when any parameter storage or version changed (optimizer step,
-        load_state_dict, .to())."""
+    def _signature(self, model: "TANTE"):
         params = dict(model.named_parameters())
         def version(p):
             try:
                 return p._version
             except RuntimeError:      # inference tensors carry no version counter (immutable outside inference mode)
                 return -1
-        sig = tuple((n, params[n].data_ptr(), version(params[n])) for n in self.names)
+        return tuple((n, params[n].data_ptr(), version(params[n])) for n in self.names)
+
+    def mark_synced(self, model: "TANTE"):
+        """The packed weights were refreshed by the library itself (tante_optimizer_step + tante_pack_params)."""
+        self.bound_sig = self._signature(model)
+
+    def sync_params(self, model: "TANTE", stream: int):
+        """(Re)bind + repack when any parameter storage or version changed (optimizer step,
+        load_state_dict, .to())."""
+        params = dict(model.named_parameters())
+        sig = self._signature(model)
         if sig == self.bound_sig:
             return
         for n in self.names:
@@ -351,6 +359,16 @@ class _TanteStep(torch.autograd.Function):
         return (None, g_in, None, None, *grads)
 
 
+import weakref
+
+_LIVE_MODELS: "weakref.WeakSet" = weakref.WeakSet()
+
+
+def live_models():
+    """The TANTE modules alive in this process (FusedAdamW finds the module its parameters belong to)."""
+    return list(_LIVE_MODELS)
+
+
 class TANTE(nn.Module):
     """B200-native TANTE.  Constructor mirrors reference models/tante.py:38-60."""
 
@@ -456,6 +474,7 @@ class TANTE(nn.Module):
             self.interprators = nn.ModuleList([_Interprator(self.C) for _ in range(taylor_order)])
             self.modifiers = nn.ModuleList([_Film(self.C) for _ in range(taylor_order)])
         self._engines: Dict[Tuple[int, str], _Engine] = {}
+        _LIVE_MODELS.add(self)
 
     def __getstate__(self):
         st = self.__dict__.copy()

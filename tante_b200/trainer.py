@@ -156,6 +156,42 @@ class GradBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.mul_(1.0 / dist.get_world_size())
 
+    # ---- native data-parallel exchange (tante_allreduce_grads: SURVEY.md 8(b) / 8(e)) ----------------------------------
+    def init_native_comm(self, model) -> bool:
+        """One NCCL communicator inside the library (tante_comm_init), its id broadcast through torch.distributed.
+        Returns False (and changes nothing) outside a multi-rank CUDA job or when TANTE_NATIVE_ALLREDUCE=0."""
+        import os
+        self._native = None
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and self.flat.is_cuda):
+            return False
+        if os.environ.get("TANTE_NATIVE_ALLREDUCE", "1") == "0" or not hasattr(model, "grad_layout"):
+            return False
+        import ctypes
+        from . import _abi
+        eng = model._engine(self.flat.device)
+        buf = ctypes.create_string_buffer(128)
+        if dist.get_rank() == 0:
+            _abi.check(eng.lib.tante_comm_unique_id(buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        _abi.check(eng.lib.tante_comm_init(eng.handle, box[0], dist.get_world_size(), dist.get_rank()))
+        self._native = eng
+        return True
+
+    def all_reduce_sum(self) -> int:
+        """SUM all-reduce of the flat bucket on the current stream; returns the world size (the 1 / world scaling is folded
+        into the optimizer step).  Uses the library's communicator when init_native_comm succeeded."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return 1
+        eng = getattr(self, "_native", None)
+        if eng is not None:
+            from . import _abi
+            stream = torch.cuda.current_stream(self.flat.device).cuda_stream
+            _abi.check(eng.lib.tante_allreduce_grads(eng.handle, self.flat.data_ptr(), None, stream))
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        return dist.get_world_size()
+
 
 def train_step(model, optimizer, x, y_ref, n_steps: int = 4, bucket: Optional[GradBucket] = None,
                clip: str = "norm", rt_eps: float = 0.5, rt_n: int = 2):
@@ -172,6 +208,12 @@ def train_step(model, optimizer, x, y_ref, n_steps: int = 4, bucket: Optional[Gr
     else:
         optimizer.zero_grad(set_to_none=True)
     loss.backward()
+    from .optim import FusedAdamW
+    if isinstance(optimizer, FusedAdamW) and bucket is not None:
+        # all-reduce (sum) + mean + clip + AdamW + repack: the NCCL kernel and three launches of the library
+        world = bucket.all_reduce_sum()
+        optimizer.step(clip=clip, clip_value=1.0, grad_scale=1.0 / world)
+        return loss.detach()
     if bucket is not None:
         bucket.all_reduce_mean()          # before clipping: clipping must see the averaged gradient
     params = bucket.params if bucket is not None else list(model.parameters())

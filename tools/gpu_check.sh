@@ -2,7 +2,7 @@
 # full GPU test suite + the two bench lines (no extras) -> gpurun_out/${TAG}_*
 mkdir -p gpurun_out
 TAG=${1:-chk}
-( time timeout 1500 python -m pytest tests -m gpu -q -x ) > gpurun_out/${TAG}_pytest.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --no-extras --no-eager --no-cpu-baseline > gpurun_out/${TAG}_train.json 2> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --workload rollout --no-eager --no-cpu-baseline > gpurun_out/${TAG}_rollout.json 2>> gpurun_out/${TAG}_bench.err

@@ -144,14 +144,15 @@ taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) 
         const int wpc = (int)(tile % tpr);
         const int b = (int)(bh / g.Hp), hpp = (int)(bh % g.Hp);
         const int xvalid = min(NT, g.Wp - wpc * NT) * P;             // pixel columns of this tile that exist
-        const int n = hp.n_arr[b];
-        const int fc = hp.fcount ? hp.fcount[b] : g.T;
+        const int bt = hp.act ? hp.act[b] : b;                       // trajectory of ring / counters / history (compaction)
+        const int n = hp.n_arr[bt];
+        const int fc = hp.fcount ? hp.fcount[bt] : g.T;
         const size_t pix0 = (size_t)hpp * P * g.W + (size_t)wpc * XW;
         // u0 of this thread's items: in flight during phase 1  (requesting them one tile ahead was measured SLOWER on B200:
         // K = 1, n = 1 on the TRL shape 45.7 -> 63 us -- the extra per-tile index chain costs more than the latency it hides)
         float4 u0r[NJ];
         {
-            const float* u0p = hp.u_ring + (size_t)(b * g.T + (fc + g.T - 1) % g.T) * g.D * HW + pix0;
+            const float* u0p = hp.u_ring + (size_t)(bt * g.T + (fc + g.T - 1) % g.T) * g.D * HW + pix0;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 u0r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -210,7 +211,7 @@ taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) 
         if (n <= 0 && !hp.deriv_dbg) continue;
 
         // ---- phase 2: channels-first emit ----
-        const int cum = hp.cum ? hp.cum[b] : 0;
+        const int cum = hp.cum ? hp.cum[bt] : 0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int item = tid + THREADS * j;
@@ -242,7 +243,7 @@ taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) 
                 if (hp.frames) *reinterpret_cast<float4*>(hp.frames + ((size_t)b * hp.n_cap + (i - 1)) * g.D * HW + goff) = v;
                 if (y_out && i > n - g.T) {
                     const int slot = (fc + i - 1) % g.T;
-                    *reinterpret_cast<float4*>(hp.ring_out + (size_t)(b * g.T + slot) * g.D * HW + goff) = v;
+                    *reinterpret_cast<float4*>(hp.ring_out + (size_t)(bt * g.T + slot) * g.D * HW + goff) = v;
                 }
             }
         }
@@ -262,7 +263,7 @@ taylor_head_mma_kernel(HeadParams hp, PatchGeom g, long long rows_total, int B) 
                 const int fidx = cum + i - 1;
                 if (fidx >= hp.n_roll) break;
                 const float dt = (float)i * hp.fi;
-                float* yp = y_out + (((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D;
+                float* yp = y_out + (((size_t)bt * hp.n_roll + fidx) * HW + pix) * g.D;
                 if (vec4) {
                     float o[4];
 #pragma unroll

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) embed_cached_kernel(const float* __restri
                                                            const int* __restrict__ enc_map, const int* __restrict__ fcount,
                                                            const float* __restrict__ film, const float* __restrict__ s_emb,
                                                            const float* __restrict__ t_emb, float* __restrict__ x, int B, int T,
-                                                           int L, int C) {
+                                                           int L, int C, const int* __restrict__ act = nullptr) {
     // 32-bit index arithmetic (B*T*L*C/4 < 2^31 is checked by the launcher): the 64-bit div/mod chain cost more than the copy
     const unsigned c4n = (unsigned)C / 4;
     const unsigned total = (unsigned)B * T * L * c4n;
@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(256) embed_cached_kernel(const float* __restri
         unsigned tok = i / c4n;
         const int l = (int)(tok % (unsigned)L); tok /= (unsigned)L;
         const int t = (int)(tok % (unsigned)T);
-        const int b = (int)(tok / (unsigned)T);
+        const int bc = (int)(tok / (unsigned)T);            // compact index of the latent
+        const int b = act ? act[bc] : bc;                   // trajectory (ring slot, cache)
         const int slot = (fcount[b] + t) % T;
         const int e = enc_map[b * T + slot];
         float* cp = cache + ((size_t)(b * T + slot) * L + l) * C + c;
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(256) embed_cached_kernel(const float* __restri
         float4 o;
         o.x = embed_value(v.x, sc.x, sh.x, se.x, te.x); o.y = embed_value(v.y, sc.y, sh.y, se.y, te.y);
         o.z = embed_value(v.z, sc.z, sh.z, se.z, te.z); o.w = embed_value(v.w, sc.w, sh.w, se.w, te.w);
-        *reinterpret_cast<float4*>(x + ((size_t)(b * T + t) * L + l) * C + c) = o;
+        *reinterpret_cast<float4*>(x + ((size_t)(bc * T + t) * L + l) * C + c) = o;
     }
 }
 
@@ -513,6 +514,16 @@ struct RolloutState {
     const RolloutPtrs* ptrs;
     int n_roll;
     int max_steps;
+    // Compaction (per-sample rollouts): act[0 .. n_active) = trajectories still running, in a stable order, followed by the
+    // finished ones.  A model call works on the FIRST `B` entries of act (its "bucket": the smallest captured batch size
+    // that holds every running trajectory): compact index i of the latent = trajectory act[i] of the ring / caches / outputs.
+    // act == nullptr: identity (no compaction).
+    int* act;       // [B_full]
+    int* n_active;  // [1]
+    int B_full;     // trajectories of the rollout (= stride of rts_out / ns_out)
+    int n_buckets;  // captured batch sizes, descending (bucket_sz[0] = B_full); 0 = no SWITCH node
+    int bucket_sz[4];
+    cudaGraphConditionalHandle sw;
 };
 
 __global__ void set_rollout_ptrs_kernel(RolloutPtrs* dst, float* y, float* rts, int* ns) {
@@ -522,8 +533,10 @@ __global__ void set_rollout_ptrs_kernel(RolloutPtrs* dst, float* y, float* rts, 
 __global__ void select_step_kernel(const float* __restrict__ rt /* [K][Bstride] */, int K, int Bstride, int B,
                                    int deg, int output_length, int per_sample, int n_cap,
                                    float* __restrict__ R_t, int* __restrict__ n_out, RolloutState rs, int rollout) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;      // compact index (rt / R_t / n_out are compact)
     if (b >= B) return;
+    const int bt = (rollout && rs.act) ? rs.act[b] : b;       // trajectory
+    const int Bs = (rollout && rs.B_full > 0) ? rs.B_full : B;
     int n;
     float Rb = 0.f;
     if (deg) {
@@ -542,36 +555,41 @@ __global__ void select_step_kernel(const float* __restrict__ rt /* [K][Bstride] 
     }
     n = max(1, min(n, n_cap));
     if (rollout) {
-        const bool active = rs.cum[b] < rs.n_roll;
+        const bool active = rs.cum[bt] < rs.n_roll;
         if (!active) n = 0;
         else {
-            const int s = rs.steps[b];
+            const int s = rs.steps[bt];
             if (s < rs.max_steps) {
-                rs.ptrs->ns_out[(size_t)s * B + b] = n;
-                if (!deg) rs.ptrs->rts_out[(size_t)s * B + b] = Rb;
+                rs.ptrs->ns_out[(size_t)s * Bs + bt] = n;
+                if (!deg) rs.ptrs->rts_out[(size_t)s * Bs + bt] = Rb;
             }
         }
-        rs.n_cur[b] = n;
+        rs.n_cur[bt] = n;
     }
     if (n_out) n_out[b] = n;
 }
 
 __global__ void advance_state_kernel(RolloutState rs, int B, cudaGraphConditionalHandle cond, int use_cond) {
-    // single CTA; after the head kernel of a step.  When the step runs as the body of a CUDA-graph WHILE
-    // node, the loop condition (any trajectory still short of n_roll frames) is set here, on the device.
+    // single CTA; after the head kernel of a step over the bucket act[0 .. B).  When the step runs as the body of a
+    // CUDA-graph WHILE node, the loop condition (any trajectory still short of n_roll frames) is set here, on the device,
+    // and so is the bucket (SWITCH node) of the next model call.
     __shared__ int rem, cnt;
     if (threadIdx.x == 0) { rem = 0; cnt = 0; }
+    const int Bf = rs.B_full > 0 ? rs.B_full : B;
     if (rs.enc_count)
-        for (int i = threadIdx.x; i < B * rs.T; i += blockDim.x) rs.enc_map[i] = -1;
+        for (int i = threadIdx.x; i < Bf * rs.T; i += blockDim.x) rs.enc_map[i] = -1;
     __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const int b = rs.act ? rs.act[i] : i;
         const int n = rs.n_cur[b];
         if (n > 0) {
             rs.cum[b] += n;
             const int fc = rs.fcount[b] + n;
             rs.fcount[b] = fc;
             rs.steps[b] += 1;
-            if (rs.enc_count) {      // the min(n, T) newest frames of the window sit in slots (fc - 1 - j) % T
+            // (a trajectory that just finished is never encoded again: its frames stay off the list, which therefore
+            //  never outgrows the next call's bucket)
+            if (rs.enc_count && rs.cum[b] < rs.n_roll) {      // the min(n, T) newest frames of the window sit in slots (fc - 1 - j) % T
                 const int m = min(n, rs.T);
                 const int e0 = atomicAdd(&cnt, m);
                 for (int j = 0; j < m; ++j) {
@@ -590,6 +608,25 @@ __global__ void advance_state_kernel(RolloutState rs, int B, cudaGraphConditiona
         const int it = *rs.iter + 1;
         *rs.iter = it;
         if (use_cond) cudaGraphSetConditional(cond, (rem > 0 && it < rs.max_steps) ? 1u : 0u);
+        if (rs.act) {
+            // stable partition of the bucket: running trajectories first (B is small: one thread, in place through a
+            // bounded scratch walk -- finished ones are appended behind in their old order)
+            int w = 0;
+            for (int i = 0; i < B; ++i) {
+                const int b = rs.act[i];
+                if (rs.cum[b] < rs.n_roll) {
+                    // rotate b down to position w, shifting the finished ones in [w, i) up by one
+                    for (int j = i; j > w; --j) rs.act[j] = rs.act[j - 1];
+                    rs.act[w++] = b;
+                }
+            }
+            *rs.n_active = w;
+            if (rs.n_buckets > 1 && use_cond) {
+                int k = 0;
+                while (k + 1 < rs.n_buckets && rs.bucket_sz[k + 1] >= w) ++k;
+                cudaGraphSetConditional(rs.sw, (unsigned)k);
+            }
+        }
     }
 }
 
@@ -597,10 +634,11 @@ __global__ void init_state_kernel(RolloutState rs, int B, int T) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
         rs.cum[b] = 0; rs.fcount[b] = T; rs.steps[b] = 0; rs.n_cur[b] = 0;
+        if (rs.act) rs.act[b] = b;
         if (rs.enc_count)
             for (int t = 0; t < T; ++t) { rs.enc_list[b * T + t] = b * T + t; rs.enc_map[b * T + t] = b * T + t; }
     }
-    if (b == 0) { *rs.remaining = B; *rs.iter = 0; if (rs.enc_count) *rs.enc_count = B * T; }
+    if (b == 0) { *rs.remaining = B; *rs.iter = 0; if (rs.enc_count) *rs.enc_count = B * T; if (rs.act) *rs.n_active = B; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -629,6 +667,8 @@ struct HeadParams {
     const RolloutPtrs* ptrs; float* ring_out; const int* cum; int n_roll;
     // optional: decoded derivative fields for debugging/tests [K][B][D][H][W]
     float* deriv_dbg;
+    // rollout compaction: sample index of the stage-1 rows (compact) -> trajectory of ring / counters / history (null: identity)
+    const int* act;
 };
 
 // Exact-mode (FFMA) variant: one thread per stage-1 row; the thread streams its own C1-long row(s)
@@ -658,13 +698,14 @@ __global__ void __launch_bounds__(128) taylor_head_kernel(HeadParams hp, PatchGe
     int h1, w1;
     stage1_row_to_hw(g, hpp, wp, r, h1, w1);
 
-    const int n = hp.n_arr[b];
+    const int bt = hp.act ? hp.act[b] : b;
+    const int n = hp.n_arr[bt];
     if (n <= 0 && !hp.deriv_dbg) return;
     const size_t HW = (size_t)g.H * g.W;
-    const int fc = hp.fcount ? hp.fcount[b] : g.T;
+    const int fc = hp.fcount ? hp.fcount[bt] : g.T;
     const int u_slot = (fc + g.T - 1) % g.T;
-    const float* u0p = hp.u_ring + ((size_t)(b * g.T + u_slot) * g.D) * HW;
-    const int cum = hp.cum ? hp.cum[b] : 0;
+    const float* u0p = hp.u_ring + ((size_t)(bt * g.T + u_slot) * g.D) * HW;
+    const int cum = hp.cum ? hp.cum[bt] : 0;
     float* y_out = hp.ptrs ? hp.ptrs->y_out : nullptr;
 
     for (int o0 = 0; o0 < NO; o0 += MAXO) {
@@ -709,10 +750,10 @@ __global__ void __launch_bounds__(128) taylor_head_kernel(HeadParams hp, PatchGe
                 if (hp.frames) hp.frames[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix] = val;
                 if (y_out) {
                     const int fidx = cum + i - 1;
-                    if (fidx < hp.n_roll) y_out[(((size_t)b * hp.n_roll + fidx) * HW + pix) * g.D + d] = val;
+                    if (fidx < hp.n_roll) y_out[(((size_t)bt * hp.n_roll + fidx) * HW + pix) * g.D + d] = val;
                     if (i > n - g.T) {
                         const int slot = (fc + i - 1) % g.T;
-                        hp.ring_out[((size_t)(b * g.T + slot) * g.D + d) * HW + pix] = val;
+                        hp.ring_out[((size_t)(bt * g.T + slot) * g.D + d) * HW + pix] = val;
                     }
                 }
             }

@@ -155,6 +155,7 @@ struct tante_handle_s {
     DevBuf wbuf, dfield;                // wide: patch / sub-pixel matrix scratch; decoded derivative fields [K][B][D][H][W]
     float drop_p = 0.f;                 // tante_set_dropout: applies to the NEXT tante_train_forward calls
     unsigned long long drop_seed = 0;
+    bool no_switch = false;             // SWITCH conditional nodes unavailable on this driver: rollouts run without compaction
     bool fuse_tail = true;              // tensor mode: out-proj + LN2 + MLP + LN1' of a block as ONE kernel (TANTE_FUSE_TAIL=0: three GEMMs)
 
     // workspace
@@ -175,6 +176,7 @@ struct tante_handle_s {
     int rollout_mode = 2;       // 0 = eager launches, 1 = one graph per step + host loop, 2 = device WHILE graph
     cudaGraphConditionalHandle cond_handle = 0;
     int use_cond = 0;
+    cudaGraphConditionalHandle sw_handle = 0;   // SWITCH node of the compaction buckets
     int last_graph_steps = 0;
     // live GEMM timing (tante_profile)
     bool prof_on = false;
@@ -476,6 +478,8 @@ RolloutState make_state(tante_handle_s* h, int B, int n_roll) {
     rs.ptrs = reinterpret_cast<const RolloutPtrs*>(s + 4 * mb + 8);   // 32-byte aligned slot after the counters
     rs.n_roll = n_roll; rs.max_steps = n_roll;
     rs.T = h->T;
+    rs.act = nullptr; rs.n_active = s + 4 * mb + 2; rs.B_full = B; rs.n_buckets = 0; rs.sw = 0;
+    for (int& v : rs.bucket_sz) v = 0;
     rs.enc_count = nullptr; rs.enc_list = nullptr; rs.enc_map = nullptr;
     if (h->enc_cache.p && h->use_enc_cache) {
         int* e = reinterpret_cast<int*>(h->enc_state.p);
@@ -656,6 +660,7 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
     hp.frames = io.frames; hp.n_cap = io.n_cap;
     hp.ptrs = io.rollout ? rs.ptrs : nullptr; hp.ring_out = io.ring_out; hp.cum = io.rollout ? rs.cum : nullptr; hp.n_roll = io.n_roll;
     hp.deriv_dbg = deriv_dbg;
+    hp.act = io.rollout ? rs.act : nullptr;
     const long long rows = (long long)B * h->L * h->geom.R1;
     if (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
@@ -1005,7 +1010,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             REQUIRE(tot4 < (1LL << 31), "latent too large for the 32-bit indexing of the cached embed pass");
             embed_cached_kernel<<<(unsigned)std::min<long long>((tot4 + 255) / 256, 32LL * h->num_sms), 256, 0, st>>>(
                 cnew, reinterpret_cast<float*>(h->enc_cache.p), rs.enc_map, io.fcount, AF(h, h->film_t_off), AF(h, h->s_emb),
-                AF(h, h->t_emb), x, B, T, L, C);
+                AF(h, h->t_emb), x, B, T, L, C, rs.act);
             CK(cudaGetLastError());
             h->launches++;
         } else {
@@ -1804,12 +1809,57 @@ void destroy_graphs(tante_handle_s* h) {
     h->graphs.clear();
 }
 
+// Compaction buckets of a per-sample rollout (TANTE_ROLLOUT_COMPACT=0 disables): the step body is captured once per batch
+// size B, 3B/4, B/2, B/4 and a SWITCH node inside the WHILE body runs the smallest one that holds every running trajectory.
+// Needs the encoder cache (its frame lists already speak trajectory ids) and the patch-GEMM encoder.
+static bool compaction_wanted(const tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs) {
+    static const bool on = !(getenv("TANTE_ROLLOUT_COMPACT") && atoi(getenv("TANTE_ROLLOUT_COMPACT")) == 0);
+    return on && io.per_sample && B >= 8 && rs.enc_count && !h->wide && !h->fno && !h->cfg.deg;
+}
+
 template <typename TA>
 void build_roll_graph(tante_handle_s* h, tante_handle_s::RollGraph& rg, const StepIO& io, int B,
-                             const RolloutState& rs, bool while_node) {
+                             const RolloutState& rs_in, bool while_node) {
     if (!h->cap_stream) CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     const int64_t launches0 = h->launches;
-    if (while_node) {
+    RolloutState rs = rs_in;
+    if (while_node && rs.act && rs.n_buckets > 1) {
+        // WHILE { SWITCH(bucket) { step(B_0) | step(B_1) | ... } }
+        CK(cudaGraphCreate(&rg.graph, 0));
+        CK(cudaGraphConditionalHandleCreate(&h->cond_handle, rg.graph, 1, cudaGraphCondAssignDefault));
+        CK(cudaGraphConditionalHandleCreate(&h->sw_handle, rg.graph, 0, cudaGraphCondAssignDefault));
+        rs.sw = h->sw_handle;
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        np.conditional.handle = h->cond_handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        CK(cudaGraphAddNode(&node, rg.graph, nullptr, 0, &np));
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        cudaGraphNodeParams sp = {cudaGraphNodeTypeConditional};
+        sp.conditional.handle = h->sw_handle;
+        sp.conditional.type = cudaGraphCondTypeSwitch;
+        sp.conditional.size = (unsigned)rs.n_buckets;
+        cudaGraphNode_t snode;
+        CK(cudaGraphAddNode(&snode, body, nullptr, 0, &sp));
+        h->use_cond = 1;
+        for (int k = 0; k < rs.n_buckets; ++k) {
+            CK(cudaStreamBeginCaptureToGraph(h->cap_stream, sp.conditional.phGraph_out[k], nullptr, nullptr, 0,
+                                             cudaStreamCaptureModeThreadLocal));
+            const int64_t l0 = h->launches;
+            try {
+                run_step<TA>(h, io, rs.bucket_sz[k], rs, h->cap_stream);
+            } catch (...) {
+                cudaGraph_t dummy = nullptr;
+                cudaStreamEndCapture(h->cap_stream, &dummy);
+                h->use_cond = 0;
+                throw;
+            }
+            CK(cudaStreamEndCapture(h->cap_stream, nullptr));
+            if (k > 0) h->launches = l0;      // the per-step launch count is that of the full bucket
+        }
+        h->use_cond = 0;
+    } else if (while_node) {
         CK(cudaGraphCreate(&rg.graph, 0));
         CK(cudaGraphConditionalHandleCreate(&h->cond_handle, rg.graph, 1, cudaGraphCondAssignDefault));
         cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
@@ -2027,7 +2077,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         dev_alloc(h, h->nbuf, (size_t)max_batch * 4);
         dev_alloc(h, h->filmbuf, (size_t)max_batch * 2 * C * 4);
         dev_alloc(h, h->ring, (size_t)max_batch * h->T * h->D * h->cfg.H * h->cfg.W * 4);
-        dev_alloc(h, h->state, ((size_t)4 * max_batch + 64) * 4);
+        dev_alloc(h, h->state, ((size_t)5 * max_batch + 64) * 4);      // counters (4 per trajectory), scalars, pointer table, act list
         if (max_roll > 0 && h->use_enc_cache) {
             dev_alloc(h, h->enc_cache, tokens * C * 4);
             dev_alloc(h, h->enc_state, ((size_t)2 * max_batch * h->T + 8) * 4);
@@ -2112,6 +2162,17 @@ int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_ro
         const size_t wbytes = (size_t)B * h->T * h->D * h->cfg.H * h->cfg.W * 4;
         CK(cudaMemcpyAsync(h->ring.p, window, wbytes, cudaMemcpyDeviceToDevice, st));
         RolloutState rs = make_state(h, B, n_roll);
+        {
+            StepIO probe; probe.per_sample = per_sample;
+            const int mode0 = h->prof_on || h->debug ? 0 : h->rollout_mode;
+            if (mode0 == 2 && !h->no_switch && compaction_wanted(h, probe, B, rs)) {
+                rs.act = reinterpret_cast<int*>(h->state.p) + 4 * h->max_batch + 32;
+                const int cand[4] = {B, (3 * B + 3) / 4, (B + 1) / 2, (B + 3) / 4};
+                static const bool one_bucket = getenv("TANTE_ROLLOUT_COMPACT") && atoi(getenv("TANTE_ROLLOUT_COMPACT")) == 2;   // debug: reorder only
+                for (int c : cand)
+                    if (rs.n_buckets == 0 || (!one_bucket && c < rs.bucket_sz[rs.n_buckets - 1])) rs.bucket_sz[rs.n_buckets++] = c;
+            }
+        }
         init_state_kernel<<<(B + 127) / 128, 128, 0, st>>>(rs, B, h->T);
         CK(cudaGetLastError());
         set_rollout_ptrs_kernel<<<1, 1, 0, st>>>(const_cast<RolloutPtrs*>(rs.ptrs), y_out, rts_out, ns_out);
@@ -2132,8 +2193,19 @@ int tante_rollout(tante_handle_t h, const float* window, int32_t B, int32_t n_ro
             if (it == h->graphs.end()) {
                 tante_handle_s::RollGraph g;
                 try {
-                    if (f32) build_roll_graph<float>(h, g, io, B, rs, mode == 2);
-                    else build_roll_graph<__nv_bfloat16>(h, g, io, B, rs, mode == 2);
+                    try {
+                        if (f32) build_roll_graph<float>(h, g, io, B, rs, mode == 2);
+                        else build_roll_graph<__nv_bfloat16>(h, g, io, B, rs, mode == 2);
+                    } catch (const Error&) {
+                        if (!(mode == 2 && rs.act)) throw;
+                        // SWITCH conditional nodes unavailable: same WHILE graph without the compaction buckets
+                        (void)cudaGetLastError();
+                        if (g.graph) { cudaGraphDestroy(g.graph); g.graph = nullptr; }
+                        h->no_switch = true;
+                        rs.act = nullptr; rs.n_buckets = 0;
+                        if (f32) build_roll_graph<float>(h, g, io, B, rs, true);
+                        else build_roll_graph<__nv_bfloat16>(h, g, io, B, rs, true);
+                    }
                 } catch (const Error& e) {
                     if (mode != 2) throw;
                     // conditional nodes unavailable: fall back to per-step graphs for this handle

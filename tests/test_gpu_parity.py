@@ -371,3 +371,27 @@ def test_training_refused_for_inference_only_scopes():
         model = make_model(cfg, O.make_state_dict(cfg, 1)).train()
         with pytest.raises(Exception, match="not implemented"):
             model(O.make_input(cfg, 1, 2).cuda())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_compacted_rollout_equals_single_trajectory_runs_bitwise(precision):
+    """Per-sample rollouts drop finished trajectories from the batch on the device (bucketed step graphs behind a SWITCH
+    node, trajectories addressed through an index list): every trajectory must come out exactly as when it is rolled out
+    alone (B = 1: no compaction), whatever finished around it and whichever bucket its last calls ran in."""
+    from gpu_util import make_model
+    cfg = O.OracleConfig(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="THW-HWT", deg=False)
+    sd = O.make_state_dict(cfg, 5, rt_bias=3.0585)      # first-call R_t of the 12 trajectories: 3.98 .. 4.09, about half above 4
+    B = 12
+    x = O.make_input(cfg, B, 6)
+    scale = torch.tensor([8.0, 0.05, 3.0, 1.0, 20.0, 8.0, 0.05, 1.0, 30.0, 8.0, 1.0, 50.0])
+    x = (x * scale.view(B, 1, 1, 1, 1)).cuda()
+    model = make_model(cfg, sd, precision=precision)
+    with torch.inference_mode():
+        y, R, ns, steps = model.rollout(x, 8, per_sample=True)
+        seqs = [ns[: int(steps[b]), b].tolist() for b in range(B)]
+        assert len({int(s) for s in steps.tolist()}) > 1, "test inputs should finish after different numbers of calls"
+        for b in range(B):
+            y1, R1, ns1, steps1 = model.rollout(x[b:b + 1], 8, per_sample=True)
+            assert ns1[: int(steps1[0]), 0].tolist() == seqs[b]
+            assert torch.equal(y[b:b + 1], y1), f"trajectory {b}"
+            assert torch.equal(R[: int(steps[b]), b], R1[: int(steps1[0]), 0])

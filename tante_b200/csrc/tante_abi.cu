@@ -18,6 +18,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "attention_mma.cuh"
+#include "attention_flash.cuh"
 #include "propagator_mma.cuh"
 #include "propagator_bwd_mma.cuh"
 #include "propagator_small.cuh"
@@ -581,6 +582,16 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
     else if (axis == 'L') { S = L; inner = 1; nseq = B * T; }               // (b t) (h w)
     else if (axis == 'Y') { S = T * Hp; inner = Wp; nseq = B * Wp; }        // (b w) (t h)
     else { S = T * L; inner = 1; nseq = B; }                                // 'A': b (t h w)
+    if (sizeof(TA) == 2 && drop.p <= 0.f) {
+        // long sequences (composite axes, 65 .. 96-token axes): tiled online-softmax kernel
+        cudaError_t e = cudaSuccess;
+        if (launch_attention_flash(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
+                                   inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
     if (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
         if (launch_attention_mma(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,

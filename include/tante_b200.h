@@ -150,6 +150,21 @@ TANTE_API int tante_train_forward(tante_handle_t h, int32_t slot, const float* i
 TANTE_API int tante_backward(tante_handle_t h, int32_t slot, const float* input, const float* grad_frames,
                    int32_t n_frames, const float* grad_Rt, float* grad_input, float* grad_params, void* stream);
 
+/* Frame-table variants of the two calls above for the chained BPTT rollout of the training drivers (trainer/trainer.py:144-159,
+ * trainer/r_trainer.py:122-126: window = cat(window[:, n:], y), NOT detached): the window of a call is given as in_T separate
+ * frames -- frame_ptrs[t] = device pointer of frame t of sample 0 (a contiguous (D, H, W) plane set, 16-byte aligned),
+ * sample b at + b * frame_bstride[t] elements -- so that consecutive calls slide over ONE history buffer and no window is ever
+ * concatenated; the emitted frames go to frames + b * frames_bstride (+ i * D * H * W).  tante_backward_win reads the frame
+ * gradients with batch stride gf_bstride and ACCUMULATES (+=) the window gradient into grad_frame_ptrs[t] + b * grad_bstride[t]
+ * (NULL entry: that frame needs no gradient; grad_frame_ptrs == NULL: none does), which is how BPTT sums the contributions of
+ * later calls into the gradient of an earlier prediction in place. */
+TANTE_API int tante_train_forward_win(tante_handle_t h, int32_t slot, const float* const* frame_ptrs,
+                                      const int64_t* frame_bstride, int32_t B, float out_T, int32_t n_cap, float* frames,
+                                      int64_t frames_bstride, float* R_t, int32_t* n_host, void* stream);
+TANTE_API int tante_backward_win(tante_handle_t h, int32_t slot, const float* grad_frames, int64_t gf_bstride, int32_t n_frames,
+                                 const float* grad_Rt, float* const* grad_frame_ptrs, const int64_t* grad_bstride,
+                                 float* grad_params, void* stream);
+
 /* ---- introspection for tests / profiling ------------------------------------------ */
 /* Copy an internal stage tensor of the last tante_forward into `dst` (f32, device).
  * stage: "latent_in" (after embed), "latent" (after the last backbone), "deriv<k>"

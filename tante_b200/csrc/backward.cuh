@@ -792,11 +792,19 @@ struct HeadBwdParams {
     void* G[kMaxOrder];             // [rows][kHeadPad]
     int K;
     float fi;
-    const float* gframes;           // (B, n_cap, D, H, W)
+    const float* gframes;           // frame i of sample b at gframes + b * gf_bs + i * D * H * W
+    long long gf_bs;                // (contiguous (B, n_cap, D, H, W): n_cap * D * H * W)
     int n_cap;
     const int* n_arr;               // [B]
-    float* grad_input;              // (B, T, D, H, W) or null
+    float* gi_last;                 // gradient of the LAST window frame (u0 path) of sample 0, += ; null: not needed
+    long long gi_bs;                // its batch stride in elements
 };
+
+// Window of a training call given as T separate frames (the chained BPTT rollout of the training drivers slides its window over
+// ONE history instead of torch.cat-ing a new tensor per call, trainer/trainer.py:151-157): frame t of sample b lives at
+// base + off[t] + b * bs[t] (elements, relative to the base pointer the kernel is given).  off[t] = kFrameSkip: no gradient wanted.
+constexpr long long kFrameSkip = (long long)(-0x7fffffffffffffffLL - 1);
+struct FrameTab { long long off[16]; long long bs[16]; int on; };
 
 // thread = (stage-1 row, group of 4 consecutive outputs): 16 threads per row, coalesced 128-byte row writes
 __device__ __forceinline__ void patch_pixel(const PatchGeom& g, int h1, int w1, int oo, int& d, size_t& pix) {
@@ -830,7 +838,20 @@ struct PatchTile {
     int stab[32];                             // RH[8], RW[8], OH[8], OW[8]   (see taylor_head_mma_kernel)
     long long pix0[kPatchRows];               // per token: pixel offset of its top-left corner in a plane
     long long img[kPatchRows];                // per token: image index (-1 = past the end)
+    long long base[kPatchRows];               // per token: element offset of its image (frame tables only)
 };
+// image index b * T + t -> address through a frame table (call after patch_tile_init, before a __syncthreads)
+__device__ __forceinline__ void patch_tile_frames(PatchTile& pt, const PatchGeom& g, const FrameTab& ft) {
+    if (threadIdx.x < kPatchRows / g.R1) {
+        const long long e = pt.img[threadIdx.x];
+        if (e >= 0) {
+            const long long b = e / g.T;
+            const int t = (int)(e - b * g.T);
+            if (ft.off[t] == kFrameSkip) pt.img[threadIdx.x] = -1;
+            else pt.base[threadIdx.x] = ft.off[t] + b * ft.bs[t];
+        }
+    }
+}
 __device__ __forceinline__ void patch_tile_init(PatchTile& pt, const PatchGeom& g, long long row0, long long rows_total) {
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -940,7 +961,7 @@ __global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, Patc
         for (int e = 0; e < VEC; ++e) { du[e] = 0.f; Gk[0][e] = Gk[1][e] = Gk[2][e] = Gk[3][e] = 0.f; }
         for (int i = 1; i <= n; ++i) {
             float gv[VEC];
-            VecN<VEC>::load(hp.gframes + (((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix, gv);
+            VecN<VEC>::load(hp.gframes + (size_t)b * hp.gf_bs + ((size_t)(i - 1) * g.D + d) * HW + pix, gv);
             const float dt = (float)i * hp.fi;
             float coef = 1.f;
 #pragma unroll
@@ -952,8 +973,8 @@ __global__ void __launch_bounds__(128) head_gather_kernel(HeadBwdParams hp, Patc
 #pragma unroll
             for (int e = 0; e < VEC; ++e) du[e] += gv[e];
         }
-        if (hp.grad_input && n > 0) {
-            float* gp = hp.grad_input + ((size_t)(b * g.T + g.T - 1) * g.D + d) * HW + pix;
+        if (hp.gi_last && n > 0) {
+            float* gp = hp.gi_last + (size_t)b * hp.gi_bs + (size_t)d * HW + pix;
             float cur[VEC];
             VecN<VEC>::load(gp, cur);
 #pragma unroll
@@ -982,7 +1003,7 @@ __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restri
                                                            TA* __restrict__ cols, long long rows_total,
                                                            const int* __restrict__ enc_list = nullptr,
                                                            const int* __restrict__ enc_count = nullptr,
-                                                           const int* __restrict__ fcount = nullptr) {
+                                                           const int* __restrict__ fcount = nullptr, FrameTab ft = FrameTab()) {
     __shared__ __align__(16) float S[kPatchRows * kPatchPitch];
     __shared__ PatchTile pt;
     const long long row0 = (long long)blockIdx.x * kPatchRows;
@@ -1006,6 +1027,7 @@ __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restri
         }
     }
     if (enc_list || fcount) __syncthreads();
+    if (ft.on) { patch_tile_frames(pt, g, ft); __syncthreads(); }
     const size_t HW = (size_t)g.H * g.W;
     const int nitems = (g.D * pt.P * pt.NT) << (pt.lP - (VEC == 4 ? 2 : 1));
     bool any = false;
@@ -1014,7 +1036,8 @@ __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restri
         size_t pix;
         if (!patch_item<VEC>(pt, g, item, tok, d, pix, soff)) continue;
         float v[VEC];
-        VecN<VEC>::load(x + ((size_t)pt.img[tok] * g.D + d) * HW + pix, v);
+        const long long ib = ft.on ? pt.base[tok] : pt.img[tok] * (long long)(g.D * HW);
+        VecN<VEC>::load(x + ib + (size_t)d * HW + pix, v);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) S[soff[e]] = v[e];
         any = true;
@@ -1027,11 +1050,13 @@ __global__ void __launch_bounds__(128) conv1_im2col_kernel(const float* __restri
 // grad_input[patch] += dpatch[row][kk]   (dpatch = da1 * W1, a thin GEMM; patches do not overlap)
 template <typename TA, int VEC>
 __global__ void __launch_bounds__(128) conv1_col2im_kernel(const TA* __restrict__ dpatch, PatchGeom g,
-                                                           float* __restrict__ grad_input, long long rows_total) {
+                                                           float* __restrict__ grad_input, long long rows_total,
+                                                           FrameTab ft = FrameTab()) {
     __shared__ __align__(16) float S[kPatchRows * kPatchPitch];
     __shared__ PatchTile pt;
     const long long row0 = (long long)blockIdx.x * kPatchRows;
     patch_tile_init(pt, g, row0, rows_total);
+    if (ft.on) { __syncthreads(); patch_tile_frames(pt, g, ft); }
     patch_rows_load<TA>(S, dpatch, row0, rows_total);
     __syncthreads();
     const size_t HW = (size_t)g.H * g.W;
@@ -1040,7 +1065,8 @@ __global__ void __launch_bounds__(128) conv1_col2im_kernel(const TA* __restrict_
         int tok, d, soff[VEC];
         size_t pix;
         if (!patch_item<VEC>(pt, g, item, tok, d, pix, soff)) continue;
-        float* gp = grad_input + ((size_t)pt.img[tok] * g.D + d) * HW + pix;
+        const long long ib = ft.on ? pt.base[tok] : pt.img[tok] * (long long)(g.D * HW);
+        float* gp = grad_input + ib + (size_t)d * HW + pix;
         float cur[VEC];
         VecN<VEC>::load(gp, cur);
 #pragma unroll

@@ -669,6 +669,9 @@ struct HeadParams {
     float* deriv_dbg;
     // rollout compaction: sample index of the stage-1 rows (compact) -> trajectory of ring / counters / history (null: identity)
     const int* act;
+    // training over a frame table: u0 = last window frame of sample b at u0_base + b * u0_bs (null: u_ring); frame i of sample b is
+    // written to frames + b * frames_bs + i * D * H * W (0: contiguous (B, n_cap, D, H, W))
+    const float* u0_base; long long u0_bs; long long frames_bs;
 };
 
 // Exact-mode (FFMA) variant: one thread per stage-1 row; the thread streams its own C1-long row(s)
@@ -704,7 +707,7 @@ __global__ void __launch_bounds__(128) taylor_head_kernel(HeadParams hp, PatchGe
     const size_t HW = (size_t)g.H * g.W;
     const int fc = hp.fcount ? hp.fcount[bt] : g.T;
     const int u_slot = (fc + g.T - 1) % g.T;
-    const float* u0p = hp.u_ring + ((size_t)(bt * g.T + u_slot) * g.D) * HW;
+    const float* u0p = hp.u0_base ? hp.u0_base + (size_t)bt * hp.u0_bs : hp.u_ring + ((size_t)(bt * g.T + u_slot) * g.D) * HW;
     const int cum = hp.cum ? hp.cum[bt] : 0;
     float* y_out = hp.ptrs ? hp.ptrs->y_out : nullptr;
 
@@ -747,7 +750,8 @@ __global__ void __launch_bounds__(128) taylor_head_kernel(HeadParams hp, PatchGe
 #pragma unroll
                 for (int k = KORD; k >= 1; --k) v = (acc[k - 1][o] + v) * (dt / (float)k);
                 const float val = v + u0;
-                if (hp.frames) hp.frames[(((size_t)b * hp.n_cap + (i - 1)) * g.D + d) * HW + pix] = val;
+                if (hp.frames)
+                    hp.frames[(size_t)b * (hp.frames_bs ? (size_t)hp.frames_bs : (size_t)hp.n_cap * g.D * HW) + ((size_t)(i - 1) * g.D + d) * HW + pix] = val;
                 if (y_out) {
                     const int fidx = cum + i - 1;
                     if (fidx < hp.n_roll) y_out[(((size_t)bt * hp.n_roll + fidx) * HW + pix) * g.D + d] = val;

@@ -1427,9 +1427,15 @@ void backward_alloc(tante_handle_s* h, int B) {
 }
 
 // One TANTE step in training mode: same arithmetic as run_step, every activation the backward needs is kept.
+// Window of a training call as a frame table (tante_train_forward_win / tante_backward_win)
+struct TrainWin {
+    FrameTab in;                  // forward: the T window frames, offsets relative to `input`
+    long long frames_bs = 0;      // batch stride of the emitted frames (0: contiguous)
+};
+
 template <typename TA>
 void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, float out_T, int n_cap, float* frames,
-                    float* R_t, cudaStream_t st) {
+                    float* R_t, cudaStream_t st, const TrainWin* win = nullptr) {
     const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K;
     const PatchGeom& g = h->geom;
     const int tokens = B * T * L;
@@ -1443,8 +1449,9 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         // enc_conv_1 as im2col (kept for the weight gradient) + GEMM over the zero-padded patch matrix
         const long long rows_in = (long long)tokens * g.R1;
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv GEMM");
-        if (g.k0 * g.k1 * g.k2 >= 4) conv1_im2col_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
-        else conv1_im2col_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in);
+        const FrameTab ft = win ? win->in : FrameTab();
+        if (g.k0 * g.k1 * g.k2 >= 4) conv1_im2col_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in, nullptr, nullptr, nullptr, ft);
+        else conv1_im2col_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(input, g, TP<TA>(tp.cols), rows_in, nullptr, nullptr, nullptr, ft);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
@@ -1566,6 +1573,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         }
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.u_ring = input; hp.fcount = nullptr;
         hp.n_arr = reinterpret_cast<int*>(h->nbuf.p); hp.frames = frames; hp.n_cap = n_cap;
+        if (win) { hp.u0_base = input + win->in.off[T - 1]; hp.u0_bs = win->in.bs[T - 1]; hp.frames_bs = win->frames_bs; }
         const long long rows = (long long)B * L * g.R1;
         bool done = false;
         if (kTensor) {
@@ -1589,11 +1597,14 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
 }
 
 // Backward of one taped step.  gframes: f32 (B, n_g, D, H, W) gradient of the emitted frames; gRt: f32 [B] or null;
-// grad_input: f32 (B, T, D, H, W) or null (written, not accumulated); flat: f32 [sum numel] parameter gradients in
+// grad_input: f32 (B, T, D, H, W) or null (written, not accumulated; but see `win`); flat: f32 [sum numel] parameter gradients in
 // tante_param order (written, not accumulated).
+// win (frame-table mode): gframes has batch stride win->gf_bs; the input gradient is ACCUMULATED into the frames of win->gin
+// (offsets relative to grad_input; kFrameSkip entries are not computed) instead of written to a contiguous (B, T, D, H, W).
+struct BackwardWin { long long gf_bs; FrameTab gin; };
 template <typename TA>
 void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* gframes, int n_g, const float* gRt,
-                  float* grad_input, float* flat, cudaStream_t st) {
+                  float* grad_input, float* flat, cudaStream_t st, const BackwardWin* win = nullptr) {
     const int B = tp.B_used;
     const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K, D = h->D;
     const PatchGeom& g = h->geom;
@@ -1614,14 +1625,23 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     CK(cudaMemsetAsync(h->garena.p, 0, (size_t)h->garena_elems * 4, st));
     CK(cudaMemsetAsync(dxs, 0, (size_t)tokens * C * 4, st));
     const size_t in_elems = (size_t)B * T * D * h->cfg.H * h->cfg.W;
-    if (grad_input) CK(cudaMemsetAsync(grad_input, 0, in_elems * 4, st));
+    if (grad_input && !win) CK(cudaMemsetAsync(grad_input, 0, in_elems * 4, st));
 
     // ---- Taylor head: all orders in one pass over the frame gradients ----
     {
         HeadBwdParams hp{};
         for (int k = 0; k < K; ++k) hp.G[k] = TP<TA>(h->hG) + (size_t)k * rows1 * kHeadPad;
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
-        hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); hp.grad_input = grad_input;
+        hp.gf_bs = win ? win->gf_bs : (long long)n_g * D * h->cfg.H * h->cfg.W;
+        hp.n_arr = reinterpret_cast<const int*>(tp.n_arr.p);
+        if (win) {
+            const bool want = grad_input && win->gin.off[T - 1] != kFrameSkip;
+            hp.gi_last = want ? grad_input + win->gin.off[T - 1] : nullptr;
+            hp.gi_bs = win->gin.bs[T - 1];
+        } else {
+            hp.gi_last = grad_input ? grad_input + (size_t)(T - 1) * D * h->cfg.H * h->cfg.W : nullptr;
+            hp.gi_bs = (long long)T * D * h->cfg.H * h->cfg.W;
+        }
         const size_t hsmem = (size_t)K * kPatchRows * kPatchPitch * sizeof(float);
         if (g.k0 * g.k1 * g.k2 >= 4) head_gather_kernel<TA, 4><<<blocks_for(rows1, kPatchRows), 128, hsmem, st>>>(hp, g, rows1);
         else head_gather_kernel<TA, 2><<<blocks_for(rows1, kPatchRows), 128, hsmem, st>>>(hp, g, rows1);
@@ -1741,8 +1761,9 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         // dpatch[rows, 64 (K1 padded)] = da1[rows, C1] * W1[C1][K1]  (thin GEMM), then scatter-add into the pixels
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
         gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], cols, kHeadPad, (int)rows_in, kHeadPad, C1, st);
-        if (g.k0 * g.k1 * g.k2 >= 4) conv1_col2im_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in);
-        else conv1_col2im_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in);
+        const FrameTab gt = win ? win->gin : FrameTab();
+        if (g.k0 * g.k1 * g.k2 >= 4) conv1_col2im_kernel<TA, 4><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in, gt);
+        else conv1_col2im_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in, gt);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -2316,6 +2337,79 @@ int tante_backward(tante_handle_t h, int32_t slot, const float* input, const flo
             run_backward<float>(h, tp, input, grad_frames, n_frames, grad_Rt, grad_input, grad_params, st);
         else
             run_backward<__nv_bfloat16>(h, tp, input, grad_frames, n_frames, grad_Rt, grad_input, grad_params, st);
+        tp.valid = false;
+    });
+}
+
+// Frame-table variants: the window of a call is T separate frames (device pointer of sample 0 + batch stride each).
+static FrameTab make_frame_tab(const float* base, const float* const* ptrs, const int64_t* bs, int T) {
+    FrameTab ft{};
+    ft.on = 1;
+    for (int t = 0; t < T; ++t) {
+        if (!ptrs[t]) { ft.off[t] = kFrameSkip; ft.bs[t] = 0; continue; }
+        const intptr_t d = reinterpret_cast<intptr_t>(ptrs[t]) - reinterpret_cast<intptr_t>(base);
+        REQUIRE(d % 4 == 0 && reinterpret_cast<uintptr_t>(ptrs[t]) % 16 == 0 && bs[t] % 4 == 0,
+                "frame pointers must be 16-byte aligned and batch strides multiples of 4 elements");
+        ft.off[t] = (long long)(d / 4);
+        ft.bs[t] = (long long)bs[t];
+    }
+    return ft;
+}
+
+int tante_train_forward_win(tante_handle_t h, int32_t slot, const float* const* frame_ptrs, const int64_t* frame_bstride,
+                            int32_t B, float out_T, int32_t n_cap, float* frames, int64_t frames_bstride, float* R_t,
+                            int32_t* n_host, void* stream) {
+    return guarded([&] {
+        REQUIRE(h && frame_ptrs && frame_bstride && frames, "null argument");
+        REQUIRE(n_cap >= 1, "n_cap must be >= 1");
+        REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
+        REQUIRE(h->T <= 16, "training supports in_T <= 16");
+        REQUIRE(!h->wide && !h->fno && !h->long_axes, "training is not implemented for this configuration (inference / rollout only)");
+        for (int t = 0; t < h->T; ++t) REQUIRE(frame_ptrs[t], "null frame pointer");
+        REQUIRE(frames_bstride % 4 == 0, "frames_bstride must be a multiple of 4 elements");
+        CK(cudaSetDevice(h->device));
+        ensure_ready(h, B);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        Tape& tp = *h->tapes[slot];
+        tape_alloc(h, tp, B);
+        const float* base = frame_ptrs[0];
+        TrainWin win;
+        win.in = make_frame_tab(base, frame_ptrs, frame_bstride, h->T);
+        win.frames_bs = frames_bstride;
+        if (h->cfg.precision == TANTE_PREC_FP32) run_step_train<float>(h, tp, base, B, out_T, n_cap, frames, R_t, st, &win);
+        else run_step_train<__nv_bfloat16>(h, tp, base, B, out_T, n_cap, frames, R_t, st, &win);
+        h->last_B = B;
+        if (n_host) {
+            CK(cudaMemcpyAsync(h->h_flag + 8, h->nbuf.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            *n_host = h->h_flag[8];
+        }
+    });
+}
+
+int tante_backward_win(tante_handle_t h, int32_t slot, const float* grad_frames, int64_t gf_bstride, int32_t n_frames,
+                       const float* grad_Rt, float* const* grad_frame_ptrs, const int64_t* grad_bstride, float* grad_params,
+                       void* stream) {
+    return guarded([&] {
+        REQUIRE(h && grad_frames && grad_params, "null argument");
+        REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range");
+        REQUIRE(n_frames >= 1 && gf_bstride % 4 == 0, "bad gradient frame layout");
+        Tape& tp = *h->tapes[slot];
+        if (!tp.valid) throw Error(TANTE_ERR_STATE, "tape slot holds no forward (or was already consumed)");
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        backward_alloc(h, tp.B_used);
+        BackwardWin win;
+        win.gf_bs = gf_bstride;
+        float* gbase = nullptr;
+        if (grad_frame_ptrs)
+            for (int t = 0; t < h->T && !gbase; ++t) gbase = grad_frame_ptrs[t];
+        if (gbase) win.gin = make_frame_tab(gbase, grad_frame_ptrs, grad_bstride, h->T);
+        else { win.gin = FrameTab{}; win.gin.on = 1; for (int t = 0; t < 16; ++t) win.gin.off[t] = kFrameSkip; }
+        if (h->cfg.precision == TANTE_PREC_FP32)
+            run_backward<float>(h, tp, nullptr, grad_frames, n_frames, grad_Rt, gbase, grad_params, st, &win);
+        else
+            run_backward<__nv_bfloat16>(h, tp, nullptr, grad_frames, n_frames, grad_Rt, gbase, grad_params, st, &win);
         tp.valid = false;
     });
 }

@@ -359,6 +359,88 @@ class _TanteStep(torch.autograd.Function):
         return (None, g_in, None, None, *grads)
 
 
+class _TanteBPTT(torch.autograd.Function):
+    """The chained fixed-step rollout of the training drivers (trainer/trainer.py:144-159: `window = cat(window[:, 1:], y)`, NOT
+    detached) as ONE autograd node: every call reads its window as a frame table over the input window and the prediction
+    buffer (tante_train_forward_win), so no window is ever concatenated, and the backward walks the calls in reverse,
+    ACCUMULATING each call's window gradient into the gradient of the earlier predictions in place (tante_backward_win) --
+    what autograd does with a cat / slice / add chain per call."""
+
+    @staticmethod
+    def forward(ctx, model, x, n_steps, *params):
+        eng = model._engine(x.device)
+        B, T = x.shape[0], model.T
+        D, (H, W) = model.n_channel, model.shape
+        DHW = D * H * W
+        eng.reserve(B)
+        pred = torch.empty((B, n_steps, D, H, W), device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        p_drop = float(model.dropout) if model.training else 0.0
+        slots = []
+        PT, I64 = ctypes.c_void_p * T, ctypes.c_int64 * T
+        try:
+            for k in range(n_steps):
+                slot = eng.acquire_slot()
+                slots.append(slot)
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p_drop > 0 else 0
+                _abi.check(eng.lib.tante_set_dropout(eng.handle, p_drop, seed))
+                ptrs, bss = PT(), I64()
+                for t in range(T):
+                    i = k + t
+                    if i < T:
+                        ptrs[t], bss[t] = x.data_ptr() + 4 * i * DHW, T * DHW
+                    else:
+                        ptrs[t], bss[t] = pred.data_ptr() + 4 * (i - T) * DHW, n_steps * DHW
+                _abi.check(eng.lib.tante_train_forward_win(eng.handle, slot, ptrs, bss, B, 1.0, 1, pred.data_ptr() + 4 * k * DHW,
+                                                           n_steps * DHW, None, None, stream))
+        except Exception:
+            for sl in slots:
+                eng.release_slot(sl)
+            raise
+        ctx.eng, ctx.model, ctx.slots, ctx.n_steps = eng, model, slots, n_steps
+        ctx.guards = [_SlotGuard(eng, sl) for sl in slots]
+        ctx.x_shape = tuple(x.shape)
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        eng, model, n_steps = ctx.eng, ctx.model, ctx.n_steps
+        B, T, D, H, W = ctx.x_shape
+        DHW = D * H * W
+        dev = g_pred.device
+        g_acc = g_pred.to(torch.float32).contiguous().clone()        # accumulated in place below: never autograd's own tensor
+        g_x = torch.zeros(ctx.x_shape, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        acc = model._flat_grad_view(eng) if all(ctx.needs_input_grad[3:]) else None
+        flat_sum = None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        PT, I64 = ctypes.c_void_p * T, ctypes.c_int64 * T
+        for k in range(n_steps - 1, -1, -1):
+            ptrs, bss = PT(), I64()
+            for t in range(T):
+                i = k + t
+                if i < T:
+                    ptrs[t], bss[t] = (g_x.data_ptr() + 4 * i * DHW if g_x is not None else None), T * DHW
+                else:
+                    ptrs[t], bss[t] = g_acc.data_ptr() + 4 * (i - T) * DHW, n_steps * DHW
+            flat = torch.empty((eng.grad_numel,), device=dev, dtype=torch.float32)
+            _abi.check(eng.lib.tante_backward_win(eng.handle, ctx.slots[k], g_acc.data_ptr() + 4 * k * DHW, n_steps * DHW, 1, None,
+                                                  ptrs, bss, flat.data_ptr(), stream))
+            ctx.guards[k].release()
+            if acc is not None:
+                acc.add_(flat)
+            else:
+                flat_sum = flat if flat_sum is None else flat_sum.add_(flat)
+        if acc is not None:
+            return (None, g_x, None, *([None] * len(eng.names)))
+        grads = []
+        for (name, shape), off in zip(model._param_shapes(eng), eng.grad_offsets):
+            n = 1
+            for d in shape:
+                n *= d
+            grads.append(flat_sum[off:off + n].view(shape))
+        return (None, g_x, None, *grads)
+
+
 import weakref
 
 _LIVE_MODELS: "weakref.WeakSet" = weakref.WeakSet()
@@ -578,6 +660,17 @@ class TANTE(nn.Module):
         if self.deg:
             return out
         return out, R_t
+
+    def rollout_train(self, window, n_steps: int):
+        """Fixed-step BPTT rollout of the training drivers (trainer/trainer.py:144-159) for the `deg=True`, `output_length=1`
+        model: (B, T, D, H, W) -> predictions (B, n_steps, D, H, W), one autograd node, no window concatenation.  Same
+        arithmetic as n_steps chained `forward` calls on `cat(window[:, 1:], y)`."""
+        if not (self.deg and int(self.output_length) == 1):
+            raise ValueError("rollout_train covers the fixed-step model (deg=True, output_length=1)")
+        x = self._prep_input(window)
+        eng = self._engine(x.device)
+        params = dict(self.named_parameters())
+        return _TanteBPTT.apply(self, x, int(n_steps), *[params[n] for n in eng.names])
 
     @torch.no_grad()
     def rollout(self, window, n_steps_rollout: int, out_T=None, per_sample: bool = False, sync: bool = True):

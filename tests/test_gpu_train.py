@@ -355,3 +355,63 @@ def test_fused_mse_matches_reference_loss_and_gradient(n_steps):
     assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
     for a, b in zip(gg, gw):
         assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("n_steps", [2, 5])
+def test_windowed_bptt_rollout_equals_chained_calls(prec, tol, n_steps):
+    """`TANTE.rollout_train` (one autograd node over frame tables: tante_train_forward_win / tante_backward_win, no torch.cat)
+    against the reference-style chain `y = model(win); win = cat(win[:, 1:], y)` (trainer/trainer.py:144-159) on the same
+    module: identical predictions, equal parameter gradients and input gradient.  n_steps = 5 > in_T: the last window holds
+    predictions only."""
+    from gpu_util import make_model
+    cfg = O.OracleConfig(n_fields=3, H=32, W=64, taylor_order=1, attn_axes="THW", deg=True)
+    sd = O.make_state_dict(cfg, 4)
+    model = make_model(cfg, sd, precision=prec).train()
+    x = O.make_input(cfg, 3, 8).cuda()
+    g = torch.randn(3, n_steps, 3, 32, 64, generator=torch.Generator().manual_seed(1)).cuda()
+
+    def run(windowed):
+        model.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        if windowed:
+            pred = model.rollout_train(xi, n_steps)
+        else:
+            moving, ys = xi, []
+            for _ in range(n_steps):
+                y = model(moving)
+                moving = torch.cat([moving[:, 1:], y], dim=1)
+                ys.append(y)
+            pred = torch.cat(ys, dim=1)
+        (pred * g).sum().backward()
+        return pred.detach(), xi.grad.detach(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+    p0, gx0, gp0 = run(False)
+    p1, gx1, gp1 = run(True)
+    assert torch.equal(p0, p1)
+    assert rel_l2(gx1.cpu().numpy(), gx0.cpu().numpy()) < tol
+    for n in gp0:
+        assert rel_l2(gp1[n].cpu().numpy(), gp0[n].cpu().numpy()) < max(tol, 5e-5), n
+
+
+def test_train_step_uses_windowed_bptt_and_matches_chained_path(monkeypatch):
+    """tante_b200.trainer.train_step (fused loss over the per-call frames) takes the windowed path for the fixed-step model:
+    same loss and gradient bucket as with TANTE_BPTT_WINDOWS=0."""
+    from gpu_util import make_model
+    from tante_b200.trainer import GradBucket, _roll_frames, mse_loss_frames
+    cfg = O.OracleConfig(n_fields=3, H=32, W=64, taylor_order=1, attn_axes="THW", deg=True)
+    model = make_model(cfg, O.make_state_dict(cfg, 4), precision="fp32").train()
+    bucket = GradBucket(model)
+    x = O.make_input(cfg, 2, 8).cuda()
+    y = torch.randn(2, 4, 32, 64, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TANTE_BPTT_WINDOWS", flag)
+        bucket.zero()
+        frames = _roll_frames(model, x, 4)
+        assert len(frames) == (1 if flag == "1" else 4)
+        loss = mse_loss_frames(frames, y, 4)
+        loss.backward()
+        out.append((float(loss), bucket.flat.clone()))
+    assert abs(out[0][0] - out[1][0]) < 1e-6 * max(1.0, abs(out[0][0]))
+    assert rel_l2(out[1][1].cpu().numpy(), out[0][1].cpu().numpy()) < 2e-5

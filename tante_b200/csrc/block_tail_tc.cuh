@@ -28,6 +28,10 @@
 namespace tante {
 
 constexpr int kBtEpiWarps = 16;
+// CTA pairs: true = the peer's 16 epilogue warps arrive on the leader's barriers themselves; false = the peer's idle warp 1 forwards
+// ONE arrival.  Measured (B200, M = 262144): direct 230 us vs forwarded 220 us -- the cluster-scope release on every epilogue
+// warp's critical path costs more than the extra hop.
+constexpr bool kBtDirect = false;
 constexpr int kBtThreads = 64 + 32 * kBtEpiWarps;
 constexpr int kBtC = 256;                   // embed_dim the kernel is specialised for
 constexpr int kBtKBlk = 128 * 128;          // one k-block of the A tile: [128 rows][64 bf16] = 16 KB
@@ -103,9 +107,9 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::mbar_init(a_full, 1);
         ptx::mbar_init(a_empty, TRAIN ? 1 + kBtEpiWarps : 1);     // the last GEMM's commit (+ training: the stores that read the A tile)
         // pair: the leader's copies also take one forwarded arrival of the peer
-        ptx::mbar_init(a_ready, kBtEpiWarps + ((NCTA == 2 && crank == 0) ? 1 : 0));
+        ptx::mbar_init(a_ready, kBtEpiWarps + ((NCTA == 2 && crank == 0) ? (kBtDirect ? kBtEpiWarps : 1) : 0));
         ptx::mbar_init(acc_full, 1);
-        ptx::mbar_init(acc_free, kBtEpiWarps + ((NCTA == 2 && crank == 0) ? 1 : 0));
+        ptx::mbar_init(acc_free, kBtEpiWarps + ((NCTA == 2 && crank == 0) ? (kBtDirect ? kBtEpiWarps : 1) : 0));
         for (int i = 0; i < 2 * kBtEpiWarps; ++i) ptx::mbar_init(&rbar[i], 1);
         ptx::fence_barrier_init();
     }
@@ -161,7 +165,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int ws = 0;
         uint32_t wph = 0, ar = 0;
         int it = 0;
-        if (NCTA == 2 && crank == 1) {
+        if (NCTA == 2 && crank == 1 && !kBtDirect) {
             // the peer's otherwise idle warp forwards its epilogue's "A tile rewritten" (twice per tile) and "accumulator
             // free" to the leader's barriers
             for (int tile = cid; tile < tiles; tile += ncl, ++it) {
@@ -364,7 +368,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::fence_proxy_async();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(a_ready);
+            if (lane == 0) { if (NCTA == 2 && crank == 1 && kBtDirect) ptx::mbar_arrive_leader(a_ready); else ptx::mbar_arrive(a_ready); }
 
             // ---------------- phase 2: hidden = gelu_tanh(acc + b1) -> A tile ----------------
             ptx::mbar_wait(acc_full, af & 1u); ++af;
@@ -420,7 +424,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::fence_proxy_async();
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(a_ready);
+            if (lane == 0) { if (NCTA == 2 && crank == 1 && kBtDirect) ptx::mbar_arrive_leader(a_ready); else ptx::mbar_arrive(a_ready); }
 
             // ---------------- phase 3: x_out = x_mid + drop(acc + b2) ; LN1' ----------------
             if (ew == 0 && lane == 0) TR(1, 24);
@@ -471,7 +475,9 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acc_free);          // the next tile's first GEMM may overwrite the accumulator
+            if (lane == 0) {                                    // the next tile's first GEMM may overwrite the accumulator
+                if (NCTA == 2 && crank == 1 && kBtDirect) ptx::mbar_arrive_leader(acc_free); else ptx::mbar_arrive(acc_free);
+            }
             if (ew == 0 && lane == 0) TR(1, 32);
             if (p.has_ln_out) {
                 float mean, rstd;

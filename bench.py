@@ -213,7 +213,8 @@ def bench_config(args, batch):
 CLASS_NAMES = {0: "gemm_tc_kernel, bf16/activation epilogue (QKV, MLP-in, convs, input gradients; K=64..768: below the ridge)",
                1: "gemm_tc_kernel, fp32 residual + LayerNorm / embedding epilogue (out-proj, MLP-out, conv3)",
                2: "wgrad_tc_kernel (weight gradients)",
-               3: "block_tail_kernel (out-proj + residual + LN2 + MLP + residual + next LN1 fused: three chained tcgen05 GEMMs)"}
+               3: "block_tail_kernel (out-proj + residual + LN2 + MLP + residual + next LN1 fused: three chained tcgen05 GEMMs)",
+               4: "mlp_bwd_kernel (input-gradient chain of the MLP fused: dY W2 -> gelu' -> W1, two chained tcgen05 GEMMs)"}
 
 
 def ncu_traffic(workload, cls):

@@ -31,6 +31,7 @@
 #include "metrics.cuh"
 #include "block_tail_tc.cuh"
 #include "block_tail2_tc.cuh"
+#include "mlp_bwd_tc.cuh"
 #include "wide_patch.cuh"
 #include "fno.cuh"
 #include "optimizer.cuh"
@@ -156,6 +157,7 @@ struct tante_handle_s {
     DevBuf wbuf, dfield;                // wide: patch / sub-pixel matrix scratch; decoded derivative fields [K][B][D][H][W]
     float drop_p = 0.f;                 // tante_set_dropout: applies to the NEXT tante_train_forward calls
     unsigned long long drop_seed = 0;
+    bool fuse_mlp_bwd = true;           // tensor mode: MLP input-gradient chain as ONE kernel (TANTE_FUSE_MLP_BWD=0: GEMM + elementwise + GEMM)
     bool no_switch = false;             // SWITCH conditional nodes unavailable on this driver: rollouts run without compaction
     bool fuse_tail = true;              // tensor mode: out-proj + LN2 + MLP + LN1' of a block as ONE kernel (TANTE_FUSE_TAIL=0: three GEMMs)
 
@@ -1713,9 +1715,21 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             const float* x_mid = FP(ot.X[2 * li + 1]);
             // MLP half: x_out = x_mid + W2 gelu_tanh(W0 ln2(x_mid) + b0) + b2
             wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), C, GA(h, lp.m2w), tokens, C, C, st, GA(h, lp.m2b));
-            gemm_dx_act<TA, ACT_GELU_TANH>(h, dxb, C, lp.m2wT, g1, TP<TA>(ot.hpre[li]), tokens, C, C, st);
-            wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
-            gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
+            if (kTensor && h->fuse_mlp_bwd && C == kBtC) {
+                // dpre = (dY W2) o gelu'(hpre) and dln2 = dpre W1 in one kernel (mlp_bwd_tc.cuh): dh never touches HBM
+                {
+                    ProfScope ps(h, st, 2.0 * 2.0 * tokens * C * C, 4, (double)tokens * 4 * 2 * C);
+                    CK(launch_mlp_bwd(reinterpret_cast<const __nv_bfloat16*>(dxb), AH(h, lp.m2wT), AH(h, lp.m0wT),
+                                      reinterpret_cast<const __nv_bfloat16*>(ot.hpre[li].p), reinterpret_cast<__nv_bfloat16*>(g1),
+                                      reinterpret_cast<__nv_bfloat16*>(g2), tokens, h->num_sms, st));
+                }
+                h->launches++;
+                wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
+            } else {
+                gemm_dx_act<TA, ACT_GELU_TANH>(h, dxb, C, lp.m2wT, g1, TP<TA>(ot.hpre[li]), tokens, C, C, st);
+                wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
+                gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
+            }
             launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st, drop,
                               drop_site(o, li, 1));
             // attention half: x_mid = x_in + Wo att(ln1(x_in)) + bo
@@ -1947,6 +1961,7 @@ int tante_create(const tante_config_t* cfg, int device, tante_handle_t* out) {
         if (const char* m = getenv("TANTE_ROLLOUT_MODE")) h->rollout_mode = std::max(0, std::min(2, atoi(m)));
         if (const char* m = getenv("TANTE_ENC_CACHE")) h->use_enc_cache = atoi(m) != 0;
         if (const char* m = getenv("TANTE_FUSE_TAIL")) h->fuse_tail = atoi(m) != 0;
+        if (const char* m = getenv("TANTE_FUSE_MLP_BWD")) h->fuse_mlp_bwd = atoi(m) != 0;
         int sms = 0;   // stays at the B200 default when no device is visible (CPU-side plan checks)
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
         else (void)cudaGetLastError();

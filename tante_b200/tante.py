@@ -728,7 +728,7 @@ class TANTE(nn.Module):
         profile_read().  0 = plain-epilogue GEMMs, 1 = fp32 residual/LayerNorm/embedding epilogues, 2 = weight gradients,
         3 = fused block tail (out-proj + LN2 + MLP + LN1' in one kernel)."""
         out = {}
-        for cls in (0, 1, 2, 3):
+        for cls in (0, 1, 2, 3, 4):
             ms = fl = by = 0.0
             n = 0
             for e in self._engines.values():

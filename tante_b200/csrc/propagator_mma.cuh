@@ -15,7 +15,7 @@ namespace tante {
 __device__ __forceinline__ uint32_t slab_off(int r, int chunk) { return (uint32_t)(r * 256 + (((chunk & 8) | ((chunk ^ r) & 7)) << 4)); }
 
 template <int MB /* S_pad / 16 */>
-__global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, float* x, int S, long long IC, long long n_outer,
+__global__ void __launch_bounds__(128, 3) propagator_mma_kernel(const float* xin, float* x, int S, long long IC, long long n_outer,
                                                              const float* __restrict__ W1, const float* __restrict__ b1,
                                                              const float* __restrict__ W2, const float* __restrict__ b2) {
     constexpr int SP = MB * 16;
@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(128) propagator_mma_kernel(const float* xin, f
     const int lchk = lane >> 4;
 
   for (long long tile = blockIdx.x; tile < n_outer * ncb; tile += gridDim.x) {
-    const long long outer = tile / ncb;
-    const long long col0 = (tile % ncb) * 128;
+    // persistent (S <= 32): column blocks fastest; one tile per CTA (S > 32, see the launcher): `outer` fastest, as measured best
+    const bool one_each = (long long)gridDim.x >= n_outer * ncb;
+    const long long outer = one_each ? tile % n_outer : tile / ncb;
+    const long long col0 = (one_each ? tile / n_outer : tile % ncb) * 128;
     float* base = x + (size_t)outer * S * IC + col0;
     const float* ibase = xin + (size_t)outer * S * IC + col0;    // xin == x: in place; else out of place (training)
     const int ncol = (int)min((long long)128, IC - col0);     // multiple of 4
@@ -154,9 +156,22 @@ static bool launch_propagator_mma(const float* xin, float* x, int S, long long I
     const size_t smem = (size_t)2 * SP * 256 + (size_t)2 * SP * (SP * 2 + 16) + 2 * SP * sizeof(float);
     // persistent CTAs: as many as are resident (shared memory / 16 CTAs per SM), each walks over its share of the tiles
     const long long tiles = outer * ((IC + 127) / 128);
-    const int per_sm = (int)std::min<size_t>(16, (227 * 1024) / (smem + 1024));
-    dim3 grid((unsigned)std::min<long long>(tiles, (long long)num_sms * per_sm));
     prop_set_attrs();
+    int per_sm = 1;      // registers, not shared memory, limit the S = 64 variant (189 registers: two CTAs per SM)
+    {
+        cudaError_t oe = cudaSuccess;
+        switch (MB) {
+            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagator_mma_kernel<1>, 128, smem); break;
+            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagator_mma_kernel<2>, 128, smem); break;
+            case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagator_mma_kernel<3>, 128, smem); break;
+            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, propagator_mma_kernel<4>, 128, smem); break;
+        }
+        if (oe != cudaSuccess || per_sm < 1) { (void)cudaGetLastError(); per_sm = 1; }
+    }
+    // S > 32 (189 registers, two CTAs of four warps per SM): a persistent CTA serialises load / pass 1 / pass 2 with nothing to
+    // overlap them -- measured 282 us vs 243 us for one tile per CTA at S = 64 -- so only the short-axis variants are persistent
+    if (MB >= 3 && tiles > 0x7fffffffLL) return false;
+    dim3 grid((unsigned)(MB >= 3 ? tiles : std::min<long long>(tiles, (long long)num_sms * per_sm)));
     switch (MB) {
         case 1: propagator_mma_kernel<1><<<grid, 128, smem, st>>>(xin, x, S, IC, outer, W1, b1, W2, b2); break;
         case 2: propagator_mma_kernel<2><<<grid, 128, smem, st>>>(xin, x, S, IC, outer, W1, b1, W2, b2); break;

@@ -24,5 +24,9 @@ ncu -i /tmp/${TAG}_full_rollout.ncu-rep --page raw --csv > gpurun_out/ncu_full_$
 timeout 900 ncu --set full --clock-control none -k regex:'block_tail|gemm_tc|wgrad_tc|ln_bwd|axial_attention_bwd|mlp_bwd' -s 700 -c 16 \
     -o /tmp/${TAG}_full_train -f python bench.py --steps 1 --warmup 3 --no-extras --no-eager --no-cpu-baseline > gpurun_out/${TAG}_ncu_full_train.log 2>&1
 ncu -i /tmp/${TAG}_full_train.ncu-rep --page raw --csv > gpurun_out/ncu_full_${TAG}_train.csv 2>/dev/null
+# the forward's block tail (the capture above starts inside the backward)
+timeout 600 ncu --set full --clock-control none -k regex:'block_tail' -s 40 -c 2 \
+    -o /tmp/${TAG}_full_train_fwd -f python bench.py --steps 1 --warmup 3 --no-extras --no-eager --no-cpu-baseline > gpurun_out/${TAG}_ncu_full_train_fwd.log 2>&1
+ncu -i /tmp/${TAG}_full_train_fwd.ncu-rep --page raw --csv > gpurun_out/ncu_full_${TAG}_train_fwd.csv 2>/dev/null
 du -sh gpurun_out
 tail -3 gpurun_out/${TAG}_pytest.log; tail -2 gpurun_out/${TAG}_smoke.log; head -c 300 gpurun_out/bench_${TAG}_train_n1.json; echo; tail -3 gpurun_out/${TAG}_bench.err; ls -la gpurun_out | grep ${TAG}

@@ -1,6 +1,6 @@
 """profiles/traffic_<tag>.json for bench.py's `roofline.traffic`: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one
 representative launch per roofline class, from the raw-metric CSV pages of the two in-situ `ncu --set full` captures that
-tools/gpu_evidence.sh takes (rollout and training bench runs).  usage: make_traffic.py <tag> <rollout.csv> <train.csv>"""
+tools/gpu_evidence.sh takes (rollout and training bench runs).  usage: make_traffic.py <tag> <rollout.csv> <train.csv> [more train csv ...]"""
 import csv, json, sys
 
 # (workload, class) -> (kernel-name prefix, grid size or None, description, algorithmic bytes of that launch)
@@ -8,7 +8,7 @@ PICK = {
     ("rollout", "3"): ("block_tail_kernel<0, 2>", None, "fused block tail, inference, M=262144 (3 KB per token)", 262144 * 3072),
     ("rollout", "0"): ("gemm_tc_kernel<256, 1>", "147", "packed QKV projection, M=262144, N=768, K=256", 262144 * 2048),
     ("train", "3"): ("block_tail_kernel<1, 2>", None, "fused block tail, training stores, M=65536 (5.5 KB per token)", 65536 * 5632),
-    ("train", "0"): ("gemm_tc_kernel<256, 1>", "147", "packed QKV projection, M=65536, N=768, K=256", 65536 * 2048),
+    ("train", "0"): ("gemm_tc_kernel<256, 1>", "148", "input-gradient GEMM, M=65536, N=K=256", 65536 * 1024),
     ("train", "2"): ("wgrad_tc_kernel<256>", "148", "weight gradient, M=65536, N=K=256", 65536 * 1024),
     ("train", "4"): ("mlp_bwd_kernel<2>", None, "fused MLP input-gradient chain, M=65536 (2 KB per token)", 65536 * 2048),
 }
@@ -34,8 +34,8 @@ def rows(path):
     return out
 
 
-def main(tag, roll_csv, train_csv):
-    data = {"rollout": rows(roll_csv), "train": rows(train_csv)}
+def main(tag, roll_csv, *train_csvs):
+    data = {"rollout": rows(roll_csv), "train": [r for f in train_csvs for r in rows(f)]}
     res = {"captured": f"round 2, tag {tag}", "source": "ncu --set full --clock-control none over `python bench.py` (rollout / training step), one B200; "
            "dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch per class (tools/gpu_evidence.sh, tools/make_traffic.py)"}
     for (wl, cls), (prefix, grid, desc, alg) in PICK.items():
@@ -50,4 +50,4 @@ def main(tag, roll_csv, train_csv):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:])

@@ -78,12 +78,13 @@ class _Dec(nn.Module):                        # dec_CNN (enc_dec_cnn.py:232-277)
 
 
 class _Block(nn.Module):                      # TransformerBlock (attn_backbone.py:38-83)
-    def __init__(self, C, n_head, dropout):
+    def __init__(self, C, n_head, dropout, mlp_ratio=1.0):
         super().__init__()
         self.ln1 = nn.LayerNorm(C)
         self.attn = nn.MultiheadAttention(C, n_head, batch_first=True, dropout=dropout, bias=True)
         self.ln2 = nn.LayerNorm(C)
-        self.mlp = nn.Sequential(nn.Linear(C, C), nn.GELU(approximate="tanh"), nn.Linear(C, C))
+        hidden = int(C * mlp_ratio)
+        self.mlp = nn.Sequential(nn.Linear(C, hidden), nn.GELU(approximate="tanh"), nn.Linear(hidden, C))
         self.drop = nn.Dropout(dropout)
 
     def forward(self, x, causal):
@@ -95,10 +96,10 @@ class _Block(nn.Module):                      # TransformerBlock (attn_backbone.
 
 
 class _Backbone(nn.Module):                   # Attn_Backbone (attn_backbone.py:88-191), axes T / H / W / L / Y / A
-    def __init__(self, T, Hp, Wp, C, axes, n_head, dropout):
+    def __init__(self, T, Hp, Wp, C, axes, n_head, dropout, mlp_ratio=1.0):
         super().__init__()
         self.axes = axes
-        self.blocks = nn.ModuleList([_Block(C, n_head, dropout) for _ in axes])
+        self.blocks = nn.ModuleList([_Block(C, n_head, dropout, mlp_ratio) for _ in axes])
         self.vertical_propagator = nn.Sequential(nn.Linear(Hp, Hp), nn.GELU(), nn.Linear(Hp, Hp))
         self.horizontal_propagator = nn.Sequential(nn.Linear(Wp, Wp), nn.GELU(), nn.Linear(Wp, Wp))
         self.temporal_propagator = nn.Sequential(nn.Linear(T, T), nn.GELU(), nn.Linear(T, T))
@@ -164,7 +165,7 @@ class EagerTANTE(nn.Module):
         self.encoder = _Enc(D, C, ks)
         for _ in range(cfg.taylor_order):
             self.decoders.append(_Dec(D, C, ks))
-        self.blocks = nn.ModuleList([_Backbone(T, cfg.Hp, cfg.Wp, C, seg, cfg.n_head, dropout) for seg in cfg.segments])
+        self.blocks = nn.ModuleList([_Backbone(T, cfg.Hp, cfg.Wp, C, seg, cfg.n_head, dropout, cfg.mlp_ratio) for seg in cfg.segments])
         self.t_emb = nn.Parameter(t_emb_init(C, T))
         self.s_emb = nn.Parameter(s_emb_init(C, cfg.Hp, cfg.Wp))
         self.t_encode = _Film(C)

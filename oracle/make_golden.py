@@ -31,7 +31,7 @@ def build_ref(ns, cfg: O.OracleConfig, sd):
     md = ref_shim.make_metadata(cfg.n_fields, cfg.H, cfg.W)
     m = ns.TANTE(in_T=cfg.in_T, dset_metadata=md, taylor_order=cfg.taylor_order,
                  frame_interval=cfg.frame_interval, output_length=cfg.output_length,
-                 attn_axes=cfg.attn_axes, n_head=cfg.n_head, mlp_ratio=1.0, dropout=0.0,
+                 attn_axes=cfg.attn_axes, n_head=cfg.n_head, mlp_ratio=cfg.mlp_ratio, dropout=0.0,
                  enc_dec_type=cfg.enc_dec_type, embed_dim=cfg.embed_dim, modes1=cfg.modes1, modes2=cfg.modes2,
                  patch_scale=cfg.patch_scale, overlap_ratio=0.0, deg=cfg.deg)
     m.load_state_dict(sd)
@@ -199,6 +199,17 @@ def main_round2(ns):
         main_fno(ns)
 
 
+def main_mlp(ns):
+    """mlp_ratio != 1 (attn_backbone.py:52-56: hidden = int(embed_dim * mlp_ratio)): forward / rollout and one training step."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_adp_k2_mlp2", C(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="THW-HWT", deg=False, mlp_ratio=2.0),
+                 B=2, out_T=6, rt_bias=2.7, stages=True, n_roll=6)
+    case_forward(ns, "fwd_deg_k1_mlp05", C(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="THW", deg=True, mlp_ratio=0.5),
+                 B=2, out_T=1, rt_bias=0.0, n_roll=3)
+    case_train(ns, "train_deg_k1_mlp4", C(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="THW", deg=True, mlp_ratio=4.0),
+               B=2, n_steps=3)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -222,6 +233,9 @@ def main():
         return
     if "--fno" in sys.argv:
         main_fno(ns)
+        return
+    if "--mlp" in sys.argv:
+        main_mlp(ns)
         return
     C = O.OracleConfig
     # 1. fixed-step (what configs/tante.yaml selects), full outputs on a small grid

@@ -52,6 +52,7 @@ class OracleConfig:
     enc_dec_type: str = "cnn"      # 'cnn' (enc_dec_cnn.py) | 'fno' (enc_dec_fno.py)
     modes1: int = 32
     modes2: int = 32
+    mlp_ratio: float = 1.0         # hidden width of the block MLP = int(embed_dim * mlp_ratio) (attn_backbone.py:52)
 
     @property
     def Hp(self):
@@ -554,8 +555,9 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
             sh[p + "attn.in_proj_weight"] = (3 * C, C); sh[p + "attn.in_proj_bias"] = (3 * C,)
             sh[p + "attn.out_proj.weight"] = (C, C); sh[p + "attn.out_proj.bias"] = (C,)
             sh[p + "ln2.weight"] = (C,); sh[p + "ln2.bias"] = (C,)
-            sh[p + "mlp.0.weight"] = (C, C); sh[p + "mlp.0.bias"] = (C,)
-            sh[p + "mlp.2.weight"] = (C, C); sh[p + "mlp.2.bias"] = (C,)
+            Hm = int(C * cfg.mlp_ratio)
+            sh[p + "mlp.0.weight"] = (Hm, C); sh[p + "mlp.0.bias"] = (Hm,)
+            sh[p + "mlp.2.weight"] = (C, Hm); sh[p + "mlp.2.bias"] = (C,)
         for name, n in (("vertical", Hp), ("horizontal", Wp), ("temporal", T)):
             for j in (0, 2):
                 sh[f"blocks.{k}.{name}_propagator.{j}.weight"] = (n, n)

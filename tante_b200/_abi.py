@@ -27,6 +27,7 @@ class TanteConfig(C.Structure):
         ("n_layers", C.c_int32 * TANTE_MAX_ORDER),
         ("axes", (C.c_char * TANTE_MAX_LAYERS) * TANTE_MAX_ORDER),
         ("enc_dec_fno", C.c_int32), ("modes1", C.c_int32), ("modes2", C.c_int32),
+        ("mlp_hidden", C.c_int32),
     ]
 
 

@@ -129,6 +129,7 @@ struct tante_handle_s {
     tante_config_t cfg{};
     int device = 0;
     int C = 0, C1 = 0, C2 = 0, Hp = 0, Wp = 0, L = 0, T = 0, D = 0, K = 0, HD = 0;
+    int Hm = 0;                          // hidden width of the block MLP = int(embed_dim * mlp_ratio) (attn_backbone.py:52)
     PatchGeom geom{};
     std::vector<Param> params;
     std::map<std::string, int> pindex;
@@ -293,6 +294,8 @@ void build_plan(tante_handle_s* h) {
     h->NOpad = h->K1pad;
     if (h->wide) h->use_enc_cache = false;
     h->C = c.embed_dim; h->C1 = h->C / 4; h->C2 = h->C / 2;
+    h->Hm = c.mlp_hidden > 0 ? c.mlp_hidden : h->C;
+    REQUIRE(h->Hm % 64 == 0 && h->Hm >= 64 && h->Hm <= 1024, "MLP hidden width (embed_dim * mlp_ratio) must be a multiple of 64 in 64..1024");
     h->Hp = c.H / c.patch_scale; h->Wp = c.W / c.patch_scale; h->L = h->Hp * h->Wp;
     h->T = c.in_T; h->D = c.n_fields; h->K = c.taylor_order; h->HD = hd;
     // checked by the model entry points, not here: the head microbenchmark (tante_bench_head) needs no backbone
@@ -373,14 +376,14 @@ void build_plan(tante_handle_s* h) {
             lp.outb = add_param(h, p + "attn.out_proj.bias", {C});
             lp.ln2w = add_param(h, p + "ln2.weight", {C});
             lp.ln2b = add_param(h, p + "ln2.bias", {C});
-            lp.m0w = add_param(h, p + "mlp.0.weight", {C, C});
-            lp.m0b = add_param(h, p + "mlp.0.bias", {C});
-            lp.m2w = add_param(h, p + "mlp.2.weight", {C, C});
+            lp.m0w = add_param(h, p + "mlp.0.weight", {h->Hm, C});      // hidden = int(C * mlp_ratio) (attn_backbone.py:52-56)
+            lp.m0b = add_param(h, p + "mlp.0.bias", {h->Hm});
+            lp.m2w = add_param(h, p + "mlp.2.weight", {C, h->Hm});
             lp.m2b = add_param(h, p + "mlp.2.bias", {C});
             lp.inwT = add_trans(h, lp.inw, 3 * C, C);
             lp.outwT = add_trans(h, lp.outw, C, C);
-            lp.m0wT = add_trans(h, lp.m0w, C, C);
-            lp.m2wT = add_trans(h, lp.m2w, C, C);
+            lp.m0wT = add_trans(h, lp.m0w, h->Hm, C);
+            lp.m2wT = add_trans(h, lp.m2w, C, h->Hm);
             op.layers.push_back(lp);
         }
         const char* pn[3] = {"vertical", "horizontal", "temporal"};
@@ -954,7 +957,7 @@ void launch_emit_wide(tante_handle_s* h, const StepIO& io, int B, const RolloutS
 // One TANTE step (reference models/tante.py:125-176) as a launch sequence on `st`.
 template <typename TA>
 void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs, cudaStream_t st) {
-    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K;
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K, Hm = h->Hm;
     const PatchGeom& g = h->geom;
     const int tokens = B * T * L;
     float* x = reinterpret_cast<float*>(h->x.p);
@@ -1054,7 +1057,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, qkv, att, B, lp.axis, st);
             if constexpr (kFuseLN) {
-                if (h->fuse_tail && C == kBtC) {
+                if (h->fuse_tail && C == kBtC && h->Hm == C) {
                     const LayerPlan* nx = li + 1 < op.layers.size() ? &op.layers[li + 1] : nullptr;
                     launch_tail(h, lp, nx, att, x, x, ln, tokens, st);
                     ln_ready = nx != nullptr;
@@ -1070,15 +1073,15 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
                 launch_layernorm<TA>(h, x, lp.ln2w, lp.ln2b, ln, tokens, st);
             }
             EpiParams e0; e0.bias = AF(h, lp.m0b);
-            gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, C, false, tokens, C, C, e0, st);
+            gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, Hm, false, tokens, Hm, C, e0, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x; e2.ldr = C;
-            if (kFuseLN && li + 1 < op.layers.size()) {
+            if (kFuseLN && li + 1 < op.layers.size() && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
                 const LayerPlan& nx = op.layers[li + 1];
                 e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ln;
-                gemm<TA>(h, EPI_BIAS_RESID_LN, hid, C, lp.m2w, x, C, true, tokens, C, C, e2, st);
+                gemm<TA>(h, EPI_BIAS_RESID_LN, hid, Hm, lp.m2w, x, C, true, tokens, C, Hm, e2, st);
                 ln_ready = true;
             } else {
-                gemm<TA>(h, EPI_BIAS_RESID, hid, C, lp.m2w, x, C, true, tokens, C, C, e2, st);
+                gemm<TA>(h, EPI_BIAS_RESID, hid, Hm, lp.m2w, x, C, true, tokens, C, Hm, e2, st);
                 ln_ready = false;
             }
         }
@@ -1370,8 +1373,8 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
             dev_alloc(h, ot.qkv[i], tokens * 3 * C * es);
             dev_alloc(h, ot.att[i], tokens * C * es);
             dev_alloc(h, ot.ln2[i], tokens * C * es);
-            dev_alloc(h, ot.hpre[i], tokens * C * es);
-            dev_alloc(h, ot.hact[i], tokens * C * es);
+            dev_alloc(h, ot.hpre[i], tokens * h->Hm * es);
+            dev_alloc(h, ot.hact[i], tokens * h->Hm * es);
         }
         dev_alloc(h, ot.dl, BL * C * es);
         dev_alloc(h, ot.d32, BL * C * 4);
@@ -1401,7 +1404,7 @@ void backward_alloc(tante_handle_s* h, int B) {
     dev_alloc(h, h->garena, (size_t)h->garena_elems * 4);
     dev_alloc(h, h->dxs, tokens * C * 4);
     dev_alloc(h, h->dxb, tokens * C * es);      // bf16 mirror of the gradient stream; in the exact mode: its dropout-masked copy
-    dev_alloc(h, h->g1, tokens * C * es);
+    dev_alloc(h, h->g1, tokens * std::max(C, h->Hm) * es);
     dev_alloc(h, h->g2, tokens * C * es);
     dev_alloc(h, h->gq, tokens * std::max(3 * C, g.R2 * C2) * es);
     dev_alloc(h, h->ga1, tokens * g.R1 * C1 * es);
@@ -1438,13 +1441,13 @@ struct TrainWin {
 template <typename TA>
 void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, float out_T, int n_cap, float* frames,
                     float* R_t, cudaStream_t st, const TrainWin* win = nullptr) {
-    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K;
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K, Hm = h->Hm;
     const PatchGeom& g = h->geom;
     const int tokens = B * T * L;
     constexpr bool kTensor = sizeof(TA) == 2;
     tp.drop = make_drop_cfg(h->drop_p, h->drop_seed);
     const DropCfg& drop = tp.drop;
-    if (drop.p > 0.f && kTensor && !(h->fuse_tail && C == kBtC))
+    if (drop.p > 0.f && kTensor && !(h->fuse_tail && C == kBtC && h->Hm == C))
         throw Error(TANTE_ERR_INVALID, "dropout in the tensor mode needs the fused block tail (TANTE_FUSE_TAIL=1, embed_dim 256)");
     // --- encoder ---
     {
@@ -1490,7 +1493,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln1[li]), C, lp.inw, ot.qkv[li].p, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, TP<TA>(ot.qkv[li]), TP<TA>(ot.att[li]), B, lp.axis, st, drop, drop_site(o, (int)li, 0));
             if constexpr (kTensor) {
-                if (h->fuse_tail && C == kBtC) {
+                if (h->fuse_tail && C == kBtC && h->Hm == C) {
                     const LayerPlan* nx = li + 1 < nl ? &op.layers[li + 1] : nullptr;
                     launch_tail(h, lp, nx, TP<TA>(ot.att[li]), x_in, x_out, nx ? TP<TA>(ot.ln1[li + 1]) : nullptr, tokens, st,
                                 x_mid, TP<TA>(ot.ln2[li]), TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), drop,
@@ -1509,17 +1512,17 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
                 launch_layernorm<TA>(h, x_mid, lp.ln2w, lp.ln2b, TP<TA>(ot.ln2[li]), tokens, st);
             }
             EpiParams e0; e0.bias = AF(h, lp.m0b);
-            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln2[li]), C, lp.m0w, ot.hpre[li].p, C, false, tokens, C, C, e0, st);
-            launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * C, st);
+            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln2[li]), C, lp.m0w, ot.hpre[li].p, Hm, false, tokens, Hm, C, e0, st);
+            launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * Hm, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x_mid; e2.ldr = C;
             e2.drop = drop; e2.drop_site = drop_site(o, (int)li, 2);
-            if (kTensor && li + 1 < nl) {
+            if (kTensor && li + 1 < nl && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
                 const LayerPlan& nx = op.layers[li + 1];
                 e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ot.ln1[li + 1].p;
-                gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.hact[li]), C, lp.m2w, x_out, C, true, tokens, C, C, e2, st);
+                gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.hact[li]), Hm, lp.m2w, x_out, C, true, tokens, C, Hm, e2, st);
                 ln_ready = true;
             } else {
-                gemm<TA>(h, EPI_BIAS_RESID, TP<TA>(ot.hact[li]), C, lp.m2w, x_out, C, true, tokens, C, C, e2, st);
+                gemm<TA>(h, EPI_BIAS_RESID, TP<TA>(ot.hact[li]), Hm, lp.m2w, x_out, C, true, tokens, C, Hm, e2, st);
                 ln_ready = false;
             }
         }
@@ -1608,7 +1611,7 @@ template <typename TA>
 void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* gframes, int n_g, const float* gRt,
                   float* grad_input, float* flat, cudaStream_t st, const BackwardWin* win = nullptr) {
     const int B = tp.B_used;
-    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K, D = h->D;
+    const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L, K = h->K, D = h->D, Hm = h->Hm;
     const PatchGeom& g = h->geom;
     const int tokens = B * T * L;
     const int BL = B * L;
@@ -1714,8 +1717,8 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             const float* x_in = FP(ot.X[2 * li]);
             const float* x_mid = FP(ot.X[2 * li + 1]);
             // MLP half: x_out = x_mid + W2 gelu_tanh(W0 ln2(x_mid) + b0) + b2
-            wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), C, GA(h, lp.m2w), tokens, C, C, st, GA(h, lp.m2b));
-            if (kTensor && h->fuse_mlp_bwd && C == kBtC) {
+            wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), Hm, GA(h, lp.m2w), tokens, C, Hm, st, GA(h, lp.m2b));
+            if (kTensor && h->fuse_mlp_bwd && C == kBtC && h->Hm == C) {
                 // dpre = (dY W2) o gelu'(hpre) and dln2 = dpre W1 in one kernel (mlp_bwd_tc.cuh): dh never touches HBM
                 {
                     ProfScope ps(h, st, 2.0 * 2.0 * tokens * C * C, 4, (double)tokens * 4 * 2 * C);
@@ -1726,9 +1729,9 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
                 h->launches++;
                 wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
             } else {
-                gemm_dx_act<TA, ACT_GELU_TANH>(h, dxb, C, lp.m2wT, g1, TP<TA>(ot.hpre[li]), tokens, C, C, st);
-                wgrad<TA>(h, g1, C, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, C, C, st, GA(h, lp.m0b));
-                gemm_dx<TA>(h, g1, C, lp.m0wT, g2, C, tokens, C, C, st);
+                gemm_dx_act<TA, ACT_GELU_TANH>(h, dxb, C, lp.m2wT, g1, TP<TA>(ot.hpre[li]), tokens, Hm, C, st);
+                wgrad<TA>(h, g1, Hm, TP<TA>(ot.ln2[li]), C, GA(h, lp.m0w), tokens, Hm, C, st, GA(h, lp.m0b));
+                gemm_dx<TA>(h, g1, Hm, lp.m0wT, g2, C, tokens, C, Hm, st);
             }
             launch_ln_bwd<TA>(h, g2, x_mid, lp.ln2w, dxs, dxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), tokens, st, drop,
                               drop_site(o, li, 1));
@@ -2108,7 +2111,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         dev_alloc(h, h->ln, tokens * C * es);
         dev_alloc(h, h->qkv, tokens * 3 * C * es);
         dev_alloc(h, h->att, tokens * C * es);
-        dev_alloc(h, h->hid, tokens * C * es);
+        dev_alloc(h, h->hid, tokens * std::max(C, h->Hm) * es);
         dev_alloc(h, h->a1, tokens * g.R1 * C1 * es);
         if (es == 2) dev_alloc(h, h->icols, tokens * g.R1 * kHeadPad * es);
         dev_alloc(h, h->a2, tokens * g.R2 * C2 * es);

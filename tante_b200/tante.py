@@ -188,6 +188,7 @@ class _Engine:
         cfg.precision = precision
         cfg.enc_dec_fno = 1 if model.enc_dec_type == "fno" else 0
         cfg.modes1, cfg.modes2 = int(model.modes1), int(model.modes2)
+        cfg.mlp_hidden = int(model.C * model.mlp_ratio)
         for k, seg in enumerate(model.blocks_axes):
             if len(seg) > _abi.TANTE_MAX_LAYERS:
                 raise ValueError("too many layers in one attn_axes segment")
@@ -505,8 +506,10 @@ class TANTE(nn.Module):
         self.enc_dec_type, self.modes1, self.modes2 = enc_dec_type, modes1, modes2
         if overlap_ratio != 0.0:
             raise NotImplementedError("overlap_ratio != 0 is not supported by the patch-GEMM kernels")
-        if float(mlp_ratio) != 1.0:
-            raise NotImplementedError("mlp_ratio != 1.0 is not supported yet")
+        hidden = int(embed_dim * float(mlp_ratio))
+        if hidden < 64 or hidden > 1024 or hidden % 64:
+            raise NotImplementedError("int(embed_dim * mlp_ratio) must be a multiple of 64 in 64..1024 (mlp_ratio 0.25 .. 4 at embed_dim 256)")
+        self.mlp_ratio = float(mlp_ratio)
         ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
         self.patch_kernels = ks
         if enc_dec_type == "fno":

@@ -318,7 +318,9 @@ def test_host_prefetcher_pipeline_matches_direct_calls():
 # ------------------------------------------------------------------------------------------------
 NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d11", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
         # enc_dec_type = 'fno' (enc_dec_fno.py): spectral layers as truncated DFTs (fno.cuh)
-        "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16"]
+        "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16",
+        # mlp_ratio 2 / 0.5 (attn_backbone.py:52-56): the block MLP as two GEMMs of width int(C * mlp_ratio)
+        "fwd_adp_k2_mlp2", "fwd_deg_k1_mlp05"]
 
 
 @pytest.mark.parametrize("name", NEXT)
@@ -350,7 +352,8 @@ def test_next_scope_forward_and_rollout_fp32(name):
 
 
 @pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
-                                  "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16"])
+                                  "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16", "fwd_adp_k2_mlp2",
+                                  "fwd_deg_k1_mlp05"])
 def test_next_scope_forward_bf16(name):
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
     with torch.inference_mode():

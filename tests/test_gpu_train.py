@@ -92,7 +92,7 @@ def _report(model, z, meta, tol):
     return bad, worst
 
 
-@pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2"])
+@pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2", "train_deg_k1_mlp4"])
 def test_training_step_fp32_matches_reference_golden(name):
     z, meta, cfg, model, x, y, loss = _train_case(name, "fp32")
     assert abs(float(loss) - float(z["loss"])) < 2e-6 * max(1.0, abs(float(z["loss"])))
@@ -104,7 +104,7 @@ def test_training_step_fp32_matches_reference_golden(name):
     assert abs(float(x.grad.norm()) - float(z["grad_input_norm"])) < FP32_GRAD_TOL * float(z["grad_input_norm"])
 
 
-@pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2"])
+@pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2", "train_deg_k1_mlp4"])
 def test_training_step_bf16_close_to_reference_golden(name):
     z, meta, cfg, model, x, y, loss = _train_case(name, "bf16")
     assert abs(float(loss) - float(z["loss"])) < 2e-2 * max(1.0, abs(float(z["loss"])))

@@ -31,7 +31,8 @@ def build_ref(ns, cfg: O.OracleConfig, sd):
     md = ref_shim.make_metadata(cfg.n_fields, cfg.H, cfg.W)
     m = ns.TANTE(in_T=cfg.in_T, dset_metadata=md, taylor_order=cfg.taylor_order,
                  frame_interval=cfg.frame_interval, output_length=cfg.output_length,
-                 attn_axes=cfg.attn_axes, n_head=cfg.n_head, mlp_ratio=cfg.mlp_ratio, dropout=0.0,
+                 attn_axes=cfg.attn_axes, expanded_channel=cfg.expanded_channel, n_head=cfg.n_head,
+                 mlp_ratio=cfg.mlp_ratio, dropout=0.0,
                  enc_dec_type=cfg.enc_dec_type, embed_dim=cfg.embed_dim, modes1=cfg.modes1, modes2=cfg.modes2,
                  patch_scale=cfg.patch_scale, overlap_ratio=0.0, deg=cfg.deg)
     m.load_state_dict(sd)
@@ -210,6 +211,18 @@ def main_mlp(ns):
                B=2, n_steps=3)
 
 
+def main_axisc(ns):
+    """Attention axis 'C' (attn_backbone.py:124-130,184-189): every latent token becomes a sequence of embed_dim channel
+    tokens, lifted 1 -> expanded_channel by a two-layer MLP, run through a TransformerBlock(expanded_channel); the last
+    feature is the new latent."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_adp_k2_axes_c", C(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="TCW-HC", deg=False),
+                 B=2, out_T=6, rt_bias=2.7, stages=True, n_roll=6)
+    case_forward(ns, "fwd_deg_k1_axes_c64", C(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="HC", deg=True,
+                                               expanded_channel=256, mlp_ratio=0.5),
+                 B=1, out_T=1, rt_bias=0.0, n_roll=2)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -236,6 +249,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--axisc" in sys.argv:
+        main_axisc(ns)
         return
     C = O.OracleConfig
     # 1. fixed-step (what configs/tante.yaml selects), full outputs on a small grid

@@ -53,6 +53,7 @@ class OracleConfig:
     modes1: int = 32
     modes2: int = 32
     mlp_ratio: float = 1.0         # hidden width of the block MLP = int(embed_dim * mlp_ratio) (attn_backbone.py:52)
+    expanded_channel: int = 128    # embedding width of the channel-attention blocks, axis 'C' (attn_backbone.py:124-130)
 
     @property
     def Hp(self):
@@ -299,9 +300,18 @@ def backbone(sd, cfg: OracleConfig, k: int, axes: str, x, drop_fn=None):
     x = (v + _axis_mlp(sd, p + "horizontal_propagator.", v)).permute(0, 1, 2, 4, 3)
     v = x.permute(0, 2, 3, 4, 1)
     x = (v + _axis_mlp(sd, p + "temporal_propagator.", v)).permute(0, 4, 1, 2, 3)
+    channel_index = 0
     for i, axis in enumerate(axes):
         bp = f"{p}blocks.{i}."
-        if axis == "T":      # (b h w) t c, causal (:149-152)
+        if axis == "C":      # (b t h w) c 1 -> lift 1 -> E -> block over the C channel tokens -> last feature (:184-189)
+            if drop_fn is not None:
+                raise ValueError("explicit dropout masks are not defined for the channel axis")
+            s = x.reshape(B * T * H * W, C, 1)
+            s = _axis_mlp(sd, f"{p}channel_blocks.{channel_index}.", s)
+            channel_index += 1
+            s = transformer_block(sd, bp, s, cfg.n_head, False)[..., -1]
+            x = s.reshape(B, T, H, W, C)
+        elif axis == "T":    # (b h w) t c, causal (:149-152)
             s = x.permute(0, 2, 3, 1, 4).reshape(B * H * W, T, C)
             dr = None if drop_fn is None else drop_fn(k, i, tok_all.permute(0, 2, 3, 1).reshape(B * H * W, T))
             s = transformer_block(sd, bp, s, cfg.n_head, True, dr)
@@ -549,15 +559,23 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
                 kk = ks[2 - i]
                 sh[f"decoders.{k}.dec_conv_{i+1}.deconv.weight"] = (dch[i], dch[i + 1], kk, kk)
                 sh[f"decoders.{k}.dec_conv_{i+1}.deconv.bias"] = (dch[i + 1],)
-        for i, _ in enumerate(axes):
+        n_chan = 0
+        for i, ax in enumerate(axes):
             p = f"blocks.{k}.blocks.{i}."
-            sh[p + "ln1.weight"] = (C,); sh[p + "ln1.bias"] = (C,)
-            sh[p + "attn.in_proj_weight"] = (3 * C, C); sh[p + "attn.in_proj_bias"] = (3 * C,)
-            sh[p + "attn.out_proj.weight"] = (C, C); sh[p + "attn.out_proj.bias"] = (C,)
-            sh[p + "ln2.weight"] = (C,); sh[p + "ln2.bias"] = (C,)
-            Hm = int(C * cfg.mlp_ratio)
-            sh[p + "mlp.0.weight"] = (Hm, C); sh[p + "mlp.0.bias"] = (Hm,)
-            sh[p + "mlp.2.weight"] = (C, Hm); sh[p + "mlp.2.bias"] = (C,)
+            Cb = cfg.embed_dim
+            if ax == "C":      # channel attention: the block works on expanded_channel features (attn_backbone.py:124-132)
+                Cb = cfg.expanded_channel
+                q = f"blocks.{k}.channel_blocks.{n_chan}."
+                n_chan += 1
+                sh[q + "0.weight"] = (Cb // 4, 1); sh[q + "0.bias"] = (Cb // 4,)
+                sh[q + "2.weight"] = (Cb, Cb // 4); sh[q + "2.bias"] = (Cb,)
+            sh[p + "ln1.weight"] = (Cb,); sh[p + "ln1.bias"] = (Cb,)
+            sh[p + "attn.in_proj_weight"] = (3 * Cb, Cb); sh[p + "attn.in_proj_bias"] = (3 * Cb,)
+            sh[p + "attn.out_proj.weight"] = (Cb, Cb); sh[p + "attn.out_proj.bias"] = (Cb,)
+            sh[p + "ln2.weight"] = (Cb,); sh[p + "ln2.bias"] = (Cb,)
+            Hm = int(Cb * cfg.mlp_ratio)
+            sh[p + "mlp.0.weight"] = (Hm, Cb); sh[p + "mlp.0.bias"] = (Hm,)
+            sh[p + "mlp.2.weight"] = (Cb, Hm); sh[p + "mlp.2.bias"] = (Cb,)
         for name, n in (("vertical", Hp), ("horizontal", Wp), ("temporal", T)):
             for j in (0, 2):
                 sh[f"blocks.{k}.{name}_propagator.{j}.weight"] = (n, n)

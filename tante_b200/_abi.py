@@ -28,6 +28,7 @@ class TanteConfig(C.Structure):
         ("axes", (C.c_char * TANTE_MAX_LAYERS) * TANTE_MAX_ORDER),
         ("enc_dec_fno", C.c_int32), ("modes1", C.c_int32), ("modes2", C.c_int32),
         ("mlp_hidden", C.c_int32),
+        ("expanded_channel", C.c_int32), ("mlp_hidden_c", C.c_int32),
     ]
 
 

@@ -34,6 +34,7 @@
 #include "mlp_bwd_tc.cuh"
 #include "wide_patch.cuh"
 #include "fno.cuh"
+#include "channel_axis.cuh"
 #include "optimizer.cuh"
 
 using namespace tante;
@@ -89,6 +90,10 @@ struct LayerPlan {
     char axis;
     int64_t ln1w, ln1b, inw, inb, outw, outb, ln2w, ln2b, m0w, m0b, m2w, m2b;
     int64_t inwT, outwT, m0wT, m2wT;      // [K][N] copies for the input-gradient GEMMs
+    // axis 'C' (channel attention, attn_backbone.py:124-130,184-189): the block works on E = expanded_channel features, its MLP
+    // on Hc hidden units; cw0 .. cb2 = channel_blocks[j] = Linear(1, E/4), GELU, Linear(E/4, E).  Other axes: E = C, Hc = Hm.
+    int E = 0, Hc = 0;
+    int64_t cw0 = 0, cb0 = 0, cw2 = 0, cb2 = 0;
 };
 struct SpecPlan {            // one SpectralLayer (enc_dec_fno.py:184-222)
     int64_t w = 0, w0 = 0, b0 = 0;      // complex weight [Cin][Cout][wm1][wm2] (as float pairs), 1x1 conv [Cout][Cin], bias [Cout]
@@ -148,6 +153,9 @@ struct tante_handle_s {
     bool use_enc_cache = true;          // TANTE_ENC_CACHE=0 re-encodes the whole window every call
     bool axes_ok = true;                // Hp, Wp, T <= 64 (what the axial kernels cover)
     bool long_axes = false;             // an L / Y / A layer or an axis longer than 64 tokens: inference / rollout only
+    bool chan = false;                  // an axis-'C' layer (channel_axis.cuh): inference / rollout only
+    int chanE = 0, chanHc = 0, chan_tokens = 0;   // widest E / hidden of the 'C' layers; latent tokens per chunk of the channel pass
+    DevBuf cx, cln, cqkv, catt, chid;   // channel pass scratch: fp32 stream [rows][E], LN / QKV / attention / hidden, rows = chan_tokens * C
     bool fno = false;                   // enc_dec_type = 'fno' (fno.cuh): spectral layers between two patch stages; inference / rollout
     int fp0 = 0, fp1 = 0;               // fno patch kernels (enc_dec_fno.py:39-46)
     SpecPlan fes1, fes2;                // fno encoder: enc_spectral_1 / enc_spectral_2
@@ -358,32 +366,52 @@ void build_plan(tante_handle_s* h) {
         const int nl = c.n_layers[o];
         REQUIRE(nl >= 1 && nl <= TANTE_MAX_LAYERS, "ValueError: Invalid block: empty segment.");
         const std::string bp = "blocks." + std::to_string(o) + ".";
+        int n_chan = 0;
         for (int i = 0; i < nl; ++i) {
             LayerPlan lp;
             lp.axis = c.axes[o][i];
-            // T / H / W: the axial layers of configs/tante.yaml; L / Y / A (attn_backbone.py:164-182): composite sequences,
-            // forward / rollout only.  'C' (channel attention with its 1 -> expanded_channel lift, :184-189) is not built;
+            // T / H / W: the axial layers of configs/tante.yaml; L / Y / A (attn_backbone.py:164-182): composite sequences;
+            // C (:184-189): channel attention behind a 1 -> expanded_channel lift.  L / Y / A / C: forward / rollout only.
             // 'X' cannot be reached through TANTE's own validation (tante.py:76).
-            REQUIRE(lp.axis == 'T' || lp.axis == 'H' || lp.axis == 'W' || lp.axis == 'L' || lp.axis == 'Y' || lp.axis == 'A',
-                    std::string("attention axis '") + lp.axis + "' is not implemented (supported: T, H, W, L, Y, A)");
-            if (lp.axis == 'L' || lp.axis == 'Y' || lp.axis == 'A') h->long_axes = true;
+            REQUIRE(lp.axis == 'T' || lp.axis == 'H' || lp.axis == 'W' || lp.axis == 'L' || lp.axis == 'Y' || lp.axis == 'A' ||
+                        lp.axis == 'C',
+                    std::string("attention axis '") + lp.axis + "' is not implemented (supported: T, H, W, L, Y, A, C)");
+            if (lp.axis == 'L' || lp.axis == 'Y' || lp.axis == 'A' || lp.axis == 'C') h->long_axes = true;
             const std::string p = bp + "blocks." + std::to_string(i) + ".";
-            lp.ln1w = add_param(h, p + "ln1.weight", {C});
-            lp.ln1b = add_param(h, p + "ln1.bias", {C});
-            lp.inw = add_param(h, p + "attn.in_proj_weight", {3 * C, C});
-            lp.inb = add_param(h, p + "attn.in_proj_bias", {3 * C});
-            lp.outw = add_param(h, p + "attn.out_proj.weight", {C, C});
-            lp.outb = add_param(h, p + "attn.out_proj.bias", {C});
-            lp.ln2w = add_param(h, p + "ln2.weight", {C});
-            lp.ln2b = add_param(h, p + "ln2.bias", {C});
-            lp.m0w = add_param(h, p + "mlp.0.weight", {h->Hm, C});      // hidden = int(C * mlp_ratio) (attn_backbone.py:52-56)
-            lp.m0b = add_param(h, p + "mlp.0.bias", {h->Hm});
-            lp.m2w = add_param(h, p + "mlp.2.weight", {C, h->Hm});
-            lp.m2b = add_param(h, p + "mlp.2.bias", {C});
-            lp.inwT = add_trans(h, lp.inw, 3 * C, C);
-            lp.outwT = add_trans(h, lp.outw, C, C);
-            lp.m0wT = add_trans(h, lp.m0w, h->Hm, C);
-            lp.m2wT = add_trans(h, lp.m2w, C, h->Hm);
+            int Cb = C, Hb = h->Hm;
+            if (lp.axis == 'C') {
+                Cb = c.expanded_channel > 0 ? c.expanded_channel : 128;
+                Hb = c.mlp_hidden_c > 0 ? c.mlp_hidden_c : Cb;
+                REQUIRE(Cb % 64 == 0 && Cb >= 64 && Cb <= 256, "expanded_channel must be a multiple of 64 in 64..256");
+                REQUIRE(Cb % c.n_head == 0 && (Cb / c.n_head == 16 || Cb / c.n_head == 32 || Cb / c.n_head == 64),
+                        "expanded_channel / n_head must be 16, 32 or 64");
+                REQUIRE(Hb % 64 == 0 && Hb >= 64 && Hb <= 1024, "int(expanded_channel * mlp_ratio) must be a multiple of 64 in 64..1024");
+                const std::string q = bp + "channel_blocks." + std::to_string(n_chan++) + ".";
+                lp.cw0 = add_param(h, q + "0.weight", {Cb / 4, 1});
+                lp.cb0 = add_param(h, q + "0.bias", {Cb / 4});
+                lp.cw2 = add_param(h, q + "2.weight", {Cb, Cb / 4});
+                lp.cb2 = add_param(h, q + "2.bias", {Cb});
+                h->chan = true;
+                h->chanE = std::max(h->chanE, Cb);
+                h->chanHc = std::max(h->chanHc, Hb);
+            }
+            lp.E = Cb; lp.Hc = Hb;
+            lp.ln1w = add_param(h, p + "ln1.weight", {Cb});
+            lp.ln1b = add_param(h, p + "ln1.bias", {Cb});
+            lp.inw = add_param(h, p + "attn.in_proj_weight", {3 * Cb, Cb});
+            lp.inb = add_param(h, p + "attn.in_proj_bias", {3 * Cb});
+            lp.outw = add_param(h, p + "attn.out_proj.weight", {Cb, Cb});
+            lp.outb = add_param(h, p + "attn.out_proj.bias", {Cb});
+            lp.ln2w = add_param(h, p + "ln2.weight", {Cb});
+            lp.ln2b = add_param(h, p + "ln2.bias", {Cb});
+            lp.m0w = add_param(h, p + "mlp.0.weight", {Hb, Cb});      // hidden = int(C * mlp_ratio) (attn_backbone.py:52-56)
+            lp.m0b = add_param(h, p + "mlp.0.bias", {Hb});
+            lp.m2w = add_param(h, p + "mlp.2.weight", {Cb, Hb});
+            lp.m2b = add_param(h, p + "mlp.2.bias", {Cb});
+            lp.inwT = add_trans(h, lp.inw, 3 * Cb, Cb);
+            lp.outwT = add_trans(h, lp.outw, Cb, Cb);
+            lp.m0wT = add_trans(h, lp.m0w, Hb, Cb);
+            lp.m2wT = add_trans(h, lp.m2w, Cb, Hb);
             op.layers.push_back(lp);
         }
         const char* pn[3] = {"vertical", "horizontal", "temporal"};
@@ -541,8 +569,8 @@ void gemm<__nv_bfloat16>(tante_handle_s* h, int epi, const __nv_bfloat16* A, int
 }
 
 template <typename TOut>
-void launch_layernorm(tante_handle_s* h, const float* x, int64_t w, int64_t b, TOut* y, int rows, cudaStream_t st) {
-    const int C = h->C;
+void launch_layernorm(tante_handle_s* h, const float* x, int64_t w, int64_t b, TOut* y, int rows, cudaStream_t st, int width = 0) {
+    const int C = width > 0 ? width : h->C;
     const int blocks = (rows + 7) / 8;
     if (C <= 256) layernorm_kernel<TOut, 2><<<blocks, 256, 0, st>>>(x, AF(h, w), AF(h, b), y, rows, C, 1e-5f);
     else layernorm_kernel<TOut, 4><<<blocks, 256, 0, st>>>(x, AF(h, w), AF(h, b), y, rows, C, 1e-5f);
@@ -575,6 +603,42 @@ void launch_tail(tante_handle_s* h, const LayerPlan& lp, const LayerPlan* nx, co
     h->launches++;
 }
 
+// Attention core over n_seq sequences of S tokens addressed in place: token(pos) = (outer * S + pos) * inner + inner_idx, packed
+// qkv rows of 3 * Cw, n_head heads of HD = Cw / n_head features.
+template <typename TA>
+void launch_attention_seq(tante_handle_s* h, const TA* qkv, TA* out, int nseq, int S, int inner, int n_head, int Cw, int HD,
+                          bool causal_b, cudaStream_t st, const DropCfg& drop = DropCfg(), uint32_t site = 0) {
+    if (sizeof(TA) == 2 && drop.p <= 0.f) {
+        // long sequences (composite axes, 65 .. 96-token axes, channel tokens): tiled online-softmax kernel
+        cudaError_t e = cudaSuccess;
+        if (launch_attention_flash(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
+                                   inner, n_head, Cw, HD, causal_b, st, &e)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
+    if (sizeof(TA) == 2) {
+        cudaError_t e = cudaSuccess;
+        if (launch_attention_mma(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
+                                 inner, n_head, Cw, HD, causal_b, st, &e, drop, site)) {
+            CK(e);
+            h->launches++;
+            return;
+        }
+    }
+    const long long total = (long long)nseq * n_head * S;
+    REQUIRE((total + 127) / 128 < (1LL << 31), "attention grid too large");
+    const int blocks = (int)((total + 127) / 128);
+    const float scale = 1.0f / sqrtf((float)HD);
+    const int causal = causal_b;
+#define ATT(HDv) axial_attention_kernel<TA, TA, HDv><<<blocks, 128, 0, st>>>(qkv, out, nseq, S, inner, n_head, Cw, causal, scale, drop, site)
+    if (HD == 32) ATT(32); else if (HD == 64) ATT(64); else ATT(16);
+#undef ATT
+    CK(cudaGetLastError());
+    h->launches++;
+}
+
 template <typename TA>
 void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axis, cudaStream_t st,
                       const DropCfg& drop = DropCfg(), uint32_t site = 0) {
@@ -587,34 +651,45 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
     else if (axis == 'L') { S = L; inner = 1; nseq = B * T; }               // (b t) (h w)
     else if (axis == 'Y') { S = T * Hp; inner = Wp; nseq = B * Wp; }        // (b w) (t h)
     else { S = T * L; inner = 1; nseq = B; }                                // 'A': b (t h w)
-    if (sizeof(TA) == 2 && drop.p <= 0.f) {
-        // long sequences (composite axes, 65 .. 96-token axes): tiled online-softmax kernel
-        cudaError_t e = cudaSuccess;
-        if (launch_attention_flash(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
-                                   inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e)) {
-            CK(e);
-            h->launches++;
-            return;
-        }
+    launch_attention_seq<TA>(h, qkv, out, nseq, S, inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, drop, site);
+}
+
+// One axis-'C' layer (attn_backbone.py:184-189; channel_axis.cuh) in place on the fp32 latent x [tokens][C]: lift every scalar to
+// E features, TransformerBlock(E) over the C channel tokens of each latent token, keep the last feature.  Runs in chunks of
+// h->chan_tokens latent tokens (rows = chunk * C) through the scratch buffers of tante_reserve.
+template <typename TA>
+void run_channel_layer(tante_handle_s* h, const LayerPlan& lp, float* x, int tokens, cudaStream_t st) {
+    const int C = h->C, E = lp.E, Hc = lp.Hc, nh = h->cfg.n_head;
+    float* xc = reinterpret_cast<float*>(h->cx.p);
+    TA* ln = reinterpret_cast<TA*>(h->cln.p);
+    TA* qkv = reinterpret_cast<TA*>(h->cqkv.p);
+    TA* att = reinterpret_cast<TA*>(h->catt.p);
+    TA* hid = reinterpret_cast<TA*>(h->chid.p);
+    REQUIRE(h->chan_tokens > 0 && xc, "channel-axis workspace not reserved");
+    const size_t lift_smem = ((size_t)(E / 4) * E + E + 10 * (size_t)(E / 4)) * sizeof(float);
+    for (int t0 = 0; t0 < tokens; t0 += h->chan_tokens) {
+        const int tc = std::min(h->chan_tokens, tokens - t0);
+        const int rows = tc * C;
+        float* xs = x + (size_t)t0 * C;
+        channel_lift_kernel<<<std::min((rows + 7) / 8, 16 * h->num_sms), 256, lift_smem, st>>>(
+            xs, AF(h, lp.cw0), AF(h, lp.cb0), AF(h, lp.cw2), AF(h, lp.cb2), xc, rows, E);
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_layernorm<TA>(h, xc, lp.ln1w, lp.ln1b, ln, rows, st, E);
+        EpiParams eq; eq.bias = AF(h, lp.inb);
+        gemm<TA>(h, EPI_BIAS, ln, E, lp.inw, qkv, 3 * E, false, rows, 3 * E, E, eq, st);
+        launch_attention_seq<TA>(h, qkv, att, tc, C, 1, nh, E, E / nh, false, st);
+        EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = xc; eo.ldr = E;
+        gemm<TA>(h, EPI_BIAS_RESID, att, E, lp.outw, xc, E, true, rows, E, E, eo, st);
+        launch_layernorm<TA>(h, xc, lp.ln2w, lp.ln2b, ln, rows, st, E);
+        EpiParams e0; e0.bias = AF(h, lp.m0b);
+        gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, E, lp.m0w, hid, Hc, false, rows, Hc, E, e0, st);
+        EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = xc; e2.ldr = E;
+        gemm<TA>(h, EPI_BIAS_RESID, hid, Hc, lp.m2w, xc, E, true, rows, E, Hc, e2, st);
+        channel_extract_kernel<<<(rows + 255) / 256, 256, 0, st>>>(xc, xs, rows, E);
+        CK(cudaGetLastError());
+        h->launches++;
     }
-    if (sizeof(TA) == 2) {
-        cudaError_t e = cudaSuccess;
-        if (launch_attention_mma(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), nseq, S,
-                                 inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e, drop, site)) {
-            CK(e);
-            h->launches++;
-            return;
-        }
-    }
-    const long long total = (long long)nseq * h->cfg.n_head * S;
-    const int blocks = (int)((total + 127) / 128);
-    const float scale = 1.0f / sqrtf((float)h->HD);
-    const int causal = axis == 'T';
-#define ATT(HDv) axial_attention_kernel<TA, TA, HDv><<<blocks, 128, 0, st>>>(qkv, out, nseq, S, inner, h->cfg.n_head, h->C, causal, scale, drop, site)
-    if (h->HD == 32) ATT(32); else if (h->HD == 64) ATT(64); else ATT(16);
-#undef ATT
-    CK(cudaGetLastError());
-    h->launches++;
 }
 
 void launch_propagator(tante_handle_s* h, const float* xin, float* x, int B, int axis /*0=H,1=W,2=T*/,
@@ -1052,13 +1127,20 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         bool ln_ready = false;
         for (size_t li = 0; li < op.layers.size(); ++li) {
             const LayerPlan& lp = op.layers[li];
+            if (lp.axis == 'C') {      // channel attention: its own width, its own LayerNorms (channel_axis.cuh)
+                run_channel_layer<TA>(h, lp, x, tokens, st);
+                ln_ready = false;
+                continue;
+            }
+            // the next layer's LN1 rides in this layer's last epilogue -- unless that layer is a channel layer (other width)
+            const bool nx_ok = li + 1 < op.layers.size() && op.layers[li + 1].axis != 'C';
             if (!ln_ready) launch_layernorm<TA>(h, x, lp.ln1w, lp.ln1b, ln, tokens, st);
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, qkv, att, B, lp.axis, st);
             if constexpr (kFuseLN) {
                 if (h->fuse_tail && C == kBtC && h->Hm == C) {
-                    const LayerPlan* nx = li + 1 < op.layers.size() ? &op.layers[li + 1] : nullptr;
+                    const LayerPlan* nx = nx_ok ? &op.layers[li + 1] : nullptr;
                     launch_tail(h, lp, nx, att, x, x, ln, tokens, st);
                     ln_ready = nx != nullptr;
                     continue;
@@ -1075,7 +1157,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             EpiParams e0; e0.bias = AF(h, lp.m0b);
             gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, C, lp.m0w, hid, Hm, false, tokens, Hm, C, e0, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x; e2.ldr = C;
-            if (kFuseLN && li + 1 < op.layers.size() && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
+            if (kFuseLN && nx_ok && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
                 const LayerPlan& nx = op.layers[li + 1];
                 e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ln;
                 gemm<TA>(h, EPI_BIAS_RESID_LN, hid, Hm, lp.m2w, x, C, true, tokens, C, Hm, e2, st);
@@ -1806,6 +1888,7 @@ void set_smem_attrs() {
     static unsigned long long done = 0;
     if (!attrs_needed(done)) return;
     const int big = 160 * 1024;
+    CK(cudaFuncSetAttribute(channel_lift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     CK(cudaFuncSetAttribute(propagator_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(propagator_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(patch_embed_conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1979,7 +2062,7 @@ int tante_destroy(tante_handle_t h) {
         DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
                           &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
                           &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols, &h->wbuf, &h->dfield, &h->ftw,
-                          &h->fA, &h->fB, &h->fg0, &h->fg1, &h->fg2};
+                          &h->fA, &h->fB, &h->fg0, &h->fg1, &h->fg2, &h->cx, &h->cln, &h->cqkv, &h->catt, &h->chid};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
@@ -2133,6 +2216,16 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             dev_alloc(h, h->enc_state, ((size_t)2 * max_batch * h->T + 8) * 4);
         }
         if (h->debug) dev_alloc(h, h->dbg_in, tokens * C * 4);
+        if (h->chan) {
+            // channel pass: chunks of latent tokens, rows = chunk * C channel tokens of width E (about 3.5 KB per row in fp32)
+            h->chan_tokens = (int)std::min<size_t>(tokens, 2048);
+            const size_t rows = (size_t)h->chan_tokens * C;
+            dev_alloc(h, h->cx, rows * h->chanE * 4);
+            dev_alloc(h, h->cln, rows * h->chanE * es);
+            dev_alloc(h, h->cqkv, rows * 3 * h->chanE * es);
+            dev_alloc(h, h->catt, rows * h->chanE * es);
+            dev_alloc(h, h->chid, rows * h->chanHc * es);
+        }
         if (h->fno) {
             const size_t NI = (size_t)max_batch * h->T, HW = (size_t)h->cfg.H * h->cfg.W, HW1 = HW / (h->fp0 * h->fp0);
             const int C8 = C / 8;
@@ -2322,7 +2415,7 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
         REQUIRE(!h->wide, "training at patch_scale 16/32/64 is not implemented (inference / rollout only)");
-        REQUIRE(!h->long_axes, "training with attention axes L / Y / A or an axis longer than 64 tokens is not implemented "
+        REQUIRE(!h->long_axes, "training with attention axes L / Y / A / C or an axis longer than 64 tokens is not implemented "
                                "(inference / rollout only)");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);

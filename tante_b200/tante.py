@@ -122,7 +122,7 @@ class _Block(_ParamsOnly):           # TransformerBlock (attn_backbone.py:38-57)
 
 
 class _Backbone(_ParamsOnly):        # Attn_Backbone (attn_backbone.py:88-132)
-    def __init__(self, T, Hp, Wp, C, axes, n_head, mlp_ratio, dropout):
+    def __init__(self, T, Hp, Wp, C, axes, n_head, mlp_ratio, dropout, expanded_channel=128):
         super().__init__()
         if axes == "":
             raise ValueError("Invalid block: empty segment.")
@@ -131,8 +131,12 @@ class _Backbone(_ParamsOnly):        # Attn_Backbone (attn_backbone.py:88-132)
         self.horizontal_propagator = nn.Sequential(nn.Linear(Wp, Wp), nn.GELU(), nn.Linear(Wp, Wp))
         self.temporal_propagator = nn.Sequential(nn.Linear(T, T), nn.GELU(), nn.Linear(T, T))
         self.channel_blocks = nn.ModuleList()
-        for _ in axes:
-            self.blocks.append(_Block(C, n_head, mlp_ratio, dropout))
+        for axis in axes:
+            width = C
+            if axis == "C":       # channel attention: 1 -> expanded_channel lift, block of that width (attn_backbone.py:124-132)
+                width = expanded_channel
+                self.channel_blocks.append(nn.Sequential(nn.Linear(1, width // 4), nn.GELU(), nn.Linear(width // 4, width)))
+            self.blocks.append(_Block(width, n_head, mlp_ratio, dropout))
 
 
 class _Film(_ParamsOnly):            # film (tante.py:203-216)
@@ -189,6 +193,8 @@ class _Engine:
         cfg.enc_dec_fno = 1 if model.enc_dec_type == "fno" else 0
         cfg.modes1, cfg.modes2 = int(model.modes1), int(model.modes2)
         cfg.mlp_hidden = int(model.C * model.mlp_ratio)
+        cfg.expanded_channel = int(model.expanded_channel)
+        cfg.mlp_hidden_c = int(model.expanded_channel * model.mlp_ratio)
         for k, seg in enumerate(model.blocks_axes):
             if len(seg) > _abi.TANTE_MAX_LAYERS:
                 raise ValueError("too many layers in one attn_axes segment")
@@ -523,9 +529,15 @@ class TANTE(nn.Module):
                 raise NotImplementedError("enc_dec_type='fno': the kept modes must fit the grid at both resolutions "
                                           "(ps[0] <= modes, 2*modes1 <= H, modes2 <= W/2)")
         # what the CUDA library does not cover is refused HERE, not at the first forward
-        if "C" in self.attn_axes:
-            raise NotImplementedError("attention axis 'C' (channel attention with a 1 -> expanded_channel lift, "
-                                      "attn_backbone.py:126-130,184-189) is not implemented; supported: T, H, W, L, Y, A")
+        self.expanded_channel = int(expanded_channel)
+        if "C" in self.attn_axes:      # channel attention (attn_backbone.py:124-130,184-189): inference / rollout
+            E = self.expanded_channel
+            hc = int(E * float(mlp_ratio))
+            if E % 64 or not 64 <= E <= 256 or n_head <= 0 or E % n_head or E // n_head not in (16, 32, 64):
+                raise NotImplementedError("attention axis 'C': expanded_channel must be a multiple of 64 in 64..256 with "
+                                          "expanded_channel / n_head in (16, 32, 64)")
+            if hc < 64 or hc > 1024 or hc % 64:
+                raise NotImplementedError("attention axis 'C': int(expanded_channel * mlp_ratio) must be a multiple of 64 in 64..1024")
         if embed_dim != 256:
             raise NotImplementedError("the CUDA kernels are specialised for embed_dim = 256 (configs/tante.yaml:31)")
         if n_head <= 0 or embed_dim % n_head or embed_dim // n_head not in (16, 32, 64):
@@ -551,7 +563,7 @@ class TANTE(nn.Module):
                 self.decoders.append(_DecCNN(self.n_channel, embed_dim, ks))
         self.blocks = nn.ModuleList()
         for seg in self.blocks_axes:
-            self.blocks.append(_Backbone(self.T, self.H_p, self.W_p, self.C, seg, n_head, mlp_ratio, dropout))
+            self.blocks.append(_Backbone(self.T, self.H_p, self.W_p, self.C, seg, n_head, mlp_ratio, dropout, expanded_channel))
         self.t_emb = nn.Parameter(_t_emb_init(self.C, self.T))
         self.s_emb = nn.Parameter(_s_emb_init(self.C, self.H_p, self.W_p))
         self.t_encode = _Film(self.C)

@@ -74,6 +74,7 @@ def test_create_validates_like_the_reference_ctor():
 @pytest.mark.parametrize("kw", [
     dict(taylor_order=1, attn_axes="THWTHWTHW", deg=True),
     dict(taylor_order=2, attn_axes="THW-HWT", deg=False),
+    dict(taylor_order=2, attn_axes="TCW-CHC", deg=False),      # channel attention: channel_blocks + blocks of width expanded_channel
 ])
 def test_param_table_matches_module_state_dict(kw):
     m = TANTE(4, TanteMetadata(spatial_resolution=(64, 96), n_fields=3), patch_scale=8, **kw)
@@ -109,7 +110,8 @@ def test_default_init_and_state_dict_equal_the_reference():
     ns = ref_shim.load_reference()
     md = ref_shim.make_metadata(3, 64, 96)
     for kw in (dict(taylor_order=1, attn_axes="THWTHW", deg=True), dict(taylor_order=2, attn_axes="THW-HW", deg=False),
-               dict(taylor_order=2, attn_axes="TH-W", deg=False, enc_dec_type="fno", modes1=16, modes2=16)):
+               dict(taylor_order=2, attn_axes="TH-W", deg=False, enc_dec_type="fno", modes1=16, modes2=16),
+               dict(taylor_order=2, attn_axes="TCW-CH", deg=False, expanded_channel=256, mlp_ratio=2.0)):
         torch.manual_seed(211)
         ref = ns.TANTE(in_T=4, dset_metadata=md, patch_scale=8, dropout=0.1, **kw)
         torch.manual_seed(211)

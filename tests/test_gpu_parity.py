@@ -320,7 +320,9 @@ NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d1
         # enc_dec_type = 'fno' (enc_dec_fno.py): spectral layers as truncated DFTs (fno.cuh)
         "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16",
         # mlp_ratio 2 / 0.5 (attn_backbone.py:52-56): the block MLP as two GEMMs of width int(C * mlp_ratio)
-        "fwd_adp_k2_mlp2", "fwd_deg_k1_mlp05"]
+        "fwd_adp_k2_mlp2", "fwd_deg_k1_mlp05",
+        # attention axis 'C' (attn_backbone.py:124-130,184-189): channel tokens behind the 1 -> expanded_channel lift
+        "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64"]
 
 
 @pytest.mark.parametrize("name", NEXT)
@@ -353,7 +355,7 @@ def test_next_scope_forward_and_rollout_fp32(name):
 
 @pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
                                   "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16", "fwd_adp_k2_mlp2",
-                                  "fwd_deg_k1_mlp05"])
+                                  "fwd_deg_k1_mlp05", "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64"])
 def test_next_scope_forward_bf16(name):
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
     with torch.inference_mode():
@@ -369,7 +371,8 @@ def test_next_scope_forward_bf16(name):
 
 def test_training_refused_for_inference_only_scopes():
     from gpu_util import make_model
-    for kw in (dict(patch_scale=16, attn_axes="TH"), dict(attn_axes="LT"), dict(attn_axes="TH", enc_dec_type="fno", modes1=8, modes2=8)):
+    for kw in (dict(patch_scale=16, attn_axes="TH"), dict(attn_axes="LT"), dict(attn_axes="CT"),
+               dict(attn_axes="TH", enc_dec_type="fno", modes1=8, modes2=8)):
         cfg = O.OracleConfig(n_fields=2, H=64, W=64, taylor_order=1, deg=True, **kw)
         model = make_model(cfg, O.make_state_dict(cfg, 1)).train()
         with pytest.raises(Exception, match="not implemented"):

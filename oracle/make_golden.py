@@ -223,6 +223,13 @@ def main_axisc(ns):
                  B=1, out_T=1, rt_bias=0.0, n_roll=2)
 
 
+def main_train_long(ns):
+    """One training step (r_trainer.py:112-159) with the composite attention axes L / Y / A (sequences of 96 / 32 / 384 tokens)."""
+    C = O.OracleConfig
+    case_train(ns, "train_adp_k2_lya", C(n_fields=2, H=64, W=96, taylor_order=2, attn_axes="LTY-AW", deg=False), B=2, n_steps=3,
+               rt_bias=0.0)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -249,6 +256,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--trainlong" in sys.argv:
+        main_train_long(ns)
         return
     if "--axisc" in sys.argv:
         main_axisc(ns)

@@ -781,6 +781,102 @@ __global__ void __launch_bounds__(256) propagator_bwd_kernel(const float* __rest
     for (int j = threadIdx.x; j < S; j += blockDim.x) { atomicAdd(gb1 + j, rb[j]); atomicAdd(gb2 + j, rb[S4 + j]); }
 }
 
+// ---- propagator backward for axes of 65 .. 96 tokens ---------------------------------------------------------------
+// The tiled kernel above needs a power-of-two axis of at most 64 rows; this one keeps both S x S matrices and a slab of 32
+// columns in shared memory and lets one lane own one column (warp w: rows w, w + 8, ...).  Weight gradients: thread t owns the
+// entries t, t + 256, ... of the two S x S matrices, accumulated in registers over the slabs of a persistent CTA and flushed with
+// one atomic per entry.  Same math as propagator_bwd_kernel.
+constexpr int kPropWideMaxS = 96;
+constexpr int kPropWideCols = 32;
+constexpr int kPropWidePitch = kPropWideCols + 1;
+constexpr int kPropWidePairs = (kPropWideMaxS * kPropWideMaxS + 255) / 256;
+static inline size_t prop_bwd_wide_smem(int S) { return ((size_t)4 * S * kPropWidePitch + (size_t)2 * S * S + S) * sizeof(float); }
+template <typename TM>
+__global__ void __launch_bounds__(256) propagator_bwd_wide_kernel(const float* __restrict__ xin, float* __restrict__ dy, int S,
+                                                                  long long IC, long long n_outer, const float* __restrict__ W1,
+                                                                  const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                  float* __restrict__ gW1, float* __restrict__ gb1,
+                                                                  float* __restrict__ gW2, float* __restrict__ gb2) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int CP = kPropWidePitch;
+    float* sx = smem;               // [S][33] x
+    float* sd = sx + S * CP;        // dy
+    float* sp = sd + S * CP;        // pre -> dpre
+    float* sh = sp + S * CP;        // h
+    float* w1 = sh + S * CP;        // [S][S] W1[j][i]
+    float* w2 = w1 + S * S;         // [S][S] W2[j][i]
+    float* sb1 = w2 + S * S;        // [S]
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) { w1[i] = W1[i]; w2[i] = W2[i]; }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sb1[i] = b1[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float aw1[kPropWidePairs], aw2[kPropWidePairs];
+#pragma unroll
+    for (int k = 0; k < kPropWidePairs; ++k) aw1[k] = aw2[k] = 0.f;
+    float ab1 = 0.f, ab2 = 0.f;
+    const long long ncb = (IC + kPropWideCols - 1) / kPropWideCols;
+    const long long nslab = n_outer * ncb;
+    for (long long slab = blockIdx.x; slab < nslab; slab += gridDim.x) {
+        const long long outer = slab / ncb;
+        const long long col0 = (slab % ncb) * kPropWideCols;
+        const int ncol = (int)min((long long)kPropWideCols, IC - col0);
+        const float* xb = xin + (size_t)outer * S * IC + col0;
+        float* db = dy + (size_t)outer * S * IC + col0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < S * kPropWideCols; i += blockDim.x) {
+            const int p = i / kPropWideCols, c = i % kPropWideCols;
+            const bool ok = c < ncol;
+            sx[p * CP + c] = ok ? xb[(size_t)p * IC + c] : 0.f;
+            sd[p * CP + c] = ok ? db[(size_t)p * IC + c] : 0.f;
+        }
+        __syncthreads();
+        // pre = W1 x + b1, h = gelu(pre);  dh[i] = sum_j W2[j][i] dy[j], dpre = dh * gelu'(pre)  (row i: the same warp, same lane)
+        for (int j = warp; j < S; j += 8) {
+            float acc = sb1[j], dh = 0.f;
+            for (int i = 0; i < S; ++i) {
+                acc = fmaf(w1[j * S + i], sx[i * CP + lane], acc);
+                dh = fmaf(w2[i * S + j], sd[i * CP + lane], dh);
+            }
+            sh[j * CP + lane] = ActMath<TM>::gelu_erf_f(acc);
+            sp[j * CP + lane] = dh * ActMath<TM>::gelu_erf_g(acc);
+        }
+        __syncthreads();
+        // dx[i] = dy[i] + sum_j W1[j][i] dpre[j]
+        for (int i = warp; i < S; i += 8) {
+            float acc = sd[i * CP + lane];
+            for (int j = 0; j < S; ++j) acc = fmaf(w1[j * S + i], sp[j * CP + lane], acc);
+            if (lane < ncol) db[(size_t)i * IC + lane] = acc;
+        }
+        // weight gradients: gW2[j][i] += sum_c dy[j][c] h[i][c];  gW1[j][i] += sum_c dpre[j][c] x[i][c]  (padding columns hold zeros)
+#pragma unroll
+        for (int k = 0; k < kPropWidePairs; ++k) {
+            const int q = threadIdx.x + 256 * k;
+            if (q < S * S) {
+                const int j = q / S, i = q % S;
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+                for (int c = 0; c < kPropWideCols; ++c) {
+                    a2 = fmaf(sd[j * CP + c], sh[i * CP + c], a2);
+                    a1 = fmaf(sp[j * CP + c], sx[i * CP + c], a1);
+                }
+                aw1[k] += a1;
+                aw2[k] += a2;
+            }
+        }
+        if (threadIdx.x < S) {
+            float a1 = 0.f, a2 = 0.f;
+            for (int c = 0; c < kPropWideCols; ++c) { a2 += sd[threadIdx.x * CP + c]; a1 += sp[threadIdx.x * CP + c]; }
+            ab1 += a1;
+            ab2 += a2;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kPropWidePairs; ++k) {
+        const int q = threadIdx.x + 256 * k;
+        if (q < S * S) { atomicAdd(gW1 + q, aw1[k]); atomicAdd(gW2 + q, aw2[k]); }
+    }
+    if (threadIdx.x < S) { atomicAdd(gb1 + threadIdx.x, ab1); atomicAdd(gb2 + threadIdx.x, ab2); }
+}
+
 // ---- Taylor head backward (tante.py:156-171 + dec_conv_3, enc_dec_cnn.py:273) ---------------------------
 // frames_i = u0 + sum_k d_k c_ik, c_ik = (i*fi)^k/k!.  One thread per stage-1 row (k0 x k0 x D outputs) gathers
 //   Gk[o]  = sum_{i<=n_b} gframes_i[o] * c_ik   -> G[k][row][kHeadPad]  (TA, zero-padded to 64 columns)

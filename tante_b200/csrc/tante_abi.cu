@@ -27,6 +27,7 @@
 #include "pack.cuh"
 #include "backward.cuh"
 #include "attention_bwd_mma.cuh"
+#include "attention_long_bwd.cuh"
 #include "wgrad_tc.cuh"
 #include "metrics.cuh"
 #include "block_tail_tc.cuh"
@@ -208,7 +209,7 @@ struct tante_handle_s {
     DevBuf garena, tdesc_dev, udesc_dev;
     std::vector<std::unique_ptr<Tape>> tapes;
     int bw_batch = 0;
-    DevBuf dxs, dxb, g1, g2, gq, ga1, cols, hz, hG, hz1, hd, hi1, hi2, dfilm, dcond;
+    DevBuf dxs, dxb, g1, g2, gq, ga1, cols, hz, hG, hz1, hd, hi1, hi2, dfilm, dcond, att_stats;
     // ---- optimizer tail (optimizer.cuh) ----
     DevBuf opt_segs, opt_norm;                 // parameter segments of the flat gradient; f64 sum of squares
     std::vector<char> opt_seg_cache;
@@ -1341,7 +1342,20 @@ void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* 
     const int T = h->T, L = h->L, Hp = h->Hp, Wp = h->Wp;
     if (axis == 'T') { S = T; inner = L; nseq = (long long)B * L; }
     else if (axis == 'H') { S = Hp; inner = Wp; nseq = (long long)B * T * Wp; }
-    else { S = Wp; inner = 1; nseq = (long long)B * T * Hp; }
+    else if (axis == 'W') { S = Wp; inner = 1; nseq = (long long)B * T * Hp; }
+    else if (axis == 'L') { S = L; inner = 1; nseq = (long long)B * T; }               // (b t) (h w)
+    else if (axis == 'Y') { S = T * Hp; inner = Wp; nseq = (long long)B * Wp; }        // (b w) (t h)
+    else { S = T * L; inner = 1; nseq = B; }                                           // 'A': b (t h w)
+    if (S > 64) {
+        // composite axes and 65 .. 96-token axes: tiled recompute backward (attention_long_bwd.cuh), both precisions
+        cudaError_t e = cudaSuccess;
+        REQUIRE(launch_attention_long_bwd<TA>(qkv, dout, dqkv, FP(h->att_stats), nseq, S, inner, h->cfg.n_head, h->C, h->HD,
+                                              axis == 'T', st, &e, drop, site),
+                "attention backward: sequence shape not covered");
+        CK(e);
+        h->launches += 3;
+        return;
+    }
     if constexpr (sizeof(TA) == 2) {
         cudaError_t e = cudaSuccess;
         if (launch_attention_bwd_mma(qkv, dout, dqkv, nseq, S, inner, h->cfg.n_head, h->C, h->HD, axis == 'T', st, &e, drop, site)) {
@@ -1394,6 +1408,26 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
             h->launches++;
             return;
         }
+    }
+    if (S > 64) {      // 65 .. 96-token axes: the one-lane-per-column kernel (both S x S matrices in shared memory)
+        REQUIRE(S <= kPropWideMaxS, "propagator backward: axis longer than 96 tokens");
+        const long long nslabw = outer * ((IC + kPropWideCols - 1) / kPropWideCols);
+        const unsigned gridw = (unsigned)std::min<long long>(nslabw, 2LL * h->num_sms);
+        const size_t smw = prop_bwd_wide_smem(S);
+        if (h->cfg.precision == TANTE_PREC_BF16) {
+            CK(cudaFuncSetAttribute(propagator_bwd_wide_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+            propagator_bwd_wide_kernel<__nv_bfloat16><<<gridw, 256, smw, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                                                              AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
+                                                                              GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));
+        } else {
+            CK(cudaFuncSetAttribute(propagator_bwd_wide_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+            propagator_bwd_wide_kernel<float><<<gridw, 256, smw, st>>>(xin, dy, S, IC, outer, AF(h, op.prop[axis][0]), AF(h, op.prop[axis][1]),
+                                                                      AF(h, op.prop[axis][2]), GA(h, op.prop[axis][0]), GA(h, op.prop[axis][1]),
+                                                                      GA(h, op.prop[axis][2]), GA(h, op.prop[axis][3]));
+        }
+        CK(cudaGetLastError());
+        h->launches++;
+        return;
     }
     int S4 = (S + 3) & ~3;
     if (S4 > 4 && (S4 & (S4 - 1))) { int p2 = 8; while (p2 < S4) p2 <<= 1; S4 = p2; }
@@ -1500,6 +1534,7 @@ void backward_alloc(tante_handle_s* h, int B) {
     dev_alloc(h, h->hi2, BL * (C / 4) * es);
     dev_alloc(h, h->dfilm, (size_t)std::max(B, h->T) * 2 * C * 4);
     dev_alloc(h, h->dcond, (size_t)B * 4);
+    if (h->long_axes) dev_alloc(h, h->att_stats, tokens * h->cfg.n_head * 2 * 4);      // LSE + delta per (token, head)
     if (!h->udesc_dev.p) {
         std::vector<UnpackDesc> ud;
         for (const Param& p : h->params) {
@@ -2066,7 +2101,7 @@ int tante_destroy(tante_handle_t h) {
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
-                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->opt_segs, &h->opt_norm};
+                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->opt_segs, &h->opt_norm};
         for (DevBuf* b : tb) b->free();
         if (h->nccl_comm && nccl_api().ok()) nccl_api().CommDestroy(h->nccl_comm);
         for (auto& tp : h->tapes) free_tape(*tp);
@@ -2415,7 +2450,7 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
         REQUIRE(!h->wide, "training at patch_scale 16/32/64 is not implemented (inference / rollout only)");
-        REQUIRE(!h->long_axes, "training with attention axes L / Y / A / C or an axis longer than 64 tokens is not implemented "
+        REQUIRE(!h->chan, "training with the attention axis C is not implemented "
                                "(inference / rollout only)");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);
@@ -2475,7 +2510,7 @@ int tante_train_forward_win(tante_handle_t h, int32_t slot, const float* const* 
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
-        REQUIRE(!h->wide && !h->fno && !h->long_axes, "training is not implemented for this configuration (inference / rollout only)");
+        REQUIRE(!h->wide && !h->fno && !h->chan, "training is not implemented for this configuration (inference / rollout only)");
         for (int t = 0; t < h->T; ++t) REQUIRE(frame_ptrs[t], "null frame pointer");
         REQUIRE(frames_bstride % 4 == 0, "frames_bstride must be a multiple of 4 elements");
         CK(cudaSetDevice(h->device));

@@ -230,6 +230,15 @@ def main_train_long(ns):
                rt_bias=0.0)
 
 
+def main_train_wide(ns):
+    """Training steps at patch_scale 16 / 32 (shifted 4x4 windows + bilinear resize, enc_dec_cnn.py:75-81,93-95,176-184)."""
+    C = O.OracleConfig
+    case_train(ns, "train_adp_k2_p16", C(n_fields=3, H=64, W=96, taylor_order=2, attn_axes="THW-WT", deg=False, patch_scale=16),
+               B=2, n_steps=3, rt_bias=0.0)
+    case_train(ns, "train_deg_k1_p32", C(n_fields=4, H=128, W=192, taylor_order=1, attn_axes="THW", deg=True, patch_scale=32),
+               B=2, n_steps=3)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -256,6 +265,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--trainwide" in sys.argv:
+        main_train_wide(ns)
         return
     if "--trainlong" in sys.argv:
         main_train_long(ns)

@@ -344,6 +344,7 @@ void build_plan(tante_handle_s* h) {
         if (i > 0) h->enc_wT[i] = add_trans(h, h->enc_w[i], ech[i + 1], ech[i] * k[i] * k[i]);
         else if (h->wide) {
             h->enc_w1wide = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 0, ech[1], h->K1pad);   // [C1][K1pad]
+            h->enc_wT[0] = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 1, h->K1pad, ech[1]);    // [K1pad][C1] (input gradient)
         } else {
             REQUIRE(k[0] * k[0] * D <= kHeadPad, "n_fields too large for the padded first-conv backward (k0*k0*D <= 64)");
             h->enc_wT[0] = add_trans(h, h->enc_w[0], ech[1], k[0] * k[0] * D, 1, kHeadPad, ech[1]);   // [64 (K1 pad)][C1]
@@ -452,6 +453,7 @@ void build_plan(tante_handle_s* h) {
                 h->garena_elems += (bp3.gnumel + 63) / 64 * 64;
                 if (h->wide) {
                     op.w3nk = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 1, h->NOpad, dch[i]);   // [NOpad][C1]
+                    op.w3pad = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 0, dch[i], h->NOpad);  // [C1][NOpad] (dz = G * W3^T)
                 } else {
                     // [C1][64]: the packed [C1][k0*k0*D] weight zero-padded along its columns (dz = G * W3^T as a GEMM)
                     op.w3pad = add_trans(h, op.decw[i], dch[i], kk * kk * dch[i + 1], 0, dch[i], kHeadPad);
@@ -1294,6 +1296,19 @@ template <typename TA>
 void gemm_dx(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* out, int ldc, int M, int N, int K, cudaStream_t st) {
     EpiParams ep; ep.bias = AF(h, h->zero_off);
     REQUIRE(N <= 4096, "input-gradient GEMM wider than the zero-bias vector");
+    if (sizeof(TA) == 2 && K > 1024) {
+        // the tcgen05 GEMM keeps a K <= 1024 weight slice resident (K = 2048: first deconv of patch_scale 64): two K halves
+        // accumulated through an fp32 scratch, then one conversion pass
+        REQUIRE(K % 128 == 0 && K <= 2048 && ldc == N && (size_t)M * N * 4 <= h->gq.bytes, "input-gradient GEMM: K not covered");
+        float* v = FP(h->gq);
+        gemm<TA>(h, EPI_BIAS, A, lda, wT_off, v, N, true, M, N, K / 2, ep, st, K);
+        EpiParams e2; e2.bias = AF(h, h->zero_off); e2.resid = v; e2.ldr = N;
+        gemm<TA>(h, EPI_BIAS_RESID, A + K / 2, lda, wT_off + K / 2, v, N, true, M, N, K / 2, e2, st, K);
+        convert_kernel<TA><<<blocks_for((long long)M * N / 4, 256), 256, 0, st>>>(v, out, (long long)M * N / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        return;
+    }
     gemm<TA>(h, EPI_BIAS, A, lda, wT_off, out, ldc, sizeof(TA) == 4, M, N, K, ep, st);
 }
 
@@ -1469,7 +1484,7 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
     const size_t BL = (size_t)B * h->L;
     const int C = h->C, C1 = h->C1, C2 = h->C2;
     const PatchGeom& g = h->geom;
-    dev_alloc(h, tp.cols, tokens * g.R1 * kHeadPad * es);
+    dev_alloc(h, tp.cols, tokens * g.R1 * (size_t)std::max(kHeadPad, h->wide ? h->K1pad : 0) * es);
     dev_alloc(h, tp.a1pre, tokens * g.R1 * C1 * es);
     dev_alloc(h, tp.a1act, tokens * g.R1 * C1 * es);
     dev_alloc(h, tp.a2pre, tokens * g.R2 * C2 * es);
@@ -1527,7 +1542,7 @@ void backward_alloc(tante_handle_s* h, int B) {
     (void)NO;
     dev_alloc(h, h->cols, tokens * g.R1 * kHeadPad * es);
     dev_alloc(h, h->hz, (size_t)h->K * BL * g.R1 * C1 * es);
-    dev_alloc(h, h->hG, (size_t)h->K * BL * g.R1 * kHeadPad * es);
+    dev_alloc(h, h->hG, (size_t)h->K * BL * g.R1 * (size_t)std::max(kHeadPad, h->wide ? h->NOpad : 0) * es);
     dev_alloc(h, h->hz1, BL * g.R2 * C2 * es);
     dev_alloc(h, h->hd, BL * C * es);
     dev_alloc(h, h->hi1, BL * (C / 2) * es);
@@ -1567,7 +1582,48 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     if (drop.p > 0.f && kTensor && !(h->fuse_tail && C == kBtC && h->Hm == C))
         throw Error(TANTE_ERR_INVALID, "dropout in the tensor mode needs the fused block tail (TANTE_FUSE_TAIL=1, embed_dim 256)");
     // --- encoder ---
-    {
+    if (h->wide) {
+        // patch_scale 16 / 32 / 64 (wide_patch.cuh): natural-order stages, window gathers + GEMMs; the first patch matrix and every
+        // pre-activation / activation grid are kept for the backward
+        REQUIRE(!win, "windowed BPTT is not available at patch_scale >= 16");
+        const int H = h->cfg.H, W = h->cfg.W, D = h->D;
+        TA* wb = TP<TA>(h->wbuf);
+        const int H1 = H / g.k0, W1 = W / g.k0, H2 = H1 / g.k1, W2 = W1 / g.k1;
+        const long long rows1 = (long long)B * T * H1 * W1, rows2 = (long long)B * T * H2 * W2;
+        REQUIRE(rows1 < (1LL << 31), "input too large for the wide first-conv GEMM");
+        const long long total = rows1 * h->K1pad;
+        wide_im2col_cf_kernel<TA><<<blocks_for(total, 256), 256, 0, st>>>(input, nullptr, T, D, H, W, g.k0, (g.k0 - 1) / 2, h->K1pad,
+                                                                         TP<TA>(tp.cols), total);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
+        gemm<TA>(h, EPI_BIAS, TP<TA>(tp.cols), h->K1pad, h->enc_w1wide, tp.a1pre.p, C1, false, (int)rows1, C1, h->K1pad, e1, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), rows1 * C1, st);
+        const int K2 = g.k1 * g.k1 * C1, K3 = g.k2 * g.k2 * C2;
+        wide_im2col_cl_kernel<TA><<<blocks_for(rows2 * K2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a1act), H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb,
+                                                                                  rows2 * K2 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
+        gemm<TA>(h, EPI_BIAS, wb, K2, h->enc_w[1], tp.a2pre.p, C2, false, (int)rows2, C2, K2, e2, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a2pre), TP<TA>(tp.a2act), rows2 * C2, st);
+        wide_im2col_cl_kernel<TA><<<blocks_for((long long)tokens * K3 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H2, W2, C2, g.k2,
+                                                                                              (g.k2 - 1) / 2, wb, (long long)tokens * K3 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
+        if (kTensor && K3 > 1024) {      // (K = 2048 at patch_scale 64: two K halves, as in run_encoder_wide)
+            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], tp.v.p, C, true, tokens, C, K3 / 2, e3, st, K3);
+            EpiParams e4; e4.bias = AF(h, h->zero_off); e4.resid = FP(tp.v); e4.ldr = C;
+            gemm<TA>(h, EPI_BIAS_RESID, wb + K3 / 2, K3, h->enc_w[2] + K3 / 2, tp.v.p, C, true, tokens, C, K3 / 2, e4, st, K3);
+        } else {
+            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], tp.v.p, C, true, tokens, C, K3, e3, st);
+        }
+        embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(
+            FP(tp.v), AF(h, h->film_t_off), AF(h, h->s_emb), AF(h, h->t_emb), FP(tp.ord[0].P[0]), tokens, T, L, C);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
         // enc_conv_1 as im2col (kept for the weight gradient) + GEMM over the zero-padded patch matrix
         const long long rows_in = (long long)tokens * g.R1;
         REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv GEMM");
@@ -1671,6 +1727,35 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             h->launches++;
             dmod = TP<TA>(ot.dmod);
         }
+        if (h->wide) {
+            // decoder stage = GEMM to the sub-pixel matrix -> crop + bilinear resample to the grid (pre-activation kept) -> GELU
+            TA* wb = TP<TA>(h->wbuf);
+            const int Hp = h->Hp, Wp = h->Wp, D = h->D;
+            const int H2 = Hp * g.k2, W2 = Wp * g.k2, H1 = H2 * g.k1, W1 = W2 * g.k1;
+            const int N1 = g.k2 * g.k2 * C2, N2 = g.k1 * g.k1 * C1;
+            float* field = FP(h->dfield) + (size_t)o * B * D * h->cfg.H * h->cfg.W;
+            EpiParams ew; ew.bias = AF(h, op.decb[0]);
+            gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ew, st);
+            long long tot = (long long)B * H2 * W2 * C2;
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N1, Hp, Wp, C2, g.k2, nullptr, TP<TA>(ot.z1pre), nullptr, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z1pre), TP<TA>(ot.z1act), tot, st);
+            ew.bias = AF(h, op.decb[1]);
+            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z1act), C2, op.decw[1], wb, N2, false, B * H2 * W2, N2, C2, ew, st);
+            tot = (long long)B * H1 * W1 * C1;
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N2, H2, W2, C1, g.k1, nullptr, TP<TA>(ot.z2pre), nullptr, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z2pre), TP<TA>(ot.z2act), tot, st);
+            EpiParams e3; e3.bias = AF(h, h->zero_off);
+            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z2act), C1, op.w3nk, wb, h->NOpad, false, B * H1 * W1, h->NOpad, C1, e3, st);
+            tot = (long long)B * D * h->cfg.H * h->cfg.W;
+            wide_deconv_post_kernel<TA, false, true><<<blocks_for(tot, 256), 256, 0, st>>>(wb, h->NOpad, H1, W1, D, g.k0, AF(h, op.decb[2]), nullptr, field, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            continue;
+        }
         EpiParams ed; ed.bias = AF(h, op.decb[0]);
         gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], ot.z1pre.p, g.k2 * g.k2 * C2, false, B * L, g.k2 * g.k2 * C2, C, ed, st);
         launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z1pre), TP<TA>(ot.z1act), (long long)B * L * g.R2 * C2, st);
@@ -1685,6 +1770,19 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     CK(cudaGetLastError());
     h->launches++;
     CK(cudaMemcpyAsync(tp.n_arr.p, h->nbuf.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    if (h->wide) {      // Horner sum + residual over the decoded derivative fields (boundary C)
+        EmitParams ep{};
+        ep.dfield = FP(h->dfield);
+        ep.K = K; ep.fi = h->cfg.frame_interval;
+        ep.u_ring = input; ep.fcount = nullptr;
+        ep.n_arr = reinterpret_cast<int*>(h->nbuf.p);
+        ep.frames = frames; ep.n_cap = n_cap;
+        ep.B = B; ep.D = h->D; ep.T = T; ep.HW = (long long)h->cfg.H * h->cfg.W;
+        REQUIRE(ep.HW % 4 == 0, "H * W must be a multiple of 4");
+        taylor_emit_kernel<<<dim3(blocks_for(ep.HW / 4, 256), (unsigned)h->D, (unsigned)B), 256, 0, st>>>(ep);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else
     // fused Taylor head on the kept stage-1 activations
     {
         HeadParams hp{};
@@ -1750,7 +1848,20 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     if (grad_input && !win) CK(cudaMemsetAsync(grad_input, 0, in_elems * 4, st));
 
     // ---- Taylor head: all orders in one pass over the frame gradients ----
-    {
+    if (h->wide) {
+        // field-level emit (boundary C): gradient of every order's derivative field + of u0, from the frame gradients
+        REQUIRE(!win, "windowed BPTT is not available at patch_scale >= 16");
+        EmitBwdParams ep{};
+        ep.gframes = gframes; ep.gf_bs = (long long)n_g * D * h->cfg.H * h->cfg.W;
+        ep.n_arr = reinterpret_cast<const int*>(tp.n_arr.p); ep.n_g = n_g;
+        ep.gfield = FP(h->dfield);
+        ep.gu0 = grad_input ? grad_input + (size_t)(T - 1) * D * h->cfg.H * h->cfg.W : nullptr;
+        ep.gu0_bs = (long long)T * D * h->cfg.H * h->cfg.W;
+        ep.K = K; ep.fi = h->cfg.frame_interval; ep.B = B; ep.D = D; ep.HW = (long long)h->cfg.H * h->cfg.W;
+        taylor_emit_bwd_kernel<<<dim3(blocks_for(ep.HW / 4, 256), (unsigned)D, (unsigned)B), 256, 0, st>>>(ep);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
         HeadBwdParams hp{};
         for (int k = 0; k < K; ++k) hp.G[k] = TP<TA>(h->hG) + (size_t)k * rows1 * kHeadPad;
         hp.K = K; hp.fi = h->cfg.frame_interval; hp.gframes = gframes; hp.n_cap = n_g;
@@ -1774,22 +1885,52 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         const OrderPlan& op = h->orders[o];
         OrderTape& ot = tp.ord[o];
         TA* dz = TP<TA>(h->hz) + (size_t)o * rows1 * C1;
+        const int M2 = BL * g.R2, N2 = g.k1 * g.k1 * C1;
+        const int N1 = g.k2 * g.k2 * C2;
+        TA* dz1 = TP<TA>(h->hz1);
+        TA* dmod = h->cfg.deg ? TP<TA>(ot.dl) : TP<TA>(ot.dmod);
+        TA* hd = TP<TA>(h->hd);
+        if (h->wide) {
+            // natural-order stages (wide_patch.cuh): transpose of (crop + bilinear resample) back to the sub-pixel matrix, then the
+            // same weight / input gradient GEMMs as below, stage by stage
+            TA* wb = TP<TA>(h->wbuf);
+            TA* G = TP<TA>(h->hG);                                   // dS3 [rows1][NOpad]
+            const int NP = h->NOpad;
+            const int Hp = h->Hp, Wp = h->Wp;
+            const int H2 = Hp * g.k2, W2 = Wp * g.k2, H1 = H2 * g.k1, W1 = W2 * g.k1;
+            const float* gf = FP(h->dfield) + (size_t)o * B * D * h->cfg.H * h->cfg.W;
+            long long tot = rows1 * NP;
+            wide_deconv_post_bwd_kernel<TA, true><<<blocks_for(tot, 256), 256, 0, st>>>(nullptr, gf, NP, H1, W1, D, g.k0, G, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            wgrad_pad<TA>(h, TP<TA>(ot.z2act), C1, C1, G, NP, NP, GA(h, op.decw[2]), NO, NO, rows1, st);
+            launch_colsum<TA>(h, G, NP, rows1, NO, GA(h, op.decb[2]), st);
+            gemm_dx_act<TA, ACT_GELU_ERF>(h, G, NP, op.w3pad, dz, TP<TA>(ot.z2pre), (int)rows1, C1, NP, st);
+            tot = (long long)M2 * N2;
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(dz, nullptr, N2, H2, W2, C1, g.k1, wb, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            wgrad<TA>(h, wb, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st, GA(h, op.decb[1]));
+            gemm_dx_act<TA, ACT_GELU_ERF>(h, wb, N2, op.decwT[1], dz1, TP<TA>(ot.z1pre), M2, C2, N2, st);
+            tot = (long long)BL * N1;
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(dz1, nullptr, N1, Hp, Wp, C2, g.k2, wb, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            wgrad<TA>(h, wb, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st, GA(h, op.decb[0]));
+            gemm_dx<TA>(h, wb, N1, op.decwT[0], hd, C, BL, C, N1, st);
+        } else {
         TA* G = TP<TA>(h->hG) + (size_t)o * rows1 * kHeadPad;
         // dec_conv_3: d_k = z2act * W3 + b3  ->  dW3 = z2act^T G, db3 = colsum(G), dz2 = (G W3^T) o gelu'(z2pre)
         wgrad_pad<TA>(h, TP<TA>(ot.z2act), C1, C1, G, kHeadPad, kHeadPad, GA(h, op.decw[2]), NO, NO, rows1, st);
         launch_colsum<TA>(h, G, kHeadPad, rows1, NO, GA(h, op.decb[2]), st);
         gemm_dx_act<TA, ACT_GELU_ERF>(h, G, kHeadPad, op.w3pad, dz, TP<TA>(ot.z2pre), (int)rows1, C1, kHeadPad, st);
         // dec_conv_2: z2pre[M2, N2] = z1act[M2, C2] * Wd2^T + b
-        const int M2 = BL * g.R2, N2 = g.k1 * g.k1 * C1;
         wgrad<TA>(h, dz, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st, GA(h, op.decb[1]));
-        TA* dz1 = TP<TA>(h->hz1);
         gemm_dx_act<TA, ACT_GELU_ERF>(h, dz, N2, op.decwT[1], dz1, TP<TA>(ot.z1pre), M2, C2, N2, st);
         // dec_conv_1: z1pre[BL, N1] = dmod[BL, C] * Wd1^T + b
-        const int N1 = g.k2 * g.k2 * C2;
-        TA* dmod = h->cfg.deg ? TP<TA>(ot.dl) : TP<TA>(ot.dmod);
         wgrad<TA>(h, dz1, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st, GA(h, op.decb[0]));
-        TA* hd = TP<TA>(h->hd);
         gemm_dx<TA>(h, dz1, N1, op.decwT[0], hd, C, BL, C, N1, st);
+        }
         if (!h->cfg.deg) {
             // FiLM modifier (tante.py:151) and interprator (tante.py:149)
             CK(cudaMemsetAsync(h->dfilm.p, 0, (size_t)B * 2 * C * 4, st));
@@ -1883,6 +2024,44 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     const int K3 = g.k2 * g.k2 * C2, K2 = g.k1 * g.k1 * C1;
     const int M2 = tokens * g.R2;
     const long long rows_in = (long long)tokens * g.R1;
+    if (h->wide) {
+        // natural-order stages: the patch matrices of conv3 / conv2 are re-gathered from the kept activation grids (cheap, one
+        // pass), their gradients go back to the grids through the transposed gather
+        TA* wb = TP<TA>(h->wbuf);
+        const int H = h->cfg.H, W = h->cfg.W;
+        const int H1 = H / g.k0, W1 = W / g.k0, H2 = H1 / g.k1, W2 = W1 / g.k1;
+        wide_im2col_cl_kernel<TA><<<blocks_for((long long)tokens * K3 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H2, W2, C2, g.k2,
+                                                                                              (g.k2 - 1) / 2, wb, (long long)tokens * K3 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        wgrad<TA>(h, g2, C, wb, K3, GA(h, h->enc_w[2]), tokens, C, K3, st, GA(h, h->enc_b[2]));
+        gemm_dx<TA>(h, g2, C, h->enc_wT[2], wb, K3, tokens, K3, C, st);
+        wide_col2im_cl_kernel<TA><<<blocks_for((long long)M2 * C2 / 4, 256), 256, 0, st>>>(wb, H2, W2, C2, g.k2, (g.k2 - 1) / 2, gq,
+                                                                                          (long long)M2 * C2 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, gq, TP<TA>(tp.a2pre), (long long)M2 * C2, st);
+        wide_im2col_cl_kernel<TA><<<blocks_for((long long)M2 * K2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a1act), H1, W1, C1, g.k1,
+                                                                                          (g.k1 - 1) / 2, wb, (long long)M2 * K2 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        wgrad<TA>(h, gq, C2, wb, K2, GA(h, h->enc_w[1]), M2, C2, K2, st, GA(h, h->enc_b[1]));
+        gemm_dx<TA>(h, gq, C2, h->enc_wT[1], wb, K2, M2, K2, C2, st);
+        TA* ga1 = TP<TA>(h->ga1);
+        wide_col2im_cl_kernel<TA><<<blocks_for(rows_in * C1 / 4, 256), 256, 0, st>>>(wb, H1, W1, C1, g.k1, (g.k1 - 1) / 2, ga1, rows_in * C1 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), rows_in * C1, st);
+        wgrad_pad<TA>(h, ga1, C1, C1, TP<TA>(tp.cols), h->K1pad, h->K1pad, GA(h, h->enc_w[0]), NO, NO, rows_in, st, GA(h, h->enc_b[0]));
+        if (grad_input) {
+            REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
+            gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], wb, h->K1pad, (int)rows_in, h->K1pad, C1, st);
+            const long long tot = (long long)in_elems;
+            wide_col2im_cf_kernel<TA><<<blocks_for(tot, 256), 256, 0, st>>>(wb, D, H, W, g.k0, (g.k0 - 1) / 2, h->K1pad, grad_input, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+    } else {
     wgrad<TA>(h, g2, C, TP<TA>(tp.a2act), K3, GA(h, h->enc_w[2]), tokens, C, K3, st, GA(h, h->enc_b[2]));
     gemm_dx_act<TA, ACT_GELU_ERF>(h, g2, C, h->enc_wT[2], gq, TP<TA>(tp.a2pre), tokens, K3, C, st);
     wgrad<TA>(h, gq, C2, TP<TA>(tp.a1act), K2, GA(h, h->enc_w[1]), M2, C2, K2, st, GA(h, h->enc_b[1]));
@@ -1900,6 +2079,7 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         else conv1_col2im_kernel<TA, 2><<<blocks_for(rows_in, kPatchRows), 128, 0, st>>>(cols, g, grad_input, rows_in, gt);
         CK(cudaGetLastError());
         h->launches++;
+    }
     }
     // ---- packed gradient arena -> flat state_dict-layout buffer ----
     {
@@ -2449,7 +2629,7 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
-        REQUIRE(!h->wide, "training at patch_scale 16/32/64 is not implemented (inference / rollout only)");
+        REQUIRE(!h->fno, "training with enc_dec_type='fno' is not implemented (inference / rollout only)");
         REQUIRE(!h->chan, "training with the attention axis C is not implemented "
                                "(inference / rollout only)");
         CK(cudaSetDevice(h->device));

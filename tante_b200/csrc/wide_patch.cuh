@@ -7,7 +7,7 @@
 //     encoder stage = gather of the (shifted) k x k windows into a patch matrix  ->  GEMM (+ GELU / embed epilogue)
 //     decoder stage = GEMM to the k x k sub-pixel matrix  ->  crop + bilinear resample (+ bias, GELU) back to the grid
 //     head          = Horner sum + residual + emit over the decoded derivative FIELDS (boundary C of SURVEY.md 8(d))
-// Inference / rollout only; the kernels are plain gather / scatter passes (HBM-bound, one pass each).
+// The kernels are plain gather passes (HBM-bound, one pass each); the training passes further down are their transposes.
 #pragma once
 #include "common.cuh"
 #include "kernels_simt.cuh"
@@ -124,6 +124,144 @@ wide_deconv_post_kernel(const TA* __restrict__ S, int ldS, int hi, int wi, int C
     if (ACT) v = ActMath<TA>::gelu_erf_f(v);
     if (FIELD) field[idx] = v;
     else out[idx] = from_f32<TA>(v);
+}
+
+// ---- training (backward) passes of the natural-order stages ------------------------------------------------------
+// Every forward pass above is a gather, so its transpose is written as a gather too (no atomics): with stride == kernel size a
+// grid pixel belongs to at most ONE window, and a transposed-conv sample feeds at most 4 x 4 resized pixels.
+
+// transpose of wide_im2col_cl_kernel: grid gradient [n][Hs][Ws][Cin] from the patch-matrix gradient; thread = 4 channels
+template <typename TA>
+__global__ void __launch_bounds__(256)
+wide_col2im_cl_kernel(const TA* __restrict__ dcols, int Hs, int Ws, int Cin, int k, int shift, TA* __restrict__ dgrid, long long total4) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total4) return;
+    const int C4 = Cin / 4;
+    const int c4 = (int)(idx % C4);
+    long long r = idx / C4;
+    const int x = (int)(r % Ws); r /= Ws;
+    const int y = (int)(r % Hs);
+    const long long n = r / Hs;
+    const int Ho = Hs / k, Wo = Ws / k;
+    const int yy = y + shift, xx = x + shift;
+    const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i < Ho && j < Wo) Vec4<TA>::load(dcols + ((((size_t)n * Ho + i) * Wo + j) * (k * k) + (di * k + dj)) * Cin + c4 * 4, v);
+    Vec4<TA>::store(dgrid + idx * 4, v);
+}
+
+// transpose of wide_im2col_cf_kernel (contiguous (B, T, D, H, W) input): grad_input += the window-matrix gradient
+template <typename TA>
+__global__ void __launch_bounds__(256)
+wide_col2im_cf_kernel(const TA* __restrict__ dcols, int D, int H, int W, int k, int shift, int Kpad, float* __restrict__ gin,
+                      long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((bt * D + d) * H + y) * W + x
+    if (idx >= total) return;
+    long long r = idx;
+    const int x = (int)(r % W); r /= W;
+    const int y = (int)(r % H); r /= H;
+    const int d = (int)(r % D);
+    const long long bt = r / D;
+    const int Ho = H / k, Wo = W / k;
+    const int yy = y + shift, xx = x + shift;
+    const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
+    if (i < Ho && j < Wo) gin[idx] += to_f32(dcols[(((size_t)bt * Ho + i) * Wo + j) * Kpad + (di * k + dj) * D + d]);
+}
+
+// weight with which resized pixel `dst` reads source sample `src` (bilinear_src above; both taps may hit the same sample at the border)
+__device__ __forceinline__ float bilinear_w(int dst, int src, int in_size, int out_size) {
+    int i0, i1;
+    float w1;
+    bilinear_src(dst, in_size, out_size, i0, i1, w1);
+    return (i0 == src ? 1.f - w1 : 0.f) + (i1 == src ? w1 : 0.f);
+}
+
+// transpose of wide_deconv_post_kernel (without its bias / GELU): gradient of the sub-pixel matrix dS[(n, i, j)][ldS] from the
+// gradient of the stage output -- a channels-last TA grid g[n][k*hi][k*wi][Cout], or (FIELD) the channels-first fp32 field
+// gradient gf[n][Cout][k*hi][k*wi].  Columns beyond k*k*Cout (padding of the last stage) are zeroed.
+template <typename TA, bool FIELD>
+__global__ void __launch_bounds__(256)
+wide_deconv_post_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ gf, int ldS, int hi, int wi, int Cout, int k,
+                            TA* __restrict__ dS, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // row * ldS + col
+    if (idx >= total) return;
+    const int col = (int)(idx % ldS);
+    long long row = idx / ldS;
+    float v = 0.f;
+    if (col < k * k * Cout) {
+        const int co = col % Cout, tap = col / Cout;
+        const int di = tap / k, dj = tap - di * k;
+        const int j = (int)(row % wi); row /= wi;
+        const int i = (int)(row % hi);
+        const long long n = row / hi;
+        const int Ho = hi * k, Wo = wi * k;
+        const int pad = (k - 1) / 2;
+        const int y = k * i + di - pad, x = k * j + dj - pad;
+        auto at = [&](int Y, int X) -> float {
+            return FIELD ? gf[(((size_t)n * Cout + co) * Ho + Y) * Wo + X] : to_f32(g[(((size_t)n * Ho + Y) * Wo + X) * Cout + co]);
+        };
+        if (pad == 0) {
+            v = at(y, x);
+        } else {
+            const int Hd = Ho - 2 * pad, Wd = Wo - 2 * pad;
+            if (y >= 0 && y < Hd && x >= 0 && x < Wd) {
+                for (int Y = max(y - 1, 0); Y <= min(y + 3, Ho - 1); ++Y) {
+                    const float wy = bilinear_w(Y, y, Hd, Ho);
+                    if (wy == 0.f) continue;
+                    float acc = 0.f;
+                    for (int X = max(x - 1, 0); X <= min(x + 3, Wo - 1); ++X) {
+                        const float wx = bilinear_w(X, x, Wd, Wo);
+                        if (wx != 0.f) acc = fmaf(wx, at(Y, X), acc);
+                    }
+                    v = fmaf(wy, acc, v);
+                }
+            }
+        }
+    }
+    dS[idx] = from_f32<TA>(v);
+}
+
+// transpose of the Horner emit (training: contiguous window, frames (B, n_cap, D, H, W)): gradient of the K derivative fields
+// gk[k-1] = sum_{i <= n_b} gframes_i (i fi)^k / k!  and of u0 (the last window frame): sum_i gframes_i, accumulated into gu0.
+struct EmitBwdParams {
+    const float* gframes; long long gf_bs;      // frame i of sample b at gframes + b * gf_bs + i * D * HW
+    const int* n_arr; int n_g;
+    float* gfield;                               // [K][B][D][HW]
+    float* gu0; long long gu0_bs;                // nullable; sample stride
+    int K; float fi; int B, D; long long HW;
+};
+__global__ void __launch_bounds__(256) taylor_emit_bwd_kernel(EmitBwdParams p) {
+    const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (pix >= p.HW) return;
+    const int d = blockIdx.y, b = blockIdx.z;
+    const int n = min(p.n_arr[b], p.n_g);
+    const long long per = (long long)p.D * p.HW;
+    const size_t plane = (size_t)d * p.HW + pix;
+    float4 gk[kMaxOrder], g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kMaxOrder; ++k) gk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 1; i <= n; ++i) {
+        const float4 gv = *reinterpret_cast<const float4*>(p.gframes + (size_t)b * p.gf_bs + (size_t)(i - 1) * per + plane);
+        g0.x += gv.x; g0.y += gv.y; g0.z += gv.z; g0.w += gv.w;
+        const float dt = (float)i * p.fi;
+        float c = 1.f;
+#pragma unroll
+        for (int k = 1; k <= kMaxOrder; ++k)
+            if (k <= p.K) {
+                c *= dt / (float)k;
+                gk[k - 1].x = fmaf(c, gv.x, gk[k - 1].x); gk[k - 1].y = fmaf(c, gv.y, gk[k - 1].y);
+                gk[k - 1].z = fmaf(c, gv.z, gk[k - 1].z); gk[k - 1].w = fmaf(c, gv.w, gk[k - 1].w);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxOrder; ++k)
+        if (k < p.K) *reinterpret_cast<float4*>(p.gfield + ((size_t)k * p.B + b) * per + plane) = gk[k];
+    if (p.gu0) {
+        float4* q = reinterpret_cast<float4*>(p.gu0 + (size_t)b * p.gu0_bs + plane);
+        float4 o = *q;
+        o.x += g0.x; o.y += g0.y; o.z += g0.z; o.w += g0.w;
+        *q = o;
+    }
 }
 
 // Taylor / Horner emit over decoded derivative fields (tante.py:165-171 + formatter transpose + window cat, as head_mma.cuh);

@@ -676,6 +676,11 @@ class TANTE(nn.Module):
             return out
         return out, R_t
 
+    @property
+    def bptt_windows_ok(self) -> bool:
+        """The windowed BPTT entry points (frame tables) exist for the nested-order patch stages only (patch_scale <= 8, cnn)."""
+        return self.patch_scale <= 8 and self.enc_dec_type == "cnn"
+
     def rollout_train(self, window, n_steps: int):
         """Fixed-step BPTT rollout of the training drivers (trainer/trainer.py:144-159) for the `deg=True`, `output_length=1`
         model: (B, T, D, H, W) -> predictions (B, n_steps, D, H, W), one autograd node, no window concatenation.  Same

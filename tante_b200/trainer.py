@@ -90,7 +90,7 @@ def mse_loss_frames(frames, y_ref, n_steps: int):
 def _roll_frames(model, window, n_steps: int):
     """`_roll` for the fixed-step model without the formatter permute and the cat over calls."""
     if (hasattr(model, "rollout_train") and window.is_cuda and int(getattr(model, "output_length", 0)) == 1
-            and torch.is_grad_enabled() and os.environ.get("TANTE_BPTT_WINDOWS", "1") != "0"):
+            and getattr(model, "bptt_windows_ok", True) and torch.is_grad_enabled() and os.environ.get("TANTE_BPTT_WINDOWS", "1") != "0"):
         return [model.rollout_train(window, n_steps)]      # one autograd node, the window slides over one history buffer
     moving, ys, cum = window, [], 0
     while cum < n_steps:

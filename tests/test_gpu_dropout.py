@@ -22,12 +22,15 @@ def _model(cfg, sd, prec, p):
 
 
 @pytest.mark.parametrize("prec,tol_y,tol_g", [("fp32", 1e-5, 3e-4), ("bf16", 2e-2, 8e-2)])
-@pytest.mark.parametrize("case", ["deg_thw", "adp_k2"])
+@pytest.mark.parametrize("case", ["deg_thw", "adp_k2", "adp_lya"])
 def test_dropout_training_matches_oracle_with_same_masks(case, prec, tol_y, tol_g):
     p = 0.25
     if case == "deg_thw":
         cfg = O.OracleConfig(n_fields=3, H=32, W=48, taylor_order=1, attn_axes="THW", deg=True)
         rt_bias, out_T = 0.0, 1
+    elif case == "adp_lya":      # composite axes: L = 96 and A = 384 tokens (general forward kernel + tiled recompute backward)
+        cfg = O.OracleConfig(n_fields=2, H=64, W=96, taylor_order=2, attn_axes="LT-AY", deg=False)
+        rt_bias, out_T = 1.3, 4
     else:
         cfg = O.OracleConfig(n_fields=2, H=64, W=32, taylor_order=2, attn_axes="WT-H", deg=False)
         rt_bias, out_T = 1.3, 4

@@ -239,6 +239,15 @@ def main_train_wide(ns):
                B=2, n_steps=3)
 
 
+def main_train_fno(ns):
+    """Training steps with enc_dec_type='fno' (enc_dec_fno.py:184-323): gradients of the complex spectral weights included."""
+    C = O.OracleConfig
+    case_train(ns, "train_deg_k1_fno_p8", C(n_fields=3, H=64, W=96, taylor_order=1, attn_axes="THW", deg=True, enc_dec_type="fno",
+                                             patch_scale=8, modes1=16, modes2=16), B=2, n_steps=2)
+    case_train(ns, "train_adp_k2_fno_p4", C(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="TH-W", deg=False, enc_dec_type="fno",
+                                             patch_scale=4, modes1=8, modes2=8), B=2, n_steps=3, rt_bias=0.0)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -265,6 +274,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--trainfno" in sys.argv:
+        main_train_fno(ns)
         return
     if "--trainwide" in sys.argv:
         main_train_wide(ns)

@@ -7,7 +7,8 @@
 //     B[n,o,h,k2]  = sum_j Y[n,o,j,k2] e^{+2 pi i k1(j) h / H}                     (idft_h)
 //     y[n,o,h,w]   = (1 / HW) (Re B[..,0] + 2 sum_{k2>=1} Re(B[..,k2] e^{+2 pi i k2 w / W})) + sum_c w0[o,c] x[n,c,h,w] + b[o]
 // (the C2R half of irfft2 ignores the imaginary part of the k2 = 0 column).  All five in fp32 in both precision modes; the
-// patch convolutions between the spectral layers are the gather + GEMM stages of wide_patch.cuh.  Inference / rollout only.
+// patch convolutions between the spectral layers are the gather + GEMM stages of wide_patch.cuh.  The training passes at the end
+// of the file are the adjoints of the same five passes.
 #pragma once
 #include "common.cuh"
 
@@ -146,6 +147,119 @@ __global__ void __launch_bounds__(256) spec_out_kernel(const float2* __restrict_
     if (ACT) v = ActMath<TA>::gelu_erf_f(v);
     if (FIELD) field[idx] = v;
     else out[idx] = from_f32<TA>(v);
+}
+
+// ---- training: adjoints of the five passes ----------------------------------------------------------------------------------
+// With g = dL/dy (after the GELU backward), every pass above is real-linear, so the input gradient runs the same transforms in
+// reverse order on g:
+//     gB[n,o,h,k2] = sum_w g[n,o,h,w] e^{-2 pi i k2 w / W}                          (dft_w of g; the weights c_k2 / HW, c_0 = 1,
+//     gY[n,o,j,k2] = sum_h gB[n,o,h,k2] e^{-2 pi i k1(j) h / H}                      c_k = 2, are applied where gY is consumed)
+//     gX[n,c,j,k2] = (c_k2 / HW) sum_o gY[n,o,j,k2] conj(Wt[c,o,j mod m1,k2])       (spec_mix_adj_kernel)
+//     gA[n,c,h,k2] = sum_j gX[n,c,j,k2] e^{+2 pi i k1(j) h / H}                      (idft_h)
+//     dx[n,c,h,w]  = sum_k2 Re(gA[n,c,h,k2] e^{+2 pi i k2 w / W}) + sum_o w0[o,c] g[n,o,h,w]     (spec_in_bwd_kernel)
+// and the parameter gradients are  dWt[c,o,jw,k2] = (c_k2 / HW) sum_{n, j = jw, jw + m1} conj(X[n,c,j,k2]) gY[n,o,j,k2]  (PyTorch's
+// convention for complex leaves: real part = d/dRe, imaginary part = d/dIm),  dw0[o,c] = sum g[n,o,h,w] x[n,c,h,w],  db[o] = sum g.
+
+__device__ __forceinline__ float spec_ck(int k2, int H, int W) { return (k2 == 0 ? 1.f : 2.f) / ((float)H * (float)W); }
+
+__global__ void __launch_bounds__(256) spec_mix_adj_kernel(const float2* __restrict__ gY, const float2* __restrict__ Wt, int Cin, int Cout,
+                                                           int m1, int m2, int wm2, int wm1, int H, int W, float2* __restrict__ gX,
+                                                           long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((n * Cin + c) * 2 m1 + j) * m2 + k2
+    if (idx >= total) return;
+    const int k2 = (int)(idx % m2);
+    const int j = (int)((idx / m2) % (2 * m1));
+    const int c = (int)((idx / ((long long)m2 * 2 * m1)) % Cin);
+    const long long n = idx / ((long long)m2 * 2 * m1 * Cin);
+    const int jw = j < m1 ? j : j - m1;
+    float re = 0.f, im = 0.f;
+    for (int o = 0; o < Cout; ++o) {
+        const float2 g = gY[(((size_t)n * Cout + o) * 2 * m1 + j) * m2 + k2];
+        const float2 w = Wt[(((size_t)c * Cout + o) * wm1 + jw) * wm2 + k2];
+        re = fmaf(g.x, w.x, fmaf(g.y, w.y, re));          // g * conj(w)
+        im = fmaf(g.y, w.x, fmaf(-g.x, w.y, im));
+    }
+    const float s = spec_ck(k2, H, W);
+    gX[idx] = make_float2(re * s, im * s);
+}
+
+__global__ void __launch_bounds__(256) spec_wt_grad_kernel(const float2* __restrict__ X, const float2* __restrict__ gY, int Cin, int Cout,
+                                                           int m1, int m2, int wm2, int wm1, int H, int W, long long N,
+                                                           float2* __restrict__ gWt, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((c * Cout + o) * m1 + jw) * m2 + k2
+    if (idx >= total) return;
+    const int k2 = (int)(idx % m2);
+    const int jw = (int)((idx / m2) % m1);
+    const int o = (int)((idx / ((long long)m2 * m1)) % Cout);
+    const int c = (int)(idx / ((long long)m2 * m1 * Cout));
+    float re = 0.f, im = 0.f;
+    for (long long n = 0; n < N; ++n) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int j = jw + half * m1;
+            const float2 x = X[(((size_t)n * Cin + c) * 2 * m1 + j) * m2 + k2];
+            const float2 g = gY[(((size_t)n * Cout + o) * 2 * m1 + j) * m2 + k2];
+            re = fmaf(x.x, g.x, fmaf(x.y, g.y, re));      // conj(x) * g
+            im = fmaf(x.x, g.y, fmaf(-x.y, g.x, im));
+        }
+    }
+    const float s = spec_ck(k2, H, W);
+    float2* dst = gWt + (((size_t)c * Cout + o) * wm1 + jw) * wm2 + k2;
+    dst->x += re * s;
+    dst->y += im * s;
+}
+
+// dx of one spectral layer: the C2R-like pass over gA plus the 1x1-conv path.  Output: TA channels-last grid dx[n][h][w][c]
+// (written) or, for the first encoder layer, the fp32 channels-first input gradient (ACCUMULATED: gin[((n * Cin + c) * H + h) * W + w]).
+template <typename TA, bool CF>
+__global__ void __launch_bounds__(256) spec_in_bwd_kernel(const float2* __restrict__ gA, SpecView g, const float* __restrict__ w0, int Cin,
+                                                          int Cout, int H, int W, int m2, const float2* __restrict__ twW,
+                                                          TA* __restrict__ dx, float* __restrict__ gin, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c, w, h;
+    long long n;
+    if (CF) { long long r = idx; w = (int)(r % W); r /= W; h = (int)(r % H); r /= H; c = (int)(r % Cin); n = r / Cin; }
+    else { long long r = idx; c = (int)(r % Cin); r /= Cin; w = (int)(r % W); r /= W; h = (int)(r % H); n = r / H; }
+    const float2* ga = gA + (((size_t)n * Cin + c) * H + h) * m2;
+    float acc = ga[0].x;
+    int t = 0;
+    for (int k2 = 1; k2 < m2; ++k2) {
+        t += w; if (t >= W) t -= W;
+        const float2 tw = twW[t];
+        const float2 v = ga[k2];
+        acc += fmaf(v.x, tw.x, -v.y * tw.y);
+    }
+    for (int o = 0; o < Cout; ++o) acc = fmaf(w0[(size_t)o * Cin + c], spec_read<TA>(g, n, o, h, w, Cout, H, W), acc);
+    if (CF) gin[idx] += acc;
+    else dx[idx] = from_f32<TA>(acc);
+}
+
+// dw0[o][c] += sum_{n,h,w} g[n,o,h,w] x[n,c,h,w] and db[o] += sum g  for the thin layers (a field or frame side: few channels);
+// one CTA per (o, c), c == Cin computes the bias entry
+template <typename TA>
+__global__ void __launch_bounds__(256) spec_w0_grad_kernel(SpecView g, SpecView x, int Cin, int Cout, int H, int W, long long N,
+                                                           float* __restrict__ gw0, float* __restrict__ gb0) {
+    const int o = blockIdx.x / (Cin + 1), c = blockIdx.x % (Cin + 1);
+    const long long total = N * H * W;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int w = (int)(i % W);
+        const int h = (int)((i / W) % H);
+        const long long n = i / ((long long)W * H);
+        const float gv = spec_read<TA>(g, n, o, h, w, Cout, H, W);
+        acc = c < Cin ? fmaf(gv, spec_read<TA>(x, n, c, h, w, Cin, H, W), acc) : acc + gv;
+    }
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        if (c < Cin) gw0[(size_t)o * Cin + c] += s;
+        else gb0[o] += s;
+    }
 }
 
 }  // namespace tante

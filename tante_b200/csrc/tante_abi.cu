@@ -75,6 +75,7 @@ struct Param {
     // gradient arena entry (packed layout, see unpack_grads_kernel) and position in the flat gradient buffer
     int64_t goff = -1, gnumel = 0, flat_off = 0;
     int gmode = PACK_COPY, gd0 = 0, gd1 = 0, gk = 1;
+    bool cplx = false;      // complex64 parameter bound as (re, im) float pairs (SpectralLayer.weight)
 };
 
 struct DevBuf {
@@ -120,9 +121,11 @@ struct OrderTape {
     std::vector<DevBuf> X;              // fp32 residual stream: X[0] after the propagators, X[2i+1] mid, X[2i+2] out of layer i
     std::vector<DevBuf> ln1, qkv, att, ln2, hpre, hact;
     DevBuf dl, d32, dmod, i1, i2, rt, film, z1pre, z1act, z2pre, z2act;
+    DevBuf f0pre, f0act;                // fno decoder: [B][H][W][C/8] grid behind dec_conv_2 (the stages above reuse z1* = [B][H1][W1][C/2], z2* = [B][H1][W1][C/4])
 };
 struct Tape {
     DevBuf cols, a1pre, a1act, a2pre, a2act, v, n_arr;
+    DevBuf f0pre, f0act;                // fno encoder: [B*T][H][W][C/8] grid behind enc_spectral_1 (a1* = [..][H1][W1][C/4], a2* = [..][H1][W1][C/2])
     std::vector<OrderTape> ord;
     int B = 0;          // allocated batch
     int B_used = 0;     // batch of the taped forward
@@ -161,6 +164,8 @@ struct tante_handle_s {
     int fp0 = 0, fp1 = 0;               // fno patch kernels (enc_dec_fno.py:39-46)
     SpecPlan fes1, fes2;                // fno encoder: enc_spectral_1 / enc_spectral_2
     DevBuf ftw, fA, fB, fg0, fg1, fg2;  // fno: twiddle tables, complex scratch x2, channels-last stage grids
+    DevBuf fC, fD, fgr0, fgr1, fgr2;    // fno training: two more complex scratch buffers, gradient grids of the three stages
+    size_t f_ca = 0;                    // complex elements per scratch buffer (tante_reserve)
     bool wide = false;                  // patch_scale >= 16: natural-order stages with shifted 4x4 windows (wide_patch.cuh)
     int K1pad = 0, NOpad = 0;           // wide: first-conv reduction / last-deconv output width rounded up to 64
     int64_t enc_w1wide = 0;             // wide: first conv weight [C1][K1pad]
@@ -323,6 +328,7 @@ void build_plan(tante_handle_s* h) {
         SpecPlan sp;
         sp.Cin = Cin; sp.Cout = Cout; sp.wm1 = wm1; sp.wm2 = wm2;
         sp.w = add_param(h, pre + "weight", {Cin, Cout, wm1, wm2, 2});        // cfloat viewed as (..., 2) floats
+        h->params.back().cplx = true;
         sp.w0 = add_param(h, pre + "w0.weight", {Cout, Cin, 1, 1});
         sp.b0 = add_param(h, pre + "w0.bias", {Cout});
         return sp;
@@ -336,6 +342,8 @@ void build_plan(tante_handle_s* h) {
         h->fes2 = add_spec("encoder.enc_spectral_2.", C1, C2, c.modes1 / p0, c.modes2 / p0);
         h->enc_w[1] = add_param(h, "encoder.enc_conv_2.conv.weight", {C, C2, p1, p1}, PACK_CONV, C, C2, p1);
         h->enc_b[1] = add_param(h, "encoder.enc_conv_2.conv.bias", {C});
+        h->enc_wT[0] = add_trans(h, h->enc_w[0], C1, C8 * p0 * p0);      // [K][N] copies for the input-gradient GEMMs (training)
+        h->enc_wT[1] = add_trans(h, h->enc_w[1], C, C2 * p1 * p1);
     }
     for (int i = 0; i < 3 && !h->fno; ++i) {
         const std::string p = "encoder.enc_conv_" + std::to_string(i + 1) + ".conv.";
@@ -435,6 +443,8 @@ void build_plan(tante_handle_s* h) {
             op.decw[1] = add_param(h, p + "dec_conv_2.deconv.weight", {C1, C8, p0, p0}, PACK_DECONV_NK, C1, C8, p0);
             op.decb[1] = add_param(h, p + "dec_conv_2.deconv.bias", {C8}, PACK_BIAS_REP, C8, 0, p0);
             op.fs2 = add_spec(p + "dec_spectral_2.", C8, D, c.modes1, c.modes2);
+            op.decwT[0] = add_trans(h, op.decw[0], p1 * p1 * C2, C);
+            op.decwT[1] = add_trans(h, op.decw[1], p0 * p0 * C8, C1);
         }
         for (int i = 0; i < 3 && !h->fno; ++i) {
             const int kk = k[2 - i];
@@ -470,6 +480,13 @@ void build_plan(tante_handle_s* h) {
             }
             add_film("modifiers." + std::to_string(o) + ".", op.mod);
         }
+    }
+    // flat gradient layout: the complex parameters first, so that each starts at an EVEN element offset and the host can view
+    // its slice of the flat fp32 buffer as complex64 (torch.view_as_complex); the rest in tante_param order
+    {
+        int64_t off = 0;
+        for (Param& p : h->params) if (p.cplx) { p.flat_off = off; off += p.numel; }
+        for (Param& p : h->params) if (!p.cplx) { p.flat_off = off; off += p.numel; }
     }
     // derived tensors
     h->film_t_off = h->arena_elems; h->arena_elems += (int64_t)T * 2 * C;
@@ -1333,6 +1350,62 @@ void gemm_dx_act(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* ou
     }
 }
 
+// Backward of one SpectralLayer (fno.cuh, "training"): x = the layer's saved input, g = the gradient of its output (after the
+// GELU backward).  Accumulates the gradients of weight / w0 / bias, and writes the input gradient to the channels-last grid
+// `dx` or accumulates it into the channels-first fp32 `gin` (first encoder layer); both null: parameters only.
+template <typename TA>
+void run_spectral_bwd(tante_handle_s* h, const SpecPlan& sp, const SpecView& x, const SpecView& g, long long N, int H, int W,
+                      int level, TA* dx, float* gin, cudaStream_t st) {
+    const int W0 = h->cfg.W, H0 = h->cfg.H, W1 = W0 / h->fp0;
+    const float2* tw = reinterpret_cast<const float2*>(h->ftw.p);
+    const float2* twW = level == 0 ? tw : tw + W0 + H0;
+    const float2* twH = level == 0 ? tw + W0 : tw + W0 + H0 + W1;
+    const int m1 = sp.wm1, m2 = sp.wm2, Cin = sp.Cin, Cout = sp.Cout;
+    float2* A = reinterpret_cast<float2*>(h->fA.p);
+    float2* Bc = reinterpret_cast<float2*>(h->fB.p);
+    float2* Cc = reinterpret_cast<float2*>(h->fC.p);
+    float2* Dd = reinterpret_cast<float2*>(h->fD.p);
+    // gY = dft_h(dft_w(g))  -> Bc
+    const long long rows_o = N * Cout * H, rows_i = N * Cin * H;
+    spec_dft_w_kernel<TA><<<blocks_for(rows_o, 4), 128, 0, st>>>(g, Cout, H, W, m2, twW, A, rows_o);
+    CK(cudaGetLastError());
+    const long long ty = N * Cout * 2 * m1 * m2, tx = N * Cin * 2 * m1 * m2;
+    spec_dft_h_kernel<<<blocks_for(ty, 256), 256, 0, st>>>(A, H, m1, m2, twH, Bc, ty);
+    CK(cudaGetLastError());
+    // X = dft_h(dft_w(x))  -> Cc (recomputed: two passes over the saved input)
+    spec_dft_w_kernel<TA><<<blocks_for(rows_i, 4), 128, 0, st>>>(x, Cin, H, W, m2, twW, A, rows_i);
+    CK(cudaGetLastError());
+    spec_dft_h_kernel<<<blocks_for(tx, 256), 256, 0, st>>>(A, H, m1, m2, twH, Cc, tx);
+    CK(cudaGetLastError());
+    const long long tw_ = (long long)Cin * Cout * m1 * m2;
+    spec_wt_grad_kernel<<<blocks_for(tw_, 256), 256, 0, st>>>(Cc, Bc, Cin, Cout, m1, m2, sp.wm2, sp.wm1, H, W, N,
+                                                             reinterpret_cast<float2*>(GA(h, sp.w)), tw_);
+    CK(cudaGetLastError());
+    h->launches += 5;
+    if (dx || gin) {
+        spec_mix_adj_kernel<<<blocks_for(tx, 256), 256, 0, st>>>(Bc, reinterpret_cast<const float2*>(AF(h, sp.w)), Cin, Cout, m1, m2,
+                                                                 sp.wm2, sp.wm1, H, W, A, tx);
+        CK(cudaGetLastError());
+        const long long ta = N * Cin * H * m2;
+        spec_idft_h_kernel<<<blocks_for(ta, 256), 256, 0, st>>>(A, H, m1, m2, twH, Dd, ta);
+        CK(cudaGetLastError());
+        const long long to = N * Cin * H * W;
+        if (gin) spec_in_bwd_kernel<TA, true><<<blocks_for(to, 256), 256, 0, st>>>(Dd, g, AF(h, sp.w0), Cin, Cout, H, W, m2, twW, nullptr, gin, to);
+        else spec_in_bwd_kernel<TA, false><<<blocks_for(to, 256), 256, 0, st>>>(Dd, g, AF(h, sp.w0), Cin, Cout, H, W, m2, twW, dx, nullptr, to);
+        CK(cudaGetLastError());
+        h->launches += 3;
+    }
+    // 1x1 conv: dw0 = g^T x, db = colsum(g)
+    if (x.mode == 1 && g.mode == 1 && Cin % 64 == 0 && Cout % 64 == 0) {
+        wgrad<TA>(h, reinterpret_cast<const TA*>(g.p), Cout, reinterpret_cast<const TA*>(x.p), Cin, GA(h, sp.w0), N * H * W, Cout, Cin, st,
+                  GA(h, sp.b0));
+    } else {
+        spec_w0_grad_kernel<TA><<<Cout * (Cin + 1), 256, 0, st>>>(g, x, Cin, Cout, H, W, N, GA(h, sp.w0), GA(h, sp.b0));
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+}
+
 template <typename TA>
 void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamma, float* dxs, TA* dxb, float* dg, float* db,
                    long long rows, cudaStream_t st, const DropCfg& drop = DropCfg(), uint32_t site = 0) {
@@ -1463,11 +1536,11 @@ void launch_propagator_bwd(tante_handle_s* h, const float* xin, float* dy, int B
 }
 
 void free_tape(Tape& tp) {
-    DevBuf* bufs[] = {&tp.cols, &tp.a1pre, &tp.a1act, &tp.a2pre, &tp.a2act, &tp.v, &tp.n_arr};
+    DevBuf* bufs[] = {&tp.cols, &tp.a1pre, &tp.a1act, &tp.a2pre, &tp.a2act, &tp.v, &tp.n_arr, &tp.f0pre, &tp.f0act};
     for (DevBuf* b : bufs) b->free();
     for (OrderTape& ot : tp.ord) {
         DevBuf* ob[] = {&ot.P[0], &ot.P[1], &ot.P[2], &ot.dl, &ot.d32, &ot.dmod, &ot.i1, &ot.i2, &ot.rt, &ot.film, &ot.z1pre,
-                        &ot.z1act, &ot.z2pre, &ot.z2act};
+                        &ot.z1act, &ot.z2pre, &ot.z2act, &ot.f0pre, &ot.f0act};
         for (DevBuf* b : ob) b->free();
         for (auto* v : {&ot.X, &ot.ln1, &ot.qkv, &ot.att, &ot.ln2, &ot.hpre, &ot.hact})
             for (auto& b : *v) b.free();
@@ -1487,8 +1560,15 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
     dev_alloc(h, tp.cols, tokens * g.R1 * (size_t)std::max(kHeadPad, h->wide ? h->K1pad : 0) * es);
     dev_alloc(h, tp.a1pre, tokens * g.R1 * C1 * es);
     dev_alloc(h, tp.a1act, tokens * g.R1 * C1 * es);
-    dev_alloc(h, tp.a2pre, tokens * g.R2 * C2 * es);
-    dev_alloc(h, tp.a2act, tokens * g.R2 * C2 * es);
+    // fno: the C/2 grid sits at the H1 x W1 resolution (R1 rows per token), and there is a C/8 grid at full resolution
+    const size_t r2 = h->fno ? g.R1 : g.R2;
+    dev_alloc(h, tp.a2pre, tokens * r2 * C2 * es);
+    dev_alloc(h, tp.a2act, tokens * r2 * C2 * es);
+    if (h->fno) {
+        const size_t f0 = (size_t)B * h->T * h->cfg.H * h->cfg.W * (C / 8) * es;
+        dev_alloc(h, tp.f0pre, f0);
+        dev_alloc(h, tp.f0act, f0);
+    }
     dev_alloc(h, tp.v, tokens * C * 4);
     dev_alloc(h, tp.n_arr, (size_t)B * 4);
     tp.ord.resize(h->K);
@@ -1516,8 +1596,13 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
             dev_alloc(h, ot.rt, (size_t)B * 4);
             dev_alloc(h, ot.film, (size_t)B * 2 * C * 4);
         }
-        dev_alloc(h, ot.z1pre, BL * g.R2 * C2 * es);
-        dev_alloc(h, ot.z1act, BL * g.R2 * C2 * es);
+        dev_alloc(h, ot.z1pre, BL * r2 * C2 * es);
+        dev_alloc(h, ot.z1act, BL * r2 * C2 * es);
+        if (h->fno) {
+            const size_t f0 = (size_t)B * h->cfg.H * h->cfg.W * (C / 8) * es;
+            dev_alloc(h, ot.f0pre, f0);
+            dev_alloc(h, ot.f0act, f0);
+        }
         dev_alloc(h, ot.z2pre, BL * g.R1 * C1 * es);
         dev_alloc(h, ot.z2act, BL * g.R1 * C1 * es);
     }
@@ -1525,6 +1610,10 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
 }
 
 void backward_alloc(tante_handle_s* h, int B) {
+    if (h->fno) {      // sized by tante_reserve's max_batch, which may have grown since the last call
+        dev_alloc(h, h->fC, h->f_ca * 8);
+        dev_alloc(h, h->fD, h->f_ca * 8);
+    }
     if (h->bw_batch >= B) return;
     const size_t es = h->cfg.precision == TANTE_PREC_BF16 ? 2 : 4;
     const size_t tokens = (size_t)B * h->T * h->L;
@@ -1549,6 +1638,12 @@ void backward_alloc(tante_handle_s* h, int B) {
     dev_alloc(h, h->hi2, BL * (C / 4) * es);
     dev_alloc(h, h->dfilm, (size_t)std::max(B, h->T) * 2 * C * 4);
     dev_alloc(h, h->dcond, (size_t)B * 4);
+    if (h->fno) {
+        const size_t NI = (size_t)B * h->T, HW = (size_t)h->cfg.H * h->cfg.W, HW1 = HW / (h->fp0 * h->fp0);
+        dev_alloc(h, h->fgr0, NI * HW * (C / 8) * es);
+        dev_alloc(h, h->fgr1, NI * HW1 * C1 * es);
+        dev_alloc(h, h->fgr2, NI * HW1 * C2 * es);
+    }
     if (h->long_axes) dev_alloc(h, h->att_stats, tokens * h->cfg.n_head * 2 * 4);      // LSE + delta per (token, head)
     if (!h->udesc_dev.p) {
         std::vector<UnpackDesc> ud;
@@ -1582,7 +1677,28 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     if (drop.p > 0.f && kTensor && !(h->fuse_tail && C == kBtC && h->Hm == C))
         throw Error(TANTE_ERR_INVALID, "dropout in the tensor mode needs the fused block tail (TANTE_FUSE_TAIL=1, embed_dim 256)");
     // --- encoder ---
-    if (h->wide) {
+    if (h->fno) {
+        // enc_FNO.forward (enc_dec_fno.py:254-272): spectral layer -> GELU -> patch conv -> GELU -> spectral layer -> GELU -> patch conv;
+        // every pre-activation / activation grid is kept
+        REQUIRE(!win, "windowed BPTT is not available with enc_dec_type='fno'");
+        const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0, C8 = C / 8;
+        const long long NI = (long long)B * T;
+        SpecView v0{input, 0, nullptr, T};
+        run_spectral<TA>(h, h->fes1, v0, NI, H, W, 0, false, TP<TA>(tp.f0pre), nullptr, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.f0pre), TP<TA>(tp.f0act), NI * H * W * C8, st);
+        EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
+        conv_cl_gemm<TA>(h, EPI_BIAS, TP<TA>(tp.f0act), H, W, C8, p0, h->enc_w[0], tp.a1pre.p, C1, false, NI, e1, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), NI * H1 * W1 * C1, st);
+        SpecView v1{tp.a1act.p, 1, nullptr, 1};
+        run_spectral<TA>(h, h->fes2, v1, NI, H1, W1, 1, false, TP<TA>(tp.a2pre), nullptr, st);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a2pre), TP<TA>(tp.a2act), NI * H1 * W1 * C2, st);
+        EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
+        conv_cl_gemm<TA>(h, EPI_BIAS, TP<TA>(tp.a2act), H1, W1, C2, p1, h->enc_w[1], tp.v.p, C, true, NI, e2, st);
+        embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(
+            FP(tp.v), AF(h, h->film_t_off), AF(h, h->s_emb), AF(h, h->t_emb), FP(tp.ord[0].P[0]), tokens, T, L, C);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else if (h->wide) {
         // patch_scale 16 / 32 / 64 (wide_patch.cuh): natural-order stages, window gathers + GEMMs; the first patch matrix and every
         // pre-activation / activation grid are kept for the backward
         REQUIRE(!win, "windowed BPTT is not available at patch_scale >= 16");
@@ -1726,6 +1842,33 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             CK(cudaGetLastError());
             h->launches++;
             dmod = TP<TA>(ot.dmod);
+        }
+        if (h->fno) {
+            // dec_FNO.forward (enc_dec_fno.py:303-323): deconv -> GELU -> spectral -> GELU -> deconv -> GELU -> spectral
+            TA* wb = TP<TA>(h->wbuf);
+            const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0, C8 = C / 8, D = h->D;
+            const int N1 = p1 * p1 * C2, N2 = p0 * p0 * C8;
+            float* field = FP(h->dfield) + (size_t)o * B * D * H * W;
+            EpiParams ew; ew.bias = AF(h, op.decb[0]);
+            gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ew, st);
+            long long tot = (long long)B * H1 * W1 * C2;
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N1, h->Hp, h->Wp, C2, p1, nullptr, TP<TA>(ot.z1pre), nullptr, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z1pre), TP<TA>(ot.z1act), tot, st);
+            SpecView v2{ot.z1act.p, 1, nullptr, 1};
+            run_spectral<TA>(h, op.fs1, v2, B, H1, W1, 1, false, TP<TA>(ot.z2pre), nullptr, st);
+            launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z2pre), TP<TA>(ot.z2act), (long long)B * H1 * W1 * C1, st);
+            ew.bias = AF(h, op.decb[1]);
+            gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z2act), C1, op.decw[1], wb, N2, false, B * H1 * W1, N2, C1, ew, st);
+            tot = (long long)B * H * W * C8;
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N2, H1, W1, C8, p0, nullptr, TP<TA>(ot.f0pre), nullptr, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.f0pre), TP<TA>(ot.f0act), tot, st);
+            SpecView v0{ot.f0act.p, 1, nullptr, 1};
+            run_spectral<TA>(h, op.fs2, v0, B, H, W, 0, false, nullptr, field, st);
+            continue;
         }
         if (h->wide) {
             // decoder stage = GEMM to the sub-pixel matrix -> crop + bilinear resample to the grid (pre-activation kept) -> GELU
@@ -1890,7 +2033,38 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         TA* dz1 = TP<TA>(h->hz1);
         TA* dmod = h->cfg.deg ? TP<TA>(ot.dl) : TP<TA>(ot.dmod);
         TA* hd = TP<TA>(h->hd);
-        if (h->wide) {
+        if (h->fno) {
+            TA* wb = TP<TA>(h->wbuf);
+            const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0, C8 = C / 8;
+            const int NF1 = p1 * p1 * C2, NF2 = p0 * p0 * C8;
+            TA* gr0 = TP<TA>(h->fgr0);
+            TA* gr1 = TP<TA>(h->fgr1);
+            TA* gr2 = TP<TA>(h->fgr2);
+            const float* gf = FP(h->dfield) + (size_t)o * B * D * H * W;
+            // dec_spectral_2 (field output, no activation)
+            SpecView xg0{ot.f0act.p, 1, nullptr, 1}, gv0{gf, 0, nullptr, 1};
+            run_spectral_bwd<TA>(h, op.fs2, xg0, gv0, B, H, W, 0, gr0, nullptr, st);
+            launch_act_bwd<TA, ACT_GELU_ERF>(h, gr0, TP<TA>(ot.f0pre), (long long)B * H * W * C8, st);
+            // dec_conv_2 (p0)
+            const long long MF2 = (long long)B * H1 * W1;
+            long long tot = MF2 * NF2;
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(gr0, nullptr, NF2, H1, W1, C8, p0, wb, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            wgrad<TA>(h, wb, NF2, TP<TA>(ot.z2act), C1, GA(h, op.decw[1]), MF2, NF2, C1, st, GA(h, op.decb[1]));
+            gemm_dx_act<TA, ACT_GELU_ERF>(h, wb, NF2, op.decwT[1], gr1, TP<TA>(ot.z2pre), (int)MF2, C1, NF2, st);
+            // dec_spectral_1
+            SpecView xg1{ot.z1act.p, 1, nullptr, 1}, gv1{gr1, 1, nullptr, 1};
+            run_spectral_bwd<TA>(h, op.fs1, xg1, gv1, B, H1, W1, 1, gr2, nullptr, st);
+            launch_act_bwd<TA, ACT_GELU_ERF>(h, gr2, TP<TA>(ot.z1pre), MF2 * C2, st);
+            // dec_conv_1 (p1)
+            tot = (long long)BL * NF1;
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(gr2, nullptr, NF1, h->Hp, h->Wp, C2, p1, wb, tot);
+            CK(cudaGetLastError());
+            h->launches++;
+            wgrad<TA>(h, wb, NF1, dmod, C, GA(h, op.decw[0]), BL, NF1, C, st, GA(h, op.decb[0]));
+            gemm_dx<TA>(h, wb, NF1, op.decwT[0], hd, C, BL, C, NF1, st);
+        } else if (h->wide) {
             // natural-order stages (wide_patch.cuh): transpose of (crop + bilinear resample) back to the sub-pixel matrix, then the
             // same weight / input gradient GEMMs as below, stage by stage
             TA* wb = TP<TA>(h->wbuf);
@@ -2024,7 +2198,44 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
     const int K3 = g.k2 * g.k2 * C2, K2 = g.k1 * g.k1 * C1;
     const int M2 = tokens * g.R2;
     const long long rows_in = (long long)tokens * g.R1;
-    if (h->wide) {
+    if (h->fno) {
+        TA* wb = TP<TA>(h->wbuf);
+        const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0, C8 = C / 8;
+        const long long NI = (long long)B * T, MF1 = NI * H1 * W1;
+        const int KF2 = p1 * p1 * C2, KF1 = p0 * p0 * C8;
+        TA* gr0 = TP<TA>(h->fgr0);
+        TA* gr1 = TP<TA>(h->fgr1);
+        TA* gr2 = TP<TA>(h->fgr2);
+        // enc_conv_2 (p1): windows of the kept C/2 grid
+        wide_im2col_cl_kernel<TA><<<blocks_for((long long)tokens * KF2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H1, W1, C2, p1, (p1 - 1) / 2,
+                                                                                               wb, (long long)tokens * KF2 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        wgrad<TA>(h, g2, C, wb, KF2, GA(h, h->enc_w[1]), tokens, C, KF2, st, GA(h, h->enc_b[1]));
+        gemm_dx<TA>(h, g2, C, h->enc_wT[1], wb, KF2, tokens, KF2, C, st);
+        wide_col2im_cl_kernel<TA><<<blocks_for(MF1 * C2 / 4, 256), 256, 0, st>>>(wb, H1, W1, C2, p1, (p1 - 1) / 2, gr2, MF1 * C2 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, gr2, TP<TA>(tp.a2pre), MF1 * C2, st);
+        // enc_spectral_2
+        SpecView xs1{tp.a1act.p, 1, nullptr, 1}, gs1{gr2, 1, nullptr, 1};
+        run_spectral_bwd<TA>(h, h->fes2, xs1, gs1, NI, H1, W1, 1, gr1, nullptr, st);
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, gr1, TP<TA>(tp.a1pre), MF1 * C1, st);
+        // enc_conv_1 (p0): windows of the kept C/8 grid
+        wide_im2col_cl_kernel<TA><<<blocks_for(MF1 * KF1 / 4, 256), 256, 0, st>>>(TP<TA>(tp.f0act), H, W, C8, p0, (p0 - 1) / 2, wb, MF1 * KF1 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        wgrad<TA>(h, gr1, C1, wb, KF1, GA(h, h->enc_w[0]), MF1, C1, KF1, st, GA(h, h->enc_b[0]));
+        REQUIRE(MF1 < (1LL << 31), "input too large for the first-conv backward GEMM");
+        gemm_dx<TA>(h, gr1, C1, h->enc_wT[0], wb, KF1, (int)MF1, KF1, C1, st);
+        wide_col2im_cl_kernel<TA><<<blocks_for(NI * H * W * C8 / 4, 256), 256, 0, st>>>(wb, H, W, C8, p0, (p0 - 1) / 2, gr0, NI * H * W * C8 / 4);
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, gr0, TP<TA>(tp.f0pre), NI * H * W * C8, st);
+        // enc_spectral_1 on the input frames (input gradient accumulated on top of the u0 path)
+        SpecView xs0{input, 0, nullptr, T}, gs0{gr0, 1, nullptr, 1};
+        run_spectral_bwd<TA>(h, h->fes1, xs0, gs0, NI, H, W, 0, nullptr, grad_input, st);
+    } else if (h->wide) {
         // natural-order stages: the patch matrices of conv3 / conv2 are re-gathered from the kept activation grids (cheap, one
         // pass), their gradients go back to the grids through the transposed gather
         TA* wb = TP<TA>(h->wbuf);
@@ -2281,7 +2492,7 @@ int tante_destroy(tante_handle_t h) {
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
-                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->opt_segs, &h->opt_norm};
+                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->fC, &h->fD, &h->fgr0, &h->fgr1, &h->fgr2, &h->opt_segs, &h->opt_norm};
         for (DevBuf* b : tb) b->free();
         if (h->nccl_comm && nccl_api().ok()) nccl_api().CommDestroy(h->nccl_comm);
         for (auto& tp : h->tapes) free_tape(*tp);
@@ -2453,6 +2664,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             ca = std::max(ca, NI * (size_t)C2 * H1 * m2b);                            // level 1 (up to C/2 channels)
             dev_alloc(h, h->fA, ca * 8);
             dev_alloc(h, h->fB, ca * 8);
+            h->f_ca = ca;
             size_t m = NI * HW1 * (size_t)(h->fp0 * h->fp0 * C8);                     // conv_1 windows
             m = std::max(m, NI * (HW1 / (h->fp1 * h->fp1)) * (size_t)(h->fp1 * h->fp1 * C2));      // conv_2 windows
             m = std::max(m, (size_t)max_batch * h->L * (size_t)(h->fp1 * h->fp1 * C2));            // deconv_1 sub-pixel matrix
@@ -2629,7 +2841,6 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
-        REQUIRE(!h->fno, "training with enc_dec_type='fno' is not implemented (inference / rollout only)");
         REQUIRE(!h->chan, "training with the attention axis C is not implemented "
                                "(inference / rollout only)");
         CK(cudaSetDevice(h->device));

@@ -357,13 +357,7 @@ class _TanteStep(torch.autograd.Function):
             if acc is not None:
                 acc.add_(flat)
                 return (None, g_in, None, None, *([None] * len(eng.names)))
-        grads = []
-        for (name, shape), off in zip(ctx.model._param_shapes(eng), eng.grad_offsets):
-            n = 1
-            for d in shape:
-                n *= d
-            grads.append(flat[off:off + n].view(shape))
-        return (None, g_in, None, None, *grads)
+        return (None, g_in, None, None, *ctx.model._grad_views(eng, flat))
 
 
 class _TanteBPTT(torch.autograd.Function):
@@ -439,12 +433,7 @@ class _TanteBPTT(torch.autograd.Function):
                 flat_sum = flat if flat_sum is None else flat_sum.add_(flat)
         if acc is not None:
             return (None, g_x, None, *([None] * len(eng.names)))
-        grads = []
-        for (name, shape), off in zip(model._param_shapes(eng), eng.grad_offsets):
-            n = 1
-            for d in shape:
-                n *= d
-            grads.append(flat_sum[off:off + n].view(shape))
+        grads = model._grad_views(eng, flat_sum)
         return (None, g_x, None, *grads)
 
 
@@ -611,13 +600,27 @@ class TANTE(nn.Module):
         base = g0.data_ptr() - 4 * eng.grad_offsets[0]
         for n, off in zip(eng.names, eng.grad_offsets):
             g = params[n].grad
-            if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != base + 4 * off:
+            if (g is None or g.dtype not in (torch.float32, torch.complex64) or not g.is_contiguous()
+                    or g.data_ptr() != base + 4 * off):
                 return None
         st = g0.untyped_storage()
         first = g0.storage_offset() - eng.grad_offsets[0]
         if first < 0 or (first + eng.grad_numel) * 4 > st.nbytes():
             return None
         return torch.as_strided(g0, (eng.grad_numel,), (1,), first)
+
+    def _grad_views(self, eng: _Engine, flat: torch.Tensor):
+        """Per-parameter views of the library's flat fp32 gradient (tante_param order); complex parameters (SpectralLayer.weight)
+        are stored as (re, im) float pairs."""
+        params = dict(self.named_parameters())
+        out = []
+        for n, off in zip(eng.names, eng.grad_offsets):
+            p = params[n]
+            if p.dtype == torch.complex64:
+                out.append(torch.view_as_complex(flat[off:off + 2 * p.numel()].view(*p.shape, 2)))
+            else:
+                out.append(flat[off:off + p.numel()].view(p.shape))
+        return out
 
     def _param_shapes(self, eng: _Engine):
         params = dict(self.named_parameters())

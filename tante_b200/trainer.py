@@ -144,7 +144,10 @@ class GradBucket:
             self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
             for name, off in zip(names, offsets):
                 p = named[name]
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                if p.dtype == torch.complex64:      # SpectralLayer.weight: (re, im) float pairs in the flat buffer
+                    p.grad = torch.view_as_complex(self.flat[off:off + 2 * p.numel()].view(*p.shape, 2))
+                else:
+                    p.grad = self.flat[off:off + p.numel()].view_as(p)
             return
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)

@@ -47,6 +47,8 @@ def golden_cfg(meta):
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(dt)
+    b = b.astype(dt)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))

@@ -93,7 +93,7 @@ def _report(model, z, meta, tol):
 
 
 @pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16",
-                                  "train_deg_k1_p32"])
+                                  "train_deg_k1_p32", "train_deg_k1_fno_p8", "train_adp_k2_fno_p4"])
 def test_training_step_fp32_matches_reference_golden(name):
     z, meta, cfg, model, x, y, loss = _train_case(name, "fp32")
     assert abs(float(loss) - float(z["loss"])) < 2e-6 * max(1.0, abs(float(z["loss"])))
@@ -106,7 +106,7 @@ def test_training_step_fp32_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16",
-                                  "train_deg_k1_p32"])
+                                  "train_deg_k1_p32", "train_deg_k1_fno_p8", "train_adp_k2_fno_p4"])
 def test_training_step_bf16_close_to_reference_golden(name):
     z, meta, cfg, model, x, y, loss = _train_case(name, "bf16")
     assert abs(float(loss) - float(z["loss"])) < 2e-2 * max(1.0, abs(float(z["loss"])))
@@ -177,7 +177,7 @@ def _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=False):
 
 
 @pytest.mark.parametrize("prec,tol", [("fp32", FP32_GRAD_TOL), ("bf16", BF16_GRAD_TOL)])
-@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48", "adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16"])
+@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48", "adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16"])
 def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
     """One model call with a random cotangent on the frames AND on R_t, multi-frame emit (n = 3) included:
     every parameter gradient and the input gradient against torch autograd over the CPU oracle."""
@@ -209,6 +209,11 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         # patch_scale 16 (kernels 4, 2, 2), 11 fields (K1 = 176 -> padded to 192), two orders
         cfg = O.OracleConfig(n_fields=11, H=64, W=64, taylor_order=2, attn_axes="TW-H", deg=True, patch_scale=16, output_length=2)
         rt_bias, out_T = 0.0, 1
+    elif case == "adp_k1_fno_p16":
+        # enc_dec_type='fno' at patch_scale 16: 4x4 patch stages (shifted windows / bilinear resize) between the spectral layers
+        cfg = O.OracleConfig(n_fields=4, H=64, W=128, taylor_order=1, attn_axes="WT", deg=False, enc_dec_type="fno", patch_scale=16,
+                             modes1=12, modes2=20)
+        rt_bias, out_T = 2.7, 8
     elif case == "adp_k1_axes48":
         # TRL geometry: axis length 48 (padded to 64 in the tensor-core propagator kernels)
         cfg = O.OracleConfig(n_fields=4, H=128, W=384, taylor_order=1, attn_axes="WHT", deg=False)
@@ -217,7 +222,7 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         cfg = O.OracleConfig(n_fields=2, H=16, W=24, taylor_order=3, attn_axes="T-H-W", deg=False, patch_scale=2)
         rt_bias, out_T = 1.3, 4
     sd = O.make_state_dict(cfg, 311, rt_bias)
-    B = 2 if ("axes" in case or case in ("adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16")) else 3
+    B = 2 if ("axes" in case or case in ("adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16")) else 3
     x = O.make_input(cfg, B, 312)
     with torch.no_grad():
         y0 = O.forward(sd, cfg, x, out_T)
@@ -329,13 +334,17 @@ def test_grad_accumulation_and_slot_reuse():
     assert eng.n_slots <= 2
 
 
-def test_grad_bucket_direct_accumulation_matches_autograd_path():
+@pytest.mark.parametrize("kind", ["cnn", "fno"])
+def test_grad_bucket_direct_accumulation_matches_autograd_path(kind):
     """GradBucket lays `p.grad` out like the library's flat gradient, so the backward accumulates with one add per
     model call and returns no per-parameter gradients: the result must equal the plain autograd path, also when the
     same parameters are used by several chained calls (BPTT) and after the bucket is zeroed."""
     from gpu_util import make_model
     from tante_b200.trainer import GradBucket, rollout_train
     cfg = O.OracleConfig(n_fields=3, H=32, W=48, taylor_order=1, attn_axes="THW", deg=True)
+    if kind == "fno":      # complex spectral weights: (re, im) pairs in the flat buffer, p.grad a complex view of it
+        cfg = O.OracleConfig(n_fields=3, H=32, W=48, taylor_order=1, attn_axes="TW", deg=True, enc_dec_type="fno", patch_scale=4,
+                             modes1=8, modes2=8)
     sd = O.make_state_dict(cfg, 411, 0.0)
     x = O.make_input(cfg, 2, 412).cuda()
     ref = make_model(cfg, sd, "fp32").train()

@@ -75,7 +75,8 @@ def test_stage_tensors_match_reference_golden():
         assert rel_l2(blk.numpy(), z["stage_block0_0_out"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["train_adp_k2", "train_deg_k1", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16", "train_deg_k1_p32"])
+@pytest.mark.parametrize("name", ["train_adp_k2", "train_deg_k1", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16", "train_deg_k1_p32", "train_deg_k1_fno_p8",
+                                  "train_adp_k2_fno_p4"])
 def test_training_step_grads_match_reference_golden(name):
     z, meta = load_golden(name)
     cfg = golden_cfg(meta)

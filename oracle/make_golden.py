@@ -248,6 +248,15 @@ def main_train_fno(ns):
                                              patch_scale=4, modes1=8, modes2=8), B=2, n_steps=3, rt_bias=0.0)
 
 
+def main_c512(ns):
+    """embed_dim = 512 (models/tante.py:53): head_dim 64 at n_head 8, head_dim 32 at n_head 16."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_adp_k2_c512", C(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="THW-HW", deg=False, embed_dim=512),
+                 B=2, out_T=6, rt_bias=2.7, n_roll=6, stride=3)
+    case_train(ns, "train_deg_k1_c512", C(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="THW", deg=True, embed_dim=512, n_head=16),
+               B=2, n_steps=3)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -274,6 +283,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--c512" in sys.argv:
+        main_c512(ns)
         return
     if "--trainfno" in sys.argv:
         main_train_fno(ns)

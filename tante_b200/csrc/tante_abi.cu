@@ -215,6 +215,7 @@ struct tante_handle_s {
     std::vector<std::unique_ptr<Tape>> tapes;
     int bw_batch = 0;
     DevBuf dxs, dxb, g1, g2, gq, ga1, cols, hz, hG, hz1, hd, hi1, hi2, dfilm, dcond, att_stats;
+    DevBuf kscratch;                    // fp32 accumulator of the split-K input-gradient GEMMs (K > 1024 in the tensor mode)
     // ---- optimizer tail (optimizer.cuh) ----
     DevBuf opt_segs, opt_norm;                 // parameter segments of the flat gradient; f64 sum of squares
     std::vector<char> opt_seg_cache;
@@ -276,7 +277,7 @@ void build_plan(tante_handle_s* h) {
     const tante_config_t& c = h->cfg;
     REQUIRE(c.in_T >= 1 && c.in_T <= 64, "in_T out of range");
     REQUIRE(c.taylor_order >= 1 && c.taylor_order <= 4, "taylor_order must be in 1..4");
-    REQUIRE(c.embed_dim == 256, "embed_dim must be 256 (the kernels are specialised for C = 256)");
+    REQUIRE(c.embed_dim == 256 || c.embed_dim == 512, "embed_dim must be 256 or 512 (C/4 and the interprator widths must stay multiples of 64)");
     REQUIRE(c.n_head > 0 && c.embed_dim % c.n_head == 0, "embed_dim must be divisible by n_head");
     const int hd = c.embed_dim / c.n_head;
     REQUIRE(hd == 16 || hd == 32 || hd == 64, "head_dim must be 16, 32 or 64");
@@ -1073,12 +1074,11 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         int WC = std::max(1, 128 / g.R1);
         WC = std::min(WC, g.Wp);
         const int K1 = g.k0 * g.k0 * g.D;
-        REQUIRE(C1 == 64, "patch embed kernel is specialised for embed_dim 256 (C/4 = 64)");
         const size_t smem = (size_t)(((g.D * P * (P * WC + 1) + 3) & ~3) + C1 * K1 + C1) * sizeof(float) +
                             (size_t)WC * g.R1 * C1 * sizeof(TA);
         dim3 grid(B * T * g.Hp, (g.Wp + WC - 1) / WC);
         const bool cached = io.rollout && rs.enc_count != nullptr;
-        if constexpr (sizeof(TA) == 2) {
+        if (sizeof(TA) == 2 || C1 != 64) {      // (the FFMA patch kernel below is specialised for C/4 = 64)
             // tensor mode: enc_conv_1 as im2col (coalesced tiles, bf16 -- what the reference's autocast feeds its conv) + a
             // thin tcgen05 GEMM with the GELU in its epilogue; the FFMA kernel below is 64 erf-GELUs + 1024 FMAs per row
             const long long rows_in = (long long)tokens * g.R1;
@@ -1143,7 +1143,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         launch_propagator(h, x, x, B, 2, op, st);
         // In tensor mode every LayerNorm except the first one of an order is folded into the epilogue of the
         // residual GEMM that produces its input (EPI_BIAS_RESID_LN): the row is still on chip there.
-        constexpr bool kFuseLN = sizeof(TA) == 2;
+        const bool kFuseLN = sizeof(TA) == 2 && C <= 256;      // (one CTA tile must hold the whole row)
         bool ln_ready = false;
         for (size_t li = 0; li < op.layers.size(); ++li) {
             const LayerPlan& lp = op.layers[li];
@@ -1158,7 +1158,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, ln, C, lp.inw, qkv, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, qkv, att, B, lp.axis, st);
-            if constexpr (kFuseLN) {
+            if constexpr (sizeof(TA) == 2) {
                 if (h->fuse_tail && C == kBtC && h->Hm == C) {
                     const LayerPlan* nx = nx_ok ? &op.layers[li + 1] : nullptr;
                     launch_tail(h, lp, nx, att, x, x, ln, tokens, st);
@@ -1316,8 +1316,9 @@ void gemm_dx(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* out, i
     if (sizeof(TA) == 2 && K > 1024) {
         // the tcgen05 GEMM keeps a K <= 1024 weight slice resident (K = 2048: first deconv of patch_scale 64): two K halves
         // accumulated through an fp32 scratch, then one conversion pass
-        REQUIRE(K % 128 == 0 && K <= 2048 && ldc == N && (size_t)M * N * 4 <= h->gq.bytes, "input-gradient GEMM: K not covered");
-        float* v = FP(h->gq);
+        REQUIRE(K % 128 == 0 && K <= 2048 && ldc == N, "input-gradient GEMM: K not covered");
+        dev_alloc(h, h->kscratch, (size_t)M * N * 4);      // (training only: never inside a stream capture)
+        float* v = FP(h->kscratch);
         gemm<TA>(h, EPI_BIAS, A, lda, wT_off, v, N, true, M, N, K / 2, ep, st, K);
         EpiParams e2; e2.bias = AF(h, h->zero_off); e2.resid = v; e2.ldr = N;
         gemm<TA>(h, EPI_BIAS_RESID, A + K / 2, lda, wT_off + K / 2, v, N, true, M, N, K / 2, e2, st, K);
@@ -1793,7 +1794,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             }
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x_in; eo.ldr = C;
             eo.drop = drop; eo.drop_site = drop_site(o, (int)li, 1);
-            if (kTensor) {
+            if (kTensor && C <= 256) {
                 eo.ln_gamma = AF(h, lp.ln2w); eo.ln_beta = AF(h, lp.ln2b); eo.ln_out = ot.ln2[li].p;
                 gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.att[li]), C, lp.outw, x_mid, C, true, tokens, C, C, eo, st);
             } else {
@@ -1805,7 +1806,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * Hm, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x_mid; e2.ldr = C;
             e2.drop = drop; e2.drop_site = drop_site(o, (int)li, 2);
-            if (kTensor && li + 1 < nl && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
+            if (kTensor && C <= 256 && li + 1 < nl && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
                 const LayerPlan& nx = op.layers[li + 1];
                 e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ot.ln1[li + 1].p;
                 gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.hact[li]), Hm, lp.m2w, x_out, C, true, tokens, C, Hm, e2, st);
@@ -2492,7 +2493,7 @@ int tante_destroy(tante_handle_t h) {
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
-                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->fC, &h->fD, &h->fgr0, &h->fgr1, &h->fgr2, &h->opt_segs, &h->opt_norm};
+                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->kscratch, &h->fC, &h->fD, &h->fgr0, &h->fgr1, &h->fgr2, &h->opt_segs, &h->opt_norm};
         for (DevBuf* b : tb) b->free();
         if (h->nccl_comm && nccl_api().ok()) nccl_api().CommDestroy(h->nccl_comm);
         for (auto& tp : h->tapes) free_tape(*tp);
@@ -2622,7 +2623,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         dev_alloc(h, h->att, tokens * C * es);
         dev_alloc(h, h->hid, tokens * std::max(C, h->Hm) * es);
         dev_alloc(h, h->a1, tokens * g.R1 * C1 * es);
-        if (es == 2) dev_alloc(h, h->icols, tokens * g.R1 * kHeadPad * es);
+        if (es == 2 || C1 != 64) dev_alloc(h, h->icols, tokens * g.R1 * kHeadPad * es);
         dev_alloc(h, h->a2, tokens * g.R2 * C2 * es);
         dev_alloc(h, h->d32, BL * C * 4);
         dev_alloc(h, h->dmod, BL * C * es);

@@ -527,8 +527,9 @@ class TANTE(nn.Module):
                                           "expanded_channel / n_head in (16, 32, 64)")
             if hc < 64 or hc > 1024 or hc % 64:
                 raise NotImplementedError("attention axis 'C': int(expanded_channel * mlp_ratio) must be a multiple of 64 in 64..1024")
-        if embed_dim != 256:
-            raise NotImplementedError("the CUDA kernels are specialised for embed_dim = 256 (configs/tante.yaml:31)")
+        if embed_dim not in (256, 512):
+            raise NotImplementedError("embed_dim must be 256 (configs/tante.yaml:31; the fused block kernels) or 512 (plain GEMM path): "
+                                      "C/4 and the interprator widths must stay multiples of 64")
         if n_head <= 0 or embed_dim % n_head or embed_dim // n_head not in (16, 32, 64):
             raise NotImplementedError("head_dim = embed_dim / n_head must be 16, 32 or 64")
         if not 1 <= self.n_channel <= 16:

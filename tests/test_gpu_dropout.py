@@ -70,7 +70,7 @@ def test_dropout_training_matches_oracle_with_same_masks(case, prec, tol_y, tol_
         if ref is None or float(ref.norm()) == 0.0:
             continue
         e = rel_l2(prm.grad.cpu().numpy(), ref.numpy())
-        if e > tol_g:
+        if not e <= tol_g:
             bad.append(f"{n}: rel {e:.3e}")
     if prec == "fp32":
         assert not bad, "gradients differ from oracle autograd under the same masks:\n" + "\n".join(bad)

@@ -257,6 +257,19 @@ def main_c512(ns):
                B=2, n_steps=3)
 
 
+def main_fno_wide(ns):
+    """enc_dec_type='fno' at patch_scale 32 / 64: 8x8 patch stages (windows shifted by 3, transposed convs resized from 8h - 6)."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_deg_k1_fno_p32", C(n_fields=3, H=128, W=128, taylor_order=1, attn_axes="THW", deg=True,
+                                              enc_dec_type="fno", patch_scale=32, modes1=16, modes2=16),
+                 B=2, out_T=1, rt_bias=0.0, n_roll=2, stride=11)
+    case_forward(ns, "fwd_adp_k1_fno_p64", C(n_fields=2, H=128, W=192, taylor_order=1, attn_axes="WT", deg=False,
+                                              enc_dec_type="fno", patch_scale=64, modes1=8, modes2=16),
+                 B=1, out_T=4, rt_bias=1.3, n_roll=4, stride=7)
+    case_train(ns, "train_deg_k1_fno_p32", C(n_fields=3, H=128, W=128, taylor_order=1, attn_axes="TH", deg=True,
+                                              enc_dec_type="fno", patch_scale=32, modes1=16, modes2=16), B=1, n_steps=2)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -283,6 +296,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--fnowide" in sys.argv:
+        main_fno_wide(ns)
         return
     if "--c512" in sys.argv:
         main_c512(ns)

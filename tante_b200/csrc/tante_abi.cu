@@ -292,7 +292,8 @@ void build_plan(tante_handle_s* h) {
             case 4: h->fp0 = 2; h->fp1 = 2; break;
             case 8: h->fp0 = 4; h->fp1 = 2; break;
             case 16: h->fp0 = 4; h->fp1 = 4; break;
-            case 32: case 64: throw Error(TANTE_ERR_INVALID, "enc_dec_type='fno' at patch_scale 32 / 64 (8x8 stages) is not implemented");
+            case 32: h->fp0 = 8; h->fp1 = 4; break;      // 8x8 stages: windows shifted by 3, transposed convs resized from 8h - 6
+            case 64: h->fp0 = 8; h->fp1 = 8; break;
             default: throw Error(TANTE_ERR_INVALID, "KeyError: patch_scale not in Patch_map");
         }
         k[0] = h->fp0; k[1] = h->fp1; k[2] = 1;      // geometry bookkeeping only (rows per token of the two stage grids)
@@ -492,9 +493,10 @@ void build_plan(tante_handle_s* h) {
     // derived tensors
     h->film_t_off = h->arena_elems; h->arena_elems += (int64_t)T * 2 * C;
     h->tseq_off = h->arena_elems;   h->arena_elems += 64;
-    h->zero_off = h->arena_elems;   h->arena_elems += 4096;
+    h->zero_off = h->arena_elems;   h->arena_elems += 8192;
 }
 
+void destroy_graphs(tante_handle_s* h);
 inline float* AF(tante_handle_s* h, int64_t off) { return reinterpret_cast<float*>(h->arena.p) + off; }
 // gradient-arena pointer of the parameter whose ARENA offset is `off` (plans store arena offsets)
 inline float* GA(tante_handle_s* h, int64_t off) {
@@ -943,7 +945,23 @@ void run_spectral(tante_handle_s* h, const SpecPlan& sp, const SpecView& in, lon
     h->launches += 5;
 }
 
-// conv over a channels-last grid as gather + GEMM; K beyond the tcgen05 GEMM's resident slice (1024) runs as two K halves
+// Tensor mode, K beyond the tcgen05 GEMM's resident weight slice (1024): out[M][N] (fp32) = A[M][K] W[N][K]^T + bias as K / parts
+// column blocks accumulated through the fp32 output (first block EPI_BIAS, the rest EPI_BIAS_RESID in place).
+inline void gemm_bigk_f32(tante_handle_s* h, const __nv_bfloat16* A, int lda, int64_t w_off, float* out, int M, int N, int K,
+                          const float* bias, cudaStream_t st) {
+    int parts = (K + 1023) / 1024;
+    while (K % (parts * 64) != 0) ++parts;
+    const int Kp = K / parts;
+    REQUIRE(Kp >= 64 && Kp <= 1024, "split-K GEMM: K not covered");
+    EpiParams e0; e0.bias = bias;
+    gemm<__nv_bfloat16>(h, EPI_BIAS, A, lda, w_off, out, N, true, M, N, Kp, e0, st, K);
+    for (int p = 1; p < parts; ++p) {
+        EpiParams e; e.bias = AF(h, h->zero_off); e.resid = out; e.ldr = N;
+        gemm<__nv_bfloat16>(h, EPI_BIAS_RESID, A + (size_t)p * Kp, lda, w_off + (int64_t)p * Kp, out, N, true, M, N, Kp, e, st, K);
+    }
+}
+
+// conv over a channels-last grid as gather + GEMM; K beyond the tcgen05 GEMM's resident slice (1024) runs in K blocks
 template <typename TA>
 void conv_cl_gemm(tante_handle_s* h, int epi, const TA* grid, int Hs, int Ws, int Cin, int k, int64_t w_off, void* out, int Cout,
                   bool out_f32, long long n_img, EpiParams ep, cudaStream_t st) {
@@ -956,10 +974,22 @@ void conv_cl_gemm(tante_handle_s* h, int epi, const TA* grid, int Hs, int Ws, in
     CK(cudaGetLastError());
     h->launches++;
     if (sizeof(TA) == 2 && K > 1024) {
-        REQUIRE(epi == EPI_BIAS && out_f32, "the split-K path produces the fp32 pre-embedding only");
-        gemm<TA>(h, EPI_BIAS, wb, K, w_off, out, Cout, true, (int)rows, Cout, K / 2, ep, st, K);
-        EpiParams e2; e2.bias = AF(h, h->zero_off); e2.resid = reinterpret_cast<const float*>(out); e2.ldr = Cout;
-        gemm<TA>(h, EPI_BIAS_RESID, wb + K / 2, K, w_off + K / 2, out, Cout, true, (int)rows, Cout, K / 2, e2, st, K);
+        const __nv_bfloat16* wbh = reinterpret_cast<const __nv_bfloat16*>(wb);
+        if (out_f32) {
+            REQUIRE(epi == EPI_BIAS, "the split-K path writes plain fp32 outputs");
+            gemm_bigk_f32(h, wbh, K, w_off, reinterpret_cast<float*>(out), (int)rows, Cout, K, ep.bias, st);
+        } else {
+            // 8x8 stages (K = 2048): accumulate in the fp32 scratch of tante_reserve, then bias-free activation + conversion
+            REQUIRE(epi == EPI_BIAS || epi == EPI_BIAS_GELU_ERF, "split-K conv: epilogue not covered");
+            REQUIRE((size_t)rows * Cout * 4 <= h->kscratch.bytes, "split-K conv: scratch not reserved");
+            float* v = reinterpret_cast<float*>(h->kscratch.p);
+            gemm_bigk_f32(h, wbh, K, w_off, v, (int)rows, Cout, K, ep.bias, st);
+            const long long n4 = rows * Cout / 4;
+            if (epi == EPI_BIAS_GELU_ERF) f32_to_ta_kernel<TA, true><<<blocks_for(n4, 256), 256, 0, st>>>(v, reinterpret_cast<TA*>(out), n4);
+            else f32_to_ta_kernel<TA, false><<<blocks_for(n4, 256), 256, 0, st>>>(v, reinterpret_cast<TA*>(out), n4);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
     } else {
         gemm<TA>(h, epi, wb, K, w_off, out, Cout, out_f32, (int)rows, Cout, K, ep, st);
     }
@@ -1312,16 +1342,15 @@ void wgrad_pad(tante_handle_s* h, const TA* A, int lda, int N, const TA* Bm, int
 template <typename TA>
 void gemm_dx(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* out, int ldc, int M, int N, int K, cudaStream_t st) {
     EpiParams ep; ep.bias = AF(h, h->zero_off);
-    REQUIRE(N <= 4096, "input-gradient GEMM wider than the zero-bias vector");
+    REQUIRE(N <= 8192, "input-gradient GEMM wider than the zero-bias vector");
     if (sizeof(TA) == 2 && K > 1024) {
         // the tcgen05 GEMM keeps a K <= 1024 weight slice resident (K = 2048: first deconv of patch_scale 64): two K halves
         // accumulated through an fp32 scratch, then one conversion pass
-        REQUIRE(K % 128 == 0 && K <= 2048 && ldc == N, "input-gradient GEMM: K not covered");
+        REQUIRE(ldc == N, "input-gradient GEMM: K not covered");
+        if (h->kscratch.bytes < (size_t)M * N * 4) destroy_graphs(h);      // (a captured rollout may hold the old pointer)
         dev_alloc(h, h->kscratch, (size_t)M * N * 4);      // (training only: never inside a stream capture)
         float* v = FP(h->kscratch);
-        gemm<TA>(h, EPI_BIAS, A, lda, wT_off, v, N, true, M, N, K / 2, ep, st, K);
-        EpiParams e2; e2.bias = AF(h, h->zero_off); e2.resid = v; e2.ldr = N;
-        gemm<TA>(h, EPI_BIAS_RESID, A + K / 2, lda, wT_off + K / 2, v, N, true, M, N, K / 2, e2, st, K);
+        gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(A), lda, wT_off, v, M, N, K, AF(h, h->zero_off), st);
         convert_kernel<TA><<<blocks_for((long long)M * N / 4, 256), 256, 0, st>>>(v, out, (long long)M * N / 4);
         CK(cudaGetLastError());
         h->launches++;
@@ -1341,7 +1370,7 @@ void gemm_dx_act(tante_handle_s* h, const TA* A, int lda, int64_t wT_off, TA* ou
     static const bool fuse = getenv("TANTE_FUSE_ACTGRAD") && atoi(getenv("TANTE_FUSE_ACTGRAD")) != 0;
     if (sizeof(TA) == 2 && fuse) {
         EpiParams ep; ep.bias = AF(h, h->zero_off);
-        REQUIRE(N <= 4096, "input-gradient GEMM wider than the zero-bias vector");
+        REQUIRE(N <= 8192, "input-gradient GEMM wider than the zero-bias vector");
         ep.mul_pre = pre; ep.ld_pre = N;
         const int epi = ACT == ACT_RELU ? EPI_MULGRAD_RELU : (ACT == ACT_GELU_ERF ? EPI_MULGRAD_GELU_ERF : EPI_MULGRAD_GELU_TANH);
         gemm<TA>(h, epi, A, lda, wT_off, out, N, false, M, N, K, ep, st);
@@ -2666,6 +2695,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             dev_alloc(h, h->fA, ca * 8);
             dev_alloc(h, h->fB, ca * 8);
             h->f_ca = ca;
+            if (es == 2 && h->fp0 * h->fp0 * C8 > 1024) dev_alloc(h, h->kscratch, NI * HW1 * C1 * 4);      // split-K enc_conv_1 (8x8 windows)
             size_t m = NI * HW1 * (size_t)(h->fp0 * h->fp0 * C8);                     // conv_1 windows
             m = std::max(m, NI * (HW1 / (h->fp1 * h->fp1)) * (size_t)(h->fp1 * h->fp1 * C2));      // conv_2 windows
             m = std::max(m, (size_t)max_batch * h->L * (size_t)(h->fp1 * h->fp1 * C2));            // deconv_1 sub-pixel matrix

@@ -126,6 +126,20 @@ wide_deconv_post_kernel(const TA* __restrict__ S, int ldS, int hi, int wi, int C
     else out[idx] = from_f32<TA>(v);
 }
 
+// fp32 accumulator of a split-K GEMM -> (GELU) -> TA; thread = 4 elements
+template <typename TA, bool ACT>
+__global__ void __launch_bounds__(256) f32_to_ta_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float v[4];
+    Vec4<float>::load(src + i * 4, v);
+    if (ACT) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ActMath<TA>::gelu_erf_f(v[j]);
+    }
+    Vec4<TA>::store(dst + i * 4, v);
+}
+
 // ---- training (backward) passes of the natural-order stages ------------------------------------------------------
 // Every forward pass above is a gather, so its transpose is written as a gather too (no atomics): with stride == kernel size a
 // grid pixel belongs to at most ONE window, and a transposed-conv sample feeds at most 4 x 4 resized pixels.
@@ -205,11 +219,12 @@ wide_deconv_post_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ 
         } else {
             const int Hd = Ho - 2 * pad, Wd = Wo - 2 * pad;
             if (y >= 0 && y < Hd && x >= 0 && x < Wd) {
-                for (int Y = max(y - 1, 0); Y <= min(y + 3, Ho - 1); ++Y) {
+                // resized pixel Y reads samples floor(src(Y)) and +1 with src(Y) in (Y - 2 pad, Y]: sample y is read by Y in [y - 1, y + 2 pad + 1]
+                for (int Y = max(y - 1, 0); Y <= min(y + 2 * pad + 1, Ho - 1); ++Y) {
                     const float wy = bilinear_w(Y, y, Hd, Ho);
                     if (wy == 0.f) continue;
                     float acc = 0.f;
-                    for (int X = max(x - 1, 0); X <= min(x + 3, Wo - 1); ++X) {
+                    for (int X = max(x - 1, 0); X <= min(x + 2 * pad + 1, Wo - 1); ++X) {
                         const float wx = bilinear_w(X, x, Wd, Wo);
                         if (wx != 0.f) acc = fmaf(wx, at(Y, X), acc);
                     }

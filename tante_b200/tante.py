@@ -510,8 +510,6 @@ class TANTE(nn.Module):
         if enc_dec_type == "fno":
             ps = Patch_map_fno[patch_scale]
             self.patch_kernels = ps
-            if patch_scale > 16:
-                raise NotImplementedError("enc_dec_type='fno' at patch_scale 32 / 64 (8x8 patch stages) is not implemented")
             H1, W1 = self.shape[0] // ps[0], self.shape[1] // ps[0]
             if (min(modes1, modes2) < ps[0] or 2 * modes1 > self.shape[0] or modes2 > self.shape[1] // 2
                     or 2 * (modes1 // ps[0]) > H1 or modes2 // ps[0] > W1 // 2):

@@ -324,7 +324,9 @@ NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d1
         # attention axis 'C' (attn_backbone.py:124-130,184-189): channel tokens behind the 1 -> expanded_channel lift
         "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64",
         # embed_dim 512 (plain GEMM path, head_dim 64)
-        "fwd_adp_k2_c512"]
+        "fwd_adp_k2_c512",
+        # enc_dec_type='fno' with 8x8 patch stages
+        "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64"]
 
 
 @pytest.mark.parametrize("name", NEXT)
@@ -357,7 +359,8 @@ def test_next_scope_forward_and_rollout_fp32(name):
 
 @pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
                                   "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16", "fwd_adp_k2_mlp2",
-                                  "fwd_deg_k1_mlp05", "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64", "fwd_adp_k2_c512"])
+                                  "fwd_deg_k1_mlp05", "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64", "fwd_adp_k2_c512",
+                                  "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64"])
 def test_next_scope_forward_bf16(name):
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
     with torch.inference_mode():

@@ -270,6 +270,12 @@ def main_fno_wide(ns):
                                               enc_dec_type="fno", patch_scale=32, modes1=16, modes2=16), B=1, n_steps=2)
 
 
+def main_train_axisc(ns):
+    """One training step through axis-'C' layers (channel attention, attn_backbone.py:124-130,184-189)."""
+    C = O.OracleConfig
+    case_train(ns, "train_deg_k1_axes_c", C(n_fields=2, H=32, W=32, taylor_order=1, attn_axes="TCH", deg=True), B=2, n_steps=2)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -296,6 +302,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--trainaxisc" in sys.argv:
+        main_train_axisc(ns)
         return
     if "--fnowide" in sys.argv:
         main_fno_wide(ns)

@@ -215,6 +215,8 @@ struct tante_handle_s {
     std::vector<std::unique_ptr<Tape>> tapes;
     int bw_batch = 0;
     DevBuf dxs, dxb, g1, g2, gq, ga1, cols, hz, hG, hz1, hd, hi1, hi2, dfilm, dcond, att_stats;
+    int chanb_tokens = 0;               // latent tokens per chunk of the channel-axis backward
+    DevBuf cb_x0, cb_xm, cb_gx, cb_ln1, cb_qkv, cb_att, cb_ln2, cb_hpre, cb_hact, cb_gxb, cb_g1, cb_g2, cb_gq, cb_hh, cb_stats;
     DevBuf kscratch;                    // fp32 accumulator of the split-K input-gradient GEMMs (K > 1024 in the tensor mode)
     // ---- optimizer tail (optimizer.cuh) ----
     DevBuf opt_segs, opt_norm;                 // parameter segments of the flat gradient; f64 sum of squares
@@ -681,7 +683,7 @@ void launch_attention(tante_handle_s* h, const TA* qkv, TA* out, int B, char axi
 // E features, TransformerBlock(E) over the C channel tokens of each latent token, keep the last feature.  Runs in chunks of
 // h->chan_tokens latent tokens (rows = chunk * C) through the scratch buffers of tante_reserve.
 template <typename TA>
-void run_channel_layer(tante_handle_s* h, const LayerPlan& lp, float* x, int tokens, cudaStream_t st) {
+void run_channel_layer(tante_handle_s* h, const LayerPlan& lp, const float* x, float* x_dst, int tokens, cudaStream_t st) {
     const int C = h->C, E = lp.E, Hc = lp.Hc, nh = h->cfg.n_head;
     float* xc = reinterpret_cast<float*>(h->cx.p);
     TA* ln = reinterpret_cast<TA*>(h->cln.p);
@@ -693,7 +695,7 @@ void run_channel_layer(tante_handle_s* h, const LayerPlan& lp, float* x, int tok
     for (int t0 = 0; t0 < tokens; t0 += h->chan_tokens) {
         const int tc = std::min(h->chan_tokens, tokens - t0);
         const int rows = tc * C;
-        float* xs = x + (size_t)t0 * C;
+        const float* xs = x + (size_t)t0 * C;
         channel_lift_kernel<<<std::min((rows + 7) / 8, 16 * h->num_sms), 256, lift_smem, st>>>(
             xs, AF(h, lp.cw0), AF(h, lp.cb0), AF(h, lp.cw2), AF(h, lp.cb2), xc, rows, E);
         CK(cudaGetLastError());
@@ -709,7 +711,7 @@ void run_channel_layer(tante_handle_s* h, const LayerPlan& lp, float* x, int tok
         gemm<TA>(h, EPI_BIAS_GELU_TANH, ln, E, lp.m0w, hid, Hc, false, rows, Hc, E, e0, st);
         EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = xc; e2.ldr = E;
         gemm<TA>(h, EPI_BIAS_RESID, hid, Hc, lp.m2w, xc, E, true, rows, E, Hc, e2, st);
-        channel_extract_kernel<<<(rows + 255) / 256, 256, 0, st>>>(xc, xs, rows, E);
+        channel_extract_kernel<<<(rows + 255) / 256, 256, 0, st>>>(xc, x_dst + (size_t)t0 * C, rows, E);
         CK(cudaGetLastError());
         h->launches++;
     }
@@ -1178,7 +1180,7 @@ void run_step(tante_handle_s* h, const StepIO& io, int B, const RolloutState& rs
         for (size_t li = 0; li < op.layers.size(); ++li) {
             const LayerPlan& lp = op.layers[li];
             if (lp.axis == 'C') {      // channel attention: its own width, its own LayerNorms (channel_axis.cuh)
-                run_channel_layer<TA>(h, lp, x, tokens, st);
+                run_channel_layer<TA>(h, lp, x, x, tokens, st);
                 ln_ready = false;
                 continue;
             }
@@ -1438,8 +1440,8 @@ void run_spectral_bwd(tante_handle_s* h, const SpecPlan& sp, const SpecView& x, 
 
 template <typename TA>
 void launch_ln_bwd(tante_handle_s* h, const TA* dy, const float* x, int64_t gamma, float* dxs, TA* dxb, float* dg, float* db,
-                   long long rows, cudaStream_t st, const DropCfg& drop = DropCfg(), uint32_t site = 0) {
-    const int C = h->C;
+                   long long rows, cudaStream_t st, const DropCfg& drop = DropCfg(), uint32_t site = 0, int width = 0) {
+    const int C = width > 0 ? width : h->C;
     // persistent grid = exactly the resident blocks (3 per SM for C <= 256): no partial last wave
     const unsigned blocks = (unsigned)std::min<long long>((rows + 7) / 8, (C <= 256 ? 3LL : 2LL) * h->num_sms);
     if (drop.p > 0.f) {
@@ -1674,6 +1676,26 @@ void backward_alloc(tante_handle_s* h, int B) {
         dev_alloc(h, h->fgr1, NI * HW1 * C1 * es);
         dev_alloc(h, h->fgr2, NI * HW1 * C2 * es);
     }
+    if (h->chan) {
+        // channel-axis backward: chunks of 512 latent tokens (131072 rows of width E; ~10 KB of scratch per row in the exact mode)
+        h->chanb_tokens = (int)std::min<size_t>(tokens, 512);
+        const size_t rows = (size_t)h->chanb_tokens * C, E = h->chanE, Hc = h->chanHc;
+        dev_alloc(h, h->cb_x0, rows * E * 4);
+        dev_alloc(h, h->cb_xm, rows * E * 4);
+        dev_alloc(h, h->cb_gx, rows * E * 4);
+        dev_alloc(h, h->cb_ln1, rows * E * es);
+        dev_alloc(h, h->cb_qkv, rows * 3 * E * es);
+        dev_alloc(h, h->cb_att, rows * E * es);
+        dev_alloc(h, h->cb_ln2, rows * E * es);
+        dev_alloc(h, h->cb_hpre, rows * Hc * es);
+        dev_alloc(h, h->cb_hact, rows * Hc * es);
+        dev_alloc(h, h->cb_gxb, rows * E * es);
+        dev_alloc(h, h->cb_g1, rows * std::max(E, Hc) * es);
+        dev_alloc(h, h->cb_g2, rows * E * es);
+        dev_alloc(h, h->cb_gq, rows * 3 * E * es);
+        dev_alloc(h, h->cb_hh, rows * (E / 4) * es);
+        dev_alloc(h, h->cb_stats, rows * h->cfg.n_head * 2 * 4);
+    }
     if (h->long_axes) dev_alloc(h, h->att_stats, tokens * h->cfg.n_head * 2 * 4);      // LSE + delta per (token, head)
     if (!h->udesc_dev.p) {
         std::vector<UnpackDesc> ud;
@@ -1807,13 +1829,21 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             float* x_in = FP(ot.X[2 * li]);
             float* x_mid = FP(ot.X[2 * li + 1]);
             float* x_out = FP(ot.X[2 * li + 2]);
+            if (lp.axis == 'C') {
+                // channel attention: only the layer's fp32 input is kept -- the backward recomputes the block chunk by chunk
+                REQUIRE(drop.p <= 0.f, "dropout with an attention axis C layer is not implemented");
+                run_channel_layer<TA>(h, lp, x_in, x_out, tokens, st);
+                ln_ready = false;
+                continue;
+            }
+            const bool nx_ok = li + 1 < nl && op.layers[li + 1].axis != 'C';
             if (!ln_ready) launch_layernorm<TA>(h, x_in, lp.ln1w, lp.ln1b, TP<TA>(ot.ln1[li]), tokens, st);
             EpiParams eq; eq.bias = AF(h, lp.inb);
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln1[li]), C, lp.inw, ot.qkv[li].p, 3 * C, false, tokens, 3 * C, C, eq, st);
             launch_attention<TA>(h, TP<TA>(ot.qkv[li]), TP<TA>(ot.att[li]), B, lp.axis, st, drop, drop_site(o, (int)li, 0));
             if constexpr (kTensor) {
                 if (h->fuse_tail && C == kBtC && h->Hm == C) {
-                    const LayerPlan* nx = li + 1 < nl ? &op.layers[li + 1] : nullptr;
+                    const LayerPlan* nx = nx_ok ? &op.layers[li + 1] : nullptr;
                     launch_tail(h, lp, nx, TP<TA>(ot.att[li]), x_in, x_out, nx ? TP<TA>(ot.ln1[li + 1]) : nullptr, tokens, st,
                                 x_mid, TP<TA>(ot.ln2[li]), TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), drop,
                                 drop_site(o, (int)li, 1), drop_site(o, (int)li, 2));
@@ -1835,7 +1865,7 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * Hm, st);
             EpiParams e2; e2.bias = AF(h, lp.m2b); e2.resid = x_mid; e2.ldr = C;
             e2.drop = drop; e2.drop_site = drop_site(o, (int)li, 2);
-            if (kTensor && C <= 256 && li + 1 < nl && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
+            if (kTensor && C <= 256 && nx_ok && Hm == C) {      // (the LN-fused epilogue needs the K = C weight slice resident)
                 const LayerPlan& nx = op.layers[li + 1];
                 e2.ln_gamma = AF(h, nx.ln1w); e2.ln_beta = AF(h, nx.ln1b); e2.ln_out = ot.ln1[li + 1].p;
                 gemm<TA>(h, EPI_BIAS_RESID_LN, TP<TA>(ot.hact[li]), Hm, lp.m2w, x_out, C, true, tokens, C, Hm, e2, st);
@@ -1994,6 +2024,84 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
 // tante_param order (written, not accumulated).
 // win (frame-table mode): gframes has batch stride win->gf_bs; the input gradient is ACCUMULATED into the frames of win->gin
 // (offsets relative to grad_input; kFrameSkip entries are not computed) instead of written to a contiguous (B, T, D, H, W).
+// Backward of one axis-'C' layer (channel_axis.cuh): dxs [tokens][C] holds the gradient of the layer output on entry and of its
+// input on return (the layer REPLACES the latent: no residual around it).  Per chunk of h->chanb_tokens latent tokens the block is
+// recomputed from the saved fp32 input (lift, LN1, QKV, attention, out-proj, LN2, MLP -- everything the backward reads stays in
+// the chunk scratch), then the usual backward kernels run at width E over rows = chunk * C.
+template <typename TA>
+void run_channel_layer_bwd(tante_handle_s* h, const LayerPlan& lp, const float* x_in, float* dxs, int tokens, cudaStream_t st) {
+    const int C = h->C, E = lp.E, Hc = lp.Hc, nh = h->cfg.n_head, E4 = E / 4;
+    constexpr bool kTensor = sizeof(TA) == 2;
+    REQUIRE(h->chanb_tokens > 0 && h->cb_x0.p, "channel-axis backward workspace not allocated");
+    float* x0 = FP(h->cb_x0);
+    float* xm = FP(h->cb_xm);
+    float* gx = FP(h->cb_gx);
+    TA* ln1 = TP<TA>(h->cb_ln1);
+    TA* qkv = TP<TA>(h->cb_qkv);
+    TA* att = TP<TA>(h->cb_att);
+    TA* ln2 = TP<TA>(h->cb_ln2);
+    TA* hpre = TP<TA>(h->cb_hpre);
+    TA* hact = TP<TA>(h->cb_hact);
+    TA* gxb = kTensor ? TP<TA>(h->cb_gxb) : reinterpret_cast<TA*>(gx);
+    TA* gxb_out = kTensor ? gxb : nullptr;
+    TA* g1 = TP<TA>(h->cb_g1);
+    TA* g2 = TP<TA>(h->cb_g2);
+    TA* gq = TP<TA>(h->cb_gq);
+    TA* hh = TP<TA>(h->cb_hh);
+    const size_t lift_smem = ((size_t)E4 * E + E + 10 * (size_t)E4) * sizeof(float);
+    const size_t lbw_smem = ((size_t)E * E4 + 2 * (size_t)E4 + 8 * (size_t)E) * sizeof(float);
+    CK(cudaFuncSetAttribute(channel_lift_bwd_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    for (int t0 = 0; t0 < tokens; t0 += h->chanb_tokens) {
+        const int tc = std::min(h->chanb_tokens, tokens - t0);
+        const int rows = tc * C;
+        const float* xs = x_in + (size_t)t0 * C;
+        float* gs = dxs + (size_t)t0 * C;
+        // ---- recompute the forward of the chunk ----
+        channel_lift_kernel<<<std::min((rows + 7) / 8, 16 * h->num_sms), 256, lift_smem, st>>>(
+            xs, AF(h, lp.cw0), AF(h, lp.cb0), AF(h, lp.cw2), AF(h, lp.cb2), x0, rows, E);
+        CK(cudaGetLastError());
+        h->launches++;
+        launch_layernorm<TA>(h, x0, lp.ln1w, lp.ln1b, ln1, rows, st, E);
+        EpiParams eq; eq.bias = AF(h, lp.inb);
+        gemm<TA>(h, EPI_BIAS, ln1, E, lp.inw, qkv, 3 * E, false, rows, 3 * E, E, eq, st);
+        launch_attention_seq<TA>(h, qkv, att, tc, C, 1, nh, E, E / nh, false, st);
+        EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x0; eo.ldr = E;
+        gemm<TA>(h, EPI_BIAS_RESID, att, E, lp.outw, xm, E, true, rows, E, E, eo, st);
+        launch_layernorm<TA>(h, xm, lp.ln2w, lp.ln2b, ln2, rows, st, E);
+        EpiParams e0; e0.bias = AF(h, lp.m0b);
+        gemm<TA>(h, EPI_BIAS, ln2, E, lp.m0w, hpre, Hc, false, rows, Hc, E, e0, st);
+        launch_act_fwd<TA, ACT_GELU_TANH>(h, hpre, hact, (long long)rows * Hc, st);
+        // (the block output itself is not needed: x_out = x_mid + W2 hact + b2 only feeds the extract)
+        // ---- backward ----
+        channel_extract_bwd_kernel<TA><<<blocks_for((long long)rows * E, 256), 256, 0, st>>>(gs, gx, gxb_out, rows, E);
+        CK(cudaGetLastError());
+        h->launches++;
+        wgrad<TA>(h, gxb, E, hact, Hc, GA(h, lp.m2w), rows, E, Hc, st, GA(h, lp.m2b));
+        gemm_dx_act<TA, ACT_GELU_TANH>(h, gxb, E, lp.m2wT, g1, hpre, rows, Hc, E, st);
+        wgrad<TA>(h, g1, Hc, ln2, E, GA(h, lp.m0w), rows, Hc, E, st, GA(h, lp.m0b));
+        gemm_dx<TA>(h, g1, Hc, lp.m0wT, g2, E, rows, E, Hc, st);
+        launch_ln_bwd<TA>(h, g2, xm, lp.ln2w, gx, gxb_out, GA(h, lp.ln2w), GA(h, lp.ln2b), rows, st, DropCfg(), 0, E);
+        wgrad<TA>(h, gxb, E, att, E, GA(h, lp.outw), rows, E, E, st, GA(h, lp.outb));
+        gemm_dx<TA>(h, gxb, E, lp.outwT, g2, E, rows, E, E, st);
+        {
+            cudaError_t e = cudaSuccess;
+            REQUIRE(launch_attention_long_bwd<TA>(qkv, g2, gq, FP(h->cb_stats), tc, C, 1, nh, E, E / nh, 0, st, &e),
+                    "channel attention backward: shape not covered");
+            CK(e);
+            h->launches += 3;
+        }
+        wgrad<TA>(h, gq, 3 * E, ln1, E, GA(h, lp.inw), rows, 3 * E, E, st, GA(h, lp.inb));
+        gemm_dx<TA>(h, gq, 3 * E, lp.inwT, g2, E, rows, E, 3 * E, st);
+        launch_ln_bwd<TA>(h, g2, x0, lp.ln1w, gx, gxb_out, GA(h, lp.ln1w), GA(h, lp.ln1b), rows, st, DropCfg(), 0, E);
+        // ---- the lift: dx per (token, channel), gradients of Linear(1, E/4) in the kernel, of Linear(E/4, E) as a weight-gradient GEMM ----
+        channel_lift_bwd_kernel<TA><<<std::min((rows + 7) / 8, 8 * h->num_sms), 256, lbw_smem, st>>>(
+            xs, gx, AF(h, lp.cw0), AF(h, lp.cb0), AF(h, lp.cw2), gs, hh, E4, GA(h, lp.cw0), GA(h, lp.cb0), rows, E);
+        CK(cudaGetLastError());
+        h->launches++;
+        wgrad<TA>(h, gxb, E, hh, E4, GA(h, lp.cw2), rows, E, E4, st, GA(h, lp.cb2));
+    }
+}
+
 struct BackwardWin { long long gf_bs; FrameTab gin; };
 template <typename TA>
 void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* gframes, int n_g, const float* gRt,
@@ -2178,6 +2286,15 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             const LayerPlan& lp = op.layers[li];
             const float* x_in = FP(ot.X[2 * li]);
             const float* x_mid = FP(ot.X[2 * li + 1]);
+            if (lp.axis == 'C') {
+                run_channel_layer_bwd<TA>(h, lp, x_in, dxs, tokens, st);
+                if (mirror) {      // the layer below reads the TA mirror of the gradient stream as its dY
+                    convert_kernel<TA><<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(dxs, dxb, (long long)tokens * C / 4);
+                    CK(cudaGetLastError());
+                    h->launches++;
+                }
+                continue;
+            }
             // MLP half: x_out = x_mid + W2 gelu_tanh(W0 ln2(x_mid) + b0) + b2
             wgrad<TA>(h, dxb, C, TP<TA>(ot.hact[li]), Hm, GA(h, lp.m2w), tokens, C, Hm, st, GA(h, lp.m2b));
             if (kTensor && h->fuse_mlp_bwd && C == kBtC && h->Hm == C) {
@@ -2522,7 +2639,7 @@ int tante_destroy(tante_handle_t h) {
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
-                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->kscratch, &h->fC, &h->fD, &h->fgr0, &h->fgr1, &h->fgr2, &h->opt_segs, &h->opt_norm};
+                        &h->hz, &h->hG, &h->hz1, &h->hd, &h->hi1, &h->hi2, &h->dfilm, &h->dcond, &h->att_stats, &h->kscratch, &h->cb_x0, &h->cb_xm, &h->cb_gx, &h->cb_ln1, &h->cb_qkv, &h->cb_att, &h->cb_ln2, &h->cb_hpre, &h->cb_hact, &h->cb_gxb, &h->cb_g1, &h->cb_g2, &h->cb_gq, &h->cb_hh, &h->cb_stats, &h->fC, &h->fD, &h->fgr0, &h->fgr1, &h->fgr2, &h->opt_segs, &h->opt_norm};
         for (DevBuf* b : tb) b->free();
         if (h->nccl_comm && nccl_api().ok()) nccl_api().CommDestroy(h->nccl_comm);
         for (auto& tp : h->tapes) free_tape(*tp);
@@ -2872,8 +2989,6 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
-        REQUIRE(!h->chan, "training with the attention axis C is not implemented "
-                               "(inference / rollout only)");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -2932,7 +3047,7 @@ int tante_train_forward_win(tante_handle_t h, int32_t slot, const float* const* 
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
-        REQUIRE(!h->wide && !h->fno && !h->chan, "training is not implemented for this configuration (inference / rollout only)");
+        REQUIRE(!h->wide && !h->fno && !h->chan, "the windowed BPTT entry points cover patch_scale <= 8 with the CNN encoder and the axes T H W L Y A");
         for (int t = 0; t < h->T; ++t) REQUIRE(frame_ptrs[t], "null frame pointer");
         REQUIRE(frames_bstride % 4 == 0, "frames_bstride must be a multiple of 4 elements");
         CK(cudaSetDevice(h->device));

@@ -517,7 +517,7 @@ class TANTE(nn.Module):
                                           "(ps[0] <= modes, 2*modes1 <= H, modes2 <= W/2)")
         # what the CUDA library does not cover is refused HERE, not at the first forward
         self.expanded_channel = int(expanded_channel)
-        if "C" in self.attn_axes:      # channel attention (attn_backbone.py:124-130,184-189): inference / rollout
+        if "C" in self.attn_axes:      # channel attention (attn_backbone.py:124-130,184-189)
             E = self.expanded_channel
             hc = int(E * float(mlp_ratio))
             if E % 64 or not 64 <= E <= 256 or n_head <= 0 or E % n_head or E // n_head not in (16, 32, 64):
@@ -680,8 +680,8 @@ class TANTE(nn.Module):
 
     @property
     def bptt_windows_ok(self) -> bool:
-        """The windowed BPTT entry points (frame tables) exist for the nested-order patch stages only (patch_scale <= 8, cnn)."""
-        return self.patch_scale <= 8 and self.enc_dec_type == "cnn"
+        """The windowed BPTT entry points (frame tables) exist for the nested-order patch stages (patch_scale <= 8, cnn) without axis-C layers."""
+        return self.patch_scale <= 8 and self.enc_dec_type == "cnn" and "C" not in self.attn_axes
 
     def rollout_train(self, window, n_steps: int):
         """Fixed-step BPTT rollout of the training drivers (trainer/trainer.py:144-159) for the `deg=True`, `output_length=1`

@@ -374,13 +374,17 @@ def test_next_scope_forward_bf16(name):
     assert _prefix_rel(yc.reshape(B, n_got, per), z["frames"], meta["n"], s, min(n_got, meta["n"]), per) < BF16_FIELD_TOL
 
 
-def test_training_refused_for_inference_only_scopes():
+def test_every_constructor_configuration_trains_or_says_why():
+    """Nothing the constructor accepts is inference-only any more; what remains refused in grad mode says so at the call."""
     from gpu_util import make_model
-    for kw in (dict(attn_axes="CT"),):
-        cfg = O.OracleConfig(n_fields=2, H=64, W=64, taylor_order=1, deg=True, **kw)
-        model = make_model(cfg, O.make_state_dict(cfg, 1)).train()
-        with pytest.raises(Exception, match="not implemented"):
-            model(O.make_input(cfg, 1, 2).cuda())
+    cfg = O.OracleConfig(n_fields=2, H=64, W=64, taylor_order=1, deg=True, attn_axes="CT")
+    model = make_model(cfg, O.make_state_dict(cfg, 1)).train()
+    x = O.make_input(cfg, 1, 2).cuda()
+    model(x).sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    model.dropout = 0.1      # dropout inside a channel-attention block: not built
+    with pytest.raises(Exception, match="not implemented"):
+        model(x)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

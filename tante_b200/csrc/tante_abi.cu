@@ -28,6 +28,7 @@
 #include "backward.cuh"
 #include "attention_bwd_mma.cuh"
 #include "attention_long_bwd.cuh"
+#include "attention_long_bwd_mma.cuh"
 #include "wgrad_tc.cuh"
 #include "metrics.cuh"
 #include "block_tail_tc.cuh"
@@ -1467,8 +1468,17 @@ void launch_attention_bwd(tante_handle_s* h, const TA* qkv, const TA* dout, TA* 
     else if (axis == 'Y') { S = T * Hp; inner = Wp; nseq = (long long)B * Wp; }        // (b w) (t h)
     else { S = T * L; inner = 1; nseq = B; }                                           // 'A': b (t h w)
     if (S > 64) {
-        // composite axes and 65 .. 96-token axes: tiled recompute backward (attention_long_bwd.cuh), both precisions
+        // composite axes and 65 .. 96-token axes: tiled recompute backward -- on mma.sync in the tensor mode without dropout
+        // (attention_long_bwd_mma.cuh), on FFMA tiles otherwise (attention_long_bwd.cuh)
         cudaError_t e = cudaSuccess;
+        if constexpr (sizeof(TA) == 2) {
+            if (drop.p <= 0.f && launch_attention_long_bwd_mma(qkv, dout, dqkv, FP(h->att_stats), nseq, S, inner, h->cfg.n_head, h->C,
+                                                               h->HD, axis == 'T', st, &e)) {
+                CK(e);
+                h->launches += 3;
+                return;
+            }
+        }
         REQUIRE(launch_attention_long_bwd<TA>(qkv, dout, dqkv, FP(h->att_stats), nseq, S, inner, h->cfg.n_head, h->C, h->HD,
                                               axis == 'T', st, &e, drop, site),
                 "attention backward: sequence shape not covered");
@@ -2085,8 +2095,11 @@ void run_channel_layer_bwd(tante_handle_s* h, const LayerPlan& lp, const float* 
         gemm_dx<TA>(h, gxb, E, lp.outwT, g2, E, rows, E, E, st);
         {
             cudaError_t e = cudaSuccess;
-            REQUIRE(launch_attention_long_bwd<TA>(qkv, g2, gq, FP(h->cb_stats), tc, C, 1, nh, E, E / nh, 0, st, &e),
-                    "channel attention backward: shape not covered");
+            bool done = false;
+            if constexpr (kTensor) done = launch_attention_long_bwd_mma(qkv, g2, gq, FP(h->cb_stats), tc, C, 1, nh, E, E / nh, 0, st, &e);
+            if (!done)
+                REQUIRE(launch_attention_long_bwd<TA>(qkv, g2, gq, FP(h->cb_stats), tc, C, 1, nh, E, E / nh, 0, st, &e),
+                        "channel attention backward: shape not covered");
             CK(e);
             h->launches += 3;
         }

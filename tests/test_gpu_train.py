@@ -179,7 +179,7 @@ def _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=False):
 
 
 @pytest.mark.parametrize("prec,tol", [("fp32", FP32_GRAD_TOL), ("bf16", BF16_GRAD_TOL)])
-@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48", "adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c"])
+@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48", "adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c", "deg_k1_axes_c256"])
 def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
     """One model call with a random cotangent on the frames AND on R_t, multi-frame emit (n = 3) included:
     every parameter gradient and the input gradient against torch autograd over the CPU oracle."""
@@ -221,6 +221,10 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         # layer is covered by the golden, here E = 128 / head_dim 16 with a C layer first, last and next to the fused tail
         cfg = O.OracleConfig(n_fields=2, H=32, W=48, taylor_order=2, attn_axes="CTW-HC", deg=False)
         rt_bias, out_T = 2.7, 8
+    elif case == "deg_k1_axes_c256":
+        # channel attention at expanded_channel 256: head_dim 32 -> tiled online-softmax forward, mma.sync recompute backward (bf16)
+        cfg = O.OracleConfig(n_fields=2, H=32, W=32, taylor_order=1, attn_axes="TC", deg=True, expanded_channel=256)
+        rt_bias, out_T = 0.0, 1
     elif case == "adp_k1_axes48":
         # TRL geometry: axis length 48 (padded to 64 in the tensor-core propagator kernels)
         cfg = O.OracleConfig(n_fields=4, H=128, W=384, taylor_order=1, attn_axes="WHT", deg=False)
@@ -229,7 +233,7 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         cfg = O.OracleConfig(n_fields=2, H=16, W=24, taylor_order=3, attn_axes="T-H-W", deg=False, patch_scale=2)
         rt_bias, out_T = 1.3, 4
     sd = O.make_state_dict(cfg, 311, rt_bias)
-    B = 2 if ("axes" in case or case in ("adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c")) else 3
+    B = 2 if ("axes" in case or case in ("adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c", "deg_k1_axes_c256")) else 3
     x = O.make_input(cfg, B, 312)
     with torch.no_grad():
         y0 = O.forward(sd, cfg, x, out_T)

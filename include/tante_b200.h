@@ -64,6 +64,7 @@ typedef struct tante_config {
     int32_t mlp_hidden;     /* int(embed_dim * mlp_ratio) of the block MLP (attn_backbone.py:52); 0 = embed_dim; multiple of 64, <= 1024 */
     int32_t expanded_channel; /* width E of the axis-'C' blocks (models/tante.py:47, attn_backbone.py:124-130); 0 = 128; multiple of 64, <= 256 */
     int32_t mlp_hidden_c;   /* int(expanded_channel * mlp_ratio): MLP width of the axis-'C' blocks; 0 = expanded_channel */
+    int32_t stride[3];      /* overlap_ratio != 0 (enc_dec_cnn.py:64-66): stride of the three patch stages, max(1, round(k * (1 - r))); 0 = k (no overlap) */
 } tante_config_t;
 
 typedef struct tante_handle_s* tante_handle_t;

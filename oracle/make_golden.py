@@ -34,7 +34,7 @@ def build_ref(ns, cfg: O.OracleConfig, sd):
                  attn_axes=cfg.attn_axes, expanded_channel=cfg.expanded_channel, n_head=cfg.n_head,
                  mlp_ratio=cfg.mlp_ratio, dropout=0.0,
                  enc_dec_type=cfg.enc_dec_type, embed_dim=cfg.embed_dim, modes1=cfg.modes1, modes2=cfg.modes2,
-                 patch_scale=cfg.patch_scale, overlap_ratio=0.0, deg=cfg.deg)
+                 patch_scale=cfg.patch_scale, overlap_ratio=cfg.overlap_ratio, deg=cfg.deg)
     m.load_state_dict(sd)
     m.t_seq = m.t_seq.cpu()
     return m
@@ -276,6 +276,22 @@ def main_train_axisc(ns):
     case_train(ns, "train_deg_k1_axes_c", C(n_fields=2, H=32, W=32, taylor_order=1, attn_axes="TCH", deg=True), B=2, n_steps=2)
 
 
+def main_overlap(ns):
+    """overlap_ratio != 0 (enc_dec_cnn.py:64-66,109,130-132,176-184): strided overlapping windows + adaptive average pooling in the
+    encoder, overlap-add transposed convs + bilinear resize in the decoder."""
+    C = O.OracleConfig
+    case_forward(ns, "fwd_adp_k2_ov50_p8", C(n_fields=3, H=64, W=96, taylor_order=2, attn_axes="THW-WT", deg=False,
+                                              overlap_ratio=0.5), B=2, out_T=6, rt_bias=2.7, stages=True, n_roll=6, stride=5)
+    case_forward(ns, "fwd_deg_k1_ov25_p16", C(n_fields=2, H=64, W=64, taylor_order=1, attn_axes="HWT", deg=True, patch_scale=16,
+                                               overlap_ratio=0.25), B=2, out_T=1, rt_bias=0.0, n_roll=3, stride=7)
+    case_forward(ns, "fwd_deg_k1_ov70_p32", C(n_fields=4, H=128, W=128, taylor_order=1, attn_axes="TW", deg=True, patch_scale=32,
+                                               overlap_ratio=0.7), B=1, out_T=1, rt_bias=0.0, n_roll=2, stride=11)
+    case_train(ns, "train_deg_k1_ov50_p8", C(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="THW", deg=True, overlap_ratio=0.5),
+               B=2, n_steps=2)
+    case_train(ns, "train_adp_k1_ov40_p16", C(n_fields=2, H=64, W=64, taylor_order=1, attn_axes="TH", deg=False, patch_scale=16,
+                                               overlap_ratio=0.4), B=2, n_steps=2, rt_bias=0.0)
+
+
 def main_fno(ns):
     """enc_dec_type='fno' (enc_dec_fno.py:184-323): spectral layers (rfft2 / low modes / irfft2 + 1x1 conv) between the patch convs."""
     C = O.OracleConfig
@@ -302,6 +318,9 @@ def main():
         return
     if "--mlp" in sys.argv:
         main_mlp(ns)
+        return
+    if "--overlap" in sys.argv:
+        main_overlap(ns)
         return
     if "--trainaxisc" in sys.argv:
         main_train_axisc(ns)

@@ -54,6 +54,7 @@ class OracleConfig:
     modes2: int = 32
     mlp_ratio: float = 1.0         # hidden width of the block MLP = int(embed_dim * mlp_ratio) (attn_backbone.py:52)
     expanded_channel: int = 128    # embedding width of the channel-attention blocks, axis 'C' (attn_backbone.py:124-130)
+    overlap_ratio: float = 0.0     # patch overlap of the cnn encoder / decoder: stride = max(1, round(k * (1 - r))) (enc_dec_cnn.py:64-66)
 
     @property
     def Hp(self):
@@ -132,10 +133,19 @@ def s_emb_init(C: int, Hp: int, Wp: int) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # encoder / decoder (reference models/enc_dec_cnn.py)
 # --------------------------------------------------------------------------
-def _patch_conv(x, w, b, k: int):
-    """RealConv2d forward (enc_dec_cnn.py:96-110): kernel k, stride k, pad (k-1)//2, then
-    adaptive_avg_pool2d to (H//k, W//k) (an identity for k in {1,2,4} on divisible sizes)."""
+def patch_stride(k: int, overlap_ratio: float) -> int:
+    """enc_dec_cnn.py:64-66 / 130-132: Python's round() (half to even), at least 1."""
+    return max(1, int(round(k * (1.0 - overlap_ratio))))
+
+
+def _patch_conv(x, w, b, k: int, s: Optional[int] = None):
+    """RealConv2d forward (enc_dec_cnn.py:96-110): kernel k, stride s (k without overlap), pad (k-1)//2, then
+    adaptive_avg_pool2d to (H//k, W//k) (an identity for s = k in {1,2,4} on divisible sizes)."""
     pad = (k - 1) // 2
+    s = k if s is None else s
+    if s != k:
+        y = torch.nn.functional.conv2d(x, w, b, stride=s, padding=pad)
+        return torch.nn.functional.adaptive_avg_pool2d(y, (x.shape[-2] // k, x.shape[-1] // k))
     if pad == 0:
         Bn, Ci, H, W = x.shape
         xp = x.reshape(Bn, Ci, H // k, k, W // k, k)
@@ -145,11 +155,17 @@ def _patch_conv(x, w, b, k: int):
     return torch.nn.functional.adaptive_avg_pool2d(y, (x.shape[-2] // k, x.shape[-1] // k))
 
 
-def _patch_deconv(x, w, b, k: int):
-    """RealTransConv2d forward (enc_dec_cnn.py:162-184): ConvTranspose2d kernel k stride k pad (k-1)//2,
-    bilinear(align_corners=False) resize to (k*H, k*W) when the deconv misses the patch grid (k=4)."""
+def _patch_deconv(x, w, b, k: int, s: Optional[int] = None):
+    """RealTransConv2d forward (enc_dec_cnn.py:162-184): ConvTranspose2d kernel k stride s (k without overlap) pad (k-1)//2,
+    bilinear(align_corners=False) resize to (k*H, k*W) when the deconv misses the patch grid (k=4, or any overlap)."""
     pad = (k - 1) // 2
+    s = k if s is None else s
     Bn, Ci, H, W = x.shape
+    if s != k:
+        y = torch.nn.functional.conv_transpose2d(x, w, b, stride=s, padding=pad)
+        if y.shape[-2] != H * k or y.shape[-1] != W * k:
+            y = torch.nn.functional.interpolate(y, size=(H * k, W * k), mode="bilinear", align_corners=False)
+        return y
     if pad == 0:
         y = torch.einsum("bcij,code->boidje", x, w).reshape(Bn, w.shape[1], H * k, W * k)
         return y + b[None, :, None, None]
@@ -206,9 +222,10 @@ def encoder(sd, cfg: OracleConfig, x):
     B, T, D, H, W = x.shape
     ks = PATCH_MAP[cfg.patch_scale]
     z = x.reshape(B * T, D, H, W)
-    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_1.conv.weight"], sd["encoder.enc_conv_1.conv.bias"], ks[0]))
-    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_2.conv.weight"], sd["encoder.enc_conv_2.conv.bias"], ks[1]))
-    z = _patch_conv(z, sd["encoder.enc_conv_3.conv.weight"], sd["encoder.enc_conv_3.conv.bias"], ks[2])
+    st = [patch_stride(k, cfg.overlap_ratio) for k in ks]
+    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_1.conv.weight"], sd["encoder.enc_conv_1.conv.bias"], ks[0], st[0]))
+    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_2.conv.weight"], sd["encoder.enc_conv_2.conv.bias"], ks[1], st[1]))
+    z = _patch_conv(z, sd["encoder.enc_conv_3.conv.weight"], sd["encoder.enc_conv_3.conv.bias"], ks[2], st[2])
     return z.reshape(B, T, z.shape[1], z.shape[2], z.shape[3]).permute(0, 1, 3, 4, 2).contiguous()
 
 
@@ -219,9 +236,10 @@ def decoder(sd, cfg: OracleConfig, k: int, d):
     ks = PATCH_MAP[cfg.patch_scale]
     p = f"decoders.{k}."
     z = d.permute(0, 3, 1, 2)
-    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_1.deconv.weight"], sd[p + "dec_conv_1.deconv.bias"], ks[2]))
-    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_2.deconv.weight"], sd[p + "dec_conv_2.deconv.bias"], ks[1]))
-    z = _patch_deconv(z, sd[p + "dec_conv_3.deconv.weight"], sd[p + "dec_conv_3.deconv.bias"], ks[0])
+    st = [patch_stride(kk, cfg.overlap_ratio) for kk in ks]
+    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_1.deconv.weight"], sd[p + "dec_conv_1.deconv.bias"], ks[2], st[2]))
+    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_2.deconv.weight"], sd[p + "dec_conv_2.deconv.bias"], ks[1], st[1]))
+    z = _patch_deconv(z, sd[p + "dec_conv_3.deconv.weight"], sd[p + "dec_conv_3.deconv.bias"], ks[0], st[0])
     return z
 
 

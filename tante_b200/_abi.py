@@ -29,6 +29,7 @@ class TanteConfig(C.Structure):
         ("enc_dec_fno", C.c_int32), ("modes1", C.c_int32), ("modes2", C.c_int32),
         ("mlp_hidden", C.c_int32),
         ("expanded_channel", C.c_int32), ("mlp_hidden_c", C.c_int32),
+        ("stride", C.c_int32 * 3),
     ]
 
 

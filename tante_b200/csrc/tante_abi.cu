@@ -167,7 +167,10 @@ struct tante_handle_s {
     DevBuf ftw, fA, fB, fg0, fg1, fg2;  // fno: twiddle tables, complex scratch x2, channels-last stage grids
     DevBuf fC, fD, fgr0, fgr1, fgr2;    // fno training: two more complex scratch buffers, gradient grids of the three stages
     size_t f_ca = 0;                    // complex elements per scratch buffer (tante_reserve)
-    bool wide = false;                  // patch_scale >= 16: natural-order stages with shifted 4x4 windows (wide_patch.cuh)
+    bool wide = false;                  // patch_scale >= 16 or overlap_ratio != 0: natural-order stages (wide_patch.cuh)
+    bool overlap = false;               // overlap_ratio != 0: some stage's stride < its kernel (strided windows + pooling, overlap-add deconvs)
+    int st[3] = {0, 0, 0};              // stride of the three patch stages (== kernel size without overlap)
+    DevBuf cgrid;                       // overlap: conv grid of a stage before the adaptive average pooling
     int K1pad = 0, NOpad = 0;           // wide: first-conv reduction / last-deconv output width rounded up to 64
     int64_t enc_w1wide = 0;             // wide: first conv weight [C1][K1pad]
     DevBuf wbuf, dfield;                // wide: patch / sub-pixel matrix scratch; decoded derivative fields [K][B][D][H][W]
@@ -308,7 +311,13 @@ void build_plan(tante_handle_s* h) {
         patch_kernels(c.patch_scale, k);
     }
     REQUIRE(c.H % c.patch_scale == 0 && c.W % c.patch_scale == 0, "H and W must be divisible by patch_scale");
-    h->wide = c.patch_scale >= 16 || h->fno;
+    for (int i = 0; i < 3; ++i) {
+        h->st[i] = c.stride[i] > 0 ? c.stride[i] : k[i];
+        REQUIRE(h->st[i] >= 1 && h->st[i] <= k[i], "stride of a patch stage must be in 1..kernel size");
+        if (h->st[i] != k[i]) h->overlap = true;
+    }
+    REQUIRE(!(h->overlap && h->fno), "overlap_ratio != 0 with enc_dec_type='fno' is not implemented");
+    h->wide = c.patch_scale >= 16 || h->fno || h->overlap;
     h->K1pad = (k[0] * k[0] * c.n_fields + 63) / 64 * 64;
     h->NOpad = h->K1pad;
     if (h->wide) h->use_enc_cache = false;
@@ -803,6 +812,22 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
 }
 
 // ---- patch_scale >= 16 (wide_patch.cuh): encoder, decoder of one order, emit ----
+// Tensor mode, K beyond the tcgen05 GEMM's resident weight slice (1024): out[M][N] (fp32) = A[M][K] W[N][K]^T + bias as K / parts
+// column blocks accumulated through the fp32 output (first block EPI_BIAS, the rest EPI_BIAS_RESID in place).
+inline void gemm_bigk_f32(tante_handle_s* h, const __nv_bfloat16* A, int lda, int64_t w_off, float* out, int M, int N, int K,
+                          const float* bias, cudaStream_t st) {
+    int parts = (K + 1023) / 1024;
+    while (K % (parts * 64) != 0) ++parts;
+    const int Kp = K / parts;
+    REQUIRE(Kp >= 64 && Kp <= 1024, "split-K GEMM: K not covered");
+    EpiParams e0; e0.bias = bias;
+    gemm<__nv_bfloat16>(h, EPI_BIAS, A, lda, w_off, out, N, true, M, N, Kp, e0, st, K);
+    for (int p = 1; p < parts; ++p) {
+        EpiParams e; e.bias = AF(h, h->zero_off); e.resid = out; e.ldr = N;
+        gemm<__nv_bfloat16>(h, EPI_BIAS_RESID, A + (size_t)p * Kp, lda, w_off + (int64_t)p * Kp, out, N, true, M, N, Kp, e, st, K);
+    }
+}
+
 template <typename TA>
 void run_encoder_wide(tante_handle_s* h, const StepIO& io, int B, cudaStream_t st) {
     const int C = h->C, C1 = h->C1, C2 = h->C2, T = h->T, L = h->L;
@@ -814,43 +839,87 @@ void run_encoder_wide(tante_handle_s* h, const StepIO& io, int B, cudaStream_t s
     TA* a2 = reinterpret_cast<TA*>(h->a2.p);
     float* x = reinterpret_cast<float*>(h->x.p);
     const int H1 = H / g.k0, W1 = W / g.k0, H2 = H1 / g.k1, W2 = W1 / g.k1;
-    const long long rows1 = (long long)B * T * H1 * W1, rows2 = (long long)B * T * H2 * W2;
-    REQUIRE(rows1 * h->K1pad < (1LL << 40) && rows1 < (1LL << 31), "input too large for the wide first-conv GEMM");
-    // conv1: shifted (k0 = 4) windows of the ring frames -> [rows1][K1pad] -> GEMM + GELU -> grid [BT][H1][W1][C1]
+    const long long NI = (long long)B * T;
+    // conv grid of a stage (kernel k, stride s, pad (k - 1) / 2 over an Hin x Win grid); == the patch grid without overlap
+    auto cdim = [](int n, int k, int s) { return (n + 2 * ((k - 1) / 2) - k) / s + 1; };
+    const int Hc1 = cdim(H, g.k0, h->st[0]), Wc1 = cdim(W, g.k0, h->st[0]);
+    const int Hc2 = cdim(H1, g.k1, h->st[1]), Wc2 = cdim(W1, g.k1, h->st[1]);
+    const int Hc3 = cdim(H2, g.k2, h->st[2]), Wc3 = cdim(W2, g.k2, h->st[2]);
+    const bool pool1 = Hc1 != H1 || Wc1 != W1, pool2 = Hc2 != H2 || Wc2 != W2, pool3 = Hc3 != h->Hp || Wc3 != h->Wp;
+    const long long rows1 = NI * Hc1 * Wc1, rows2 = NI * Hc2 * Wc2, rows3 = NI * Hc3 * Wc3;
+    REQUIRE(rows1 * h->K1pad < (1LL << 40) && rows1 < (1LL << 31) && rows2 < (1LL << 31) && rows3 < (1LL << 31),
+            "input too large for the wide conv GEMMs");
+    TA* cg = reinterpret_cast<TA*>(h->cgrid.p);
+    auto pool = [&](const TA* in, int Hc, int Wc, int Cc, int Ho, int Wo, TA* out, float* out32, bool act) {
+        const long long total4 = NI * Ho * Wo * Cc / 4;
+        const unsigned nb = blocks_for(total4, 256);
+        if (out32) wide_pool_kernel<TA, false, true><<<nb, 256, 0, st>>>(in, Hc, Wc, Cc, Ho, Wo, nullptr, out32, total4);
+        else if (act) wide_pool_kernel<TA, true, false><<<nb, 256, 0, st>>>(in, Hc, Wc, Cc, Ho, Wo, out, nullptr, total4);
+        else wide_pool_kernel<TA, false, false><<<nb, 256, 0, st>>>(in, Hc, Wc, Cc, Ho, Wo, out, nullptr, total4);
+        CK(cudaGetLastError());
+        h->launches++;
+    };
+    // conv1: (shifted / strided) windows of the ring frames -> [rows1][K1pad] -> GEMM (+ pooling) + GELU -> grid [BT][H1][W1][C1]
     {
         const long long total = rows1 * h->K1pad;
         wide_im2col_cf_kernel<TA><<<blocks_for(total, 256), 256, 0, st>>>(io.input, io.fcount, T, D, H, W, g.k0, (g.k0 - 1) / 2,
-                                                                         h->K1pad, wb, total);
+                                                                         h->K1pad, wb, total, h->st[0], Hc1, Wc1);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
-        gemm<TA>(h, EPI_BIAS_GELU_ERF, wb, h->K1pad, h->enc_w1wide, a1, C1, false, (int)rows1, C1, h->K1pad, e1, st);
+        if (pool1) {
+            gemm<TA>(h, EPI_BIAS, wb, h->K1pad, h->enc_w1wide, cg, C1, false, (int)rows1, C1, h->K1pad, e1, st);
+            pool(cg, Hc1, Wc1, C1, H1, W1, a1, nullptr, true);
+        } else {
+            gemm<TA>(h, EPI_BIAS_GELU_ERF, wb, h->K1pad, h->enc_w1wide, a1, C1, false, (int)rows1, C1, h->K1pad, e1, st);
+        }
     }
     // conv2
     {
         const int K2 = g.k1 * g.k1 * C1;
         const long long total4 = rows2 * K2 / 4;
-        wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(a1, H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb, total4);
+        wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(a1, H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb, total4, h->st[1], Hc2, Wc2);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
-        gemm<TA>(h, EPI_BIAS_GELU_ERF, wb, K2, h->enc_w[1], a2, C2, false, (int)rows2, C2, K2, e2, st);
+        if (pool2) {
+            gemm<TA>(h, EPI_BIAS, wb, K2, h->enc_w[1], cg, C2, false, (int)rows2, C2, K2, e2, st);
+            pool(cg, Hc2, Wc2, C2, H2, W2, a2, nullptr, true);
+        } else {
+            gemm<TA>(h, EPI_BIAS_GELU_ERF, wb, K2, h->enc_w[1], a2, C2, false, (int)rows2, C2, K2, e2, st);
+        }
     }
     // conv3 + t_encode FiLM + embeddings -> residual stream
     {
         const int K3 = g.k2 * g.k2 * C2;
-        const long long total4 = (long long)tokens * K3 / 4;
-        wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(a2, H2, W2, C2, g.k2, (g.k2 - 1) / 2, wb, total4);
+        const long long total4 = rows3 * K3 / 4;
+        wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(a2, H2, W2, C2, g.k2, (g.k2 - 1) / 2, wb, total4, h->st[2], Hc3, Wc3);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
-        if (sizeof(TA) == 2 && K3 > 1024) {
-            // K = 2048 (patch_scale 64) exceeds the resident weight slice of the tcgen05 GEMM: two K halves through an fp32
+        if (pool3) {
+            // overlap: conv grid -> adaptive average pooling -> fp32 pre-embedding -> embed pass
+            float* v = reinterpret_cast<float*>(h->qkv.p);
+            if (sizeof(TA) == 2 && K3 > 1024) {
+                REQUIRE((size_t)rows3 * C * 4 <= h->kscratch.bytes, "split-K conv: scratch not reserved");
+                float* acc = reinterpret_cast<float*>(h->kscratch.p);
+                gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(wb), K3, h->enc_w[2], acc, (int)rows3, C, K3, e3.bias, st);
+                f32_to_ta_kernel<TA, false><<<blocks_for(rows3 * C / 4, 256), 256, 0, st>>>(acc, cg, rows3 * C / 4);
+                CK(cudaGetLastError());
+                h->launches++;
+            } else {
+                gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], cg, C, false, (int)rows3, C, K3, e3, st);
+            }
+            pool(cg, Hc3, Wc3, C, h->Hp, h->Wp, nullptr, v, false);
+            embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(v, AF(h, h->film_t_off), AF(h, h->s_emb),
+                                                                                      AF(h, h->t_emb), x, tokens, T, L, C);
+            CK(cudaGetLastError());
+            h->launches++;
+        } else if (sizeof(TA) == 2 && K3 > 1024) {
+            // K = 2048 (patch_scale 64) exceeds the resident weight slice of the tcgen05 GEMM: K blocks through an fp32
             // scratch, then the embed pass
             float* v = reinterpret_cast<float*>(h->qkv.p);
-            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], v, C, true, tokens, C, K3 / 2, e3, st, K3);
-            EpiParams e4; e4.bias = AF(h, h->zero_off); e4.resid = v; e4.ldr = C;
-            gemm<TA>(h, EPI_BIAS_RESID, wb + K3 / 2, K3, h->enc_w[2] + K3 / 2, v, C, true, tokens, C, K3 / 2, e4, st, K3);
+            gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(wb), K3, h->enc_w[2], v, tokens, C, K3, e3.bias, st);
             embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(v, AF(h, h->film_t_off), AF(h, h->s_emb),
                                                                                       AF(h, h->t_emb), x, tokens, T, L, C);
             CK(cudaGetLastError());
@@ -875,28 +944,32 @@ void run_decoder_wide(tante_handle_s* h, int o, const TA* dmod, int B, cudaStrea
     TA* z2 = reinterpret_cast<TA*>(h->z2[o].p);
     float* field = reinterpret_cast<float*>(h->dfield.p) + (size_t)o * B * D * H * W;
     const int H2 = Hp * g.k2, W2 = Wp * g.k2, H1 = H2 * g.k1, W1 = W2 * g.k1;
-    auto post = [&](const TA* S, int ldS, int hi, int wi, int Cout, int k, const float* bias, TA* out, float* fld, bool act) {
+    auto post = [&](const TA* S, int ldS, int hi, int wi, int Cout, int k, int sd, const float* bias, TA* out, float* fld, bool act) {
         const long long total = (long long)B * (hi * k) * (wi * k) * Cout;
         const unsigned blocks = blocks_for(total, 256);
-        if (fld) wide_deconv_post_kernel<TA, false, true><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, nullptr, fld, total);
-        else if (act) wide_deconv_post_kernel<TA, true, false><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total);
-        else wide_deconv_post_kernel<TA, false, false><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total);
+        if (fld) wide_deconv_post_kernel<TA, false, true><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, nullptr, fld, total, sd);
+        else if (act) wide_deconv_post_kernel<TA, true, false><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total, sd);
+        else wide_deconv_post_kernel<TA, false, false><<<blocks, 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total, sd);
         CK(cudaGetLastError());
         h->launches++;
     };
+    // With stride == kernel every output sample has ONE tap, so the (replicated) bias rides in the GEMM epilogue; with overlap
+    // (stride < kernel) several taps are summed per sample: the GEMM runs bias-free and the pass after it adds bias[co] once (the
+    // first Cout entries of the replicated vector are the raw bias).
+    const bool ov1 = h->st[2] != g.k2, ov2 = h->st[1] != g.k1;
     // dec_conv_1 (k2): [B*L][C] -> sub-pixel [B*L][k2*k2*C2] (+ replicated bias) -> resample + GELU -> grid [B][H2][W2][C2]
     const int N1 = g.k2 * g.k2 * C2, N2 = g.k1 * g.k1 * C1;
-    EpiParams ed; ed.bias = AF(h, op.decb[0]);
+    EpiParams ed; ed.bias = ov1 ? AF(h, h->zero_off) : AF(h, op.decb[0]);
     gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ed, st);
-    post(wb, N1, Hp, Wp, C2, g.k2, nullptr, z1, nullptr, true);
+    post(wb, N1, Hp, Wp, C2, g.k2, h->st[2], ov1 ? AF(h, op.decb[0]) : nullptr, z1, nullptr, true);
     // dec_conv_2 (k1)
-    ed.bias = AF(h, op.decb[1]);
+    ed.bias = ov2 ? AF(h, h->zero_off) : AF(h, op.decb[1]);
     gemm<TA>(h, EPI_BIAS, z1, C2, op.decw[1], wb, N2, false, B * H2 * W2, N2, C2, ed, st);
-    post(wb, N2, H2, W2, C1, g.k1, nullptr, z2, nullptr, true);
+    post(wb, N2, H2, W2, C1, g.k1, h->st[1], ov2 ? AF(h, op.decb[1]) : nullptr, z2, nullptr, true);
     // dec_conv_3 (k0): output width k0*k0*D padded to NOpad, bias added after the resample (its weights sum to one)
     EpiParams e3; e3.bias = AF(h, h->zero_off);
     gemm<TA>(h, EPI_BIAS, z2, C1, op.w3nk, wb, h->NOpad, false, B * H1 * W1, h->NOpad, C1, e3, st);
-    post(wb, h->NOpad, H1, W1, D, g.k0, AF(h, op.decb[2]), nullptr, field, false);
+    post(wb, h->NOpad, H1, W1, D, g.k0, h->st[0], AF(h, op.decb[2]), nullptr, field, false);
 }
 
 // ---- enc_dec_type = 'fno' (fno.cuh) ----
@@ -946,22 +1019,6 @@ void run_spectral(tante_handle_s* h, const SpecPlan& sp, const SpecView& in, lon
     else spec_out_kernel<TA, false, false><<<nb, 256, 0, st>>>(Bc, in, AF(h, sp.w0), AF(h, sp.b0), sp.Cin, sp.Cout, H, W, m2, twW, out, nullptr, to);
     CK(cudaGetLastError());
     h->launches += 5;
-}
-
-// Tensor mode, K beyond the tcgen05 GEMM's resident weight slice (1024): out[M][N] (fp32) = A[M][K] W[N][K]^T + bias as K / parts
-// column blocks accumulated through the fp32 output (first block EPI_BIAS, the rest EPI_BIAS_RESID in place).
-inline void gemm_bigk_f32(tante_handle_s* h, const __nv_bfloat16* A, int lda, int64_t w_off, float* out, int M, int N, int K,
-                          const float* bias, cudaStream_t st) {
-    int parts = (K + 1023) / 1024;
-    while (K % (parts * 64) != 0) ++parts;
-    const int Kp = K / parts;
-    REQUIRE(Kp >= 64 && Kp <= 1024, "split-K GEMM: K not covered");
-    EpiParams e0; e0.bias = bias;
-    gemm<__nv_bfloat16>(h, EPI_BIAS, A, lda, w_off, out, N, true, M, N, Kp, e0, st, K);
-    for (int p = 1; p < parts; ++p) {
-        EpiParams e; e.bias = AF(h, h->zero_off); e.resid = out; e.ldr = N;
-        gemm<__nv_bfloat16>(h, EPI_BIAS_RESID, A + (size_t)p * Kp, lda, w_off + (int64_t)p * Kp, out, N, true, M, N, Kp, e, st, K);
-    }
 }
 
 // conv over a channels-last grid as gather + GEMM; K beyond the tcgen05 GEMM's resident slice (1024) runs in K blocks
@@ -2648,7 +2705,7 @@ int tante_destroy(tante_handle_t h) {
         DevBuf* bufs[] = {&h->arena, &h->arena_bf16, &h->descs, &h->x, &h->ln, &h->qkv, &h->att, &h->hid, &h->a1, &h->a2,
                           &h->d32, &h->dmod, &h->i1, &h->i2, &h->z1, &h->rt, &h->Rt, &h->nbuf, &h->filmbuf, &h->ring,
                           &h->state, &h->dbg_in, &h->enc_cache, &h->enc_state, &h->icols, &h->wbuf, &h->dfield, &h->ftw,
-                          &h->fA, &h->fB, &h->fg0, &h->fg1, &h->fg2, &h->cx, &h->cln, &h->cqkv, &h->catt, &h->chid};
+                          &h->fA, &h->fB, &h->fg0, &h->fg1, &h->fg2, &h->cgrid, &h->cx, &h->cln, &h->cqkv, &h->catt, &h->chid};
         for (DevBuf* b : bufs) b->free();
         for (auto& b : h->z2) b.free();
         DevBuf* tb[] = {&h->garena, &h->tdesc_dev, &h->udesc_dev, &h->dxs, &h->dxb, &h->g1, &h->g2, &h->gq, &h->ga1, &h->cols,
@@ -2835,9 +2892,20 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             fno_twiddles(h);      // (a synchronous upload: here, never inside a stream capture)
         } else if (h->wide) {
             const size_t BLs = BL;
-            size_t m = tokens * g.R1 * (size_t)h->K1pad;                                  // conv1 windows
-            m = std::max(m, tokens * g.R2 * (size_t)(g.k1 * g.k1 * C1));                   // conv2 windows
-            m = std::max(m, tokens * (size_t)(g.k2 * g.k2 * C2));                          // conv3 windows
+            // conv grids of the three encoder stages (== the patch grids without overlap)
+            auto cdim = [](int n, int k, int s) { return (size_t)((n + 2 * ((k - 1) / 2) - k) / s + 1); };
+            const size_t NIw = (size_t)max_batch * h->T;
+            const int Hh1 = h->cfg.H / g.k0, Ww1 = h->cfg.W / g.k0, Hh2 = Hh1 / g.k1, Ww2 = Ww1 / g.k1;
+            const size_t r1 = NIw * cdim(h->cfg.H, g.k0, h->st[0]) * cdim(h->cfg.W, g.k0, h->st[0]);
+            const size_t r2 = NIw * cdim(Hh1, g.k1, h->st[1]) * cdim(Ww1, g.k1, h->st[1]);
+            const size_t r3 = NIw * cdim(Hh2, g.k2, h->st[2]) * cdim(Ww2, g.k2, h->st[2]);
+            size_t m = r1 * (size_t)h->K1pad;                                              // conv1 windows
+            m = std::max(m, r2 * (size_t)(g.k1 * g.k1 * C1));                               // conv2 windows
+            m = std::max(m, r3 * (size_t)(g.k2 * g.k2 * C2));                               // conv3 windows
+            if (h->overlap) {
+                dev_alloc(h, h->cgrid, std::max(std::max(r1 * C1, r2 * C2), r3 * C) * es);
+                if (es == 2 && g.k2 * g.k2 * C2 > 1024) dev_alloc(h, h->kscratch, r3 * C * 4);
+            }
             m = std::max(m, BLs * (size_t)(g.k2 * g.k2 * C2));                             // sub-pixel matrices of the decoder
             m = std::max(m, BLs * g.R2 * (size_t)(g.k1 * g.k1 * C1));
             m = std::max(m, BLs * g.R1 * (size_t)h->NOpad);
@@ -3002,6 +3070,7 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
+        REQUIRE(!h->overlap, "training with overlap_ratio != 0 is not implemented (inference / rollout only)");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

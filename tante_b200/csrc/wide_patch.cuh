@@ -18,14 +18,16 @@ namespace tante {
 template <typename TA>
 __global__ void __launch_bounds__(256)
 wide_im2col_cf_kernel(const float* __restrict__ x, const int* __restrict__ fcount, int T, int D, int H, int W, int k, int shift,
-                      int Kpad, TA* __restrict__ out, long long total) {
+                      int Kpad, TA* __restrict__ out, long long total, int stride = 0, int Hc = 0, int Wc = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int col = (int)(idx % Kpad);
     long long row = idx / Kpad;
     float v = 0.f;
     if (col < k * k * D) {
-        const int Ho = H / k, Wo = W / k;
+        // windows: stride == k on the (H / k, W / k) grid, or (overlap_ratio != 0) stride < k on the (Hc, Wc) conv grid
+        const int sd = stride > 0 ? stride : k;
+        const int Ho = stride > 0 ? Hc : H / k, Wo = stride > 0 ? Wc : W / k;
         const int d = col % D, tap = col / D;
         const int di = tap / k, dj = tap % k;
         const int j = (int)(row % Wo); row /= Wo;
@@ -34,7 +36,7 @@ wide_im2col_cf_kernel(const float* __restrict__ x, const int* __restrict__ fcoun
         const long long b = bt / T;
         const int t = (int)(bt % T);
         const int slot = fcount ? (fcount[b] + t) % T : t;
-        const int y = i * k + di - shift, xx = j * k + dj - shift;
+        const int y = i * sd + di - shift, xx = j * sd + dj - shift;
         if (y >= 0 && y < H && xx >= 0 && xx < W)
             v = x[((size_t)(b * T + slot) * D + d) * H * W + (size_t)y * W + xx];
     }
@@ -44,19 +46,21 @@ wide_im2col_cf_kernel(const float* __restrict__ x, const int* __restrict__ fcoun
 // conv2 / conv3 windows from a channels-last grid [n][Hs][Ws][Cin]: out[row = (n, i, j)][(di*k + dj)*Cin + ci]; thread = 4 channels
 template <typename TA>
 __global__ void __launch_bounds__(256)
-wide_im2col_cl_kernel(const TA* __restrict__ in, int Hs, int Ws, int Cin, int k, int shift, TA* __restrict__ out, long long total4) {
+wide_im2col_cl_kernel(const TA* __restrict__ in, int Hs, int Ws, int Cin, int k, int shift, TA* __restrict__ out, long long total4,
+                      int stride = 0, int Hc = 0, int Wc = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total4) return;
     const int C4 = Cin / 4;
     const int c4 = (int)(idx % C4);
     long long r = idx / C4;
     const int tap = (int)(r % (k * k)); r /= k * k;
-    const int Ho = Hs / k, Wo = Ws / k;
+    const int sd = stride > 0 ? stride : k;
+    const int Ho = stride > 0 ? Hc : Hs / k, Wo = stride > 0 ? Wc : Ws / k;
     const int j = (int)(r % Wo); r /= Wo;
     const int i = (int)(r % Ho);
     const long long n = r / Ho;
     const int di = tap / k, dj = tap % k;
-    const int y = i * k + di - shift, xx = j * k + dj - shift;
+    const int y = i * sd + di - shift, xx = j * sd + dj - shift;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (y >= 0 && y < Hs && xx >= 0 && xx < Ws) Vec4<TA>::load(in + (((size_t)n * Hs + y) * Ws + xx) * Cin + c4 * 4, v);
     Vec4<TA>::store(out + idx * 4, v);
@@ -76,10 +80,24 @@ __device__ __forceinline__ void bilinear_src(int dst, int in_size, int out_size,
 // y + pad = k*i + di  (pad = (k-1)//2: 0 for k = 2, 1 for k = 4)
 template <typename TA>
 __device__ __forceinline__ float deconv_at(const TA* __restrict__ S, int ldS, long long n, int hi, int wi, int Cout, int k, int pad,
-                                           int y, int x, int co) {
+                                           int y, int x, int co, int sd = 0) {
     const int yy = y + pad, xx = x + pad;
-    const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
-    return to_f32(S[(((size_t)n * hi + i) * wi + j) * ldS + (di * k + dj) * Cout + co]);
+    if (sd <= 0 || sd == k) {
+        const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
+        return to_f32(S[(((size_t)n * hi + i) * wi + j) * ldS + (di * k + dj) * Cout + co]);
+    }
+    // overlap_ratio != 0: stride sd < k, every output sample sums the taps di = yy mod sd, + sd, ... of the inputs (yy - di) / sd
+    float v = 0.f;
+    for (int di = yy % sd; di < k; di += sd) {
+        const int i = (yy - di) / sd;
+        if (i < 0 || i >= hi) continue;
+        for (int dj = xx % sd; dj < k; dj += sd) {
+            const int j = (xx - dj) / sd;
+            if (j < 0 || j >= wi) continue;
+            v += to_f32(S[(((size_t)n * hi + i) * wi + j) * ldS + (di * k + dj) * Cout + co]);
+        }
+    }
+    return v;
 }
 
 // decoder stage tail: sub-pixel matrix (bias already added by the GEMM epilogue when `bias` is null) -> [crop + bilinear resize
@@ -88,7 +106,7 @@ __device__ __forceinline__ float deconv_at(const TA* __restrict__ S, int ldS, lo
 template <typename TA, bool ACT, bool FIELD>
 __global__ void __launch_bounds__(256)
 wide_deconv_post_kernel(const TA* __restrict__ S, int ldS, int hi, int wi, int Cout, int k, const float* __restrict__ bias,
-                        TA* __restrict__ out, float* __restrict__ field, long long total) {
+                        TA* __restrict__ out, float* __restrict__ field, long long total, int sd = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int Ho = hi * k, Wo = wi * k;
@@ -106,17 +124,18 @@ wide_deconv_post_kernel(const TA* __restrict__ S, int ldS, int hi, int wi, int C
         Y = (int)(r % Ho); n = r / Ho;
     }
     const int pad = (k - 1) / 2;
+    const int se = sd > 0 ? sd : k;
+    const int Hd = (hi - 1) * se - 2 * pad + k, Wd = (wi - 1) * se - 2 * pad + k;       // what ConvTranspose2d produced (enc_dec_cnn.py:162-166)
     float v;
-    if (pad == 0) {
-        v = deconv_at(S, ldS, n, hi, wi, Cout, k, 0, Y, X, co);
+    if (Hd == Ho && Wd == Wo) {
+        v = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, Y, X, co, sd);
     } else {
-        const int Hd = Ho - 2 * pad, Wd = Wo - 2 * pad;       // what ConvTranspose2d produced (enc_dec_cnn.py:162-166)
         int y0, y1, x0, x1;
         float wy, wx;
         bilinear_src(Y, Hd, Ho, y0, y1, wy);
         bilinear_src(X, Wd, Wo, x0, x1, wx);
-        const float v00 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y0, x0, co), v01 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y0, x1, co);
-        const float v10 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y1, x0, co), v11 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y1, x1, co);
+        const float v00 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y0, x0, co, sd), v01 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y0, x1, co, sd);
+        const float v10 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y1, x0, co, sd), v11 = deconv_at(S, ldS, n, hi, wi, Cout, k, pad, y1, x1, co, sd);
         // aten upsample_bilinear2d: h0lambda * (w0lambda * v00 + w1lambda * v01) + h1lambda * (w0lambda * v10 + w1lambda * v11)
         v = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
     }
@@ -124,6 +143,41 @@ wide_deconv_post_kernel(const TA* __restrict__ S, int ldS, int hi, int wi, int C
     if (ACT) v = ActMath<TA>::gelu_erf_f(v);
     if (FIELD) field[idx] = v;
     else out[idx] = from_f32<TA>(v);
+}
+
+// adaptive_avg_pool2d of the conv grid [n][Hc][Wc][C] (TA) to the patch grid [n][Ho][Wo][C] (enc_dec_cnn.py:109; torch's windows:
+// rows floor(i Hc / Ho) .. ceil((i + 1) Hc / Ho) - 1), then the stage's GELU; output TA, or fp32 (OUT32: the pre-embedding of the
+// last stage).  Thread = 4 channels.
+template <typename TA, bool ACT, bool OUT32>
+__global__ void __launch_bounds__(256)
+wide_pool_kernel(const TA* __restrict__ in, int Hc, int Wc, int C, int Ho, int Wo, TA* __restrict__ out, float* __restrict__ out32,
+                 long long total4) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total4) return;
+    const int C4 = C / 4;
+    const int c4 = (int)(idx % C4);
+    long long r = idx / C4;
+    const int j = (int)(r % Wo); r /= Wo;
+    const int i = (int)(r % Ho);
+    const long long n = r / Ho;
+    const int y0 = (i * Hc) / Ho, y1 = ((i + 1) * Hc + Ho - 1) / Ho;
+    const int x0 = (j * Wc) / Wo, x1 = ((j + 1) * Wc + Wo - 1) / Wo;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x) {
+            float v[4];
+            Vec4<TA>::load(in + (((size_t)n * Hc + y) * Wc + x) * C + c4 * 4, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] += v[e];
+        }
+    const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        acc[e] *= inv;
+        if (ACT) acc[e] = ActMath<TA>::gelu_erf_f(acc[e]);
+    }
+    if (OUT32) Vec4<float>::store(out32 + idx * 4, acc);
+    else Vec4<TA>::store(out + idx * 4, acc);
 }
 
 // fp32 accumulator of a split-K GEMM -> (GELU) -> TA; thread = 4 elements

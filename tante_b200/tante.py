@@ -193,6 +193,9 @@ class _Engine:
         cfg.enc_dec_fno = 1 if model.enc_dec_type == "fno" else 0
         cfg.modes1, cfg.modes2 = int(model.modes1), int(model.modes2)
         cfg.mlp_hidden = int(model.C * model.mlp_ratio)
+        for i, k in enumerate(model.patch_kernels[:3] if model.enc_dec_type == "cnn" else ()):
+            # enc_dec_cnn.py:64-66 / 130-132: Python's round() (half to even) -- computed here so that both sides agree
+            cfg.stride[i] = max(1, int(round(k * (1.0 - model.overlap_ratio))))
         cfg.expanded_channel = int(model.expanded_channel)
         cfg.mlp_hidden_c = int(model.expanded_channel * model.mlp_ratio)
         for k, seg in enumerate(model.blocks_axes):
@@ -499,14 +502,17 @@ class TANTE(nn.Module):
         if enc_dec_type not in ("cnn", "fno"):
             raise ValueError(f"unknown enc_dec_type {enc_dec_type!r}")
         self.enc_dec_type, self.modes1, self.modes2 = enc_dec_type, modes1, modes2
-        if overlap_ratio != 0.0:
-            raise NotImplementedError("overlap_ratio != 0 is not supported by the patch-GEMM kernels")
+        if not 0.0 <= overlap_ratio < 1.0:
+            raise AssertionError("overlap_ratio must be in [0, 1).")      # enc_dec_cnn.py:63
+        self.overlap_ratio = float(overlap_ratio)
         hidden = int(embed_dim * float(mlp_ratio))
         if hidden < 64 or hidden > 1024 or hidden % 64:
             raise NotImplementedError("int(embed_dim * mlp_ratio) must be a multiple of 64 in 64..1024 (mlp_ratio 0.25 .. 4 at embed_dim 256)")
         self.mlp_ratio = float(mlp_ratio)
         ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
         self.patch_kernels = ks
+        if enc_dec_type == "fno" and overlap_ratio != 0.0:
+            raise NotImplementedError("overlap_ratio != 0 with enc_dec_type='fno' is not implemented")
         if enc_dec_type == "fno":
             ps = Patch_map_fno[patch_scale]
             self.patch_kernels = ps
@@ -681,7 +687,7 @@ class TANTE(nn.Module):
     @property
     def bptt_windows_ok(self) -> bool:
         """The windowed BPTT entry points (frame tables) exist for the nested-order patch stages (patch_scale <= 8, cnn) without axis-C layers."""
-        return self.patch_scale <= 8 and self.enc_dec_type == "cnn" and "C" not in self.attn_axes
+        return self.patch_scale <= 8 and self.enc_dec_type == "cnn" and "C" not in self.attn_axes and self.overlap_ratio == 0.0
 
     def rollout_train(self, window, n_steps: int):
         """Fixed-step BPTT rollout of the training drivers (trainer/trainer.py:144-159) for the `deg=True`, `output_length=1`

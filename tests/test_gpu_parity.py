@@ -326,7 +326,9 @@ NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d1
         # embed_dim 512 (plain GEMM path, head_dim 64)
         "fwd_adp_k2_c512",
         # enc_dec_type='fno' with 8x8 patch stages
-        "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64"]
+        "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64",
+        # overlap_ratio != 0: strided windows + adaptive pooling, overlap-add transposed convs + resize
+        "fwd_adp_k2_ov50_p8", "fwd_deg_k1_ov25_p16", "fwd_deg_k1_ov70_p32"]
 
 
 @pytest.mark.parametrize("name", NEXT)
@@ -360,7 +362,8 @@ def test_next_scope_forward_and_rollout_fp32(name):
 @pytest.mark.parametrize("name", ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k2_axes_lya", "fwd_deg_k1_w96",
                                   "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16", "fwd_adp_k2_mlp2",
                                   "fwd_deg_k1_mlp05", "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64", "fwd_adp_k2_c512",
-                                  "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64"])
+                                  "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64", "fwd_adp_k2_ov50_p8", "fwd_deg_k1_ov25_p16",
+                                  "fwd_deg_k1_ov70_p32"])
 def test_next_scope_forward_bf16(name):
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
     with torch.inference_mode():

@@ -812,6 +812,30 @@ void launch_head(tante_handle_s* h, const StepIO& io, int B, const RolloutState&
 }
 
 // ---- patch_scale >= 16 (wide_patch.cuh): encoder, decoder of one order, emit ----
+// Grids of the natural-order encoder stages for a batch of B windows: patch grids (H1 x W1, H2 x W2, Hp x Wp) and the conv grids in
+// front of them (kernel k, stride s, pad (k - 1) / 2); the two differ -- and an adaptive average pooling sits between -- only with
+// overlap_ratio != 0.
+struct WideDims {
+    int H1, W1, H2, W2, Hc1, Wc1, Hc2, Wc2, Hc3, Wc3;
+    bool pool1, pool2, pool3;
+    long long rows1, rows2, rows3;
+};
+inline WideDims wide_dims(const tante_handle_s* h, int B) {
+    const PatchGeom& g = h->geom;
+    auto cdim = [](int n, int k, int s) { return (n + 2 * ((k - 1) / 2) - k) / s + 1; };
+    WideDims d;
+    d.H1 = h->cfg.H / g.k0; d.W1 = h->cfg.W / g.k0; d.H2 = d.H1 / g.k1; d.W2 = d.W1 / g.k1;
+    d.Hc1 = cdim(h->cfg.H, g.k0, h->st[0]); d.Wc1 = cdim(h->cfg.W, g.k0, h->st[0]);
+    d.Hc2 = cdim(d.H1, g.k1, h->st[1]); d.Wc2 = cdim(d.W1, g.k1, h->st[1]);
+    d.Hc3 = cdim(d.H2, g.k2, h->st[2]); d.Wc3 = cdim(d.W2, g.k2, h->st[2]);
+    d.pool1 = d.Hc1 != d.H1 || d.Wc1 != d.W1;
+    d.pool2 = d.Hc2 != d.H2 || d.Wc2 != d.W2;
+    d.pool3 = d.Hc3 != h->Hp || d.Wc3 != h->Wp;
+    const long long NI = (long long)B * h->T;
+    d.rows1 = NI * d.Hc1 * d.Wc1; d.rows2 = NI * d.Hc2 * d.Wc2; d.rows3 = NI * d.Hc3 * d.Wc3;
+    return d;
+}
+
 // Tensor mode, K beyond the tcgen05 GEMM's resident weight slice (1024): out[M][N] (fp32) = A[M][K] W[N][K]^T + bias as K / parts
 // column blocks accumulated through the fp32 output (first block EPI_BIAS, the rest EPI_BIAS_RESID in place).
 inline void gemm_bigk_f32(tante_handle_s* h, const __nv_bfloat16* A, int lda, int64_t w_off, float* out, int M, int N, int K,
@@ -1656,7 +1680,7 @@ void tape_alloc(tante_handle_s* h, Tape& tp, int B) {
     const size_t BL = (size_t)B * h->L;
     const int C = h->C, C1 = h->C1, C2 = h->C2;
     const PatchGeom& g = h->geom;
-    dev_alloc(h, tp.cols, tokens * g.R1 * (size_t)std::max(kHeadPad, h->wide ? h->K1pad : 0) * es);
+    dev_alloc(h, tp.cols, (h->overlap ? (size_t)wide_dims(h, B).rows1 : tokens * g.R1) * (size_t)std::max(kHeadPad, h->wide ? h->K1pad : 0) * es);
     dev_alloc(h, tp.a1pre, tokens * g.R1 * C1 * es);
     dev_alloc(h, tp.a1act, tokens * g.R1 * C1 * es);
     // fno: the C/2 grid sits at the H1 x W1 resolution (R1 rows per token), and there is a C/8 grid at full resolution
@@ -1820,37 +1844,51 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     } else if (h->wide) {
         // patch_scale 16 / 32 / 64 (wide_patch.cuh): natural-order stages, window gathers + GEMMs; the first patch matrix and every
         // pre-activation / activation grid are kept for the backward
-        REQUIRE(!win, "windowed BPTT is not available at patch_scale >= 16");
+        REQUIRE(!win, "windowed BPTT is not available at patch_scale >= 16 / with overlap");
         const int H = h->cfg.H, W = h->cfg.W, D = h->D;
         TA* wb = TP<TA>(h->wbuf);
-        const int H1 = H / g.k0, W1 = W / g.k0, H2 = H1 / g.k1, W2 = W1 / g.k1;
-        const long long rows1 = (long long)B * T * H1 * W1, rows2 = (long long)B * T * H2 * W2;
-        REQUIRE(rows1 < (1LL << 31), "input too large for the wide first-conv GEMM");
-        const long long total = rows1 * h->K1pad;
+        TA* cg = TP<TA>(h->cgrid);
+        const WideDims wd = wide_dims(h, B);
+        const int H1 = wd.H1, W1 = wd.W1, H2 = wd.H2, W2 = wd.W2;
+        const long long NI = (long long)B * T;
+        REQUIRE(wd.rows1 < (1LL << 31) && wd.rows2 < (1LL << 31) && wd.rows3 < (1LL << 31), "input too large for the wide conv GEMMs");
+        auto pool = [&](const TA* in, int Hc, int Wc, int Cc, int Ho, int Wo, TA* out, float* out32) {
+            const long long total4 = NI * Ho * Wo * Cc / 4;
+            if (out32) wide_pool_kernel<TA, false, true><<<blocks_for(total4, 256), 256, 0, st>>>(in, Hc, Wc, Cc, Ho, Wo, nullptr, out32, total4);
+            else wide_pool_kernel<TA, false, false><<<blocks_for(total4, 256), 256, 0, st>>>(in, Hc, Wc, Cc, Ho, Wo, out, nullptr, total4);
+            CK(cudaGetLastError());
+            h->launches++;
+        };
+        const long long total = wd.rows1 * h->K1pad;
         wide_im2col_cf_kernel<TA><<<blocks_for(total, 256), 256, 0, st>>>(input, nullptr, T, D, H, W, g.k0, (g.k0 - 1) / 2, h->K1pad,
-                                                                         TP<TA>(tp.cols), total);
+                                                                         TP<TA>(tp.cols), total, h->st[0], wd.Hc1, wd.Wc1);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
-        gemm<TA>(h, EPI_BIAS, TP<TA>(tp.cols), h->K1pad, h->enc_w1wide, tp.a1pre.p, C1, false, (int)rows1, C1, h->K1pad, e1, st);
-        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), rows1 * C1, st);
+        gemm<TA>(h, EPI_BIAS, TP<TA>(tp.cols), h->K1pad, h->enc_w1wide, wd.pool1 ? (void*)cg : tp.a1pre.p, C1, false, (int)wd.rows1, C1,
+                 h->K1pad, e1, st);
+        if (wd.pool1) pool(cg, wd.Hc1, wd.Wc1, C1, H1, W1, TP<TA>(tp.a1pre), nullptr);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), NI * H1 * W1 * C1, st);
         const int K2 = g.k1 * g.k1 * C1, K3 = g.k2 * g.k2 * C2;
-        wide_im2col_cl_kernel<TA><<<blocks_for(rows2 * K2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a1act), H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb,
-                                                                                  rows2 * K2 / 4);
+        wide_im2col_cl_kernel<TA><<<blocks_for(wd.rows2 * K2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a1act), H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb,
+                                                                                     wd.rows2 * K2 / 4, h->st[1], wd.Hc2, wd.Wc2);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
-        gemm<TA>(h, EPI_BIAS, wb, K2, h->enc_w[1], tp.a2pre.p, C2, false, (int)rows2, C2, K2, e2, st);
-        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a2pre), TP<TA>(tp.a2act), rows2 * C2, st);
-        wide_im2col_cl_kernel<TA><<<blocks_for((long long)tokens * K3 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H2, W2, C2, g.k2,
-                                                                                              (g.k2 - 1) / 2, wb, (long long)tokens * K3 / 4);
+        gemm<TA>(h, EPI_BIAS, wb, K2, h->enc_w[1], wd.pool2 ? (void*)cg : tp.a2pre.p, C2, false, (int)wd.rows2, C2, K2, e2, st);
+        if (wd.pool2) pool(cg, wd.Hc2, wd.Wc2, C2, H2, W2, TP<TA>(tp.a2pre), nullptr);
+        launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a2pre), TP<TA>(tp.a2act), NI * H2 * W2 * C2, st);
+        wide_im2col_cl_kernel<TA><<<blocks_for(wd.rows3 * K3 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H2, W2, C2, g.k2, (g.k2 - 1) / 2, wb,
+                                                                                     wd.rows3 * K3 / 4, h->st[2], wd.Hc3, wd.Wc3);
         CK(cudaGetLastError());
         h->launches++;
         EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
-        if (kTensor && K3 > 1024) {      // (K = 2048 at patch_scale 64: two K halves, as in run_encoder_wide)
-            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], tp.v.p, C, true, tokens, C, K3 / 2, e3, st, K3);
-            EpiParams e4; e4.bias = AF(h, h->zero_off); e4.resid = FP(tp.v); e4.ldr = C;
-            gemm<TA>(h, EPI_BIAS_RESID, wb + K3 / 2, K3, h->enc_w[2] + K3 / 2, tp.v.p, C, true, tokens, C, K3 / 2, e4, st, K3);
+        if (wd.pool3) {
+            REQUIRE(!(kTensor && K3 > 1024), "overlap_ratio != 0 at patch_scale 64 in the tensor mode: training not implemented");
+            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], cg, C, false, (int)wd.rows3, C, K3, e3, st);
+            pool(cg, wd.Hc3, wd.Wc3, C, h->Hp, h->Wp, nullptr, FP(tp.v));
+        } else if (kTensor && K3 > 1024) {      // (K = 2048 at patch_scale 64: K blocks, as in run_encoder_wide)
+            gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(wb), K3, h->enc_w[2], FP(tp.v), tokens, C, K3, e3.bias, st);
         } else {
             gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], tp.v.p, C, true, tokens, C, K3, e3, st);
         }
@@ -2004,24 +2042,28 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             const int H2 = Hp * g.k2, W2 = Wp * g.k2, H1 = H2 * g.k1, W1 = W2 * g.k1;
             const int N1 = g.k2 * g.k2 * C2, N2 = g.k1 * g.k1 * C1;
             float* field = FP(h->dfield) + (size_t)o * B * D * h->cfg.H * h->cfg.W;
-            EpiParams ew; ew.bias = AF(h, op.decb[0]);
+            // (overlapped stages: bias-free GEMM, the bias once per output sample in the pass after it -- see run_decoder_wide)
+            const bool ov1 = h->st[2] != g.k2, ov2 = h->st[1] != g.k1;
+            EpiParams ew; ew.bias = ov1 ? AF(h, h->zero_off) : AF(h, op.decb[0]);
             gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ew, st);
             long long tot = (long long)B * H2 * W2 * C2;
-            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N1, Hp, Wp, C2, g.k2, nullptr, TP<TA>(ot.z1pre), nullptr, tot);
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N1, Hp, Wp, C2, g.k2, ov1 ? AF(h, op.decb[0]) : nullptr,
+                                                                                          TP<TA>(ot.z1pre), nullptr, tot, h->st[2]);
             CK(cudaGetLastError());
             h->launches++;
             launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z1pre), TP<TA>(ot.z1act), tot, st);
-            ew.bias = AF(h, op.decb[1]);
+            ew.bias = ov2 ? AF(h, h->zero_off) : AF(h, op.decb[1]);
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z1act), C2, op.decw[1], wb, N2, false, B * H2 * W2, N2, C2, ew, st);
             tot = (long long)B * H1 * W1 * C1;
-            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N2, H2, W2, C1, g.k1, nullptr, TP<TA>(ot.z2pre), nullptr, tot);
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N2, H2, W2, C1, g.k1, ov2 ? AF(h, op.decb[1]) : nullptr,
+                                                                                          TP<TA>(ot.z2pre), nullptr, tot, h->st[1]);
             CK(cudaGetLastError());
             h->launches++;
             launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z2pre), TP<TA>(ot.z2act), tot, st);
             EpiParams e3; e3.bias = AF(h, h->zero_off);
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z2act), C1, op.w3nk, wb, h->NOpad, false, B * H1 * W1, h->NOpad, C1, e3, st);
             tot = (long long)B * D * h->cfg.H * h->cfg.W;
-            wide_deconv_post_kernel<TA, false, true><<<blocks_for(tot, 256), 256, 0, st>>>(wb, h->NOpad, H1, W1, D, g.k0, AF(h, op.decb[2]), nullptr, field, tot);
+            wide_deconv_post_kernel<TA, false, true><<<blocks_for(tot, 256), 256, 0, st>>>(wb, h->NOpad, H1, W1, D, g.k0, AF(h, op.decb[2]), nullptr, field, tot, h->st[0]);
             CK(cudaGetLastError());
             h->launches++;
             continue;
@@ -2281,24 +2323,36 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             const int Hp = h->Hp, Wp = h->Wp;
             const int H2 = Hp * g.k2, W2 = Wp * g.k2, H1 = H2 * g.k1, W1 = W2 * g.k1;
             const float* gf = FP(h->dfield) + (size_t)o * B * D * h->cfg.H * h->cfg.W;
+            // bias gradients: without overlap the replicated bias rode in the GEMM (column sums of dS, folded at unpack); an overlapped
+            // stage added bias[co] once per output sample, so its gradient is the sum of the OUTPUT gradient (into the first Cout entries)
+            const bool ov0 = h->st[0] != g.k0, ov1 = h->st[2] != g.k2, ov2 = h->st[1] != g.k1;
             long long tot = rows1 * NP;
-            wide_deconv_post_bwd_kernel<TA, true><<<blocks_for(tot, 256), 256, 0, st>>>(nullptr, gf, NP, H1, W1, D, g.k0, G, tot);
+            wide_deconv_post_bwd_kernel<TA, true><<<blocks_for(tot, 256), 256, 0, st>>>(nullptr, gf, NP, H1, W1, D, g.k0, G, tot, h->st[0]);
             CK(cudaGetLastError());
             h->launches++;
             wgrad_pad<TA>(h, TP<TA>(ot.z2act), C1, C1, G, NP, NP, GA(h, op.decw[2]), NO, NO, rows1, st);
-            launch_colsum<TA>(h, G, NP, rows1, NO, GA(h, op.decb[2]), st);
+            if (ov0) {
+                const long long HWp = (long long)h->cfg.H * h->cfg.W;
+                field_bias_grad_kernel<<<dim3((unsigned)D, 32), 256, 0, st>>>(gf, D, HWp, B, GA(h, op.decb[2]));
+                CK(cudaGetLastError());
+                h->launches++;
+            } else {
+                launch_colsum<TA>(h, G, NP, rows1, NO, GA(h, op.decb[2]), st);
+            }
             gemm_dx_act<TA, ACT_GELU_ERF>(h, G, NP, op.w3pad, dz, TP<TA>(ot.z2pre), (int)rows1, C1, NP, st);
+            if (ov2) launch_colsum<TA>(h, dz, C1, rows1, C1, GA(h, op.decb[1]), st);
             tot = (long long)M2 * N2;
-            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(dz, nullptr, N2, H2, W2, C1, g.k1, wb, tot);
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(dz, nullptr, N2, H2, W2, C1, g.k1, wb, tot, h->st[1]);
             CK(cudaGetLastError());
             h->launches++;
-            wgrad<TA>(h, wb, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st, GA(h, op.decb[1]));
+            wgrad<TA>(h, wb, N2, TP<TA>(ot.z1act), C2, GA(h, op.decw[1]), M2, N2, C2, st, ov2 ? nullptr : GA(h, op.decb[1]));
             gemm_dx_act<TA, ACT_GELU_ERF>(h, wb, N2, op.decwT[1], dz1, TP<TA>(ot.z1pre), M2, C2, N2, st);
+            if (ov1) launch_colsum<TA>(h, dz1, C2, M2, C2, GA(h, op.decb[0]), st);
             tot = (long long)BL * N1;
-            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(dz1, nullptr, N1, Hp, Wp, C2, g.k2, wb, tot);
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(dz1, nullptr, N1, Hp, Wp, C2, g.k2, wb, tot, h->st[2]);
             CK(cudaGetLastError());
             h->launches++;
-            wgrad<TA>(h, wb, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st, GA(h, op.decb[0]));
+            wgrad<TA>(h, wb, N1, dmod, C, GA(h, op.decw[0]), BL, N1, C, st, ov1 ? nullptr : GA(h, op.decb[0]));
             gemm_dx<TA>(h, wb, N1, op.decwT[0], hd, C, BL, C, N1, st);
         } else {
         TA* G = TP<TA>(h->hG) + (size_t)o * rows1 * kHeadPad;
@@ -2454,38 +2508,59 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         run_spectral_bwd<TA>(h, h->fes1, xs0, gs0, NI, H, W, 0, nullptr, grad_input, st);
     } else if (h->wide) {
         // natural-order stages: the patch matrices of conv3 / conv2 are re-gathered from the kept activation grids (cheap, one
-        // pass), their gradients go back to the grids through the transposed gather
+        // pass), their gradients go back to the grids through the transposed gather; with overlap_ratio != 0 the gradient of a
+        // stage's (pooled) output first goes back to its conv grid (wide_pool_bwd_kernel)
         TA* wb = TP<TA>(h->wbuf);
+        TA* cg = TP<TA>(h->cgrid);
         const int H = h->cfg.H, W = h->cfg.W;
-        const int H1 = H / g.k0, W1 = W / g.k0, H2 = H1 / g.k1, W2 = W1 / g.k1;
-        wide_im2col_cl_kernel<TA><<<blocks_for((long long)tokens * K3 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H2, W2, C2, g.k2,
-                                                                                              (g.k2 - 1) / 2, wb, (long long)tokens * K3 / 4);
+        const WideDims wd = wide_dims(h, B);
+        const int H1 = wd.H1, W1 = wd.W1, H2 = wd.H2, W2 = wd.W2;
+        const long long NI = (long long)B * T;
+        auto pool_bwd = [&](const TA* gp, int Hc, int Wc, int Cc, int Ho, int Wo) {
+            const long long total4 = NI * Hc * Wc * Cc / 4;
+            wide_pool_bwd_kernel<TA, false><<<blocks_for(total4, 256), 256, 0, st>>>(gp, nullptr, Hc, Wc, Cc, Ho, Wo, cg, total4);
+            CK(cudaGetLastError());
+            h->launches++;
+        };
+        // stage 3
+        const TA* dY3 = g2;
+        if (wd.pool3) { pool_bwd(g2, wd.Hc3, wd.Wc3, C, h->Hp, h->Wp); dY3 = cg; }
+        wide_im2col_cl_kernel<TA><<<blocks_for(wd.rows3 * K3 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H2, W2, C2, g.k2, (g.k2 - 1) / 2, wb,
+                                                                                     wd.rows3 * K3 / 4, h->st[2], wd.Hc3, wd.Wc3);
         CK(cudaGetLastError());
         h->launches++;
-        wgrad<TA>(h, g2, C, wb, K3, GA(h, h->enc_w[2]), tokens, C, K3, st, GA(h, h->enc_b[2]));
-        gemm_dx<TA>(h, g2, C, h->enc_wT[2], wb, K3, tokens, K3, C, st);
-        wide_col2im_cl_kernel<TA><<<blocks_for((long long)M2 * C2 / 4, 256), 256, 0, st>>>(wb, H2, W2, C2, g.k2, (g.k2 - 1) / 2, gq,
-                                                                                          (long long)M2 * C2 / 4);
+        wgrad<TA>(h, dY3, C, wb, K3, GA(h, h->enc_w[2]), wd.rows3, C, K3, st, GA(h, h->enc_b[2]));
+        gemm_dx<TA>(h, dY3, C, h->enc_wT[2], wb, K3, (int)wd.rows3, K3, C, st);
+        wide_col2im_cl_kernel<TA><<<blocks_for(NI * H2 * W2 * C2 / 4, 256), 256, 0, st>>>(wb, H2, W2, C2, g.k2, (g.k2 - 1) / 2, gq,
+                                                                                         NI * H2 * W2 * C2 / 4, h->st[2], wd.Hc3, wd.Wc3);
         CK(cudaGetLastError());
         h->launches++;
-        launch_act_bwd<TA, ACT_GELU_ERF>(h, gq, TP<TA>(tp.a2pre), (long long)M2 * C2, st);
-        wide_im2col_cl_kernel<TA><<<blocks_for((long long)M2 * K2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a1act), H1, W1, C1, g.k1,
-                                                                                          (g.k1 - 1) / 2, wb, (long long)M2 * K2 / 4);
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, gq, TP<TA>(tp.a2pre), NI * H2 * W2 * C2, st);
+        // stage 2
+        const TA* dY2 = gq;
+        if (wd.pool2) { pool_bwd(gq, wd.Hc2, wd.Wc2, C2, H2, W2); dY2 = cg; }
+        wide_im2col_cl_kernel<TA><<<blocks_for(wd.rows2 * K2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a1act), H1, W1, C1, g.k1, (g.k1 - 1) / 2, wb,
+                                                                                     wd.rows2 * K2 / 4, h->st[1], wd.Hc2, wd.Wc2);
         CK(cudaGetLastError());
         h->launches++;
-        wgrad<TA>(h, gq, C2, wb, K2, GA(h, h->enc_w[1]), M2, C2, K2, st, GA(h, h->enc_b[1]));
-        gemm_dx<TA>(h, gq, C2, h->enc_wT[1], wb, K2, M2, K2, C2, st);
+        wgrad<TA>(h, dY2, C2, wb, K2, GA(h, h->enc_w[1]), wd.rows2, C2, K2, st, GA(h, h->enc_b[1]));
+        gemm_dx<TA>(h, dY2, C2, h->enc_wT[1], wb, K2, (int)wd.rows2, K2, C2, st);
         TA* ga1 = TP<TA>(h->ga1);
-        wide_col2im_cl_kernel<TA><<<blocks_for(rows_in * C1 / 4, 256), 256, 0, st>>>(wb, H1, W1, C1, g.k1, (g.k1 - 1) / 2, ga1, rows_in * C1 / 4);
+        wide_col2im_cl_kernel<TA><<<blocks_for(NI * H1 * W1 * C1 / 4, 256), 256, 0, st>>>(wb, H1, W1, C1, g.k1, (g.k1 - 1) / 2, ga1,
+                                                                                         NI * H1 * W1 * C1 / 4, h->st[1], wd.Hc2, wd.Wc2);
         CK(cudaGetLastError());
         h->launches++;
-        launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), rows_in * C1, st);
-        wgrad_pad<TA>(h, ga1, C1, C1, TP<TA>(tp.cols), h->K1pad, h->K1pad, GA(h, h->enc_w[0]), NO, NO, rows_in, st, GA(h, h->enc_b[0]));
+        launch_act_bwd<TA, ACT_GELU_ERF>(h, ga1, TP<TA>(tp.a1pre), NI * H1 * W1 * C1, st);
+        // stage 1
+        const TA* dY1 = ga1;
+        if (wd.pool1) { pool_bwd(ga1, wd.Hc1, wd.Wc1, C1, H1, W1); dY1 = cg; }
+        wgrad_pad<TA>(h, dY1, C1, C1, TP<TA>(tp.cols), h->K1pad, h->K1pad, GA(h, h->enc_w[0]), NO, NO, wd.rows1, st, GA(h, h->enc_b[0]));
         if (grad_input) {
-            REQUIRE(rows_in < (1LL << 31), "input too large for the first-conv backward GEMM");
-            gemm_dx<TA>(h, ga1, C1, h->enc_wT[0], wb, h->K1pad, (int)rows_in, h->K1pad, C1, st);
+            REQUIRE(wd.rows1 < (1LL << 31), "input too large for the first-conv backward GEMM");
+            gemm_dx<TA>(h, dY1, C1, h->enc_wT[0], wb, h->K1pad, (int)wd.rows1, h->K1pad, C1, st);
             const long long tot = (long long)in_elems;
-            wide_col2im_cf_kernel<TA><<<blocks_for(tot, 256), 256, 0, st>>>(wb, D, H, W, g.k0, (g.k0 - 1) / 2, h->K1pad, grad_input, tot);
+            wide_col2im_cf_kernel<TA><<<blocks_for(tot, 256), 256, 0, st>>>(wb, D, H, W, g.k0, (g.k0 - 1) / 2, h->K1pad, grad_input, tot,
+                                                                           h->st[0], wd.Hc1, wd.Wc1);
             CK(cudaGetLastError());
             h->launches++;
         }
@@ -3070,7 +3145,6 @@ int tante_train_forward(tante_handle_t h, int32_t slot, const float* input, int3
         REQUIRE(n_cap >= 1, "n_cap must be >= 1");
         REQUIRE(slot >= 0 && slot < (int)h->tapes.size(), "tape slot out of range: call tante_reserve(.., training = slots)");
         REQUIRE(h->T <= 16, "training supports in_T <= 16");
-        REQUIRE(!h->overlap, "training with overlap_ratio != 0 is not implemented (inference / rollout only)");
         CK(cudaSetDevice(h->device));
         ensure_ready(h, B);
         cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

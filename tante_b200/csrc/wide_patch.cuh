@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(256) f32_to_ta_kernel(const float* __restrict_
 // transpose of wide_im2col_cl_kernel: grid gradient [n][Hs][Ws][Cin] from the patch-matrix gradient; thread = 4 channels
 template <typename TA>
 __global__ void __launch_bounds__(256)
-wide_col2im_cl_kernel(const TA* __restrict__ dcols, int Hs, int Ws, int Cin, int k, int shift, TA* __restrict__ dgrid, long long total4) {
+wide_col2im_cl_kernel(const TA* __restrict__ dcols, int Hs, int Ws, int Cin, int k, int shift, TA* __restrict__ dgrid, long long total4,
+                      int stride = 0, int Hc = 0, int Wc = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total4) return;
     const int C4 = Cin / 4;
@@ -210,11 +211,27 @@ wide_col2im_cl_kernel(const TA* __restrict__ dcols, int Hs, int Ws, int Cin, int
     const int x = (int)(r % Ws); r /= Ws;
     const int y = (int)(r % Hs);
     const long long n = r / Hs;
-    const int Ho = Hs / k, Wo = Ws / k;
     const int yy = y + shift, xx = x + shift;
-    const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (i < Ho && j < Wo) Vec4<TA>::load(dcols + ((((size_t)n * Ho + i) * Wo + j) * (k * k) + (di * k + dj)) * Cin + c4 * 4, v);
+    if (stride <= 0 || stride == k) {
+        const int Ho = Hs / k, Wo = Ws / k;
+        const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
+        if (i < Ho && j < Wo) Vec4<TA>::load(dcols + ((((size_t)n * Ho + i) * Wo + j) * (k * k) + (di * k + dj)) * Cin + c4 * 4, v);
+    } else {
+        // overlapping windows: the pixel is tap (di, dj) of every window ((yy - di) / stride, (xx - dj) / stride) on the conv grid
+        for (int di = yy % stride; di < k; di += stride) {
+            const int i = (yy - di) / stride;
+            if (i < 0 || i >= Hc) continue;
+            for (int dj = xx % stride; dj < k; dj += stride) {
+                const int j = (xx - dj) / stride;
+                if (j < 0 || j >= Wc) continue;
+                float t4[4];
+                Vec4<TA>::load(dcols + ((((size_t)n * Hc + i) * Wc + j) * (k * k) + (di * k + dj)) * Cin + c4 * 4, t4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] += t4[e];
+            }
+        }
+    }
     Vec4<TA>::store(dgrid + idx * 4, v);
 }
 
@@ -222,7 +239,7 @@ wide_col2im_cl_kernel(const TA* __restrict__ dcols, int Hs, int Ws, int Cin, int
 template <typename TA>
 __global__ void __launch_bounds__(256)
 wide_col2im_cf_kernel(const TA* __restrict__ dcols, int D, int H, int W, int k, int shift, int Kpad, float* __restrict__ gin,
-                      long long total) {
+                      long long total, int stride = 0, int Hc = 0, int Wc = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // ((bt * D + d) * H + y) * W + x
     if (idx >= total) return;
     long long r = idx;
@@ -230,10 +247,24 @@ wide_col2im_cf_kernel(const TA* __restrict__ dcols, int D, int H, int W, int k, 
     const int y = (int)(r % H); r /= H;
     const int d = (int)(r % D);
     const long long bt = r / D;
-    const int Ho = H / k, Wo = W / k;
     const int yy = y + shift, xx = x + shift;
-    const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
-    if (i < Ho && j < Wo) gin[idx] += to_f32(dcols[(((size_t)bt * Ho + i) * Wo + j) * Kpad + (di * k + dj) * D + d]);
+    if (stride <= 0 || stride == k) {
+        const int Ho = H / k, Wo = W / k;
+        const int i = yy / k, di = yy - i * k, j = xx / k, dj = xx - j * k;
+        if (i < Ho && j < Wo) gin[idx] += to_f32(dcols[(((size_t)bt * Ho + i) * Wo + j) * Kpad + (di * k + dj) * D + d]);
+        return;
+    }
+    float v = 0.f;
+    for (int di = yy % stride; di < k; di += stride) {
+        const int i = (yy - di) / stride;
+        if (i < 0 || i >= Hc) continue;
+        for (int dj = xx % stride; dj < k; dj += stride) {
+            const int j = (xx - dj) / stride;
+            if (j < 0 || j >= Wc) continue;
+            v += to_f32(dcols[(((size_t)bt * Hc + i) * Wc + j) * Kpad + (di * k + dj) * D + d]);
+        }
+    }
+    gin[idx] += v;
 }
 
 // weight with which resized pixel `dst` reads source sample `src` (bilinear_src above; both taps may hit the same sample at the border)
@@ -250,7 +281,7 @@ __device__ __forceinline__ float bilinear_w(int dst, int src, int in_size, int o
 template <typename TA, bool FIELD>
 __global__ void __launch_bounds__(256)
 wide_deconv_post_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ gf, int ldS, int hi, int wi, int Cout, int k,
-                            TA* __restrict__ dS, long long total) {
+                            TA* __restrict__ dS, long long total, int sd = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // row * ldS + col
     if (idx >= total) return;
     const int col = (int)(idx % ldS);
@@ -264,21 +295,26 @@ wide_deconv_post_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ 
         const long long n = row / hi;
         const int Ho = hi * k, Wo = wi * k;
         const int pad = (k - 1) / 2;
-        const int y = k * i + di - pad, x = k * j + dj - pad;
+        const int se = sd > 0 ? sd : k;      // (with overlap several (i, di) pairs land on the same sample: each receives its gradient)
+        const int y = se * i + di - pad, x = se * j + dj - pad;
+        const int Hd = (hi - 1) * se - 2 * pad + k, Wd = (wi - 1) * se - 2 * pad + k;
         auto at = [&](int Y, int X) -> float {
             return FIELD ? gf[(((size_t)n * Cout + co) * Ho + Y) * Wo + X] : to_f32(g[(((size_t)n * Ho + Y) * Wo + X) * Cout + co]);
         };
-        if (pad == 0) {
-            v = at(y, x);
+        if (Hd == Ho && Wd == Wo) {
+            if (y >= 0 && y < Ho && x >= 0 && x < Wo) v = at(y, x);
         } else {
-            const int Hd = Ho - 2 * pad, Wd = Wo - 2 * pad;
             if (y >= 0 && y < Hd && x >= 0 && x < Wd) {
-                // resized pixel Y reads samples floor(src(Y)) and +1 with src(Y) in (Y - 2 pad, Y]: sample y is read by Y in [y - 1, y + 2 pad + 1]
-                for (int Y = max(y - 1, 0); Y <= min(y + 2 * pad + 1, Ho - 1); ++Y) {
+                // resized pixel Y reads the samples floor(src(Y)), + 1 with src(Y) = (Hd / Ho)(Y + 0.5) - 0.5 (clamped at 0): sample y can only
+                // be read by Y with src(Y) in (y - 1, y + 1); bilinear_w decides exactly
+                const float ry = (float)Ho / (float)Hd, rx = (float)Wo / (float)Wd;
+                const int Ylo = max((int)floorf(((float)y - 0.5f) * ry - 0.5f) - 1, 0), Yhi = min((int)ceilf(((float)y + 1.5f) * ry - 0.5f) + 1, Ho - 1);
+                const int Xlo = max((int)floorf(((float)x - 0.5f) * rx - 0.5f) - 1, 0), Xhi = min((int)ceilf(((float)x + 1.5f) * rx - 0.5f) + 1, Wo - 1);
+                for (int Y = Ylo; Y <= Yhi; ++Y) {
                     const float wy = bilinear_w(Y, y, Hd, Ho);
                     if (wy == 0.f) continue;
                     float acc = 0.f;
-                    for (int X = max(x - 1, 0); X <= min(x + 2 * pad + 1, Wo - 1); ++X) {
+                    for (int X = Xlo; X <= Xhi; ++X) {
                         const float wx = bilinear_w(X, x, Wd, Wo);
                         if (wx != 0.f) acc = fmaf(wx, at(Y, X), acc);
                     }
@@ -288,6 +324,61 @@ wide_deconv_post_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ 
         }
     }
     dS[idx] = from_f32<TA>(v);
+}
+
+// transpose of wide_pool_kernel: conv-grid gradient [n][Hc][Wc][C] from the patch-grid gradient g [n][Ho][Wo][C] (TA; or fp32 G32 for
+// the last encoder stage, whose pooled output is the fp32 pre-embedding).  A conv-grid pixel may sit in two neighbouring windows
+// per axis (torch's adaptive windows overlap when Hc is not a multiple of Ho).  Thread = 4 channels.
+template <typename TA, bool G32>
+__global__ void __launch_bounds__(256)
+wide_pool_bwd_kernel(const TA* __restrict__ g, const float* __restrict__ g32, int Hc, int Wc, int C, int Ho, int Wo, TA* __restrict__ dconv,
+                     long long total4) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total4) return;
+    const int C4 = C / 4;
+    const int c4 = (int)(idx % C4);
+    long long r = idx / C4;
+    const int x = (int)(r % Wc); r /= Wc;
+    const int y = (int)(r % Hc);
+    const long long n = r / Hc;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ilo = max((int)(((long long)y * Ho) / Hc) - 1, 0), ihi = min((int)(((long long)(y + 1) * Ho + Hc - 1) / Hc), Ho - 1);
+    const int jlo = max((int)(((long long)x * Wo) / Wc) - 1, 0), jhi = min((int)(((long long)(x + 1) * Wo + Wc - 1) / Wc), Wo - 1);
+    for (int i = ilo; i <= ihi; ++i) {
+        const int y0 = (i * Hc) / Ho, y1 = ((i + 1) * Hc + Ho - 1) / Ho;
+        if (y < y0 || y >= y1) continue;
+        for (int j = jlo; j <= jhi; ++j) {
+            const int x0 = (j * Wc) / Wo, x1 = ((j + 1) * Wc + Wo - 1) / Wo;
+            if (x < x0 || x >= x1) continue;
+            const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+            float v[4];
+            const size_t off = (((size_t)n * Ho + i) * Wo + j) * C + c4 * 4;
+            if (G32) Vec4<float>::load(g32 + off, v);
+            else Vec4<TA>::load(g + off, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = fmaf(v[e], inv, acc[e]);
+        }
+    }
+    Vec4<TA>::store(dconv + idx * 4, acc);
+}
+
+// bias gradient of an overlapped last decoder stage: db[d] += sum over (n, pixels) of the field gradient gf [n][D][HW]
+__global__ void __launch_bounds__(256) field_bias_grad_kernel(const float* __restrict__ gf, int D, long long HW, long long N,
+                                                              float* __restrict__ gb) {
+    const int d = blockIdx.x;
+    const long long chunk = blockIdx.y, nchunk = gridDim.y;
+    float acc = 0.f;
+    for (long long n = 0; n < N; ++n)
+        for (long long i = chunk * blockDim.x + threadIdx.x; i < HW; i += nchunk * blockDim.x) acc += gf[((size_t)n * D + d) * HW + i];
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        atomicAdd(gb + d, t);
+    }
 }
 
 // transpose of the Horner emit (training: contiguous window, frames (B, n_cap, D, H, W)): gradient of the K derivative fields

@@ -58,7 +58,7 @@ typedef struct tante_config {
     float frame_interval;
     int32_t precision;      /* TANTE_PREC_*                                         */
     int32_t n_layers[TANTE_MAX_ORDER];                 /* len(segment k) of attn_axes */
-    char axes[TANTE_MAX_ORDER][TANTE_MAX_LAYERS];      /* axis letter per layer: T/H/W (L/Y/A/C: inference) */
+    char axes[TANTE_MAX_ORDER][TANTE_MAX_LAYERS];      /* axis letter per layer: T / H / W / L / Y / A / C          */
     int32_t enc_dec_fno;    /* 0: enc_dec_type='cnn' (enc_dec_cnn.py), 1: 'fno' (enc_dec_fno.py; inference / rollout) */
     int32_t modes1, modes2; /* SpectralLayer modes of the fno encoder / decoder (models/tante.py:56-57)            */
     int32_t mlp_hidden;     /* int(embed_dim * mlp_ratio) of the block MLP (attn_backbone.py:52); 0 = embed_dim; multiple of 64, <= 1024 */

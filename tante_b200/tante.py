@@ -547,7 +547,7 @@ class TANTE(nn.Module):
 
         # parameter containers, created in the reference's order (tante.py:85-123)
         self.decoders = nn.ModuleList()
-        if enc_dec_type == "fno":             # enc_dec_fno.py:224-301 (inference / rollout only)
+        if enc_dec_type == "fno":             # enc_dec_fno.py:224-301
             self.encoder = _EncFNO(self.n_channel, embed_dim, self.patch_kernels, modes1, modes2)
             for _ in range(taylor_order):
                 self.decoders.append(_DecFNO(self.n_channel, embed_dim, self.patch_kernels, modes1, modes2))

@@ -124,13 +124,15 @@ template <typename TA, bool ACT, bool FIELD>
 __global__ void __launch_bounds__(256) spec_out_kernel(const float2* __restrict__ Bh, SpecView in, const float* __restrict__ w0,
                                                        const float* __restrict__ b0, int Cin, int Cout, int H, int W, int m2,
                                                        const float2* __restrict__ twW, TA* __restrict__ out, float* __restrict__ field,
-                                                       long long total) {
+                                                       long long total, int conv_done = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     int o, w, h;
     long long n;
+    // thread order: w fastest in both cases, so that a warp shares one Bh row (broadcast loads) -- with the channel fastest every
+    // thread walked its own row (32 cache lines per load); the channels-last stores are strided instead, a far smaller cost
     if (FIELD) { long long r = idx; w = (int)(r % W); r /= W; h = (int)(r % H); r /= H; o = (int)(r % Cout); n = r / Cout; }
-    else { long long r = idx; o = (int)(r % Cout); r /= Cout; w = (int)(r % W); r /= W; h = (int)(r % H); n = r / H; }
+    else { long long r = idx; w = (int)(r % W); r /= W; o = (int)(r % Cout); r /= Cout; h = (int)(r % H); n = r / H; }
     const float2* bh = Bh + (((size_t)n * Cout + o) * H + h) * m2;
     float acc = bh[0].x;
     int t = 0;
@@ -141,12 +143,18 @@ __global__ void __launch_bounds__(256) spec_out_kernel(const float2* __restrict_
         acc = fmaf(2.f, fmaf(v.x, tw.x, -v.y * tw.y), acc);
     }
     float v = acc / ((float)H * (float)W);
-    float s = b0[o];
-    for (int c = 0; c < Cin; ++c) s = fmaf(w0[(size_t)o * Cin + c], spec_read<TA>(in, n, c, h, w, Cin, H, W), s);
+    // 1x1 conv + bias: computed here (thin layers), or already sitting in `out` (conv_done: a GEMM wrote it -- run_spectral)
+    float s;
+    if (conv_done) {
+        s = to_f32(out[(((size_t)n * H + h) * W + w) * Cout + o]);
+    } else {
+        s = b0[o];
+        for (int c = 0; c < Cin; ++c) s = fmaf(w0[(size_t)o * Cin + c], spec_read<TA>(in, n, c, h, w, Cin, H, W), s);
+    }
     v += s;
     if (ACT) v = ActMath<TA>::gelu_erf_f(v);
     if (FIELD) field[idx] = v;
-    else out[idx] = from_f32<TA>(v);
+    else out[(((size_t)n * H + h) * W + w) * Cout + o] = from_f32<TA>(v);
 }
 
 // ---- training: adjoints of the five passes ----------------------------------------------------------------------------------
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(256) spec_in_bwd_kernel(const float2* __restri
     int c, w, h;
     long long n;
     if (CF) { long long r = idx; w = (int)(r % W); r /= W; h = (int)(r % H); r /= H; c = (int)(r % Cin); n = r / Cin; }
-    else { long long r = idx; c = (int)(r % Cin); r /= Cin; w = (int)(r % W); r /= W; h = (int)(r % H); n = r / H; }
+    else { long long r = idx; w = (int)(r % W); r /= W; c = (int)(r % Cin); r /= Cin; h = (int)(r % H); n = r / H; }      // (w fastest: see spec_out_kernel)
     const float2* ga = gA + (((size_t)n * Cin + c) * H + h) * m2;
     float acc = ga[0].x;
     int t = 0;
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(256) spec_in_bwd_kernel(const float2* __restri
     }
     for (int o = 0; o < Cout; ++o) acc = fmaf(w0[(size_t)o * Cin + c], spec_read<TA>(g, n, o, h, w, Cout, H, W), acc);
     if (CF) gin[idx] += acc;
-    else dx[idx] = from_f32<TA>(acc);
+    else dx[(((size_t)n * H + h) * W + w) * Cin + c] = from_f32<TA>(acc);
 }
 
 // dw0[o][c] += sum_{n,h,w} g[n,o,h,w] x[n,c,h,w] and db[o] += sum g  for the thin layers (a field or frame side: few channels);

@@ -1780,6 +1780,7 @@ void backward_alloc(tante_handle_s* h, int B) {
     if (h->chan) {
         // channel-axis backward: chunks of 512 latent tokens (131072 rows of width E; ~10 KB of scratch per row in the exact mode)
         h->chanb_tokens = (int)std::min<size_t>(tokens, 512);
+        if (const char* e = getenv("TANTE_CHAN_CHUNK")) h->chanb_tokens = std::max(1, std::min(h->chanb_tokens, atoi(e)));
         const size_t rows = (size_t)h->chanb_tokens * C, E = h->chanE, Hc = h->chanHc;
         dev_alloc(h, h->cb_x0, rows * E * 4);
         dev_alloc(h, h->cb_xm, rows * E * 4);
@@ -2947,6 +2948,7 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
         if (h->chan) {
             // channel pass: chunks of latent tokens, rows = chunk * C channel tokens of width E (about 3.5 KB per row in fp32)
             h->chan_tokens = (int)std::min<size_t>(tokens, 2048);
+            if (const char* e = getenv("TANTE_CHAN_CHUNK")) h->chan_tokens = std::max(1, std::min(h->chan_tokens, atoi(e)));      // (tests: ragged chunks)
             const size_t rows = (size_t)h->chan_tokens * C;
             dev_alloc(h, h->cx, rows * h->chanE * 4);
             dev_alloc(h, h->cln, rows * h->chanE * es);

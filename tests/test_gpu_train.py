@@ -464,3 +464,26 @@ def test_train_step_uses_windowed_bptt_and_matches_chained_path(monkeypatch):
         out.append((float(loss), bucket.flat.clone()))
     assert abs(out[0][0] - out[1][0]) < 1e-6 * max(1.0, abs(out[0][0]))
     assert rel_l2(out[1][1].cpu().numpy(), out[0][1].cpu().numpy()) < 2e-5
+
+
+def test_channel_axis_chunking_is_invisible(monkeypatch):
+    """The axis-C pass runs in chunks of latent tokens (forward: 2048, backward: 512): with a chunk size that does not divide the
+    token count (TANTE_CHAN_CHUNK=80 over 192 tokens) outputs and gradients must equal the single-chunk run bitwise."""
+    from gpu_util import make_model
+    cfg = O.OracleConfig(n_fields=2, H=32, W=48, taylor_order=1, attn_axes="TCW", deg=True)
+    sd = O.make_state_dict(cfg, 611, 0.0)
+    x = O.make_input(cfg, 2, 612).cuda()
+
+    def run():
+        model = make_model(cfg, sd, "fp32").train()
+        xg = x.clone().requires_grad_(True)
+        y = model(xg)
+        y.square().sum().backward()
+        return y.detach().clone(), xg.grad.clone(), {n: p.grad.clone() for n, p in model.named_parameters()}
+    y0, gx0, g0 = run()
+    monkeypatch.setenv("TANTE_CHAN_CHUNK", "80")
+    y1, gx1, g1 = run()
+    assert torch.equal(y0, y1)
+    assert rel_l2(gx1.cpu().numpy(), gx0.cpu().numpy()) < 1e-6      # (weight gradients accumulate per chunk: summation order differs)
+    for n in g0:
+        assert rel_l2(g1[n].cpu().numpy(), g0[n].cpu().numpy()) < 1e-5, n

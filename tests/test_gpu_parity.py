@@ -219,7 +219,10 @@ def test_forward_bf16_matches_reference_golden(name):
     assert _prefix_rel(d_got, z["frames"] - u0_ref, meta["n"], s, n_common, per) < 5e-2
 
 
-@pytest.mark.parametrize("name", ["fwd_stages_k2_p8", "trl_k1_b13", "fwd_deg_k1_p8"])
+@pytest.mark.parametrize("name", ["fwd_stages_k2_p8", "trl_k1_b13", "fwd_deg_k1_p8",
+                                  # the 8(f) configurations inside the captured rollout graph in the tensor mode: wide patch stages
+                                  # (split-K GEMMs at P = 64), overlap, channel attention, fno with 8x8 stages, composite axes
+                                  "fwd_adp_k1_p64", "fwd_adp_k2_ov50_p8", "fwd_adp_k2_axes_c", "fwd_deg_k1_fno_p32", "fwd_adp_k2_axes_lya"])
 def test_rollout_bf16_matches_reference_golden(name):
     from tante_b200 import rollout_eval
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")

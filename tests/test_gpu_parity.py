@@ -69,7 +69,10 @@ def test_stage_tensors_fp32():
 
 
 @pytest.mark.parametrize("name", ["fwd_deg_k1_p8", "fwd_stages_k2_p8", "fwd_adp_k3_p4", "fwd_adp_k1_p2",
-                                  "trl_k1_b13", "trl_k2_b52"])
+                                  "trl_k1_b13", "trl_k2_b52",
+                                  # 8(f) configurations: whole-batch AND per-sample rollouts against the reference's
+                                  "fwd_adp_k2_p16", "fwd_adp_k1_p64", "fwd_adp_k2_ov50_p8", "fwd_adp_k2_axes_c", "fwd_adp_k2_fno_p4",
+                                  "fwd_adp_k2_axes_lya"])
 def test_rollout_fp32_matches_reference_golden(name):
     from tante_b200 import rollout_eval
     z, meta, cfg, sd, x, model = _setup(name)

@@ -288,6 +288,11 @@ def main_overlap(ns):
                                                overlap_ratio=0.7), B=1, out_T=1, rt_bias=0.0, n_roll=2, stride=11)
     case_train(ns, "train_deg_k1_ov50_p8", C(n_fields=3, H=32, W=32, taylor_order=1, attn_axes="THW", deg=True, overlap_ratio=0.5),
                B=2, n_steps=2)
+    case_forward(ns, "fwd_adp_k1_fno_ov50_p8", C(n_fields=3, H=64, W=96, taylor_order=1, attn_axes="TW", deg=False, enc_dec_type="fno",
+                                                  patch_scale=8, modes1=16, modes2=16, overlap_ratio=0.5), B=2, out_T=4, rt_bias=1.3,
+                 n_roll=4, stride=7)
+    case_train(ns, "train_deg_k1_fno_ov30_p16", C(n_fields=2, H=64, W=64, taylor_order=1, attn_axes="TH", deg=True, enc_dec_type="fno",
+                                                   patch_scale=16, modes1=8, modes2=8, overlap_ratio=0.3), B=1, n_steps=2)
     case_train(ns, "train_adp_k1_ov40_p16", C(n_fields=2, H=64, W=64, taylor_order=1, attn_axes="TH", deg=False, patch_scale=16,
                                                overlap_ratio=0.4), B=2, n_steps=2, rt_bias=0.0)
 

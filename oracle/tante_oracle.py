@@ -198,9 +198,10 @@ def encoder_fno(sd, cfg: OracleConfig, x):
     ps = PATCH_MAP_FNO[cfg.patch_scale]
     z = x.reshape(B * T, D, H, W)
     z = gelu_erf(spectral_layer(sd, "encoder.enc_spectral_1.", z, cfg.modes1, cfg.modes2))
-    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_1.conv.weight"], sd["encoder.enc_conv_1.conv.bias"], ps[0]))
+    st = [patch_stride(k, cfg.overlap_ratio) for k in ps]
+    z = gelu_erf(_patch_conv(z, sd["encoder.enc_conv_1.conv.weight"], sd["encoder.enc_conv_1.conv.bias"], ps[0], st[0]))
     z = gelu_erf(spectral_layer(sd, "encoder.enc_spectral_2.", z, cfg.modes1 // ps[0], cfg.modes2 // ps[0]))
-    z = _patch_conv(z, sd["encoder.enc_conv_2.conv.weight"], sd["encoder.enc_conv_2.conv.bias"], ps[1])
+    z = _patch_conv(z, sd["encoder.enc_conv_2.conv.weight"], sd["encoder.enc_conv_2.conv.bias"], ps[1], st[1])
     return z.reshape(B, T, z.shape[1], z.shape[2], z.shape[3]).permute(0, 1, 3, 4, 2).contiguous()
 
 
@@ -209,9 +210,10 @@ def decoder_fno(sd, cfg: OracleConfig, k: int, d):
     ps = PATCH_MAP_FNO[cfg.patch_scale]
     p = f"decoders.{k}."
     z = d.permute(0, 3, 1, 2)
-    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_1.deconv.weight"], sd[p + "dec_conv_1.deconv.bias"], ps[1]))
+    st = [patch_stride(kk, cfg.overlap_ratio) for kk in ps]
+    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_1.deconv.weight"], sd[p + "dec_conv_1.deconv.bias"], ps[1], st[1]))
     z = gelu_erf(spectral_layer(sd, p + "dec_spectral_1.", z, cfg.modes1 // ps[0], cfg.modes2 // ps[0]))
-    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_2.deconv.weight"], sd[p + "dec_conv_2.deconv.bias"], ps[0]))
+    z = gelu_erf(_patch_deconv(z, sd[p + "dec_conv_2.deconv.weight"], sd[p + "dec_conv_2.deconv.bias"], ps[0], st[0]))
     return spectral_layer(sd, p + "dec_spectral_2.", z, cfg.modes1, cfg.modes2)
 
 

@@ -316,7 +316,6 @@ void build_plan(tante_handle_s* h) {
         REQUIRE(h->st[i] >= 1 && h->st[i] <= k[i], "stride of a patch stage must be in 1..kernel size");
         if (h->st[i] != k[i]) h->overlap = true;
     }
-    REQUIRE(!(h->overlap && h->fno), "overlap_ratio != 0 with enc_dec_type='fno' is not implemented");
     h->wide = c.patch_scale >= 16 || h->fno || h->overlap;
     h->K1pad = (k[0] * k[0] * c.n_fields + 63) / 64 * 64;
     h->NOpad = h->K1pad;
@@ -1058,16 +1057,46 @@ void run_spectral(tante_handle_s* h, const SpecPlan& sp, const SpecView& in, lon
 // conv over a channels-last grid as gather + GEMM; K beyond the tcgen05 GEMM's resident slice (1024) runs in K blocks
 template <typename TA>
 void conv_cl_gemm(tante_handle_s* h, int epi, const TA* grid, int Hs, int Ws, int Cin, int k, int64_t w_off, void* out, int Cout,
-                  bool out_f32, long long n_img, EpiParams ep, cudaStream_t st) {
+                  bool out_f32, long long n_img, EpiParams ep, cudaStream_t st, int sd = 0) {
     TA* wb = reinterpret_cast<TA*>(h->wbuf.p);
     const int K = k * k * Cin;
-    const long long rows = n_img * (Hs / k) * (Ws / k);
+    const int se = sd > 0 ? sd : k, pad = (k - 1) / 2;
+    const int Hc = (Hs + 2 * pad - k) / se + 1, Wc = (Ws + 2 * pad - k) / se + 1;      // conv grid; == the patch grid without overlap
+    const int Ho = Hs / k, Wo = Ws / k;
+    const bool pooled = Hc != Ho || Wc != Wo;
+    const long long rows = n_img * Hc * Wc;
     REQUIRE(rows < (1LL << 31), "input too large for the gather GEMM");
     const long long total4 = rows * K / 4;
-    wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(grid, Hs, Ws, Cin, k, (k - 1) / 2, wb, total4);
+    wide_im2col_cl_kernel<TA><<<blocks_for(total4, 256), 256, 0, st>>>(grid, Hs, Ws, Cin, k, pad, wb, total4, se, Hc, Wc);
     CK(cudaGetLastError());
     h->launches++;
-    if (sizeof(TA) == 2 && K > 1024) {
+    const bool bigk = sizeof(TA) == 2 && K > 1024;
+    if (pooled) {
+        // overlap_ratio != 0: GEMM (+ bias) onto the conv grid, adaptive average pooling (+ GELU) to the patch grid
+        REQUIRE(epi == EPI_BIAS || epi == EPI_BIAS_GELU_ERF, "pooled conv: epilogue not covered");
+        REQUIRE((size_t)rows * Cout * sizeof(TA) <= h->cgrid.bytes, "pooled conv: conv-grid scratch not reserved");
+        TA* cg = reinterpret_cast<TA*>(h->cgrid.p);
+        if (bigk) {
+            REQUIRE((size_t)rows * Cout * 4 <= h->kscratch.bytes, "split-K conv: scratch not reserved");
+            float* v = reinterpret_cast<float*>(h->kscratch.p);
+            gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(wb), K, w_off, v, (int)rows, Cout, K, ep.bias, st);
+            f32_to_ta_kernel<TA, false><<<blocks_for(rows * Cout / 4, 256), 256, 0, st>>>(v, cg, rows * Cout / 4);
+            CK(cudaGetLastError());
+            h->launches++;
+        } else {
+            EpiParams eb; eb.bias = ep.bias;
+            gemm<TA>(h, EPI_BIAS, wb, K, w_off, cg, Cout, false, (int)rows, Cout, K, eb, st);
+        }
+        const long long p4 = n_img * Ho * Wo * Cout / 4;
+        const unsigned nb = blocks_for(p4, 256);
+        if (out_f32) wide_pool_kernel<TA, false, true><<<nb, 256, 0, st>>>(cg, Hc, Wc, Cout, Ho, Wo, nullptr, reinterpret_cast<float*>(out), p4);
+        else if (epi == EPI_BIAS_GELU_ERF) wide_pool_kernel<TA, true, false><<<nb, 256, 0, st>>>(cg, Hc, Wc, Cout, Ho, Wo, reinterpret_cast<TA*>(out), nullptr, p4);
+        else wide_pool_kernel<TA, false, false><<<nb, 256, 0, st>>>(cg, Hc, Wc, Cout, Ho, Wo, reinterpret_cast<TA*>(out), nullptr, p4);
+        CK(cudaGetLastError());
+        h->launches++;
+        return;
+    }
+    if (bigk) {
         const __nv_bfloat16* wbh = reinterpret_cast<const __nv_bfloat16*>(wb);
         if (out_f32) {
             REQUIRE(epi == EPI_BIAS, "the split-K path writes plain fp32 outputs");
@@ -1105,15 +1134,15 @@ void run_encoder_fno(tante_handle_s* h, const StepIO& io, int B, cudaStream_t st
     run_spectral<TA>(h, h->fes1, v0, NI, H, W, 0, true, g0, nullptr, st);
     // enc_conv_1 + GELU (:260-261)
     EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
-    conv_cl_gemm<TA>(h, EPI_BIAS_GELU_ERF, g0, H, W, C8, p0, h->enc_w[0], g1, C1, false, NI, e1, st);
+    conv_cl_gemm<TA>(h, EPI_BIAS_GELU_ERF, g0, H, W, C8, p0, h->enc_w[0], g1, C1, false, NI, e1, st, h->st[0]);
     // enc_spectral_2 + GELU (:263-264)
     SpecView v1{g1, 1, nullptr, 1};
     run_spectral<TA>(h, h->fes2, v1, NI, H1, W1, 1, true, g2, nullptr, st);
     // enc_conv_2 (:265) + t_encode FiLM + embeddings -> residual stream
     EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
-    if (sizeof(TA) == 2 && p1 * p1 * C2 > 1024) {
+    if ((sizeof(TA) == 2 && p1 * p1 * C2 > 1024) || h->st[1] != p1) {      // (split-K or pooled: fp32 pre-embedding, then the embed pass)
         float* v = reinterpret_cast<float*>(h->qkv.p);
-        conv_cl_gemm<TA>(h, EPI_BIAS, g2, H1, W1, C2, p1, h->enc_w[1], v, C, true, NI, e2, st);
+        conv_cl_gemm<TA>(h, EPI_BIAS, g2, H1, W1, C2, p1, h->enc_w[1], v, C, true, NI, e2, st, h->st[1]);
         embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(v, AF(h, h->film_t_off), AF(h, h->s_emb),
                                                                                   AF(h, h->t_emb), x, tokens, T, L, C);
         CK(cudaGetLastError());
@@ -1136,24 +1165,26 @@ void run_decoder_fno(tante_handle_s* h, int o, const TA* dmod, int B, cudaStream
     TA* g1 = reinterpret_cast<TA*>(h->fg1.p);      // [B][H1][W1][C1]
     TA* g2 = reinterpret_cast<TA*>(h->fg2.p);      // [B][H1][W1][C2]
     float* field = reinterpret_cast<float*>(h->dfield.p) + (size_t)o * B * D * H * W;
-    auto post = [&](const TA* S, int ldS, int hi, int wi, int Cout, int k, TA* out) {
+    auto post = [&](const TA* S, int ldS, int hi, int wi, int Cout, int k, int sd, const float* bias, TA* out) {
         const long long total = (long long)B * (hi * k) * (wi * k) * Cout;
-        wide_deconv_post_kernel<TA, true, false><<<blocks_for(total, 256), 256, 0, st>>>(S, ldS, hi, wi, Cout, k, nullptr, out, nullptr, total);
+        wide_deconv_post_kernel<TA, true, false><<<blocks_for(total, 256), 256, 0, st>>>(S, ldS, hi, wi, Cout, k, bias, out, nullptr, total, sd);
         CK(cudaGetLastError());
         h->launches++;
     };
+    // (overlapped stages: bias-free GEMM, bias once per output sample in the resample pass -- see run_decoder_wide)
+    const bool ov1 = h->st[1] != p1, ov0 = h->st[0] != p0;
     // dec_conv_1 (p1) + GELU
     const int N1 = p1 * p1 * C2, N2 = p0 * p0 * C8;
-    EpiParams ed; ed.bias = AF(h, op.decb[0]);
+    EpiParams ed; ed.bias = ov1 ? AF(h, h->zero_off) : AF(h, op.decb[0]);
     gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ed, st);
-    post(wb, N1, Hp, Wp, C2, p1, g2);
+    post(wb, N1, Hp, Wp, C2, p1, h->st[1], ov1 ? AF(h, op.decb[0]) : nullptr, g2);
     // dec_spectral_1 + GELU
     SpecView v2{g2, 1, nullptr, 1};
     run_spectral<TA>(h, op.fs1, v2, B, H1, W1, 1, true, g1, nullptr, st);
     // dec_conv_2 (p0) + GELU
-    ed.bias = AF(h, op.decb[1]);
+    ed.bias = ov0 ? AF(h, h->zero_off) : AF(h, op.decb[1]);
     gemm<TA>(h, EPI_BIAS, g1, C1, op.decw[1], wb, N2, false, B * H1 * W1, N2, C1, ed, st);
-    post(wb, N2, H1, W1, C8, p0, g0);
+    post(wb, N2, H1, W1, C8, p0, h->st[0], ov0 ? AF(h, op.decb[1]) : nullptr, g0);
     // dec_spectral_2 -> derivative field
     SpecView v0{g0, 1, nullptr, 1};
     run_spectral<TA>(h, op.fs2, v0, B, H, W, 0, false, nullptr, field, st);
@@ -1841,13 +1872,13 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         run_spectral<TA>(h, h->fes1, v0, NI, H, W, 0, false, TP<TA>(tp.f0pre), nullptr, st);
         launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.f0pre), TP<TA>(tp.f0act), NI * H * W * C8, st);
         EpiParams e1; e1.bias = AF(h, h->enc_b[0]);
-        conv_cl_gemm<TA>(h, EPI_BIAS, TP<TA>(tp.f0act), H, W, C8, p0, h->enc_w[0], tp.a1pre.p, C1, false, NI, e1, st);
+        conv_cl_gemm<TA>(h, EPI_BIAS, TP<TA>(tp.f0act), H, W, C8, p0, h->enc_w[0], tp.a1pre.p, C1, false, NI, e1, st, h->st[0]);
         launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a1pre), TP<TA>(tp.a1act), NI * H1 * W1 * C1, st);
         SpecView v1{tp.a1act.p, 1, nullptr, 1};
         run_spectral<TA>(h, h->fes2, v1, NI, H1, W1, 1, false, TP<TA>(tp.a2pre), nullptr, st);
         launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(tp.a2pre), TP<TA>(tp.a2act), NI * H1 * W1 * C2, st);
         EpiParams e2; e2.bias = AF(h, h->enc_b[1]);
-        conv_cl_gemm<TA>(h, EPI_BIAS, TP<TA>(tp.a2act), H1, W1, C2, p1, h->enc_w[1], tp.v.p, C, true, NI, e2, st);
+        conv_cl_gemm<TA>(h, EPI_BIAS, TP<TA>(tp.a2act), H1, W1, C2, p1, h->enc_w[1], tp.v.p, C, true, NI, e2, st, h->st[1]);
         embed_fwd_kernel<<<blocks_for((long long)tokens * C / 4, 256), 256, 0, st>>>(
             FP(tp.v), AF(h, h->film_t_off), AF(h, h->s_emb), AF(h, h->t_emb), FP(tp.ord[0].P[0]), tokens, T, L, C);
         CK(cudaGetLastError());
@@ -2025,20 +2056,23 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
             const int H = h->cfg.H, W = h->cfg.W, p0 = h->fp0, p1 = h->fp1, H1 = H / p0, W1 = W / p0, C8 = C / 8, D = h->D;
             const int N1 = p1 * p1 * C2, N2 = p0 * p0 * C8;
             float* field = FP(h->dfield) + (size_t)o * B * D * H * W;
-            EpiParams ew; ew.bias = AF(h, op.decb[0]);
+            const bool ovf1 = h->st[1] != p1, ovf0 = h->st[0] != p0;
+            EpiParams ew; ew.bias = ovf1 ? AF(h, h->zero_off) : AF(h, op.decb[0]);
             gemm<TA>(h, EPI_BIAS, dmod, C, op.decw[0], wb, N1, false, B * L, N1, C, ew, st);
             long long tot = (long long)B * H1 * W1 * C2;
-            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N1, h->Hp, h->Wp, C2, p1, nullptr, TP<TA>(ot.z1pre), nullptr, tot);
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N1, h->Hp, h->Wp, C2, p1, ovf1 ? AF(h, op.decb[0]) : nullptr,
+                                                                                          TP<TA>(ot.z1pre), nullptr, tot, h->st[1]);
             CK(cudaGetLastError());
             h->launches++;
             launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z1pre), TP<TA>(ot.z1act), tot, st);
             SpecView v2{ot.z1act.p, 1, nullptr, 1};
             run_spectral<TA>(h, op.fs1, v2, B, H1, W1, 1, false, TP<TA>(ot.z2pre), nullptr, st);
             launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.z2pre), TP<TA>(ot.z2act), (long long)B * H1 * W1 * C1, st);
-            ew.bias = AF(h, op.decb[1]);
+            ew.bias = ovf0 ? AF(h, h->zero_off) : AF(h, op.decb[1]);
             gemm<TA>(h, EPI_BIAS, TP<TA>(ot.z2act), C1, op.decw[1], wb, N2, false, B * H1 * W1, N2, C1, ew, st);
             tot = (long long)B * H * W * C8;
-            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N2, H1, W1, C8, p0, nullptr, TP<TA>(ot.f0pre), nullptr, tot);
+            wide_deconv_post_kernel<TA, false, false><<<blocks_for(tot, 256), 256, 0, st>>>(wb, N2, H1, W1, C8, p0, ovf0 ? AF(h, op.decb[1]) : nullptr,
+                                                                                          TP<TA>(ot.f0pre), nullptr, tot, h->st[0]);
             CK(cudaGetLastError());
             h->launches++;
             launch_act_fwd<TA, ACT_GELU_ERF>(h, TP<TA>(ot.f0pre), TP<TA>(ot.f0act), tot, st);
@@ -2308,22 +2342,25 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
             launch_act_bwd<TA, ACT_GELU_ERF>(h, gr0, TP<TA>(ot.f0pre), (long long)B * H * W * C8, st);
             // dec_conv_2 (p0)
             const long long MF2 = (long long)B * H1 * W1;
+            const bool ovf1 = h->st[1] != p1, ovf0 = h->st[0] != p0;      // overlapped stage: bias gradient = sum of the stage-output gradient
+            if (ovf0) launch_colsum<TA>(h, gr0, C8, (long long)B * H * W, C8, GA(h, op.decb[1]), st);
             long long tot = MF2 * NF2;
-            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(gr0, nullptr, NF2, H1, W1, C8, p0, wb, tot);
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(gr0, nullptr, NF2, H1, W1, C8, p0, wb, tot, h->st[0]);
             CK(cudaGetLastError());
             h->launches++;
-            wgrad<TA>(h, wb, NF2, TP<TA>(ot.z2act), C1, GA(h, op.decw[1]), MF2, NF2, C1, st, GA(h, op.decb[1]));
+            wgrad<TA>(h, wb, NF2, TP<TA>(ot.z2act), C1, GA(h, op.decw[1]), MF2, NF2, C1, st, ovf0 ? nullptr : GA(h, op.decb[1]));
             gemm_dx_act<TA, ACT_GELU_ERF>(h, wb, NF2, op.decwT[1], gr1, TP<TA>(ot.z2pre), (int)MF2, C1, NF2, st);
             // dec_spectral_1
             SpecView xg1{ot.z1act.p, 1, nullptr, 1}, gv1{gr1, 1, nullptr, 1};
             run_spectral_bwd<TA>(h, op.fs1, xg1, gv1, B, H1, W1, 1, gr2, nullptr, st);
             launch_act_bwd<TA, ACT_GELU_ERF>(h, gr2, TP<TA>(ot.z1pre), MF2 * C2, st);
             // dec_conv_1 (p1)
+            if (ovf1) launch_colsum<TA>(h, gr2, C2, MF2, C2, GA(h, op.decb[0]), st);
             tot = (long long)BL * NF1;
-            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(gr2, nullptr, NF1, h->Hp, h->Wp, C2, p1, wb, tot);
+            wide_deconv_post_bwd_kernel<TA, false><<<blocks_for(tot, 256), 256, 0, st>>>(gr2, nullptr, NF1, h->Hp, h->Wp, C2, p1, wb, tot, h->st[1]);
             CK(cudaGetLastError());
             h->launches++;
-            wgrad<TA>(h, wb, NF1, dmod, C, GA(h, op.decw[0]), BL, NF1, C, st, GA(h, op.decb[0]));
+            wgrad<TA>(h, wb, NF1, dmod, C, GA(h, op.decw[0]), BL, NF1, C, st, ovf1 ? nullptr : GA(h, op.decb[0]));
             gemm_dx<TA>(h, wb, NF1, op.decwT[0], hd, C, BL, C, NF1, st);
         } else if (h->wide) {
             // natural-order stages (wide_patch.cuh): transpose of (crop + bilinear resample) back to the sub-pixel matrix, then the
@@ -2488,14 +2525,29 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         TA* gr0 = TP<TA>(h->fgr0);
         TA* gr1 = TP<TA>(h->fgr1);
         TA* gr2 = TP<TA>(h->fgr2);
+        // conv grids (== the patch grids without overlap); with overlap the gradient of a pooled output first goes back to its conv grid
+        auto cdimf = [](int n, int k, int sdv) { return (n + 2 * ((k - 1) / 2) - k) / sdv + 1; };
+        const int Hc2 = cdimf(H1, p1, h->st[1]), Wc2 = cdimf(W1, p1, h->st[1]), Hc1 = cdimf(H, p0, h->st[0]), Wc1 = cdimf(W, p0, h->st[0]);
+        const bool pool2 = Hc2 != h->Hp || Wc2 != h->Wp, pool1 = Hc1 != H1 || Wc1 != W1;
+        const long long rows2 = NI * Hc2 * Wc2, rows1 = NI * Hc1 * Wc1;
+        REQUIRE(rows1 < (1LL << 31) && rows2 < (1LL << 31), "input too large for the conv backward GEMMs");
+        TA* cg = TP<TA>(h->cgrid);
         // enc_conv_2 (p1): windows of the kept C/2 grid
-        wide_im2col_cl_kernel<TA><<<blocks_for((long long)tokens * KF2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H1, W1, C2, p1, (p1 - 1) / 2,
-                                                                                               wb, (long long)tokens * KF2 / 4);
+        const TA* dY2 = g2;
+        if (pool2) {
+            const long long t4 = rows2 * C / 4;
+            wide_pool_bwd_kernel<TA, false><<<blocks_for(t4, 256), 256, 0, st>>>(g2, nullptr, Hc2, Wc2, C, h->Hp, h->Wp, cg, t4);
+            CK(cudaGetLastError());
+            h->launches++;
+            dY2 = cg;
+        }
+        wide_im2col_cl_kernel<TA><<<blocks_for(rows2 * KF2 / 4, 256), 256, 0, st>>>(TP<TA>(tp.a2act), H1, W1, C2, p1, (p1 - 1) / 2, wb,
+                                                                                   rows2 * KF2 / 4, h->st[1], Hc2, Wc2);
         CK(cudaGetLastError());
         h->launches++;
-        wgrad<TA>(h, g2, C, wb, KF2, GA(h, h->enc_w[1]), tokens, C, KF2, st, GA(h, h->enc_b[1]));
-        gemm_dx<TA>(h, g2, C, h->enc_wT[1], wb, KF2, tokens, KF2, C, st);
-        wide_col2im_cl_kernel<TA><<<blocks_for(MF1 * C2 / 4, 256), 256, 0, st>>>(wb, H1, W1, C2, p1, (p1 - 1) / 2, gr2, MF1 * C2 / 4);
+        wgrad<TA>(h, dY2, C, wb, KF2, GA(h, h->enc_w[1]), rows2, C, KF2, st, GA(h, h->enc_b[1]));
+        gemm_dx<TA>(h, dY2, C, h->enc_wT[1], wb, KF2, (int)rows2, KF2, C, st);
+        wide_col2im_cl_kernel<TA><<<blocks_for(MF1 * C2 / 4, 256), 256, 0, st>>>(wb, H1, W1, C2, p1, (p1 - 1) / 2, gr2, MF1 * C2 / 4, h->st[1], Hc2, Wc2);
         CK(cudaGetLastError());
         h->launches++;
         launch_act_bwd<TA, ACT_GELU_ERF>(h, gr2, TP<TA>(tp.a2pre), MF1 * C2, st);
@@ -2504,13 +2556,22 @@ void run_backward(tante_handle_s* h, Tape& tp, const float* input, const float* 
         run_spectral_bwd<TA>(h, h->fes2, xs1, gs1, NI, H1, W1, 1, gr1, nullptr, st);
         launch_act_bwd<TA, ACT_GELU_ERF>(h, gr1, TP<TA>(tp.a1pre), MF1 * C1, st);
         // enc_conv_1 (p0): windows of the kept C/8 grid
-        wide_im2col_cl_kernel<TA><<<blocks_for(MF1 * KF1 / 4, 256), 256, 0, st>>>(TP<TA>(tp.f0act), H, W, C8, p0, (p0 - 1) / 2, wb, MF1 * KF1 / 4);
+        const TA* dY1 = gr1;
+        if (pool1) {
+            const long long t4 = rows1 * C1 / 4;
+            wide_pool_bwd_kernel<TA, false><<<blocks_for(t4, 256), 256, 0, st>>>(gr1, nullptr, Hc1, Wc1, C1, H1, W1, cg, t4);
+            CK(cudaGetLastError());
+            h->launches++;
+            dY1 = cg;
+        }
+        wide_im2col_cl_kernel<TA><<<blocks_for(rows1 * KF1 / 4, 256), 256, 0, st>>>(TP<TA>(tp.f0act), H, W, C8, p0, (p0 - 1) / 2, wb, rows1 * KF1 / 4,
+                                                                                   h->st[0], Hc1, Wc1);
         CK(cudaGetLastError());
         h->launches++;
-        wgrad<TA>(h, gr1, C1, wb, KF1, GA(h, h->enc_w[0]), MF1, C1, KF1, st, GA(h, h->enc_b[0]));
-        REQUIRE(MF1 < (1LL << 31), "input too large for the first-conv backward GEMM");
-        gemm_dx<TA>(h, gr1, C1, h->enc_wT[0], wb, KF1, (int)MF1, KF1, C1, st);
-        wide_col2im_cl_kernel<TA><<<blocks_for(NI * H * W * C8 / 4, 256), 256, 0, st>>>(wb, H, W, C8, p0, (p0 - 1) / 2, gr0, NI * H * W * C8 / 4);
+        wgrad<TA>(h, dY1, C1, wb, KF1, GA(h, h->enc_w[0]), rows1, C1, KF1, st, GA(h, h->enc_b[0]));
+        gemm_dx<TA>(h, dY1, C1, h->enc_wT[0], wb, KF1, (int)rows1, KF1, C1, st);
+        wide_col2im_cl_kernel<TA><<<blocks_for(NI * H * W * C8 / 4, 256), 256, 0, st>>>(wb, H, W, C8, p0, (p0 - 1) / 2, gr0, NI * H * W * C8 / 4,
+                                                                                       h->st[0], Hc1, Wc1);
         CK(cudaGetLastError());
         h->launches++;
         launch_act_bwd<TA, ACT_GELU_ERF>(h, gr0, TP<TA>(tp.f0pre), NI * H * W * C8, st);
@@ -2970,8 +3031,16 @@ int tante_reserve(tante_handle_t h, int32_t max_batch, int32_t max_roll, int32_t
             dev_alloc(h, h->fB, ca * 8);
             h->f_ca = ca;
             if (es == 2 && h->fp0 * h->fp0 * C8 > 1024) dev_alloc(h, h->kscratch, NI * HW1 * C1 * 4);      // split-K enc_conv_1 (8x8 windows)
-            size_t m = NI * HW1 * (size_t)(h->fp0 * h->fp0 * C8);                     // conv_1 windows
-            m = std::max(m, NI * (HW1 / (h->fp1 * h->fp1)) * (size_t)(h->fp1 * h->fp1 * C2));      // conv_2 windows
+            auto cdimf = [](int n, int k, int sdv) { return (size_t)((n + 2 * ((k - 1) / 2) - k) / sdv + 1); };
+            const int H1f = h->cfg.H / h->fp0, W1f = h->cfg.W / h->fp0;
+            const size_t rc1 = NI * cdimf(h->cfg.H, h->fp0, h->st[0]) * cdimf(h->cfg.W, h->fp0, h->st[0]);      // conv grids (== patch grids
+            const size_t rc2 = NI * cdimf(H1f, h->fp1, h->st[1]) * cdimf(W1f, h->fp1, h->st[1]);                // without overlap)
+            size_t m = rc1 * (size_t)(h->fp0 * h->fp0 * C8);                          // conv_1 windows
+            m = std::max(m, rc2 * (size_t)(h->fp1 * h->fp1 * C2));                    // conv_2 windows
+            if (h->overlap) {
+                dev_alloc(h, h->cgrid, std::max(rc1 * C1, rc2 * C) * es);
+                if (es == 2) dev_alloc(h, h->kscratch, std::max(rc1 * C1, rc2 * C) * 4);
+            }
             m = std::max(m, (size_t)max_batch * h->L * (size_t)(h->fp1 * h->fp1 * C2));            // deconv_1 sub-pixel matrix
             m = std::max(m, (size_t)max_batch * HW1 * (size_t)(h->fp0 * h->fp0 * C8));             // deconv_2 sub-pixel matrix
             dev_alloc(h, h->wbuf, m * es);

@@ -193,7 +193,7 @@ class _Engine:
         cfg.enc_dec_fno = 1 if model.enc_dec_type == "fno" else 0
         cfg.modes1, cfg.modes2 = int(model.modes1), int(model.modes2)
         cfg.mlp_hidden = int(model.C * model.mlp_ratio)
-        for i, k in enumerate(model.patch_kernels[:3] if model.enc_dec_type == "cnn" else ()):
+        for i, k in enumerate(model.patch_kernels[:3]):      # (cnn: three stages; fno: two)
             # enc_dec_cnn.py:64-66 / 130-132: Python's round() (half to even) -- computed here so that both sides agree
             cfg.stride[i] = max(1, int(round(k * (1.0 - model.overlap_ratio))))
         cfg.expanded_channel = int(model.expanded_channel)
@@ -511,8 +511,6 @@ class TANTE(nn.Module):
         self.mlp_ratio = float(mlp_ratio)
         ks = Patch_map[patch_scale]   # KeyError for unknown patch scales, as in enc_dec_cnn.py:199
         self.patch_kernels = ks
-        if enc_dec_type == "fno" and overlap_ratio != 0.0:
-            raise NotImplementedError("overlap_ratio != 0 with enc_dec_type='fno' is not implemented")
         if enc_dec_type == "fno":
             ps = Patch_map_fno[patch_scale]
             self.patch_kernels = ps

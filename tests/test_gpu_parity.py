@@ -334,7 +334,7 @@ NEXT = ["fwd_adp_k2_p16", "fwd_deg_k1_p32", "fwd_adp_k1_p64", "fwd_adp_k1_p16_d1
         # enc_dec_type='fno' with 8x8 patch stages
         "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64",
         # overlap_ratio != 0: strided windows + adaptive pooling, overlap-add transposed convs + resize
-        "fwd_adp_k2_ov50_p8", "fwd_deg_k1_ov25_p16", "fwd_deg_k1_ov70_p32"]
+        "fwd_adp_k2_ov50_p8", "fwd_deg_k1_ov25_p16", "fwd_deg_k1_ov70_p32", "fwd_adp_k1_fno_ov50_p8"]
 
 
 @pytest.mark.parametrize("name", NEXT)
@@ -369,7 +369,7 @@ def test_next_scope_forward_and_rollout_fp32(name):
                                   "fwd_deg_k1_fno_p8", "fwd_adp_k2_fno_p4", "fwd_deg_k1_fno_p16", "fwd_adp_k2_mlp2",
                                   "fwd_deg_k1_mlp05", "fwd_adp_k2_axes_c", "fwd_deg_k1_axes_c64", "fwd_adp_k2_c512",
                                   "fwd_deg_k1_fno_p32", "fwd_adp_k1_fno_p64", "fwd_adp_k2_ov50_p8", "fwd_deg_k1_ov25_p16",
-                                  "fwd_deg_k1_ov70_p32"])
+                                  "fwd_deg_k1_ov70_p32", "fwd_adp_k1_fno_ov50_p8"])
 def test_next_scope_forward_bf16(name):
     z, meta, cfg, sd, x, model = _setup(name, precision="bf16")
     with torch.inference_mode():

@@ -95,7 +95,7 @@ def _report(model, z, meta, tol):
 @pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16",
                                   "train_deg_k1_p32", "train_deg_k1_fno_p8", "train_adp_k2_fno_p4",
                                   "train_deg_k1_c512", "train_deg_k1_fno_p32", "train_deg_k1_axes_c",
-                                  "train_deg_k1_ov50_p8", "train_adp_k1_ov40_p16"])
+                                  "train_deg_k1_ov50_p8", "train_adp_k1_ov40_p16", "train_deg_k1_fno_ov30_p16"])
 def test_training_step_fp32_matches_reference_golden(name):
     z, meta, cfg, model, x, y, loss = _train_case(name, "fp32")
     assert abs(float(loss) - float(z["loss"])) < 2e-6 * max(1.0, abs(float(z["loss"])))
@@ -110,7 +110,7 @@ def test_training_step_fp32_matches_reference_golden(name):
 @pytest.mark.parametrize("name", ["train_deg_k1", "train_adp_k2", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16",
                                   "train_deg_k1_p32", "train_deg_k1_fno_p8", "train_adp_k2_fno_p4",
                                   "train_deg_k1_c512", "train_deg_k1_fno_p32", "train_deg_k1_axes_c",
-                                  "train_deg_k1_ov50_p8", "train_adp_k1_ov40_p16"])
+                                  "train_deg_k1_ov50_p8", "train_adp_k1_ov40_p16", "train_deg_k1_fno_ov30_p16"])
 def test_training_step_bf16_close_to_reference_golden(name):
     z, meta, cfg, model, x, y, loss = _train_case(name, "bf16")
     assert abs(float(loss) - float(z["loss"])) < 2e-2 * max(1.0, abs(float(z["loss"])))

@@ -77,7 +77,8 @@ def test_stage_tensors_match_reference_golden():
 
 @pytest.mark.parametrize("name", ["train_adp_k2", "train_deg_k1", "train_deg_k1_mlp4", "train_adp_k2_lya", "train_adp_k2_p16", "train_deg_k1_p32", "train_deg_k1_fno_p8",
                                   "train_adp_k2_fno_p4", "train_deg_k1_c512", "train_deg_k1_fno_p32",
-                                  "train_deg_k1_axes_c", "train_deg_k1_ov50_p8", "train_adp_k1_ov40_p16"])
+                                  "train_deg_k1_axes_c", "train_deg_k1_ov50_p8", "train_adp_k1_ov40_p16",
+                                  "train_deg_k1_fno_ov30_p16"])
 def test_training_step_grads_match_reference_golden(name):
     z, meta = load_golden(name)
     cfg = golden_cfg(meta)

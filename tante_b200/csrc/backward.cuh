@@ -90,6 +90,22 @@ __global__ void __launch_bounds__(256) mse_cf_cl_kernel(const float* __restrict_
     }
 }
 
+// out = resid + mask / (1 - p) * y: residual add of a dropped-out branch output (tensor mode outside the fused block tail);
+// element index = position in the [tokens][C] stream, as in the fused epilogues
+template <typename TA>
+__global__ void __launch_bounds__(256) resid_drop_kernel(const TA* __restrict__ y, const float* __restrict__ resid, float* __restrict__ out,
+                                                         long long n4, DropCfg drop, uint32_t site) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float v[4], r[4];
+    Vec4<TA>::load(y + i * 4, v);
+    Vec4<float>::load(resid + i * 4, r);
+    const uint4 w = drop_words(drop, site, (unsigned long long)(i >> 1));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = fmaf(v[j], drop_mul(drop, w, (int)((i & 1) * 4 + j)), r[j]);
+    Vec4<float>::store(out + i * 4, r);
+}
+
 // fp32 -> TA copy (gradient stream -> GEMM operand)
 template <typename TA>
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ src, TA* __restrict__ dst, long long n4,

@@ -1859,8 +1859,6 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
     constexpr bool kTensor = sizeof(TA) == 2;
     tp.drop = make_drop_cfg(h->drop_p, h->drop_seed);
     const DropCfg& drop = tp.drop;
-    if (drop.p > 0.f && kTensor && !(h->fuse_tail && C == kBtC && h->Hm == C))
-        throw Error(TANTE_ERR_INVALID, "dropout in the tensor mode needs the fused block tail (TANTE_FUSE_TAIL=1, embed_dim 256)");
     // --- encoder ---
     if (h->fno) {
         // enc_FNO.forward (enc_dec_fno.py:254-272): spectral layer -> GELU -> patch conv -> GELU -> spectral layer -> GELU -> patch conv;
@@ -1997,6 +1995,29 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
                     ln_ready = nx != nullptr;
                     continue;
                 }
+            }
+            if (kTensor && drop.p > 0.f) {
+                // Tensor mode with dropout outside the fused tail (mlp_ratio != 1, embed_dim 512, TANTE_FUSE_TAIL=0): the tcgen05 GEMM
+                // epilogues carry no mask generator, so each residual branch is a plain GEMM into a bf16 scratch followed by one
+                // pass  x <- x + mask * branch  (what autocast + nn.Dropout do in the reference); LayerNorms as their own passes.
+                TA* br = TP<TA>(h->hid);
+                const long long n4 = (long long)tokens * C / 4;
+                EpiParams eb; eb.bias = AF(h, lp.outb);
+                gemm<TA>(h, EPI_BIAS, TP<TA>(ot.att[li]), C, lp.outw, br, C, false, tokens, C, C, eb, st);
+                resid_drop_kernel<TA><<<blocks_for(n4, 256), 256, 0, st>>>(br, x_in, x_mid, n4, drop, drop_site(o, (int)li, 1));
+                CK(cudaGetLastError());
+                h->launches++;
+                launch_layernorm<TA>(h, x_mid, lp.ln2w, lp.ln2b, TP<TA>(ot.ln2[li]), tokens, st);
+                EpiParams eh; eh.bias = AF(h, lp.m0b);
+                gemm<TA>(h, EPI_BIAS, TP<TA>(ot.ln2[li]), C, lp.m0w, ot.hpre[li].p, Hm, false, tokens, Hm, C, eh, st);
+                launch_act_fwd<TA, ACT_GELU_TANH>(h, TP<TA>(ot.hpre[li]), TP<TA>(ot.hact[li]), (long long)tokens * Hm, st);
+                eb.bias = AF(h, lp.m2b);
+                gemm<TA>(h, EPI_BIAS, TP<TA>(ot.hact[li]), Hm, lp.m2w, br, C, false, tokens, C, Hm, eb, st);
+                resid_drop_kernel<TA><<<blocks_for(n4, 256), 256, 0, st>>>(br, x_mid, x_out, n4, drop, drop_site(o, (int)li, 2));
+                CK(cudaGetLastError());
+                h->launches++;
+                ln_ready = false;
+                continue;
             }
             EpiParams eo; eo.bias = AF(h, lp.outb); eo.resid = x_in; eo.ldr = C;
             eo.drop = drop; eo.drop_site = drop_site(o, (int)li, 1);

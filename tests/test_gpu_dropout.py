@@ -16,17 +16,24 @@ pytestmark = pytest.mark.gpu
 def _model(cfg, sd, prec, p):
     from tante_b200 import TANTE, TanteMetadata
     m = TANTE(cfg.in_T, TanteMetadata(spatial_resolution=(cfg.H, cfg.W), n_fields=cfg.n_fields), taylor_order=cfg.taylor_order,
-              attn_axes=cfg.attn_axes, patch_scale=cfg.patch_scale, deg=cfg.deg, dropout=p, precision=prec)
+              attn_axes=cfg.attn_axes, patch_scale=cfg.patch_scale, deg=cfg.deg, dropout=p, precision=prec,
+              mlp_ratio=cfg.mlp_ratio, embed_dim=cfg.embed_dim, n_head=cfg.n_head)
     m.load_state_dict(sd)
     return m.cuda().train()
 
 
 @pytest.mark.parametrize("prec,tol_y,tol_g", [("fp32", 1e-5, 3e-4), ("bf16", 2e-2, 8e-2)])
-@pytest.mark.parametrize("case", ["deg_thw", "adp_k2", "adp_lya"])
+@pytest.mark.parametrize("case", ["deg_thw", "adp_k2", "adp_lya", "deg_mlp2", "deg_c512"])
 def test_dropout_training_matches_oracle_with_same_masks(case, prec, tol_y, tol_g):
     p = 0.25
     if case == "deg_thw":
         cfg = O.OracleConfig(n_fields=3, H=32, W=48, taylor_order=1, attn_axes="THW", deg=True)
+        rt_bias, out_T = 0.0, 1
+    elif case == "deg_mlp2":      # mlp_ratio 2: the block outside the fused tail (tensor mode: GEMM + masked residual pass)
+        cfg = O.OracleConfig(n_fields=2, H=32, W=32, taylor_order=1, attn_axes="HWT", deg=True, mlp_ratio=2.0)
+        rt_bias, out_T = 0.0, 1
+    elif case == "deg_c512":      # embed_dim 512, head_dim 32
+        cfg = O.OracleConfig(n_fields=2, H=32, W=32, taylor_order=1, attn_axes="TH", deg=True, embed_dim=512, n_head=16)
         rt_bias, out_T = 0.0, 1
     elif case == "adp_lya":      # composite axes: L = 96 and A = 384 tokens (general forward kernel + tiled recompute backward)
         cfg = O.OracleConfig(n_fields=2, H=64, W=96, taylor_order=2, attn_axes="LT-AY", deg=False)

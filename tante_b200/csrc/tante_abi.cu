@@ -1924,8 +1924,16 @@ void run_step_train(tante_handle_s* h, Tape& tp, const float* input, int B, floa
         h->launches++;
         EpiParams e3; e3.bias = AF(h, h->enc_b[2]);
         if (wd.pool3) {
-            REQUIRE(!(kTensor && K3 > 1024), "overlap_ratio != 0 at patch_scale 64 in the tensor mode: training not implemented");
-            gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], cg, C, false, (int)wd.rows3, C, K3, e3, st);
+            if (kTensor && K3 > 1024) {      // (patch_scale 64: K blocks through the fp32 scratch of tante_reserve, as in run_encoder_wide)
+                REQUIRE((size_t)wd.rows3 * C * 4 <= h->kscratch.bytes, "split-K conv: scratch not reserved");
+                float* acc = FP(h->kscratch);
+                gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(wb), K3, h->enc_w[2], acc, (int)wd.rows3, C, K3, e3.bias, st);
+                f32_to_ta_kernel<TA, false><<<blocks_for(wd.rows3 * C / 4, 256), 256, 0, st>>>(acc, cg, wd.rows3 * C / 4);
+                CK(cudaGetLastError());
+                h->launches++;
+            } else {
+                gemm<TA>(h, EPI_BIAS, wb, K3, h->enc_w[2], cg, C, false, (int)wd.rows3, C, K3, e3, st);
+            }
             pool(cg, wd.Hc3, wd.Wc3, C, h->Hp, h->Wp, nullptr, FP(tp.v));
         } else if (kTensor && K3 > 1024) {      // (K = 2048 at patch_scale 64: K blocks, as in run_encoder_wide)
             gemm_bigk_f32(h, reinterpret_cast<const __nv_bfloat16*>(wb), K3, h->enc_w[2], FP(tp.v), tokens, C, K3, e3.bias, st);

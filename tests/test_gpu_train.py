@@ -181,7 +181,7 @@ def _oracle_grads(cfg, sd, x, gy, grt, out_T, autocast=False):
 
 
 @pytest.mark.parametrize("prec,tol", [("fp32", FP32_GRAD_TOL), ("bf16", BF16_GRAD_TOL)])
-@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48", "adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c", "deg_k1_axes_c256", "adp_k1_ov70_p32", "deg_k2_ov30_p4"])
+@pytest.mark.parametrize("case", ["adp_k2_n3", "deg_k1_p4", "adp_k3_p2", "deg_k1_axes32", "adp_k1_axes48", "adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c", "deg_k1_axes_c256", "adp_k1_ov70_p32", "deg_k2_ov30_p4", "deg_k1_ov50_p64"])
 def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
     """One model call with a random cotangent on the frames AND on R_t, multi-frame emit (n = 3) included:
     every parameter gradient and the input gradient against torch autograd over the CPU oracle."""
@@ -231,6 +231,11 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         # overlap_ratio 0.7 at patch_scale 32: strides (1, 1, 1) under kernels (4, 4, 2) -- every stage pools / overlap-adds
         cfg = O.OracleConfig(n_fields=4, H=64, W=96, taylor_order=1, attn_axes="WT", deg=False, patch_scale=32, overlap_ratio=0.7)
         rt_bias, out_T = 2.7, 8
+    elif case == "deg_k1_ov50_p64":
+        # overlap 0.5 at patch_scale 64: strides (2, 2, 2) under kernels (4, 4, 4); the last encoder conv has K = 2048 (split-K in the
+        # tensor mode) in front of its pooling
+        cfg = O.OracleConfig(n_fields=2, H=256, W=128, taylor_order=1, attn_axes="HW", deg=True, patch_scale=64, overlap_ratio=0.5)
+        rt_bias, out_T = 0.0, 1
     elif case == "deg_k2_ov30_p4":
         # overlap_ratio 0.3 at patch_scale 4: kernels (2, 2, 1), strides (1, 1, 1): non-divisible pooling windows (H - 1 -> H / 2)
         cfg = O.OracleConfig(n_fields=3, H=32, W=48, taylor_order=2, attn_axes="TH-W", deg=True, patch_scale=4, overlap_ratio=0.3,
@@ -244,7 +249,7 @@ def test_single_step_backward_vs_oracle_autograd(case, prec, tol):
         cfg = O.OracleConfig(n_fields=2, H=16, W=24, taylor_order=3, attn_axes="T-H-W", deg=False, patch_scale=2)
         rt_bias, out_T = 1.3, 4
     sd = O.make_state_dict(cfg, 311, rt_bias)
-    B = 2 if ("axes" in case or case in ("adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c", "deg_k1_axes_c256", "adp_k1_ov70_p32", "deg_k2_ov30_p4")) else 3
+    B = 2 if ("axes" in case or case in ("adp_k2_lya", "deg_k1_w96", "adp_k1_p64", "deg_k2_p16", "adp_k1_fno_p16", "adp_k2_axes_c", "deg_k1_axes_c256", "adp_k1_ov70_p32", "deg_k2_ov30_p4", "deg_k1_ov50_p64")) else 3
     x = O.make_input(cfg, B, 312)
     with torch.no_grad():
         y0 = O.forward(sd, cfg, x, out_T)
